@@ -1,0 +1,56 @@
+"""Synthetic designs shaped like the reference's ``gen.data`` (R/R/gen.data.R:93-166, cortype 1, rho = 0;
+python twin python/bess/gen_data.py:22-102).  R's RNG streams cannot be reproduced without R, so draws come
+from ``numpy.random.Generator(PCG64(seed))``; the *recipe* (effect sizes, noise level, link, censoring) is
+the reference's.  For cox the rows are returned already time-sorted with ``y = status`` -- what the
+front-ends hand to ``bessCpp`` (R/R/bess.R:527-534, python/bess/linear.py:257-263)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class SynthData:
+    x: np.ndarray        # n x p, C-contiguous float64
+    y: np.ndarray        # n (cox: status after time-sorting)
+    beta: np.ndarray     # true coefficients
+    time: np.ndarray | None = None
+
+
+def gen_data(n, p, family="gaussian", k=10, seed=1, snr=10.0, scal=10.0, c=10.0, x=None) -> SynthData:
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if x is None:
+        x = rng.standard_normal((n, p))
+    nonzero = rng.choice(p, size=k, replace=False)
+    tbeta = np.zeros(p)
+    m = 5.0 * np.sqrt(2.0 * np.log(p) / n)
+    if family == "gaussian":
+        tbeta[nonzero] = rng.uniform(m, 100.0 * m, k)
+        sigma = np.sqrt((tbeta @ tbeta) / snr)
+        y = x[:, nonzero] @ tbeta[nonzero] + rng.normal(0.0, sigma, n)
+        return SynthData(x, y, tbeta)
+    if family == "binomial":
+        tbeta[nonzero] = rng.uniform(2 * m, 10 * m, k)
+        sigma = np.sqrt((tbeta @ tbeta) / snr)
+        eta = x[:, nonzero] @ tbeta[nonzero] + rng.normal(0.0, sigma, n)
+        eta = np.clip(eta, -30, 30)
+        pr = np.exp(eta) / (1 + np.exp(eta))
+        y = rng.binomial(1, pr).astype(np.float64)
+        return SynthData(x, y, tbeta)
+    if family == "poisson":
+        x /= 16.0
+        tbeta[nonzero] = rng.uniform(2 * m, 10 * m, k)
+        sigma = np.sqrt((tbeta @ tbeta) / snr)
+        eta = np.clip(x[:, nonzero] @ tbeta[nonzero] + rng.normal(0.0, sigma, n), -30, 30)
+        y = rng.poisson(np.exp(eta)).astype(np.float64)
+        return SynthData(x, y, tbeta)
+    if family == "cox":
+        tbeta[nonzero] = rng.uniform(2 * m, 10 * m, k)
+        time = (-np.log(rng.uniform(size=n)) / np.exp(x[:, nonzero] @ tbeta[nonzero])) ** (1.0 / scal)
+        ctime = c * rng.uniform(size=n)
+        status = (time < ctime).astype(np.float64)
+        time = np.minimum(time, ctime)
+        order = np.argsort(time, kind="stable")
+        return SynthData(np.ascontiguousarray(x[order]), status[order], tbeta, time[order])
+    raise ValueError("family should be 'gaussian', 'binomial', 'poisson' or 'cox'")

@@ -1,0 +1,600 @@
+"""CPU restatement (numpy, fp64) of the BeSS primal-dual active-set hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``bess_b200/`` may import this module;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline leg do,
+and only as the *checker*.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function here
+against outputs of the real reference (Mamba413/bess ``src/*.cpp`` compiled unmodified
+into ``oracle/_ref/libbess_ref.so`` by ``oracle/Makefile``; fixtures committed under
+``tests/golden/`` by ``tests/golden/make_golden.py``).  The reference itself ships no
+golden vectors or tests.
+
+All ``file:line`` citations are into ``/root/reference/src``.  Everything is the
+gsize==1, lambda==0 specialisation that ``bessCpp`` reaches for ``type="bss"``.
+
+Known, deliberate deviations from the reference (none changes a result on
+continuous data):
+  * ``max_k`` boundary ties: the reference's order among *exactly equal* keys that
+    straddle the k-th position is whatever libstdc++'s introselect leaves
+    (utilities.cpp:179-188).  Here: larger value first, lower index first.
+  * CV fold assignment is an *input* (``fold_of_row``) because it comes from
+    ``std::shuffle(mt19937)`` (Metric.h:49-106); the golden fixtures store it.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+DBL_MAX = np.finfo(np.float64).max
+
+
+# --------------------------------------------------------------------------------------
+# Data + normalisation: Data.h:41-77, normalize.cpp:20-86
+# --------------------------------------------------------------------------------------
+@dataclass
+class Data:
+    x: np.ndarray  # n x p, normalised (and sqrt(w)-row-scaled for gaussian)
+    y: np.ndarray
+    weight: np.ndarray
+    x_mean: np.ndarray
+    x_norm: np.ndarray
+    y_mean: float
+    data_type: int
+    is_normal: bool
+    n: int = 0
+    p: int = 0
+
+
+def make_data(x, y, weight, data_type, is_normal, model_type):
+    """Data ctor (Data.h:41-68) + Normalize/Normalize3/Normalize4 (normalize.cpp:20-86)
+    + add_weight for gaussian (Data.h:70-77, called from bess.cpp:97)."""
+    x = np.array(x, dtype=np.float64, order="F", copy=True)
+    y = np.array(y, dtype=np.float64, copy=True)
+    w = np.array(weight, dtype=np.float64, copy=True)
+    n, p = x.shape
+    x_mean = np.zeros(p)
+    x_norm = np.zeros(p)
+    y_mean = 0.0
+    if is_normal:
+        if data_type in (1, 2):
+            x_mean = (w @ x) / float(n)  # normalize.cpp:25-28 / 52-55
+            x = x - x_mean
+        if data_type == 1:
+            y_mean = float(y @ w) / float(n)  # normalize.cpp:29
+            y = y - y_mean
+        x_norm = np.sqrt(w @ (x * x))  # normalize.cpp:36-41
+        x = math.sqrt(float(n)) * x / x_norm  # normalize.cpp:42-45
+    if model_type == 1:
+        sw = np.sqrt(w)  # Data.h:70-77
+        x = x * sw[:, None]
+        y = y * sw
+    return Data(np.asfortranarray(x), y, w, x_mean, x_norm, y_mean, data_type, is_normal, n, p)
+
+
+# --------------------------------------------------------------------------------------
+# Selection: utilities.cpp:179-199
+# --------------------------------------------------------------------------------------
+def max_k(vec, k):
+    """Indices of the k largest entries, returned ascending (utilities.cpp:179-188).
+    Tie rule at the boundary: see module docstring."""
+    p = vec.shape[0]
+    order = np.lexsort((np.arange(p), -vec))  # primary: value desc; secondary: index asc
+    return np.sort(order[:k]).astype(np.int32)
+
+
+def boundary_gap(vec, k):
+    """Relative gap between the k-th and (k+1)-th largest sacrifice (margin logging)."""
+    if k >= vec.shape[0]:
+        return np.inf
+    s = np.sort(vec)[::-1]
+    return float((s[k - 1] - s[k]) / max(abs(s[k - 1]), 1e-300))
+
+
+# --------------------------------------------------------------------------------------
+# log-likelihoods: logistic.cpp:15-59, poisson.cpp:15-82, coxph.cpp:16-40
+# --------------------------------------------------------------------------------------
+def _clip(v, c):
+    return np.minimum(np.maximum(v, -c), c)
+
+
+def loglik_cox(X, status, beta, weights):
+    """coxph.cpp:16-40 (rows time-sorted; suffix sums are the risk sets)."""
+    eta = _clip(X @ beta, 30.0)
+    e = np.exp(eta)
+    cum = np.cumsum(e[::-1])[::-1]
+    return float((np.log(e / cum) * status) @ weights)
+
+
+def _log_factorial_term(y):
+    """poisson.cpp:29-44: sum_{j=1..y} log(j), with y==1 short-circuited to 0."""
+    out = np.zeros_like(y)
+    for i, yi in enumerate(y):
+        if yi == 1:
+            out[i] = 0.0
+        else:
+            t = 0.0
+            j = 1.0
+            while j <= yi:
+                t += math.log(j)
+                j += 1.0
+            out[i] = t
+    return out
+
+
+def loglik_poisson(x, y, coef, weights):
+    """poisson.cpp:15-47 (coef[0] is the intercept; includes the -log y! term)."""
+    eta = _clip(x @ coef[1:] + coef[0], 30.0)
+    return float((y * eta - np.exp(eta) - _log_factorial_term(y)) @ weights)
+
+
+def loglik_poiss(x, y, coef, weights):
+    """poisson.cpp:67-82 (no factorial term)."""
+    eta = _clip(x @ coef[1:] + coef[0], 30.0)
+    return float((y * eta - np.exp(eta)) @ weights)
+
+
+# --------------------------------------------------------------------------------------
+# primary_model_fit x4: Algorithm.h:1131-1135, 1148-1204, 1273-1322, 1377-1490
+# --------------------------------------------------------------------------------------
+def fit_lm(XA, y, w, coef0):
+    """Algorithm.h:1131-1135.  coef0 untouched."""
+    G = XA.T @ XA
+    beta = np.linalg.solve(G, XA.T @ y)
+    return beta, coef0
+
+
+def _pi(X1, coef):
+    """logistic.cpp:15-59 with the intercept column already in X1."""
+    eta = _clip(X1 @ coef, 30.0)
+    e = np.exp(eta)
+    return e / (1.0 + e)
+
+
+def fit_logistic(XA, y, w, coef0, floor_w=True):
+    """Algorithm.h:1148-1204 (floor_w=True) and logistic.cpp:61-157 ``logit_fit`` (floor_w=False).
+    Starts from 0, returns the iterate *before* the last solve."""
+    n, k = XA.shape
+    X = np.hstack([np.ones((n, 1)), XA])
+    beta0 = np.zeros(k + 1)
+    Pi = _pi(X, beta0)
+    ll0 = float((y * np.log(Pi) + (1 - y) * np.log(1 - Pi)) @ w)
+    W = Pi * (1 - Pi)
+    Z = X @ beta0 + (y - Pi) / W
+    W = W * w
+    beta1 = np.linalg.solve((X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
+    for _ in range(30):
+        Pi = _pi(X, beta1)
+        ll1 = float((y * np.log(Pi) + (1 - y) * np.log(1 - Pi)) @ w)
+        if abs(ll0 - ll1) / (0.1 + abs(ll1)) < 1e-6:
+            break
+        beta0 = beta1
+        ll0 = ll1
+        W = Pi * (1 - Pi)
+        if floor_w:
+            W = np.maximum(W, 0.001)
+        Z = X @ beta0 + (y - Pi) / W
+        W = W * w
+        beta1 = np.linalg.solve((X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
+    return beta0[1:].copy(), float(beta0[0])
+
+
+def fit_poisson(XA, y, w, coef0):
+    """Algorithm.h:1273-1322.  Intercept warm-started from coef0, slopes from 0."""
+    n, k = XA.shape
+    X = np.hstack([np.ones((n, 1)), XA])
+    beta0 = np.zeros(k + 1)
+    beta0[0] = coef0
+    eta = X @ beta0
+    expeta = np.exp(eta)
+    ll0 = 1e5
+    for _ in range(50):
+        ww = expeta * w
+        z = eta + (y - expeta) / expeta
+        XtW = (X * ww[:, None]).T
+        beta0 = np.linalg.solve(XtW @ X, XtW @ z)
+        eta = _clip(X @ beta0, 30.0)
+        expeta = np.maximum(np.exp(eta), 0.001)
+        ll1 = float((y * eta - expeta) @ w)
+        if abs(ll0 - ll1) / abs(0.1 + ll0) < 1e-6:
+            break
+        ll0 = ll1
+    return beta0[1:].copy(), float(beta0[0])
+
+
+def fit_cox(XA, status, w, coef0, clamp=30.0):
+    """Algorithm.h:1377-1490 (clamp 30) and coxph.cpp:42-109 ``cox_fit`` (clamp 50).
+    theta has NO weights here; first Newton step is always d/32 (ll0 starts at 1e5)."""
+    n, k = XA.shape
+    beta0 = np.zeros(k)
+    ll0 = 1e5
+    ws = w * status
+    for _ in range(30):
+        theta = np.exp(_clip(XA @ beta0, clamp))
+        cum = np.cumsum(theta[::-1])[::-1]
+        xt = np.cumsum((XA * theta[:, None])[::-1], axis=0)[::-1] / cum[:, None]
+        g = (XA - xt).T @ ws
+        h = np.empty((k, k))
+        for a in range(k):
+            for b in range(a, k):
+                s = np.cumsum((theta * XA[:, a] * XA[:, b])[::-1])[::-1]
+                h[a, b] = h[b, a] = -float((s / cum - xt[:, a] * xt[:, b]) @ ws)
+        d = np.linalg.solve(h, g)
+        m = 1
+        beta1 = beta0 - 0.5 ** m * d
+        ll1 = loglik_cox(XA, status, beta1, w)
+        while ll0 > ll1 and m < 5:
+            m += 1
+            beta1 = beta0 - 0.5 ** m * d
+            ll1 = loglik_cox(XA, status, beta1, w)
+        if abs(ll0 - ll1) / abs(0.1 + ll0) < 1e-5:
+            break
+        beta0 = beta1
+        ll0 = ll1
+    return beta0, coef0
+
+
+# --------------------------------------------------------------------------------------
+# get_A x4 (sacrifices): Algorithm.h:1097-1129, 1206-1263, 1324-1367, 1569-1640
+# --------------------------------------------------------------------------------------
+def sacrifice_lm(X, y, w, beta, coef0, xtx):
+    n = X.shape[0]
+    d = X.T @ (y - X @ beta - coef0) / float(n)  # :1109
+    phi = np.sqrt(xtx / float(n))  # utilities.cpp:142-151 (1x1 sqrt)
+    inv = 1.0 / phi  # utilities.cpp:167-177 (1x1 ldlt inverse)
+    return (phi * beta + inv * d) ** 2  # :1116-1122
+
+
+def sacrifice_logistic(X, y, w, beta, coef0, xtx=None):
+    eta = _clip(X @ beta + coef0, 30.0)  # :1223-1231
+    e = np.exp(eta)
+    pr = e / (e + 1.0)
+    g = w * (y - pr)
+    h = w * pr * (1 - pr)
+    d = X.T @ g  # :1236
+    phi = np.sqrt((X * X).T @ h)  # :1238-1250
+    return (phi * beta + d / phi) ** 2
+
+
+def sacrifice_poisson(X, y, w, beta, coef0, xtx=None):
+    eta = X @ beta + coef0  # :1338 (NOT clamped)
+    e = np.exp(eta)
+    g = (y - e) * w
+    d = X.T @ g
+    phi = np.sqrt((X * X).T @ (e * w))  # :1342-1350
+    return (phi * beta + d / phi) ** 2
+
+
+def sacrifice_cox(X, y, w, beta, coef0=0.0, xtx=None):
+    """Algorithm.h:1569-1640 (algorithm_type 1 branch).  y is the 0/1 status, rows time-sorted."""
+    theta = w * np.exp(_clip(X @ beta, 30.0))  # :1579-1587
+    cum = np.cumsum(theta[::-1])[::-1]
+    xth = np.cumsum((X * theta[:, None])[::-1], axis=0)[::-1] / cum[:, None]
+    x2th = np.cumsum((X * X * theta[:, None])[::-1], axis=0)[::-1] / cum[:, None]
+    x2th = x2th - xth ** 2
+    xth = X - xth
+    ev = (y != 0.0)  # :1618-1625 rows with status 0 are zeroed
+    l1 = -(xth[ev].T @ w[ev])
+    l2 = x2th[ev].T @ w[ev]
+    d = -l1 / l2
+    return np.abs(beta + d) * np.sqrt(l2)  # :1631-1634 (not squared)
+
+
+_SACRIFICE = {1: sacrifice_lm, 2: sacrifice_logistic, 3: sacrifice_poisson, 4: sacrifice_cox}
+_FIT = {1: fit_lm, 2: fit_logistic, 3: fit_poisson, 4: fit_cox}
+
+
+# --------------------------------------------------------------------------------------
+# Algorithm::fit  (Algorithm.h:113-171)
+# --------------------------------------------------------------------------------------
+@dataclass
+class FitResult:
+    beta: np.ndarray
+    coef0: float
+    l: int
+    A: np.ndarray
+    A_hist: list = field(default_factory=list)
+    min_gap: float = np.inf
+
+
+def pdas_fit(data: Data, model_type, T0, beta_init, coef0_init, train_mask, xtx, max_iter=20, always_select=()):
+    X = data.x[train_mask] if len(train_mask) != data.n else data.x
+    y = data.y[train_mask] if len(train_mask) != data.n else data.y
+    w = data.weight[train_mask] if len(train_mask) != data.n else data.weight
+    p = data.p
+    beta = beta_init.copy()
+    coef0 = float(coef0_init)
+    seen = [np.zeros(T0, dtype=np.int32)]  # A_list.col(0) = 0  (:142-143)
+    res = FitResult(beta, coef0, 0, seen[0])
+    for l in range(1, max_iter + 1):
+        bd = _SACRIFICE[model_type](X, y, w, beta, coef0, xtx)
+        if len(always_select):
+            bd[np.asarray(always_select)] = DBL_MAX  # slice_assignment, utilities.cpp:190-199
+        res.min_gap = min(res.min_gap, boundary_gap(bd, T0))
+        A = max_k(bd, T0)
+        beta_A, coef0 = _FIT[model_type](X[:, A], y, w, coef0)  # beta_A reset to 0 before the fit (:157)
+        beta = np.zeros(p)
+        beta[A] = beta_A
+        res.A_hist.append(A)
+        res.l = l
+        if any(np.array_equal(A, s) for s in seen):  # :164-170
+            break
+        seen.append(A)
+    else:
+        res.l = max_iter + 1  # loop variable after a non-returning for (:151)
+    res.beta, res.coef0, res.A = beta, coef0, A
+    return res
+
+
+# --------------------------------------------------------------------------------------
+# Metric: Metric.h:138-676
+# --------------------------------------------------------------------------------------
+def train_loss(data: Data, model_type, beta, coef0):
+    if model_type == 1:
+        return float(((data.y - data.x @ beta) ** 2).sum() / data.n)  # :145-148
+    if model_type == 2:  # :266-290
+        e = np.exp(_clip(data.x @ beta + coef0, 30.0))
+        pr = e / (e + 1.0)
+        return float(-2 * (data.weight * (data.y * np.log(pr) + (1 - data.y) * np.log(1 - pr))).sum())
+    if model_type == 3:  # :426-440
+        return -2 * loglik_poisson(data.x, data.y, np.concatenate([[coef0], beta]), data.weight)
+    return -2 * loglik_cox(data.x, data.y, beta, data.weight)  # :565-568
+
+
+def fold_loss(data: Data, model_type, beta, coef0, test_mask):
+    X, y, w = data.x[test_mask], data.y[test_mask], data.weight[test_mask]
+    if model_type == 1:
+        return float(((y - X @ beta) ** 2).sum() / float(2 * len(test_mask)))  # :190
+    if model_type == 2:  # :336-351 (clamp 25!)
+        e = np.exp(_clip(X @ beta + coef0, 25.0))
+        pr = e / (e + 1.0)
+        return float(-2 * (w * (y * np.log(pr) + (1 - y) * np.log(1 - pr))).sum())
+    if model_type == 3:  # :489 (factor 1, not 2)
+        return -loglik_poisson(X, y, np.concatenate([[coef0], beta]), w)
+    return -2 * loglik_cox(X, y, beta, w)  # :609
+
+
+def ic_penalty(ic_type, n, p, s):
+    if ic_type == 1:
+        return 2.0 * s
+    if ic_type == 2:
+        return math.log(float(n)) * s
+    if ic_type == 3:
+        return math.log(float(p)) * math.log(math.log(float(n))) * s
+    if ic_type == 4:
+        return (math.log(float(n)) + 2 * math.log(float(p))) * s
+    return None
+
+
+class PathState:
+    """The mutable state the reference keeps in Algorithm + Metric between calls."""
+
+    def __init__(self, data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, warm_start, always_select=()):
+        self.data, self.model_type, self.ic_type, self.is_cv, self.K = data, model_type, ic_type, is_cv, K
+        self.max_iter, self.warm, self.always = max_iter, warm_start, tuple(always_select)
+        n, p = data.n, data.p
+        self.full_mask = np.arange(n)
+        self.xtx_full = (data.x * data.x).sum(axis=0) if model_type == 1 else None  # utilities.cpp:153-165
+        self.alg_coef0_init = 0.0
+        self.alg_beta = np.zeros(p)
+        self.alg_coef0 = 0.0
+        self.T = 0
+        self.n_fits = 0
+        self.n_iters = 0
+        self.min_gap = np.inf
+        if is_cv:
+            fold_of_row = np.asarray(fold_of_row)
+            self.test_masks = [np.nonzero(fold_of_row == k)[0] for k in range(K)]
+            self.train_masks = [np.nonzero(fold_of_row != k)[0] for k in range(K)]
+            self.cv_param = np.zeros((K, p))  # Metric.h:39-42
+            self.xtx_folds = ([(data.x[m] ** 2).sum(axis=0) for m in self.train_masks]
+                              if model_type == 1 else [None] * K)  # Metric.h:108-129
+
+    def _fit(self, T, beta_init, coef0_init, mask, xtx):
+        r = pdas_fit(self.data, self.model_type, T, beta_init, coef0_init, mask, xtx, self.max_iter, self.always)
+        self.n_fits += 1
+        self.n_iters += min(r.l, self.max_iter)
+        self.min_gap = min(self.min_gap, r.min_gap)
+        self.alg_beta, self.alg_coef0, self.last = r.beta, r.coef0, r
+        return r
+
+    def full_fit(self, T, beta_init, coef0_init):
+        self.T = T
+        self.alg_coef0_init = coef0_init  # update_coef0_init, path.cpp:57
+        return self._fit(T, beta_init, coef0_init, self.full_mask, self.xtx_full)
+
+    def train_loss(self):
+        return train_loss(self.data, self.model_type, self.alg_beta, self.alg_coef0)
+
+    def ic(self):
+        if self.is_cv:  # Metric::test_loss
+            losses = []
+            for k in range(self.K):
+                binit = self.cv_param[k].copy() if self.warm else np.zeros(self.data.p)
+                # NB: the reference never resets beta_init when warm_start is false either: it keeps
+                # whatever update_beta_init last set (the path's beta_init).  With warm_start=false the
+                # path's beta_init stays zero, so zeros is the same thing.
+                r = self._fit(self.T, binit, self.alg_coef0_init, self.train_masks[k], self.xtx_folds[k])
+                if self.warm:
+                    self.cv_param[k] = r.beta
+                losses.append(fold_loss(self.data, self.model_type, r.beta, r.coef0, self.test_masks[k]))
+            return float(np.mean(losses))
+        tl = self.train_loss()
+        pen = ic_penalty(self.ic_type, self.data.n, self.data.p, self.T)
+        if pen is None:
+            return 0.0
+        if self.model_type == 1:
+            return float(self.data.n) * math.log(tl) + pen  # Metric.h:205-229
+        return tl + pen  # Metric.h:365-388 etc.
+
+
+def _denormalise(data: Data, beta, coef0, gs):
+    """path.cpp:76-110 (sequential) / :330-343 (gs: the non-gaussian branch also subtracts beta.x_mean
+    for data_type 3, where x_mean is all zero)."""
+    n = data.n
+    if not data.is_normal:
+        return beta, coef0
+    beta = math.sqrt(float(n)) * beta / data.x_norm
+    if data.data_type == 1:
+        coef0 = data.y_mean - float(beta @ data.x_mean)
+    elif data.data_type == 2 or gs:
+        coef0 = coef0 - float(beta @ data.x_mean)
+    return beta, coef0
+
+
+def sequential_path(st: PathState, sequence):
+    """path.cpp:25-132 (lambda_seq = [0])."""
+    p = st.data.p
+    beta_init, coef0_init = np.zeros(p), 0.0
+    betas, coef0s, losses, ics, ls = [], [], [], [], []
+    for s in sequence:
+        r = st.full_fit(int(s), beta_init, coef0_init)
+        if st.warm:
+            beta_init, coef0_init = r.beta.copy(), r.coef0
+        betas.append(r.beta.copy())
+        coef0s.append(r.coef0)
+        ls.append(r.l)
+        losses.append(st.train_loss())
+        ics.append(st.ic())
+    best = int(np.argmin(np.array(ics)))  # first minimum, path.cpp:113
+    beta, coef0 = _denormalise(st.data, betas[best], coef0s[best], gs=False)
+    return dict(beta=beta, coef0=coef0, train_loss=losses[best], ic=ics[best], best=best, s=int(sequence[best]),
+                beta_all=np.array(betas), coef0_all=np.array(coef0s), loss_all=np.array(losses),
+                ic_all=np.array(ics), l_all=np.array(ls))
+
+
+def gs_path(st: PathState, s_min, s_max):
+    """path.cpp:134-389, including the double ic() evaluation and the read-after-ic() of beta."""
+    p = st.data.p
+    beta_init, coef0_init = np.zeros(p), 0.0
+
+    def rnd(v):  # C round(): half away from zero
+        return int(math.floor(v + 0.5)) if v >= 0 else -int(math.floor(-v + 0.5))
+
+    def ev(T):
+        nonlocal beta_init, coef0_init
+        r = st.full_fit(T, beta_init, coef0_init)
+        if st.warm:
+            beta_init, coef0_init = r.beta.copy(), r.coef0
+        return r
+
+    Tmin, Tmax = s_min, s_max
+    T1 = rnd(0.618 * Tmin + 0.382 * Tmax)
+    T2 = rnd(0.382 * Tmin + 0.618 * Tmax)
+    ic_seq = [0.0] * 4
+    trace = []
+    ev(T1); st.train_loss(); ic_seq[1] = st.ic(); icT1 = ic_seq[1]; trace.append(T1)
+    ev(T2); st.train_loss(); ic_seq[2] = st.ic(); icT2 = st.ic(); trace.append(T2)
+    while T1 != T2:
+        if icT1 < icT2:
+            Tmax = T2
+            ic_seq[3] = ic_seq[2]
+            T2 = T1
+            ic_seq[2] = ic_seq[1]
+            icT2 = ic_seq[1]
+            T1 = rnd(0.618 * Tmin + 0.382 * Tmax)
+            ev(T1); ic_seq[1] = st.ic(); icT1 = st.ic(); trace.append(T1)
+        else:
+            Tmin = T1
+            ic_seq[0] = ic_seq[1]
+            T1 = T2
+            ic_seq[1] = ic_seq[2]
+            icT1 = ic_seq[2]
+            T2 = rnd(0.382 * Tmin + 0.618 * Tmax)
+            ev(T2); ic_seq[2] = st.ic(); icT2 = st.ic(); trace.append(T2)
+    best_ic, best = DBL_MAX, None
+    for T in range(Tmin, Tmax + 1):
+        ev(T)
+        v = st.ic()
+        if v < best_ic:
+            # algorithm->get_beta() AFTER ic(): under CV this is the last fold's fit (path.cpp:314-319)
+            best = (st.alg_beta.copy(), st.alg_coef0, st.train_loss(), T)
+            best_ic = v
+    beta, coef0 = _denormalise(st.data, best[0], best[1], gs=True)
+    return dict(beta=beta, coef0=coef0, train_loss=best[2], ic=best_ic, s=best[3], trace=trace,
+                Tmin=Tmin, Tmax=Tmax)
+
+
+# --------------------------------------------------------------------------------------
+# Screening: screening.cpp:26-105 + marginal fits
+# --------------------------------------------------------------------------------------
+def poisson_fit_marginal(xj, y, w):
+    """poisson.cpp:84-137, *literally*, including the vector*vector product that (asserts off)
+    evaluates to X.col(i)*expeta_w(0) (:117) and the wrong-sign step (:122,:128)."""
+    n = xj.shape[0]
+    X = np.column_stack([np.ones(n), xj])
+    beta0 = np.zeros(2)
+    for _ in range(100):
+        eta = _clip(X @ beta0, 30.0)
+        expeta = np.exp(eta)
+        ew0 = expeta[0] * w[0]
+        temp = X * ew0
+        g = X.T @ ((y - expeta) * w)
+        h = X.T @ temp
+        d = np.linalg.solve(h, g)
+        m = 0
+        beta1 = beta0 - 0.2 ** m * d
+        ll0 = loglik_poiss(xj[:, None], y, beta0, w)
+        ll1 = loglik_poiss(xj[:, None], y, beta1, w)
+        while ll0 >= ll1 and m < 10:
+            m += 1
+            beta1 = beta0 - 0.2 ** m * d
+            ll1 = loglik_poiss(xj[:, None], y, beta1, w)
+        beta0 = beta1
+        if abs(ll0 - ll1) / abs(ll0) < 1e-8:
+            break
+    return beta0
+
+
+def screening_utility(x, y, w, model_type):
+    """coef_norm of screening.cpp:40-61 on RAW x (gsize 1): squared marginal slope."""
+    n, p = x.shape
+    u = np.empty(p)
+    if model_type == 1:
+        u[:] = ((x.T @ y) / (x * x).sum(axis=0)) ** 2  # 1-column colPivHouseholderQr().solve(y)
+        return u
+    for j in range(p):
+        xj = x[:, j]
+        if model_type == 2:
+            b, _ = fit_logistic(xj[:, None], y, w, 0.0, floor_w=False)
+            u[j] = b[0] ** 2
+        elif model_type == 3:
+            u[j] = poisson_fit_marginal(xj, y, w)[1] ** 2
+        else:
+            b, _ = fit_cox(xj[:, None], y, w, 0.0, clamp=50.0)
+            u[j] = b[0] ** 2
+    return u
+
+
+def screening(x, y, w, model_type, screening_size, always_select=()):
+    u = screening_utility(np.asarray(x, dtype=np.float64), y, w, model_type)
+    if len(always_select):
+        u[np.asarray(always_select)] = DBL_MAX
+    return max_k(u, screening_size)
+
+
+# --------------------------------------------------------------------------------------
+# bessCpp: bess.cpp:37-214
+# --------------------------------------------------------------------------------------
+def bess_cpp(x, y, data_type, weight, is_normal, model_type, max_iter, path_type, is_warm_start, ic_type, is_cv, K,
+             sequence, s_min, s_max, is_screening, screening_size, always_select=(), fold_of_row=None):
+    x = np.asarray(x, dtype=np.float64)
+    p0 = x.shape[1]
+    always = np.asarray(always_select, dtype=np.int64)
+    scr = None
+    if is_screening:
+        scr = screening(x, y, weight, model_type, screening_size, always)
+        x = x[:, scr]
+        always = np.searchsorted(scr, always) if len(always) else always  # screening.cpp:91-102
+    data = make_data(x, y, weight, data_type, is_normal, model_type)
+    st = PathState(data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, is_warm_start, always)
+    out = sequential_path(st, sequence) if path_type == 1 else gs_path(st, s_min, s_max)
+    if is_screening:
+        b = np.zeros(p0)
+        b[scr] = out["beta"]
+        out["beta"] = b
+        out["screening_A"] = scr
+    out["n_fits"], out["n_iters"], out["min_gap"] = st.n_fits, st.n_iters, st.min_gap
+    return out
