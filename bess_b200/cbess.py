@@ -1,0 +1,129 @@
+"""Stand-in for the reference's SWIG module ``bess.cbess`` (python/bess/cbess.py:65-66, generated from
+python/src/bess.i:17-30).  Same Python-visible calling convention: 38 positional arguments (arrays as ndarrays or
+sequences, then the 8 ARGOUT lengths) -> a 10-element list ``[beta, coef0, train_loss, ic, nullloss, aic, bic, gic,
+A_out, l_out]``, of which the reference only fills the first four (bess.cpp:277-280)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BessB200Error, Ext, dp, ip
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(ip)
+
+
+def _prep(x, y, weight, g_index, state, sequence, lambda_sequence, always_select):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if x.ndim != 2:
+        raise ValueError("x must be 2-D")
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    w = np.ascontiguousarray(weight, dtype=np.float64).ravel()
+    g = np.ascontiguousarray(list(g_index) if not isinstance(g_index, np.ndarray) else g_index, dtype=np.int32)
+    st = np.ascontiguousarray(state, dtype=np.float64).ravel()
+    seq = np.ascontiguousarray(sequence, dtype=np.int32).ravel()
+    lam = np.ascontiguousarray(lambda_sequence, dtype=np.float64).ravel()
+    alw = np.ascontiguousarray(list(always_select), dtype=np.int32).ravel()
+    if st.size == 0:
+        st = np.zeros(1)
+    if lam.size == 0:
+        lam = np.zeros(1)
+    return x, y, w, g, st, seq, lam, alw
+
+
+def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
+                is_warm_start, ic_type, is_cv, K, g_index, state, sequence, lambda_sequence, s_min, s_max, K_max,
+                epsilon, lambda_min, lambda_max, n_lambda, is_screening, screening_size, powell_path, always_select, tao,
+                beta_len, coef0_len=1, train_loss_len=1, ic_len=1, aic_len=1, bic_len=1, gic_len=1, A_len=None):
+    """Drop-in for ``bess.cbess.pywrap_bess`` (SWIG typemaps of python/src/bess.i)."""
+    lib = _lib.load()
+    x, y, w, g, st, seq, lam, alw = _prep(x, y, weight, g_index, state, sequence, lambda_sequence, always_select)
+    n, p = x.shape
+    beta = np.zeros(int(beta_len))
+    c0, tl, ic = np.zeros(1), np.zeros(1), np.zeros(1)
+    nullloss, aic, bic, gic = np.zeros(1), np.zeros(aic_len), np.zeros(bic_len), np.zeros(gic_len)
+    A_out = np.zeros(int(A_len if A_len is not None else beta_len), dtype=np.int32)
+    l_out = np.zeros(1, dtype=np.int32)
+    lib.pywrap_bess(_d(x), n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal), int(algorithm_type),
+                    int(model_type), int(max_iter), int(exchange_num), int(path_type), bool(is_warm_start),
+                    int(ic_type), bool(is_cv), int(K), _i(g), g.size, _d(st), st.size, _i(seq), seq.size, _d(lam),
+                    lam.size, int(s_min), int(s_max), int(K_max), float(epsilon), float(lambda_min), float(lambda_max),
+                    int(n_lambda), bool(is_screening), int(screening_size), int(powell_path), _i(alw), alw.size,
+                    float(tao), _d(beta), beta.size, _d(c0), 1, _d(tl), 1, _d(ic), 1, _d(nullloss), _d(aic), aic.size,
+                    _d(bic), bic.size, _d(gic), gic.size, _i(A_out), A_out.size, _i(l_out))
+    err = _lib.last_error()
+    if err:
+        raise BessB200Error(err)
+    return [beta, c0[0], tl[0], ic[0], nullloss[0], aic, bic, gic, A_out, l_out[0]]
+
+
+def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
+        is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
+        fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True):
+    """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
+    ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``."""
+    lib = _lib.load()
+    if x_device_ptr is None:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n, p = x.shape
+        xptr = _d(x)
+    else:
+        xptr = C.cast(C.c_void_p(int(x_device_ptr)), dp)
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    w = np.ascontiguousarray(weight, dtype=np.float64).ravel()
+    g = np.arange(p, dtype=np.int32)
+    st, lam = np.zeros(1), np.zeros(1)
+    seq = np.ascontiguousarray(sequence, dtype=np.int32).ravel()
+    alw = np.ascontiguousarray(list(always_select), dtype=np.int32).ravel()
+    beta = np.zeros(p)
+    c0, tl, ic = C.c_double(0), C.c_double(0), C.c_double(0)
+    ext = Ext()
+    fold = None
+    if fold_of_row is not None:
+        fold = np.ascontiguousarray(fold_of_row, dtype=np.int32)
+        ext.fold_of_row = _i(fold)
+    ext.cv_seed = int(cv_seed)
+    ext.x_on_device = 1 if x_device_ptr is not None else 0
+    ext.device = int(device)
+    scrA = np.zeros(max(int(screening_size), 1), dtype=np.int32)
+    ext.screening_A_out = _i(scrA)
+    chosen = C.c_int(0)
+    ext.chosen_s_out = C.pointer(chosen)
+    stats = np.zeros(8)
+    ext.stats_out = _d(stats)
+    rc = lib.bess_b200_fit(xptr, n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal),
+                           int(algorithm_type), int(model_type), int(max_iter), int(exchange_num), int(path_type),
+                           bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g), g.size, _d(st), 1, _i(seq),
+                           seq.size, _d(lam), 1, int(s_min), int(s_max), 10, 10.0, 0.0, 0.0, 1, bool(is_screening),
+                           int(screening_size), 1, _i(alw), alw.size, 1.1, _d(beta), p, C.byref(c0), C.byref(tl),
+                           C.byref(ic), C.byref(ext))
+    _lib.check(rc)
+    out = dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, s=chosen.value,
+               stats=dict(n_fits=int(stats[0]), n_pdas_iters=int(stats[1]), n_sweeps=int(stats[2]),
+                          n_batches=int(stats[3]), n_boundary_ties=int(stats[4]), sweep_bytes=float(stats[5]),
+                          kernel_launches=int(stats[6])))
+    if is_screening:
+        out["screening_A"] = scrA[:int(screening_size)].copy()
+    L = int(stats[7])
+    if want_trace and L > 0:
+        s_all, l_all = np.zeros(L, dtype=np.int32), np.zeros(L, dtype=np.int32)
+        c_all, t_all, i_all = np.zeros(L), np.zeros(L), np.zeros(L)
+        b_all = np.zeros((L, p)) if path_type == 1 else None
+        lib.bess_b200_trace(_i(s_all), _i(l_all), _d(c_all) if path_type == 1 else None, _d(t_all), _d(i_all),
+                            _d(b_all) if b_all is not None else None, p)
+        out.update(s_all=s_all, l_all=l_all, coef0_all=c_all, loss_all=t_all, ic_all=i_all, beta_all=b_all)
+    return out
+
+
+def cv_fold_ids(n, K, seed=123):
+    lib = _lib.load()
+    out = np.zeros(n, dtype=np.int32)
+    _lib.check(lib.bess_b200_cv_fold_ids(int(n), int(K), int(seed), _i(out)))
+    return out

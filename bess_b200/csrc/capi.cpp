@@ -1,0 +1,355 @@
+// extern "C" surface of libbess_b200.so (declared in include/bess_b200.h).
+#include "../../include/bess_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+
+#include "kernels.cuh"
+#include "path.h"
+
+using namespace bess;
+
+namespace {
+thread_local std::string g_err;
+thread_local BessResult g_last;
+
+unsigned env_seed()
+{
+    const char *s = std::getenv("BESS_CV_SEED");
+    return s ? (unsigned)std::strtoul(s, nullptr, 10) : 123u;
+}
+
+template <class F>
+int guarded(F &&f)
+{
+    try {
+        g_err.clear();
+        f();
+        return 0;
+    } catch (const EngineError &e) {
+        g_err = e.msg;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+    } catch (...) {
+        g_err = "unknown error";
+    }
+    return 1;
+}
+}  // namespace
+
+struct bessgpu_handle {
+    Engine *eng = nullptr;
+};
+
+// shared by both linkages of pywrap_bess and by bess_b200_fit
+int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, int data_type, double *weight,
+                       int weight_len, bool is_normal, int algorithm_type, int model_type, int max_iter,
+                       int exchange_num, int path_type, bool is_warm_start, int ic_type, bool is_cv, int K, int *gindex,
+                       int gindex_len, double *state, int state_len, int *sequence, int sequence_len,
+                       double *lambda_sequence, int lambda_sequence_len, int s_min, int s_max, int K_max, double epsilon,
+                       double lambda_min, double lambda_max, int n_lambda, bool is_screening, int screening_size,
+                       int powell_path, int *always_select, int always_select_len, double tao, double *beta_out,
+                       int beta_out_len, double *coef0_out, double *train_loss_out, double *ic_out,
+                       const bess_b200_ext *ext)
+{
+    return guarded([&] {
+        if (y_len != x_row || weight_len != x_row) throw EngineError{"y/weight length must equal the number of rows of x"};
+        if (beta_out && beta_out_len < x_col) throw EngineError{"beta_out shorter than p"};
+        BessArgs a;
+        a.x = x; a.n = x_row; a.p = x_col; a.y = y; a.data_type = data_type; a.weight = weight;
+        a.is_normal = is_normal; a.algorithm_type = algorithm_type; a.model_type = model_type; a.max_iter = max_iter;
+        a.exchange_num = exchange_num; a.path_type = path_type; a.is_warm_start = is_warm_start; a.ic_type = ic_type;
+        a.is_cv = is_cv; a.K = K;
+        if (state && state_len > 0) a.state.assign(state, state + state_len);
+        if (sequence && sequence_len > 0) a.sequence.assign(sequence, sequence + sequence_len);
+        if (lambda_sequence && lambda_sequence_len > 0) a.lambda_seq.assign(lambda_sequence, lambda_sequence + lambda_sequence_len);
+        a.s_min = s_min; a.s_max = s_max; a.K_max = K_max; a.epsilon = epsilon; a.lambda_min = lambda_min;
+        a.lambda_max = lambda_max; a.nlambda = n_lambda; a.is_screening = is_screening;
+        a.screening_size = screening_size; a.powell_path = powell_path;
+        if (gindex && gindex_len > 0) a.g_index.assign(gindex, gindex + gindex_len);
+        if (always_select && always_select_len > 0) a.always_select.assign(always_select, always_select + always_select_len);
+        a.tao = tao;
+        a.cv_seed = env_seed();
+        if (ext) {
+            a.fold_of_row = ext->fold_of_row;
+            if (ext->cv_seed) a.cv_seed = ext->cv_seed;
+            a.x_on_device = ext->x_on_device != 0;
+            a.device = ext->device;
+        }
+        BessResult r;
+        bess_run(a, r);
+        if (beta_out) std::copy(r.beta.begin(), r.beta.end(), beta_out);
+        if (coef0_out) *coef0_out = r.coef0;
+        if (train_loss_out) *train_loss_out = r.train_loss;
+        if (ic_out) *ic_out = r.ic;
+        if (ext) {
+            if (ext->screening_A_out && !r.screening_A.empty())
+                std::copy(r.screening_A.begin(), r.screening_A.end(), ext->screening_A_out);
+            if (ext->chosen_s_out) *ext->chosen_s_out = r.chosen_s;
+            if (ext->stats_out) {
+                ext->stats_out[0] = (double)r.stats.n_fits;
+                ext->stats_out[1] = (double)r.stats.n_pdas_iters;
+                ext->stats_out[2] = (double)r.stats.n_sweeps;
+                ext->stats_out[3] = (double)r.stats.n_batches;
+                ext->stats_out[4] = (double)r.stats.n_boundary_ties;
+                ext->stats_out[5] = r.stats.sweep_bytes;
+                ext->stats_out[6] = (double)r.stats.kernel_launches;
+                ext->stats_out[7] = (double)r.s_all.size();
+            }
+        }
+        g_last = std::move(r);
+    });
+}
+
+void bess_b200_pywrap_impl(double *x, int x_row, int x_col, double *y, int y_len, int data_type, double *weight,
+                           int weight_len, bool is_normal, int algorithm_type, int model_type, int max_iter,
+                           int exchange_num, int path_type, bool is_warm_start, int ic_type, bool is_cv, int K,
+                           int *gindex, int gindex_len, double *state, int state_len, int *sequence, int sequence_len,
+                           double *lambda_sequence, int lambda_sequence_len, int s_min, int s_max, int K_max,
+                           double epsilon, double lambda_min, double lambda_max, int n_lambda, bool is_screening,
+                           int screening_size, int powell_path, int *always_select, int always_select_len, double tao,
+                           double *beta_out, int beta_out_len, double *coef0_out, double *train_loss_out, double *ic_out)
+{
+    const int rc = bess_b200_fit_impl(x, x_row, x_col, y, y_len, data_type, weight, weight_len, is_normal, algorithm_type,
+                                      model_type, max_iter, exchange_num, path_type, is_warm_start, ic_type, is_cv, K,
+                                      gindex, gindex_len, state, state_len, sequence, sequence_len, lambda_sequence,
+                                      lambda_sequence_len, s_min, s_max, K_max, epsilon, lambda_min, lambda_max, n_lambda,
+                                      is_screening, screening_size, powell_path, always_select, always_select_len, tao,
+                                      beta_out, beta_out_len, coef0_out, train_loss_out, ic_out, nullptr);
+    if (rc != 0) {
+        std::fprintf(stderr, "bess_b200: pywrap_bess failed: %s\n", g_err.c_str());
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        if (coef0_out) *coef0_out = nan;
+        if (train_loss_out) *train_loss_out = nan;
+        if (ic_out) *ic_out = nan;
+    }
+}
+
+extern "C" {
+
+void pywrap_bess(double *x, int x_row, int x_col, double *y, int y_len, int data_type, double *weight, int weight_len,
+                 bool is_normal, int algorithm_type, int model_type, int max_iter, int exchange_num, int path_type,
+                 bool is_warm_start, int ic_type, bool is_cv, int K, int *gindex, int gindex_len, double *state,
+                 int state_len, int *sequence, int sequence_len, double *lambda_sequence, int lambda_sequence_len,
+                 int s_min, int s_max, int K_max, double epsilon, double lambda_min, double lambda_max, int n_lambda,
+                 bool is_screening, int screening_size, int powell_path, int *always_select, int always_select_len,
+                 double tao, double *beta_out, int beta_out_len, double *coef0_out, int, double *train_loss_out, int,
+                 double *ic_out, int, double *, double *, int, double *, int, double *, int, int *, int, int *)
+{
+    bess_b200_pywrap_impl(x, x_row, x_col, y, y_len, data_type, weight, weight_len, is_normal, algorithm_type, model_type,
+                          max_iter, exchange_num, path_type, is_warm_start, ic_type, is_cv, K, gindex, gindex_len, state,
+                          state_len, sequence, sequence_len, lambda_sequence, lambda_sequence_len, s_min, s_max, K_max,
+                          epsilon, lambda_min, lambda_max, n_lambda, is_screening, screening_size, powell_path,
+                          always_select, always_select_len, tao, beta_out, beta_out_len, coef0_out, train_loss_out, ic_out);
+}
+
+int bess_b200_fit(double *x, int x_row, int x_col, double *y, int y_len, int data_type, double *weight, int weight_len,
+                  bool is_normal, int algorithm_type, int model_type, int max_iter, int exchange_num, int path_type,
+                  bool is_warm_start, int ic_type, bool is_cv, int K, int *gindex, int gindex_len, double *state,
+                  int state_len, int *sequence, int sequence_len, double *lambda_sequence, int lambda_sequence_len,
+                  int s_min, int s_max, int K_max, double epsilon, double lambda_min, double lambda_max, int n_lambda,
+                  bool is_screening, int screening_size, int powell_path, int *always_select, int always_select_len,
+                  double tao, double *beta_out, int beta_out_len, double *coef0_out, double *train_loss_out,
+                  double *ic_out, const bess_b200_ext *ext)
+{
+    return bess_b200_fit_impl(x, x_row, x_col, y, y_len, data_type, weight, weight_len, is_normal, algorithm_type,
+                              model_type, max_iter, exchange_num, path_type, is_warm_start, ic_type, is_cv, K, gindex,
+                              gindex_len, state, state_len, sequence, sequence_len, lambda_sequence, lambda_sequence_len,
+                              s_min, s_max, K_max, epsilon, lambda_min, lambda_max, n_lambda, is_screening,
+                              screening_size, powell_path, always_select, always_select_len, tao, beta_out, beta_out_len,
+                              coef0_out, train_loss_out, ic_out, ext);
+}
+
+int bess_b200_trace(int *s_all, int *l_all, double *coef0_all, double *train_loss_all, double *ic_all, double *beta_all,
+                    int p)
+{
+    const BessResult &r = g_last;
+    const size_t L = r.s_all.size();
+    if (s_all) std::copy(r.s_all.begin(), r.s_all.end(), s_all);
+    if (l_all) std::copy(r.l_all.begin(), r.l_all.end(), l_all);
+    if (coef0_all) std::copy(r.coef0_all.begin(), r.coef0_all.end(), coef0_all);
+    if (train_loss_all) std::copy(r.train_loss_all.begin(), r.train_loss_all.end(), train_loss_all);
+    if (ic_all) std::copy(r.ic_all.begin(), r.ic_all.end(), ic_all);
+    if (beta_all)
+        for (size_t i = 0; i < r.beta_all.size(); i++)
+            std::copy(r.beta_all[i].begin(), r.beta_all[i].begin() + std::min<size_t>((size_t)p, r.beta_all[i].size()),
+                      beta_all + i * (size_t)p);
+    return (int)L;
+}
+
+int bess_b200_cv_fold_ids(int n, int K, unsigned seed, int *out)
+{
+    return guarded([&] {
+        if (n < 1 || K < 1 || K > n) throw EngineError{"cv_fold_ids: need 1 <= K <= n"};
+        std::vector<int> f = cv_fold_ids(n, K, seed);
+        std::copy(f.begin(), f.end(), out);
+    });
+}
+
+const char *bess_b200_last_error(void) { return g_err.c_str(); }
+int bess_b200_version(void) { return BESS_B200_VERSION; }
+int bess_b200_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+
+// ---- device shim -------------------------------------------------------------------------------------------------
+int bessgpu_create(bessgpu_handle **h, int device)
+{
+    return guarded([&] {
+        bessgpu_handle *hh = new bessgpu_handle();
+        try {
+            hh->eng = new Engine(device);
+        } catch (...) {
+            delete hh;
+            throw;
+        }
+        *h = hh;
+    });
+}
+int bessgpu_destroy(bessgpu_handle *h)
+{
+    return guarded([&] {
+        if (h) {
+            delete h->eng;
+            delete h;
+        }
+    });
+}
+int bessgpu_load(bessgpu_handle *h, const double *x, int n, int p, int x_on_device, const double *y,
+                 const double *weight, int model_type)
+{
+    return guarded([&] { h->eng->load(x, n, p, x_on_device != 0, y, weight, model_type); });
+}
+int bessgpu_screen(bessgpu_handle *h, int size, const int *always, int n_always, int *out)
+{
+    return guarded([&] {
+        std::vector<int> al(always, always + (always ? n_always : 0));
+        std::vector<int> r = h->eng->screen(size, al);
+        std::copy(r.begin(), r.end(), out);
+    });
+}
+int bessgpu_normalize(bessgpu_handle *h, int data_type, int is_normal)
+{
+    return guarded([&] { h->eng->normalize(data_type, is_normal != 0); });
+}
+int bessgpu_get_norm(bessgpu_handle *h, double *xm, double *xn, double *ym)
+{
+    return guarded([&] {
+        if (xm) std::copy(h->eng->x_mean().begin(), h->eng->x_mean().end(), xm);
+        if (xn) std::copy(h->eng->x_norm().begin(), h->eng->x_norm().end(), xn);
+        if (ym) *ym = h->eng->y_mean();
+    });
+}
+int bessgpu_setup_chains(bessgpu_handle *h, int K, const int *fold_of_row, int kcap, int max_iter, int warm,
+                         const int *always, int n_always)
+{
+    return guarded([&] {
+        std::vector<int> al(always, always + (always ? n_always : 0));
+        h->eng->setup_chains(K, fold_of_row, kcap, max_iter, warm != 0, al);
+    });
+}
+int bessgpu_run_batch(bessgpu_handle *h, int T, const int *chains, int nch, int new_path_step, int *l_out,
+                      double *coef0_out, int *A_out, double *bA_out)
+{
+    return guarded([&] {
+        std::vector<int> ch(chains, chains + nch);
+        BatchResult br;
+        h->eng->run_batch(T, ch, new_path_step != 0, br);
+        for (int i = 0; i < nch; i++) {
+            if (l_out) l_out[i] = br.l[i];
+            if (coef0_out) coef0_out[i] = br.coef0[i];
+            if (A_out) std::copy(br.A[i].begin(), br.A[i].end(), A_out + (size_t)i * T);
+            if (bA_out) std::copy(br.bA[i].begin(), br.bA[i].end(), bA_out + (size_t)i * T);
+        }
+    });
+}
+int bessgpu_losses(bessgpu_handle *h, const int *chain, const int *kind, const int *fold, int njobs, double *out)
+{
+    return guarded([&] {
+        std::vector<LossJob> jobs;
+        for (int i = 0; i < njobs; i++) jobs.push_back({chain[i], kind[i], fold[i]});
+        std::vector<double> v;
+        h->eng->losses(jobs, v);
+        std::copy(v.begin(), v.end(), out);
+    });
+}
+int bessgpu_time_dual_sweep(bessgpu_handle *h, int reps, float *ms_out, double *bytes_out)
+{
+    return guarded([&] {
+        *ms_out = h->eng->time_dual_sweep(0, reps);
+        if (bytes_out) *bytes_out = 8.0 * (double)h->eng->n() * (double)h->eng->p();
+    });
+}
+int bessgpu_stats(bessgpu_handle *h, double *o)
+{
+    return guarded([&] {
+        const EngineStats &s = h->eng->stats();
+        o[0] = (double)s.n_fits; o[1] = (double)s.n_pdas_iters; o[2] = (double)s.n_sweeps; o[3] = (double)s.n_batches;
+        o[4] = (double)s.n_boundary_ties; o[5] = s.sweep_bytes; o[6] = (double)s.kernel_launches; o[7] = 0.0;
+    });
+}
+int bessgpu_topk(const double *vals, int n, int k, int *idx_out, int *tie_out)
+{
+    return guarded([&] {
+        if (k < 1 || k > n) throw EngineError{"topk: need 1 <= k <= n"};
+        auto ck = [](cudaError_t e) { if (e != cudaSuccess) throw EngineError{cudaGetErrorString(e)}; };
+        configure_kernels();
+        double *dv = nullptr, *ck0 = nullptr, *ck1 = nullptr;
+        int *ci0 = nullptr, *ci1 = nullptr, *dout = nullptr, *dtie = nullptr;
+        const long long cs = std::max<long long>(2LL * k + 16, ((long long)n / 8192 + 2) * std::min(k, TOPK_LMAX));
+        ck(cudaMalloc(&dv, (size_t)n * 8));
+        ck(cudaMalloc(&ck0, (size_t)cs * 8)); ck(cudaMalloc(&ck1, (size_t)cs * 8));
+        ck(cudaMalloc(&ci0, (size_t)cs * 4)); ck(cudaMalloc(&ci1, (size_t)cs * 4));
+        ck(cudaMalloc(&dout, (size_t)k * 4)); ck(cudaMalloc(&dtie, 4));
+        ck(cudaMemcpy(dv, vals, (size_t)n * 8, cudaMemcpyHostToDevice));
+        ck(cudaMemset(dtie, 0, 4));
+        launch_topk(dv, n, n, k, 1, dout, k, dtie, ck0, ci0, ck1, ci1, cs, 0);
+        ck(cudaMemcpy(idx_out, dout, (size_t)k * 4, cudaMemcpyDeviceToHost));
+        if (tie_out) ck(cudaMemcpy(tie_out, dtie, 4, cudaMemcpyDeviceToHost));
+        cudaFree(dv); cudaFree(ck0); cudaFree(ck1); cudaFree(ci0); cudaFree(ci1); cudaFree(dout); cudaFree(dtie);
+    });
+}
+
+// ---- multi-GPU host helpers ------------------------------------------------------------------------------------------
+void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi)
+{
+    // contiguous, even-aligned shards (16-byte loads need even column offsets), remainder spread over the first ranks
+    const long long pairs = (p + 1) / 2;
+    const long long base = pairs / world, rem = pairs % world;
+    const long long b = rank * base + std::min<long long>(rank, rem);
+    const long long e = b + base + (rank < rem ? 1 : 0);
+    *lo = std::min(p, 2 * b);
+    *hi = std::min(p, 2 * e);
+}
+int bess_b200_chain_owner(int chain, int world) { return world > 0 ? chain % world : 0; }
+int bess_b200_merge_candidates(const double *vals, const int *idx, int count, int k, int *idx_out)
+{
+    return guarded([&] {
+        if (k < 0 || k > count) throw EngineError{"merge_candidates: need 0 <= k <= count"};
+        std::vector<int> ord((size_t)count);
+        for (int i = 0; i < count; i++) ord[(size_t)i] = i;
+        std::sort(ord.begin(), ord.end(), [&](int a, int b) {
+            if (vals[a] != vals[b]) return vals[a] > vals[b];
+            return idx[a] < idx[b];
+        });
+        std::vector<int> sel((size_t)k);
+        for (int i = 0; i < k; i++) sel[(size_t)i] = idx[ord[(size_t)i]];
+        std::sort(sel.begin(), sel.end());
+        std::copy(sel.begin(), sel.end(), idx_out);
+    });
+}
+
+}  // extern "C"

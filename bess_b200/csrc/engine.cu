@@ -1,0 +1,591 @@
+// Device engine: owns the design matrix and all chain state in HBM and drives the kernels of kernels.cu.
+// See engine.h for the vocabulary.  All compute is on the GPU; there is no CPU fallback anywhere in this file.
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace bess {
+
+#define CUDA_CHECK(x)                                                               \
+    do {                                                                            \
+        cudaError_t e_ = (x);                                                       \
+        if (e_ != cudaSuccess) {                                                    \
+            throw EngineError{std::string(#x) + ": " + cudaGetErrorString(e_)};     \
+        }                                                                           \
+    } while (0)
+
+namespace {
+template <class T>
+T *dalloc(size_t count)
+{
+    T *p = nullptr;
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    return p;
+}
+template <class T>
+void dfree(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+int pick_fs(int nch)
+{
+    const int opts[] = {1, 2, 4, 6, 8, 12, 16};
+    for (int o : opts)
+        if (o >= nch) return o;
+    throw EngineError{"too many chains (K must be <= 15)"};
+}
+}  // namespace
+
+struct Engine::Impl {
+    cudaStream_t st = nullptr;
+    int sm_count = 148;
+    Dev d{};
+    // design
+    double *X = nullptr;
+    long long ldx = 0;
+    int n = 0, p = 0, npad = 0;
+    double *y = nullptr, *w = nullptr;  // [npad] device
+    std::vector<double> hy, hw;          // host copies (current, i.e. after normalisation)
+    // sweep scratch for the setup phases (screening / normalisation), FS = 1
+    double *raw = nullptr;  // [2][FS][pstride]
+    // chain setup
+    int K = 0, nchains = 1;
+    int *testrows = nullptr, *ntest = nullptr;
+    double *lfact = nullptr;
+    double *loss_scratch = nullptr, *loss_out = nullptr;
+    int *always = nullptr;
+    int n_always = 0;
+    double *ck0 = nullptr, *ck1 = nullptr;
+    int *ci0 = nullptr, *ci1 = nullptr;
+    long long cstride = 0;
+    // pinned host mirrors
+    int *h_done = nullptr, *h_l = nullptr, *h_ks = nullptr, *h_A = nullptr, *h_tie = nullptr;
+    double *h_coef0 = nullptr, *h_bA = nullptr, *h_loss = nullptr;
+    bool chains_ready = false;
+
+    void free_sweep_buffers()
+    {
+        dfree(d.G); dfree(d.W); dfree(d.TH); dfree(d.C2);
+        dfree(d.part); dfree(d.c2sum); dfree(d.bd); dfree(raw);
+    }
+    void free_chain_buffers()
+    {
+        dfree(d.rows); dfree(d.ntrain); dfree(d.ytr); dfree(d.wtr); dfree(d.ks); dfree(d.A); dfree(d.bA);
+        dfree(d.coef0); dfree(d.coef0_level); dfree(d.Anew); dfree(d.hist); dfree(d.l); dfree(d.done); dfree(d.tie);
+        dfree(d.betaD); dfree(d.XA); dfree(d.XB); dfree(d.vec); dfree(d.Smat); dfree(d.xtx);
+        dfree(testrows); dfree(ntest); dfree(lfact); dfree(loss_scratch); dfree(loss_out); dfree(always);
+        dfree(ck0); dfree(ck1); dfree(ci0); dfree(ci1);
+        chains_ready = false;
+    }
+    // (re)allocate the sweep vectors / partial buffers for FS chain slots over the current (n, p)
+    void config_sweep(int FS)
+    {
+        free_sweep_buffers();
+        d.X = X; d.ldx = ldx; d.n = n; d.p = p; d.FS = FS;
+        d.pstride = (p + 1) & ~1LL;
+        // row splits: enough CTAs to fill the machine several times over
+        const long long ntiles = (p + 2LL * SWEEP_NT - 1) / (2LL * SWEEP_NT);
+        long long want = (6LL * sm_count + ntiles - 1) / ntiles;
+        long long smax = std::max<long long>(1, n / SWEEP_RC);
+        long long S = std::max<long long>(1, std::min(want, smax));
+        int rps = (int)((n + S - 1) / S);
+        rps = (rps + 1) & ~1;
+        d.rows_per_split = rps;
+        d.S = (n + rps - 1) / rps;
+        const size_t vsz = (size_t)npad * FS;
+        d.G = dalloc<double>(vsz); d.W = dalloc<double>(vsz); d.TH = dalloc<double>(vsz); d.C2 = dalloc<double>(vsz);
+        CUDA_CHECK(cudaMemsetAsync(d.G, 0, vsz * 8, st));
+        CUDA_CHECK(cudaMemsetAsync(d.W, 0, vsz * 8, st));
+        CUDA_CHECK(cudaMemsetAsync(d.TH, 0, vsz * 8, st));
+        CUDA_CHECK(cudaMemsetAsync(d.C2, 0, vsz * 8, st));
+        d.part = dalloc<double>((size_t)d.S * 5 * FS * d.pstride);
+        d.c2sum = dalloc<double>((size_t)d.S * FS);
+        d.bd = dalloc<double>((size_t)FS * d.pstride);
+        raw = dalloc<double>((size_t)2 * FS * d.pstride);
+    }
+    // upload a host vector into slot f of a [npad][FS] sweep vector
+    void put_vec(double *dst, int f, const std::vector<double> &v)
+    {
+        CUDA_CHECK(cudaMemcpy2DAsync(dst + f, (size_t)d.FS * 8, v.data(), 8, 8, v.size(), cudaMemcpyHostToDevice, st));
+    }
+};
+
+Engine::Engine(int device)
+{
+    d_ = new Impl();
+    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) throw EngineError{"bess_b200 needs an sm_100a (Blackwell) device"};
+    d_->sm_count = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&d_->st, cudaStreamNonBlocking));
+    configure_kernels();
+    CUDA_CHECK(cudaMallocHost(&d_->h_done, MAXC * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&d_->h_l, MAXC * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&d_->h_ks, MAXC * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&d_->h_tie, MAXC * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&d_->h_coef0, MAXC * sizeof(double)));
+    CUDA_CHECK(cudaMallocHost(&d_->h_loss, 2 * MAXC * sizeof(double)));
+}
+
+Engine::~Engine()
+{
+    if (!d_) return;
+    cudaStreamSynchronize(d_->st);
+    d_->free_chain_buffers();
+    d_->free_sweep_buffers();
+    dfree(d_->X); dfree(d_->y); dfree(d_->w);
+    cudaFreeHost(d_->h_done); cudaFreeHost(d_->h_l); cudaFreeHost(d_->h_ks); cudaFreeHost(d_->h_tie);
+    cudaFreeHost(d_->h_coef0); cudaFreeHost(d_->h_loss);
+    if (d_->h_A) cudaFreeHost(d_->h_A);
+    if (d_->h_bA) cudaFreeHost(d_->h_bA);
+    cudaStreamDestroy(d_->st);
+    delete d_;
+}
+
+void Engine::load(const double *x, int n, int p, bool x_on_device, const double *y, const double *weight, int family)
+{
+    Impl &m = *d_;
+    if (n < 2 || p < 1) throw EngineError{"load: need n >= 2 and p >= 1"};
+    if (family < 1 || family > 4) throw EngineError{"load: model_type must be 1..4"};
+    m.free_chain_buffers();
+    m.free_sweep_buffers();
+    dfree(m.X); dfree(m.y); dfree(m.w);
+    n_ = n; p_ = p; family_ = family;
+    m.n = n; m.p = p; m.npad = (n + 1) & ~1;
+    m.ldx = (p + 1) & ~1LL;
+    m.X = dalloc<double>((size_t)n * m.ldx);
+    if (m.ldx != p) CUDA_CHECK(cudaMemsetAsync(m.X, 0, (size_t)n * m.ldx * 8, m.st));
+    CUDA_CHECK(cudaMemcpy2DAsync(m.X, (size_t)m.ldx * 8, x, (size_t)p * 8, (size_t)p * 8, n,
+                                 x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m.st));
+    m.hy.assign(y, y + n);
+    m.hw.assign(weight, weight + n);
+    m.y = dalloc<double>(m.npad);
+    m.w = dalloc<double>(m.npad);
+    CUDA_CHECK(cudaMemsetAsync(m.y, 0, m.npad * 8, m.st));
+    CUDA_CHECK(cudaMemsetAsync(m.w, 0, m.npad * 8, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.y, y, n * 8, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.w, weight, n * 8, cudaMemcpyHostToDevice, m.st));
+    m.d = Dev{};
+    m.d.family = family;
+    h_xmean_.assign(p, 0.0);
+    h_xnorm_.assign(p, 0.0);
+    y_mean_ = 0.0;
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+}
+
+// screening.cpp:26-105
+std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
+{
+    Impl &m = *d_;
+    if (size < 1 || size > m.p) throw EngineError{"screening_size must be in [1, p]"};
+    m.config_sweep(1);
+    BatchDesc b{};
+    b.nch = 1;
+    b.chain[0] = 0;
+    if (family_ == FAM_LM) {
+        // one-column least squares on RAW x (screening.cpp:46): (x_j.y / x_j.x_j)^2
+        std::vector<double> ones(m.n, 1.0);
+        m.put_vec(m.d.G, 0, m.hy);
+        m.put_vec(m.d.W, 0, ones);
+        launch_dual_sweep(m.d, MODE_DH, m.st);
+        launch_finish(m.d, MODE_DH, EPI_SCREEN_LM, b, nullptr, m.st);
+        stats_.n_sweeps++;
+        stats_.sweep_bytes += 8.0 * m.n * m.p;
+        stats_.kernel_launches += 2;
+    } else {
+        launch_screen_glm(m.X, m.ldx, m.n, m.p, m.y, m.w, family_, m.d.bd, m.st);
+        stats_.kernel_launches += 1;
+    }
+    int *d_alw = nullptr;
+    if (!always_select.empty()) {
+        d_alw = dalloc<int>(always_select.size());
+        CUDA_CHECK(cudaMemcpyAsync(d_alw, always_select.data(), always_select.size() * 4, cudaMemcpyHostToDevice, m.st));
+        launch_pin(m.d, m.d.bd, m.d.pstride, 1, d_alw, (int)always_select.size(), m.st);
+    }
+    // top-k scratch
+    const long long cstride = std::max<long long>(2LL * size + 16, ((long long)m.p / 8192 + 2) * std::min(size, TOPK_LMAX));
+    double *ck0 = dalloc<double>(cstride), *ck1 = dalloc<double>(cstride);
+    int *ci0 = dalloc<int>(cstride), *ci1 = dalloc<int>(cstride);
+    int *d_sel = dalloc<int>(size);
+    int *d_tie = dalloc<int>(1);
+    launch_topk(m.d.bd, m.d.pstride, m.p, size, 1, d_sel, size, d_tie, ck0, ci0, ck1, ci1, cstride, m.st);
+    std::vector<int> sel(size);
+    int tie = 0;
+    CUDA_CHECK(cudaMemcpyAsync(sel.data(), d_sel, size * 4, cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
+    // X <- X[:, sel]  (screening.cpp:83-88)
+    const long long ldn = (size + 1) & ~1LL;
+    double *Xn = dalloc<double>((size_t)m.n * ldn);
+    if (ldn != size) CUDA_CHECK(cudaMemsetAsync(Xn, 0, (size_t)m.n * ldn * 8, m.st));
+    launch_gather_cols(m.X, m.ldx, m.n, d_sel, size, Xn, ldn, m.st);
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    stats_.n_boundary_ties += tie;
+    stats_.kernel_launches += 3;
+    dfree(m.X);
+    m.X = Xn;
+    m.ldx = ldn;
+    m.p = size;
+    p_ = size;
+    dfree(ck0); dfree(ck1); dfree(ci0); dfree(ci1); dfree(d_sel); dfree(d_tie); dfree(d_alw);
+    m.free_sweep_buffers();
+    h_xmean_.assign(size, 0.0);
+    h_xnorm_.assign(size, 0.0);
+    return sel;
+}
+
+// Data ctor (Data.h:41-68) + normalize.cpp + add_weight (Data.h:70-77, bess.cpp:97)
+void Engine::normalize(int data_type, bool is_normal)
+{
+    Impl &m = *d_;
+    const int n = m.n, p = m.p;
+    m.config_sweep(1);
+    BatchDesc b{};
+    b.nch = 1;
+    b.chain[0] = 0;
+    double *d_mean = nullptr, *d_mul = nullptr, *d_rowmul = nullptr;
+    if (is_normal) {
+        if (data_type == 1 || data_type == 2) {
+            // meanx_j = w.x_j / n  (normalize.cpp:25-28, 52-55)
+            std::vector<double> g(n);
+            for (int i = 0; i < n; i++) g[i] = m.hw[i] / (double)n;
+            m.put_vec(m.d.G, 0, g);
+            launch_dual_sweep(m.d, MODE_D, m.st);
+            launch_finish(m.d, MODE_D, EPI_RAW, b, m.raw, m.st);
+            d_mean = dalloc<double>(m.d.pstride);
+            CUDA_CHECK(cudaMemcpyAsync(d_mean, m.raw, (size_t)p * 8, cudaMemcpyDeviceToDevice, m.st));
+            CUDA_CHECK(cudaMemcpyAsync(h_xmean_.data(), m.raw, (size_t)p * 8, cudaMemcpyDeviceToHost, m.st));
+            launch_center_scale(m.X, m.ldx, n, p, d_mean, nullptr, nullptr, m.st);
+            stats_.kernel_launches += 3;
+        }
+        if (data_type == 1) {
+            double s = 0.0;
+            for (int i = 0; i < n; i++) s += m.hy[i] * m.hw[i];  // normalize.cpp:29
+            y_mean_ = s / (double)n;
+            for (int i = 0; i < n; i++) m.hy[i] -= y_mean_;
+        }
+        // normx_j = sqrt(w.(x_j)^2) on the centred column (normalize.cpp:36-41)
+        std::vector<double> zero(n, 0.0);
+        m.put_vec(m.d.G, 0, zero);
+        m.put_vec(m.d.W, 0, m.hw);
+        launch_dual_sweep(m.d, MODE_DH, m.st);
+        launch_finish(m.d, MODE_DH, EPI_RAW, b, m.raw, m.st);
+        std::vector<double> h(p);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), m.raw + (size_t)m.d.FS * m.d.pstride, (size_t)p * 8, cudaMemcpyDeviceToHost,
+                                   m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        std::vector<double> mul(p);
+        const double sn = std::sqrt((double)n);
+        for (int j = 0; j < p; j++) {
+            h_xnorm_[j] = std::sqrt(h[j]);
+            mul[j] = sn / h_xnorm_[j];  // normalize.cpp:42-45
+        }
+        d_mul = dalloc<double>(m.d.pstride);
+        CUDA_CHECK(cudaMemcpyAsync(d_mul, mul.data(), (size_t)p * 8, cudaMemcpyHostToDevice, m.st));
+        stats_.kernel_launches += 2;
+        stats_.n_sweeps += 2;
+        stats_.sweep_bytes += 16.0 * n * p;
+    }
+    if (family_ == FAM_LM) {
+        // add_weight: rows scaled by sqrt(w) (Data.h:70-77)
+        std::vector<double> rm(n);
+        for (int i = 0; i < n; i++) {
+            rm[i] = std::sqrt(m.hw[i]);
+            m.hy[i] *= rm[i];
+        }
+        d_rowmul = dalloc<double>(n);
+        CUDA_CHECK(cudaMemcpyAsync(d_rowmul, rm.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
+    }
+    if (d_mul || d_rowmul) {
+        launch_center_scale(m.X, m.ldx, n, p, nullptr, d_mul, d_rowmul, m.st);
+        stats_.kernel_launches += 1;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(m.y, m.hy.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    dfree(d_mean); dfree(d_mul); dfree(d_rowmul);
+    m.free_sweep_buffers();
+}
+
+void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter, bool warm_start,
+                          const std::vector<int> &always_select)
+{
+    Impl &m = *d_;
+    const int n = m.n, p = m.p;
+    if (K < 0 || K > MAXC - 1) throw EngineError{"K (nfolds) must be in [0, 15]"};
+    if (max_iter < 1 || max_iter > MAX_HIST - 2) throw EngineError{"max_iter must be in [1, 64]"};
+    if (kcap < 1 || kcap > p) throw EngineError{"support size must be in [1, p]"};
+    m.free_chain_buffers();
+    m.K = K;
+    m.nchains = 1 + K;
+    const int C = m.nchains;
+    m.config_sweep(pick_fs(C));
+    Dev &d = m.d;
+    d.kcap = kcap;
+    d.ldA = (kcap + 2 + 1) & ~1;
+    d.max_iter = max_iter;
+    d.warm = warm_start ? 1 : 0;
+
+    // ---- row lists (Metric.h:80-103: train masks are the sorted complement of each fold)
+    std::vector<int> rows((size_t)MAXC * n, 0), ntrain(MAXC, 0), testrows((size_t)MAXC * n, 0), ntest(MAXC, 0);
+    for (int i = 0; i < n; i++) rows[i] = i;
+    ntrain[0] = n;
+    for (int k = 0; k < K; k++) {
+        int a = 0, t = 0;
+        for (int i = 0; i < n; i++) {
+            if (fold_of_row[i] < 0 || fold_of_row[i] >= K) throw EngineError{"fold_of_row out of range"};
+            if (fold_of_row[i] == k) testrows[(size_t)k * n + t++] = i;
+            else rows[(size_t)(1 + k) * n + a++] = i;
+        }
+        ntrain[1 + k] = a;
+        ntest[k] = t;
+        if (a < 2) throw EngineError{"a CV fold leaves fewer than 2 training rows"};
+    }
+    std::vector<double> ytr((size_t)MAXC * n, 0.0), wtr((size_t)MAXC * n, 0.0);
+    for (int c = 0; c < C; c++)
+        for (int r = 0; r < ntrain[c]; r++) {
+            ytr[(size_t)c * n + r] = m.hy[rows[(size_t)c * n + r]];
+            wtr[(size_t)c * n + r] = m.hw[rows[(size_t)c * n + r]];
+        }
+    d.rows = dalloc<int>((size_t)MAXC * n);
+    d.ntrain = dalloc<int>(MAXC);
+    d.ytr = dalloc<double>((size_t)MAXC * n);
+    d.wtr = dalloc<double>((size_t)MAXC * n);
+    m.testrows = dalloc<int>((size_t)MAXC * n);
+    m.ntest = dalloc<int>(MAXC);
+    CUDA_CHECK(cudaMemcpyAsync(d.rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(d.ntrain, ntrain.data(), MAXC * 4, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(d.ytr, ytr.data(), ytr.size() * 8, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(d.wtr, wtr.data(), wtr.size() * 8, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.testrows, testrows.data(), testrows.size() * 4, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.ntest, ntest.data(), MAXC * 4, cudaMemcpyHostToDevice, m.st));
+
+    // ---- chain tables
+    d.ks = dalloc<int>(MAXC);
+    d.A = dalloc<int>((size_t)MAXC * kcap);
+    d.bA = dalloc<double>((size_t)MAXC * kcap);
+    d.coef0 = dalloc<double>(MAXC);
+    d.coef0_level = dalloc<double>(1);
+    d.Anew = dalloc<int>((size_t)MAXC * kcap);
+    d.hist = dalloc<int>((size_t)MAXC * MAX_HIST * kcap);
+    d.l = dalloc<int>(MAXC);
+    d.done = dalloc<int>(MAXC);
+    d.tie = dalloc<int>(MAXC);
+    d.betaD = dalloc<double>((size_t)C * d.pstride);
+    d.XA = dalloc<double>((size_t)C * n * d.ldA);
+    d.XB = family_ == FAM_COX ? dalloc<double>((size_t)C * n * d.ldA) : nullptr;
+    d.vec = dalloc<double>((size_t)C * NVEC * n);
+    d.Smat = dalloc<double>((size_t)C * 2 * d.ldA * d.ldA);
+    CUDA_CHECK(cudaMemsetAsync(d.ks, 0, MAXC * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.A, 0, (size_t)MAXC * kcap * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.bA, 0, (size_t)MAXC * kcap * 8, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.coef0, 0, MAXC * 8, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.coef0_level, 0, 8, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.l, 0, MAXC * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.done, 0, MAXC * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.tie, 0, MAXC * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.betaD, 0, (size_t)C * d.pstride * 8, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.XA, 0, (size_t)C * n * d.ldA * 8, m.st));
+
+    // ---- x_j.x_j over each chain's train rows (utilities.cpp:153-165, Metric.h:108-129); gaussian only
+    if (family_ == FAM_LM) {
+        d.xtx = dalloc<double>((size_t)C * d.pstride);
+        std::vector<double> ind((size_t)m.npad * d.FS, 0.0);
+        for (int c = 0; c < C; c++)
+            for (int r = 0; r < ntrain[c]; r++) ind[(size_t)rows[(size_t)c * n + r] * d.FS + c] = 1.0;
+        CUDA_CHECK(cudaMemcpyAsync(d.W, ind.data(), ind.size() * 8, cudaMemcpyHostToDevice, m.st));
+        BatchDesc b{};
+        b.nch = C;
+        for (int c = 0; c < C; c++) b.chain[c] = c;
+        launch_dual_sweep(d, MODE_DH, m.st);
+        launch_finish(d, MODE_DH, EPI_RAW, b, m.raw, m.st);
+        for (int c = 0; c < C; c++)
+            CUDA_CHECK(cudaMemcpyAsync(d.xtx + (size_t)c * d.pstride, m.raw + ((size_t)d.FS + c) * d.pstride,
+                                       (size_t)d.pstride * 8, cudaMemcpyDeviceToDevice, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));  // `ind` must outlive the copy
+        CUDA_CHECK(cudaMemsetAsync(d.W, 0, ind.size() * 8, m.st));
+        stats_.n_sweeps++;
+        stats_.sweep_bytes += 8.0 * n * p;
+        stats_.kernel_launches += 2;
+    }
+    // ---- poisson: sum_{j<=y} log j (poisson.cpp:29-44), same summation order as the reference
+    {
+        std::vector<double> lf(n, 0.0);
+        if (family_ == FAM_POISSON) {
+            double ymax = 0.0;
+            for (int i = 0; i < n; i++) ymax = std::max(ymax, m.hy[i]);
+            if (ymax <= 5.0e7) {
+                std::vector<double> cum((size_t)ymax + 2, 0.0);
+                for (size_t j = 1; j < cum.size(); j++) cum[j] = cum[j - 1] + std::log((double)j);
+                for (int i = 0; i < n; i++) {
+                    const double yi = m.hy[i];
+                    lf[i] = (yi == 1.0 || yi < 1.0) ? 0.0 : cum[(size_t)std::floor(yi)];
+                }
+            } else {
+                for (int i = 0; i < n; i++) lf[i] = m.hy[i] < 1.0 ? 0.0 : std::lgamma(std::floor(m.hy[i]) + 1.0);
+            }
+        }
+        m.lfact = dalloc<double>(n);
+        CUDA_CHECK(cudaMemcpyAsync(m.lfact, lf.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+    }
+    m.loss_scratch = dalloc<double>((size_t)2 * MAXC * 2 * n);
+    m.loss_out = dalloc<double>(2 * MAXC);
+    m.n_always = (int)always_select.size();
+    if (m.n_always) {
+        m.always = dalloc<int>(m.n_always);
+        CUDA_CHECK(cudaMemcpyAsync(m.always, always_select.data(), (size_t)m.n_always * 4, cudaMemcpyHostToDevice, m.st));
+    }
+    m.cstride = std::max<long long>(2LL * kcap + 16, ((long long)p / 8192 + 2) * std::min(kcap, TOPK_LMAX));
+    m.ck0 = dalloc<double>((size_t)C * m.cstride);
+    m.ck1 = dalloc<double>((size_t)C * m.cstride);
+    m.ci0 = dalloc<int>((size_t)C * m.cstride);
+    m.ci1 = dalloc<int>((size_t)C * m.cstride);
+    if (m.h_A) cudaFreeHost(m.h_A);
+    if (m.h_bA) cudaFreeHost(m.h_bA);
+    CUDA_CHECK(cudaMallocHost(&m.h_A, (size_t)MAXC * kcap * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&m.h_bA, (size_t)MAXC * kcap * sizeof(double)));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    S_ = d.S;
+    m.chains_ready = true;
+}
+
+static inline int sweep_mode(int family) { return family == FAM_LM ? MODE_D : (family == FAM_COX ? MODE_COX : MODE_DH); }
+static inline int sweep_epi(int family)
+{
+    return family == FAM_LM ? EPI_SACR_LM : (family == FAM_COX ? EPI_SACR_COX : EPI_SACR_GLM);
+}
+
+void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out)
+{
+    Impl &m = *d_;
+    if (!m.chains_ready) throw EngineError{"run_batch before setup_chains"};
+    Dev &d = m.d;
+    if (T < 1 || T > d.kcap) throw EngineError{"sparsity level outside [1, kcap]"};
+    if (chains.empty() || (int)chains.size() > m.nchains) throw EngineError{"bad chain set"};
+    BatchDesc b{};
+    b.nch = (int)chains.size();
+    b.T = T;
+    b.new_path_step = new_path_step ? 1 : 0;
+    int cmin = MAXC, cmax = -1;
+    for (int i = 0; i < b.nch; i++) {
+        if (chains[i] < 0 || chains[i] >= m.nchains) throw EngineError{"chain id out of range"};
+        b.chain[i] = chains[i];
+        cmin = std::min(cmin, chains[i]);
+        cmax = std::max(cmax, chains[i]);
+    }
+    if (new_path_step && chains[0] != 0) throw EngineError{"a new path step must include the full-data chain"};
+    const int mode = sweep_mode(family_), epi = sweep_epi(family_);
+    const double vec_bytes = 8.0 * d.n * b.nch * (mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 4)) + 8.0 * d.p * b.nch;
+
+    launch_chain_begin(d, b, m.st);
+    stats_.kernel_launches++;
+    int iters = 0;
+    for (int it = 1; it <= d.max_iter; it++) {
+        launch_dual_sweep(d, mode, m.st);
+        launch_finish(d, mode, epi, b, nullptr, m.st);
+        if (m.n_always) launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
+        launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1, d.Anew + (size_t)cmin * d.kcap,
+                    d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st);
+        launch_chain_fit(d, b, m.st);
+        CUDA_CHECK(cudaMemcpyAsync(m.h_done, d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_tie, d.tie, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        iters = it;
+        stats_.n_sweeps++;
+        stats_.sweep_bytes += 8.0 * d.n * d.p + vec_bytes;
+        stats_.kernel_launches += 4 + (m.n_always ? 1 : 0);
+        bool all = true;
+        for (int i = 0; i < b.nch; i++) {
+            all = all && m.h_done[b.chain[i]];
+            stats_.n_boundary_ties += m.h_tie[b.chain[i]];
+        }
+        if (all) break;
+    }
+    (void)iters;
+    CUDA_CHECK(cudaMemcpyAsync(m.h_l, d.l, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.h_coef0, d.coef0, MAXC * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.h_A, d.A, (size_t)MAXC * d.kcap * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.h_bA, d.bA, (size_t)MAXC * d.kcap * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    out.T = T;
+    out.nchains = b.nch;
+    for (int i = 0; i < b.nch; i++) {
+        const int c = b.chain[i];
+        out.chain_ids[i] = c;
+        out.l[i] = m.h_l[c];
+        out.coef0[i] = m.h_coef0[c];
+        out.A[i].assign(m.h_A + (size_t)c * d.kcap, m.h_A + (size_t)c * d.kcap + T);
+        out.bA[i].assign(m.h_bA + (size_t)c * d.kcap, m.h_bA + (size_t)c * d.kcap + T);
+        stats_.n_pdas_iters += std::min(m.h_l[c], d.max_iter);
+    }
+    stats_.n_fits += b.nch;
+    stats_.n_batches++;
+}
+
+void Engine::losses(const std::vector<LossJob> &jobs, std::vector<double> &out)
+{
+    Impl &m = *d_;
+    if (jobs.empty()) { out.clear(); return; }
+    if ((int)jobs.size() > 2 * MAXC) throw EngineError{"too many loss jobs"};
+    LossDesc ld{};
+    ld.njobs = (int)jobs.size();
+    for (int i = 0; i < ld.njobs; i++) {
+        ld.chain[i] = jobs[i].chain;
+        ld.kind[i] = jobs[i].kind;
+        ld.fold[i] = jobs[i].fold;
+    }
+    launch_losses(m.d, ld, m.testrows, m.ntest, m.y, m.w, m.lfact, m.loss_scratch, m.loss_out, m.st);
+    CUDA_CHECK(cudaMemcpyAsync(m.h_loss, m.loss_out, ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    stats_.kernel_launches++;
+    out.assign(m.h_loss, m.h_loss + ld.njobs);
+}
+
+// Roofline probe: `reps` back-to-back dual sweeps (+ finish) for all chain slots; returns mean ms per sweep kernel.
+float Engine::time_dual_sweep(int nch, int reps)
+{
+    Impl &m = *d_;
+    if (!m.chains_ready) throw EngineError{"time_dual_sweep before setup_chains"};
+    (void)nch;
+    const int mode = sweep_mode(family_);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    launch_dual_sweep(m.d, mode, m.st);
+    CUDA_CHECK(cudaEventRecord(e0, m.st));
+    for (int r = 0; r < reps; r++) launch_dual_sweep(m.d, mode, m.st);
+    CUDA_CHECK(cudaEventRecord(e1, m.st));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    stats_.kernel_launches += reps + 1;
+    return ms / (float)reps;
+}
+
+// Recompute the sacrifice of `chain` for its CURRENT beta (test hook for the sweep + finish kernels).
+void Engine::debug_sacrifice(int chain, std::vector<double> &bd_out)
+{
+    Impl &m = *d_;
+    Dev &d = m.d;
+    BatchDesc b{};
+    b.nch = 1;
+    b.chain[0] = chain;
+    const int mode = sweep_mode(family_), epi = sweep_epi(family_);
+    launch_dual_sweep(d, mode, m.st);
+    launch_finish(d, mode, epi, b, nullptr, m.st);
+    bd_out.resize(d.p);
+    CUDA_CHECK(cudaMemcpyAsync(bd_out.data(), d.bd + (size_t)chain * d.pstride, (size_t)d.p * 8, cudaMemcpyDeviceToHost,
+                               m.st));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+}
+
+}  // namespace bess

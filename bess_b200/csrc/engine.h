@@ -1,0 +1,105 @@
+// bess_b200 device engine -- internal C++ interface between the host path driver (path.cpp)
+// and the CUDA kernels (kernels.cu / engine.cu).  Not installed; the public boundary is
+// include/bess_b200.h.
+//
+// Vocabulary (follows the reference, /root/reference/src):
+//   chain   one warm-start lineage: chain 0 = the full-data fit of sequential_path/gs_path
+//           (path.cpp:48-74), chain 1+k = CV fold k (Metric.h:163-191).  A chain owns its train-row
+//           list, its current support A / beta_A / coef0 and its gathered active columns X_A.
+//   batch   all chains that run one sparsity level T concurrently (Algorithm::fit, Algorithm.h:113-171,
+//           advanced in lock-step: one dual sweep over X serves every chain of the batch).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace bess {
+
+constexpr int MAXC = 16;      // max chains = 1 + K folds
+constexpr int MAX_HIST = 66;  // max_iter + 2 columns of A_list (Algorithm.h:142)
+
+enum Family { FAM_LM = 1, FAM_LOGIT = 2, FAM_POISSON = 3, FAM_COX = 4 };
+
+struct BatchResult {
+    int T = 0;
+    int nchains = 0;
+    int chain_ids[MAXC];
+    int l[MAXC];                 // PDAS iterations used (Algorithm::l)
+    double coef0[MAXC];
+    std::vector<int> A[MAXC];     // support, ascending
+    std::vector<double> bA[MAXC]; // coefficients on the support (normalised scale)
+};
+
+struct LossJob {
+    int chain;   // whose beta/coef0
+    int kind;    // 0 = train_loss formula on ALL rows (Metric::train_loss); 1 = fold test loss on fold `fold`
+    int fold;    // for kind 1
+};
+
+struct EngineStats {
+    long long n_fits = 0, n_pdas_iters = 0, n_sweeps = 0, n_batches = 0, n_boundary_ties = 0;
+    double sweep_bytes = 0.0;     // algorithmic bytes swept (8*n*p per sweep launch + vectors)
+    long long kernel_launches = 0;
+};
+
+class Engine {
+public:
+    explicit Engine(int device = -1);
+    ~Engine();
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+
+    // ---- design upload.  x: row-major n x p (pywrap_bess layout, utilities.cpp:13-25).
+    // x_on_device: x already lives in device memory (bench "resident" mode); it is still copied
+    // into engine-owned storage because normalisation is in place.
+    void load(const double *x, int n, int p, bool x_on_device, const double *y, const double *weight, int family);
+
+    // ---- screening.cpp:26-105: marginal utilities on RAW x, top `size`, X <- X[:, A].  Returns A ascending.
+    std::vector<int> screen(int size, const std::vector<int> &always_select);
+
+    // ---- Data ctor normalisation (Data.h:41-68, normalize.cpp) + add_weight for gaussian (Data.h:70-77).
+    void normalize(int data_type, bool is_normal);
+
+    // ---- CV folds (Metric.h:49-129).  fold_of_row[i] in [0,K) or K == 0 for no CV.  Also (re)allocates all
+    // chain workspaces for supports up to kcap.
+    void setup_chains(int K, const int *fold_of_row, int kcap, int max_iter, bool warm_start,
+                      const std::vector<int> &always_select);
+
+    // ---- one sparsity level for a set of chains (ascending chain ids).  with_full: the batch starts a new
+    // path step (update_coef0_init, path.cpp:57) -- chain 0 must then be in the set.
+    void run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out);
+
+    // ---- Metric::train_loss / fold test losses for the chains' current beta.
+    void losses(const std::vector<LossJob> &jobs, std::vector<double> &out);
+
+    // ---- primitives exposed for tests / roofline benchmarking through the C-ABI
+    // Dual sweep + sacrifice for `nch` chains (chain slots f0..f0+nch) -> bd on device; returns kernel ms if timed.
+    float time_dual_sweep(int nch, int reps);
+    void debug_sacrifice(int chain, std::vector<double> &bd_out);   // after run_batch: recompute bd for chain's current beta
+
+    int n() const { return n_; }
+    int p() const { return p_; }
+    int family() const { return family_; }
+    const std::vector<double> &x_mean() const { return h_xmean_; }
+    const std::vector<double> &x_norm() const { return h_xnorm_; }
+    double y_mean() const { return y_mean_; }
+    EngineStats &stats() { return stats_; }
+    int sweep_splits() const { return S_; }
+
+    struct Impl;
+private:
+    Impl *d_ = nullptr;
+    int n_ = 0, p_ = 0, family_ = 0;
+    int S_ = 1;
+    std::vector<double> h_xmean_, h_xnorm_;
+    double y_mean_ = 0.0;
+    EngineStats stats_;
+};
+
+// thrown by the engine on CUDA errors / misuse; the C-ABI turns it into an error code + message
+struct EngineError {
+    std::string msg;
+};
+
+}  // namespace bess

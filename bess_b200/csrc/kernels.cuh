@@ -1,0 +1,98 @@
+// Kernel-side declarations shared by kernels.cu (device code + launchers) and engine.cu (orchestration).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "engine.h"
+
+namespace bess {
+
+constexpr int NVEC = 8;          // per-chain scratch vectors of length n
+constexpr int SWEEP_NT = 128;    // threads per dual-sweep CTA
+constexpr int SWEEP_RC = 64;     // rows per TMA-staged chunk of the gradient vectors
+constexpr int FIT_NT = 512;      // threads per chain_fit CTA (one CTA per chain)
+constexpr int TOPK_NT = 1024;
+constexpr int TOPK_LMAX = 16384; // keys per top-k slice held in shared memory (128 KB)
+
+// sweep modes
+enum { MODE_D = 0, MODE_DH = 1, MODE_COX = 2 };
+// finish epilogues
+enum { EPI_RAW = 0, EPI_SACR_LM = 1, EPI_SACR_GLM = 2, EPI_SACR_COX = 3, EPI_SCREEN_LM = 4 };
+
+// Everything the kernels need, passed by value.
+struct Dev {
+    // design (row-major n x ldx, ldx even, zero padded)
+    double *X;
+    long long ldx;
+    int n, p;
+    int family;
+    int FS;      // chain-slot stride of the sweep vectors (compile-time FT of the sweep kernel)
+    int kcap;    // max support size
+    int ldA;     // leading dim of gathered active columns: kcap + 2 rounded to even
+    int max_iter;
+    int warm;
+    // per-chain tables (index with chain id c)
+    int *rows;          // [MAXC][n] train rows (ascending) of the chain's mask
+    int *ntrain;        // [MAXC]
+    double *ytr, *wtr;  // [MAXC][n] compacted response / weights
+    int *ks;            // [MAXC] current support size
+    int *A;             // [MAXC][kcap] current support
+    double *bA;         // [MAXC][kcap] coefficients on the support
+    double *coef0;      // [MAXC]
+    double *coef0_level;// [1]  Algorithm::coef0_init of the current path step (path.cpp:57)
+    int *Anew;          // [MAXC][kcap] output of top-k
+    int *hist;          // [MAXC][MAX_HIST][kcap]  A_list (Algorithm.h:141-143)
+    int *l;             // [MAXC]
+    int *done;          // [MAXC]
+    int *tie;           // [MAXC] boundary-tie counter of the last top-k
+    double *betaD;      // [MAXC][p] dense beta (for the sacrifice)
+    double *XA;         // [MAXC][n][ldA] gathered active columns (+ intercept / working response columns)
+    double *XB;         // [MAXC][n][ldA] cox: risk-set means
+    double *vec;        // [MAXC][NVEC][n]
+    double *Smat;       // [MAXC][ldA*ldA] Gram / Cholesky workspace (when it does not fit in smem)
+    double *xtx;        // [MAXC][p] x_j.x_j over the chain's train rows (gaussian only)
+    // sweep vectors [n][FS]
+    double *G, *W, *TH, *C2;
+    // sweep outputs
+    double *part;       // [S][NQ][FS][pstride]
+    double *c2sum;      // [S][FS]
+    double *bd;         // [FS][pstride]
+    long long pstride;
+    int S;              // row splits
+    int rows_per_split; // multiple of 2
+};
+
+struct BatchDesc {
+    int nch;
+    int chain[MAXC];
+    int T;
+    int new_path_step;
+};
+
+struct LossDesc {
+    int njobs;
+    int chain[2 * MAXC];
+    int kind[2 * MAXC];
+    int fold[2 * MAXC];
+};
+
+// ---- launchers (kernels.cu) ----
+void launch_dual_sweep(const Dev &d, int mode, cudaStream_t st);
+void launch_finish(const Dev &d, int mode, int epi, const BatchDesc &b, double *raw_out, cudaStream_t st);
+void launch_pin(const Dev &d, double *vals, long long stride, int nch, const int *idx, int nidx, cudaStream_t st);
+// exact top-k of `vals` ([nch][stride], first n_in of each row) -> out_idx [nch][out_ld] ascending; uses ping-pong scratch
+void launch_topk(const double *vals, long long stride, int n_in, int k, int nch, int *out_idx, int out_ld, int *tie,
+                 double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st);
+void launch_chain_begin(const Dev &d, const BatchDesc &b, cudaStream_t st);
+void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st);
+void launch_losses(const Dev &d, const LossDesc &jobs, const int *testrows, const int *ntest, const double *y,
+                   const double *w, const double *lfact, double *scratch, double *out, cudaStream_t st);
+void launch_center_scale(double *X, long long ldx, int n, int p, const double *sub, const double *mul,
+                         const double *rowmul, cudaStream_t st);
+void launch_gather_cols(const double *X, long long ldx, int n, const int *cols, int pnew, double *Xn, long long ldn,
+                        cudaStream_t st);
+void launch_screen_glm(const double *X, long long ldx, int n, int p, const double *y, const double *w, int family,
+                       double *util, cudaStream_t st);
+size_t fit_smem_bytes(const Dev &d);
+void configure_kernels();
+
+}  // namespace bess

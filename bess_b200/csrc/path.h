@@ -1,0 +1,65 @@
+// Host-side driver of the BeSS PDAS path: the B200-native counterpart of bessCpp
+// (/root/reference/src/bess.cpp:37-214), sequential_path (/root/reference/src/path.cpp:25-132),
+// gs_path (path.cpp:134-389) and the Metric family (/root/reference/src/Metric.h).
+// Control flow (which sparsity level next, argmin of the criterion) stays on the host; every fit,
+// sweep, selection and loss runs on the device through bess::Engine.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace bess {
+
+struct BessArgs {
+    // --- the 30 bessCpp arguments (bess.h:20-33); x is row-major n x p as in pywrap_bess
+    const double *x = nullptr;
+    int n = 0, p = 0;
+    const double *y = nullptr;
+    int data_type = 1;
+    const double *weight = nullptr;
+    bool is_normal = true;
+    int algorithm_type = 1, model_type = 1, max_iter = 20, exchange_num = 2;
+    int path_type = 1;
+    bool is_warm_start = true;
+    int ic_type = 1;
+    bool is_cv = false;
+    int K = 5;
+    std::vector<double> state;        // accepted and ignored
+    std::vector<int> sequence;
+    std::vector<double> lambda_seq;
+    int s_min = 1, s_max = 1, K_max = 10;
+    double epsilon = 10.0, lambda_min = 0.0, lambda_max = 0.0;
+    int nlambda = 1;
+    bool is_screening = false;
+    int screening_size = 1, powell_path = 1;
+    std::vector<int> g_index;
+    std::vector<int> always_select;
+    double tao = 1.1;
+    // --- extensions (not in the reference)
+    const int *fold_of_row = nullptr;  // explicit CV folds (length n); else drawn like Metric.h:49-106 from cv_seed
+    unsigned cv_seed = 123;
+    bool x_on_device = false;          // x is a device pointer (bench "resident" mode)
+    int device = -1;
+};
+
+struct BessResult {
+    std::vector<double> beta;  // length p (original, un-screened), de-normalised
+    double coef0 = 0.0, train_loss = 0.0, ic = 0.0, lambda = 0.0;
+    std::vector<int> screening_A;
+    int chosen_s = 0;
+    // per-level trace (sequential path; normalised scale like beta_all before de-normalisation is NOT kept:
+    // these are de-normalised, as the R build returns them, path.cpp:76-123)
+    std::vector<std::vector<double>> beta_all;
+    std::vector<double> coef0_all, train_loss_all, ic_all;
+    std::vector<int> s_all, l_all;
+    EngineStats stats;
+};
+
+// Metric.h:49-106 with the seed pinned (same std::mt19937 + std::shuffle + chunking)
+std::vector<int> cv_fold_ids(int n, int K, unsigned seed);
+
+// throws EngineError
+void bess_run(const BessArgs &a, BessResult &out);
+
+}  // namespace bess

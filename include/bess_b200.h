@@ -1,0 +1,133 @@
+/* bess_b200 -- C ABI of the B200-native BeSS primal-dual active-set (PDAS) hot path.
+ *
+ * One shared library (bess_b200/libbess_b200.so) exports two layers:
+ *
+ *  1. The drop-in boundary: `pywrap_bess`, argument for argument what the reference exports from
+ *     /root/reference/src/bess.h:35-51 (implemented there in bess.cpp:218-281 on top of bessCpp, bess.cpp:37-214).
+ *     It is exported twice: with C linkage (this header) and with the reference's own C++ linkage
+ *     (_Z11pywrap_bessPdiiS_iiS_ibiiiiibibiPiiS_iS0_iS_iiiidddibiiS0_idS_iS_iS_iS_iS_S_iS_iS_iS0_iS0_), so that a SWIG
+ *     wrapper generated from the reference's python/src/bess.i links against it unchanged.
+ *     `bess_b200_fit` is the same call with a status code and the extensions a GPU build needs (explicit CV folds,
+ *     device-resident x, per-level trace, counters).
+ *
+ *  2. `bessgpu_*`: the thin device shim the host path driver itself sits on (north_star: "C++ host code calls CUDA
+ *     through a thin C-ABI shim").  One handle = one design matrix resident in HBM + its chain state.  Used directly by
+ *     the parity tests and by bench.py's roofline probe.
+ *
+ * Everything computes on the GPU (sm_100a kernels); there is NO CPU fallback: without a CUDA device every compute entry
+ * point returns a non-zero status and bess_b200_last_error() says why.
+ *
+ * Layout conventions (identical to the reference): x is ROW-major n x p (x[i*p + j], utilities.cpp:13-25), fp64; indices
+ * are 0-based int32; all output buffers are caller-allocated.
+ */
+#ifndef BESS_B200_H
+#define BESS_B200_H
+
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BESS_B200_VERSION 100
+
+/* ---- 1. drop-in boundary ------------------------------------------------------------------------------------- */
+
+/* Replaces /root/reference/src/bess.h:35-51 `pywrap_bess` (bess.cpp:218-281).  Writes beta_out[0..x_col), *coef0_out,
+ * *train_loss_out, *ic_out -- exactly the four outputs the reference writes (bess.cpp:277-280); nullloss/aic/bic/gic/
+ * A_out/l_out are accepted and left untouched, as in the reference.  Arguments the reference ignores on this
+ * path (state, exchange_num, K_max, epsilon, tao) are ignored here too.  On failure the three scalars are
+ * set to NaN and bess_b200_last_error() holds the message (the reference would dereference null).
+ * CV folds are drawn like Metric.h:49-106 from seed $BESS_CV_SEED (default 123) -- the reference seeds from
+ * std::random_device and is not reproducible under CV. */
+void pywrap_bess(double *x, int x_row, int x_col, double *y, int y_len, int data_type, double *weight, int weight_len,
+                 bool is_normal, int algorithm_type, int model_type, int max_iter, int exchange_num, int path_type,
+                 bool is_warm_start, int ic_type, bool is_cv, int K, int *gindex, int gindex_len, double *state,
+                 int state_len, int *sequence, int sequence_len, double *lambda_sequence, int lambda_sequence_len,
+                 int s_min, int s_max, int K_max, double epsilon, double lambda_min, double lambda_max, int n_lambda,
+                 bool is_screening, int screening_size, int powell_path, int *always_select, int always_select_len,
+                 double tao, double *beta_out, int beta_out_len, double *coef0_out, int coef0_out_len,
+                 double *train_loss_out, int train_loss_out_len, double *ic_out, int ic_out_len, double *nullloss_out,
+                 double *aic_out, int aic_out_len, double *bic_out, int bic_out_len, double *gic_out, int gic_out_len,
+                 int *A_out, int A_out_len, int *l_out);
+
+/* Extensions for bess_b200_fit (all optional; zero-initialise the struct for defaults). */
+typedef struct bess_b200_ext {
+    const int *fold_of_row;   /* explicit CV fold of every row (length n, values 0..K-1); NULL = draw from cv_seed   */
+    unsigned cv_seed;         /* used when fold_of_row == NULL; 0 = $BESS_CV_SEED or 123                              */
+    int x_on_device;          /* x is a device pointer (row-major, same layout)                                       */
+    int device;               /* CUDA device ordinal, -1 = current                                                    */
+    int *screening_A_out;     /* [screening_size] kept columns, ascending (List key "screening_A", bess.cpp:199)     */
+    int *chosen_s_out;        /* sparsity level of the returned model                                                 */
+    double *stats_out;        /* [8]: n_fits, n_pdas_iters, n_sweeps, n_batches, n_boundary_ties, sweep_bytes,        */
+                              /*      kernel_launches, trace_len                                                      */
+} bess_b200_ext;
+
+/* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's
+ * R build returns as beta_all/coef0_all/train_loss_all/ic_all, path.cpp:116-123, 376-380) is kept until the next call
+ * on this thread; fetch it with bess_b200_trace. */
+int bess_b200_fit(double *x, int x_row, int x_col, double *y, int y_len, int data_type, double *weight, int weight_len,
+                  bool is_normal, int algorithm_type, int model_type, int max_iter, int exchange_num, int path_type,
+                  bool is_warm_start, int ic_type, bool is_cv, int K, int *gindex, int gindex_len, double *state,
+                  int state_len, int *sequence, int sequence_len, double *lambda_sequence, int lambda_sequence_len,
+                  int s_min, int s_max, int K_max, double epsilon, double lambda_min, double lambda_max, int n_lambda,
+                  bool is_screening, int screening_size, int powell_path, int *always_select, int always_select_len,
+                  double tao, double *beta_out, int beta_out_len, double *coef0_out, double *train_loss_out,
+                  double *ic_out, const bess_b200_ext *ext);
+
+/* Trace of the last bess_b200_fit/pywrap_bess on this thread.  Any pointer may be NULL.  beta_all is [len][p] and only
+ * filled for the sequential path.  Returns the trace length. */
+int bess_b200_trace(int *s_all, int *l_all, double *coef0_all, double *train_loss_all, double *ic_all, double *beta_all,
+                    int p);
+
+/* Metric.h:49-106 with the seed pinned: fold index of every row. */
+int bess_b200_cv_fold_ids(int n, int K, unsigned seed, int *fold_of_row_out);
+
+const char *bess_b200_last_error(void);
+int bess_b200_version(void);
+/* number of CUDA devices visible (0 = no GPU: every compute call will fail) */
+int bess_b200_device_count(void);
+
+/* ---- 2. device shim ------------------------------------------------------------------------------------------ */
+typedef struct bessgpu_handle bessgpu_handle;
+
+int bessgpu_create(bessgpu_handle **h, int device);
+int bessgpu_destroy(bessgpu_handle *h);
+/* upload (or device-to-device copy) the design; replaces the by-value copies of bess.cpp:233/61 and Algorithm.h:58 */
+int bessgpu_load(bessgpu_handle *h, const double *x, int n, int p, int x_on_device, const double *y,
+                 const double *weight, int model_type);
+/* screening.cpp:26-105; out: screening_size kept columns, ascending */
+int bessgpu_screen(bessgpu_handle *h, int screening_size, const int *always_select, int n_always, int *screening_A_out);
+/* Data.h:41-77 + normalize.cpp:20-86 */
+int bessgpu_normalize(bessgpu_handle *h, int data_type, int is_normal);
+int bessgpu_get_norm(bessgpu_handle *h, double *x_mean_out, double *x_norm_out, double *y_mean_out);
+/* Metric.h:49-129 (fold row lists, per-fold x_j.x_j) + workspace for supports up to kcap */
+int bessgpu_setup_chains(bessgpu_handle *h, int K, const int *fold_of_row, int kcap, int max_iter, int warm_start,
+                         const int *always_select, int n_always);
+/* Algorithm::fit (Algorithm.h:113-171) for `nch` chains at sparsity T in lock-step.  Outputs are [nch] / [nch][T]. */
+int bessgpu_run_batch(bessgpu_handle *h, int T, const int *chains, int nch, int new_path_step, int *l_out,
+                      double *coef0_out, int *A_out, double *beta_A_out);
+/* Metric::train_loss (kind 0) / fold test loss (kind 1) of a chain's current model */
+int bessgpu_losses(bessgpu_handle *h, const int *chain, const int *kind, const int *fold, int njobs, double *out);
+/* roofline probe: mean device time (ms) of one dual-sweep launch over all chain slots and its algorithmic bytes */
+int bessgpu_time_dual_sweep(bessgpu_handle *h, int reps, float *ms_out, double *bytes_out);
+int bessgpu_stats(bessgpu_handle *h, double *out8);
+/* stand-alone exact top-k (utilities.cpp:179-188 max_k): host vals[n] -> ascending indices; tie_out = 1 when keys equal to
+ * the k-th straddle the boundary */
+int bessgpu_topk(const double *vals, int n, int k, int *idx_out, int *tie_out);
+
+/* ---- 3. multi-GPU host helpers (pure host code, no CUDA) ------------------------------------------------------ */
+/* contiguous column shard [lo, hi) of rank r out of `world` (SURVEY 8e axis B) */
+void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi);
+/* chain -> rank assignment for fold sharding (SURVEY 8e axis A): round-robin, chain 0 on rank 0 */
+int bess_b200_chain_owner(int chain, int world);
+/* merge per-rank local top-k candidate lists (value, global index) into the global top-k, ascending indices.
+ * Total order: larger value first, lower index first.  vals/idx: [count]. */
+int bess_b200_merge_candidates(const double *vals, const int *idx, int count, int k, int *idx_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BESS_B200_H */
