@@ -323,6 +323,11 @@ int bessgpu_topk(const double *vals, int n, int k, int *idx_out, int *tie_out)
     });
 }
 
+int bess_b200_debug_set(int key, int val)
+{
+    return guarded([&] { debug_set(key, val); });
+}
+
 // ---- multi-GPU host helpers ------------------------------------------------------------------------------------------
 void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi)
 {

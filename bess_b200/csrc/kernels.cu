@@ -60,6 +60,8 @@ __device__ __forceinline__ double block_sum(double v, double *sh)
 }
 
 // block exclusive scan of one value per thread (thread order); returns exclusive prefix, *total = block total.
+// The exclusive value is obtained by SHIFTING the inclusive scan, never by subtracting the thread's own value:
+// "inclusive - own" cancels catastrophically when one term dwarfs the prefix (Cox risk sets span e^+-30).
 template <int NT>
 __device__ __forceinline__ double block_excl_scan(double v, double *sh, double *total)
 {
@@ -70,6 +72,8 @@ __device__ __forceinline__ double block_excl_scan(double v, double *sh, double *
         double t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
+    double excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) excl = 0.0;
     __syncthreads();
     if (lane == 31) sh[wid] = inc;
     __syncthreads();
@@ -81,12 +85,14 @@ __device__ __forceinline__ double block_excl_scan(double v, double *sh, double *
             double t = __shfl_up_sync(0xffffffffu, winc, o);
             if (lane >= o) winc += t;
         }
-        if (lane < NT / 32) sh[lane] = winc - w;  // exclusive warp offsets
+        double wex = __shfl_up_sync(0xffffffffu, winc, 1);
+        if (lane == 0) wex = 0.0;
+        if (lane < NT / 32) sh[lane] = wex;  // exclusive warp offsets
         if (lane == 31) sh[32] = winc;
     }
     __syncthreads();
     *total = sh[32];
-    return sh[wid] + (inc - v);
+    return sh[wid] + excl;
 }
 
 // In-place inclusive scans over v[0..nr): each thread owns a contiguous chunk.
@@ -983,15 +989,17 @@ __device__ void cox_riskset_means(const ChainCtx &cx, int ldA, double *XB, const
     }
     __syncthreads();
 }
+__device__ int g_dbg_cox_iters = 30;  // debug knob (bess_b200_debug_set key 1); 30 = reference behaviour
 __device__ void fit_cox(const ChainCtx &cx, int ldA, double *XB, double *S2, int lds2, const FitSmem &sm)
 {
+    const int max_newton = g_dbg_cox_iters;
     const int m = cx.m, nt = cx.nt;
     double *b0 = sm.b0, *b1 = sm.b1;
     double *th = cx.v[0], *s0 = cx.v[1], *ev = cx.v[2], *om = cx.v[3], *gv = cx.v[4];
     for (int a = threadIdx.x; a < m; a += FIT_NT) b0[a] = 0.0;
     __syncthreads();
     double ll0 = 1e5;
-    for (int l = 1; l <= 30; l++) {
+    for (int l = 1; l <= max_newton; l++) {
         // theta (no weights here, Algorithm.h:1423), S0
         for (int r = threadIdx.x; r < nt; r += FIT_NT) {
             const double t = exp(clampd(row_dot(cx.XA + (size_t)r * ldA, b0, m), 30.0));
@@ -1263,6 +1271,11 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     }
     if (finished) return;
     chain_gradient(d, cx, slopes, T, coef0, sm);
+}
+
+void debug_set(int key, int val)
+{
+    if (key == 1) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_cox_iters, &val, sizeof(int)));
 }
 
 void configure_kernels()

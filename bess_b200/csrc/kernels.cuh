@@ -94,5 +94,6 @@ void launch_screen_glm(const double *X, long long ldx, int n, int p, const doubl
                        double *util, cudaStream_t st);
 size_t fit_smem_bytes(const Dev &d);
 void configure_kernels();
+void debug_set(int key, int val);
 
 }  // namespace bess
