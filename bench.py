@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE config 5 (the configuration the metric is quoted on):
+
+    full PDAS s-path + 10-fold CV fits/sec  (and the dual-sweep HBM GB/s against the roofline)
+
+Workload ("C5"): gaussian gen.data-shaped design n=1000, p=500000, true s=10, screening.num=5000, 10-fold CV,
+sequential s.list=1..20  => one step = one full bessCpp call = 220 PDAS fits (20 levels x (1 full fit + 10 folds)).
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm, one GPU
+  torchrun ... bench.py --gpus N ...                        our arm, columns of X sharded over N ranks (NCCL)
+  python bench.py --impl reference ...                      the reference's own CPU code (oracle/_ref) on host cores
+
+`value`  : whole-job fits/s with X already resident in HBM when the timed region starts.
+`e2e`    : same metric through the reference-facing C-ABI call with X in pinned HOST memory (H2D inside the region).
+Timing: CUDA events on the current stream around K steps, synchronize + barrier on both sides, max over ranks.
+L2: the design is 4 GB (>> 126 MB L2), every step streams it from HBM again; no explicit flush needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, P_COLS, K_TRUE, SCREEN, NFOLDS, SMAX = 1000, 500000, 10, 5000, 10, 20
+WORKLOAD = ("C5: gaussian gen.data n=1000 p=500000 true-s=10, screening.num=5000, 10-fold CV, sequential s.list=1..20 "
+            "(220 PDAS fits per call)")
+# CPU sample: a proportional slice of C5 (same n, folds, screening.num => same per-fit cost; 15% of the columns and the
+# first 3 of 20 levels => same screening-to-fit ratio as the full call)
+CPU_P, CPU_SMAX = 75000, 3
+
+
+def make_c5_on_device(torch, device, p=P_COLS, seed=5):
+    gen = torch.Generator(device=device).manual_seed(seed)
+    X = torch.randn(N_ROWS, p, dtype=torch.float64, device=device, generator=gen)
+    rng = np.random.default_rng(seed)
+    nz = np.sort(rng.choice(p, K_TRUE, replace=False))
+    m = 5 * np.sqrt(2 * np.log(p) / N_ROWS)
+    beta = rng.uniform(m, 100 * m, K_TRUE)
+    sigma = np.sqrt((beta @ beta) / 10.0)
+    y = (X[:, torch.as_tensor(nz, device=device)] @ torch.as_tensor(beta, device=device)).cpu().numpy()
+    y = y + rng.normal(0.0, sigma, N_ROWS)
+    return X, y, nz
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline():
+    """The reference's own C++ (oracle/_ref, single thread as shipped) on a bounded slice of the workload."""
+    from bess_b200.gen_data import gen_data
+    from oracle import ref
+    if not ref.available():
+        return None
+    d = gen_data(N_ROWS, CPU_P, "gaussian", K_TRUE, seed=5)
+    w = np.ones(N_ROWS)
+    seq = np.arange(1, CPU_SMAX + 1)
+    t0 = time.perf_counter()
+    ref.pywrap_bess(d.x, d.y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, CPU_SMAX, True, SCREEN, cv_seed=123)
+    dt = time.perf_counter() - t0
+    fits = CPU_SMAX * (1 + NFOLDS)
+    return {"value": fits / dt, "unit": "fits/s", "cores": 1, "kind": "reference", "seconds": dt,
+            "sample": f"oracle/_ref (reference src/*.cpp, -O2, 1 thread) on a 15% slice of C5: n=1000, p={CPU_P}, "
+                      f"screening.num=5000, 10-fold CV, s.list=1..{CPU_SMAX} ({fits} fits)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbess_ref.so was not built"}))
+        return
+    times = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_baseline()
+        if i >= args.warmup:
+            times.append(base["seconds"])
+    dt = float(np.mean(times))
+    fits = CPU_SMAX * (1 + NFOLDS)
+    val = fits / dt
+    base["value"] = val
+    print(json.dumps({"impl": "reference", "metric": "pdas_path_cv_fits_per_sec", "value": val, "unit": "fits/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": base["sample"]},
+                      "cpu_baseline": base,
+                      "e2e": {"value": val, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bess_b200 import _lib, cbess
+    from bess_b200 import dist as bdist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    _lib.require_gpu()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = f"cuda:{local_rank}"
+    X, y, nz = make_c5_on_device(torch, dev)
+    w = np.ones(N_ROWS)
+    seq = np.arange(1, SMAX + 1)
+    lo, hi = (0, P_COLS) if world == 1 else bdist.shard_range(P_COLS, world, rank)
+    Xs = X if world == 1 else X[:, lo:hi].contiguous()
+    del X
+    torch.cuda.empty_cache()
+
+    def step(host_x=None, profile=False):
+        if world == 1:
+            if host_x is None:
+                return cbess.fit(None, y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, SMAX, True, SCREEN,
+                                 cv_seed=123, device=local_rank, x_device_ptr=Xs.data_ptr(), n=N_ROWS, p=P_COLS,
+                                 want_trace=False, profile=profile)
+            return cbess.fit(host_x, y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, SMAX, True, SCREEN,
+                             cv_seed=123, device=local_rank, want_trace=False, profile=profile)
+        if host_x is None:
+            return bdist.fit_column_sharded(None, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
+                                            SCREEN, cv_seed=123, device=local_rank, x_shard_device_ptr=Xs.data_ptr(),
+                                            n=N_ROWS, p_local=hi - lo, profile=profile)
+        return bdist.fit_column_sharded(host_x, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
+                                        SCREEN, cv_seed=123, device=local_rank, profile=profile)
+
+    def timed(nsteps, host_x=None):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(nsteps):
+            out = step(host_x)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), out
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, out = timed(args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    fits_per_step = 220
+    value = fits_per_step * args.steps / (ms / 1e3)
+
+    # ---- e2e: X in pinned host memory, H2D inside the timed region, results (beta, coef0, losses) read back
+    Xh = torch.empty(Xs.shape, dtype=torch.float64, pin_memory=True)
+    Xh.copy_(Xs)
+    xh = Xh.numpy()
+    step(xh)
+    e2e_steps = max(1, min(args.steps, 5))
+    ms_e2e, out_e = timed(e2e_steps, xh)
+    e2e_val = fits_per_step * e2e_steps / (ms_e2e / 1e3)
+    st = out["stats"]
+    d2h = st["n_batches"] * (16 * SMAX * 12 + 16 * 12) + st["n_sweeps"] * 16 * 8 + SCREEN * 4 + P_COLS * 0
+    h2d = int(Xs.numel() * 8 + 2 * N_ROWS * 8)
+
+    # ---- roofline of the dual-sweep kernel: CUDA events around every launch on the engine's own stream, over a
+    # profiled repeat of the timed region (event recording costs ~1 ms per call, so it is kept out of `value`)
+    prof_ms = np.zeros(6)
+    prof_n = np.zeros(6)
+    big_bytes = pdas_bytes = 0.0
+    for _ in range(args.steps):
+        o = step(profile=True)
+        prof_ms += np.array(list(o["stats"]["prof_ms"].values()))
+        prof_n += np.array(list(o["stats"]["prof_launches"].values()))
+        big_bytes += o["stats"]["big_sweep_bytes"]
+        pdas_bytes += o["stats"]["sweep_bytes"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    sweep_ms = prof_ms[0] + prof_ms[1]
+    sweep_n = max(prof_n[0] + prof_n[1], 1)
+    achieved = (big_bytes + pdas_bytes) / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
+    hbm_ms = prof_ms[0]
+    hbm_gbs = big_bytes / (hbm_ms * 1e-3) / 1e9 if hbm_ms > 0 else None
+    total_kernel_ms = float(prof_ms.sum())
+
+    # ---- the p=500k PDAS dual sweep itself (config 5 with screening off, "C5b"): all 11 chains in one pass over X
+    probe = None
+    if world == 1:
+        from bess_b200.engine import GpuEngine
+        eng = GpuEngine(local_rank)
+        eng.load(None, y, w, 1, x_device_ptr=Xs.data_ptr(), n=N_ROWS, p=P_COLS)
+        eng.normalize(1, True)
+        eng.setup_chains(NFOLDS, cbess.cv_fold_ids(N_ROWS, NFOLDS, 123), SMAX, 20, True)
+        eng.run_batch(5, list(range(NFOLDS + 1)), True)
+        pms, pbytes = eng.time_dual_sweep(20)
+        eng.close()
+        probe = {"what": "dual_sweep_kernel<FT=12,MODE_D>: X^T r for 11 chains (full fit + 10 folds) in ONE pass over the "
+                         "normalised 1000 x 500000 design (config 5 without screening)",
+                 "ms_per_launch": pms, "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                 "frac": pbytes / (pms * 1e-3) / 1e9 / peak, "algorithmic_bytes": pbytes}
+
+    base = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if rank == 0:
+        line = {
+            "metric": "pdas_path_cv_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": "single GPU" if world == 1 else
+                       f"columns of X sharded over {world} ranks for the screening sweep (local top-k + NCCL all-gather "
+                       f"of candidates + all-reduce of the kept columns); PDAS path on the 1000 x 5000 screened design "
+                       f"replicated",
+                       "l2_policy": "inputs larger than L2 (4 GB design streamed from HBM every step)",
+                       "cv_seed": 123, "chosen_s": int(out["s"]), "support_recovered": int(np.isin(nz, np.nonzero(out["beta"])[0]).sum())},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": int(st["kernel_launches"] * args.steps),
+            "roofline": {"bound": "hbm", "achieved": hbm_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": (hbm_gbs / peak) if hbm_gbs else None, "traffic": None,
+                         "kernel": "dual_sweep_kernel (HBM-streaming launches of the step: screening pass over the "
+                                   "4 GB design + normalisation/x_j.x_j passes)",
+                         "peak_source": peak_src, "launches_per_step": float(prof_n[0] / args.steps),
+                         "ms_per_step": float(hbm_ms / args.steps),
+                         "all_dual_sweep_launches": {"achieved": achieved, "launches_per_step": float(sweep_n / args.steps),
+                                                     "note": "incl. the ~50 L2-resident 40 MB PDAS sweeps per call"},
+                         "kernel_ms_per_step": {k: float(v / args.steps) for k, v in zip(cbess.PROF_CATS, prof_ms)},
+                         "kernel_share_of_step": float(total_kernel_ms / args.steps / (ms / args.steps)),
+                         "p500k_pdas_sweep": probe},
+            "cpu_baseline": base,
+            "fits_per_step": fits_per_step, "n_boundary_ties": int(st["n_boundary_ties"]),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,7 +22,7 @@ class BessB200Error(RuntimeError):
 class Ext(C.Structure):
     """struct bess_b200_ext (include/bess_b200.h)"""
     _fields_ = [("fold_of_row", ip), ("cv_seed", C.c_uint), ("x_on_device", C.c_int), ("device", C.c_int),
-                ("screening_A_out", ip), ("chosen_s_out", ip), ("stats_out", dp)]
+                ("screening_A_out", ip), ("chosen_s_out", ip), ("stats_out", dp), ("profile", C.c_int)]
 
 
 _PYWRAP_ARGS = [dp, C.c_int, C.c_int, dp, C.c_int, C.c_int, dp, C.c_int, C.c_bool, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -53,6 +53,8 @@ def load():
     lib.bessgpu_destroy.argtypes = [C.c_void_p]
     lib.bessgpu_load.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int]
     lib.bessgpu_screen.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, ip]
+    lib.bessgpu_screen_local.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, dp, ip, ip]
+    lib.bessgpu_gather_columns.argtypes = [C.c_void_p, ip, ip, C.c_int, C.c_void_p, C.c_longlong]
     lib.bessgpu_normalize.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bessgpu_get_norm.argtypes = [C.c_void_p, dp, dp, dp]
     lib.bessgpu_setup_chains.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, C.c_int, C.c_int, ip, C.c_int]

@@ -12,6 +12,9 @@ from . import _lib
 from ._lib import BessB200Error, Ext, dp, ip
 
 
+PROF_CATS = ("setup_passes", "dual_sweep", "finish", "topk", "chain", "other")
+
+
 def _d(a):
     return a.ctypes.data_as(dp)
 
@@ -66,7 +69,7 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
 
 def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
-        fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True):
+        fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
     ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``."""
     lib = _lib.load()
@@ -96,8 +99,9 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     ext.screening_A_out = _i(scrA)
     chosen = C.c_int(0)
     ext.chosen_s_out = C.pointer(chosen)
-    stats = np.zeros(8)
+    stats = np.zeros(24)
     ext.stats_out = _d(stats)
+    ext.profile = 1 if profile else 0
     rc = lib.bess_b200_fit(xptr, n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal),
                            int(algorithm_type), int(model_type), int(max_iter), int(exchange_num), int(path_type),
                            bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g), g.size, _d(st), 1, _i(seq),
@@ -108,7 +112,10 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     out = dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, s=chosen.value,
                stats=dict(n_fits=int(stats[0]), n_pdas_iters=int(stats[1]), n_sweeps=int(stats[2]),
                           n_batches=int(stats[3]), n_boundary_ties=int(stats[4]), sweep_bytes=float(stats[5]),
-                          kernel_launches=int(stats[6])))
+                          kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[20]),
+                          sweep_splits=int(stats[21]),
+                          prof_ms=dict(zip(PROF_CATS, stats[8:14].tolist())),
+                          prof_launches=dict(zip(PROF_CATS, [int(v) for v in stats[14:20]]))))
     if is_screening:
         out["screening_A"] = scrA[:int(screening_size)].copy()
     L = int(stats[7])

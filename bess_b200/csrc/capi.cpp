@@ -82,6 +82,7 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
             if (ext->cv_seed) a.cv_seed = ext->cv_seed;
             a.x_on_device = ext->x_on_device != 0;
             a.device = ext->device;
+            a.profile = ext->profile != 0;
         }
         BessResult r;
         bess_run(a, r);
@@ -102,6 +103,12 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
                 ext->stats_out[5] = r.stats.sweep_bytes;
                 ext->stats_out[6] = (double)r.stats.kernel_launches;
                 ext->stats_out[7] = (double)r.s_all.size();
+                for (int q = 0; q < 6; q++) {
+                    ext->stats_out[8 + q] = r.prof_ms[q];
+                    ext->stats_out[14 + q] = (double)r.prof_n[q];
+                }
+                ext->stats_out[20] = r.stats.big_sweep_bytes;
+                ext->stats_out[21] = (double)r.sweep_splits;
             }
         }
         g_last = std::move(r);
@@ -240,6 +247,23 @@ int bessgpu_screen(bessgpu_handle *h, int size, const int *always, int n_always,
         std::vector<int> r = h->eng->screen(size, al);
         std::copy(r.begin(), r.end(), out);
     });
+}
+int bessgpu_screen_local(bessgpu_handle *h, int size, const int *always, int n_always, double *vals_out, int *idx_out,
+                         int *count_out)
+{
+    return guarded([&] {
+        std::vector<int> al(always, always + (always ? n_always : 0));
+        std::vector<double> v;
+        std::vector<int> ix;
+        h->eng->screen_local(size, al, v, ix);
+        std::copy(v.begin(), v.end(), vals_out);
+        std::copy(ix.begin(), ix.end(), idx_out);
+        *count_out = (int)ix.size();
+    });
+}
+int bessgpu_gather_columns(bessgpu_handle *h, const int *cols, const int *pos, int m, double *dst_dev, long long ld)
+{
+    return guarded([&] { h->eng->gather_columns(cols, pos, m, dst_dev, ld); });
 }
 int bessgpu_normalize(bessgpu_handle *h, int data_type, int is_normal)
 {

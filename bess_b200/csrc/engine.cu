@@ -17,6 +17,7 @@ namespace bess {
         }                                                                           \
     } while (0)
 
+constexpr int PROF_NCAT = 6;  // 0 sweep(big: screening/normalise), 1 sweep(PDAS), 2 finish, 3 topk, 4 chain kernels, 5 other
 namespace {
 template <class T>
 T *dalloc(size_t count)
@@ -67,6 +68,47 @@ struct Engine::Impl {
     int *h_done = nullptr, *h_l = nullptr, *h_ks = nullptr, *h_A = nullptr, *h_tie = nullptr;
     double *h_coef0 = nullptr, *h_bA = nullptr, *h_loss = nullptr;
     bool chains_ready = false;
+    bool x_owned = true;
+    // ---- per-category device timing (CUDA events on the engine stream), enabled by Engine::set_profiling
+    bool prof = false;
+    struct Span { cudaEvent_t a, b; int cat; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    double cat_ms[PROF_NCAT] = {0, 0, 0, 0, 0, 0};
+    long long cat_n[PROF_NCAT] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t get_event()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreate(&e));
+        return e;
+    }
+    int span_begin(int cat)
+    {
+        if (!prof) return -1;
+        Span sp{get_event(), get_event(), cat};
+        CUDA_CHECK(cudaEventRecord(sp.a, st));
+        spans.push_back(sp);
+        return (int)spans.size() - 1;
+    }
+    void span_end(int id)
+    {
+        if (id >= 0) CUDA_CHECK(cudaEventRecord(spans[id].b, st));
+    }
+    // call only after a stream synchronize
+    void collect_spans()
+    {
+        for (Span &sp : spans) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+                cat_ms[sp.cat] += ms;
+                cat_n[sp.cat]++;
+            }
+            pool.push_back(sp.a);
+            pool.push_back(sp.b);
+        }
+        spans.clear();
+    }
 
     void free_sweep_buffers()
     {
@@ -139,9 +181,12 @@ Engine::~Engine()
 {
     if (!d_) return;
     cudaStreamSynchronize(d_->st);
+    d_->collect_spans();
+    for (cudaEvent_t e : d_->pool) cudaEventDestroy(e);
     d_->free_chain_buffers();
     d_->free_sweep_buffers();
-    dfree(d_->X); dfree(d_->y); dfree(d_->w);
+    if (d_->x_owned) dfree(d_->X);
+    dfree(d_->y); dfree(d_->w);
     cudaFreeHost(d_->h_done); cudaFreeHost(d_->h_l); cudaFreeHost(d_->h_ks); cudaFreeHost(d_->h_tie);
     cudaFreeHost(d_->h_coef0); cudaFreeHost(d_->h_loss);
     if (d_->h_A) cudaFreeHost(d_->h_A);
@@ -150,21 +195,42 @@ Engine::~Engine()
     delete d_;
 }
 
-void Engine::load(const double *x, int n, int p, bool x_on_device, const double *y, const double *weight, int family)
+void Engine::set_profiling(bool on) { d_->prof = on; }
+void Engine::profile(double *ms_out, long long *n_out) const
+{
+    for (int i = 0; i < PROF_NCAT; i++) {
+        ms_out[i] = d_->cat_ms[i];
+        n_out[i] = d_->cat_n[i];
+    }
+}
+
+void Engine::load(const double *x, int n, int p, bool x_on_device, const double *y, const double *weight, int family,
+                  bool borrow)
 {
     Impl &m = *d_;
     if (n < 2 || p < 1) throw EngineError{"load: need n >= 2 and p >= 1"};
     if (family < 1 || family > 4) throw EngineError{"load: model_type must be 1..4"};
     m.free_chain_buffers();
     m.free_sweep_buffers();
-    dfree(m.X); dfree(m.y); dfree(m.w);
+    if (m.x_owned) dfree(m.X);
+    dfree(m.y); dfree(m.w);
     n_ = n; p_ = p; family_ = family;
     m.n = n; m.p = p; m.npad = (n + 1) & ~1;
     m.ldx = (p + 1) & ~1LL;
-    m.X = dalloc<double>((size_t)n * m.ldx);
-    if (m.ldx != p) CUDA_CHECK(cudaMemsetAsync(m.X, 0, (size_t)n * m.ldx * 8, m.st));
-    CUDA_CHECK(cudaMemcpy2DAsync(m.X, (size_t)m.ldx * 8, x, (size_t)p * 8, (size_t)p * 8, n,
-                                 x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m.st));
+    // A device-resident design with an even column count can be used in place while it is only READ (screening
+    // replaces it by the gathered columns); normalize() takes a private copy otherwise.
+    if (borrow && x_on_device && (p % 2 == 0) && ((uintptr_t)x % 16 == 0)) {
+        m.X = const_cast<double *>(x);
+        m.x_owned = false;
+    } else {
+        m.x_owned = true;
+        m.X = dalloc<double>((size_t)n * m.ldx);
+        if (m.ldx != p) CUDA_CHECK(cudaMemsetAsync(m.X, 0, (size_t)n * m.ldx * 8, m.st));
+        const int sp = m.span_begin(5);
+        CUDA_CHECK(cudaMemcpy2DAsync(m.X, (size_t)m.ldx * 8, x, (size_t)p * 8, (size_t)p * 8, n,
+                                     x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m.st));
+        m.span_end(sp);
+    }
     m.hy.assign(y, y + n);
     m.hw.assign(weight, weight + n);
     m.y = dalloc<double>(m.npad);
@@ -181,11 +247,73 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     CUDA_CHECK(cudaStreamSynchronize(m.st));
 }
 
-// screening.cpp:26-105
+// screening.cpp:26-61: marginal utility of every column on RAW x -> m.d.bd (device), always_select pinned.
+// Selects the top `size` (ascending indices) into d_sel; if vals_out != nullptr also returns their utilities.
+static void screen_select(Engine::Impl &m, EngineStats &st, int family, int size, const std::vector<int> &always_select,
+                          int *d_sel, std::vector<double> *vals_out, std::vector<int> *sel_out);
+
 std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
 {
     Impl &m = *d_;
     if (size < 1 || size > m.p) throw EngineError{"screening_size must be in [1, p]"};
+    int *d_sel = dalloc<int>(size);
+    std::vector<int> sel;
+    screen_select(m, stats_, family_, size, always_select, d_sel, nullptr, &sel);
+    // X <- X[:, sel]  (screening.cpp:83-88)
+    const long long ldn = (size + 1) & ~1LL;
+    double *Xn = dalloc<double>((size_t)m.n * ldn);
+    if (ldn != size) CUDA_CHECK(cudaMemsetAsync(Xn, 0, (size_t)m.n * ldn * 8, m.st));
+    const int spk = m.span_begin(5);
+    launch_gather_cols(m.X, m.ldx, m.n, d_sel, size, Xn, ldn, m.st);
+    m.span_end(spk);
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    m.collect_spans();
+    stats_.kernel_launches += 1;
+    if (m.x_owned) dfree(m.X);
+    m.x_owned = true;
+    m.X = Xn;
+    m.ldx = ldn;
+    m.p = size;
+    p_ = size;
+    dfree(d_sel);
+    m.free_sweep_buffers();
+    h_xmean_.assign(size, 0.0);
+    h_xnorm_.assign(size, 0.0);
+    return sel;
+}
+
+// Column-sharded screening (SURVEY 8e axis B): the local top-`size` candidates (utility, local column index) of this
+// rank's columns; X is left untouched.
+void Engine::screen_local(int size, const std::vector<int> &always_select, std::vector<double> &vals,
+                          std::vector<int> &idx)
+{
+    Impl &m = *d_;
+    size = std::min(size, m.p);
+    int *d_sel = dalloc<int>(size);
+    screen_select(m, stats_, family_, size, always_select, d_sel, &vals, &idx);
+    dfree(d_sel);
+    m.free_sweep_buffers();
+}
+
+// dst[i*ld + pos[q]] = X[i][cols[q]] for q < m  (dst is a device buffer shared by all ranks' selections)
+void Engine::gather_columns(const int *cols, const int *pos, int mcols, double *dst_dev, long long ld)
+{
+    Impl &m = *d_;
+    if (mcols <= 0) return;
+    int *d_cols = dalloc<int>(mcols), *d_pos = dalloc<int>(mcols);
+    CUDA_CHECK(cudaMemcpyAsync(d_cols, cols, (size_t)mcols * 4, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(d_pos, pos, (size_t)mcols * 4, cudaMemcpyHostToDevice, m.st));
+    launch_gather_cols_pos(m.X, m.ldx, m.n, d_cols, d_pos, mcols, dst_dev, ld, m.st);
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    stats_.kernel_launches += 1;
+    dfree(d_cols);
+    dfree(d_pos);
+}
+
+static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int size,
+                          const std::vector<int> &always_select, int *d_sel, std::vector<double> *vals_out,
+                          std::vector<int> *sel_out)
+{
     m.config_sweep(1);
     BatchDesc b{};
     b.nch = 1;
@@ -195,13 +323,19 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
         std::vector<double> ones(m.n, 1.0);
         m.put_vec(m.d.G, 0, m.hy);
         m.put_vec(m.d.W, 0, ones);
+        int sp = m.span_begin(0);
         launch_dual_sweep(m.d, MODE_DH, m.st);
+        m.span_end(sp);
+        sp = m.span_begin(2);
         launch_finish(m.d, MODE_DH, EPI_SCREEN_LM, b, nullptr, m.st);
+        m.span_end(sp);
+        stats_.big_sweep_bytes += 8.0 * m.n * m.p;
         stats_.n_sweeps++;
-        stats_.sweep_bytes += 8.0 * m.n * m.p;
         stats_.kernel_launches += 2;
     } else {
+        const int sp = m.span_begin(5);
         launch_screen_glm(m.X, m.ldx, m.n, m.p, m.y, m.w, family_, m.d.bd, m.st);
+        m.span_end(sp);
         stats_.kernel_launches += 1;
     }
     int *d_alw = nullptr;
@@ -210,35 +344,29 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
         CUDA_CHECK(cudaMemcpyAsync(d_alw, always_select.data(), always_select.size() * 4, cudaMemcpyHostToDevice, m.st));
         launch_pin(m.d, m.d.bd, m.d.pstride, 1, d_alw, (int)always_select.size(), m.st);
     }
-    // top-k scratch
     const long long cstride = std::max<long long>(2LL * size + 16, ((long long)m.p / 8192 + 2) * std::min(size, TOPK_LMAX));
     double *ck0 = dalloc<double>(cstride), *ck1 = dalloc<double>(cstride);
     int *ci0 = dalloc<int>(cstride), *ci1 = dalloc<int>(cstride);
-    int *d_sel = dalloc<int>(size);
     int *d_tie = dalloc<int>(1);
+    const int spk = m.span_begin(3);
     launch_topk(m.d.bd, m.d.pstride, m.p, size, 1, d_sel, size, d_tie, ck0, ci0, ck1, ci1, cstride, m.st);
-    std::vector<int> sel(size);
+    m.span_end(spk);
+    sel_out->resize(size);
     int tie = 0;
-    CUDA_CHECK(cudaMemcpyAsync(sel.data(), d_sel, size * 4, cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(sel_out->data(), d_sel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
     CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
-    // X <- X[:, sel]  (screening.cpp:83-88)
-    const long long ldn = (size + 1) & ~1LL;
-    double *Xn = dalloc<double>((size_t)m.n * ldn);
-    if (ldn != size) CUDA_CHECK(cudaMemsetAsync(Xn, 0, (size_t)m.n * ldn * 8, m.st));
-    launch_gather_cols(m.X, m.ldx, m.n, d_sel, size, Xn, ldn, m.st);
     CUDA_CHECK(cudaStreamSynchronize(m.st));
+    if (vals_out) {
+        std::vector<double> all((size_t)m.p);
+        CUDA_CHECK(cudaMemcpyAsync(all.data(), m.d.bd, (size_t)m.p * 8, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        vals_out->resize(size);
+        for (int q = 0; q < size; q++) (*vals_out)[q] = all[(size_t)(*sel_out)[q]];
+    }
+    m.collect_spans();
     stats_.n_boundary_ties += tie;
-    stats_.kernel_launches += 3;
-    dfree(m.X);
-    m.X = Xn;
-    m.ldx = ldn;
-    m.p = size;
-    p_ = size;
-    dfree(ck0); dfree(ck1); dfree(ci0); dfree(ci1); dfree(d_sel); dfree(d_tie); dfree(d_alw);
-    m.free_sweep_buffers();
-    h_xmean_.assign(size, 0.0);
-    h_xnorm_.assign(size, 0.0);
-    return sel;
+    stats_.kernel_launches += 2;
+    dfree(ck0); dfree(ck1); dfree(ci0); dfree(ci1); dfree(d_tie); dfree(d_alw);
 }
 
 // Data ctor (Data.h:41-68) + normalize.cpp + add_weight (Data.h:70-77, bess.cpp:97)
@@ -246,11 +374,18 @@ void Engine::normalize(int data_type, bool is_normal)
 {
     Impl &m = *d_;
     const int n = m.n, p = m.p;
+    if (!m.x_owned) {  // normalisation is in place: take a private copy of a borrowed design
+        double *Xc = dalloc<double>((size_t)n * m.ldx);
+        CUDA_CHECK(cudaMemcpyAsync(Xc, m.X, (size_t)n * m.ldx * 8, cudaMemcpyDeviceToDevice, m.st));
+        m.X = Xc;
+        m.x_owned = true;
+    }
     m.config_sweep(1);
     BatchDesc b{};
     b.nch = 1;
     b.chain[0] = 0;
     double *d_mean = nullptr, *d_mul = nullptr, *d_rowmul = nullptr;
+    const int sp_all = m.span_begin(0);
     if (is_normal) {
         if (data_type == 1 || data_type == 2) {
             // meanx_j = w.x_j / n  (normalize.cpp:25-28, 52-55)
@@ -291,7 +426,6 @@ void Engine::normalize(int data_type, bool is_normal)
         CUDA_CHECK(cudaMemcpyAsync(d_mul, mul.data(), (size_t)p * 8, cudaMemcpyHostToDevice, m.st));
         stats_.kernel_launches += 2;
         stats_.n_sweeps += 2;
-        stats_.sweep_bytes += 16.0 * n * p;
     }
     if (family_ == FAM_LM) {
         // add_weight: rows scaled by sqrt(w) (Data.h:70-77)
@@ -307,8 +441,13 @@ void Engine::normalize(int data_type, bool is_normal)
         launch_center_scale(m.X, m.ldx, n, p, nullptr, d_mul, d_rowmul, m.st);
         stats_.kernel_launches += 1;
     }
+    m.span_end(sp_all);
     CUDA_CHECK(cudaMemcpyAsync(m.y, m.hy.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
     CUDA_CHECK(cudaStreamSynchronize(m.st));
+    m.collect_spans();
+    // passes over X: [mean sweep 8np + centre 16np] (data_type 1,2) + norm sweep 8np + scale 16np
+    if (is_normal) stats_.big_sweep_bytes += (data_type == 3 ? 24.0 : 48.0) * n * p;
+    else if (family_ == FAM_LM) stats_.big_sweep_bytes += 16.0 * n * p;
     dfree(d_mean); dfree(d_mul); dfree(d_rowmul);
     m.free_sweep_buffers();
 }
@@ -403,15 +542,17 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
         BatchDesc b{};
         b.nch = C;
         for (int c = 0; c < C; c++) b.chain[c] = c;
+        const int spx = m.span_begin(0);
         launch_dual_sweep(d, MODE_DH, m.st);
         launch_finish(d, MODE_DH, EPI_RAW, b, m.raw, m.st);
+        m.span_end(spx);
         for (int c = 0; c < C; c++)
             CUDA_CHECK(cudaMemcpyAsync(d.xtx + (size_t)c * d.pstride, m.raw + ((size_t)d.FS + c) * d.pstride,
                                        (size_t)d.pstride * 8, cudaMemcpyDeviceToDevice, m.st));
         CUDA_CHECK(cudaStreamSynchronize(m.st));  // `ind` must outlive the copy
         CUDA_CHECK(cudaMemsetAsync(d.W, 0, ind.size() * 8, m.st));
         stats_.n_sweeps++;
-        stats_.sweep_bytes += 8.0 * n * p;
+        stats_.big_sweep_bytes += 8.0 * n * p;
         stats_.kernel_launches += 2;
     }
     // ---- poisson: sum_{j<=y} log j (poisson.cpp:29-44), same summation order as the reference
@@ -484,16 +625,26 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
     const int mode = sweep_mode(family_), epi = sweep_epi(family_);
     const double vec_bytes = 8.0 * d.n * b.nch * (mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 4)) + 8.0 * d.p * b.nch;
 
+    int sp = m.span_begin(4);
     launch_chain_begin(d, b, m.st);
+    m.span_end(sp);
     stats_.kernel_launches++;
     int iters = 0;
     for (int it = 1; it <= d.max_iter; it++) {
+        sp = m.span_begin(1);
         launch_dual_sweep(d, mode, m.st);
+        m.span_end(sp);
+        sp = m.span_begin(2);
         launch_finish(d, mode, epi, b, nullptr, m.st);
+        m.span_end(sp);
         if (m.n_always) launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
+        sp = m.span_begin(3);
         launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1, d.Anew + (size_t)cmin * d.kcap,
                     d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st);
+        m.span_end(sp);
+        sp = m.span_begin(4);
         launch_chain_fit(d, b, m.st);
+        m.span_end(sp);
         CUDA_CHECK(cudaMemcpyAsync(m.h_done, d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
         CUDA_CHECK(cudaMemcpyAsync(m.h_tie, d.tie, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
         CUDA_CHECK(cudaStreamSynchronize(m.st));
@@ -514,6 +665,7 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
     CUDA_CHECK(cudaMemcpyAsync(m.h_A, d.A, (size_t)MAXC * d.kcap * sizeof(int), cudaMemcpyDeviceToHost, m.st));
     CUDA_CHECK(cudaMemcpyAsync(m.h_bA, d.bA, (size_t)MAXC * d.kcap * sizeof(double), cudaMemcpyDeviceToHost, m.st));
     CUDA_CHECK(cudaStreamSynchronize(m.st));
+    m.collect_spans();
     out.T = T;
     out.nchains = b.nch;
     for (int i = 0; i < b.nch; i++) {
@@ -541,7 +693,9 @@ void Engine::losses(const std::vector<LossJob> &jobs, std::vector<double> &out)
         ld.kind[i] = jobs[i].kind;
         ld.fold[i] = jobs[i].fold;
     }
+    const int sp = m.span_begin(5);
     launch_losses(m.d, ld, m.testrows, m.ntest, m.y, m.w, m.lfact, m.loss_scratch, m.loss_out, m.st);
+    m.span_end(sp);
     CUDA_CHECK(cudaMemcpyAsync(m.h_loss, m.loss_out, ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     stats_.kernel_launches++;

@@ -39,7 +39,8 @@ struct LossJob {
 
 struct EngineStats {
     long long n_fits = 0, n_pdas_iters = 0, n_sweeps = 0, n_batches = 0, n_boundary_ties = 0;
-    double sweep_bytes = 0.0;     // algorithmic bytes swept (8*n*p per sweep launch + vectors)
+    double sweep_bytes = 0.0;     // algorithmic bytes of the PDAS dual sweeps (8*n*p per launch + vectors)
+    double big_sweep_bytes = 0.0; // algorithmic bytes of the screening / normalisation passes
     long long kernel_launches = 0;
 };
 
@@ -53,10 +54,21 @@ public:
     // ---- design upload.  x: row-major n x p (pywrap_bess layout, utilities.cpp:13-25).
     // x_on_device: x already lives in device memory (bench "resident" mode); it is still copied
     // into engine-owned storage because normalisation is in place.
-    void load(const double *x, int n, int p, bool x_on_device, const double *y, const double *weight, int family);
+    // borrow: a device-resident x may be used in place (no copy) until something needs to write to it.
+    void load(const double *x, int n, int p, bool x_on_device, const double *y, const double *weight, int family,
+              bool borrow = false);
+    // per-category device time (CUDA events on the engine's stream): 0 big sweeps (screening/normalise),
+    // 1 PDAS dual sweeps, 2 finish, 3 top-k, 4 chain kernels, 5 other
+    void set_profiling(bool on);
+    void profile(double *ms_out6, long long *n_out6) const;
 
     // ---- screening.cpp:26-105: marginal utilities on RAW x, top `size`, X <- X[:, A].  Returns A ascending.
     std::vector<int> screen(int size, const std::vector<int> &always_select);
+
+    // ---- column-sharded screening (multi-GPU axis B): local top-`size` candidates, X untouched
+    void screen_local(int size, const std::vector<int> &always_select, std::vector<double> &vals, std::vector<int> &idx);
+    // dst_dev[i*ld + pos[q]] = X[i][cols[q]]  (dst_dev: device buffer)
+    void gather_columns(const int *cols, const int *pos, int m, double *dst_dev, long long ld);
 
     // ---- Data ctor normalisation (Data.h:41-68, normalize.cpp) + add_weight for gaussian (Data.h:70-77).
     void normalize(int data_type, bool is_normal);

@@ -1418,6 +1418,23 @@ void launch_gather_cols(const double *X, long long ldx, int n, const int *cols, 
     CUDA_CHECK(cudaGetLastError());
 }
 
+__global__ void gather_cols_pos_kernel(const double *X, long long ldx, int n, const int *cols, const int *pos, int m,
+                                       double *dst, long long ld)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const int src = cols[q], dp = pos[q];
+    const int r0 = blockIdx.y * 32, r1 = min(n, r0 + 32);
+    for (int i = r0; i < r1; i++) dst[(size_t)i * ld + dp] = X[(size_t)i * ldx + src];
+}
+void launch_gather_cols_pos(const double *X, long long ldx, int n, const int *cols, const int *pos, int m, double *dst,
+                            long long ld, cudaStream_t st)
+{
+    dim3 grid((m + 127) / 128, (n + 31) / 32);
+    gather_cols_pos_kernel<<<grid, 128, 0, st>>>(X, ldx, n, cols, pos, m, dst, ld);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // Marginal GLM utilities for screening (screening.cpp:48-61): one thread per column, the column is re-read from
 // L2/HBM each Newton/IRLS step (coalesced across the warp because X is row-major).
 //   binomial: logit_fit, logistic.cpp:61-157 (2-parameter IRLS, no W floor, returns the previous iterate)

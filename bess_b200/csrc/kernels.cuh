@@ -90,6 +90,8 @@ void launch_center_scale(double *X, long long ldx, int n, int p, const double *s
                          const double *rowmul, cudaStream_t st);
 void launch_gather_cols(const double *X, long long ldx, int n, const int *cols, int pnew, double *Xn, long long ldn,
                         cudaStream_t st);
+void launch_gather_cols_pos(const double *X, long long ldx, int n, const int *cols, const int *pos, int m, double *dst,
+                            long long ld, cudaStream_t st);
 void launch_screen_glm(const double *X, long long ldx, int n, int p, const double *y, const double *w, int family,
                        double *util, cudaStream_t st);
 size_t fit_smem_bytes(const Dev &d);

@@ -269,7 +269,8 @@ void bess_run(const BessArgs &a, BessResult &out)
         if (j < 0 || j >= a.p) throw EngineError{"always_select index out of range"};
 
     Engine eng(a.device);
-    eng.load(a.x, a.n, a.p, a.x_on_device, a.y, a.weight, a.model_type);
+    eng.set_profiling(a.profile);
+    eng.load(a.x, a.n, a.p, a.x_on_device, a.y, a.weight, a.model_type, /*borrow=*/a.is_screening);
 
     std::vector<int> always = a.always_select;
     std::sort(always.begin(), always.end());
@@ -330,6 +331,8 @@ void bess_run(const BessArgs &a, BessResult &out)
         out.beta = std::move(beta);
     }
     out.stats = eng.stats();
+    eng.profile(out.prof_ms, out.prof_n);
+    out.sweep_splits = eng.sweep_splits();
 }
 
 }  // namespace bess

@@ -41,6 +41,7 @@ struct BessArgs {
     unsigned cv_seed = 123;
     bool x_on_device = false;          // x is a device pointer (bench "resident" mode)
     int device = -1;
+    bool profile = false;              // CUDA-event timing per kernel category
 };
 
 struct BessResult {
@@ -54,6 +55,9 @@ struct BessResult {
     std::vector<double> coef0_all, train_loss_all, ic_all;
     std::vector<int> s_all, l_all;
     EngineStats stats;
+    double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+    long long prof_n[6] = {0, 0, 0, 0, 0, 0};
+    int sweep_splits = 1;
 };
 
 // Metric.h:49-106 with the seed pinned (same std::mt19937 + std::shuffle + chunking)

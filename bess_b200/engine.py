@@ -58,6 +58,21 @@ class GpuEngine:
         self.p = size
         return out
 
+    def screen_local(self, size, always_select=()):
+        alw = np.ascontiguousarray(list(always_select), dtype=np.int32)
+        size = min(size, self.p)
+        vals = np.zeros(size)
+        idx = np.zeros(size, dtype=np.int32)
+        cnt = C.c_int(0)
+        _lib.check(self._lib.bessgpu_screen_local(self._h, size, _i(alw), alw.size, _d(vals), _i(idx), C.byref(cnt)))
+        return vals[:cnt.value], idx[:cnt.value]
+
+    def gather_columns(self, cols, pos, dst_device_ptr, ld):
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        _lib.check(self._lib.bessgpu_gather_columns(self._h, _i(cols), _i(pos), cols.size, C.c_void_p(int(dst_device_ptr)),
+                                                    int(ld)))
+
     def normalize(self, data_type, is_normal=True):
         _lib.check(self._lib.bessgpu_normalize(self._h, data_type, int(is_normal)))
         xm, xn = np.zeros(self.p), np.zeros(self.p)

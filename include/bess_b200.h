@@ -61,8 +61,12 @@ typedef struct bess_b200_ext {
     int device;               /* CUDA device ordinal, -1 = current                                                    */
     int *screening_A_out;     /* [screening_size] kept columns, ascending (List key "screening_A", bess.cpp:199)     */
     int *chosen_s_out;        /* sparsity level of the returned model                                                 */
-    double *stats_out;        /* [8]: n_fits, n_pdas_iters, n_sweeps, n_batches, n_boundary_ties, sweep_bytes,        */
-                              /*      kernel_launches, trace_len                                                      */
+    double *stats_out;        /* [24]: 0 n_fits, 1 n_pdas_iters, 2 n_sweeps, 3 n_batches, 4 n_boundary_ties,          */
+                              /*  5 PDAS dual-sweep algorithmic bytes, 6 kernel_launches, 7 trace_len,                */
+                              /*  8..13 device ms per kernel category (profile != 0): screening/normalise passes,     */
+                              /*  PDAS dual sweeps, finish, top-k, chain kernels, other; 14..19 launches per category;*/
+                              /*  20 algorithmic bytes of the screening/normalise passes; 21 sweep row splits         */
+    int profile;              /* record CUDA events around every kernel category on the engine's stream               */
 } bess_b200_ext;
 
 /* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's
@@ -100,6 +104,12 @@ int bessgpu_load(bessgpu_handle *h, const double *x, int n, int p, int x_on_devi
                  const double *weight, int model_type);
 /* screening.cpp:26-105; out: screening_size kept columns, ascending */
 int bessgpu_screen(bessgpu_handle *h, int screening_size, const int *always_select, int n_always, int *screening_A_out);
+/* column-sharded screening (multi-GPU): the local top-`size` candidates of this handle's columns as (utility, local
+ * column index) pairs, ascending index; the design stays untouched.  count_out = min(size, p_local). */
+int bessgpu_screen_local(bessgpu_handle *h, int screening_size, const int *always_select, int n_always,
+                         double *vals_out, int *idx_out, int *count_out);
+/* dst_dev[i*ld + pos[q]] = x[i][cols[q]], q < m: copies chosen columns into a DEVICE buffer (row-major, leading dim ld) */
+int bessgpu_gather_columns(bessgpu_handle *h, const int *cols, const int *pos, int m, double *dst_dev, long long ld);
 /* Data.h:41-77 + normalize.cpp:20-86 */
 int bessgpu_normalize(bessgpu_handle *h, int data_type, int is_normal);
 int bessgpu_get_norm(bessgpu_handle *h, double *x_mean_out, double *x_norm_out, double *y_mean_out);

@@ -1,0 +1,122 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every symbol include/bess_b200.h declares (and the
+reference's C++-mangled pywrap_bess), refuses loudly to compute without a GPU, and its pure-host helpers are right."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.helpers import golden_names, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MANGLED = "_Z11pywrap_bessPdiiS_iiS_ibiiiiibibiPiiS_iS0_iS_iiiidddibiiS0_idS_iS_iS_iS_iS_S_iS_iS_iS0_iS0_"
+
+
+def _lib():
+    from bess_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib()
+    hdr = open(os.path.join(ROOT, "include", "bess_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b((?:bess_b200|bessgpu)_[a-z0-9_]+|pywrap_bess)\s*\(", hdr))
+    assert {"pywrap_bess", "bess_b200_fit", "bessgpu_run_batch", "bess_b200_merge_candidates"} <= names
+    for nm in sorted(names):
+        assert hasattr(lib, nm), f"{nm} declared in include/bess_b200.h but not exported"
+    assert lib.bess_b200_version() == 100
+
+
+def test_reference_cxx_linkage_symbol_is_exported():
+    """The reference's pywrap_bess has C++ linkage (bess.h:35-51); a SWIG module built from its bess.i must link."""
+    from bess_b200 import _lib
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert MANGLED in out
+    assert re.search(r"\bT pywrap_bess\b", out)
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    from bess_b200 import _lib, cbess
+    lib = _lib.load()
+    if lib.bess_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    x = np.random.default_rng(0).standard_normal((20, 8))
+    with pytest.raises(_lib.BessB200Error):
+        cbess.fit(x, x[:, 0], 1, np.ones(20), True, 1, 1, 20, 2, 1, True, 3, False, 5, [1, 2], 1, 2, False, 1)
+    with pytest.raises(_lib.BessB200Error):
+        from bess_b200.engine import GpuEngine
+        GpuEngine()
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "bess_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("numpy oracle", ""), f
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "cv" in n])
+def test_cv_folds_match_the_reference_draw(name):
+    """Metric.h:49-106 restated in path.cpp: same mt19937 + std::shuffle + chunking => the folds the reference drew."""
+    from bess_b200 import cbess
+    g = load_golden(name)
+    assert cbess.cv_fold_ids(g["x"].shape[0], g["K"], 123).tolist() == g["fold_of_row"].tolist()
+
+
+def test_shard_ranges_cover_columns_contiguously():
+    import ctypes as C
+    lib = _lib()
+    for p in (1, 2, 7, 5000, 500000, 500001):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = C.c_longlong(), C.c_longlong()
+                lib.bess_b200_shard_range(p, world, r, C.byref(lo), C.byref(hi))
+                assert lo.value == prev and hi.value >= lo.value and (lo.value % 2 == 0 or lo.value == p)
+                prev = hi.value
+            assert prev == p
+    assert [lib.bess_b200_chain_owner(c, 4) for c in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+def test_merge_candidates_is_exact_topk():
+    from bess_b200._lib import dp, ip
+    lib = _lib()
+    rng = np.random.default_rng(1)
+    v = np.floor(rng.random(1000) * 50)
+    idx = rng.permutation(1000).astype(np.int32)
+    k = 37
+    out = np.zeros(k, dtype=np.int32)
+    assert lib.bess_b200_merge_candidates(v.ctypes.data_as(dp), idx.ctypes.data_as(ip), 1000, k, out.ctypes.data_as(ip)) == 0
+    order = np.lexsort((idx, -v))
+    assert out.tolist() == sorted(idx[order[:k]].tolist())
+
+
+def test_frontend_argument_surface(monkeypatch):
+    """family/method/s.list/nfolds/IC/screening.num -> the integer codes of the reference (linear.py:138-324)."""
+    from bess_b200 import linear
+    seen = {}
+
+    def fake(*args):
+        seen["args"] = args
+        p = args[0].shape[1]
+        return [np.zeros(p), 0.0, 0.0, 0.0, 0.0, None, None, None, None, 0]
+    monkeypatch.setattr(linear, "pywrap_bess", fake)
+    x = np.random.default_rng(0).standard_normal((50, 30))
+    m = linear.PdasLogistic(path_type="pgs", ic_type="gic", is_cv=True, K=7, is_screening=True, screening_size=20)
+    m.fit(x, (x[:, 0] > 0).astype(float))
+    a = seen["args"]
+    assert a[2] == 2 and a[5] == 1 and a[6] == 2 and a[9] == 2 and a[11] == 3 and a[12] is True and a[13] == 7
+    assert a[18] == 1 and a[19] == 30 and a[25] is True and a[26] == 20 and a[30] == 30
+    m = linear.PdasCox(path_type="seq", sequence=[1, 2, 3])
+    t = np.random.default_rng(1).random(50)
+    m.fit(x, np.column_stack([t, np.ones(50)]))
+    a = seen["args"]
+    assert a[2] == 3 and a[6] == 4 and a[9] == 1 and list(a[16]) == [1, 2, 3]
+    assert np.allclose(a[0], x[np.argsort(t)])  # rows time-sorted (linear.py:257-263)
+    with pytest.raises(ValueError):
+        linear.PdasLm(is_screening=True, screening_size=2, sequence=[1, 2, 3]).fit(x, x[:, 0])
+    with pytest.raises(ValueError):
+        linear.bess_base("Nope", "Lm", "seq")
