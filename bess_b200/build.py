@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
             print(f"nvcc failed on {src}:\n{out}", file=sys.stderr)
     if failed:
         raise RuntimeError("bess_b200: nvcc build failed")
-    cmd = [_nvcc(), "-shared", "-o", SO, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", SO, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

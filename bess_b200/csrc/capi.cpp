@@ -185,9 +185,12 @@ int bess_b200_trace(int *s_all, int *l_all, double *coef0_all, double *train_los
     if (train_loss_all) std::copy(r.train_loss_all.begin(), r.train_loss_all.end(), train_loss_all);
     if (ic_all) std::copy(r.ic_all.begin(), r.ic_all.end(), ic_all);
     if (beta_all)
-        for (size_t i = 0; i < r.beta_all.size(); i++)
-            std::copy(r.beta_all[i].begin(), r.beta_all[i].begin() + std::min<size_t>((size_t)p, r.beta_all[i].size()),
-                      beta_all + i * (size_t)p);
+        for (size_t i = 0; i < r.A_all.size(); i++) {
+            double *row = beta_all + i * (size_t)p;
+            std::fill(row, row + p, 0.0);
+            for (size_t q = 0; q < r.A_all[i].size(); q++)
+                if (r.A_all[i][q] < p) row[r.A_all[i][q]] = r.bA_all[i][q];
+        }
     return (int)L;
 }
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 
 namespace bess {
@@ -19,19 +20,86 @@ namespace bess {
 
 constexpr int PROF_NCAT = 6;  // 0 sweep(big: screening/normalise), 1 sweep(PDAS), 2 finish, 3 topk, 4 chain kernels, 5 other
 namespace {
+// Stream-ordered allocation from the device's default memory pool (release threshold raised to "never" in
+// DeviceContext): after the first call every alloc/free is a pool hit, no cudaMalloc/cudaFree (and no implicit
+// device synchronisation) on the hot path.  All engine work is on ONE stream, so stream order == program order.
 template <class T>
-T *dalloc(size_t count)
+T *dalloc(cudaStream_t st, size_t count)
 {
     T *p = nullptr;
     if (count == 0) count = 1;
-    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    CUDA_CHECK(cudaMallocAsync((void **)&p, count * sizeof(T), st));
     return p;
 }
 template <class T>
-void dfree(T *&p)
+void dfree(cudaStream_t st, T *&p)
 {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync((void *)p, st);
     p = nullptr;
+}
+
+// Per-device resources that are expensive to create (stream, pinned mirrors) are cached for the life of the process
+// and lent to one Engine at a time.
+struct DeviceContext {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t st = nullptr;
+    int *h_int = nullptr;        // pinned: [4][MAXC] done, l, ks, tie
+    double *h_dbl = nullptr;     // pinned: [MAXC] coef0 + [2*MAXC] losses
+    int *h_A = nullptr;          // pinned, grow-only: [MAXC][kcap]
+    double *h_bA = nullptr;
+    size_t cap_A = 0;
+    bool in_use = false;
+    void reserve_support(size_t count)
+    {
+        if (count <= cap_A) return;
+        if (h_A) cudaFreeHost(h_A);
+        if (h_bA) cudaFreeHost(h_bA);
+        h_A = nullptr; h_bA = nullptr; cap_A = 0;
+        CUDA_CHECK(cudaMallocHost(&h_A, count * sizeof(int)));
+        CUDA_CHECK(cudaMallocHost(&h_bA, count * sizeof(double)));
+        cap_A = count;
+    }
+};
+std::mutex g_ctx_mu;
+std::vector<DeviceContext *> g_ctx;
+
+DeviceContext *acquire_context(int device)
+{
+    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        for (DeviceContext *c : g_ctx)
+            if (c->device == dev && !c->in_use) {
+                c->in_use = true;
+                return c;
+            }
+    }
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) throw EngineError{"bess_b200 needs an sm_100a (Blackwell) device"};
+    DeviceContext *c = new DeviceContext();
+    c->device = dev;
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ULL;
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    CUDA_CHECK(cudaMallocHost(&c->h_int, 4 * MAXC * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&c->h_dbl, 3 * MAXC * sizeof(double)));
+    configure_kernels();
+    c->in_use = true;
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    g_ctx.push_back(c);
+    return c;
+}
+void release_context(DeviceContext *c)
+{
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    c->in_use = false;
 }
 int pick_fs(int nch)
 {
@@ -43,6 +111,7 @@ int pick_fs(int nch)
 }  // namespace
 
 struct Engine::Impl {
+    DeviceContext *ctx = nullptr;
     cudaStream_t st = nullptr;
     int sm_count = 148;
     Dev d{};
@@ -64,8 +133,8 @@ struct Engine::Impl {
     double *ck0 = nullptr, *ck1 = nullptr;
     int *ci0 = nullptr, *ci1 = nullptr;
     long long cstride = 0;
-    // pinned host mirrors
-    int *h_done = nullptr, *h_l = nullptr, *h_ks = nullptr, *h_A = nullptr, *h_tie = nullptr;
+    // pinned host mirrors (owned by the DeviceContext)
+    int *h_done = nullptr, *h_l = nullptr, *h_tie = nullptr, *h_A = nullptr;
     double *h_coef0 = nullptr, *h_bA = nullptr, *h_loss = nullptr;
     bool chains_ready = false;
     bool x_owned = true;
@@ -112,22 +181,27 @@ struct Engine::Impl {
 
     void free_sweep_buffers()
     {
-        dfree(d.G); dfree(d.W); dfree(d.TH); dfree(d.C2);
-        dfree(d.part); dfree(d.c2sum); dfree(d.bd); dfree(raw);
+        Impl &m = *this;
+        dfree(m.st, d.G); dfree(m.st, d.W); dfree(m.st, d.TH); dfree(m.st, d.C2);
+        dfree(m.st, d.part); dfree(m.st, d.c2sum); dfree(m.st, d.bd); dfree(m.st, raw);
     }
     void free_chain_buffers()
     {
-        dfree(d.rows); dfree(d.ntrain); dfree(d.ytr); dfree(d.wtr); dfree(d.ks); dfree(d.A); dfree(d.bA);
-        dfree(d.coef0); dfree(d.coef0_level); dfree(d.Anew); dfree(d.hist); dfree(d.l); dfree(d.done); dfree(d.tie);
-        dfree(d.betaD); dfree(d.XA); dfree(d.XB); dfree(d.vec); dfree(d.Smat); dfree(d.xtx);
-        dfree(testrows); dfree(ntest); dfree(lfact); dfree(loss_scratch); dfree(loss_out); dfree(always);
-        dfree(ck0); dfree(ck1); dfree(ci0); dfree(ci1);
+        Impl &m = *this;
+        dfree(m.st, d.rows); dfree(m.st, d.ntrain); dfree(m.st, d.ytr); dfree(m.st, d.wtr); dfree(m.st, d.ks); dfree(m.st, d.A); dfree(m.st, d.bA);
+        dfree(m.st, d.coef0); dfree(m.st, d.coef0_level); dfree(m.st, d.Anew); dfree(m.st, d.hist); dfree(m.st, d.l); dfree(m.st, d.done); dfree(m.st, d.tie);
+        dfree(m.st, d.tie_acc); dfree(m.st, d.n_active);
+        dfree(m.st, d.betaD); dfree(m.st, d.XA); dfree(m.st, d.XB); dfree(m.st, d.vec); dfree(m.st, d.Smat); dfree(m.st, d.xtx);
+        dfree(m.st, testrows); dfree(m.st, ntest); dfree(m.st, lfact); dfree(m.st, loss_scratch); dfree(m.st, loss_out); dfree(m.st, always);
+        dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
         chains_ready = false;
     }
     // (re)allocate the sweep vectors / partial buffers for FS chain slots over the current (n, p)
     void config_sweep(int FS)
     {
+        Impl &m = *this;
         free_sweep_buffers();
+        d.gate = nullptr;
         d.X = X; d.ldx = ldx; d.n = n; d.p = p; d.FS = FS;
         d.pstride = (p + 1) & ~1LL;
         // row splits: enough CTAs to fill the machine several times over
@@ -140,15 +214,15 @@ struct Engine::Impl {
         d.rows_per_split = rps;
         d.S = (n + rps - 1) / rps;
         const size_t vsz = (size_t)npad * FS;
-        d.G = dalloc<double>(vsz); d.W = dalloc<double>(vsz); d.TH = dalloc<double>(vsz); d.C2 = dalloc<double>(vsz);
+        d.G = dalloc<double>(m.st, vsz); d.W = dalloc<double>(m.st, vsz); d.TH = dalloc<double>(m.st, vsz); d.C2 = dalloc<double>(m.st, vsz);
         CUDA_CHECK(cudaMemsetAsync(d.G, 0, vsz * 8, st));
         CUDA_CHECK(cudaMemsetAsync(d.W, 0, vsz * 8, st));
         CUDA_CHECK(cudaMemsetAsync(d.TH, 0, vsz * 8, st));
         CUDA_CHECK(cudaMemsetAsync(d.C2, 0, vsz * 8, st));
-        d.part = dalloc<double>((size_t)d.S * 5 * FS * d.pstride);
-        d.c2sum = dalloc<double>((size_t)d.S * FS);
-        d.bd = dalloc<double>((size_t)FS * d.pstride);
-        raw = dalloc<double>((size_t)2 * FS * d.pstride);
+        d.part = dalloc<double>(m.st, (size_t)d.S * 5 * FS * d.pstride);
+        d.c2sum = dalloc<double>(m.st, (size_t)d.S * FS);
+        d.bd = dalloc<double>(m.st, (size_t)FS * d.pstride);
+        raw = dalloc<double>(m.st, (size_t)2 * FS * d.pstride);
     }
     // upload a host vector into slot f of a [npad][FS] sweep vector
     void put_vec(double *dst, int f, const std::vector<double> &v)
@@ -160,38 +234,37 @@ struct Engine::Impl {
 Engine::Engine(int device)
 {
     d_ = new Impl();
-    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
-    int dev = 0;
-    CUDA_CHECK(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10) throw EngineError{"bess_b200 needs an sm_100a (Blackwell) device"};
-    d_->sm_count = prop.multiProcessorCount;
-    CUDA_CHECK(cudaStreamCreateWithFlags(&d_->st, cudaStreamNonBlocking));
-    configure_kernels();
-    CUDA_CHECK(cudaMallocHost(&d_->h_done, MAXC * sizeof(int)));
-    CUDA_CHECK(cudaMallocHost(&d_->h_l, MAXC * sizeof(int)));
-    CUDA_CHECK(cudaMallocHost(&d_->h_ks, MAXC * sizeof(int)));
-    CUDA_CHECK(cudaMallocHost(&d_->h_tie, MAXC * sizeof(int)));
-    CUDA_CHECK(cudaMallocHost(&d_->h_coef0, MAXC * sizeof(double)));
-    CUDA_CHECK(cudaMallocHost(&d_->h_loss, 2 * MAXC * sizeof(double)));
+    try {
+        d_->ctx = acquire_context(device);
+    } catch (...) {
+        delete d_;
+        d_ = nullptr;
+        throw;
+    }
+    DeviceContext *c = d_->ctx;
+    d_->st = c->st;
+    d_->sm_count = c->sm_count;
+    d_->h_done = c->h_int;
+    d_->h_l = c->h_int + MAXC;
+    d_->h_tie = c->h_int + 2 * MAXC;
+    d_->h_coef0 = c->h_dbl;
+    d_->h_loss = c->h_dbl + MAXC;
 }
 
 Engine::~Engine()
 {
     if (!d_) return;
-    cudaStreamSynchronize(d_->st);
-    d_->collect_spans();
-    for (cudaEvent_t e : d_->pool) cudaEventDestroy(e);
-    d_->free_chain_buffers();
-    d_->free_sweep_buffers();
-    if (d_->x_owned) dfree(d_->X);
-    dfree(d_->y); dfree(d_->w);
-    cudaFreeHost(d_->h_done); cudaFreeHost(d_->h_l); cudaFreeHost(d_->h_ks); cudaFreeHost(d_->h_tie);
-    cudaFreeHost(d_->h_coef0); cudaFreeHost(d_->h_loss);
-    if (d_->h_A) cudaFreeHost(d_->h_A);
-    if (d_->h_bA) cudaFreeHost(d_->h_bA);
-    cudaStreamDestroy(d_->st);
+    Impl &m = *d_;
+    cudaSetDevice(m.ctx->device);
+    cudaStreamSynchronize(m.st);
+    m.collect_spans();
+    for (cudaEvent_t e : m.pool) cudaEventDestroy(e);
+    m.free_chain_buffers();
+    m.free_sweep_buffers();
+    if (m.x_owned) dfree(m.st, m.X);
+    dfree(m.st, m.y); dfree(m.st, m.w);
+    cudaStreamSynchronize(m.st);
+    release_context(m.ctx);
     delete d_;
 }
 
@@ -212,8 +285,8 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     if (family < 1 || family > 4) throw EngineError{"load: model_type must be 1..4"};
     m.free_chain_buffers();
     m.free_sweep_buffers();
-    if (m.x_owned) dfree(m.X);
-    dfree(m.y); dfree(m.w);
+    if (m.x_owned) dfree(m.st, m.X);
+    dfree(m.st, m.y); dfree(m.st, m.w);
     n_ = n; p_ = p; family_ = family;
     m.n = n; m.p = p; m.npad = (n + 1) & ~1;
     m.ldx = (p + 1) & ~1LL;
@@ -224,7 +297,7 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
         m.x_owned = false;
     } else {
         m.x_owned = true;
-        m.X = dalloc<double>((size_t)n * m.ldx);
+        m.X = dalloc<double>(m.st, (size_t)n * m.ldx);
         if (m.ldx != p) CUDA_CHECK(cudaMemsetAsync(m.X, 0, (size_t)n * m.ldx * 8, m.st));
         const int sp = m.span_begin(5);
         CUDA_CHECK(cudaMemcpy2DAsync(m.X, (size_t)m.ldx * 8, x, (size_t)p * 8, (size_t)p * 8, n,
@@ -233,8 +306,8 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     }
     m.hy.assign(y, y + n);
     m.hw.assign(weight, weight + n);
-    m.y = dalloc<double>(m.npad);
-    m.w = dalloc<double>(m.npad);
+    m.y = dalloc<double>(m.st, m.npad);
+    m.w = dalloc<double>(m.st, m.npad);
     CUDA_CHECK(cudaMemsetAsync(m.y, 0, m.npad * 8, m.st));
     CUDA_CHECK(cudaMemsetAsync(m.w, 0, m.npad * 8, m.st));
     CUDA_CHECK(cudaMemcpyAsync(m.y, y, n * 8, cudaMemcpyHostToDevice, m.st));
@@ -256,12 +329,12 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
 {
     Impl &m = *d_;
     if (size < 1 || size > m.p) throw EngineError{"screening_size must be in [1, p]"};
-    int *d_sel = dalloc<int>(size);
+    int *d_sel = dalloc<int>(m.st, size);
     std::vector<int> sel;
     screen_select(m, stats_, family_, size, always_select, d_sel, nullptr, &sel);
     // X <- X[:, sel]  (screening.cpp:83-88)
     const long long ldn = (size + 1) & ~1LL;
-    double *Xn = dalloc<double>((size_t)m.n * ldn);
+    double *Xn = dalloc<double>(m.st, (size_t)m.n * ldn);
     if (ldn != size) CUDA_CHECK(cudaMemsetAsync(Xn, 0, (size_t)m.n * ldn * 8, m.st));
     const int spk = m.span_begin(5);
     launch_gather_cols(m.X, m.ldx, m.n, d_sel, size, Xn, ldn, m.st);
@@ -269,13 +342,13 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     m.collect_spans();
     stats_.kernel_launches += 1;
-    if (m.x_owned) dfree(m.X);
+    if (m.x_owned) dfree(m.st, m.X);
     m.x_owned = true;
     m.X = Xn;
     m.ldx = ldn;
     m.p = size;
     p_ = size;
-    dfree(d_sel);
+    dfree(m.st, d_sel);
     m.free_sweep_buffers();
     h_xmean_.assign(size, 0.0);
     h_xnorm_.assign(size, 0.0);
@@ -289,9 +362,9 @@ void Engine::screen_local(int size, const std::vector<int> &always_select, std::
 {
     Impl &m = *d_;
     size = std::min(size, m.p);
-    int *d_sel = dalloc<int>(size);
+    int *d_sel = dalloc<int>(m.st, size);
     screen_select(m, stats_, family_, size, always_select, d_sel, &vals, &idx);
-    dfree(d_sel);
+    dfree(m.st, d_sel);
     m.free_sweep_buffers();
 }
 
@@ -300,14 +373,14 @@ void Engine::gather_columns(const int *cols, const int *pos, int mcols, double *
 {
     Impl &m = *d_;
     if (mcols <= 0) return;
-    int *d_cols = dalloc<int>(mcols), *d_pos = dalloc<int>(mcols);
+    int *d_cols = dalloc<int>(m.st, mcols), *d_pos = dalloc<int>(m.st, mcols);
     CUDA_CHECK(cudaMemcpyAsync(d_cols, cols, (size_t)mcols * 4, cudaMemcpyHostToDevice, m.st));
     CUDA_CHECK(cudaMemcpyAsync(d_pos, pos, (size_t)mcols * 4, cudaMemcpyHostToDevice, m.st));
     launch_gather_cols_pos(m.X, m.ldx, m.n, d_cols, d_pos, mcols, dst_dev, ld, m.st);
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     stats_.kernel_launches += 1;
-    dfree(d_cols);
-    dfree(d_pos);
+    dfree(m.st, d_cols);
+    dfree(m.st, d_pos);
 }
 
 static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int size,
@@ -340,14 +413,14 @@ static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int
     }
     int *d_alw = nullptr;
     if (!always_select.empty()) {
-        d_alw = dalloc<int>(always_select.size());
+        d_alw = dalloc<int>(m.st, always_select.size());
         CUDA_CHECK(cudaMemcpyAsync(d_alw, always_select.data(), always_select.size() * 4, cudaMemcpyHostToDevice, m.st));
         launch_pin(m.d, m.d.bd, m.d.pstride, 1, d_alw, (int)always_select.size(), m.st);
     }
     const long long cstride = std::max<long long>(2LL * size + 16, ((long long)m.p / 8192 + 2) * std::min(size, TOPK_LMAX));
-    double *ck0 = dalloc<double>(cstride), *ck1 = dalloc<double>(cstride);
-    int *ci0 = dalloc<int>(cstride), *ci1 = dalloc<int>(cstride);
-    int *d_tie = dalloc<int>(1);
+    double *ck0 = dalloc<double>(m.st, cstride), *ck1 = dalloc<double>(m.st, cstride);
+    int *ci0 = dalloc<int>(m.st, cstride), *ci1 = dalloc<int>(m.st, cstride);
+    int *d_tie = dalloc<int>(m.st, 1);
     const int spk = m.span_begin(3);
     launch_topk(m.d.bd, m.d.pstride, m.p, size, 1, d_sel, size, d_tie, ck0, ci0, ck1, ci1, cstride, m.st);
     m.span_end(spk);
@@ -366,7 +439,7 @@ static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int
     m.collect_spans();
     stats_.n_boundary_ties += tie;
     stats_.kernel_launches += 2;
-    dfree(ck0); dfree(ck1); dfree(ci0); dfree(ci1); dfree(d_tie); dfree(d_alw);
+    dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1); dfree(m.st, d_tie); dfree(m.st, d_alw);
 }
 
 // Data ctor (Data.h:41-68) + normalize.cpp + add_weight (Data.h:70-77, bess.cpp:97)
@@ -375,7 +448,7 @@ void Engine::normalize(int data_type, bool is_normal)
     Impl &m = *d_;
     const int n = m.n, p = m.p;
     if (!m.x_owned) {  // normalisation is in place: take a private copy of a borrowed design
-        double *Xc = dalloc<double>((size_t)n * m.ldx);
+        double *Xc = dalloc<double>(m.st, (size_t)n * m.ldx);
         CUDA_CHECK(cudaMemcpyAsync(Xc, m.X, (size_t)n * m.ldx * 8, cudaMemcpyDeviceToDevice, m.st));
         m.X = Xc;
         m.x_owned = true;
@@ -394,7 +467,7 @@ void Engine::normalize(int data_type, bool is_normal)
             m.put_vec(m.d.G, 0, g);
             launch_dual_sweep(m.d, MODE_D, m.st);
             launch_finish(m.d, MODE_D, EPI_RAW, b, m.raw, m.st);
-            d_mean = dalloc<double>(m.d.pstride);
+            d_mean = dalloc<double>(m.st, m.d.pstride);
             CUDA_CHECK(cudaMemcpyAsync(d_mean, m.raw, (size_t)p * 8, cudaMemcpyDeviceToDevice, m.st));
             CUDA_CHECK(cudaMemcpyAsync(h_xmean_.data(), m.raw, (size_t)p * 8, cudaMemcpyDeviceToHost, m.st));
             launch_center_scale(m.X, m.ldx, n, p, d_mean, nullptr, nullptr, m.st);
@@ -422,7 +495,7 @@ void Engine::normalize(int data_type, bool is_normal)
             h_xnorm_[j] = std::sqrt(h[j]);
             mul[j] = sn / h_xnorm_[j];  // normalize.cpp:42-45
         }
-        d_mul = dalloc<double>(m.d.pstride);
+        d_mul = dalloc<double>(m.st, m.d.pstride);
         CUDA_CHECK(cudaMemcpyAsync(d_mul, mul.data(), (size_t)p * 8, cudaMemcpyHostToDevice, m.st));
         stats_.kernel_launches += 2;
         stats_.n_sweeps += 2;
@@ -434,7 +507,7 @@ void Engine::normalize(int data_type, bool is_normal)
             rm[i] = std::sqrt(m.hw[i]);
             m.hy[i] *= rm[i];
         }
-        d_rowmul = dalloc<double>(n);
+        d_rowmul = dalloc<double>(m.st, n);
         CUDA_CHECK(cudaMemcpyAsync(d_rowmul, rm.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
     }
     if (d_mul || d_rowmul) {
@@ -448,7 +521,7 @@ void Engine::normalize(int data_type, bool is_normal)
     // passes over X: [mean sweep 8np + centre 16np] (data_type 1,2) + norm sweep 8np + scale 16np
     if (is_normal) stats_.big_sweep_bytes += (data_type == 3 ? 24.0 : 48.0) * n * p;
     else if (family_ == FAM_LM) stats_.big_sweep_bytes += 16.0 * n * p;
-    dfree(d_mean); dfree(d_mul); dfree(d_rowmul);
+    dfree(m.st, d_mean); dfree(m.st, d_mul); dfree(m.st, d_rowmul);
     m.free_sweep_buffers();
 }
 
@@ -492,12 +565,12 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
             ytr[(size_t)c * n + r] = m.hy[rows[(size_t)c * n + r]];
             wtr[(size_t)c * n + r] = m.hw[rows[(size_t)c * n + r]];
         }
-    d.rows = dalloc<int>((size_t)MAXC * n);
-    d.ntrain = dalloc<int>(MAXC);
-    d.ytr = dalloc<double>((size_t)MAXC * n);
-    d.wtr = dalloc<double>((size_t)MAXC * n);
-    m.testrows = dalloc<int>((size_t)MAXC * n);
-    m.ntest = dalloc<int>(MAXC);
+    d.rows = dalloc<int>(m.st, (size_t)MAXC * n);
+    d.ntrain = dalloc<int>(m.st, MAXC);
+    d.ytr = dalloc<double>(m.st, (size_t)MAXC * n);
+    d.wtr = dalloc<double>(m.st, (size_t)MAXC * n);
+    m.testrows = dalloc<int>(m.st, (size_t)MAXC * n);
+    m.ntest = dalloc<int>(m.st, MAXC);
     CUDA_CHECK(cudaMemcpyAsync(d.rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, m.st));
     CUDA_CHECK(cudaMemcpyAsync(d.ntrain, ntrain.data(), MAXC * 4, cudaMemcpyHostToDevice, m.st));
     CUDA_CHECK(cudaMemcpyAsync(d.ytr, ytr.data(), ytr.size() * 8, cudaMemcpyHostToDevice, m.st));
@@ -506,21 +579,23 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     CUDA_CHECK(cudaMemcpyAsync(m.ntest, ntest.data(), MAXC * 4, cudaMemcpyHostToDevice, m.st));
 
     // ---- chain tables
-    d.ks = dalloc<int>(MAXC);
-    d.A = dalloc<int>((size_t)MAXC * kcap);
-    d.bA = dalloc<double>((size_t)MAXC * kcap);
-    d.coef0 = dalloc<double>(MAXC);
-    d.coef0_level = dalloc<double>(1);
-    d.Anew = dalloc<int>((size_t)MAXC * kcap);
-    d.hist = dalloc<int>((size_t)MAXC * MAX_HIST * kcap);
-    d.l = dalloc<int>(MAXC);
-    d.done = dalloc<int>(MAXC);
-    d.tie = dalloc<int>(MAXC);
-    d.betaD = dalloc<double>((size_t)C * d.pstride);
-    d.XA = dalloc<double>((size_t)C * n * d.ldA);
-    d.XB = family_ == FAM_COX ? dalloc<double>((size_t)C * n * d.ldA) : nullptr;
-    d.vec = dalloc<double>((size_t)C * NVEC * n);
-    d.Smat = dalloc<double>((size_t)C * 2 * d.ldA * d.ldA);
+    d.ks = dalloc<int>(m.st, MAXC);
+    d.A = dalloc<int>(m.st, (size_t)MAXC * kcap);
+    d.bA = dalloc<double>(m.st, (size_t)MAXC * kcap);
+    d.coef0 = dalloc<double>(m.st, MAXC);
+    d.coef0_level = dalloc<double>(m.st, 1);
+    d.Anew = dalloc<int>(m.st, (size_t)MAXC * kcap);
+    d.hist = dalloc<int>(m.st, (size_t)MAXC * MAX_HIST * kcap);
+    d.l = dalloc<int>(m.st, MAXC);
+    d.done = dalloc<int>(m.st, MAXC);
+    d.tie = dalloc<int>(m.st, MAXC);
+    d.tie_acc = dalloc<int>(m.st, MAXC);
+    d.n_active = dalloc<int>(m.st, 1);
+    d.betaD = dalloc<double>(m.st, (size_t)C * d.pstride);
+    d.XA = dalloc<double>(m.st, (size_t)C * n * d.ldA);
+    d.XB = family_ == FAM_COX ? dalloc<double>(m.st, (size_t)C * n * d.ldA) : nullptr;
+    d.vec = dalloc<double>(m.st, (size_t)C * NVEC * n);
+    d.Smat = dalloc<double>(m.st, (size_t)C * 2 * d.ldA * d.ldA);
     CUDA_CHECK(cudaMemsetAsync(d.ks, 0, MAXC * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.A, 0, (size_t)MAXC * kcap * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.bA, 0, (size_t)MAXC * kcap * 8, m.st));
@@ -529,12 +604,14 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     CUDA_CHECK(cudaMemsetAsync(d.l, 0, MAXC * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.done, 0, MAXC * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.tie, 0, MAXC * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.tie_acc, 0, MAXC * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.betaD, 0, (size_t)C * d.pstride * 8, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.XA, 0, (size_t)C * n * d.ldA * 8, m.st));
 
     // ---- x_j.x_j over each chain's train rows (utilities.cpp:153-165, Metric.h:108-129); gaussian only
     if (family_ == FAM_LM) {
-        d.xtx = dalloc<double>((size_t)C * d.pstride);
+        d.xtx = dalloc<double>(m.st, (size_t)C * d.pstride);
         std::vector<double> ind((size_t)m.npad * d.FS, 0.0);
         for (int c = 0; c < C; c++)
             for (int r = 0; r < ntrain[c]; r++) ind[(size_t)rows[(size_t)c * n + r] * d.FS + c] = 1.0;
@@ -572,26 +649,25 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
                 for (int i = 0; i < n; i++) lf[i] = m.hy[i] < 1.0 ? 0.0 : std::lgamma(std::floor(m.hy[i]) + 1.0);
             }
         }
-        m.lfact = dalloc<double>(n);
+        m.lfact = dalloc<double>(m.st, n);
         CUDA_CHECK(cudaMemcpyAsync(m.lfact, lf.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
         CUDA_CHECK(cudaStreamSynchronize(m.st));
     }
-    m.loss_scratch = dalloc<double>((size_t)2 * MAXC * 2 * n);
-    m.loss_out = dalloc<double>(2 * MAXC);
+    m.loss_scratch = dalloc<double>(m.st, (size_t)2 * MAXC * 2 * n);
+    m.loss_out = dalloc<double>(m.st, 2 * MAXC);
     m.n_always = (int)always_select.size();
     if (m.n_always) {
-        m.always = dalloc<int>(m.n_always);
+        m.always = dalloc<int>(m.st, m.n_always);
         CUDA_CHECK(cudaMemcpyAsync(m.always, always_select.data(), (size_t)m.n_always * 4, cudaMemcpyHostToDevice, m.st));
     }
     m.cstride = std::max<long long>(2LL * kcap + 16, ((long long)p / 8192 + 2) * std::min(kcap, TOPK_LMAX));
-    m.ck0 = dalloc<double>((size_t)C * m.cstride);
-    m.ck1 = dalloc<double>((size_t)C * m.cstride);
-    m.ci0 = dalloc<int>((size_t)C * m.cstride);
-    m.ci1 = dalloc<int>((size_t)C * m.cstride);
-    if (m.h_A) cudaFreeHost(m.h_A);
-    if (m.h_bA) cudaFreeHost(m.h_bA);
-    CUDA_CHECK(cudaMallocHost(&m.h_A, (size_t)MAXC * kcap * sizeof(int)));
-    CUDA_CHECK(cudaMallocHost(&m.h_bA, (size_t)MAXC * kcap * sizeof(double)));
+    m.ck0 = dalloc<double>(m.st, (size_t)C * m.cstride);
+    m.ck1 = dalloc<double>(m.st, (size_t)C * m.cstride);
+    m.ci0 = dalloc<int>(m.st, (size_t)C * m.cstride);
+    m.ci1 = dalloc<int>(m.st, (size_t)C * m.cstride);
+    m.ctx->reserve_support((size_t)MAXC * kcap);
+    m.h_A = m.ctx->h_A;
+    m.h_bA = m.ctx->h_bA;
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     S_ = d.S;
     m.chains_ready = true;
@@ -603,7 +679,8 @@ static inline int sweep_epi(int family)
     return family == FAM_LM ? EPI_SACR_LM : (family == FAM_COX ? EPI_SACR_COX : EPI_SACR_GLM);
 }
 
-void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out)
+void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out,
+                       const std::vector<LossJob> *jobs, std::vector<double> *loss_out)
 {
     Impl &m = *d_;
     if (!m.chains_ready) throw EngineError{"run_batch before setup_chains"};
@@ -622,52 +699,72 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         cmax = std::max(cmax, chains[i]);
     }
     if (new_path_step && chains[0] != 0) throw EngineError{"a new path step must include the full-data chain"};
+    LossDesc ld{};
+    if (jobs) {
+        if ((int)jobs->size() > 2 * MAXC) throw EngineError{"too many loss jobs"};
+        ld.njobs = (int)jobs->size();
+        for (int i = 0; i < ld.njobs; i++) {
+            ld.chain[i] = (*jobs)[i].chain;
+            ld.kind[i] = (*jobs)[i].kind;
+            ld.fold[i] = (*jobs)[i].fold;
+        }
+    }
     const int mode = sweep_mode(family_), epi = sweep_epi(family_);
     const double vec_bytes = 8.0 * d.n * b.nch * (mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 4)) + 8.0 * d.p * b.nch;
 
     int sp = m.span_begin(4);
     launch_chain_begin(d, b, m.st);
     m.span_end(sp);
-    stats_.kernel_launches++;
-    int iters = 0;
-    for (int it = 1; it <= d.max_iter; it++) {
-        sp = m.span_begin(1);
-        launch_dual_sweep(d, mode, m.st);
-        m.span_end(sp);
-        sp = m.span_begin(2);
-        launch_finish(d, mode, epi, b, nullptr, m.st);
-        m.span_end(sp);
-        if (m.n_always) launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
-        sp = m.span_begin(3);
-        launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1, d.Anew + (size_t)cmin * d.kcap,
-                    d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st);
-        m.span_end(sp);
-        sp = m.span_begin(4);
-        launch_chain_fit(d, b, m.st);
-        m.span_end(sp);
-        CUDA_CHECK(cudaMemcpyAsync(m.h_done, d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaMemcpyAsync(m.h_tie, d.tie, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));
-        iters = it;
-        stats_.n_sweeps++;
-        stats_.sweep_bytes += 8.0 * d.n * d.p + vec_bytes;
-        stats_.kernel_launches += 4 + (m.n_always ? 1 : 0);
-        bool all = true;
-        for (int i = 0; i < b.nch; i++) {
-            all = all && m.h_done[b.chain[i]];
-            stats_.n_boundary_ties += m.h_tie[b.chain[i]];
+    long long launches = 1;
+    // PDAS iterations are enqueued speculatively: the kernels of an iteration return at once when every chain of the
+    // batch has already met the stopping rule (Dev::gate), so the host only synchronises once per group.  PDAS needs
+    // 2-4 iterations per warm-started fit; the first group covers that, later groups are shorter.
+    d.gate = d.n_active;
+    int enq = 0;
+    bool all = false;
+    while (!all && enq < d.max_iter) {
+        const int group = std::min(enq == 0 ? 3 : 2, d.max_iter - enq);
+        for (int q = 0; q < group; q++) {
+            sp = m.span_begin(1);
+            launch_dual_sweep(d, mode, m.st);
+            m.span_end(sp);
+            sp = m.span_begin(2);
+            launch_finish(d, mode, epi, b, nullptr, m.st);
+            m.span_end(sp);
+            if (m.n_always)
+                launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
+            sp = m.span_begin(3);
+            launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1,
+                        d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st,
+                        d.gate);
+            m.span_end(sp);
+            sp = m.span_begin(4);
+            launch_chain_fit(d, b, m.st);
+            m.span_end(sp);
         }
-        if (all) break;
+        enq += group;
+        // results are enqueued behind the group; they are only used if the batch turns out to be finished
+        if (jobs) {
+            sp = m.span_begin(5);
+            launch_losses(d, ld, m.testrows, m.ntest, m.y, m.w, m.lfact, m.loss_scratch, m.loss_out, m.st);
+            m.span_end(sp);
+            CUDA_CHECK(cudaMemcpyAsync(m.h_loss, m.loss_out, ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(m.h_done, d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_l, d.l, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_tie, d.tie_acc, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_coef0, d.coef0, MAXC * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_A, d.A, (size_t)MAXC * d.kcap * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_bA, d.bA, (size_t)MAXC * d.kcap * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        all = true;
+        for (int i = 0; i < b.nch; i++) all = all && m.h_done[b.chain[i]];
     }
-    (void)iters;
-    CUDA_CHECK(cudaMemcpyAsync(m.h_l, d.l, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(m.h_coef0, d.coef0, MAXC * sizeof(double), cudaMemcpyDeviceToHost, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(m.h_A, d.A, (size_t)MAXC * d.kcap * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(m.h_bA, d.bA, (size_t)MAXC * d.kcap * sizeof(double), cudaMemcpyDeviceToHost, m.st));
-    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    d.gate = nullptr;
     m.collect_spans();
     out.T = T;
     out.nchains = b.nch;
+    int executed = 0;  // iterations that actually ran (the rest of the last group returned at the gate)
     for (int i = 0; i < b.nch; i++) {
         const int c = b.chain[i];
         out.chain_ids[i] = c;
@@ -675,10 +772,18 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         out.coef0[i] = m.h_coef0[c];
         out.A[i].assign(m.h_A + (size_t)c * d.kcap, m.h_A + (size_t)c * d.kcap + T);
         out.bA[i].assign(m.h_bA + (size_t)c * d.kcap, m.h_bA + (size_t)c * d.kcap + T);
-        stats_.n_pdas_iters += std::min(m.h_l[c], d.max_iter);
+        const int iters = std::min(m.h_l[c], d.max_iter);
+        stats_.n_pdas_iters += iters;
+        stats_.n_boundary_ties += m.h_tie[c];
+        executed = std::max(executed, iters);
     }
+    launches += (long long)executed * (4 + (m.n_always ? 1 : 0)) + (jobs ? 1 : 0);
+    stats_.n_sweeps += executed;
+    stats_.sweep_bytes += executed * (8.0 * d.n * d.p + vec_bytes);
+    stats_.kernel_launches += launches;  // launches that did work; gated no-op launches are not counted
     stats_.n_fits += b.nch;
     stats_.n_batches++;
+    if (jobs && loss_out) loss_out->assign(m.h_loss, m.h_loss + ld.njobs);
 }
 
 void Engine::losses(const std::vector<LossJob> &jobs, std::vector<double> &out)

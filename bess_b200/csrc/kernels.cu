@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(SWEEP_NT) dual_sweep_kernel(const Dev d)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tile = reinterpret_cast<double *>(smem_raw);  // [2][NV][RC][FT]
     __shared__ __align__(8) uint64_t bar[2];
+    if (d.gate && *d.gate == 0) return;  // every chain of the batch already stopped (speculative launch)
 
     const int tid = threadIdx.x;
     const int s = blockIdx.y;
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const Dev d, int mode, cons
 {
     const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
     if (j >= d.p) return;
+    if (d.gate && *d.gate == 0) return;
     const int c = b.chain[blockIdx.y];  // chain id == slot in the sweep vectors
     const int NQ = mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 5);
     const int FT = d.FS;
@@ -439,17 +441,18 @@ void launch_finish(const Dev &d, int mode, int epi, const BatchDesc &b, double *
 }
 
 // always_select -> DBL_MAX (utilities.cpp:190-199)
-__global__ void pin_kernel(double *vals, long long stride, int nch, const int *idx, int nidx)
+__global__ void pin_kernel(double *vals, long long stride, int nch, const int *idx, int nidx, const int *gate)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nidx * nch) return;
+    if (gate && *gate == 0) return;
     vals[(size_t)(i / nidx) * stride + idx[i % nidx]] = DBL_MAX;
 }
-void launch_pin(const Dev &, double *vals, long long stride, int nch, const int *idx, int nidx, cudaStream_t st)
+void launch_pin(const Dev &d, double *vals, long long stride, int nch, const int *idx, int nidx, cudaStream_t st)
 {
     if (nidx <= 0) return;
     const int tot = nidx * nch;
-    pin_kernel<<<(tot + 255) / 256, 256, 0, st>>>(vals, stride, nch, idx, nidx);
+    pin_kernel<<<(tot + 255) / 256, 256, 0, st>>>(vals, stride, nch, idx, nidx, d.gate);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -463,10 +466,11 @@ __global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__re
                                                               const int *__restrict__ idx_in, long long in_stride,
                                                               int n_in, int k, int slice_len, double *keys_out,
                                                               int *idx_out, long long out_stride, int *final_out,
-                                                              int final_ld, int *tie)
+                                                              int final_ld, int *tie, const int *gate)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    if (gate && *gate == 0) return;
     __shared__ int hist[256];
     __shared__ unsigned long long sh_prefix;
     __shared__ int sh_krem, sh_neq;
@@ -601,7 +605,7 @@ __global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__re
 }
 
 void launch_topk(const double *vals, long long stride, int n_in, int k, int nch, int *out_idx, int out_ld, int *tie,
-                 double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st)
+                 double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st, const int *gate)
 {
     if (k > n_in) throw EngineError{"top-k: k > number of candidates"};
     const double *kin = vals;
@@ -614,7 +618,7 @@ void launch_topk(const double *vals, long long stride, int n_in, int k, int nch,
             const size_t smem = (size_t)cur_n * 8;
             dim3 grid(1, nch);
             topk_slices_kernel<<<grid, TOPK_NT, smem, st>>>(kin, iin, in_stride, cur_n, k, cur_n, nullptr, nullptr, 0,
-                                                            out_idx, out_ld, tie);
+                                                            out_idx, out_ld, tie, gate);
             CUDA_CHECK(cudaGetLastError());
             return;
         }
@@ -636,7 +640,7 @@ void launch_topk(const double *vals, long long stride, int n_in, int k, int nch,
         if ((long long)out_n > cstride) throw EngineError{"top-k: candidate scratch too small"};
         dim3 grid(nsl, nch);
         topk_slices_kernel<<<grid, TOPK_NT, (size_t)slice * 8, st>>>(kin, iin, in_stride, cur_n, k, slice, ko, io,
-                                                                    cstride, nullptr, 0, nullptr);
+                                                                    cstride, nullptr, 0, nullptr, gate);
         CUDA_CHECK(cudaGetLastError());
         kin = ko;
         iin = io;
@@ -1177,6 +1181,8 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, con
     __syncthreads();
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0 && b.new_path_step) *d.coef0_level = level;
+        if (blockIdx.x == 0) *d.n_active = b.nch;
+        d.tie_acc[c] = 0;
         if (!(c == 0 && b.new_path_step && d.warm)) d.coef0[c] = level;
         d.ks[c] = ks;
         d.l[c] = 0;
@@ -1268,6 +1274,8 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
         d.ks[c] = T;
         d.coef0[c] = coef0;
         d.done[c] = finished;
+        d.tie_acc[c] += d.tie[c];
+        if (finished) atomicSub(d.n_active, 1);
     }
     if (finished) return;
     chain_gradient(d, cx, slopes, T, coef0, sm);

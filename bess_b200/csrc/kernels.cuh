@@ -43,7 +43,11 @@ struct Dev {
     int *hist;          // [MAXC][MAX_HIST][kcap]  A_list (Algorithm.h:141-143)
     int *l;             // [MAXC]
     int *done;          // [MAXC]
-    int *tie;           // [MAXC] boundary-tie counter of the last top-k
+    int *tie;           // [MAXC] boundary-tie flag of the last top-k
+    int *tie_acc;       // [MAXC] boundary ties consumed by the chain's fits since chain_begin
+    int *n_active;      // [1] chains of the running batch that have not met the stopping rule yet
+    const int *gate;    // == n_active while a batch runs: every per-iteration kernel returns at once when *gate == 0,
+                        // so iterations can be enqueued speculatively without a host round trip; nullptr = no gate
     double *betaD;      // [MAXC][p] dense beta (for the sacrifice)
     double *XA;         // [MAXC][n][ldA] gathered active columns (+ intercept / working response columns)
     double *XB;         // [MAXC][n][ldA] cox: risk-set means
@@ -79,9 +83,11 @@ struct LossDesc {
 void launch_dual_sweep(const Dev &d, int mode, cudaStream_t st);
 void launch_finish(const Dev &d, int mode, int epi, const BatchDesc &b, double *raw_out, cudaStream_t st);
 void launch_pin(const Dev &d, double *vals, long long stride, int nch, const int *idx, int nidx, cudaStream_t st);
+// `gate`: see Dev::gate
 // exact top-k of `vals` ([nch][stride], first n_in of each row) -> out_idx [nch][out_ld] ascending; uses ping-pong scratch
 void launch_topk(const double *vals, long long stride, int n_in, int k, int nch, int *out_idx, int out_ld, int *tie,
-                 double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st);
+                 double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st,
+                 const int *gate = nullptr);
 void launch_chain_begin(const Dev &d, const BatchDesc &b, cudaStream_t st);
 void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st);
 void launch_losses(const Dev &d, const LossDesc &jobs, const int *testrows, const int *ntest, const double *y,

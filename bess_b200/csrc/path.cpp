@@ -84,13 +84,12 @@ struct Driver {
     Eval step(int T, Eval *last_fold = nullptr)
     {
         BatchResult br;
-        eng.run_batch(T, all_chains, /*new_path_step=*/true, br);
         std::vector<LossJob> jobs;
         jobs.push_back({0, 0, 0});
         for (int k = 0; k < K; k++) jobs.push_back({1 + k, 1, k});
         if (last_fold && K > 0) jobs.push_back({K, 0, 0});
         std::vector<double> v;
-        eng.losses(jobs, v);
+        eng.run_batch(T, all_chains, /*new_path_step=*/true, br, &jobs, &v);
         Eval e;
         e.T = T;
         e.l = br.l[0];
@@ -121,29 +120,25 @@ struct Driver {
     {
         if (K == 0) return e.ic;
         BatchResult br;
-        eng.run_batch(e.T, fold_chains, /*new_path_step=*/false, br);
         std::vector<LossJob> jobs;
         for (int k = 0; k < K; k++) jobs.push_back({1 + k, 1, k});
         std::vector<double> v;
-        eng.losses(jobs, v);
+        eng.run_batch(e.T, fold_chains, /*new_path_step=*/false, br, &jobs, &v);
         return mean_of(v, 0, (size_t)K);
     }
 
-    // path.cpp:76-110 / :330-343
-    void denormalise(const Eval &e, std::vector<double> &beta, double &coef0) const
+    // path.cpp:76-110 / :330-343.  bA_out: de-normalised coefficients on the support e.A
+    void denormalise(const Eval &e, std::vector<double> &bA_out, double &coef0) const
     {
-        beta.assign((size_t)p, 0.0);
+        bA_out.assign(e.bA.begin(), e.bA.end());
         coef0 = e.coef0;
-        if (!a.is_normal) {
-            for (size_t i = 0; i < e.A.size(); i++) beta[(size_t)e.A[i]] = e.bA[i];
-            return;
-        }
+        if (!a.is_normal) return;
         const double sn = std::sqrt((double)n);
         double dot = 0.0;
         for (size_t i = 0; i < e.A.size(); i++) {
             const int j = e.A[i];
             const double b = sn * e.bA[i] / eng.x_norm()[(size_t)j];
-            beta[(size_t)j] = b;
+            bA_out[i] = b;
             dot += b * eng.x_mean()[(size_t)j];
         }
         if (a.data_type == 1) coef0 = eng.y_mean() - dot;
@@ -166,7 +161,8 @@ void sequential_path(Driver &dr, BessResult &out, Eval &best)
         std::vector<double> b;
         double c0;
         dr.denormalise(e, b, c0);
-        out.beta_all.push_back(std::move(b));
+        out.A_all.push_back(e.A);
+        out.bA_all.push_back(std::move(b));
         out.coef0_all.push_back(c0);
         out.train_loss_all.push_back(e.train_loss);
         out.ic_all.push_back(e.ic);
@@ -310,26 +306,20 @@ void bess_run(const BessArgs &a, BessResult &out)
     if (a.path_type == 1) sequential_path(dr, out, best);
     else gs_path(dr, out, best);
 
-    std::vector<double> beta;
+    std::vector<double> bA;
     double coef0;
-    dr.denormalise(best, beta, coef0);
+    dr.denormalise(best, bA, coef0);
     out.coef0 = coef0;
     out.train_loss = best.train_loss;
     out.ic = best.ic;
     out.lambda = 0.0;
     out.chosen_s = best.T;
-    if (a.is_screening) {
-        // bess.cpp:186-209
-        out.beta.assign((size_t)a.p, 0.0);
-        for (size_t i = 0; i < out.screening_A.size(); i++) out.beta[(size_t)out.screening_A[i]] = beta[i];
-        for (auto &b : out.beta_all) {
-            std::vector<double> full((size_t)a.p, 0.0);
-            for (size_t i = 0; i < out.screening_A.size(); i++) full[(size_t)out.screening_A[i]] = b[i];
-            b.swap(full);
-        }
-    } else {
-        out.beta = std::move(beta);
-    }
+    // scatter to the ORIGINAL column numbering (un-screen: bess.cpp:186-209)
+    out.beta.assign((size_t)a.p, 0.0);
+    auto orig = [&](int j) { return a.is_screening ? out.screening_A[(size_t)j] : j; };
+    for (size_t i = 0; i < best.A.size(); i++) out.beta[(size_t)orig(best.A[i])] = bA[i];
+    for (auto &A : out.A_all)
+        for (int &j : A) j = orig(j);
     out.stats = eng.stats();
     eng.profile(out.prof_ms, out.prof_n);
     out.sweep_splits = eng.sweep_splits();

@@ -51,7 +51,10 @@ struct BessResult {
     int chosen_s = 0;
     // per-level trace (sequential path; normalised scale like beta_all before de-normalisation is NOT kept:
     // these are de-normalised, as the R build returns them, path.cpp:76-123)
-    std::vector<std::vector<double>> beta_all;
+    // kept sparse: support (ORIGINAL column numbering, ascending) + de-normalised coefficients per level; expanded
+    // to dense rows only on request (bess_b200_trace)
+    std::vector<std::vector<int>> A_all;
+    std::vector<std::vector<double>> bA_all;
     std::vector<double> coef0_all, train_loss_all, ic_all;
     std::vector<int> s_all, l_all;
     EngineStats stats;
