@@ -31,3 +31,25 @@ def assert_same_support(beta_a, beta_b):
     sa = np.nonzero(beta_a)[0]
     sb = np.nonzero(beta_b)[0]
     assert sa.tolist() == sb.tolist(), f"support differs: {sa.tolist()} vs {sb.tolist()}"
+
+
+# The five BASELINE configs at full size (tests/golden/full/*.npz, made by tests/golden/make_full_size.py from the real
+# reference).  name -> family, n, p, k, path_type, is_cv, K, ic_type, s_min, s_max, screening_size, data seed
+FULL_CONFIGS = {
+    "c1": ("gaussian", 500, 1000, 10, 1, False, 5, 3, 1, 20, 0, 1),
+    "c1cv": ("gaussian", 500, 1000, 10, 1, True, 10, 1, 1, 20, 0, 1),
+    "c2": ("binomial", 2000, 20000, 20, 2, True, 10, 1, 1, 263, 0, 2),
+    "c3": ("poisson", 5000, 50000, 30, 1, False, 5, 3, 1, 40, 0, 3),
+    "c4": ("cox", 2000, 10000, 15, 1, True, 5, 1, 1, 30, 0, 4),
+    "c5": ("gaussian", 1000, 500000, 10, 1, True, 10, 1, 1, 20, 5000, 5),
+}
+
+
+def full_checksum(d):
+    """Cheap fingerprint of the regenerated inputs (guards against a numpy RNG stream change)."""
+    return np.array([float(d.x[::7, ::13].sum()), float(np.abs(d.x[-1]).sum()), float(d.y.sum())])
+
+
+def load_full_golden(name):
+    path = os.path.join(GOLDEN_DIR, "full", name + ".npz")
+    return dict(np.load(path)) if os.path.exists(path) else None

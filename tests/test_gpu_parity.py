@@ -9,7 +9,8 @@ import pytest
 
 from oracle import pdas_oracle as orc
 from oracle import ref as refso
-from tests.helpers import RTOL, assert_same_support, golden_names, load_golden, rel_err
+from tests.helpers import (FULL_CONFIGS, RTOL, assert_same_support, full_checksum, golden_names, load_full_golden,
+                           load_golden, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -236,6 +237,37 @@ def test_config1_against_the_real_reference():
         r = refso.pywrap_bess(d.x, d.y, 1, w, True, 1, 1, 20, 2, 1, True, ic, is_cv, 10, seq, 1, 20, False, 1, cv_seed=123)
         out = cbess.fit(d.x, d.y, 1, w, True, 1, 1, 20, 2, 1, True, ic, is_cv, 10, seq, 1, 20, False, 1, cv_seed=123)
         _check_final(out, r)
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c1cv", "c2", "c3", "c4", "c5"])
+def test_full_size_baseline_configs_against_reference_golden(cfg):
+    """All five BASELINE configs at FULL size against the outputs of the real reference (tests/golden/full/<cfg>.npz,
+    made by tests/golden/make_full_size.py: 1-18 CPU-minutes per config on the reference).  The design is regenerated
+    from its seed (checksummed); the CV folds are the ones the reference drew.  Bar: identical support and chosen s
+    (and screening set), beta / coef0 / train_loss / ic within 1e-8 relative."""
+    from bess_b200 import cbess
+    from bess_b200.gen_data import gen_data
+    g = load_full_golden(cfg)
+    if g is None:
+        pytest.skip(f"tests/golden/full/{cfg}.npz not generated")
+    fam, n, p, k, path_type, is_cv, K, ic_type, s_min, s_max, scr, seed = FULL_CONFIGS[cfg]
+    model_type, data_type = FAM[fam]
+    d = gen_data(n, p, fam, k, seed=seed)
+    assert np.array_equal(full_checksum(d), g["checksum"]), "regenerated inputs differ from the ones the golden was made on"
+    w = np.ones(n)
+    seq = np.arange(s_min, s_max + 1) if path_type == 1 else np.arange(1, 2)
+    out = cbess.fit(d.x, d.y, data_type, w, True, 1, model_type, 20, 2, path_type, True, ic_type, is_cv, K, seq, s_min,
+                    s_max, scr > 0, max(scr, 1), fold_of_row=g["fold_of_row"] if is_cv else None, want_trace=False)
+    sup = np.nonzero(out["beta"])[0]
+    assert sup.tolist() == g["support"].tolist()
+    assert out["s"] == g["support"].size
+    assert rel_err(out["beta"][sup], g["beta_support"]) < RTOL
+    assert abs(out["coef0"] - float(g["coef0"])) <= RTOL * max(1.0, abs(float(g["coef0"])))
+    assert _close(out["train_loss"], float(g["train_loss"]))
+    assert _close(out["ic"], float(g["ic"]))
+    assert out["stats"]["n_boundary_ties"] == 0
+    if scr > 0:
+        assert out["screening_A"].tolist() == g["screening_A"].tolist()
 
 
 def test_full_size_config5_properties():
