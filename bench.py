@@ -186,13 +186,14 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
-    for _ in range(args.warmup):
-        step()
+    # clocks are sampled from the warm-up to the end of the e2e region (the timed region alone lasts well under a second,
+    # shorter than nvidia-smi's start-up); every sample is taken under load
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
     ms, out = timed(args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     fits_per_step = 220
     value = fits_per_step * args.steps / (ms / 1e3)
 
@@ -203,6 +204,9 @@ def run_ours(args):
     step(xh)
     e2e_steps = max(1, min(args.steps, 5))
     ms_e2e, out_e = timed(e2e_steps, xh)
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + e2e region"
     e2e_val = fits_per_step * e2e_steps / (ms_e2e / 1e3)
     st = out["stats"]
     d2h = st["n_batches"] * (16 * SMAX * 12 + 16 * 12) + st["n_sweeps"] * 16 * 8 + SCREEN * 4 + P_COLS * 0
@@ -210,8 +214,9 @@ def run_ours(args):
 
     # ---- roofline of the dual-sweep kernel: CUDA events around every launch on the engine's own stream, over a
     # profiled repeat of the timed region (event recording costs ~1 ms per call, so it is kept out of `value`)
-    prof_ms = np.zeros(6)
-    prof_n = np.zeros(6)
+    ncat = len(cbess.PROF_CATS)
+    prof_ms = np.zeros(ncat)
+    prof_n = np.zeros(ncat)
     big_bytes = pdas_bytes = 0.0
     for _ in range(args.steps):
         o = step(profile=True)
@@ -226,12 +231,20 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    sweep_ms = prof_ms[0] + prof_ms[1]
-    sweep_n = max(prof_n[0] + prof_n[1], 1)
+    cat = dict(zip(cbess.PROF_CATS, range(ncat)))
+    scr_ms, scr_n = prof_ms[cat["screen_sweep"]], max(prof_n[cat["screen_sweep"]], 1)
+    hbm_gbs = big_bytes / (scr_ms * 1e-3) / 1e9 if scr_ms > 0 else None
+    sweep_ms = scr_ms + prof_ms[cat["dual_sweep"]]
+    sweep_n = max(scr_n + prof_n[cat["dual_sweep"]], 1)
     achieved = (big_bytes + pdas_bytes) / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
-    hbm_ms = prof_ms[0]
-    hbm_gbs = big_bytes / (hbm_ms * 1e-3) / 1e9 if hbm_ms > 0 else None
-    total_kernel_ms = float(prof_ms.sum())
+    total_kernel_ms = float(prof_ms.sum() - prof_ms[cat["upload"]])
+    # DRAM traffic of the same kernel instantiation and grid, from the committed ncu --set full capture
+    traffic = traffic_src = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["screen_sweep_4GB"]
+        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    except Exception:
+        pass
 
     # ---- the p=500k PDAS dual sweep itself (config 5 with screening off, "C5b"): all 11 chains in one pass over X
     probe = None
@@ -266,11 +279,12 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(st["kernel_launches"] * args.steps),
             "roofline": {"bound": "hbm", "achieved": hbm_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": (hbm_gbs / peak) if hbm_gbs else None, "traffic": None,
-                         "kernel": "dual_sweep_kernel (HBM-streaming launches of the step: screening pass over the "
-                                   "4 GB design + normalisation/x_j.x_j passes)",
-                         "peak_source": peak_src, "launches_per_step": float(prof_n[0] / args.steps),
-                         "ms_per_step": float(hbm_ms / args.steps),
+                         "frac": (hbm_gbs / peak) if hbm_gbs else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "dual_sweep_kernel<FT=1,MODE_DH,CPT=2>: the marginal-utility sweep over the "
+                                   f"{N_ROWS} x {hi - lo} raw design (d = X^T y, h = (X.X)^T 1 in one pass)",
+                         "algorithmic_bytes_per_launch": float(big_bytes / scr_n),
+                         "peak_source": peak_src, "launches_per_step": float(scr_n / args.steps),
+                         "ms_per_launch": float(scr_ms / scr_n),
                          "all_dual_sweep_launches": {"achieved": achieved, "launches_per_step": float(sweep_n / args.steps),
                                                      "note": "incl. the ~50 L2-resident 40 MB PDAS sweeps per call"},
                          "kernel_ms_per_step": {k: float(v / args.steps) for k, v in zip(cbess.PROF_CATS, prof_ms)},
@@ -287,7 +301,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import BessB200Error, Ext, dp, ip
 
 
-PROF_CATS = ("setup_passes", "dual_sweep", "finish", "topk", "chain", "other")
+PROF_CATS = ("screen_sweep", "dual_sweep", "finish", "topk", "chain", "other", "normalize", "upload")
 
 
 def _d(a):
@@ -99,7 +99,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     ext.screening_A_out = _i(scrA)
     chosen = C.c_int(0)
     ext.chosen_s_out = C.pointer(chosen)
-    stats = np.zeros(24)
+    stats = np.zeros(32)
     ext.stats_out = _d(stats)
     ext.profile = 1 if profile else 0
     rc = lib.bess_b200_fit(xptr, n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal),
@@ -112,10 +112,10 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     out = dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, s=chosen.value,
                stats=dict(n_fits=int(stats[0]), n_pdas_iters=int(stats[1]), n_sweeps=int(stats[2]),
                           n_batches=int(stats[3]), n_boundary_ties=int(stats[4]), sweep_bytes=float(stats[5]),
-                          kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[20]),
-                          sweep_splits=int(stats[21]),
-                          prof_ms=dict(zip(PROF_CATS, stats[8:14].tolist())),
-                          prof_launches=dict(zip(PROF_CATS, [int(v) for v in stats[14:20]]))))
+                          kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[24]),
+                          sweep_splits=int(stats[25]), norm_bytes=float(stats[26]),
+                          prof_ms=dict(zip(PROF_CATS, stats[8:16].tolist())),
+                          prof_launches=dict(zip(PROF_CATS, [int(v) for v in stats[16:24]]))))
     if is_screening:
         out["screening_A"] = scrA[:int(screening_size)].copy()
     L = int(stats[7])

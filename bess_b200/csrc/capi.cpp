@@ -103,12 +103,13 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
                 ext->stats_out[5] = r.stats.sweep_bytes;
                 ext->stats_out[6] = (double)r.stats.kernel_launches;
                 ext->stats_out[7] = (double)r.s_all.size();
-                for (int q = 0; q < 6; q++) {
+                for (int q = 0; q < PROF_NCAT; q++) {
                     ext->stats_out[8 + q] = r.prof_ms[q];
-                    ext->stats_out[14 + q] = (double)r.prof_n[q];
+                    ext->stats_out[16 + q] = (double)r.prof_n[q];
                 }
-                ext->stats_out[20] = r.stats.big_sweep_bytes;
-                ext->stats_out[21] = (double)r.sweep_splits;
+                ext->stats_out[24] = r.stats.big_sweep_bytes;
+                ext->stats_out[25] = (double)r.sweep_splits;
+                ext->stats_out[26] = r.stats.norm_bytes;
             }
         }
         g_last = std::move(r);

@@ -1,0 +1,1083 @@
+// Chain kernels: the active-set side of one PDAS iteration (Algorithm::fit, /root/reference/src/Algorithm.h:154-170).
+//
+//   chain_begin_kernel   Algorithm::fit prologue (Algorithm.h:141-148) + gradient vectors of the first dual sweep.
+//   chain_fit_kernel     after the top-k: gather X_A (utilities.cpp:132-140), the family's primary_model_fit
+//                        (Algorithm.h:1131-1135 Lm / 1148-1204 Logistic / 1273-1322 Poisson / 1377-1490 Cox, iteration-exact),
+//                        scatter + cycle test (Algorithm.h:159-170) and the gradient vectors of the next sweep
+//                        (get_A prologues, Algorithm.h:1109 / 1223-1236 / 1338-1341 / 1579-1630).
+//
+// One thread-block CLUSTER of CL in {1,2,4,8} CTAs works on one chain.  The train rows are cut into CL contiguous
+// slices; everything per-row (gather, linear predictor, IRLS weights, gradient vectors) is slice-local, Gram/Hessian
+// matrices are accumulated per slice and reduced in a fixed order (bitwise reproducible), scalars are exchanged through
+// distributed shared memory, the risk-set scans of the Cox model carry their totals from slice to slice.  Rank 0 of the
+// cluster factors the (small) normal equations and broadcasts the solution.  CL = 1 (the k <= 20 configs) runs the very
+// same code with every cluster operation compiled to a no-op branch.
+#include <cooperative_groups.h>
+
+#include <cfloat>
+#include <cmath>
+
+#include "device_utils.cuh"
+#include "kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bess {
+
+constexpr int FIT_TILE_DOUBLES = 8192;  // 64 KB row tile for the Gram / panel of the blocked Cholesky
+constexpr int FIT_SMEM_MS = 64;         // normal equations up to 64 x 64 are factored in shared memory
+constexpr int CHOL_NB = 16;             // panel width of the blocked Cholesky (systems larger than FIT_SMEM_MS)
+
+struct FitSmem {
+    double *tile;     // FIT_TILE_DOUBLES
+    double *scratch;  // FIT_NT * 16
+    double *Ssm;      // FIT_SMEM_MS^2
+    double *b0, *b1, *rhs, *dg;  // ldA each
+    double *red;      // 40
+    double *xch;      // 2 * CLMAX: cluster scalar exchange (written remotely through DSMEM)
+};
+__device__ __forceinline__ FitSmem carve_fit_smem(unsigned char *raw, int ldA)
+{
+    FitSmem s;
+    double *p = reinterpret_cast<double *>(raw);
+    s.tile = p; p += FIT_TILE_DOUBLES;
+    s.scratch = p; p += FIT_NT * 16;
+    s.Ssm = p; p += FIT_SMEM_MS * FIT_SMEM_MS;
+    s.b0 = p; p += ldA;
+    s.b1 = p; p += ldA;
+    s.rhs = p; p += ldA;
+    s.dg = p; p += ldA;
+    s.red = p; p += 40;
+    s.xch = p; p += 2 * CLMAX;
+    return s;
+}
+size_t fit_smem_bytes(const Dev &d)
+{
+    return sizeof(double) *
+           ((size_t)FIT_TILE_DOUBLES + FIT_NT * 16 + FIT_SMEM_MS * FIT_SMEM_MS + 4 * (size_t)d.ldA + 40 + 2 * CLMAX);
+}
+
+// =====================================================================================================
+// cluster plumbing
+// =====================================================================================================
+struct Clu {
+    int CL, rank;
+    double *xch;
+    int phase;
+};
+__device__ __forceinline__ void clu_sync(const Clu &cl)
+{
+    if (cl.CL > 1) cg::this_cluster().sync();
+    else __syncthreads();
+}
+// Every thread of every CTA passes its CTA's value `local` (uniform inside a CTA); on return out[q] = value of rank q.
+// Two alternating slot sets: a CTA can only reach exchange t+2 after every CTA has passed the barrier of exchange t+1,
+// i.e. after everybody has finished reading the slots of exchange t.
+__device__ __forceinline__ void clu_allgather(Clu &cl, double local, double (&out)[CLMAX])
+{
+#pragma unroll
+    for (int q = 0; q < CLMAX; q++) out[q] = 0.0;
+    if (cl.CL == 1) {
+        out[0] = local;
+        return;
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    double *slot = cl.xch + cl.phase * CLMAX;
+    if ((int)threadIdx.x < cl.CL) {
+        double *remote = cluster.map_shared_rank(slot, threadIdx.x);
+        remote[cl.rank] = local;
+    }
+    cluster.sync();
+#pragma unroll
+    for (int q = 0; q < CLMAX; q++)
+        if (q < cl.CL) out[q] = slot[q];
+    cl.phase ^= 1;
+}
+__device__ __forceinline__ double clu_allsum(Clu &cl, double local)
+{
+    if (cl.CL == 1) return local;
+    double t[CLMAX];
+    clu_allgather(cl, local, t);
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < CLMAX; q++)
+        if (q < cl.CL) s += t[q];
+    return s;
+}
+
+struct ChainCtx {
+    int c, nt, T, off, m;  // m = number of columns of the design incl. intercept
+    int rb, re;            // this CTA's slice of the chain's (compacted) train rows
+    double *XA;
+    const double *y, *w;
+    double *v[NVEC];
+    double *S;             // where rank 0 factors the normal equations (smem or global), leading dim lds
+    int lds;
+    double *Sp0;           // cluster mode: partial-Gram buffers of the chain, rank q at Sp0 + q * sp_stride, [nmat][ldA*ldA]
+    size_t sp_stride;
+    double *Sfin;          // the chain's global matrices [2][ldA*ldA] (reduced normal equations / Cox second Gram)
+    double *cw;            // exchange vectors of the chain [CLMAX][4][ldA]
+    int ldA;
+};
+__device__ __forceinline__ double *cw_slot(const ChainCtx &cx, int rank, int s) { return cx.cw + (size_t)(rank * 4 + s) * cx.ldA; }
+
+// =====================================================================================================
+// Gram: S (mm x mm, both triangles) = sum_{r in [r0,r1)} wt[r] * V[r][a] * V[r][b]; V row-major, ld ldv, global memory
+// =====================================================================================================
+__device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
+                           const FitSmem &sm)
+{
+    const int tid = threadIdx.x;
+    const int mb = (mm + 3) >> 2, mp = mb * 4;
+    const int nblk = mb * (mb + 1) / 2;
+    int R = FIT_TILE_DOUBLES / (mp + 1);
+    if (R > 512) R = 512;
+    double *tile = sm.tile;
+    double *tw = sm.tile + (size_t)R * mp;
+    const int nsl = nblk >= FIT_NT ? 1 : FIT_NT / nblk;
+    const int nbatch = nsl > 1 ? 1 : (nblk + FIT_NT - 1) / FIT_NT;
+    for (int batch = 0; batch < nbatch; batch++) {
+        int blk, sl;
+        bool valid;
+        if (nsl > 1) {
+            blk = tid % nblk;
+            sl = tid / nblk;
+            valid = sl < nsl;
+        } else {
+            blk = batch * FIT_NT + tid;
+            sl = 0;
+            valid = blk < nblk;
+        }
+        int bi = 0, bj = 0;
+        if (valid) {
+            bi = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
+            while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+            while (bi * (bi + 1) / 2 > blk) bi--;
+            bj = blk - bi * (bi + 1) / 2;
+        }
+        double acc[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) acc[e] = 0.0;
+        for (int rb = r0; rb < r1; rb += R) {
+            const int rc = min(R, r1 - rb);
+            const int tot = rc * mp;
+            __syncthreads();
+            // stage rc rows (zero-padded to mp columns): flattened and unrolled so 4 loads are in flight per thread
+            for (int e0 = tid; e0 < tot; e0 += 4 * FIT_NT) {
+                double val[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int e = e0 + q * FIT_NT;
+                    val[q] = 0.0;
+                    if (e < tot) {
+                        const int r = e / mp, cidx = e - r * mp;
+                        if (cidx < mm) val[q] = V[(size_t)(rb + r) * ldv + cidx];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int e = e0 + q * FIT_NT;
+                    if (e < tot) tile[e] = val[q];
+                }
+            }
+            for (int r = tid; r < rc; r += FIT_NT) tw[r] = wt ? wt[rb + r] : 1.0;
+            __syncthreads();
+            if (valid) {
+                for (int r = sl; r < rc; r += nsl) {
+                    const double w = tw[r];
+                    const double *ta = tile + r * mp + 4 * bi;
+                    const double *tb = tile + r * mp + 4 * bj;
+                    const double2 a01 = *reinterpret_cast<const double2 *>(ta);
+                    const double2 a23 = *reinterpret_cast<const double2 *>(ta + 2);
+                    const double2 b01 = *reinterpret_cast<const double2 *>(tb);
+                    const double2 b23 = *reinterpret_cast<const double2 *>(tb + 2);
+                    const double a[4] = {a01.x * w, a01.y * w, a23.x * w, a23.y * w};
+                    const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int qa = 0; qa < 4; qa++)
+#pragma unroll
+                        for (int qb = 0; qb < 4; qb++) acc[qa * 4 + qb] = fma(a[qa], bb[qb], acc[qa * 4 + qb]);
+                }
+            }
+        }
+        if (nsl > 1) {
+            __syncthreads();
+            if (valid) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) sm.scratch[(size_t)(sl * nblk + blk) * 16 + e] = acc[e];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nblk * 16; idx += FIT_NT) {
+                const int bk = idx >> 4, e = idx & 15;
+                double v = 0.0;
+                for (int q = 0; q < nsl; q++) v += sm.scratch[(size_t)(q * nblk + bk) * 16 + e];
+                int ci = (int)((sqrt(8.0 * (double)bk + 1.0) - 1.0) * 0.5);
+                while ((ci + 1) * (ci + 2) / 2 <= bk) ci++;
+                while (ci * (ci + 1) / 2 > bk) ci--;
+                const int cj = bk - ci * (ci + 1) / 2;
+                const int a = 4 * ci + (e >> 2), bcol = 4 * cj + (e & 3);
+                if (a < mm && bcol < mm && a >= bcol) {
+                    S[(size_t)a * lds + bcol] = v;
+                    S[(size_t)bcol * lds + a] = v;
+                }
+            }
+        } else if (valid) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int a = 4 * bi + (e >> 2), bcol = 4 * bj + (e & 3);
+                if (a < mm && bcol < mm && a >= bcol) {
+                    S[(size_t)a * lds + bcol] = acc[e];
+                    S[(size_t)bcol * lds + a] = acc[e];
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// =====================================================================================================
+// Cholesky solves.  The systems are "bordered": rows 0..mm-1 hold the SPD matrix (lower triangle used), row mm holds the
+// right-hand side.  Factoring the bordered matrix leaves z = L^{-1} rhs in row mm (forward substitution for free);
+// a back substitution then gives x = S^{-1} rhs.
+// (The reference uses Eigen's pivoted ldlt()/colPivHouseholderQr(); for the SPD, well-conditioned active-set systems of
+//  this path the solutions agree to ~1e-13 relative.)
+// =====================================================================================================
+// unblocked, for systems resident in shared memory
+__device__ void block_chol_solve_small(double *S, int lds, int mm, double *x, double *dg)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int j = 0; j < mm; j++) {
+        __syncthreads();
+        const double djj = sqrt(S[(size_t)j * lds + j]);
+        if (tid == 0) dg[j] = djj;
+        const double inv = 1.0 / djj;
+        for (int i = j + 1 + tid; i <= mm; i += FIT_NT) S[(size_t)i * lds + j] *= inv;
+        __syncthreads();
+        for (int i = j + 1 + wid; i <= mm; i += FIT_NT / 32) {
+            const double lij = S[(size_t)i * lds + j];
+            const int cend = min(i, mm - 1);
+            for (int c = j + 1 + lane; c <= cend; c += 32) S[(size_t)i * lds + c] -= lij * S[(size_t)c * lds + j];
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        for (int c = lane; c < mm; c += 32) x[c] = S[(size_t)mm * lds + c];  // z
+        __syncwarp();
+        for (int j = mm - 1; j >= 0; j--) {  // L^T x = z, column oriented
+            const double xj = x[j] / dg[j];
+            __syncwarp();
+            if (lane == 0) x[j] = xj;
+            for (int c = lane; c < j; c += 32) x[c] -= S[(size_t)j * lds + c] * xj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// blocked right-looking version for systems that live in global memory (L2): panels of CHOL_NB columns are factored in
+// shared memory, the trailing matrix is updated with register-blocked 4x4 tiles.
+__device__ void block_chol_solve_blocked(double *S, int lds, int mm, double *x, const FitSmem &sm)
+{
+    constexpr int NB = CHOL_NB, PS = NB + 1;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *P = sm.tile;  // panel rows j0..mm, PS doubles each: (mm + 1) * 17 <= FIT_TILE_DOUBLES for mm <= 480
+    for (int j0 = 0; j0 < mm; j0 += NB) {
+        const int nb = min(NB, mm - j0);
+        const int mr = mm + 1 - j0;
+        __syncthreads();
+        for (int e = tid; e < mr * nb; e += FIT_NT) {
+            const int i = e / nb, q = e - i * nb;
+            P[i * PS + q] = S[(size_t)(j0 + i) * lds + j0 + q];
+        }
+        __syncthreads();
+        if (wid == 0) {  // diagonal block, unblocked, one warp
+            for (int q = 0; q < nb; q++) {
+                const double dqq = sqrt(P[q * PS + q]);
+                __syncwarp();
+                if (lane == q) P[q * PS + q] = dqq;
+                if (lane > q && lane < nb) P[lane * PS + q] /= dqq;
+                __syncwarp();
+                if (lane > q && lane < nb) {
+                    const double liq = P[lane * PS + q];
+                    for (int c = q + 1; c <= lane; c++) P[lane * PS + c] -= liq * P[c * PS + q];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // rows below the diagonal block: row_i <- row_i * L_diag^{-T}
+        for (int i = nb + tid; i < mr; i += FIT_NT) {
+            double row[NB];
+#pragma unroll
+            for (int q = 0; q < NB; q++) row[q] = q < nb ? P[i * PS + q] : 0.0;
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+                if (q < nb) {
+                    double s = row[q];
+#pragma unroll
+                    for (int c = 0; c < NB; c++)
+                        if (c < q) s -= row[c] * P[q * PS + c];
+                    row[q] = s / P[q * PS + q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; q++)
+                if (q < nb) P[i * PS + q] = row[q];
+        }
+        __syncthreads();
+        // L panel back to global (needed by the back substitution)
+        for (int e = tid; e < mr * nb; e += FIT_NT) {
+            const int i = e / nb, q = e - i * nb;
+            if (i >= nb || q <= i) S[(size_t)(j0 + i) * lds + j0 + q] = P[i * PS + q];
+        }
+        // trailing update: S[a][b] -= sum_q P[a][q] P[b][q] for a in [t0, mm], b in [t0, min(a, mm-1)], t0 = j0 + nb
+        const int t0 = j0 + nb;
+        const int mt = mm - t0;  // trailing columns
+        if (mt > 0) {
+            const int rbk = (mt + 1 + 3) >> 2;  // row blocks (incl. the rhs row)
+            const int nblk = rbk * (rbk + 1) / 2;
+            for (int blk = tid; blk < nblk; blk += FIT_NT) {
+                int bi = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
+                while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+                while (bi * (bi + 1) / 2 > blk) bi--;
+                const int bj = blk - bi * (bi + 1) / 2;
+                double acc[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) acc[e] = 0.0;
+                const double *pa = P + (size_t)(nb + 4 * bi) * PS;
+                const double *pb = P + (size_t)(nb + 4 * bj) * PS;
+                for (int q = 0; q < nb; q++) {
+                    double a[4], bb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        a[u] = (4 * bi + u <= mt) ? pa[u * PS + q] : 0.0;
+                        bb[u] = (4 * bj + u <= mt) ? pb[u * PS + q] : 0.0;
+                    }
+#pragma unroll
+                    for (int qa = 0; qa < 4; qa++)
+#pragma unroll
+                        for (int qb = 0; qb < 4; qb++) acc[qa * 4 + qb] = fma(a[qa], bb[qb], acc[qa * 4 + qb]);
+                }
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int a = t0 + 4 * bi + (e >> 2), b = t0 + 4 * bj + (e & 3);
+                    if (a <= mm && b < mm && b <= a) S[(size_t)a * lds + b] -= acc[e];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // back substitution L^T x = z, z = row mm
+    for (int c = tid; c < mm; c += FIT_NT) x[c] = S[(size_t)mm * lds + c];
+    __syncthreads();
+    const int jlast = ((mm - 1) / NB) * NB;
+    for (int j0 = jlast; j0 >= 0; j0 -= NB) {
+        const int nb = min(NB, mm - j0);
+        const int t0 = j0 + nb;
+        // v[q] = sum_{i in [t0, mm)} L[i][j0+q] * x[i]
+        double acc[NB];
+#pragma unroll
+        for (int q = 0; q < NB; q++) acc[q] = 0.0;
+        for (int i = t0 + tid; i < mm; i += FIT_NT) {
+            const double xi = x[i];
+            const double *Li = S + (size_t)i * lds + j0;
+#pragma unroll
+            for (int q = 0; q < NB; q++)
+                if (q < nb) acc[q] = fma(Li[q], xi, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NB; q++) acc[q] = warp_sum(acc[q]);
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NB; q++) sm.scratch[wid * NB + q] = acc[q];
+        }
+        // diagonal block to smem
+        for (int e = tid; e < nb * nb; e += FIT_NT) {
+            const int i = e / nb, q = e - i * nb;
+            P[i * PS + q] = q <= i ? S[(size_t)(j0 + i) * lds + j0 + q] : 0.0;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            double t = 0.0;
+            if (lane < nb) {
+                double vsum = 0.0;
+                for (int w2 = 0; w2 < FIT_NT / 32; w2++) vsum += sm.scratch[w2 * NB + lane];
+                t = x[j0 + lane] - vsum;
+            }
+            for (int q = nb - 1; q >= 0; q--) {
+                const double yq = __shfl_sync(0xffffffffu, t, q) / P[q * PS + q];
+                if (lane == q) t = yq;
+                if (lane < q) t -= P[q * PS + lane] * yq;
+            }
+            if (lane < nb) x[j0 + lane] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// Solve the bordered system held at S (rank 0 of the cluster only); x <- solution (mm entries, shared memory).
+__device__ __forceinline__ void chol_solve(double *S, int lds, int mm, double *x, const FitSmem &sm)
+{
+    if (S == sm.Ssm) block_chol_solve_small(S, lds, mm, x, sm.dg);
+    else block_chol_solve_blocked(S, lds, mm, x, sm);
+}
+
+// Rank 0 holds a bordered system (nu unknowns) at S: solve it and hand the solution to every CTA of the cluster (out: smem).
+__device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds, int nu, double *out, const FitSmem &sm)
+{
+    if (cl.rank == 0) {
+        chol_solve(S, lds, nu, sm.rhs, sm);
+        if (cl.CL > 1) {
+            double *bc = cw_slot(cx, 0, 2);
+            for (int a = threadIdx.x; a < nu; a += FIT_NT) bc[a] = sm.rhs[a];
+        }
+    }
+    if (cl.CL > 1) {
+        clu_sync(cl);
+        const double *bc = cw_slot(cx, 0, 2);
+        for (int a = threadIdx.x; a < nu; a += FIT_NT) out[a] = bc[a];
+    } else {
+        for (int a = threadIdx.x; a < nu; a += FIT_NT) out[a] = sm.rhs[a];
+    }
+    __syncthreads();
+}
+
+// Cluster mode: Sfin[a][b] = sum_q P_q[0][a][b] (- sum_q P_q[1][a][b] when nmat == 2) for a < rows, b < cols, each CTA
+// reducing a slab of rows, ranks summed in a fixed order; optional extra row `rows` = sum_q cw_slot(q, 1) (Cox gradient).
+// Ends with a cluster barrier; afterwards rank 0 stages the system where it will factor it and returns that pointer.
+__device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int cols, int nmat, bool extra_row, int *lds_out,
+                                   const FitSmem &sm)
+{
+    const int ldA = cx.ldA;
+    const int per = (rows + cl.CL - 1) / cl.CL;
+    const int a0 = cl.rank * per, a1 = min(rows, a0 + per);
+    const int cnt = max(0, a1 - a0) * cols;
+    for (int e = threadIdx.x; e < cnt; e += FIT_NT) {
+        const int a = a0 + e / cols, b = e % cols;
+        const size_t o = (size_t)a * ldA + b;
+        double s = 0.0;
+        for (int q = 0; q < cl.CL; q++) s += cx.Sp0[q * cx.sp_stride + o];
+        if (nmat == 2) {
+            double s2 = 0.0;
+            for (int q = 0; q < cl.CL; q++) s2 += cx.Sp0[q * cx.sp_stride + (size_t)ldA * ldA + o];
+            s -= s2;
+        }
+        cx.Sfin[o] = s;
+    }
+    if (extra_row && cl.rank == cl.CL - 1) {
+        for (int b = threadIdx.x; b < cols; b += FIT_NT) {
+            double s = 0.0;
+            for (int q = 0; q < cl.CL; q++) s += cw_slot(cx, q, 1)[b];
+            cx.Sfin[(size_t)rows * ldA + b] = s;
+        }
+    }
+    clu_sync(cl);
+    const int brows = rows + (extra_row ? 1 : 0);  // bordered system: brows rows, brows - 1 unknowns
+    if (brows <= FIT_SMEM_MS) {
+        if (cl.rank == 0) {
+            for (int e = threadIdx.x; e < brows * cols; e += FIT_NT) {
+                const int a = e / cols, b = e % cols;
+                sm.Ssm[a * FIT_SMEM_MS + b] = cx.Sfin[(size_t)a * ldA + b];
+            }
+            __syncthreads();
+        }
+        *lds_out = FIT_SMEM_MS;
+        return sm.Ssm;
+    }
+    *lds_out = ldA;
+    return cx.Sfin;
+}
+
+// Weighted Gram of columns [0, mm) of V over ALL train rows of the chain, then solve for the first mm-1 unknowns with
+// row mm-1 as right-hand side:  S = sum_r wt[r] V[r][a] V[r][b];  S[0:mm-1, 0:mm-1] x = S[mm-1, 0:mm-1].
+// out (shared memory of every CTA) <- x.
+__device__ void gram_solve(const ChainCtx &cx, Clu &cl, const double *V, int ldv, int mm, const double *wt, double *out,
+                           const FitSmem &sm)
+{
+    if (cl.CL == 1) {
+        block_syrk(V, ldv, cx.rb, cx.re, mm, wt, cx.S, cx.lds, sm);
+        solve_broadcast(cx, cl, cx.S, cx.lds, mm - 1, out, sm);
+        return;
+    }
+    block_syrk(V, ldv, cx.rb, cx.re, mm, wt, cx.Sp0 + cl.rank * cx.sp_stride, cx.ldA, sm);
+    clu_sync(cl);
+    int lds;
+    double *S = reduce_partials(cx, cl, mm, mm, 1, false, &lds, sm);
+    solve_broadcast(cx, cl, S, lds, mm - 1, out, sm);
+}
+
+__device__ __forceinline__ double row_dot(const double *row, const double *b, int m)
+{
+    double s = 0.0;
+    for (int a = 0; a < m; a++) s = fma(row[a], b[a], s);
+    return s;
+}
+
+// ---- gaussian: Algorithm.h:1131-1135
+__device__ void fit_lm(const ChainCtx &cx, Clu &cl, const FitSmem &sm, double *beta_out)
+{
+    const int T = cx.T, ldA = cx.ldA;
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) cx.XA[(size_t)r * ldA + T] = cx.y[r];
+    __syncthreads();
+    gram_solve(cx, cl, cx.XA, ldA, T + 1, nullptr, beta_out, sm);
+}
+
+// ---- binomial: Algorithm.h:1148-1204.  Design columns: [1 | X_A | z]
+__device__ double logit_eval(const ChainCtx &cx, Clu &cl, const double *beta, const FitSmem &sm)
+{
+    double ll = 0.0;
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+        const double eu = row_dot(cx.XA + (size_t)r * cx.ldA, beta, cx.m);
+        const double e = exp(clampd(eu, 30.0));
+        const double pi = e / (1.0 + e);
+        cx.v[0][r] = eu;
+        cx.v[1][r] = pi;
+        ll += (cx.y[r] * log(pi) + (1.0 - cx.y[r]) * log(1.0 - pi)) * cx.w[r];
+    }
+    return clu_allsum(cl, block_sum<FIT_NT>(ll, sm.red));
+}
+__device__ void logit_wz(const ChainCtx &cx, bool floor_w)
+{
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+        const double pi = cx.v[1][r];
+        double W = pi * (1.0 - pi);
+        if (floor_w && W < 0.001) W = 0.001;
+        cx.XA[(size_t)r * cx.ldA + cx.m] = cx.v[0][r] + (cx.y[r] - pi) / W;
+        cx.v[2][r] = W * cx.w[r];
+    }
+    __syncthreads();
+}
+__device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm)
+{
+    double *b0 = sm.b0, *b1 = sm.b1;
+    for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = 0.0;
+    __syncthreads();
+    double ll0 = logit_eval(cx, cl, b0, sm);
+    logit_wz(cx, false);
+    gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm);
+    for (int j = 0; j < 30; j++) {
+        const double ll1 = logit_eval(cx, cl, b1, sm);
+        if (fabs(ll0 - ll1) / (0.1 + fabs(ll1)) < 1e-6) break;
+        for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = b1[a];
+        ll0 = ll1;
+        __syncthreads();
+        logit_wz(cx, true);
+        gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm);
+    }
+    // result: b0 (the iterate before the last solve)
+}
+
+// ---- poisson: Algorithm.h:1273-1322
+__device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const FitSmem &sm)
+{
+    double *b0 = sm.b0;
+    const int ldA = cx.ldA;
+    for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = a == 0 ? coef0_in : 0.0;
+    __syncthreads();
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+        const double eta = row_dot(cx.XA + (size_t)r * ldA, b0, cx.m);
+        cx.v[0][r] = eta;
+        cx.v[1][r] = exp(eta);
+    }
+    __syncthreads();
+    double ll0 = 1e5;
+    for (int j = 0; j < 50; j++) {
+        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+            const double e = cx.v[1][r];
+            cx.v[2][r] = e * cx.w[r];
+            cx.XA[(size_t)r * ldA + cx.m] = cx.v[0][r] + (cx.y[r] - e) / e;
+        }
+        __syncthreads();
+        gram_solve(cx, cl, cx.XA, ldA, cx.m + 1, cx.v[2], b0, sm);
+        double ll = 0.0;
+        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+            const double eta = clampd(row_dot(cx.XA + (size_t)r * ldA, b0, cx.m), 30.0);
+            double e = exp(eta);
+            if (e < 0.001) e = 0.001;
+            cx.v[0][r] = eta;
+            cx.v[1][r] = e;
+            ll += (cx.y[r] * eta - e) * cx.w[r];
+        }
+        const double ll1 = clu_allsum(cl, block_sum<FIT_NT>(ll, sm.red));
+        if (fabs(ll0 - ll1) / fabs(0.1 + ll0) < 1e-6) break;
+        ll0 = ll1;
+    }
+}
+
+// ---- scans over the chain's rows, cut into the cluster's contiguous slices.  v is global, indexed by absolute row.
+// suffix: v[r] <- sum_{k >= r} v[k];  prefix: v[r] <- sum_{k <= r} v[k].  The slice total is carried from rank to rank by
+// ADDITION only (risk sets span e^+-30: never subtract, see block_excl_scan).
+__device__ void clu_suffix_scan(const ChainCtx &cx, Clu &cl, double *v, const FitSmem &sm)
+{
+    const int nr = cx.re - cx.rb;
+    block_suffix_scan<FIT_NT>(v + cx.rb, nr, sm.red);
+    if (cl.CL == 1) return;
+    double tot[CLMAX];
+    clu_allgather(cl, nr > 0 ? v[cx.rb] : 0.0, tot);
+    double carry = 0.0;
+#pragma unroll
+    for (int q = CLMAX - 1; q >= 0; q--)
+        if (q < cl.CL && q > cl.rank) carry += tot[q];
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) v[r] += carry;
+    __syncthreads();
+}
+__device__ void clu_prefix_scan(const ChainCtx &cx, Clu &cl, double *v, const FitSmem &sm)
+{
+    const int nr = cx.re - cx.rb;
+    block_prefix_scan<FIT_NT>(v + cx.rb, nr, sm.red);
+    if (cl.CL == 1) return;
+    double tot[CLMAX];
+    clu_allgather(cl, nr > 0 ? v[cx.re - 1] : 0.0, tot);
+    double carry = 0.0;
+#pragma unroll
+    for (int q = 0; q < CLMAX; q++)
+        if (q < cl.rank) carry += tot[q];
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) v[r] += carry;
+    __syncthreads();
+}
+
+// ---- cox: Algorithm.h:1377-1490 (+ loglik_cox, coxph.cpp:16-40)
+// loglik at beta: theta = exp(clip(X_A beta)), S0 = suffix(theta); sum status*w*log(theta/S0)
+__device__ double cox_loglik(const ChainCtx &cx, Clu &cl, const double *beta, double *th, double *s0, const FitSmem &sm)
+{
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+        const double t = exp(clampd(row_dot(cx.XA + (size_t)r * cx.ldA, beta, cx.m), 30.0));
+        th[r] = t;
+        s0[r] = t;
+    }
+    __syncthreads();
+    clu_suffix_scan(cx, cl, s0, sm);
+    double ll = 0.0;
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) ll += log(th[r] / s0[r]) * cx.y[r] * cx.w[r];
+    return clu_allsum(cl, block_sum<FIT_NT>(ll, sm.red));
+}
+// XB[r][a] = suffix_r(theta * XA[.][a]) / S0[r]   (risk-set means), chunked two-pass scan over the slice's rows with the
+// column totals of the later slices carried in
+__device__ void cox_riskset_means(const ChainCtx &cx, Clu &cl, double *XB, const double *th, const double *s0,
+                                  const FitSmem &sm)
+{
+    const int m = cx.m, ldA = cx.ldA;
+    const int nr = cx.re - cx.rb;
+    // rows per chunk: chunk sums [nch][m] must fit the scratch region (FIT_NT*16 doubles)
+    const int nch_max = max(1, (FIT_NT * 16) / m);
+    const int CH = max(32, (nr + nch_max - 1) / nch_max);
+    const int nch = (nr + CH - 1) / CH;
+    double *csum = sm.scratch;  // [nch][m]
+    for (int it = threadIdx.x; it < nch * m; it += FIT_NT) {
+        const int ch = it / m, a = it % m;
+        const int rb = cx.rb + ch * CH, re = min(cx.re, rb + CH);
+        double s = 0.0;
+        for (int r = re - 1; r >= rb; r--) s += th[r] * cx.XA[(size_t)r * ldA + a];
+        csum[it] = s;
+    }
+    __syncthreads();
+    if (cl.CL > 1) {  // publish this slice's column totals
+        double *mine = cw_slot(cx, cl.rank, 0);
+        for (int a = threadIdx.x; a < m; a += FIT_NT) {
+            double s = 0.0;
+            for (int ch = nch - 1; ch >= 0; ch--) s += csum[ch * m + a];
+            mine[a] = s;
+        }
+        clu_sync(cl);
+    }
+    // exclusive suffix over chunks per column (sequential over nch, parallel over columns)
+    for (int a = threadIdx.x; a < m; a += FIT_NT) {
+        double run = 0.0;
+        for (int q = cl.CL - 1; q > cl.rank; q--) run += cw_slot(cx, q, 0)[a];
+        for (int ch = nch - 1; ch >= 0; ch--) {
+            const double t = csum[ch * m + a];
+            csum[ch * m + a] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < nch * m; it += FIT_NT) {
+        const int ch = it / m, a = it % m;
+        const int rb = cx.rb + ch * CH, re = min(cx.re, rb + CH);
+        double s = csum[it];
+        for (int r = re - 1; r >= rb; r--) {
+            s += th[r] * cx.XA[(size_t)r * ldA + a];
+            XB[(size_t)r * ldA + a] = s / s0[r];
+        }
+    }
+    __syncthreads();
+}
+__device__ int g_dbg_cox_iters = 30;  // debug knob (bess_b200_debug_set key 1); 30 = reference behaviour
+__device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &sm)
+{
+    const int max_newton = g_dbg_cox_iters;
+    const int m = cx.m, ldA = cx.ldA;
+    double *b0 = sm.b0, *b1 = sm.b1;
+    double *th = cx.v[0], *s0 = cx.v[1], *ev = cx.v[2], *om = cx.v[3], *gv = cx.v[4];
+    for (int a = threadIdx.x; a < m; a += FIT_NT) b0[a] = 0.0;
+    __syncthreads();
+    double ll0 = 1e5;
+    for (int l = 1; l <= max_newton; l++) {
+        // theta (no weights here, Algorithm.h:1423), S0
+        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+            const double t = exp(clampd(row_dot(cx.XA + (size_t)r * ldA, b0, m), 30.0));
+            th[r] = t;
+            s0[r] = t;
+        }
+        __syncthreads();
+        clu_suffix_scan(cx, cl, s0, sm);
+        // e = w*status; C = prefix(e/S0); omega = theta*C; gvec = e - omega
+        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+            ev[r] = cx.w[r] * cx.y[r];
+            om[r] = ev[r] / s0[r];
+        }
+        __syncthreads();
+        clu_prefix_scan(cx, cl, om, sm);
+        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+            om[r] *= th[r];
+            gv[r] = ev[r] - om[r];
+        }
+        __syncthreads();
+        cox_riskset_means(cx, cl, XB, th, s0, sm);
+        // -h = P1 - P2,  P1 = X_A^T diag(omega) X_A,  P2 = XB^T diag(e) XB;  g = X_A^T gv
+        double *P1 = cl.CL == 1 ? cx.S : cx.Sp0 + cl.rank * cx.sp_stride;
+        double *P2 = cl.CL == 1 ? cx.Sfin + (size_t)ldA * ldA : P1 + (size_t)ldA * ldA;
+        const int ld1 = cl.CL == 1 ? cx.lds : ldA;
+        block_syrk(cx.XA, ldA, cx.rb, cx.re, m, om, P1, ld1, sm);
+        block_syrk(XB, ldA, cx.rb, cx.re, m, ev, P2, ldA, sm);
+        {
+            // g_a = sum_r XA[r][a]*gv[r] over the slice: (a, sub-slice) decomposition, deterministic reduction
+            const int nsl = max(1, FIT_NT / m);
+            for (int it = threadIdx.x; it < m * nsl; it += FIT_NT) {
+                const int a = it % m, sl = it / m;
+                double s = 0.0;
+                for (int r = cx.rb + sl; r < cx.re; r += nsl) s = fma(cx.XA[(size_t)r * ldA + a], gv[r], s);
+                sm.scratch[it] = s;
+            }
+            __syncthreads();
+            double *gdst = cl.CL == 1 ? cx.S + (size_t)m * cx.lds : cw_slot(cx, cl.rank, 1);
+            for (int a = threadIdx.x; a < m; a += FIT_NT) {
+                double s = 0.0;
+                for (int sl = 0; sl < nsl; sl++)
+                    if (a + sl * m < m * nsl) s += sm.scratch[sl * m + a];
+                gdst[a] = s;  // CL == 1: row m of the bordered system
+            }
+            __syncthreads();
+        }
+        double *S;
+        int lds;
+        if (cl.CL == 1) {
+            for (int it = threadIdx.x; it < m * m; it += FIT_NT) {
+                const int a = it / m, bcol = it % m;
+                cx.S[(size_t)a * cx.lds + bcol] -= P2[(size_t)a * ldA + bcol];
+            }
+            __syncthreads();
+            S = cx.S;
+            lds = cx.lds;
+        } else {
+            clu_sync(cl);
+            S = reduce_partials(cx, cl, m, m, 2, true, &lds, sm);
+        }
+        // P d' = g  (d' = -d of Algorithm.h:1472)
+        solve_broadcast(cx, cl, S, lds, m, sm.rhs, sm);
+        // line search (Algorithm.h:1474-1481): beta1 = beta0 - 0.5^mm * d = beta0 + 0.5^mm * rhs
+        int mm = 1;
+        double step = 0.5;
+        for (int a = threadIdx.x; a < m; a += FIT_NT) b1[a] = b0[a] + step * sm.rhs[a];
+        __syncthreads();
+        double ll1 = cox_loglik(cx, cl, b1, cx.v[5], cx.v[6], sm);
+        while (ll0 > ll1 && mm < 5) {
+            mm++;
+            step *= 0.5;
+            __syncthreads();
+            for (int a = threadIdx.x; a < m; a += FIT_NT) b1[a] = b0[a] + step * sm.rhs[a];
+            __syncthreads();
+            ll1 = cox_loglik(cx, cl, b1, cx.v[5], cx.v[6], sm);
+        }
+        if (fabs(ll0 - ll1) / fabs(0.1 + ll0) < 1e-5) break;
+        __syncthreads();
+        for (int a = threadIdx.x; a < m; a += FIT_NT) b0[a] = b1[a];
+        ll0 = ll1;
+        __syncthreads();
+    }
+}
+
+// Gradient vectors of the next dual sweep from the chain's current (A, beta_A, coef0); X_A is in cx.XA.
+__device__ void chain_gradient(const Dev &d, const ChainCtx &cx, Clu &cl, const double *bsl /*smem slopes*/, int ks,
+                               double coef0, const FitSmem &sm)
+{
+    const int c = cx.c, FS = d.FS, nt = cx.nt;
+    const int *rows = d.rows + (size_t)c * d.n;
+    const int fam = d.family;
+    if (fam != FAM_COX) {
+        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+            double eta = coef0;
+            const double *row = cx.XA + (size_t)r * d.ldA + cx.off;
+            for (int a = 0; a < ks; a++) eta = fma(row[a], bsl[a], eta);
+            const size_t o = (size_t)rows[r] * FS + c;
+            if (fam == FAM_LM) {
+                d.G[o] = (cx.y[r] - eta) / (double)nt;  // Algorithm.h:1109 (coef0 == 0 for gaussian)
+            } else if (fam == FAM_LOGIT) {
+                const double e = exp(clampd(eta, 30.0));  // Algorithm.h:1223-1236
+                const double pr = e / (e + 1.0);
+                d.G[o] = cx.w[r] * (cx.y[r] - pr);
+                d.W[o] = cx.w[r] * pr * (1.0 - pr);
+            } else {
+                const double e = exp(eta);  // Algorithm.h:1338-1341 (not clamped)
+                d.G[o] = (cx.y[r] - e) * cx.w[r];
+                d.W[o] = e * cx.w[r];
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    // cox, Algorithm.h:1579-1630 restated with prefix/suffix sums
+    double *th = cx.v[0], *s0 = cx.v[1], *cc = cx.v[2];
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+        double eta = 0.0;
+        const double *row = cx.XA + (size_t)r * d.ldA + cx.off;
+        for (int a = 0; a < ks; a++) eta = fma(row[a], bsl[a], eta);
+        const double t = cx.w[r] * exp(clampd(eta, 30.0));
+        th[r] = t;
+        s0[r] = t;
+    }
+    __syncthreads();
+    clu_suffix_scan(cx, cl, s0, sm);
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) cc[r] = (cx.y[r] != 0.0 ? cx.w[r] : 0.0) / s0[r];
+    __syncthreads();
+    clu_prefix_scan(cx, cl, cc, sm);
+    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
+        const double e = cx.y[r] != 0.0 ? cx.w[r] : 0.0;
+        const double om = th[r] * cc[r];
+        const size_t o = (size_t)rows[r] * FS + c;
+        d.G[o] = e - om;
+        d.W[o] = om;
+        d.TH[o] = th[r];
+        d.C2[o] = e / (s0[r] * s0[r]);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ ChainCtx make_ctx(const Dev &d, int c, int T, const Clu &cl, const FitSmem &sm)
+{
+    ChainCtx cx;
+    cx.c = c;
+    cx.nt = d.ntrain[c];
+    cx.T = T;
+    cx.off = (d.family == FAM_LOGIT || d.family == FAM_POISSON) ? 1 : 0;
+    cx.m = T + cx.off;
+    cx.ldA = d.ldA;
+    const int per = (cx.nt + cl.CL - 1) / cl.CL;
+    cx.rb = min(cx.nt, cl.rank * per);
+    cx.re = min(cx.nt, cx.rb + per);
+    cx.XA = d.XA + (size_t)c * d.n * d.ldA;
+    cx.y = d.ytr + (size_t)c * d.n;
+    cx.w = d.wtr + (size_t)c * d.n;
+    for (int q = 0; q < NVEC; q++) cx.v[q] = d.vec + ((size_t)c * NVEC + q) * d.n;
+    cx.Sfin = d.Smat + (size_t)c * 2 * d.ldA * d.ldA;
+    const int mmax = cx.m + 1;
+    if (mmax <= FIT_SMEM_MS) {
+        cx.S = sm.Ssm;
+        cx.lds = FIT_SMEM_MS;
+    } else {
+        cx.S = cx.Sfin;
+        cx.lds = d.ldA;
+    }
+    cx.sp_stride = (size_t)d.nmat * d.ldA * d.ldA;
+    cx.Sp0 = d.Spart ? d.Spart + (size_t)c * d.CLcap * cx.sp_stride : nullptr;
+    cx.cw = d.cw + (size_t)c * CLMAX * 4 * d.ldA;
+    return cx;
+}
+
+__device__ __forceinline__ Clu make_clu(const FitSmem &sm, int CL)
+{
+    Clu cl;
+    cl.CL = CL;
+    cl.rank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    cl.xch = sm.xch;
+    cl.phase = 0;
+    return cl;
+}
+
+// Start of a batch (Algorithm::fit prologue, Algorithm.h:141-148): coef0 <- coef0_init, l <- 0, A_list.col(0) <- 0,
+// gradient vectors from beta_init.  One CTA per chain (the gradient is a single pass over the rows).
+__global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, const BatchDesc b)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA);
+    const int c = b.chain[blockIdx.x];
+    // Algorithm::coef0_init is only refreshed when the path starts a new step (path.cpp:57); CV folds of the same
+    // step inherit it.
+    double level;
+    if (!d.warm) level = 0.0;
+    else if (b.new_path_step) level = d.coef0[0];
+    else level = *d.coef0_level;
+    __syncthreads();
+    int ks = d.ks[c];
+    if (!d.warm) {
+        // cold start: beta_init = 0
+        for (int a = threadIdx.x; a < ks; a += FIT_NT) d.betaD[(size_t)c * d.pstride + d.A[(size_t)c * d.kcap + a]] = 0.0;
+        ks = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0 && b.new_path_step) *d.coef0_level = level;
+        if (blockIdx.x == 0) *d.n_active = b.nch;
+        d.tie_acc[c] = 0;
+        if (!(c == 0 && b.new_path_step && d.warm)) d.coef0[c] = level;
+        d.ks[c] = ks;
+        d.l[c] = 0;
+        d.done[c] = 0;
+    }
+    int *h0 = d.hist + (size_t)c * MAX_HIST * d.kcap;
+    for (int a = threadIdx.x; a < b.T; a += FIT_NT) h0[a] = 0;
+    for (int a = threadIdx.x; a < ks; a += FIT_NT) sm.b0[a] = d.bA[(size_t)c * d.kcap + a];
+    __syncthreads();
+    Clu cl = make_clu(sm, 1);
+    ChainCtx cx = make_ctx(d, c, ks, cl, sm);
+    chain_gradient(d, cx, cl, sm.b0, ks, level, sm);
+}
+
+// One PDAS iteration after the top-k (Algorithm.h:154-170) + gradient vectors for the next one.
+// grid = nch * CL CTAs, cluster dimension CL (launch attribute); CTA rank inside the cluster = row slice.
+__global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const BatchDesc b)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA);
+    if (d.gate && *d.gate == 0) return;  // whole batch already finished (speculative launch)
+    const int CL = b.CL;
+    const int c = b.chain[blockIdx.x / CL];
+    if (d.done[c]) return;  // uniform over the cluster
+    Clu cl = make_clu(sm, CL);
+    if (CL > 1) cg::this_cluster().sync();  // every CTA of the cluster is running before any DSMEM traffic
+    const int T = b.T;
+    ChainCtx cx = make_ctx(d, c, T, cl, sm);
+    const int ldA = d.ldA;
+    const int *Anew = d.Anew + (size_t)c * d.kcap;
+    const int *rows = d.rows + (size_t)c * d.n;
+    int *Acur = d.A + (size_t)c * d.kcap;
+    const int ks_old = d.ks[c];
+    const double coef0_in = d.coef0[c];
+    const int l = d.l[c] + 1;
+
+    // clear the dense beta on the old support (Algorithm.h:159)
+    if (cl.rank == 0)
+        for (int a = threadIdx.x; a < ks_old; a += FIT_NT) d.betaD[(size_t)c * d.pstride + Acur[a]] = 0.0;
+    // gather X_A (utilities.cpp:132-140): XA[r][off + a] = X[rows[r]][A[a]], this CTA's row slice, 8 loads in flight
+    {
+        const int nloc = cx.re - cx.rb;
+        const int tot = nloc * T;
+        for (int it0 = threadIdx.x; it0 < tot; it0 += 8 * FIT_NT) {
+            double val[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int it = it0 + q * FIT_NT;
+                if (it < tot) {
+                    const int r = it / T, a = it - r * T;
+                    val[q] = __ldg(d.X + (size_t)rows[cx.rb + r] * d.ldx + Anew[a]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int it = it0 + q * FIT_NT;
+                if (it < tot) {
+                    const int r = it / T, a = it - r * T;
+                    cx.XA[(size_t)(cx.rb + r) * ldA + cx.off + a] = val[q];
+                }
+            }
+        }
+        if (cx.off)
+            for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) cx.XA[(size_t)r * ldA] = 1.0;
+    }
+    __syncthreads();
+
+    double coef0 = coef0_in;
+    const double *slopes;
+    if (d.family == FAM_LM) {
+        fit_lm(cx, cl, sm, sm.b0);
+        slopes = sm.b0;
+    } else if (d.family == FAM_LOGIT) {
+        fit_logistic(cx, cl, sm);
+        coef0 = sm.b0[0];
+        slopes = sm.b0 + 1;
+    } else if (d.family == FAM_POISSON) {
+        fit_poisson(cx, cl, coef0_in, sm);
+        coef0 = sm.b0[0];
+        slopes = sm.b0 + 1;
+    } else {
+        fit_cox(cx, cl, d.XB + (size_t)c * d.n * ldA, sm);
+        slopes = sm.b0;
+    }
+    __syncthreads();
+    // cycle test (Algorithm.h:164-170) against A_list[0..l-1]; every CTA of the cluster evaluates it identically
+    int seen = 0;
+    for (int ll = 0; ll < l && !seen; ll++) {
+        const int *hp = d.hist + ((size_t)c * MAX_HIST + ll) * d.kcap;
+        int same = 1;
+        for (int a = threadIdx.x; a < T; a += FIT_NT) same &= (hp[a] == Anew[a]);
+        seen = __syncthreads_and(same);
+    }
+    const int finished = seen || l >= d.max_iter;
+    clu_sync(cl);  // every CTA has read the chain state it needs; rank 0 may now overwrite it
+    // scatter (Algorithm.h:159-163), record A
+    if (cl.rank == 0) {
+        int *hl = d.hist + ((size_t)c * MAX_HIST + l) * d.kcap;
+        for (int a = threadIdx.x; a < T; a += FIT_NT) {
+            const int j = Anew[a];
+            Acur[a] = j;
+            hl[a] = j;
+            d.bA[(size_t)c * d.kcap + a] = slopes[a];
+            d.betaD[(size_t)c * d.pstride + j] = slopes[a];
+        }
+        if (threadIdx.x == 0) {
+            d.l[c] = seen ? l : (l >= d.max_iter ? d.max_iter + 1 : l);
+            d.ks[c] = T;
+            d.coef0[c] = coef0;
+            d.done[c] = finished;
+            d.tie_acc[c] += d.tie[c];
+            if (finished) atomicSub(d.n_active, 1);
+        }
+    }
+    if (finished) return;
+    chain_gradient(d, cx, cl, slopes, T, coef0, sm);
+}
+
+void debug_set(int key, int val)
+{
+    if (key == 1) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_cox_iters, &val, sizeof(int)));
+}
+
+// cluster size for sparsity level T: enough work per CTA to amortise the cluster barriers, all clusters co-resident
+int chain_cluster_size(const Dev &d, int T, int nch)
+{
+    const double m = T + 2.0;
+    double work = (double)d.n * m * m * (d.family == FAM_COX ? 2.0 : 1.0);
+    if (d.family == FAM_LM) work *= 0.25;  // a single Gram, no inner iteration
+    int CL = 1;
+    while (CL < CLMAX && CL < d.CLcap && work / CL > 1.0e6 && nch * CL * 2 <= 148 && d.n / (CL * 2) >= 128) CL *= 2;
+    return CL;
+}
+
+void launch_chain_begin(const Dev &d, const BatchDesc &b, cudaStream_t st)
+{
+    const size_t smem = fit_smem_bytes(d);
+    CUDA_CHECK(cudaFuncSetAttribute(chain_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chain_begin_kernel<<<b.nch, FIT_NT, smem, st>>>(d, b);
+    CUDA_CHECK(cudaGetLastError());
+}
+void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st)
+{
+    const size_t smem = fit_smem_bytes(d);
+    CUDA_CHECK(cudaFuncSetAttribute(chain_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b.nch * b.CL));
+    cfg.blockDim = dim3(FIT_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)b.CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, chain_fit_kernel, d, b));
+}
+
+}  // namespace bess

@@ -1,6 +1,7 @@
 // Device engine: owns the design matrix and all chain state in HBM and drives the kernels of kernels.cu.
 // See engine.h for the vocabulary.  All compute is on the GPU; there is no CPU fallback anywhere in this file.
 #include "kernels.cuh"
+#include "device_utils.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -10,15 +11,6 @@
 
 namespace bess {
 
-#define CUDA_CHECK(x)                                                               \
-    do {                                                                            \
-        cudaError_t e_ = (x);                                                       \
-        if (e_ != cudaSuccess) {                                                    \
-            throw EngineError{std::string(#x) + ": " + cudaGetErrorString(e_)};     \
-        }                                                                           \
-    } while (0)
-
-constexpr int PROF_NCAT = 6;  // 0 sweep(big: screening/normalise), 1 sweep(PDAS), 2 finish, 3 topk, 4 chain kernels, 5 other
 namespace {
 // Stream-ordered allocation from the device's default memory pool (release threshold raised to "never" in
 // DeviceContext): after the first call every alloc/free is a pool hit, no cudaMalloc/cudaFree (and no implicit
@@ -143,8 +135,8 @@ struct Engine::Impl {
     struct Span { cudaEvent_t a, b; int cat; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> pool;
-    double cat_ms[PROF_NCAT] = {0, 0, 0, 0, 0, 0};
-    long long cat_n[PROF_NCAT] = {0, 0, 0, 0, 0, 0};
+    double cat_ms[PROF_NCAT] = {};
+    long long cat_n[PROF_NCAT] = {};
     cudaEvent_t get_event()
     {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -191,7 +183,7 @@ struct Engine::Impl {
         dfree(m.st, d.rows); dfree(m.st, d.ntrain); dfree(m.st, d.ytr); dfree(m.st, d.wtr); dfree(m.st, d.ks); dfree(m.st, d.A); dfree(m.st, d.bA);
         dfree(m.st, d.coef0); dfree(m.st, d.coef0_level); dfree(m.st, d.Anew); dfree(m.st, d.hist); dfree(m.st, d.l); dfree(m.st, d.done); dfree(m.st, d.tie);
         dfree(m.st, d.tie_acc); dfree(m.st, d.n_active);
-        dfree(m.st, d.betaD); dfree(m.st, d.XA); dfree(m.st, d.XB); dfree(m.st, d.vec); dfree(m.st, d.Smat); dfree(m.st, d.xtx);
+        dfree(m.st, d.betaD); dfree(m.st, d.XA); dfree(m.st, d.XB); dfree(m.st, d.vec); dfree(m.st, d.Smat); dfree(m.st, d.Spart); dfree(m.st, d.cw); dfree(m.st, d.xtx);
         dfree(m.st, testrows); dfree(m.st, ntest); dfree(m.st, lfact); dfree(m.st, loss_scratch); dfree(m.st, loss_out); dfree(m.st, always);
         dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
         chains_ready = false;
@@ -299,7 +291,7 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
         m.x_owned = true;
         m.X = dalloc<double>(m.st, (size_t)n * m.ldx);
         if (m.ldx != p) CUDA_CHECK(cudaMemsetAsync(m.X, 0, (size_t)n * m.ldx * 8, m.st));
-        const int sp = m.span_begin(5);
+        const int sp = m.span_begin(7);
         CUDA_CHECK(cudaMemcpy2DAsync(m.X, (size_t)m.ldx * 8, x, (size_t)p * 8, (size_t)p * 8, n,
                                      x_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m.st));
         m.span_end(sp);
@@ -406,9 +398,10 @@ static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int
         stats_.n_sweeps++;
         stats_.kernel_launches += 2;
     } else {
-        const int sp = m.span_begin(5);
+        const int sp = m.span_begin(0);
         launch_screen_glm(m.X, m.ldx, m.n, m.p, m.y, m.w, family_, m.d.bd, m.st);
         m.span_end(sp);
+        stats_.big_sweep_bytes += 8.0 * m.n * m.p;  // algorithmic: one pass (the marginal fits re-read the column from L2)
         stats_.kernel_launches += 1;
     }
     int *d_alw = nullptr;
@@ -458,7 +451,7 @@ void Engine::normalize(int data_type, bool is_normal)
     b.nch = 1;
     b.chain[0] = 0;
     double *d_mean = nullptr, *d_mul = nullptr, *d_rowmul = nullptr;
-    const int sp_all = m.span_begin(0);
+    const int sp_all = m.span_begin(6);
     if (is_normal) {
         if (data_type == 1 || data_type == 2) {
             // meanx_j = w.x_j / n  (normalize.cpp:25-28, 52-55)
@@ -519,8 +512,8 @@ void Engine::normalize(int data_type, bool is_normal)
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     m.collect_spans();
     // passes over X: [mean sweep 8np + centre 16np] (data_type 1,2) + norm sweep 8np + scale 16np
-    if (is_normal) stats_.big_sweep_bytes += (data_type == 3 ? 24.0 : 48.0) * n * p;
-    else if (family_ == FAM_LM) stats_.big_sweep_bytes += 16.0 * n * p;
+    if (is_normal) stats_.norm_bytes += (data_type == 3 ? 24.0 : 48.0) * n * p;
+    else if (family_ == FAM_LM) stats_.norm_bytes += 16.0 * n * p;
     dfree(m.st, d_mean); dfree(m.st, d_mul); dfree(m.st, d_rowmul);
     m.free_sweep_buffers();
 }
@@ -596,6 +589,11 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     d.XB = family_ == FAM_COX ? dalloc<double>(m.st, (size_t)C * n * d.ldA) : nullptr;
     d.vec = dalloc<double>(m.st, (size_t)C * NVEC * n);
     d.Smat = dalloc<double>(m.st, (size_t)C * 2 * d.ldA * d.ldA);
+    d.cw = dalloc<double>(m.st, (size_t)C * CLMAX * 4 * d.ldA);
+    d.nmat = family_ == FAM_COX ? 2 : 1;
+    d.CLcap = CLMAX;
+    d.CLcap = chain_cluster_size(d, kcap, 1);  // the largest cluster any batch of this problem can ask for
+    d.Spart = d.CLcap > 1 ? dalloc<double>(m.st, (size_t)C * d.CLcap * d.nmat * d.ldA * d.ldA) : nullptr;
     CUDA_CHECK(cudaMemsetAsync(d.ks, 0, MAXC * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.A, 0, (size_t)MAXC * kcap * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.bA, 0, (size_t)MAXC * kcap * 8, m.st));
@@ -619,7 +617,7 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
         BatchDesc b{};
         b.nch = C;
         for (int c = 0; c < C; c++) b.chain[c] = c;
-        const int spx = m.span_begin(0);
+        const int spx = m.span_begin(6);
         launch_dual_sweep(d, MODE_DH, m.st);
         launch_finish(d, MODE_DH, EPI_RAW, b, m.raw, m.st);
         m.span_end(spx);
@@ -629,7 +627,7 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
         CUDA_CHECK(cudaStreamSynchronize(m.st));  // `ind` must outlive the copy
         CUDA_CHECK(cudaMemsetAsync(d.W, 0, ind.size() * 8, m.st));
         stats_.n_sweeps++;
-        stats_.big_sweep_bytes += 8.0 * n * p;
+        stats_.norm_bytes += 8.0 * n * p;
         stats_.kernel_launches += 2;
     }
     // ---- poisson: sum_{j<=y} log j (poisson.cpp:29-44), same summation order as the reference
@@ -691,6 +689,7 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
     b.nch = (int)chains.size();
     b.T = T;
     b.new_path_step = new_path_step ? 1 : 0;
+    b.CL = chain_cluster_size(d, T, b.nch);
     int cmin = MAXC, cmax = -1;
     for (int i = 0; i < b.nch; i++) {
         if (chains[i] < 0 || chains[i] >= m.nchains) throw EngineError{"chain id out of range"};

@@ -17,6 +17,7 @@
 namespace bess {
 
 constexpr int MAXC = 16;      // max chains = 1 + K folds
+constexpr int PROF_NCAT = 8;
 constexpr int MAX_HIST = 66;  // max_iter + 2 columns of A_list (Algorithm.h:142)
 
 enum Family { FAM_LM = 1, FAM_LOGIT = 2, FAM_POISSON = 3, FAM_COX = 4 };
@@ -40,7 +41,8 @@ struct LossJob {
 struct EngineStats {
     long long n_fits = 0, n_pdas_iters = 0, n_sweeps = 0, n_batches = 0, n_boundary_ties = 0;
     double sweep_bytes = 0.0;     // algorithmic bytes of the PDAS dual sweeps (8*n*p per launch + vectors)
-    double big_sweep_bytes = 0.0; // algorithmic bytes of the screening / normalisation passes
+    double big_sweep_bytes = 0.0; // algorithmic bytes of the screening sweep(s) over the raw design (8*n*p each)
+    double norm_bytes = 0.0;      // algorithmic bytes of the normalisation / x_j.x_j passes
     long long kernel_launches = 0;
 };
 
@@ -57,10 +59,10 @@ public:
     // borrow: a device-resident x may be used in place (no copy) until something needs to write to it.
     void load(const double *x, int n, int p, bool x_on_device, const double *y, const double *weight, int family,
               bool borrow = false);
-    // per-category device time (CUDA events on the engine's stream): 0 big sweeps (screening/normalise),
-    // 1 PDAS dual sweeps, 2 finish, 3 top-k, 4 chain kernels, 5 other
+    // per-category device time (CUDA events on the engine's stream): 0 screening sweep (the pass over the raw design),
+    // 1 PDAS dual sweeps, 2 finish, 3 top-k, 4 chain kernels, 5 other, 6 normalisation / x_j.x_j passes, 7 host->device upload
     void set_profiling(bool on);
-    void profile(double *ms_out6, long long *n_out6) const;
+    void profile(double *ms_out8, long long *n_out8) const;
 
     // ---- screening.cpp:26-105: marginal utilities on RAW x, top `size`, X <- X[:, A].  Returns A ascending.
     std::vector<int> screen(int size, const std::vector<int> &always_select);

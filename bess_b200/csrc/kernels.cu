@@ -16,120 +16,13 @@
 //                       and the gradient vectors of the next sweep.
 //   loss_kernel         Metric.h train_loss / fold test losses.
 #include "kernels.cuh"
+#include "device_utils.cuh"
 
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 
 namespace bess {
-
-#define CUDA_CHECK(x)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e_ = (x);                                                                           \
-        if (e_ != cudaSuccess) {                                                                        \
-            throw EngineError{std::string(#x) + ": " + cudaGetErrorString(e_)};                         \
-        }                                                                                               \
-    } while (0)
-
-// =====================================================================================================
-// small device helpers
-// =====================================================================================================
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// deterministic block sum; every thread gets the result.  sh: >= 33 doubles.
-template <int NT>
-__device__ __forceinline__ double block_sum(double v, double *sh)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) sh[wid] = v;
-    __syncthreads();
-    if (wid == 0) {
-        double t = lane < NT / 32 ? sh[lane] : 0.0;
-        t = warp_sum(t);
-        if (lane == 0) sh[32] = t;
-    }
-    __syncthreads();
-    return sh[32];
-}
-
-// block exclusive scan of one value per thread (thread order); returns exclusive prefix, *total = block total.
-// The exclusive value is obtained by SHIFTING the inclusive scan, never by subtracting the thread's own value:
-// "inclusive - own" cancels catastrophically when one term dwarfs the prefix (Cox risk sets span e^+-30).
-template <int NT>
-__device__ __forceinline__ double block_excl_scan(double v, double *sh, double *total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    double excl = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) excl = 0.0;
-    __syncthreads();
-    if (lane == 31) sh[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        double w = lane < NT / 32 ? sh[lane] : 0.0;
-        double winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        double wex = __shfl_up_sync(0xffffffffu, winc, 1);
-        if (lane == 0) wex = 0.0;
-        if (lane < NT / 32) sh[lane] = wex;  // exclusive warp offsets
-        if (lane == 31) sh[32] = winc;
-    }
-    __syncthreads();
-    *total = sh[32];
-    return sh[wid] + excl;
-}
-
-// In-place inclusive scans over v[0..nr): each thread owns a contiguous chunk.
-template <int NT>
-__device__ void block_prefix_scan(double *v, int nr, double *sh)
-{
-    const int per = (nr + NT - 1) / NT;
-    const int b = min(nr, (int)threadIdx.x * per), e = min(nr, b + per);
-    double s = 0.0;
-    for (int i = b; i < e; i++) s += v[i];
-    double tot;
-    double run = block_excl_scan<NT>(s, sh, &tot);
-    for (int i = b; i < e; i++) {
-        run += v[i];
-        v[i] = run;
-    }
-    __syncthreads();
-}
-// suffix: v[i] <- sum_{k >= i} v[k]
-template <int NT>
-__device__ void block_suffix_scan(double *v, int nr, double *sh)
-{
-    const int per = (nr + NT - 1) / NT;
-    // thread t owns the chunk counted from the END so that thread order == scan order
-    const int e = max(0, nr - (int)threadIdx.x * per), b = max(0, e - per);
-    double s = 0.0;
-    for (int i = e - 1; i >= b; i--) s += v[i];
-    double tot;
-    double run = block_excl_scan<NT>(s, sh, &tot);
-    for (int i = e - 1; i >= b; i--) {
-        run += v[i];
-        v[i] = run;
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ double clampd(double v, double c) { return v > c ? c : (v < -c ? -c : v); }
 
 // =====================================================================================================
 // mbarrier + 1-D bulk TMA (cp.async.bulk) helpers
@@ -651,659 +544,9 @@ void launch_topk(const double *vals, long long stride, int n_in, int k, int nch,
     throw EngineError{"top-k: did not converge"};
 }
 
-// =====================================================================================================
-// chain kernels: gather, active-set fits, cycle test, gradient vectors
-// =====================================================================================================
-constexpr int FIT_TILE_DOUBLES = 8192;  // 64 KB row tile for the Gram
-constexpr int FIT_SMEM_MS = 64;         // Gram matrices up to 64 x 64 live in shared memory
-
-struct FitSmem {
-    double *tile;     // FIT_TILE_DOUBLES
-    double *scratch;  // FIT_NT * 16
-    double *Ssm;      // FIT_SMEM_MS^2
-    double *b0, *b1, *rhs, *dg;  // ldA each
-    double *red;      // 40
-};
-__device__ __forceinline__ FitSmem carve_fit_smem(unsigned char *raw, int ldA)
-{
-    FitSmem s;
-    double *p = reinterpret_cast<double *>(raw);
-    s.tile = p; p += FIT_TILE_DOUBLES;
-    s.scratch = p; p += FIT_NT * 16;
-    s.Ssm = p; p += FIT_SMEM_MS * FIT_SMEM_MS;
-    s.b0 = p; p += ldA;
-    s.b1 = p; p += ldA;
-    s.rhs = p; p += ldA;
-    s.dg = p; p += ldA;
-    s.red = p; p += 40;
-    return s;
-}
-size_t fit_smem_bytes(const Dev &d)
-{
-    return sizeof(double) * ((size_t)FIT_TILE_DOUBLES + FIT_NT * 16 + FIT_SMEM_MS * FIT_SMEM_MS + 4 * (size_t)d.ldA + 40);
-}
-
-// S (mm x mm, both triangles) = sum_r wt[r] * V[r][a] * V[r][b]; V row-major [nr][ldv] in global memory.
-__device__ void block_syrk(const double *__restrict__ V, int ldv, int nr, int mm, const double *__restrict__ wt,
-                           double *S, int lds, const FitSmem &sm)
-{
-    const int tid = threadIdx.x;
-    const int mb = (mm + 3) >> 2, mp = mb * 4;
-    const int nblk = mb * (mb + 1) / 2;
-    int R = FIT_TILE_DOUBLES / (mp + 1);
-    if (R > 512) R = 512;
-    double *tile = sm.tile;
-    double *tw = sm.tile + (size_t)R * mp;
-    const int nsl = nblk >= FIT_NT ? 1 : FIT_NT / nblk;
-    const int nbatch = nsl > 1 ? 1 : (nblk + FIT_NT - 1) / FIT_NT;
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int batch = 0; batch < nbatch; batch++) {
-        int blk, sl;
-        bool valid;
-        if (nsl > 1) {
-            blk = tid % nblk;
-            sl = tid / nblk;
-            valid = sl < nsl;
-        } else {
-            blk = batch * FIT_NT + tid;
-            sl = 0;
-            valid = blk < nblk;
-        }
-        int bi = 0, bj = 0;
-        if (valid) {
-            bi = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
-            while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
-            while (bi * (bi + 1) / 2 > blk) bi--;
-            bj = blk - bi * (bi + 1) / 2;
-        }
-        double acc[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) acc[e] = 0.0;
-        for (int rb = 0; rb < nr; rb += R) {
-            const int rc = min(R, nr - rb);
-            __syncthreads();
-            for (int r = wid; r < rc; r += FIT_NT / 32) {
-                const double *src = V + (size_t)(rb + r) * ldv;
-                for (int cidx = lane; cidx < mp; cidx += 32) tile[r * mp + cidx] = cidx < mm ? src[cidx] : 0.0;
-                if (lane == 0) tw[r] = wt ? wt[rb + r] : 1.0;
-            }
-            __syncthreads();
-            if (valid) {
-                for (int r = sl; r < rc; r += nsl) {
-                    const double w = tw[r];
-                    const double *ta = tile + r * mp + 4 * bi;
-                    const double *tb = tile + r * mp + 4 * bj;
-                    const double2 a01 = *reinterpret_cast<const double2 *>(ta);
-                    const double2 a23 = *reinterpret_cast<const double2 *>(ta + 2);
-                    const double2 b01 = *reinterpret_cast<const double2 *>(tb);
-                    const double2 b23 = *reinterpret_cast<const double2 *>(tb + 2);
-                    const double a[4] = {a01.x * w, a01.y * w, a23.x * w, a23.y * w};
-                    const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int qa = 0; qa < 4; qa++)
-#pragma unroll
-                        for (int qb = 0; qb < 4; qb++) acc[qa * 4 + qb] = fma(a[qa], bb[qb], acc[qa * 4 + qb]);
-                }
-            }
-        }
-        if (nsl > 1) {
-            __syncthreads();
-            if (valid) {
-#pragma unroll
-                for (int e = 0; e < 16; e++) sm.scratch[(size_t)(sl * nblk + blk) * 16 + e] = acc[e];
-            }
-            __syncthreads();
-            for (int idx = tid; idx < nblk * 16; idx += FIT_NT) {
-                const int bk = idx >> 4, e = idx & 15;
-                double v = 0.0;
-                for (int q = 0; q < nsl; q++) v += sm.scratch[(size_t)(q * nblk + bk) * 16 + e];
-                int ci = (int)((sqrt(8.0 * (double)bk + 1.0) - 1.0) * 0.5);
-                while ((ci + 1) * (ci + 2) / 2 <= bk) ci++;
-                while (ci * (ci + 1) / 2 > bk) ci--;
-                const int cj = bk - ci * (ci + 1) / 2;
-                const int a = 4 * ci + (e >> 2), bcol = 4 * cj + (e & 3);
-                if (a < mm && bcol < mm && a >= bcol) {
-                    S[(size_t)a * lds + bcol] = v;
-                    S[(size_t)bcol * lds + a] = v;
-                }
-            }
-        } else if (valid) {
-#pragma unroll
-            for (int e = 0; e < 16; e++) {
-                const int a = 4 * bi + (e >> 2), bcol = 4 * bj + (e & 3);
-                if (a < mm && bcol < mm && a >= bcol) {
-                    S[(size_t)a * lds + bcol] = acc[e];
-                    S[(size_t)bcol * lds + a] = acc[e];
-                }
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// Cholesky solve of the leading mm x mm block of S (lower triangle used, destroyed); x <- S^{-1} x.
-// (The reference uses Eigen's pivoted ldlt()/colPivHouseholderQr(); for the SPD, well-conditioned active-set
-//  systems of this path the solutions agree to ~1e-13 relative.)
-__device__ void block_chol_solve(double *S, int lds, int mm, double *x, double *dg)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int j = 0; j < mm; j++) {
-        __syncthreads();
-        const double djj = sqrt(S[(size_t)j * lds + j]);
-        if (tid == 0) dg[j] = djj;
-        const double inv = 1.0 / djj;
-        for (int i = j + 1 + tid; i < mm; i += FIT_NT) S[(size_t)i * lds + j] *= inv;
-        __syncthreads();
-        for (int i = j + 1 + wid; i < mm; i += FIT_NT / 32) {
-            const double lij = S[(size_t)i * lds + j];
-            for (int c = j + 1 + lane; c <= i; c += 32) S[(size_t)i * lds + c] -= lij * S[(size_t)c * lds + j];
-        }
-    }
-    __syncthreads();
-    if (wid == 0) {
-        for (int j = 0; j < mm; j++) {  // L z = x
-            double part = 0.0;
-            for (int c = lane; c < j; c += 32) part += S[(size_t)j * lds + c] * x[c];
-            part = warp_sum(part);
-            if (lane == 0) x[j] = (x[j] - part) / dg[j];
-            __syncwarp();
-        }
-        for (int j = mm - 1; j >= 0; j--) {  // L^T x = z
-            double part = 0.0;
-            for (int i = j + 1 + lane; i < mm; i += 32) part += S[(size_t)i * lds + j] * x[i];
-            part = warp_sum(part);
-            if (lane == 0) x[j] = (x[j] - part) / dg[j];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-}
-
-struct ChainCtx {
-    int c, nt, T, off, m;  // m = number of columns of the design incl. intercept
-    double *XA;
-    const double *y, *w;
-    double *v[NVEC];
-    double *S;
-    int lds;
-};
-
-__device__ __forceinline__ double row_dot(const double *row, const double *b, int m)
-{
-    double s = 0.0;
-    for (int a = 0; a < m; a++) s = fma(row[a], b[a], s);
-    return s;
-}
-
-// ---- gaussian: Algorithm.h:1131-1135
-__device__ void fit_lm(const ChainCtx &cx, int ldA, const FitSmem &sm, double *beta_out)
-{
-    const int T = cx.T;
-    for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) cx.XA[(size_t)r * ldA + T] = cx.y[r];
-    __syncthreads();
-    block_syrk(cx.XA, ldA, cx.nt, T + 1, nullptr, cx.S, cx.lds, sm);
-    for (int a = threadIdx.x; a < T; a += FIT_NT) sm.rhs[a] = cx.S[(size_t)T * cx.lds + a];
-    __syncthreads();
-    block_chol_solve(cx.S, cx.lds, T, sm.rhs, sm.dg);
-    for (int a = threadIdx.x; a < T; a += FIT_NT) beta_out[a] = sm.rhs[a];
-    __syncthreads();
-}
-
-// ---- binomial: Algorithm.h:1148-1204.  Design columns: [1 | X_A | z]
-__device__ double logit_eval(const ChainCtx &cx, int ldA, const double *beta, const FitSmem &sm)
-{
-    double ll = 0.0;
-    for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) {
-        const double eu = row_dot(cx.XA + (size_t)r * ldA, beta, cx.m);
-        const double e = exp(clampd(eu, 30.0));
-        const double pi = e / (1.0 + e);
-        cx.v[0][r] = eu;
-        cx.v[1][r] = pi;
-        ll += (cx.y[r] * log(pi) + (1.0 - cx.y[r]) * log(1.0 - pi)) * cx.w[r];
-    }
-    return block_sum<FIT_NT>(ll, sm.red);
-}
-__device__ void logit_wz(const ChainCtx &cx, int ldA, bool floor_w)
-{
-    for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) {
-        const double pi = cx.v[1][r];
-        double W = pi * (1.0 - pi);
-        if (floor_w && W < 0.001) W = 0.001;
-        cx.XA[(size_t)r * ldA + cx.m] = cx.v[0][r] + (cx.y[r] - pi) / W;
-        cx.v[2][r] = W * cx.w[r];
-    }
-    __syncthreads();
-}
-__device__ void irls_solve(const ChainCtx &cx, int ldA, const FitSmem &sm, double *beta_out)
-{
-    block_syrk(cx.XA, ldA, cx.nt, cx.m + 1, cx.v[2], cx.S, cx.lds, sm);
-    for (int a = threadIdx.x; a < cx.m; a += FIT_NT) sm.rhs[a] = cx.S[(size_t)cx.m * cx.lds + a];
-    __syncthreads();
-    block_chol_solve(cx.S, cx.lds, cx.m, sm.rhs, sm.dg);
-    for (int a = threadIdx.x; a < cx.m; a += FIT_NT) beta_out[a] = sm.rhs[a];
-    __syncthreads();
-}
-__device__ void fit_logistic(const ChainCtx &cx, int ldA, const FitSmem &sm)
-{
-    double *b0 = sm.b0, *b1 = sm.b1;
-    for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = 0.0;
-    __syncthreads();
-    double ll0 = logit_eval(cx, ldA, b0, sm);
-    logit_wz(cx, ldA, false);
-    irls_solve(cx, ldA, sm, b1);
-    for (int j = 0; j < 30; j++) {
-        const double ll1 = logit_eval(cx, ldA, b1, sm);
-        if (fabs(ll0 - ll1) / (0.1 + fabs(ll1)) < 1e-6) break;
-        for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = b1[a];
-        ll0 = ll1;
-        __syncthreads();
-        logit_wz(cx, ldA, true);
-        irls_solve(cx, ldA, sm, b1);
-    }
-    // result: b0 (the iterate before the last solve)
-}
-
-// ---- poisson: Algorithm.h:1273-1322
-__device__ void fit_poisson(const ChainCtx &cx, int ldA, double coef0_in, const FitSmem &sm)
-{
-    double *b0 = sm.b0;
-    for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = a == 0 ? coef0_in : 0.0;
-    __syncthreads();
-    for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) {
-        const double eta = row_dot(cx.XA + (size_t)r * ldA, b0, cx.m);
-        cx.v[0][r] = eta;
-        cx.v[1][r] = exp(eta);
-    }
-    __syncthreads();
-    double ll0 = 1e5;
-    for (int j = 0; j < 50; j++) {
-        for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) {
-            const double e = cx.v[1][r];
-            cx.v[2][r] = e * cx.w[r];
-            cx.XA[(size_t)r * ldA + cx.m] = cx.v[0][r] + (cx.y[r] - e) / e;
-        }
-        __syncthreads();
-        irls_solve(cx, ldA, sm, b0);
-        double ll = 0.0;
-        for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) {
-            const double eta = clampd(row_dot(cx.XA + (size_t)r * ldA, b0, cx.m), 30.0);
-            double e = exp(eta);
-            if (e < 0.001) e = 0.001;
-            cx.v[0][r] = eta;
-            cx.v[1][r] = e;
-            ll += (cx.y[r] * eta - e) * cx.w[r];
-        }
-        const double ll1 = block_sum<FIT_NT>(ll, sm.red);
-        if (fabs(ll0 - ll1) / fabs(0.1 + ll0) < 1e-6) break;
-        ll0 = ll1;
-    }
-}
-
-// ---- cox: Algorithm.h:1377-1490 (+ loglik_cox, coxph.cpp:16-40)
-// loglik at beta: theta = exp(clip(X_A beta)), S0 = suffix(theta); sum status*w*log(theta/S0)
-__device__ double cox_loglik(const ChainCtx &cx, int ldA, const double *beta, double *th, double *s0, const FitSmem &sm)
-{
-    for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) {
-        const double t = exp(clampd(row_dot(cx.XA + (size_t)r * ldA, beta, cx.m), 30.0));
-        th[r] = t;
-        s0[r] = t;
-    }
-    __syncthreads();
-    block_suffix_scan<FIT_NT>(s0, cx.nt, sm.red);
-    double ll = 0.0;
-    for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) ll += log(th[r] / s0[r]) * cx.y[r] * cx.w[r];
-    return block_sum<FIT_NT>(ll, sm.red);
-}
-// XB[r][a] = suffix_r(theta * XA[.][a]) / S0[r]   (risk-set means), chunked two-pass scan over rows
-__device__ void cox_riskset_means(const ChainCtx &cx, int ldA, double *XB, const double *th, const double *s0,
-                                  const FitSmem &sm)
-{
-    const int m = cx.m, nt = cx.nt;
-    // rows per chunk: chunk sums [nch][m] must fit the scratch region (FIT_NT*16 doubles)
-    const int nch_max = max(1, (FIT_NT * 16) / m);
-    const int CH = max(32, (nt + nch_max - 1) / nch_max);
-    const int nch = (nt + CH - 1) / CH;
-    double *csum = sm.scratch;  // [nch][m]   (needs nch*m <= FIT_NT*16)
-    for (int it = threadIdx.x; it < nch * m; it += FIT_NT) {
-        const int ch = it / m, a = it % m;
-        const int rb = ch * CH, re = min(nt, rb + CH);
-        double s = 0.0;
-        for (int r = re - 1; r >= rb; r--) s += th[r] * cx.XA[(size_t)r * ldA + a];
-        csum[it] = s;
-    }
-    __syncthreads();
-    // exclusive suffix over chunks per column (sequential over nch, parallel over columns)
-    for (int a = threadIdx.x; a < m; a += FIT_NT) {
-        double run = 0.0;
-        for (int ch = nch - 1; ch >= 0; ch--) {
-            const double t = csum[ch * m + a];
-            csum[ch * m + a] = run;
-            run += t;
-        }
-    }
-    __syncthreads();
-    for (int it = threadIdx.x; it < nch * m; it += FIT_NT) {
-        const int ch = it / m, a = it % m;
-        const int rb = ch * CH, re = min(nt, rb + CH);
-        double s = csum[it];
-        for (int r = re - 1; r >= rb; r--) {
-            s += th[r] * cx.XA[(size_t)r * ldA + a];
-            XB[(size_t)r * ldA + a] = s / s0[r];
-        }
-    }
-    __syncthreads();
-}
-__device__ int g_dbg_cox_iters = 30;  // debug knob (bess_b200_debug_set key 1); 30 = reference behaviour
-__device__ void fit_cox(const ChainCtx &cx, int ldA, double *XB, double *S2, int lds2, const FitSmem &sm)
-{
-    const int max_newton = g_dbg_cox_iters;
-    const int m = cx.m, nt = cx.nt;
-    double *b0 = sm.b0, *b1 = sm.b1;
-    double *th = cx.v[0], *s0 = cx.v[1], *ev = cx.v[2], *om = cx.v[3], *gv = cx.v[4];
-    for (int a = threadIdx.x; a < m; a += FIT_NT) b0[a] = 0.0;
-    __syncthreads();
-    double ll0 = 1e5;
-    for (int l = 1; l <= max_newton; l++) {
-        // theta (no weights here, Algorithm.h:1423), S0
-        for (int r = threadIdx.x; r < nt; r += FIT_NT) {
-            const double t = exp(clampd(row_dot(cx.XA + (size_t)r * ldA, b0, m), 30.0));
-            th[r] = t;
-            s0[r] = t;
-        }
-        __syncthreads();
-        block_suffix_scan<FIT_NT>(s0, nt, sm.red);
-        // e = w*status; C = prefix(e/S0); omega = theta*C; gvec = e - omega
-        for (int r = threadIdx.x; r < nt; r += FIT_NT) {
-            ev[r] = cx.w[r] * cx.y[r];
-            om[r] = ev[r] / s0[r];
-        }
-        __syncthreads();
-        block_prefix_scan<FIT_NT>(om, nt, sm.red);
-        for (int r = threadIdx.x; r < nt; r += FIT_NT) {
-            om[r] *= th[r];
-            gv[r] = ev[r] - om[r];
-        }
-        __syncthreads();
-        cox_riskset_means(cx, ldA, XB, th, s0, sm);
-        // g = X_A^T gv : use the augmented column trick with unit weights: column m of XA <- gv
-        for (int r = threadIdx.x; r < nt; r += FIT_NT) cx.XA[(size_t)r * ldA + m] = gv[r];
-        __syncthreads();
-        // P1 = X_A^T diag(omega) X_A  (last row unused); g from an unweighted product of [X_A | gv]
-        block_syrk(cx.XA, ldA, nt, m, om, cx.S, cx.lds, sm);
-        block_syrk(XB, ldA, nt, m, ev, S2, lds2, sm);
-        // g_a = sum_r XA[r][a]*gv[r]
-        {
-            // (a, slice) decomposition, deterministic reduction through scratch
-            const int nsl = max(1, FIT_NT / m);
-            for (int it = threadIdx.x; it < m * nsl; it += FIT_NT) {
-                const int a = it % m, sl = it / m;
-                double s = 0.0;
-                for (int r = sl; r < nt; r += nsl) s = fma(cx.XA[(size_t)r * ldA + a], gv[r], s);
-                sm.scratch[it] = s;
-            }
-            __syncthreads();
-            for (int a = threadIdx.x; a < m; a += FIT_NT) {
-                double s = 0.0;
-                for (int sl = 0; sl < nsl; sl++)
-                    if (a + sl * m < m * nsl) s += sm.scratch[sl * m + a];
-                sm.rhs[a] = s;
-            }
-            __syncthreads();
-        }
-        // P = P1 - P2 = -h ;  h d = g  =>  d = -P^{-1} g
-        for (int it = threadIdx.x; it < m * m; it += FIT_NT) {
-            const int a = it / m, bcol = it % m;
-            cx.S[(size_t)a * cx.lds + bcol] -= S2[(size_t)a * lds2 + bcol];
-        }
-        __syncthreads();
-        block_chol_solve(cx.S, cx.lds, m, sm.rhs, sm.dg);  // rhs = P^{-1} g = -d
-        // line search (Algorithm.h:1474-1481): beta1 = beta0 - 0.5^mm * d = beta0 + 0.5^mm * rhs
-        int mm = 1;
-        double step = 0.5;
-        for (int a = threadIdx.x; a < m; a += FIT_NT) b1[a] = b0[a] + step * sm.rhs[a];
-        __syncthreads();
-        double ll1 = cox_loglik(cx, ldA, b1, cx.v[5], cx.v[6], sm);
-        while (ll0 > ll1 && mm < 5) {
-            mm++;
-            step *= 0.5;
-            __syncthreads();
-            for (int a = threadIdx.x; a < m; a += FIT_NT) b1[a] = b0[a] + step * sm.rhs[a];
-            __syncthreads();
-            ll1 = cox_loglik(cx, ldA, b1, cx.v[5], cx.v[6], sm);
-        }
-        if (fabs(ll0 - ll1) / fabs(0.1 + ll0) < 1e-5) break;
-        __syncthreads();
-        for (int a = threadIdx.x; a < m; a += FIT_NT) b0[a] = b1[a];
-        ll0 = ll1;
-        __syncthreads();
-    }
-}
-
-// Gradient vectors of the next dual sweep from the chain's current (A, beta_A, coef0); X_A is in cx.XA.
-__device__ void chain_gradient(const Dev &d, const ChainCtx &cx, const double *bsl /*smem slopes*/, int ks, double coef0,
-                               const FitSmem &sm)
-{
-    const int c = cx.c, FS = d.FS, nt = cx.nt;
-    const int *rows = d.rows + (size_t)c * d.n;
-    const int fam = d.family;
-    if (fam != FAM_COX) {
-        for (int r = threadIdx.x; r < nt; r += FIT_NT) {
-            double eta = coef0;
-            const double *row = cx.XA + (size_t)r * d.ldA + cx.off;
-            for (int a = 0; a < ks; a++) eta = fma(row[a], bsl[a], eta);
-            const size_t o = (size_t)rows[r] * FS + c;
-            if (fam == FAM_LM) {
-                d.G[o] = (cx.y[r] - eta) / (double)nt;  // Algorithm.h:1109 (coef0 == 0 for gaussian)
-            } else if (fam == FAM_LOGIT) {
-                const double e = exp(clampd(eta, 30.0));  // Algorithm.h:1223-1236
-                const double pr = e / (e + 1.0);
-                d.G[o] = cx.w[r] * (cx.y[r] - pr);
-                d.W[o] = cx.w[r] * pr * (1.0 - pr);
-            } else {
-                const double e = exp(eta);  // Algorithm.h:1338-1341 (not clamped)
-                d.G[o] = (cx.y[r] - e) * cx.w[r];
-                d.W[o] = e * cx.w[r];
-            }
-        }
-        __syncthreads();
-        return;
-    }
-    // cox, Algorithm.h:1579-1630 restated with prefix/suffix sums
-    double *th = cx.v[0], *s0 = cx.v[1], *cc = cx.v[2];
-    for (int r = threadIdx.x; r < nt; r += FIT_NT) {
-        double eta = 0.0;
-        const double *row = cx.XA + (size_t)r * d.ldA + cx.off;
-        for (int a = 0; a < ks; a++) eta = fma(row[a], bsl[a], eta);
-        const double t = cx.w[r] * exp(clampd(eta, 30.0));
-        th[r] = t;
-        s0[r] = t;
-    }
-    __syncthreads();
-    block_suffix_scan<FIT_NT>(s0, nt, sm.red);
-    for (int r = threadIdx.x; r < nt; r += FIT_NT) cc[r] = (cx.y[r] != 0.0 ? cx.w[r] : 0.0) / s0[r];
-    __syncthreads();
-    block_prefix_scan<FIT_NT>(cc, nt, sm.red);
-    for (int r = threadIdx.x; r < nt; r += FIT_NT) {
-        const double e = cx.y[r] != 0.0 ? cx.w[r] : 0.0;
-        const double om = th[r] * cc[r];
-        const size_t o = (size_t)rows[r] * FS + c;
-        d.G[o] = e - om;
-        d.W[o] = om;
-        d.TH[o] = th[r];
-        d.C2[o] = e / (s0[r] * s0[r]);
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ ChainCtx make_ctx(const Dev &d, int c, int T, const FitSmem &sm)
-{
-    ChainCtx cx;
-    cx.c = c;
-    cx.nt = d.ntrain[c];
-    cx.T = T;
-    cx.off = (d.family == FAM_LOGIT || d.family == FAM_POISSON) ? 1 : 0;
-    cx.m = T + cx.off;
-    cx.XA = d.XA + (size_t)c * d.n * d.ldA;
-    cx.y = d.ytr + (size_t)c * d.n;
-    cx.w = d.wtr + (size_t)c * d.n;
-    for (int q = 0; q < NVEC; q++) cx.v[q] = d.vec + ((size_t)c * NVEC + q) * d.n;
-    const int mmax = cx.m + 1;
-    if (mmax <= FIT_SMEM_MS) {
-        cx.S = sm.Ssm;
-        cx.lds = FIT_SMEM_MS;
-    } else {
-        cx.S = d.Smat + (size_t)c * 2 * d.ldA * d.ldA;
-        cx.lds = d.ldA;
-    }
-    return cx;
-}
-
-// Start of a batch (Algorithm::fit prologue, Algorithm.h:141-148): coef0 <- coef0_init, l <- 0, A_list.col(0) <- 0,
-// gradient vectors from beta_init.
-__global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, const BatchDesc b)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA);
-    const int c = b.chain[blockIdx.x];
-    // Algorithm::coef0_init is only refreshed when the path starts a new step (path.cpp:57); CV folds of the same
-    // step inherit it.
-    double level;
-    if (!d.warm) level = 0.0;
-    else if (b.new_path_step) level = d.coef0[0];
-    else level = *d.coef0_level;
-    __syncthreads();
-    int ks = d.ks[c];
-    if (!d.warm) {
-        // cold start: beta_init = 0
-        for (int a = threadIdx.x; a < ks; a += FIT_NT) d.betaD[(size_t)c * d.pstride + d.A[(size_t)c * d.kcap + a]] = 0.0;
-        ks = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (blockIdx.x == 0 && b.new_path_step) *d.coef0_level = level;
-        if (blockIdx.x == 0) *d.n_active = b.nch;
-        d.tie_acc[c] = 0;
-        if (!(c == 0 && b.new_path_step && d.warm)) d.coef0[c] = level;
-        d.ks[c] = ks;
-        d.l[c] = 0;
-        d.done[c] = 0;
-    }
-    int *h0 = d.hist + (size_t)c * MAX_HIST * d.kcap;
-    for (int a = threadIdx.x; a < b.T; a += FIT_NT) h0[a] = 0;
-    for (int a = threadIdx.x; a < ks; a += FIT_NT) sm.b0[a] = d.bA[(size_t)c * d.kcap + a];
-    __syncthreads();
-    ChainCtx cx = make_ctx(d, c, ks, sm);
-    chain_gradient(d, cx, sm.b0, ks, level, sm);
-}
-
-// One PDAS iteration after the top-k (Algorithm.h:154-170) + gradient vectors for the next one.
-__global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const BatchDesc b)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA);
-    const int c = b.chain[blockIdx.x];
-    if (d.done[c]) return;
-    const int T = b.T;
-    ChainCtx cx = make_ctx(d, c, T, sm);
-    const int ldA = d.ldA;
-    const int *Anew = d.Anew + (size_t)c * d.kcap;
-    const int *rows = d.rows + (size_t)c * d.n;
-    int *Acur = d.A + (size_t)c * d.kcap;
-    const int ks_old = d.ks[c];
-    const double coef0_in = d.coef0[c];
-
-    // clear the dense beta on the old support (Algorithm.h:159)
-    for (int a = threadIdx.x; a < ks_old; a += FIT_NT) d.betaD[(size_t)c * d.pstride + Acur[a]] = 0.0;
-    // gather X_A (utilities.cpp:132-140): XA[r][off + a] = X[rows[r]][A[a]]
-    for (int it0 = threadIdx.x; it0 < cx.nt * T; it0 += 4 * FIT_NT) {
-        double val[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int it = it0 + q * FIT_NT;
-            if (it < cx.nt * T) val[q] = __ldg(d.X + (size_t)rows[it / T] * d.ldx + Anew[it % T]);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int it = it0 + q * FIT_NT;
-            if (it < cx.nt * T) cx.XA[(size_t)(it / T) * ldA + cx.off + (it % T)] = val[q];
-        }
-    }
-    if (cx.off)
-        for (int r = threadIdx.x; r < cx.nt; r += FIT_NT) cx.XA[(size_t)r * ldA] = 1.0;
-    __syncthreads();
-
-    double coef0 = coef0_in;
-    const double *slopes;
-    if (d.family == FAM_LM) {
-        fit_lm(cx, ldA, sm, sm.b0);
-        slopes = sm.b0;
-    } else if (d.family == FAM_LOGIT) {
-        fit_logistic(cx, ldA, sm);
-        coef0 = sm.b0[0];
-        slopes = sm.b0 + 1;
-    } else if (d.family == FAM_POISSON) {
-        fit_poisson(cx, ldA, coef0_in, sm);
-        coef0 = sm.b0[0];
-        slopes = sm.b0 + 1;
-    } else {
-        fit_cox(cx, ldA, d.XB + (size_t)c * d.n * ldA, d.Smat + ((size_t)c * 2 + 1) * ldA * ldA, ldA, sm);
-        slopes = sm.b0;
-    }
-    __syncthreads();
-    // scatter (Algorithm.h:159-163), record A, cycle test (Algorithm.h:164-170)
-    const int l = d.l[c] + 1;
-    int *hl = d.hist + ((size_t)c * MAX_HIST + l) * d.kcap;
-    for (int a = threadIdx.x; a < T; a += FIT_NT) {
-        const int j = Anew[a];
-        Acur[a] = j;
-        hl[a] = j;
-        d.bA[(size_t)c * d.kcap + a] = slopes[a];
-        d.betaD[(size_t)c * d.pstride + j] = slopes[a];
-    }
-    __syncthreads();
-    int seen = 0;
-    for (int ll = 0; ll < l && !seen; ll++) {
-        const int *hp = d.hist + ((size_t)c * MAX_HIST + ll) * d.kcap;
-        int same = 1;
-        for (int a = threadIdx.x; a < T; a += FIT_NT) same &= (hp[a] == Anew[a]);
-        seen = __syncthreads_and(same);
-    }
-    const int finished = seen || l >= d.max_iter;
-    if (threadIdx.x == 0) {
-        d.l[c] = seen ? l : (l >= d.max_iter ? d.max_iter + 1 : l);
-        d.ks[c] = T;
-        d.coef0[c] = coef0;
-        d.done[c] = finished;
-        d.tie_acc[c] += d.tie[c];
-        if (finished) atomicSub(d.n_active, 1);
-    }
-    if (finished) return;
-    chain_gradient(d, cx, slopes, T, coef0, sm);
-}
-
-void debug_set(int key, int val)
-{
-    if (key == 1) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_cox_iters, &val, sizeof(int)));
-}
-
 void configure_kernels()
 {
     CUDA_CHECK(cudaFuncSetAttribute(topk_slices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_LMAX * 8));
-}
-
-void launch_chain_begin(const Dev &d, const BatchDesc &b, cudaStream_t st)
-{
-    const size_t smem = fit_smem_bytes(d);
-    CUDA_CHECK(cudaFuncSetAttribute(chain_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chain_begin_kernel<<<b.nch, FIT_NT, smem, st>>>(d, b);
-    CUDA_CHECK(cudaGetLastError());
-}
-void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st)
-{
-    const size_t smem = fit_smem_bytes(d);
-    CUDA_CHECK(cudaFuncSetAttribute(chain_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chain_fit_kernel<<<b.nch, FIT_NT, smem, st>>>(d, b);
-    CUDA_CHECK(cudaGetLastError());
 }
 
 // =====================================================================================================

@@ -12,6 +12,7 @@ constexpr int SWEEP_RC = 64;     // rows per TMA-staged chunk of the gradient ve
 constexpr int FIT_NT = 512;      // threads per chain_fit CTA (one CTA per chain)
 constexpr int TOPK_NT = 1024;
 constexpr int TOPK_LMAX = 16384; // keys per top-k slice held in shared memory (128 KB)
+constexpr int CLMAX = 8;         // max thread-block cluster size of chain_fit_kernel (portable limit)
 
 // sweep modes
 enum { MODE_D = 0, MODE_DH = 1, MODE_COX = 2 };
@@ -52,7 +53,11 @@ struct Dev {
     double *XA;         // [MAXC][n][ldA] gathered active columns (+ intercept / working response columns)
     double *XB;         // [MAXC][n][ldA] cox: risk-set means
     double *vec;        // [MAXC][NVEC][n]
-    double *Smat;       // [MAXC][ldA*ldA] Gram / Cholesky workspace (when it does not fit in smem)
+    double *Smat;       // [MAXC][2][ldA*ldA] normal equations (when they do not fit in smem) / Cox second Gram
+    double *Spart;      // [MAXC][CLcap][nmat][ldA*ldA] per-CTA partial Grams of a cluster (nullptr when CLcap == 1)
+    double *cw;         // [MAXC][CLMAX][4][ldA] cluster exchange vectors
+    int CLcap;          // largest cluster size the workspaces were sized for
+    int nmat;           // Gram matrices per fit step: 2 for cox, else 1
     double *xtx;        // [MAXC][p] x_j.x_j over the chain's train rows (gaussian only)
     // sweep vectors [n][FS]
     double *G, *W, *TH, *C2;
@@ -70,6 +75,7 @@ struct BatchDesc {
     int chain[MAXC];
     int T;
     int new_path_step;
+    int CL;  // cluster size of chain_fit_kernel for this batch
 };
 
 struct LossDesc {
@@ -101,6 +107,7 @@ void launch_gather_cols_pos(const double *X, long long ldx, int n, const int *co
 void launch_screen_glm(const double *X, long long ldx, int n, int p, const double *y, const double *w, int family,
                        double *util, cudaStream_t st);
 size_t fit_smem_bytes(const Dev &d);
+int chain_cluster_size(const Dev &d, int T, int nch);
 void configure_kernels();
 void debug_set(int key, int val);
 

@@ -58,8 +58,8 @@ struct BessResult {
     std::vector<double> coef0_all, train_loss_all, ic_all;
     std::vector<int> s_all, l_all;
     EngineStats stats;
-    double prof_ms[6] = {0, 0, 0, 0, 0, 0};
-    long long prof_n[6] = {0, 0, 0, 0, 0, 0};
+    double prof_ms[PROF_NCAT] = {};
+    long long prof_n[PROF_NCAT] = {};
     int sweep_splits = 1;
 };
 

@@ -61,11 +61,12 @@ typedef struct bess_b200_ext {
     int device;               /* CUDA device ordinal, -1 = current                                                    */
     int *screening_A_out;     /* [screening_size] kept columns, ascending (List key "screening_A", bess.cpp:199)     */
     int *chosen_s_out;        /* sparsity level of the returned model                                                 */
-    double *stats_out;        /* [24]: 0 n_fits, 1 n_pdas_iters, 2 n_sweeps, 3 n_batches, 4 n_boundary_ties,          */
+    double *stats_out;        /* [32]: 0 n_fits, 1 n_pdas_iters, 2 n_sweeps, 3 n_batches, 4 n_boundary_ties,          */
                               /*  5 PDAS dual-sweep algorithmic bytes, 6 kernel_launches, 7 trace_len,                */
-                              /*  8..13 device ms per kernel category (profile != 0): screening/normalise passes,     */
-                              /*  PDAS dual sweeps, finish, top-k, chain kernels, other; 14..19 launches per category;*/
-                              /*  20 algorithmic bytes of the screening/normalise passes; 21 sweep row splits         */
+                              /*  8..15 device ms per kernel category (profile != 0): screening sweep, PDAS dual      */
+                              /*  sweeps, finish, top-k, chain kernels, other, normalisation passes, H2D upload;      */
+                              /*  16..23 launches per category; 24 algorithmic bytes of the screening sweep (8np);    */
+                              /*  25 sweep row splits; 26 algorithmic bytes of the normalisation / x_j.x_j passes     */
     int profile;              /* record CUDA events around every kernel category on the engine's stream               */
 } bess_b200_ext;
 

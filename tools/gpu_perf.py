@@ -23,7 +23,7 @@ def show(tag, out, dt):
           f"S={st['sweep_splits']}\n    prof_ms={prof} n={st['prof_launches']}", flush=True)
     if st["prof_ms"]["dual_sweep"] > 0:
         print(f"    PDAS sweep: {st['sweep_bytes']/st['prof_ms']['dual_sweep']/1e6:.0f} GB/s algorithmic; "
-              f"setup passes: {st['big_sweep_bytes']/max(st['prof_ms']['setup_passes'],1e-9)/1e6:.0f} GB/s", flush=True)
+              f"screening sweep: {st['big_sweep_bytes']/max(st['prof_ms']['screen_sweep'],1e-9)/1e6:.0f} GB/s", flush=True)
 
 
 def run(tag, fam, n, p, k, path_type, is_cv, K, ic_type, seq, s_min, s_max, scr, seed, reps=2, x=None, d=None):
