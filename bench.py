@@ -262,6 +262,41 @@ def run_ours(args):
                  "ms_per_launch": pms, "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                  "frac": pbytes / (pms * 1e-3) / 1e9 / peak, "algorithmic_bytes": pbytes}
 
+    # ---- C5b: config 5 WITHOUT screening -- every PDAS dual sweep is p=500k-sized; at N > 1 each iteration is sharded by
+    # columns (local sweep + local top-k, NCCL all-gather of candidates, all-reduce of the k active columns).  This is the
+    # part of the path whose work grows with p and therefore the part that scales with GPUs.
+    def c5b_call():
+        if world == 1:
+            return cbess.fit(None, y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, SMAX, False, 1, cv_seed=123,
+                             device=local_rank, x_device_ptr=Xs.data_ptr(), n=N_ROWS, p=P_COLS, want_trace=False)
+        return bdist.fit_column_sharded(None, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX, 0,
+                                        cv_seed=123, device=local_rank, x_shard_device_ptr=Xs.data_ptr(), n=N_ROWS,
+                                        p_local=hi - lo)
+    c5b = None
+    if not args.no_c5b:
+        for _ in range(2):
+            ob = c5b_call()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nb = 5
+        e0.record()
+        for _ in range(nb):
+            ob = c5b_call()
+        e1.record()
+        torch.cuda.synchronize()
+        tb = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        ms_b = float(tb.item()) / nb
+        sb = ob["stats"]
+        c5b = {"workload": "C5b: config 5 with screening off (PDAS dual sweeps over all 500000 columns, 11 chains per pass)",
+               "ms_per_call": ms_b, "fits_per_s": 220 / (ms_b * 1e-3), "pdas_sweeps_per_call": sb["n_sweeps"],
+               "chosen_s": int(ob["s"]), "aggregate_sweep_GBps_incl_all_other_work": world * sb["sweep_bytes"] / (ms_b * 1e-3) / 1e9,
+               "parallelism": "single GPU" if world == 1 else f"columns sharded over {world} ranks, NCCL all-gather of "
+                              "top-k candidates + all-reduce of active columns every PDAS iteration"}
+
     base = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     if rank == 0:
         line = {
@@ -290,7 +325,7 @@ def run_ours(args):
                          "kernel_ms_per_step": {k: float(v / args.steps) for k, v in zip(cbess.PROF_CATS, prof_ms)},
                          "kernel_share_of_step": float(total_kernel_ms / args.steps / (ms / args.steps)),
                          "p500k_pdas_sweep": probe},
-            "cpu_baseline": base,
+            "cpu_baseline": base, "c5b_no_screening": c5b,
             "fits_per_step": fits_per_step, "n_boundary_ties": int(st["n_boundary_ties"]),
         }
         print(json.dumps(line))
@@ -305,6 +340,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5b", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -22,7 +22,9 @@ class BessB200Error(RuntimeError):
 class Ext(C.Structure):
     """struct bess_b200_ext (include/bess_b200.h)"""
     _fields_ = [("fold_of_row", ip), ("cv_seed", C.c_uint), ("x_on_device", C.c_int), ("device", C.c_int),
-                ("screening_A_out", ip), ("chosen_s_out", ip), ("stats_out", dp), ("profile", C.c_int)]
+                ("screening_A_out", ip), ("chosen_s_out", ip), ("stats_out", dp), ("profile", C.c_int),
+                ("world", C.c_int), ("rank", C.c_int), ("col_lo", C.c_longlong), ("p_total", C.c_longlong),
+                ("nccl_unique_id", C.c_void_p)]
 
 
 _PYWRAP_ARGS = [dp, C.c_int, C.c_int, dp, C.c_int, C.c_int, dp, C.c_int, C.c_bool, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -67,6 +69,7 @@ def load():
     lib.bess_b200_shard_range.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong),
                                           C.POINTER(C.c_longlong)]
     lib.bess_b200_chain_owner.argtypes = [C.c_int, C.c_int]
+    lib.bess_b200_nccl_unique_id.argtypes = [C.c_void_p]
     lib.bess_b200_merge_candidates.argtypes = [dp, ip, C.c_int, C.c_int, ip]
     _lib = lib
     return lib

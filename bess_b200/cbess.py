@@ -69,9 +69,13 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
 
 def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
-        fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False):
+        fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
+        world=1, rank=0, col_lo=0, p_total=None, nccl_id=None):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
-    ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``."""
+    ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``.
+    ``world > 1``: column-sharded multi-GPU call -- ``x`` is this rank's column shard ``[col_lo, col_lo + p)`` of a
+    ``p_total``-column design, ``nccl_id`` the job's 128-byte NCCL unique id (``bess_b200.dist.nccl_unique_id``); beta
+    and always_select use global column numbers."""
     lib = _lib.load()
     if x_device_ptr is None:
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -85,9 +89,18 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     st, lam = np.zeros(1), np.zeros(1)
     seq = np.ascontiguousarray(sequence, dtype=np.int32).ravel()
     alw = np.ascontiguousarray(list(always_select), dtype=np.int32).ravel()
-    beta = np.zeros(p)
+    sharded = world > 1
+    p_all = int(p_total) if sharded else p
+    beta = np.zeros(p_all)
     c0, tl, ic = C.c_double(0), C.c_double(0), C.c_double(0)
     ext = Ext()
+    if sharded:
+        if nccl_id is None or len(nccl_id) != 128:
+            raise ValueError("sharded fit needs the 128-byte NCCL unique id")
+        idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+        ext.world, ext.rank, ext.col_lo, ext.p_total = int(world), int(rank), int(col_lo), p_all
+        ext.nccl_unique_id = C.cast(idbuf, C.c_void_p)
+        want_trace = False
     fold = None
     if fold_of_row is not None:
         fold = np.ascontiguousarray(fold_of_row, dtype=np.int32)
@@ -106,7 +119,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
                            int(algorithm_type), int(model_type), int(max_iter), int(exchange_num), int(path_type),
                            bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g), g.size, _d(st), 1, _i(seq),
                            seq.size, _d(lam), 1, int(s_min), int(s_max), 10, 10.0, 0.0, 0.0, 1, bool(is_screening),
-                           int(screening_size), 1, _i(alw), alw.size, 1.1, _d(beta), p, C.byref(c0), C.byref(tl),
+                           int(screening_size), 1, _i(alw), alw.size, 1.1, _d(beta), p_all, C.byref(c0), C.byref(tl),
                            C.byref(ic), C.byref(ext))
     _lib.check(rc)
     out = dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, s=chosen.value,

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "kernels.cuh"
+#include "nccl_dl.h"
 #include "path.h"
 
 using namespace bess;
@@ -61,7 +62,8 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
 {
     return guarded([&] {
         if (y_len != x_row || weight_len != x_row) throw EngineError{"y/weight length must equal the number of rows of x"};
-        if (beta_out && beta_out_len < x_col) throw EngineError{"beta_out shorter than p"};
+        const bool shard = ext && ext->world > 1;
+        if (beta_out && beta_out_len < (shard ? ext->p_total : (long long)x_col)) throw EngineError{"beta_out shorter than p"};
         BessArgs a;
         a.x = x; a.n = x_row; a.p = x_col; a.y = y; a.data_type = data_type; a.weight = weight;
         a.is_normal = is_normal; a.algorithm_type = algorithm_type; a.model_type = model_type; a.max_iter = max_iter;
@@ -73,7 +75,7 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
         a.s_min = s_min; a.s_max = s_max; a.K_max = K_max; a.epsilon = epsilon; a.lambda_min = lambda_min;
         a.lambda_max = lambda_max; a.nlambda = n_lambda; a.is_screening = is_screening;
         a.screening_size = screening_size; a.powell_path = powell_path;
-        if (gindex && gindex_len > 0) a.g_index.assign(gindex, gindex + gindex_len);
+        if (gindex && gindex_len > 0 && !shard) a.g_index.assign(gindex, gindex + gindex_len);
         if (always_select && always_select_len > 0) a.always_select.assign(always_select, always_select + always_select_len);
         a.tao = tao;
         a.cv_seed = env_seed();
@@ -83,6 +85,13 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
             a.x_on_device = ext->x_on_device != 0;
             a.device = ext->device;
             a.profile = ext->profile != 0;
+            if (shard) {
+                a.world = ext->world;
+                a.rank = ext->rank;
+                a.col_lo = ext->col_lo;
+                a.p_total = ext->p_total;
+                a.nccl_id = ext->nccl_unique_id;
+            }
         }
         BessResult r;
         bess_run(a, r);
@@ -201,6 +210,16 @@ int bess_b200_cv_fold_ids(int n, int K, unsigned seed, int *out)
         if (n < 1 || K < 1 || K > n) throw EngineError{"cv_fold_ids: need 1 <= K <= n"};
         std::vector<int> f = cv_fold_ids(n, K, seed);
         std::copy(f.begin(), f.end(), out);
+    });
+}
+
+int bess_b200_nccl_unique_id(void *out128)
+{
+    return guarded([&] {
+        ncclUniqueId id;
+        ncclResult_t r = nccl_api().GetUniqueId(&id);
+        if (r != ncclSuccess) throw EngineError{std::string("ncclGetUniqueId: ") + nccl_api().GetErrorString(r)};
+        std::memcpy(out128, id.internal, NCCL_UNIQUE_ID_BYTES);
     });
 }
 
@@ -359,13 +378,7 @@ int bess_b200_debug_set(int key, int val)
 // ---- multi-GPU host helpers ------------------------------------------------------------------------------------------
 void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi)
 {
-    // contiguous, even-aligned shards (16-byte loads need even column offsets), remainder spread over the first ranks
-    const long long pairs = (p + 1) / 2;
-    const long long base = pairs / world, rem = pairs % world;
-    const long long b = rank * base + std::min<long long>(rank, rem);
-    const long long e = b + base + (rank < rem ? 1 : 0);
-    *lo = std::min(p, 2 * b);
-    *hi = std::min(p, 2 * e);
+    shard_range(p, world, rank, lo, hi);
 }
 int bess_b200_chain_owner(int chain, int world) { return world > 0 ? chain % world : 0; }
 int bess_b200_merge_candidates(const double *vals, const int *idx, int count, int k, int *idx_out)

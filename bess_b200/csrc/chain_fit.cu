@@ -912,7 +912,10 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, con
     int ks = d.ks[c];
     if (!d.warm) {
         // cold start: beta_init = 0
-        for (int a = threadIdx.x; a < ks; a += FIT_NT) d.betaD[(size_t)c * d.pstride + d.A[(size_t)c * d.kcap + a]] = 0.0;
+        for (int a = threadIdx.x; a < ks; a += FIT_NT) {
+            const int j = d.A[(size_t)c * d.kcap + a] - d.col_lo;
+            if (j >= 0 && j < d.p) d.betaD[(size_t)c * d.pstride + j] = 0.0;
+        }
         ks = 0;
     }
     __syncthreads();
@@ -958,7 +961,10 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
 
     // clear the dense beta on the old support (Algorithm.h:159)
     if (cl.rank == 0)
-        for (int a = threadIdx.x; a < ks_old; a += FIT_NT) d.betaD[(size_t)c * d.pstride + Acur[a]] = 0.0;
+        for (int a = threadIdx.x; a < ks_old; a += FIT_NT) {
+            const int j = Acur[a] - d.col_lo;
+            if (j >= 0 && j < d.p) d.betaD[(size_t)c * d.pstride + j] = 0.0;
+        }
     // gather X_A (utilities.cpp:132-140): XA[r][off + a] = X[rows[r]][A[a]], this CTA's row slice, 8 loads in flight
     {
         const int nloc = cx.re - cx.rb;
@@ -970,7 +976,8 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
                 const int it = it0 + q * FIT_NT;
                 if (it < tot) {
                     const int r = it / T, a = it - r * T;
-                    val[q] = __ldg(d.X + (size_t)rows[cx.rb + r] * d.ldx + Anew[a]);
+                    val[q] = d.sharded ? d.AXr[((size_t)c * d.n + rows[cx.rb + r]) * d.ldXr + a]
+                                       : __ldg(d.X + (size_t)rows[cx.rb + r] * d.ldx + Anew[a]);
                 }
             }
 #pragma unroll
@@ -984,6 +991,14 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
         }
         if (cx.off)
             for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) cx.XA[(size_t)r * ldA] = 1.0;
+        if (d.sharded) {  // keep the all-row columns of this support for the loss kernel
+            const double *src = d.AXr + (size_t)c * d.n * d.ldXr;
+            double *dst = d.AXk + (size_t)c * d.n * d.ldXk;
+            for (int e = cl.rank * FIT_NT + threadIdx.x; e < d.n * T; e += cl.CL * FIT_NT) {
+                const int i = e / T, a = e - i * T;
+                dst[(size_t)i * d.ldXk + a] = src[(size_t)i * d.ldXr + a];
+            }
+        }
     }
     __syncthreads();
 
@@ -1023,7 +1038,8 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
             Acur[a] = j;
             hl[a] = j;
             d.bA[(size_t)c * d.kcap + a] = slopes[a];
-            d.betaD[(size_t)c * d.pstride + j] = slopes[a];
+            const int jl = j - d.col_lo;
+            if (jl >= 0 && jl < d.p) d.betaD[(size_t)c * d.pstride + jl] = slopes[a];
         }
         if (threadIdx.x == 0) {
             d.l[c] = seen ? l : (l >= d.max_iter ? d.max_iter + 1 : l);

@@ -2,6 +2,7 @@
 // See engine.h for the vocabulary.  All compute is on the GPU; there is no CPU fallback anywhere in this file.
 #include "kernels.cuh"
 #include "device_utils.cuh"
+#include "nccl_dl.h"
 
 #include <algorithm>
 #include <cmath>
@@ -10,6 +11,14 @@
 #include <numeric>
 
 namespace bess {
+
+#define NCCL_CHECK(x)                                                                              \
+    do {                                                                                           \
+        ncclResult_t r_ = (x);                                                                     \
+        if (r_ != ncclSuccess) {                                                                   \
+            throw EngineError{std::string(#x) + ": " + nccl_api().GetErrorString(r_)};             \
+        }                                                                                          \
+    } while (0)
 
 namespace {
 // Stream-ordered allocation from the device's default memory pool (release threshold raised to "never" in
@@ -42,6 +51,10 @@ struct DeviceContext {
     double *h_bA = nullptr;
     size_t cap_A = 0;
     bool in_use = false;
+    // NCCL communicator of the column-sharded mode, created once per (world, rank, unique id)
+    ncclComm_t comm = nullptr;
+    int comm_world = 0, comm_rank = -1;
+    char comm_id[NCCL_UNIQUE_ID_BYTES] = {};
     void reserve_support(size_t count)
     {
         if (count <= cap_A) return;
@@ -130,6 +143,15 @@ struct Engine::Impl {
     double *h_coef0 = nullptr, *h_bA = nullptr, *h_loss = nullptr;
     bool chains_ready = false;
     bool x_owned = true;
+    // column-sharded mode
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    Cand *cand_s = nullptr, *cand_r = nullptr;  // [C][kcap] local candidates, [world][C][kcap] gathered
+    double *mv = nullptr;                        // [C][world * kcap] merged candidate values
+    int *mi = nullptr;                           // ... and global indices
+    long long mstride = 0;
+    int *Aloc = nullptr;                         // [C][kcap] local top-k (local column indices)
+    double *AXs = nullptr;                       // [C][n][T] this rank's contribution to the active columns
     // ---- per-category device timing (CUDA events on the engine stream), enabled by Engine::set_profiling
     bool prof = false;
     struct Span { cudaEvent_t a, b; int cat; };
@@ -186,6 +208,8 @@ struct Engine::Impl {
         dfree(m.st, d.betaD); dfree(m.st, d.XA); dfree(m.st, d.XB); dfree(m.st, d.vec); dfree(m.st, d.Smat); dfree(m.st, d.Spart); dfree(m.st, d.cw); dfree(m.st, d.xtx);
         dfree(m.st, testrows); dfree(m.st, ntest); dfree(m.st, lfact); dfree(m.st, loss_scratch); dfree(m.st, loss_out); dfree(m.st, always);
         dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
+        dfree(m.st, cand_s); dfree(m.st, cand_r); dfree(m.st, mv); dfree(m.st, mi); dfree(m.st, Aloc); dfree(m.st, AXs);
+        dfree(m.st, d.AXr); dfree(m.st, d.AXk);
         chains_ready = false;
     }
     // (re)allocate the sweep vectors / partial buffers for FS chain slots over the current (n, p)
@@ -261,6 +285,41 @@ Engine::~Engine()
 }
 
 void Engine::set_profiling(bool on) { d_->prof = on; }
+
+void Engine::init_shard(int world, int rank, const void *unique_id, long long col_lo, long long p_total)
+{
+    Impl &m = *d_;
+    if (world < 2) throw EngineError{"init_shard: world must be >= 2"};
+    if (rank < 0 || rank >= world) throw EngineError{"init_shard: rank out of range"};
+    if (!unique_id) throw EngineError{"init_shard: the NCCL unique id is missing"};
+    if (p_total > 2147483646LL) throw EngineError{"init_shard: p_total must fit a 32-bit index"};
+    long long lo, hi;
+    shard_range(p_total, world, rank, &lo, &hi);
+    if (lo != col_lo) throw EngineError{"init_shard: col_lo does not match bess_b200_shard_range(p_total, world, rank)"};
+    DeviceContext *c = m.ctx;
+    if (!(c->comm && c->comm_world == world && c->comm_rank == rank &&
+          std::memcmp(c->comm_id, unique_id, NCCL_UNIQUE_ID_BYTES) == 0)) {
+        const NcclApi &api = nccl_api();
+        if (c->comm) {
+            api.CommDestroy(c->comm);
+            c->comm = nullptr;
+        }
+        ncclUniqueId id;
+        std::memcpy(id.internal, unique_id, NCCL_UNIQUE_ID_BYTES);
+        NCCL_CHECK(api.CommInitRank(&c->comm, world, id, rank));
+        c->comm_world = world;
+        c->comm_rank = rank;
+        std::memcpy(c->comm_id, unique_id, NCCL_UNIQUE_ID_BYTES);
+    }
+    m.comm = c->comm;
+    m.world = world;
+    m.rank = rank;
+    sharded_ = true;
+    world_ = world;
+    rank_ = rank;
+    col_lo_ = col_lo;
+    p_total_ = p_total;
+}
 void Engine::profile(double *ms_out, long long *n_out) const
 {
     for (int i = 0; i < PROF_NCAT; i++) {
@@ -275,6 +334,11 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     Impl &m = *d_;
     if (n < 2 || p < 1) throw EngineError{"load: need n >= 2 and p >= 1"};
     if (family < 1 || family > 4) throw EngineError{"load: model_type must be 1..4"};
+    if (sharded_) {
+        long long lo, hi;
+        shard_range(p_total_, world_, rank_, &lo, &hi);
+        if (hi - lo != p) throw EngineError{"load: the shard must hold exactly the columns of bess_b200_shard_range"};
+    }
     m.free_chain_buffers();
     m.free_sweep_buffers();
     if (m.x_owned) dfree(m.st, m.X);
@@ -306,6 +370,8 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     CUDA_CHECK(cudaMemcpyAsync(m.w, weight, n * 8, cudaMemcpyHostToDevice, m.st));
     m.d = Dev{};
     m.d.family = family;
+    m.d.sharded = sharded_ ? 1 : 0;
+    m.d.col_lo = (int)col_lo_;
     h_xmean_.assign(p, 0.0);
     h_xnorm_.assign(p, 0.0);
     y_mean_ = 0.0;
@@ -320,28 +386,70 @@ static void screen_select(Engine::Impl &m, EngineStats &st, int family, int size
 std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
 {
     Impl &m = *d_;
-    if (size < 1 || size > m.p) throw EngineError{"screening_size must be in [1, p]"};
-    int *d_sel = dalloc<int>(m.st, size);
+    if (size < 1 || size > p_model()) throw EngineError{"screening_size must be in [1, p]"};
     std::vector<int> sel;
-    screen_select(m, stats_, family_, size, always_select, d_sel, nullptr, &sel);
-    // X <- X[:, sel]  (screening.cpp:83-88)
     const long long ldn = (size + 1) & ~1LL;
     double *Xn = dalloc<double>(m.st, (size_t)m.n * ldn);
     if (ldn != size) CUDA_CHECK(cudaMemsetAsync(Xn, 0, (size_t)m.n * ldn * 8, m.st));
-    const int spk = m.span_begin(5);
-    launch_gather_cols(m.X, m.ldx, m.n, d_sel, size, Xn, ldn, m.st);
-    m.span_end(spk);
+    if (!sharded_) {
+        int *d_sel = dalloc<int>(m.st, size);
+        screen_select(m, stats_, family_, size, always_select, d_sel, nullptr, &sel);
+        // X <- X[:, sel]  (screening.cpp:83-88)
+        const int spk = m.span_begin(5);
+        launch_gather_cols(m.X, m.ldx, m.n, d_sel, size, Xn, ldn, m.st);
+        m.span_end(spk);
+        stats_.kernel_launches += 1;
+        dfree(m.st, d_sel);
+    } else {
+        // Column-sharded screening (SURVEY 8e axis B): marginal utilities of the local columns, exact local top-`size`,
+        // NCCL all-gather of the (utility, global index) candidates, identical merge on every rank, then every rank
+        // contributes the kept columns it owns and an all-reduce(sum) over NVLink hands the n x size screened design
+        // to everybody (adding zeros is exact, so all ranks hold bit-identical copies).
+        const NcclApi &api = nccl_api();
+        const int kloc = std::min<long long>(size, m.p);
+        std::vector<int> alw_local;
+        for (int j : always_select)
+            if (j >= col_lo_ && j < col_lo_ + m.p) alw_local.push_back((int)(j - col_lo_));
+        int *d_sel = dalloc<int>(m.st, size);
+        screen_select(m, stats_, family_, kloc, alw_local, d_sel, nullptr, nullptr);
+        Cand *cs = dalloc<Cand>(m.st, size), *cr = dalloc<Cand>(m.st, (size_t)m.world * size);
+        const long long n_in = (long long)m.world * size;
+        double *mv = dalloc<double>(m.st, n_in);
+        int *mi = dalloc<int>(m.st, n_in), *d_gsel = dalloc<int>(m.st, size), *d_tie = dalloc<int>(m.st, 1);
+        const long long cstride = std::max<long long>(2LL * size + 16, (n_in / 8192 + 2) * std::min(size, TOPK_LMAX));
+        double *ck0 = dalloc<double>(m.st, cstride), *ck1 = dalloc<double>(m.st, cstride);
+        int *ci0 = dalloc<int>(m.st, cstride), *ci1 = dalloc<int>(m.st, cstride);
+        const int spx = m.span_begin(5);
+        launch_pack_candidates(m.d.bd, m.d.pstride, d_sel, size, kloc, size, col_lo_, 1, cs, size, nullptr, m.st);
+        NCCL_CHECK(api.AllGather(cs, cr, (size_t)size * sizeof(Cand), ncclChar, m.comm, m.st));
+        launch_unpack_candidates(cr, m.world, 1, size, size, mv, mi, n_in, nullptr, m.st);
+        launch_topk(mv, n_in, (int)n_in, size, 1, d_gsel, size, d_tie, ck0, ci0, ck1, ci1, cstride, m.st, nullptr, mi);
+        launch_gather_owned_cols(m.X, m.ldx, m.n, m.p, col_lo_, d_gsel, size, Xn, ldn, m.st);
+        NCCL_CHECK(api.AllReduce(Xn, Xn, (size_t)m.n * ldn, ncclDouble, ncclSum, m.comm, m.st));
+        m.span_end(spx);
+        sel.resize(size);
+        int tie = 0;
+        CUDA_CHECK(cudaMemcpyAsync(sel.data(), d_gsel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        stats_.n_boundary_ties += tie;
+        stats_.kernel_launches += 4;
+        dfree(m.st, d_sel); dfree(m.st, cs); dfree(m.st, cr); dfree(m.st, mv); dfree(m.st, mi); dfree(m.st, d_gsel);
+        dfree(m.st, d_tie); dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
+        // from here on every rank holds the whole (screened) design: the path runs replicated
+        sharded_ = false;
+    }
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     m.collect_spans();
-    stats_.kernel_launches += 1;
     if (m.x_owned) dfree(m.st, m.X);
     m.x_owned = true;
     m.X = Xn;
     m.ldx = ldn;
     m.p = size;
     p_ = size;
-    dfree(m.st, d_sel);
     m.free_sweep_buffers();
+    m.d.sharded = 0;
+    m.d.col_lo = 0;
     h_xmean_.assign(size, 0.0);
     h_xnorm_.assign(size, 0.0);
     return sel;
@@ -417,10 +525,12 @@ static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int
     const int spk = m.span_begin(3);
     launch_topk(m.d.bd, m.d.pstride, m.p, size, 1, d_sel, size, d_tie, ck0, ci0, ck1, ci1, cstride, m.st);
     m.span_end(spk);
-    sel_out->resize(size);
     int tie = 0;
-    CUDA_CHECK(cudaMemcpyAsync(sel_out->data(), d_sel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
+    if (sel_out) {
+        sel_out->resize(size);
+        CUDA_CHECK(cudaMemcpyAsync(sel_out->data(), d_sel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));  // a LOCAL boundary tie only matters
+    }                                                                               // when the local list is the result
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     if (vals_out) {
         std::vector<double> all((size_t)m.p);
@@ -516,6 +626,32 @@ void Engine::normalize(int data_type, bool is_normal)
     else if (family_ == FAM_LM) stats_.norm_bytes += 16.0 * n * p;
     dfree(m.st, d_mean); dfree(m.st, d_mul); dfree(m.st, d_rowmul);
     m.free_sweep_buffers();
+    if (sharded_) {
+        // column statistics are shard-local; de-normalisation (path.cpp:76-110) needs those of the selected columns,
+        // whoever owns them: all-gather both vectors once (2 * p_total doubles)
+        const NcclApi &api = nccl_api();
+        long long lo0, hi0;
+        shard_range(p_total_, world_, 0, &lo0, &hi0);
+        const size_t pmax = (size_t)(hi0 - lo0);
+        std::vector<double> send(2 * pmax, 0.0), recv((size_t)world_ * 2 * pmax);
+        std::copy(h_xmean_.begin(), h_xmean_.end(), send.begin());
+        std::copy(h_xnorm_.begin(), h_xnorm_.end(), send.begin() + pmax);
+        double *ds = dalloc<double>(m.st, 2 * pmax), *dr = dalloc<double>(m.st, (size_t)world_ * 2 * pmax);
+        CUDA_CHECK(cudaMemcpyAsync(ds, send.data(), send.size() * 8, cudaMemcpyHostToDevice, m.st));
+        NCCL_CHECK(api.AllGather(ds, dr, 2 * pmax, ncclDouble, m.comm, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(recv.data(), dr, recv.size() * 8, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        dfree(m.st, ds); dfree(m.st, dr);
+        g_xmean_.assign((size_t)p_total_, 0.0);
+        g_xnorm_.assign((size_t)p_total_, 0.0);
+        for (int q = 0; q < world_; q++) {
+            long long lo, hi;
+            shard_range(p_total_, world_, q, &lo, &hi);
+            const double *blk = recv.data() + (size_t)q * 2 * pmax;
+            std::copy(blk, blk + (hi - lo), g_xmean_.begin() + lo);
+            std::copy(blk + pmax, blk + pmax + (hi - lo), g_xnorm_.begin() + lo);
+        }
+    }
 }
 
 void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter, bool warm_start,
@@ -525,7 +661,7 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     const int n = m.n, p = m.p;
     if (K < 0 || K > MAXC - 1) throw EngineError{"K (nfolds) must be in [0, 15]"};
     if (max_iter < 1 || max_iter > MAX_HIST - 2) throw EngineError{"max_iter must be in [1, 64]"};
-    if (kcap < 1 || kcap > p) throw EngineError{"support size must be in [1, p]"};
+    if (kcap < 1 || kcap > p_model()) throw EngineError{"support size must be in [1, p]"};
     m.free_chain_buffers();
     m.K = K;
     m.nchains = 1 + K;
@@ -653,12 +789,35 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     }
     m.loss_scratch = dalloc<double>(m.st, (size_t)2 * MAXC * 2 * n);
     m.loss_out = dalloc<double>(m.st, 2 * MAXC);
-    m.n_always = (int)always_select.size();
+    std::vector<int> alw_local;  // pins are applied to the local sacrifice vector
+    for (int j : always_select)
+        if (!sharded_) alw_local.push_back(j);
+        else if (j >= col_lo_ && j < col_lo_ + p) alw_local.push_back((int)(j - col_lo_));
+    m.n_always = (int)alw_local.size();
     if (m.n_always) {
         m.always = dalloc<int>(m.st, m.n_always);
-        CUDA_CHECK(cudaMemcpyAsync(m.always, always_select.data(), (size_t)m.n_always * 4, cudaMemcpyHostToDevice, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.always, alw_local.data(), (size_t)m.n_always * 4, cudaMemcpyHostToDevice, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+    }
+    d.sharded = sharded_ ? 1 : 0;
+    d.col_lo = (int)col_lo_;
+    if (sharded_) {
+        m.cand_s = dalloc<Cand>(m.st, (size_t)C * kcap);
+        m.cand_r = dalloc<Cand>(m.st, (size_t)m.world * C * kcap);
+        m.mstride = (long long)m.world * kcap;
+        m.mv = dalloc<double>(m.st, (size_t)C * m.mstride);
+        m.mi = dalloc<int>(m.st, (size_t)C * m.mstride);
+        m.Aloc = dalloc<int>(m.st, (size_t)C * kcap);
+        m.AXs = dalloc<double>(m.st, (size_t)C * n * kcap);
+        d.AXr = dalloc<double>(m.st, (size_t)C * n * kcap);
+        d.ldXk = kcap;
+        d.AXk = dalloc<double>(m.st, (size_t)C * n * d.ldXk);
+        CUDA_CHECK(cudaMemsetAsync(m.cand_s, 0, (size_t)C * kcap * sizeof(Cand), m.st));
+        CUDA_CHECK(cudaMemsetAsync(m.AXs, 0, (size_t)C * n * kcap * 8, m.st));
+        CUDA_CHECK(cudaMemsetAsync(d.AXk, 0, (size_t)C * n * d.ldXk * 8, m.st));
     }
     m.cstride = std::max<long long>(2LL * kcap + 16, ((long long)p / 8192 + 2) * std::min(kcap, TOPK_LMAX));
+    if (sharded_) m.cstride = std::max<long long>(m.cstride, (long long)m.world * kcap + 16);
     m.ck0 = dalloc<double>(m.st, (size_t)C * m.cstride);
     m.ck1 = dalloc<double>(m.st, (size_t)C * m.cstride);
     m.ci0 = dalloc<int>(m.st, (size_t)C * m.cstride);
@@ -708,6 +867,7 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
             ld.fold[i] = (*jobs)[i].fold;
         }
     }
+    d.ldXr = T;
     const int mode = sweep_mode(family_), epi = sweep_epi(family_);
     const double vec_bytes = 8.0 * d.n * b.nch * (mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 4)) + 8.0 * d.p * b.nch;
 
@@ -733,9 +893,33 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
             if (m.n_always)
                 launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
             sp = m.span_begin(3);
-            launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1,
-                        d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st,
-                        d.gate);
+            if (!sharded_) {
+                launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1,
+                            d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride,
+                            m.st, d.gate);
+            } else {
+                // exact local top-k -> all-gather of (sacrifice, global index) candidates -> identical merge on every
+                // rank (rank-major concatenation of ascending lists is ascending, so the ordered compaction of the
+                // select keeps the reference's ascending-index output and the lower-index tie rule)
+                const NcclApi &api = nccl_api();
+                const int nspan = cmax - cmin + 1;
+                const int kloc = std::min(T, d.p);
+                launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, kloc, nspan, m.Aloc + (size_t)cmin * d.kcap,
+                            d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st, d.gate);
+                launch_pack_candidates(d.bd + (size_t)cmin * d.pstride, d.pstride, m.Aloc + (size_t)cmin * d.kcap, d.kcap,
+                                       kloc, T, col_lo_, nspan, m.cand_s + (size_t)cmin * d.kcap, d.kcap, d.gate, m.st);
+                NCCL_CHECK(api.AllGather(m.cand_s, m.cand_r, (size_t)m.nchains * d.kcap * sizeof(Cand), ncclChar, m.comm,
+                                         m.st));
+                launch_unpack_candidates(m.cand_r + (size_t)cmin * d.kcap, m.world, m.nchains, d.kcap, T,
+                                         m.mv + (size_t)cmin * m.mstride, m.mi + (size_t)cmin * m.mstride, m.mstride,
+                                         d.gate, m.st);
+                launch_topk(m.mv + (size_t)cmin * m.mstride, m.mstride, m.world * T, T, nspan,
+                            d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride,
+                            m.st, d.gate, m.mi + (size_t)cmin * m.mstride);
+                // the k active columns, all rows: owners write them, everybody sums (x + 0 is exact)
+                launch_gather_active(d, b, m.AXs, m.st);
+                NCCL_CHECK(api.AllReduce(m.AXs, d.AXr, (size_t)m.nchains * d.n * T, ncclDouble, ncclSum, m.comm, m.st));
+            }
             m.span_end(sp);
             sp = m.span_begin(4);
             launch_chain_fit(d, b, m.st);
@@ -776,7 +960,7 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         stats_.n_boundary_ties += m.h_tie[c];
         executed = std::max(executed, iters);
     }
-    launches += (long long)executed * (4 + (m.n_always ? 1 : 0)) + (jobs ? 1 : 0);
+    launches += (long long)executed * (4 + (m.n_always ? 1 : 0) + (sharded_ ? 4 : 0)) + (jobs ? 1 : 0);
     stats_.n_sweeps += executed;
     stats_.sweep_bytes += executed * (8.0 * d.n * d.p + vec_bytes);
     stats_.kernel_launches += launches;  // launches that did work; gated no-op launches are not counted

@@ -50,6 +50,17 @@ class Engine {
 public:
     explicit Engine(int device = -1);
     ~Engine();
+
+    // ---- multi-GPU, columns of X sharded over `world` ranks (SURVEY 8e axis B).  Call before load().
+    // unique_id: the 128-byte ncclUniqueId every rank received from rank 0 (bess_b200_nccl_unique_id); the
+    // communicator is cached per device for the life of the process.
+    // This rank will load columns [col_lo, col_lo + p_local) = shard_range(p_total, world, rank) of a p_total-column design.
+    void init_shard(int world, int rank, const void *unique_id, long long col_lo, long long p_total);
+    bool sharded() const { return sharded_; }
+    // column count the model sees (IC penalties, validation): p_total while sharded, else p
+    long long p_model() const { return sharded_ ? p_total_ : p_; }
+    double x_mean_at(long long j) const { return sharded_ ? g_xmean_[(size_t)j] : h_xmean_[(size_t)j]; }
+    double x_norm_at(long long j) const { return sharded_ ? g_xnorm_[(size_t)j] : h_xnorm_[(size_t)j]; }
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
 
@@ -110,8 +121,24 @@ private:
     int S_ = 1;
     std::vector<double> h_xmean_, h_xnorm_;
     double y_mean_ = 0.0;
+    // sharded mode
+    bool sharded_ = false;
+    int world_ = 1, rank_ = 0;
+    long long col_lo_ = 0, p_total_ = 0;
+    std::vector<double> g_xmean_, g_xnorm_;  // column statistics of the WHOLE design (all-gathered)
     EngineStats stats_;
 };
+
+// contiguous, even-aligned column shards (16-byte loads need even column offsets), remainder spread over the first ranks
+inline void shard_range(long long p, int world, int rank, long long *lo, long long *hi)
+{
+    const long long pairs = (p + 1) / 2;
+    const long long base = pairs / world, rem = pairs % world;
+    const long long b = rank * base + (rank < rem ? rank : rem);
+    const long long e = b + base + (rank < rem ? 1 : 0);
+    *lo = 2 * b < p ? 2 * b : p;
+    *hi = 2 * e < p ? 2 * e : p;
+}
 
 // thrown by the engine on CUDA errors / misuse; the C-ABI turns it into an error code + message
 struct EngineError {

@@ -498,11 +498,12 @@ __global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__re
 }
 
 void launch_topk(const double *vals, long long stride, int n_in, int k, int nch, int *out_idx, int out_ld, int *tie,
-                 double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st, const int *gate)
+                 double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st, const int *gate,
+                 const int *idx0)
 {
     if (k > n_in) throw EngineError{"top-k: k > number of candidates"};
     const double *kin = vals;
-    const int *iin = nullptr;
+    const int *iin = idx0;
     long long in_stride = stride;
     int cur_n = n_in;
     int pp = 0;
@@ -544,6 +545,90 @@ void launch_topk(const double *vals, long long stride, int n_in, int k, int nch,
     throw EngineError{"top-k: did not converge"};
 }
 
+// =====================================================================================================
+// column-sharded mode: candidate exchange and active-column exchange (the collectives themselves are NCCL calls in
+// engine.cu; these kernels pack / unpack their payloads)
+// =====================================================================================================
+__global__ void pack_candidates_kernel(const double *vals, long long stride, const int *sel, int sel_ld, int kloc, int kpad,
+                                       long long offset, Cand *out, int out_ld, const int *gate)
+{
+    if (gate && *gate == 0) return;
+    const int f = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= kpad) return;
+    Cand cnd;
+    if (a < kloc) {
+        const int j = sel[(size_t)f * sel_ld + a];
+        cnd.v = vals[(size_t)f * stride + j];
+        cnd.idx = (long long)j + offset;
+    } else {
+        cnd.v = -1.0;
+        cnd.idx = 2147483647LL;
+    }
+    out[(size_t)f * out_ld + a] = cnd;
+}
+void launch_pack_candidates(const double *vals, long long stride, const int *sel, int sel_ld, int kloc, int kpad,
+                            long long offset, int nch, Cand *out, int out_ld, const int *gate, cudaStream_t st)
+{
+    dim3 grid((kpad + 127) / 128, nch);
+    pack_candidates_kernel<<<grid, 128, 0, st>>>(vals, stride, sel, sel_ld, kloc, kpad, offset, out, out_ld, gate);
+    CUDA_CHECK(cudaGetLastError());
+}
+__global__ void unpack_candidates_kernel(const Cand *in, int world, int nch, int in_ld, int k, double *mv, int *mi,
+                                         long long mstride, const int *gate)
+{
+    if (gate && *gate == 0) return;
+    const int f = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= world * k) return;
+    const int q = e / k, a = e - q * k;
+    const Cand cnd = in[((size_t)q * nch + f) * in_ld + a];
+    mv[(size_t)f * mstride + e] = cnd.v;
+    mi[(size_t)f * mstride + e] = (int)cnd.idx;
+}
+void launch_unpack_candidates(const Cand *in, int world, int nch, int in_ld, int k, double *mv, int *mi, long long mstride,
+                              const int *gate, cudaStream_t st)
+{
+    dim3 grid((world * k + 127) / 128, nch);
+    unpack_candidates_kernel<<<grid, 128, 0, st>>>(in, world, nch, in_ld, k, mv, mi, mstride, gate);
+    CUDA_CHECK(cudaGetLastError());
+}
+__global__ void gather_active_kernel(const Dev d, const BatchDesc b, double *AXs)
+{
+    if (d.gate && *d.gate == 0) return;
+    const int c = b.chain[blockIdx.y];
+    if (d.done[c]) return;
+    const int T = b.T;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d.n * T) return;
+    const int i = e / T, a = e - i * T;
+    const int j = d.Anew[(size_t)c * d.kcap + a] - d.col_lo;
+    AXs[((size_t)c * d.n + i) * T + a] = (j >= 0 && j < d.p) ? __ldg(d.X + (size_t)i * d.ldx + j) : 0.0;
+}
+void launch_gather_active(const Dev &d, const BatchDesc &b, double *AXs, cudaStream_t st)
+{
+    dim3 grid((d.n * b.T + 255) / 256, b.nch);
+    gather_active_kernel<<<grid, 256, 0, st>>>(d, b, AXs);
+    CUDA_CHECK(cudaGetLastError());
+}
+__global__ void gather_owned_cols_kernel(const double *X, long long ldx, int n, int p_local, long long col_lo, const int *sel,
+                                         int m, double *Xn, long long ldn)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const long long j = (long long)sel[q] - col_lo;
+    const bool own = j >= 0 && j < p_local;
+    const int r0 = blockIdx.y * 32, r1 = min(n, r0 + 32);
+    for (int i = r0; i < r1; i++) Xn[(size_t)i * ldn + q] = own ? X[(size_t)i * ldx + j] : 0.0;
+}
+void launch_gather_owned_cols(const double *X, long long ldx, int n, int p_local, long long col_lo, const int *sel, int m,
+                              double *Xn, long long ldn, cudaStream_t st)
+{
+    dim3 grid((m + 127) / 128, (n + 31) / 32);
+    gather_owned_cols_kernel<<<grid, 128, 0, st>>>(X, ldx, n, p_local, col_lo, sel, m, Xn, ldn);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void configure_kernels()
 {
     CUDA_CHECK(cudaFuncSetAttribute(topk_slices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_LMAX * 8));
@@ -577,8 +662,13 @@ __global__ void __launch_bounds__(FIT_NT) loss_kernel(const Dev d, const LossDes
     for (int r = threadIdx.x; r < nr; r += FIT_NT) {
         const int i = rl ? rl[r] : r;
         double eta = d.family == FAM_LM || d.family == FAM_COX ? 0.0 : coef0;
-        const double *row = d.X + (size_t)i * d.ldx;
-        for (int a = 0; a < ks; a++) eta = fma(row[As[a]], bsl[a], eta);
+        if (d.sharded) {
+            const double *row = d.AXk + ((size_t)c * d.n + i) * d.ldXk;
+            for (int a = 0; a < ks; a++) eta = fma(row[a], bsl[a], eta);
+        } else {
+            const double *row = d.X + (size_t)i * d.ldx;
+            for (int a = 0; a < ks; a++) eta = fma(row[As[a]], bsl[a], eta);
+        }
         if (d.family == FAM_LM) {
             const double t = y[i] - eta;
             acc += t * t;

@@ -56,6 +56,13 @@ struct Dev {
     double *Smat;       // [MAXC][2][ldA*ldA] normal equations (when they do not fit in smem) / Cox second Gram
     double *Spart;      // [MAXC][CLcap][nmat][ldA*ldA] per-CTA partial Grams of a cluster (nullptr when CLcap == 1)
     double *cw;         // [MAXC][CLMAX][4][ldA] cluster exchange vectors
+    // column-sharded mode (multi-GPU axis B): X holds columns [col_lo, col_lo + p) of a wider design; supports (A, Anew,
+    // hist) carry GLOBAL column indices, betaD / bd / xtx are local
+    int sharded;
+    int col_lo;
+    double *AXr;        // [MAXC][n][ldXr] active columns of this iteration for ALL rows, summed over ranks (ldXr = T)
+    double *AXk;        // [MAXC][n][ldXk] all-row active columns of each chain's CURRENT support (losses)
+    int ldXr, ldXk;
     int CLcap;          // largest cluster size the workspaces were sized for
     int nmat;           // Gram matrices per fit step: 2 for cox, else 1
     double *xtx;        // [MAXC][p] x_j.x_j over the chain's train rows (gaussian only)
@@ -91,9 +98,26 @@ void launch_finish(const Dev &d, int mode, int epi, const BatchDesc &b, double *
 void launch_pin(const Dev &d, double *vals, long long stride, int nch, const int *idx, int nidx, cudaStream_t st);
 // `gate`: see Dev::gate
 // exact top-k of `vals` ([nch][stride], first n_in of each row) -> out_idx [nch][out_ld] ascending; uses ping-pong scratch
+// idx0: optional explicit index of every input key ([nch][stride], ascending inside each row); default = position
 void launch_topk(const double *vals, long long stride, int n_in, int k, int nch, int *out_idx, int out_ld, int *tie,
                  double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st,
-                 const int *gate = nullptr);
+                 const int *gate = nullptr, const int *idx0 = nullptr);
+// ---- column-sharded mode
+struct Cand {
+    double v;
+    long long idx;
+};
+// out[f][a] = (vals[f][sel[f][a]], sel[f][a] + offset) for a < kloc, padded with (-1, INT_MAX) up to kpad
+void launch_pack_candidates(const double *vals, long long stride, const int *sel, int sel_ld, int kloc, int kpad,
+                            long long offset, int nch, Cand *out, int out_ld, const int *gate, cudaStream_t st);
+// in [world][nch][in_ld] -> mv/mi [nch][world * k] (rank-major, so index-ascending)
+void launch_unpack_candidates(const Cand *in, int world, int nch, int in_ld, int k, double *mv, int *mi, long long mstride,
+                              const int *gate, cudaStream_t st);
+// AXs[c][i][a] = X[i][Anew[c][a] - col_lo] when this rank owns the column, else 0   (ld = T)
+void launch_gather_active(const Dev &d, const BatchDesc &b, double *AXs, cudaStream_t st);
+// Xn[i][q] = X[i][sel[q] - col_lo] when owned else 0
+void launch_gather_owned_cols(const double *X, long long ldx, int n, int p_local, long long col_lo, const int *sel, int m,
+                              double *Xn, long long ldn, cudaStream_t st);
 void launch_chain_begin(const Dev &d, const BatchDesc &b, cudaStream_t st);
 void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st);
 void launch_losses(const Dev &d, const LossDesc &jobs, const int *testrows, const int *ntest, const double *y,

@@ -47,7 +47,7 @@ struct Driver {
     Driver(Engine &e, const BessArgs &args) : eng(e), a(args)
     {
         n = eng.n();
-        p = eng.p();
+        p = (int)eng.p_model();
         K = a.is_cv ? a.K : 0;
         for (int c = 0; c <= K; c++) all_chains.push_back(c);
         for (int c = 1; c <= K; c++) fold_chains.push_back(c);
@@ -137,9 +137,9 @@ struct Driver {
         double dot = 0.0;
         for (size_t i = 0; i < e.A.size(); i++) {
             const int j = e.A[i];
-            const double b = sn * e.bA[i] / eng.x_norm()[(size_t)j];
+            const double b = sn * e.bA[i] / eng.x_norm_at(j);
             bA_out[i] = b;
-            dot += b * eng.x_mean()[(size_t)j];
+            dot += b * eng.x_mean_at(j);
         }
         if (a.data_type == 1) coef0 = eng.y_mean() - dot;
         else if (a.data_type == 2) coef0 = e.coef0 - dot;
@@ -261,17 +261,21 @@ void bess_run(const BessArgs &a, BessResult &out)
             if (a.g_index[(size_t)j] != j) throw EngineError{"g_index must be 0..p-1 (no groups)"};
     }
     if (a.is_cv && (a.K < 2 || a.K > MAXC - 1)) throw EngineError{"K (nfolds) must be in [2, 15]"};
+    const bool shard = a.world > 1;
+    const long long p_all = shard ? a.p_total : a.p;
+    if (shard && a.x_on_device == false && a.x == nullptr) throw EngineError{"sharded fit: x shard is null"};
     for (int j : a.always_select)
-        if (j < 0 || j >= a.p) throw EngineError{"always_select index out of range"};
+        if (j < 0 || j >= p_all) throw EngineError{"always_select index out of range"};
 
     Engine eng(a.device);
     eng.set_profiling(a.profile);
+    if (shard) eng.init_shard(a.world, a.rank, a.nccl_id, a.col_lo, a.p_total);
     eng.load(a.x, a.n, a.p, a.x_on_device, a.y, a.weight, a.model_type, /*borrow=*/a.is_screening);
 
     std::vector<int> always = a.always_select;
     std::sort(always.begin(), always.end());
     if (a.is_screening) {
-        if (a.screening_size < 1 || a.screening_size > a.p) throw EngineError{"screening_size must be in [1, p]"};
+        if (a.screening_size < 1 || a.screening_size > p_all) throw EngineError{"screening_size must be in [1, p]"};
         out.screening_A = eng.screen(a.screening_size, always);
         // screening.cpp:91-102: always_select -> positions inside the screened matrix
         for (int &j : always) {
@@ -282,7 +286,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     }
     eng.normalize(a.data_type, a.is_normal);
 
-    const int p = eng.p();
+    const long long p = eng.p_model();
     int kcap;
     if (a.path_type == 1) {
         if (a.sequence.empty()) throw EngineError{"sequence (s.list) is empty"};
@@ -315,7 +319,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     out.lambda = 0.0;
     out.chosen_s = best.T;
     // scatter to the ORIGINAL column numbering (un-screen: bess.cpp:186-209)
-    out.beta.assign((size_t)a.p, 0.0);
+    out.beta.assign((size_t)p_all, 0.0);
     auto orig = [&](int j) { return a.is_screening ? out.screening_A[(size_t)j] : j; };
     for (size_t i = 0; i < best.A.size(); i++) out.beta[(size_t)orig(best.A[i])] = bA[i];
     for (auto &A : out.A_all)

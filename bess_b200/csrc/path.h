@@ -42,6 +42,11 @@ struct BessArgs {
     bool x_on_device = false;          // x is a device pointer (bench "resident" mode)
     int device = -1;
     bool profile = false;              // CUDA-event timing per kernel category
+    // multi-GPU, columns sharded (SURVEY 8e axis B): x holds columns [col_lo, col_lo + p) of a p_total-column design,
+    // always_select / the returned beta use GLOBAL column numbers; nccl_id = the 128-byte ncclUniqueId of the job
+    int world = 1, rank = 0;
+    long long col_lo = 0, p_total = 0;
+    const void *nccl_id = nullptr;
 };
 
 struct BessResult {

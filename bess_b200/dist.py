@@ -76,47 +76,48 @@ def allreduce_sum(x: np.ndarray) -> np.ndarray:
     return t.cpu().numpy()
 
 
+_NCCL_ID = None
+
+
+def nccl_unique_id() -> bytes:
+    """The job's NCCL unique id for the library's own communicator: created on rank 0 through the C ABI
+    (``bess_b200_nccl_unique_id``), broadcast once over the existing process group, cached."""
+    global _NCCL_ID
+    if _NCCL_ID is None:
+        dist = _dist()
+        obj = [None]
+        if dist.get_rank() == 0:
+            buf = C.create_string_buffer(128)
+            _lib.check(_lib.load().bess_b200_nccl_unique_id(C.cast(buf, C.c_void_p)))
+            obj = [bytes(buf.raw)]
+        dist.broadcast_object_list(obj, src=0)
+        _NCCL_ID = obj[0]
+    return _NCCL_ID
+
+
 def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal, model_type, max_iter, path_type,
                        is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, screening_size, cv_seed=123,
-                       fold_of_row=None, device=None, x_shard_device_ptr=None, n=None, p_local=None, profile=False):
-    """Multi-GPU fit of a SCREENED problem (BASELINE config 5) with the columns of X sharded across ranks.
+                       fold_of_row=None, device=None, x_shard_device_ptr=None, n=None, p_local=None, profile=False,
+                       always_select=()):
+    """Multi-GPU fit with the columns of X sharded across the ranks of the current process group (one ``bess_b200_fit``
+    call per rank, the library talks NCCL itself).
 
-    Each rank holds columns [col_lo, col_lo + p_local) (host array ``x_shard`` -- uploaded over the rank's own PCIe
-    link -- or an HBM-resident shard via ``x_shard_device_ptr``).  Steps:
-      1. local marginal-utility sweep + exact local top-k on the rank's columns      (screening.cpp:40-61, 63-66)
-      2. all-gather of the (utility, global index) candidates, identical merge        -> screening_A on every rank
-      3. every rank copies the kept columns it owns into a shared n x m buffer, all-reduce(sum) over NVLink
-      4. the PDAS path + CV on the n x m screened design, replicated on every rank    (bess.cpp:61-185)
+    Each rank holds columns [col_lo, col_lo + p_local) = ``shard_range(p_total, world, rank)`` (host array ``x_shard`` --
+    uploaded over the rank's own PCIe link -- or an HBM-resident shard via ``x_shard_device_ptr``).
+      * ``screening_size > 0`` (BASELINE config 5): local marginal-utility sweep + exact local top-k, NCCL all-gather of
+        (utility, global index) candidates, identical merge, all-reduce of the kept columns; the PDAS path then runs
+        replicated on the n x screening_size design.
+      * ``screening_size == 0``: every PDAS iteration is sharded -- local dual sweep + local top-k, all-gather of the
+        candidates, all-reduce of the k active columns, replicated active-set fit.
     Returns the same dict as ``cbess.fit`` (beta has length p_total), identical on every rank."""
     import torch
     from . import cbess
-    from .engine import GpuEngine
     dist = _dist()
-    rank = dist.get_rank()
     if device is None:
         device = torch.cuda.current_device()
-    eng = GpuEngine(device)
-    if x_shard_device_ptr is None:
-        n, p_local = x_shard.shape
-    eng.load(x_shard, y, weight, model_type, x_device_ptr=x_shard_device_ptr, n=n, p=p_local)
-    vals, idx = eng.screen_local(screening_size)
-    A = global_topk_from_local(vals, (idx + col_lo).astype(np.int32), screening_size)
-    m = int(A.size)
-    ld = (m + 1) & ~1
-    Xs = torch.zeros((n, ld), dtype=torch.float64, device=f"cuda:{device}")
-    torch.cuda.current_stream().synchronize()
-    mine = np.nonzero((A >= col_lo) & (A < col_lo + p_local))[0]
-    eng.gather_columns(A[mine] - col_lo, mine, Xs.data_ptr(), ld)
-    eng.close()
-    dist.all_reduce(Xs)
-    torch.cuda.current_stream().synchronize()
-    xs = Xs if ld == m else Xs[:, :m].contiguous()
-    out = cbess.fit(None, y, data_type, weight, is_normal, 1, model_type, max_iter, 2, path_type, is_warm_start, ic_type,
-                    is_cv, K, sequence, s_min, s_max, False, 1, fold_of_row=fold_of_row, cv_seed=cv_seed, device=device,
-                    x_device_ptr=xs.data_ptr(), n=n, p=m, want_trace=False, profile=profile)
-    beta = np.zeros(p_total)
-    beta[A] = out["beta"]
-    out["beta"] = beta
-    out["screening_A"] = A
-    del rank
-    return out
+    scr = int(screening_size or 0)
+    return cbess.fit(x_shard, y, data_type, weight, is_normal, 1, model_type, max_iter, 2, path_type, is_warm_start,
+                     ic_type, is_cv, K, sequence, s_min, s_max, scr > 0, max(scr, 1), always_select=always_select,
+                     fold_of_row=fold_of_row, cv_seed=cv_seed, device=device, x_device_ptr=x_shard_device_ptr, n=n,
+                     p=p_local, want_trace=False, profile=profile, world=dist.get_world_size(), rank=dist.get_rank(),
+                     col_lo=col_lo, p_total=p_total, nccl_id=nccl_unique_id())

@@ -68,6 +68,14 @@ typedef struct bess_b200_ext {
                               /*  16..23 launches per category; 24 algorithmic bytes of the screening sweep (8np);    */
                               /*  25 sweep row splits; 26 algorithmic bytes of the normalisation / x_j.x_j passes     */
     int profile;              /* record CUDA events around every kernel category on the engine's stream               */
+    /* ---- multi-GPU, columns of x sharded over `world` processes (one per GPU); world <= 1: single GPU.            */
+    /* x then holds columns [col_lo, col_lo + x_col) = bess_b200_shard_range(p_total, world, rank) of the design,      */
+    /* gindex is ignored, always_select / beta_out (length p_total) / screening_A_out use GLOBAL column numbers, and   */
+    /* every rank must make the same call with the same non-x arguments.  Candidates and active columns travel over   */
+    /* NCCL (all-gather / all-reduce on the library's own communicator).                                              */
+    int world, rank;
+    long long col_lo, p_total;
+    const void *nccl_unique_id; /* 128 bytes from bess_b200_nccl_unique_id() on rank 0, broadcast by the caller       */
 } bess_b200_ext;
 
 /* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's
@@ -89,6 +97,9 @@ int bess_b200_trace(int *s_all, int *l_all, double *coef0_all, double *train_los
 
 /* Metric.h:49-106 with the seed pinned: fold index of every row. */
 int bess_b200_cv_fold_ids(int n, int K, unsigned seed, int *fold_of_row_out);
+
+/* ncclGetUniqueId through the library's run-time-loaded NCCL: call on rank 0, broadcast the 128 bytes to all ranks. */
+int bess_b200_nccl_unique_id(void *out128);
 
 const char *bess_b200_last_error(void);
 int bess_b200_version(void);
