@@ -14,8 +14,10 @@
 // same code with every cluster operation compiled to a no-op branch.
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 #include "kernels.cuh"
@@ -1059,14 +1061,23 @@ void debug_set(int key, int val)
     if (key == 1) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_cox_iters, &val, sizeof(int)));
 }
 
-// cluster size for sparsity level T: enough work per CTA to amortise the cluster barriers, all clusters co-resident
+// cluster size for sparsity level T: enough work per CTA to amortise the cluster barriers, all clusters co-resident.
+// work ~ rows x columns^2 of one Gram (x2 for cox: two Grams per Newton step).  Even the small gaussian fits of config 5
+// (900 x 21) gain from 4 CTAs: gather, Gram and gradient are row-parallel and a cluster barrier costs ~0.2 us.
 int chain_cluster_size(const Dev &d, int T, int nch)
 {
+    static double thr = -1.0;
+    static int clmax = CLMAX;
+    if (thr < 0.0) {
+        const char *e = std::getenv("BESS_B200_CL_WORK");
+        thr = e ? std::atof(e) : 1.0e5;
+        const char *e2 = std::getenv("BESS_B200_CL_MAX");
+        if (e2) clmax = std::max(1, std::min(CLMAX, std::atoi(e2)));
+    }
     const double m = T + 2.0;
-    double work = (double)d.n * m * m * (d.family == FAM_COX ? 2.0 : 1.0);
-    if (d.family == FAM_LM) work *= 0.25;  // a single Gram, no inner iteration
+    const double work = (double)d.n * m * m * (d.family == FAM_COX ? 2.0 : 1.0);
     int CL = 1;
-    while (CL < CLMAX && CL < d.CLcap && work / CL > 1.0e6 && nch * CL * 2 <= 148 && d.n / (CL * 2) >= 128) CL *= 2;
+    while (CL < clmax && CL < d.CLcap && work / CL > thr && nch * CL * 2 <= 148 && d.n / (CL * 2) >= 128) CL *= 2;
     return CL;
 }
 

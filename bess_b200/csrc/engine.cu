@@ -371,7 +371,7 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     m.d = Dev{};
     m.d.family = family;
     m.d.sharded = sharded_ ? 1 : 0;
-    m.d.col_lo = (int)col_lo_;
+    m.d.col_lo = sharded_ ? (int)col_lo_ : 0;
     h_xmean_.assign(p, 0.0);
     h_xnorm_.assign(p, 0.0);
     y_mean_ = 0.0;
@@ -438,6 +438,7 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
         dfree(m.st, d_tie); dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
         // from here on every rank holds the whole (screened) design: the path runs replicated
         sharded_ = false;
+        col_lo_ = 0;
     }
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     m.collect_spans();
@@ -800,7 +801,7 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
         CUDA_CHECK(cudaStreamSynchronize(m.st));
     }
     d.sharded = sharded_ ? 1 : 0;
-    d.col_lo = (int)col_lo_;
+    d.col_lo = sharded_ ? (int)col_lo_ : 0;
     if (sharded_) {
         m.cand_s = dalloc<Cand>(m.st, (size_t)C * kcap);
         m.cand_r = dalloc<Cand>(m.st, (size_t)m.world * C * kcap);

@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__re
     int krem = kk, neq = len;
     if (kk < len) {
         unsigned long long prefix = 0ull, mask = 0ull;
+        bool early = false;
         for (int pass = 7; pass >= 0; pass--) {
             const int shift = pass * 8;
             if (tid < 256) hist[tid] = 0;
@@ -430,8 +431,19 @@ __global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__re
             neq = sh_neq;
             mask |= 255ull << shift;
             __syncthreads();
+            // every key of the boundary bin is wanted: the select is decided, the remaining digits cannot change it
+            if (neq == krem && pass > 0 && prefix > 0ull) {
+                early = true;
+                break;
+            }
         }
-        thr = prefix;
+        if (early) {
+            thr = prefix - 1ull;  // u > thr  <=>  u >= prefix (lower digits zero): all of the boundary bin and above
+            krem = 0;             // nothing is taken from keys equal to thr (they sit in a lower bin)
+            neq = 0;
+        } else {
+            thr = prefix;
+        }
     } else {
         __syncthreads();
     }
