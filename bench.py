@@ -328,9 +328,25 @@ def run_ours(args):
             "cpu_baseline": base, "c5b_no_screening": c5b,
             "fits_per_step": fits_per_step, "n_boundary_ties": int(st["n_boundary_ties"]),
         }
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
+
+
+class StdoutToStderr:
+    """Everything libraries write to fd 1 while the benchmark runs (NCCL prints its version banner there) goes to
+    stderr, so that stdout carries exactly one line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -345,7 +361,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        with StdoutToStderr():
+            line = run_ours(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

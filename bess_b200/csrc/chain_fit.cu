@@ -13,6 +13,7 @@
 // cluster factors the (small) normal equations and broadcasts the solution.  CL = 1 (the k <= 20 configs) runs the very
 // same code with every cluster operation compiled to a no-op branch.
 #include <cooperative_groups.h>
+#include <cuda_pipeline.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -160,46 +161,82 @@ __device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, con
         double acc[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) acc[e] = 0.0;
-        for (int rb = r0; rb < r1; rb += R) {
-            const int rc = min(R, r1 - rb);
-            const int tot = rc * mp;
-            __syncthreads();
-            // stage rc rows (zero-padded to mp columns): flattened and unrolled so 4 loads are in flight per thread
-            for (int e0 = tid; e0 < tot; e0 += 4 * FIT_NT) {
-                double val[4];
+        auto fma_rows = [&](const double *tl, const double *twt, int rc) {
+            for (int r = sl; r < rc; r += nsl) {
+                const double w = twt[r];
+                const double *ta = tl + r * mp + 4 * bi;
+                const double *tb = tl + r * mp + 4 * bj;
+                const double2 a01 = *reinterpret_cast<const double2 *>(ta);
+                const double2 a23 = *reinterpret_cast<const double2 *>(ta + 2);
+                const double2 b01 = *reinterpret_cast<const double2 *>(tb);
+                const double2 b23 = *reinterpret_cast<const double2 *>(tb + 2);
+                const double a[4] = {a01.x * w, a01.y * w, a23.x * w, a23.y * w};
+                const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int e = e0 + q * FIT_NT;
-                    val[q] = 0.0;
-                    if (e < tot) {
-                        const int r = e / mp, cidx = e - r * mp;
-                        if (cidx < mm) val[q] = V[(size_t)(rb + r) * ldv + cidx];
+                for (int qa = 0; qa < 4; qa++)
+#pragma unroll
+                    for (int qb = 0; qb < 4; qb++) acc[qa * 4 + qb] = fma(a[qa], bb[qb], acc[qa * 4 + qb]);
+            }
+        };
+        if (nsl == 1) {
+            // Large systems (>= 512 tiles): the slice-reduction scratch is free, so it serves as a second row-tile buffer
+            // and the staging of tile t+1 (cp.async, 16-byte chunks, no register round trip) overlaps the FMAs of tile t.
+            // Columns in [mm, mp) receive whatever follows in the row (or stale shared memory past the row end): they only
+            // feed accumulators that are never stored.
+            double *buf[2] = {sm.tile, sm.scratch};
+            const int ntile = (r1 - r0 + R - 1) / R;
+            const int cpr = mp >> 1;  // 16-byte chunks per row
+            auto issue = [&](int t) {
+                const int rb = r0 + t * R;
+                const int rc = min(R, r1 - rb);
+                double *dst = buf[t & 1];
+                for (int e = tid; e < rc * cpr; e += FIT_NT) {
+                    const int r = e / cpr, cidx = (e - r * cpr) * 2;
+                    if (cidx < ldv) __pipeline_memcpy_async(dst + r * mp + cidx, V + (size_t)(rb + r) * ldv + cidx, 16);
+                }
+                double *twd = dst + (size_t)R * mp;
+                for (int r = tid; r < rc; r += FIT_NT) twd[r] = wt ? wt[rb + r] : 1.0;
+                __pipeline_commit();
+            };
+            __syncthreads();
+            if (ntile > 0) issue(0);
+            for (int t = 0; t < ntile; t++) {
+                if (t + 1 < ntile) {
+                    issue(t + 1);
+                    __pipeline_wait_prior(1);
+                } else {
+                    __pipeline_wait_prior(0);
+                }
+                __syncthreads();
+                if (valid) fma_rows(buf[t & 1], buf[t & 1] + (size_t)R * mp, min(R, r1 - (r0 + t * R)));
+                __syncthreads();
+            }
+        } else {
+            for (int rb = r0; rb < r1; rb += R) {
+                const int rc = min(R, r1 - rb);
+                const int tot = rc * mp;
+                __syncthreads();
+                // stage rc rows (zero-padded to mp columns): flattened and unrolled so 4 loads are in flight per thread
+                for (int e0 = tid; e0 < tot; e0 += 4 * FIT_NT) {
+                    double val[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int e = e0 + q * FIT_NT;
+                        val[q] = 0.0;
+                        if (e < tot) {
+                            const int r = e / mp, cidx = e - r * mp;
+                            if (cidx < mm) val[q] = V[(size_t)(rb + r) * ldv + cidx];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int e = e0 + q * FIT_NT;
+                        if (e < tot) tile[e] = val[q];
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int e = e0 + q * FIT_NT;
-                    if (e < tot) tile[e] = val[q];
-                }
-            }
-            for (int r = tid; r < rc; r += FIT_NT) tw[r] = wt ? wt[rb + r] : 1.0;
-            __syncthreads();
-            if (valid) {
-                for (int r = sl; r < rc; r += nsl) {
-                    const double w = tw[r];
-                    const double *ta = tile + r * mp + 4 * bi;
-                    const double *tb = tile + r * mp + 4 * bj;
-                    const double2 a01 = *reinterpret_cast<const double2 *>(ta);
-                    const double2 a23 = *reinterpret_cast<const double2 *>(ta + 2);
-                    const double2 b01 = *reinterpret_cast<const double2 *>(tb);
-                    const double2 b23 = *reinterpret_cast<const double2 *>(tb + 2);
-                    const double a[4] = {a01.x * w, a01.y * w, a23.x * w, a23.y * w};
-                    const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int qa = 0; qa < 4; qa++)
-#pragma unroll
-                        for (int qb = 0; qb < 4; qb++) acc[qa * 4 + qb] = fma(a[qa], bb[qb], acc[qa * 4 + qb]);
-                }
+                for (int r = tid; r < rc; r += FIT_NT) tw[r] = wt ? wt[rb + r] : 1.0;
+                __syncthreads();
+                if (valid) fma_rows(tile, tw, rc);
             }
         }
         if (nsl > 1) {

@@ -256,6 +256,10 @@ static void launch_sweep_m(const Dev &d, cudaStream_t st)
 
 void launch_dual_sweep(const Dev &d, int mode, cudaStream_t st)
 {
+    if (sweep_uses_tma(d)) {
+        launch_dual_sweep_tma(d, mode, st);
+        return;
+    }
     if (mode == MODE_D) launch_sweep_m<MODE_D>(d, st);
     else if (mode == MODE_DH) launch_sweep_m<MODE_DH>(d, st);
     else launch_sweep_m<MODE_COX>(d, st);

@@ -94,6 +94,9 @@ struct LossDesc {
 
 // ---- launchers (kernels.cu) ----
 void launch_dual_sweep(const Dev &d, int mode, cudaStream_t st);
+// bulk-TMA pipelined variant for batched chains (sweep_tma.cu); launch_dual_sweep dispatches to it when FS >= 2
+bool sweep_uses_tma(const Dev &d);
+void launch_dual_sweep_tma(const Dev &d, int mode, cudaStream_t st);
 void launch_finish(const Dev &d, int mode, int epi, const BatchDesc &b, double *raw_out, cudaStream_t st);
 void launch_pin(const Dev &d, double *vals, long long stride, int nch, const int *idx, int nidx, cudaStream_t st);
 // `gate`: see Dev::gate
