@@ -375,6 +375,11 @@ int bess_b200_debug_set(int key, int val)
     return guarded([&] { debug_set(key, val); });
 }
 
+int bess_b200_debug_get(unsigned long long *out32)
+{
+    return guarded([&] { debug_get(out32); });
+}
+
 // ---- multi-GPU host helpers ------------------------------------------------------------------------------------------
 void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi)
 {

@@ -63,10 +63,36 @@ size_t fit_smem_bytes(const Dev &d)
 // =====================================================================================================
 // cluster plumbing
 // =====================================================================================================
+// ---- debug phase timers (bess_b200_debug_set(2, 1) enables; bess_b200_debug_get reads): clock64 ticks spent by thread 0
+// of rank 0 between consecutive PH() markers, accumulated per phase id, plus a hit counter per phase
+__device__ int g_dbg_phase_on = 0;
+__device__ unsigned long long g_dbg_phase[2][16];
+struct PhaseTimer {
+    long long t;
+    bool on;
+    __device__ __forceinline__ void start(bool leader)
+    {
+        on = leader && g_dbg_phase_on;
+        if (on) t = clock64();
+    }
+    __device__ __forceinline__ void mark(int id)
+    {
+        if (on) {
+            const long long now = clock64();
+            atomicAdd(&g_dbg_phase[0][id], (unsigned long long)(now - t));
+            atomicAdd(&g_dbg_phase[1][id], 1ull);
+            t = now;
+        }
+    }
+};
+enum { PH_GATHER = 0, PH_EVAL = 1, PH_WZ = 2, PH_SYRK = 3, PH_REDUCE = 4, PH_CHOL = 5, PH_BCAST = 6, PH_GRAD = 7,
+       PH_CYCLE = 8, PH_OTHER = 9 };
+
 struct Clu {
     int CL, rank;
     double *xch;
     int phase;
+    PhaseTimer pt;
 };
 __device__ __forceinline__ void clu_sync(const Clu &cl)
 {
@@ -467,6 +493,7 @@ __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds,
 {
     if (cl.rank == 0) {
         chol_solve(S, lds, nu, sm.rhs, sm);
+        cl.pt.mark(PH_CHOL);
         if (cl.CL > 1) {
             double *bc = cw_slot(cx, 0, 2);
             for (int a = threadIdx.x; a < nu; a += FIT_NT) bc[a] = sm.rhs[a];
@@ -480,6 +507,7 @@ __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds,
         for (int a = threadIdx.x; a < nu; a += FIT_NT) out[a] = sm.rhs[a];
     }
     __syncthreads();
+    cl.pt.mark(PH_BCAST);
 }
 
 // Cluster mode: Sfin[a][b] = sum_q P_q[0][a][b] (- sum_q P_q[1][a][b] when nmat == 2) for a < rows, b < cols, each CTA
@@ -534,15 +562,19 @@ __device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int co
 __device__ void gram_solve(const ChainCtx &cx, Clu &cl, const double *V, int ldv, int mm, const double *wt, double *out,
                            const FitSmem &sm)
 {
+    cl.pt.mark(PH_OTHER);
     if (cl.CL == 1) {
         block_syrk(V, ldv, cx.rb, cx.re, mm, wt, cx.S, cx.lds, sm);
+        cl.pt.mark(PH_SYRK);
         solve_broadcast(cx, cl, cx.S, cx.lds, mm - 1, out, sm);
         return;
     }
     block_syrk(V, ldv, cx.rb, cx.re, mm, wt, cx.Sp0 + cl.rank * cx.sp_stride, cx.ldA, sm);
     clu_sync(cl);
+    cl.pt.mark(PH_SYRK);
     int lds;
     double *S = reduce_partials(cx, cl, mm, mm, 1, false, &lds, sm);
+    cl.pt.mark(PH_REDUCE);
     solve_broadcast(cx, cl, S, lds, mm - 1, out, sm);
 }
 
@@ -574,7 +606,9 @@ __device__ double logit_eval(const ChainCtx &cx, Clu &cl, const double *beta, co
         cx.v[1][r] = pi;
         ll += (cx.y[r] * log(pi) + (1.0 - cx.y[r]) * log(1.0 - pi)) * cx.w[r];
     }
-    return clu_allsum(cl, block_sum<FIT_NT>(ll, sm.red));
+    const double r = clu_allsum(cl, block_sum<FIT_NT>(ll, sm.red));
+    cl.pt.mark(PH_EVAL);
+    return r;
 }
 __device__ void logit_wz(const ChainCtx &cx, bool floor_w)
 {
@@ -594,6 +628,7 @@ __device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm)
     __syncthreads();
     double ll0 = logit_eval(cx, cl, b0, sm);
     logit_wz(cx, false);
+    cl.pt.mark(PH_WZ);
     gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm);
     for (int j = 0; j < 30; j++) {
         const double ll1 = logit_eval(cx, cl, b1, sm);
@@ -602,6 +637,7 @@ __device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm)
         ll0 = ll1;
         __syncthreads();
         logit_wz(cx, true);
+        cl.pt.mark(PH_WZ);
         gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm);
     }
     // result: b0 (the iterate before the last solve)
@@ -931,6 +967,7 @@ __device__ __forceinline__ Clu make_clu(const FitSmem &sm, int CL)
     cl.rank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
     cl.xch = sm.xch;
     cl.phase = 0;
+    cl.pt.start(threadIdx.x == 0 && cl.rank == 0);
     return cl;
 }
 
@@ -1040,6 +1077,7 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
         }
     }
     __syncthreads();
+    cl.pt.mark(PH_GATHER);
 
     double coef0 = coef0_in;
     const double *slopes;
@@ -1069,6 +1107,7 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     }
     const int finished = seen || l >= d.max_iter;
     clu_sync(cl);  // every CTA has read the chain state it needs; rank 0 may now overwrite it
+    cl.pt.mark(PH_CYCLE);
     // scatter (Algorithm.h:159-163), record A
     if (cl.rank == 0) {
         int *hl = d.hist + ((size_t)c * MAX_HIST + l) * d.kcap;
@@ -1091,11 +1130,22 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     }
     if (finished) return;
     chain_gradient(d, cx, cl, slopes, T, coef0, sm);
+    cl.pt.mark(PH_GRAD);
 }
 
 void debug_set(int key, int val)
 {
     if (key == 1) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_cox_iters, &val, sizeof(int)));
+    if (key == 2) {
+        CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_phase_on, &val, sizeof(int)));
+        unsigned long long z[2][16] = {};
+        CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_phase, z, sizeof(z)));
+    }
+}
+void debug_get(unsigned long long *out32)
+{
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpyFromSymbol(out32, g_dbg_phase, sizeof(unsigned long long) * 32));
 }
 
 // cluster size for sparsity level T: enough work per CTA to amortise the cluster barriers, all clusters co-resident.

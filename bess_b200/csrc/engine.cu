@@ -220,11 +220,32 @@ struct Engine::Impl {
         d.gate = nullptr;
         d.X = X; d.ldx = ldx; d.n = n; d.p = p; d.FS = FS;
         d.pstride = (p + 1) & ~1LL;
-        // row splits: enough CTAs to fill the machine several times over
+        // row splits.  One chain (streaming kernel): enough CTAs to fill the machine several times over.
+        // Batched chains (bulk-TMA kernel, 3 CTAs of 256 columns per SM): every extra split costs a set of partial
+        // vectors (written by the sweep, re-read by finish), so pick the split count that balances whole waves of
+        // CTAs against that traffic: score = wave efficiency / (1 + partial bytes / X bytes).
         const long long ntiles = (p + 2LL * SWEEP_NT - 1) / (2LL * SWEEP_NT);
-        long long want = (6LL * sm_count + ntiles - 1) / ntiles;
         long long smax = std::max<long long>(1, n / SWEEP_RC);
-        long long S = std::max<long long>(1, std::min(want, smax));
+        long long S;
+        if (FS == 1) {
+            const long long want = (6LL * sm_count + ntiles - 1) / ntiles;
+            S = std::max<long long>(1, std::min(want, smax));
+        } else {
+            const double slots = 3.0 * sm_count;
+            const int nq = d.family == FAM_LM ? 1 : (d.family == FAM_COX ? 5 : 2);
+            double best = -1.0;
+            S = 1;
+            for (long long cand = 1; cand <= smax; cand++) {
+                const double waves = (double)(ntiles * cand) / slots;
+                const double eff = waves >= 1.0 ? waves / std::ceil(waves) : waves;
+                const double extra = (double)cand * FS * nq * 16.0 / (8.0 * n);
+                const double score = eff / (1.0 + extra);
+                if (score > best * 1.0001) {
+                    best = score;
+                    S = cand;
+                }
+            }
+        }
         int rps = (int)((n + S - 1) / S);
         rps = (rps + 1) & ~1;
         d.rows_per_split = rps;

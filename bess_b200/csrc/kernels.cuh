@@ -137,5 +137,6 @@ size_t fit_smem_bytes(const Dev &d);
 int chain_cluster_size(const Dev &d, int T, int nch);
 void configure_kernels();
 void debug_set(int key, int val);
+void debug_get(unsigned long long *out32);  // chain_fit phase timers: [0][id] clock ticks, [1][id] hits
 
 }  // namespace bess
