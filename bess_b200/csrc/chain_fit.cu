@@ -32,33 +32,43 @@ constexpr int FIT_SMEM_MS = 64;         // normal equations up to 64 x 64 are fa
 constexpr int CHOL_NB = 16;             // panel width of the blocked Cholesky (systems larger than FIT_SMEM_MS)
 
 struct FitSmem {
-    double *tile;     // FIT_TILE_DOUBLES
-    double *scratch;  // FIT_NT * 16
-    double *Ssm;      // FIT_SMEM_MS^2
     double *b0, *b1, *rhs, *dg;  // ldA each
     double *red;      // 40
     double *xch;      // 2 * CLMAX: cluster scalar exchange (written remotely through DSMEM)
+    // the arena: tile | scratch | Ssm are its first three regions; the packed in-smem Cholesky uses all of it
+    double *tile;     // FIT_TILE_DOUBLES
+    double *scratch;  // FIT_NT * 16
+    double *Ssm;      // FIT_SMEM_MS^2
+    int arena_len;    // doubles from `tile` to the end of the dynamic shared memory
 };
-__device__ __forceinline__ FitSmem carve_fit_smem(unsigned char *raw, int ldA)
+constexpr int FIT_ARENA_MIN = FIT_TILE_DOUBLES + FIT_NT * 16 + FIT_SMEM_MS * FIT_SMEM_MS;
+__device__ __forceinline__ FitSmem carve_fit_smem(unsigned char *raw, int ldA, int total_doubles)
 {
     FitSmem s;
     double *p = reinterpret_cast<double *>(raw);
-    s.tile = p; p += FIT_TILE_DOUBLES;
-    s.scratch = p; p += FIT_NT * 16;
-    s.Ssm = p; p += FIT_SMEM_MS * FIT_SMEM_MS;
+    double *const base = p;
     s.b0 = p; p += ldA;
     s.b1 = p; p += ldA;
     s.rhs = p; p += ldA;
     s.dg = p; p += ldA;
     s.red = p; p += 40;
     s.xch = p; p += 2 * CLMAX;
+    s.tile = p;
+    s.scratch = p + FIT_TILE_DOUBLES;
+    s.Ssm = p + FIT_TILE_DOUBLES + FIT_NT * 16;
+    s.arena_len = total_doubles - (int)(p - base);
     return s;
 }
-size_t fit_smem_bytes(const Dev &d)
+// Dynamic shared memory of the chain kernels, in doubles: the minimum layout for small supports, everything the SM has
+// (227 KB) when the normal equations may exceed FIT_SMEM_MS (so systems up to ~230 unknowns are factored in smem).
+int fit_smem_doubles(int ldA, int kcap)
 {
-    return sizeof(double) *
-           ((size_t)FIT_TILE_DOUBLES + FIT_NT * 16 + FIT_SMEM_MS * FIT_SMEM_MS + 4 * (size_t)d.ldA + 40 + 2 * CLMAX);
+    const int fixed = 4 * ldA + 40 + 2 * CLMAX;
+    const int maxd = (232448 - 1024) / 8;
+    if (kcap + 3 <= FIT_SMEM_MS) return fixed + FIT_ARENA_MIN;
+    return std::max(fixed + FIT_ARENA_MIN, maxd);
 }
+size_t fit_smem_bytes(const Dev &d) { return sizeof(double) * (size_t)d.fit_smem_doubles; }
 
 // =====================================================================================================
 // cluster plumbing
@@ -301,6 +311,116 @@ __device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, con
 }
 
 // =====================================================================================================
+// Gram on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64) for systems wide enough to be a real dense contraction
+// (mm > 96): same contract as block_syrk.  Each warp owns a 32 x 32 block of the lower block-triangle (4 x 4 mma tiles,
+// 32 accumulators per thread); row tiles are staged with cp.async into two alternating buffers whose row stride is
+// padded to 4 (mod 8) doubles so the 4-row x 8-column fragment loads are bank-conflict free.  Per 4-row step a warp
+// issues 8 shared loads for 16 DMMAs (4096 FMAs) -- the 4x4 register-blocked FMA path needs 16x more shared-memory
+// bytes per FMA and is shared-memory bound (profiles/r01c: 168 us per Gram at m = 201, 35 % of C2's chain time).
+// =====================================================================================================
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+__device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
+                                const FitSmem &sm)
+{
+    constexpr int NTN = 2;  // warp block = 32 rows x 16 columns: 4 x 2 mma tiles, 16 accumulators per thread
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int mp = ((mm + 3) >> 2) << 2;
+    const int ts = (mp & 7) == 4 ? mp : mp + 4;  // tile row stride == 4 (mod 8) doubles
+    const int nb = (mm + 31) >> 5;                // 32-row block rows; block row bi has 2*bi + 2 column blocks of 16
+    const int nblk = nb * (nb + 1);
+    const int R = (FIT_TILE_DOUBLES / (ts + 1)) & ~3;  // rows per tile, multiple of the mma k
+    double *buf[2] = {sm.tile, sm.scratch};
+    const int ntile = (r1 - r0 + R - 1) / R;
+    const int cpr = mp >> 1;  // 16-byte chunks per row
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int round = 0; round * (FIT_NT / 32) < nblk; round++) {
+        const int blk = round * (FIT_NT / 32) + wid;
+        const bool valid = blk < nblk;
+        int bi = 0, bj = 0;  // blk = bi * (bi + 1) + bj, bj < 2 * bi + 2
+        if (valid) {
+            bi = (int)((sqrt(4.0 * (double)blk + 1.0) - 1.0) * 0.5);
+            while ((bi + 1) * (bi + 2) <= blk) bi++;
+            while (bi * (bi + 1) > blk) bi--;
+            bj = blk - bi * (bi + 1);
+        }
+        double acc[4][NTN][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NTN; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        __syncthreads();
+        for (int t = 0; t <= ntile; t++) {
+            if (t < ntile) {  // stage tile t (cp.async, 16-byte chunks) into buf[t & 1]
+                const int rb = r0 + t * R;
+                const int rc = min(R, r1 - rb);
+                double *dst = buf[t & 1];
+                for (int e = tid; e < rc * cpr; e += FIT_NT) {
+                    const int r = e / cpr, cidx = (e - r * cpr) * 2;
+                    if (cidx < ldv) __pipeline_memcpy_async(dst + r * ts + cidx, V + (size_t)(rb + r) * ldv + cidx, 16);
+                }
+                double *twd = dst + (size_t)R * ts;
+                const int rc4 = (rc + 3) & ~3;
+                for (int r = tid; r < rc4; r += FIT_NT) twd[r] = r < rc ? (wt ? wt[rb + r] : 1.0) : 0.0;
+                // rows that only pad the last k-step must be finite (their weight is 0)
+                for (int e = tid; e < (rc4 - rc) * ts; e += FIT_NT) dst[(size_t)rc * ts + e] = 0.0;
+            }
+            __pipeline_commit();
+            if (t == 0) continue;
+            // tile t-1 is complete once all but the newest commit group have landed
+            __pipeline_wait_prior(1);
+            __syncthreads();
+            if (valid) {
+                const double *tl = buf[(t - 1) & 1];
+                const double *twt = tl + (size_t)R * ts;
+                const int rc4 = (min(R, r1 - (r0 + (t - 1) * R)) + 3) & ~3;
+                const double *pa = tl + t4 * ts + bi * 32 + g;
+                const double *pb = tl + t4 * ts + bj * 16 + g;
+                for (int k0 = 0; k0 < rc4; k0 += 4) {
+                    const double w = twt[k0 + t4];
+                    double a[4], b[NTN];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) a[q] = pa[(size_t)k0 * ts + q * 8] * w;
+#pragma unroll
+                    for (int q = 0; q < NTN; q++) b[q] = pb[(size_t)k0 * ts + q * 8];
+#pragma unroll
+                    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < NTN; nt++) dmma_m8n8k4(acc[mt][nt], a[mt], b[nt]);
+                }
+            }
+            __syncthreads();
+        }
+        if (valid) {
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int a = bi * 32 + mt * 8 + g, b = bj * 16 + nt * 8 + t4 * 2 + u;
+                        if (a < mm && b < mm) {
+                            S[(size_t)a * lds + b] = acc[mt][nt][u];
+                            S[(size_t)b * lds + a] = acc[mt][nt][u];
+                        }
+                    }
+        }
+    }
+    __syncthreads();
+}
+// dispatcher: tensor cores when the system is wide, register-blocked FMAs otherwise
+__device__ __forceinline__ void gram(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
+                                     const FitSmem &sm)
+{
+    if (mm > 96) block_syrk_dmma(V, ldv, r0, r1, mm, wt, S, lds, sm);
+    else block_syrk(V, ldv, r0, r1, mm, wt, S, lds, sm);
+}
+
+// =====================================================================================================
 // Cholesky solves.  The systems are "bordered": rows 0..mm-1 hold the SPD matrix (lower triangle used), row mm holds the
 // right-hand side.  Factoring the bordered matrix leaves z = L^{-1} rhs in row mm (forward substitution for free);
 // a back substitution then gives x = S^{-1} rhs.
@@ -339,9 +459,193 @@ __device__ void block_chol_solve_small(double *S, int lds, int mm, double *x, do
     __syncthreads();
 }
 
-// blocked right-looking version for systems that live in global memory (L2): panels of CHOL_NB columns are factored in
-// shared memory, the trailing matrix is updated with register-blocked 4x4 tiles.
-__device__ void block_chol_solve_blocked(double *S, int lds, int mm, double *x, const FitSmem &sm)
+// Factor one CHOL_NB-column panel of a bordered lower-triangular system held in shared memory.  Thread i owns panel row i
+// (i < mr <= FIT_NT) in registers; rowp(i) points at its first panel column.  Per column q one block barrier: the rows of the
+// diagonal block publish their (unscaled) column-q entry, every thread derives the pivot and L[c][q] itself and updates
+// its own row.  On exit rows hold L (diagonal block: lower part only, `lower_only(i)` tells how many columns row i has).
+template <class RowPtr>
+__device__ __forceinline__ void panel_factor(RowPtr rowp, int mr, int nb, double *colbuf /* 2 * CHOL_NB */)
+{
+    constexpr int NB = CHOL_NB;
+    const int i = threadIdx.x;
+    const bool own = i < mr;
+    double row[NB];
+    double *rp = own ? rowp(i) : nullptr;
+#pragma unroll
+    for (int c = 0; c < NB; c++) row[c] = (own && c < nb && (i >= nb || c <= i)) ? rp[c] : 0.0;
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+        if (q < nb) {
+            double *cb = colbuf + (q & 1) * NB;
+            if (own && i >= q && i < nb) cb[i] = row[q];
+            __syncthreads();
+            const double inv = rsqrt(cb[q]);
+            if (i == q) row[q] = cb[q] * inv;
+            else if (i > q) row[q] *= inv;
+            if (i > q) {
+#pragma unroll
+                for (int c = 0; c < NB; c++)
+                    if (c > q && c < nb) row[c] -= row[q] * (cb[c] * inv);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NB; c++)
+        if (own && c < nb && (i >= nb || c <= i)) rp[c] = row[c];
+    __syncthreads();
+}
+
+// Bordered Cholesky solve entirely in shared memory (one CTA) for systems of 65 .. ~230 unknowns: the lower triangle is
+// copied from the global matrix into PACKED row-major storage in the arena, factored right-looking in CHOL_NB-column
+// panels (panel_factor + register-blocked 4x4 trailing update) and back-substituted in place.  x (smem) <- solution.
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+__device__ __forceinline__ bool packed_fits(int mm, int arena_len) { return tri(mm + 1) + FIT_NT <= arena_len; }
+__device__ void chol_packed_smem(const double *Sg, int lds, int mm, double *x, const FitSmem &sm, PhaseTimer &pt)
+{
+    constexpr int NB = CHOL_NB;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *Lp = sm.tile;                 // packed: row i at tri(i), columns 0..min(i, mm-1)
+    double *red = sm.tile + tri(mm + 1);  // FIT_NT doubles of reduction scratch behind the matrix
+    __syncthreads();
+    for (int i0 = wid * 8; i0 <= mm; i0 += (FIT_NT / 32) * 8) {
+        for (int c = lane; c < mm; c += 32) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u;
+                if (i <= mm && c <= i) v[u] = Sg[(size_t)i * lds + c];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u;
+                if (i <= mm && c <= i) Lp[tri(i) + c] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+    pt.mark(10);
+    for (int j0 = 0; j0 < mm; j0 += NB) {
+        const int nb = min(NB, mm - j0);
+        const int mr = mm + 1 - j0;
+        panel_factor([&](int i) { return Lp + tri(j0 + i) + j0; }, mr, nb, sm.dg);
+        const int t0 = j0 + nb;
+        const int mt = mm - t0;
+        if (mt <= 0) break;
+        // trailing update: S[a][b] -= sum_q L[a][j0+q] L[b][j0+q] for a in [t0, mm], b in [t0, min(a, mm-1)]
+        const int rbk = (mt + 1 + 3) >> 2;
+        const int nblk = rbk * (rbk + 1) / 2;
+        for (int blk = tid; blk < nblk; blk += FIT_NT) {
+            int bi = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
+            while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
+            while (bi * (bi + 1) / 2 > blk) bi--;
+            const int bj = blk - bi * (bi + 1) / 2;
+            double acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) acc[e] = 0.0;
+            const double *pa[4], *pb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int ra = min(t0 + 4 * bi + u, mm), rb = min(t0 + 4 * bj + u, mm);
+                pa[u] = Lp + tri(ra) + j0;
+                pb[u] = Lp + tri(rb) + j0;
+            }
+            for (int q = 0; q < nb; q++) {
+                double a[4], bb[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    a[u] = pa[u][q];
+                    bb[u] = pb[u][q];
+                }
+#pragma unroll
+                for (int qa = 0; qa < 4; qa++)
+#pragma unroll
+                    for (int qb = 0; qb < 4; qb++) acc[qa * 4 + qb] = fma(a[qa], bb[qb], acc[qa * 4 + qb]);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const int a = t0 + 4 * bi + (e >> 2), b = t0 + 4 * bj + (e & 3);
+                if (a <= mm && b < mm && b <= a) Lp[tri(a) + b] -= acc[e];
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    pt.mark(11);
+    // back substitution L^T x = z, z = row mm
+    for (int c = tid; c < mm; c += FIT_NT) x[c] = Lp[tri(mm) + c];
+    __syncthreads();
+    const int jlast = ((mm - 1) / NB) * NB;
+    for (int j0 = jlast; j0 >= 0; j0 -= NB) {
+        const int nb = min(NB, mm - j0);
+        const int t0 = j0 + nb;
+        double acc[NB];
+#pragma unroll
+        for (int q = 0; q < NB; q++) acc[q] = 0.0;
+        for (int i = t0 + tid; i < mm; i += FIT_NT) {
+            const double xi = x[i];
+            const double *Li = Lp + tri(i) + j0;
+#pragma unroll
+            for (int q = 0; q < NB; q++)
+                if (q < nb) acc[q] = fma(Li[q], xi, acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NB; q++) acc[q] = warp_sum(acc[q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NB; q++) red[wid * NB + q] = acc[q];
+        }
+        __syncthreads();
+        if (wid == 0) {
+            double t = 0.0;
+            if (lane < nb) {
+                double vsum = 0.0;
+                for (int w2 = 0; w2 < FIT_NT / 32; w2++) vsum += red[w2 * NB + lane];
+                t = x[j0 + lane] - vsum;
+            }
+            for (int q = nb - 1; q >= 0; q--) {
+                const double yq = __shfl_sync(0xffffffffu, t, q) / Lp[tri(j0 + q) + j0 + q];
+                if (lane == q) t = yq;
+                if (lane < q) t -= Lp[tri(j0 + q) + j0 + lane] * yq;
+            }
+            if (lane < nb) x[j0 + lane] = t;
+        }
+        __syncthreads();
+    }
+    pt.mark(12);
+}
+
+// P[i][q] = S[j0 + i][j0 + q] for i in [i0, i1), q < nb: 8 independent loads in flight per thread
+__device__ __forceinline__ void panel_load(double *P, const double *S, int lds, int j0, int i0, int i1, int nb)
+{
+    constexpr int PS = CHOL_NB + 1;
+    const int tot = (i1 - i0) * nb;
+    for (int e0 = threadIdx.x; e0 < tot; e0 += 8 * FIT_NT) {
+        double val[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * FIT_NT;
+            if (e < tot) {
+                const int i = i0 + e / nb, q = e % nb;
+                val[u] = S[(size_t)(j0 + i) * lds + j0 + q];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * FIT_NT;
+            if (e < tot) {
+                const int i = i0 + e / nb, q = e % nb;
+                P[i * PS + q] = val[u];
+            }
+        }
+    }
+}
+
+// Blocked right-looking version for systems that live in global memory (L2), run by the WHOLE cluster: rank 0 factors
+// each CHOL_NB-column panel in shared memory (diagonal block by one warp, rows below by one thread each) and writes it
+// back; after a cluster barrier every CTA loads the panel and updates its share of the trailing matrix with
+// register-blocked 4x4 tiles (read-modify-write in L2); a second barrier publishes the update.  Back substitution on
+// rank 0.  x (rank 0's shared memory) <- solution.  With CL == 1 the barriers degenerate to __syncthreads.
+__device__ __noinline__ void chol_blocked_cluster(double *S, int lds, int mm, double *x, const FitSmem &sm, Clu &cl)
 {
     constexpr int NB = CHOL_NB, PS = NB + 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -350,58 +654,32 @@ __device__ void block_chol_solve_blocked(double *S, int lds, int mm, double *x, 
         const int nb = min(NB, mm - j0);
         const int mr = mm + 1 - j0;
         __syncthreads();
-        for (int e = tid; e < mr * nb; e += FIT_NT) {
-            const int i = e / nb, q = e - i * nb;
-            P[i * PS + q] = S[(size_t)(j0 + i) * lds + j0 + q];
-        }
-        __syncthreads();
-        if (wid == 0) {  // diagonal block, unblocked, one warp
-            for (int q = 0; q < nb; q++) {
-                const double dqq = sqrt(P[q * PS + q]);
-                __syncwarp();
-                if (lane == q) P[q * PS + q] = dqq;
-                if (lane > q && lane < nb) P[lane * PS + q] /= dqq;
-                __syncwarp();
-                if (lane > q && lane < nb) {
-                    const double liq = P[lane * PS + q];
-                    for (int c = q + 1; c <= lane; c++) P[lane * PS + c] -= liq * P[c * PS + q];
-                }
-                __syncwarp();
+        if (cl.rank == 0) {
+            panel_load(P, S, lds, j0, 0, mr, nb);
+            __syncthreads();
+            cl.pt.mark(10);
+            panel_factor([&](int i) { return P + i * PS; }, mr, nb, sm.dg);
+            cl.pt.mark(12);
+            // L panel back to global (the other CTAs and the back substitution read it there)
+            for (int e = tid; e < mr * nb; e += FIT_NT) {
+                const int i = e / nb, q = e - i * nb;
+                if (i >= nb || q <= i) S[(size_t)(j0 + i) * lds + j0 + q] = P[i * PS + q];
             }
         }
-        __syncthreads();
-        // rows below the diagonal block: row_i <- row_i * L_diag^{-T}
-        for (int i = nb + tid; i < mr; i += FIT_NT) {
-            double row[NB];
-#pragma unroll
-            for (int q = 0; q < NB; q++) row[q] = q < nb ? P[i * PS + q] : 0.0;
-#pragma unroll
-            for (int q = 0; q < NB; q++) {
-                if (q < nb) {
-                    double s = row[q];
-#pragma unroll
-                    for (int c = 0; c < NB; c++)
-                        if (c < q) s -= row[c] * P[q * PS + c];
-                    row[q] = s / P[q * PS + q];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NB; q++)
-                if (q < nb) P[i * PS + q] = row[q];
-        }
-        __syncthreads();
-        // L panel back to global (needed by the back substitution)
-        for (int e = tid; e < mr * nb; e += FIT_NT) {
-            const int i = e / nb, q = e - i * nb;
-            if (i >= nb || q <= i) S[(size_t)(j0 + i) * lds + j0 + q] = P[i * PS + q];
-        }
-        // trailing update: S[a][b] -= sum_q P[a][q] P[b][q] for a in [t0, mm], b in [t0, min(a, mm-1)], t0 = j0 + nb
         const int t0 = j0 + nb;
         const int mt = mm - t0;  // trailing columns
-        if (mt > 0) {
+        if (mt <= 0) break;      // uniform over the cluster
+        clu_sync(cl);
+        cl.pt.mark(13);
+        if (cl.rank != 0) {
+            panel_load(P, S, lds, j0, nb, mr, nb);
+            __syncthreads();
+        }
+        // trailing update: S[a][b] -= sum_q P[a][q] P[b][q] for a in [t0, mm], b in [t0, min(a, mm-1)]
+        {
             const int rbk = (mt + 1 + 3) >> 2;  // row blocks (incl. the rhs row)
             const int nblk = rbk * (rbk + 1) / 2;
-            for (int blk = tid; blk < nblk; blk += FIT_NT) {
+            for (int blk = cl.rank * FIT_NT + tid; blk < nblk; blk += cl.CL * FIT_NT) {
                 int bi = (int)((sqrt(8.0 * (double)blk + 1.0) - 1.0) * 0.5);
                 while ((bi + 1) * (bi + 2) / 2 <= blk) bi++;
                 while (bi * (bi + 1) / 2 > blk) bi--;
@@ -430,7 +708,10 @@ __device__ void block_chol_solve_blocked(double *S, int lds, int mm, double *x, 
                 }
             }
         }
+        clu_sync(cl);
+        cl.pt.mark(14);
     }
+    if (cl.rank != 0) return;
     __syncthreads();
     // back substitution L^T x = z, z = row mm
     for (int c = tid; c < mm; c += FIT_NT) x[c] = S[(size_t)mm * lds + c];
@@ -481,23 +762,22 @@ __device__ void block_chol_solve_blocked(double *S, int lds, int mm, double *x, 
     }
 }
 
-// Solve the bordered system held at S (rank 0 of the cluster only); x <- solution (mm entries, shared memory).
-__device__ __forceinline__ void chol_solve(double *S, int lds, int mm, double *x, const FitSmem &sm)
-{
-    if (S == sm.Ssm) block_chol_solve_small(S, lds, mm, x, sm.dg);
-    else block_chol_solve_blocked(S, lds, mm, x, sm);
-}
-
-// Rank 0 holds a bordered system (nu unknowns) at S: solve it and hand the solution to every CTA of the cluster (out: smem).
+// Rank 0 holds a bordered system (nu unknowns) at S -- its own shared memory (small systems) or the chain's global matrix
+// (large systems, then every CTA of the cluster takes part in the factorisation): solve it and hand the solution to
+// every CTA of the cluster (out: smem).
 __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds, int nu, double *out, const FitSmem &sm)
 {
-    if (cl.rank == 0) {
-        chol_solve(S, lds, nu, sm.rhs, sm);
-        cl.pt.mark(PH_CHOL);
-        if (cl.CL > 1) {
-            double *bc = cw_slot(cx, 0, 2);
-            for (int a = threadIdx.x; a < nu; a += FIT_NT) bc[a] = sm.rhs[a];
-        }
+    if (S == sm.Ssm) {
+        if (cl.rank == 0) block_chol_solve_small(S, lds, nu, sm.rhs, sm.dg);
+    } else if (packed_fits(nu, sm.arena_len)) {
+        if (cl.rank == 0) chol_packed_smem(S, lds, nu, sm.rhs, sm, cl.pt);
+    } else {
+        chol_blocked_cluster(S, lds, nu, sm.rhs, sm, cl);
+    }
+    cl.pt.mark(PH_CHOL);  // small systems: the whole solve; blocked: the back substitution (phases 10-14 = panels)
+    if (cl.rank == 0 && cl.CL > 1) {
+        double *bc = cw_slot(cx, 0, 2);
+        for (int a = threadIdx.x; a < nu; a += FIT_NT) bc[a] = sm.rhs[a];
     }
     if (cl.CL > 1) {
         clu_sync(cl);
@@ -564,12 +844,12 @@ __device__ void gram_solve(const ChainCtx &cx, Clu &cl, const double *V, int ldv
 {
     cl.pt.mark(PH_OTHER);
     if (cl.CL == 1) {
-        block_syrk(V, ldv, cx.rb, cx.re, mm, wt, cx.S, cx.lds, sm);
+        gram(V, ldv, cx.rb, cx.re, mm, wt, cx.S, cx.lds, sm);
         cl.pt.mark(PH_SYRK);
         solve_broadcast(cx, cl, cx.S, cx.lds, mm - 1, out, sm);
         return;
     }
-    block_syrk(V, ldv, cx.rb, cx.re, mm, wt, cx.Sp0 + cl.rank * cx.sp_stride, cx.ldA, sm);
+    gram(V, ldv, cx.rb, cx.re, mm, wt, cx.Sp0 + cl.rank * cx.sp_stride, cx.ldA, sm);
     clu_sync(cl);
     cl.pt.mark(PH_SYRK);
     int lds;
@@ -814,8 +1094,8 @@ __device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &
         double *P1 = cl.CL == 1 ? cx.S : cx.Sp0 + cl.rank * cx.sp_stride;
         double *P2 = cl.CL == 1 ? cx.Sfin + (size_t)ldA * ldA : P1 + (size_t)ldA * ldA;
         const int ld1 = cl.CL == 1 ? cx.lds : ldA;
-        block_syrk(cx.XA, ldA, cx.rb, cx.re, m, om, P1, ld1, sm);
-        block_syrk(XB, ldA, cx.rb, cx.re, m, ev, P2, ldA, sm);
+        gram(cx.XA, ldA, cx.rb, cx.re, m, om, P1, ld1, sm);
+        gram(XB, ldA, cx.rb, cx.re, m, ev, P2, ldA, sm);
         {
             // g_a = sum_r XA[r][a]*gv[r] over the slice: (a, sub-slice) decomposition, deterministic reduction
             const int nsl = max(1, FIT_NT / m);
@@ -976,7 +1256,7 @@ __device__ __forceinline__ Clu make_clu(const FitSmem &sm, int CL)
 __global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, const BatchDesc b)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA);
+    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA, d.fit_smem_doubles);
     const int c = b.chain[blockIdx.x];
     // Algorithm::coef0_init is only refreshed when the path starts a new step (path.cpp:57); CV folds of the same
     // step inherit it.
@@ -1018,7 +1298,7 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, con
 __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const BatchDesc b)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA);
+    const FitSmem sm = carve_fit_smem(smem_raw, d.ldA, d.fit_smem_doubles);
     if (d.gate && *d.gate == 0) return;  // whole batch already finished (speculative launch)
     const int CL = b.CL;
     const int c = b.chain[blockIdx.x / CL];

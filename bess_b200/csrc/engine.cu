@@ -227,7 +227,9 @@ struct Engine::Impl {
         const long long ntiles = (p + 2LL * SWEEP_NT - 1) / (2LL * SWEEP_NT);
         long long smax = std::max<long long>(1, n / SWEEP_RC);
         long long S;
-        if (FS == 1) {
+        const double part_bytes_per_split = 8.0 * FS * (d.family == FAM_LM ? 1 : (d.family == FAM_COX ? 5 : 2)) * (double)p;
+        if (FS == 1 || part_bytes_per_split < 16.0e6) {
+            // partial vectors stay in L2: splits are free, fill the machine several times over
             const long long want = (6LL * sm_count + ntiles - 1) / ntiles;
             S = std::max<long long>(1, std::min(want, smax));
         } else {
@@ -692,6 +694,7 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     Dev &d = m.d;
     d.kcap = kcap;
     d.ldA = (kcap + 2 + 1) & ~1;
+    d.fit_smem_doubles = fit_smem_doubles(d.ldA, kcap);
     d.max_iter = max_iter;
     d.warm = warm_start ? 1 : 0;
 

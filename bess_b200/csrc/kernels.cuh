@@ -63,6 +63,7 @@ struct Dev {
     double *AXr;        // [MAXC][n][ldXr] active columns of this iteration for ALL rows, summed over ranks (ldXr = T)
     double *AXk;        // [MAXC][n][ldXk] all-row active columns of each chain's CURRENT support (losses)
     int ldXr, ldXk;
+    int fit_smem_doubles; // dynamic shared memory of the chain kernels, in doubles (fit_smem_doubles())
     int CLcap;          // largest cluster size the workspaces were sized for
     int nmat;           // Gram matrices per fit step: 2 for cox, else 1
     double *xtx;        // [MAXC][p] x_j.x_j over the chain's train rows (gaussian only)
@@ -134,6 +135,7 @@ void launch_gather_cols_pos(const double *X, long long ldx, int n, const int *co
 void launch_screen_glm(const double *X, long long ldx, int n, int p, const double *y, const double *w, int family,
                        double *util, cudaStream_t st);
 size_t fit_smem_bytes(const Dev &d);
+int fit_smem_doubles(int ldA, int kcap);
 int chain_cluster_size(const Dev &d, int T, int nch);
 void configure_kernels();
 void debug_set(int key, int val);

@@ -135,6 +135,32 @@ def test_fit_level_parity_with_oracle(fam, n, p, k, K):
     eng.close()
 
 
+@pytest.mark.parametrize("fam,n,p,T", [("gaussian", 700, 900, 100), ("gaussian", 700, 900, 200), ("gaussian", 700, 900, 250),
+                                        ("binomial", 1500, 800, 80), ("binomial", 1500, 800, 150), ("cox", 900, 700, 70),
+                                        ("poisson", 1200, 800, 120)])
+def test_large_support_solvers_against_oracle(fam, n, p, T):
+    """Supports wide enough for every normal-equation path: unblocked smem Cholesky (<= 64), DMMA Gram (> 96), packed
+    in-smem blocked Cholesky (65..~230 unknowns) and the cluster-distributed blocked Cholesky in L2 (> 230)."""
+    from bess_b200.engine import GpuEngine
+    from bess_b200.gen_data import gen_data
+    model_type, data_type = FAM[fam]
+    d = gen_data(n, p, fam, 10, seed=31)
+    w = np.ones(n)
+    eng = GpuEngine()
+    eng.load(d.x, d.y, w, model_type)
+    eng.normalize(data_type, True)
+    eng.setup_chains(0, None, T, 20, True)
+    data = orc.make_data(d.x, d.y, w, data_type, True, model_type)
+    st = orc.PathState(data, model_type, 3, False, 0, None, 20, True)
+    r = eng.run_batch(T, [0], True)
+    o = orc.pdas_fit(data, model_type, T, np.zeros(p), 0.0, st.full_mask, st.xtx_full, 20)
+    assert r["A"][0].tolist() == o.A.tolist()
+    assert int(r["l"][0]) == o.l
+    assert rel_err(r["bA"][0], o.beta[o.A]) < 1e-7  # ill-conditioned by design (k close to n / separation)
+    assert abs(r["coef0"][0] - o.coef0) <= 1e-7 * max(1.0, abs(o.coef0))
+    eng.close()
+
+
 @pytest.mark.parametrize("fam,path_type,is_cv", [("gaussian", 2, True), ("binomial", 1, True), ("poisson", 2, False),
                                                  ("cox", 1, True), ("binomial", 2, True)])
 def test_path_parity_with_oracle(fam, path_type, is_cv):
