@@ -70,7 +70,7 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
 def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
         fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
-        world=1, rank=0, col_lo=0, p_total=None, nccl_id=None):
+        world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,)):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
     ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``.
     ``world > 1``: column-sharded multi-GPU call -- ``x`` is this rank's column shard ``[col_lo, col_lo + p)`` of a
@@ -86,7 +86,8 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     w = np.ascontiguousarray(weight, dtype=np.float64).ravel()
     g = np.arange(p, dtype=np.int32)
-    st, lam = np.zeros(1), np.zeros(1)
+    st = np.zeros(1)
+    lam = np.ascontiguousarray(lambda_seq, dtype=np.float64).ravel()
     seq = np.ascontiguousarray(sequence, dtype=np.int32).ravel()
     alw = np.ascontiguousarray(list(always_select), dtype=np.int32).ravel()
     sharded = world > 1
@@ -112,17 +113,19 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     ext.screening_A_out = _i(scrA)
     chosen = C.c_int(0)
     ext.chosen_s_out = C.pointer(chosen)
+    chosen_lam = C.c_double(0.0)
+    ext.chosen_lambda_out = C.pointer(chosen_lam)
     stats = np.zeros(32)
     ext.stats_out = _d(stats)
     ext.profile = 1 if profile else 0
     rc = lib.bess_b200_fit(xptr, n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal),
                            int(algorithm_type), int(model_type), int(max_iter), int(exchange_num), int(path_type),
                            bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g), g.size, _d(st), 1, _i(seq),
-                           seq.size, _d(lam), 1, int(s_min), int(s_max), 10, 10.0, 0.0, 0.0, 1, bool(is_screening),
+                           seq.size, _d(lam), lam.size, int(s_min), int(s_max), 10, 10.0, 0.0, 0.0, lam.size, bool(is_screening),
                            int(screening_size), 1, _i(alw), alw.size, 1.1, _d(beta), p_all, C.byref(c0), C.byref(tl),
                            C.byref(ic), C.byref(ext))
     _lib.check(rc)
-    out = dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, s=chosen.value,
+    out = dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, s=chosen.value, lam=chosen_lam.value,
                stats=dict(n_fits=int(stats[0]), n_pdas_iters=int(stats[1]), n_sweeps=int(stats[2]),
                           n_batches=int(stats[3]), n_boundary_ties=int(stats[4]), sweep_bytes=float(stats[5]),
                           kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[24]),
@@ -138,7 +141,10 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
         b_all = np.zeros((L, p)) if path_type == 1 else None
         lib.bess_b200_trace(_i(s_all), _i(l_all), _d(c_all) if path_type == 1 else None, _d(t_all), _d(i_all),
                             _d(b_all) if b_all is not None else None, p)
-        out.update(s_all=s_all, l_all=l_all, coef0_all=c_all, loss_all=t_all, ic_all=i_all, beta_all=b_all)
+        lam_all = np.zeros(L)
+        lib.bess_b200_trace_lambda(_d(lam_all))
+        out.update(s_all=s_all, l_all=l_all, coef0_all=c_all, loss_all=t_all, ic_all=i_all, beta_all=b_all,
+                   lambda_all=lam_all)
     return out
 
 

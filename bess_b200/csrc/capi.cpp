@@ -103,6 +103,7 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
             if (ext->screening_A_out && !r.screening_A.empty())
                 std::copy(r.screening_A.begin(), r.screening_A.end(), ext->screening_A_out);
             if (ext->chosen_s_out) *ext->chosen_s_out = r.chosen_s;
+            if (ext->chosen_lambda_out) *ext->chosen_lambda_out = r.lambda;
             if (ext->stats_out) {
                 ext->stats_out[0] = (double)r.stats.n_fits;
                 ext->stats_out[1] = (double)r.stats.n_pdas_iters;
@@ -202,6 +203,13 @@ int bess_b200_trace(int *s_all, int *l_all, double *coef0_all, double *train_los
                 if (r.A_all[i][q] < p) row[r.A_all[i][q]] = r.bA_all[i][q];
         }
     return (int)L;
+}
+
+int bess_b200_trace_lambda(double *lambda_all)
+{
+    const BessResult &r = g_last;
+    if (lambda_all) std::copy(r.lambda_all.begin(), r.lambda_all.end(), lambda_all);
+    return (int)r.lambda_all.size();
 }
 
 int bess_b200_cv_fold_ids(int n, int K, unsigned seed, int *out)

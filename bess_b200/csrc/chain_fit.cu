@@ -794,7 +794,7 @@ __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds,
 // reducing a slab of rows, ranks summed in a fixed order; optional extra row `rows` = sum_q cw_slot(q, 1) (Cox gradient).
 // Ends with a cluster barrier; afterwards rank 0 stages the system where it will factor it and returns that pointer.
 __device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int cols, int nmat, bool extra_row, int *lds_out,
-                                   const FitSmem &sm)
+                                   const FitSmem &sm, double diag_add = 0.0, int diag_from = 0, int diag_to = 0)
 {
     const int ldA = cx.ldA;
     const int per = (rows + cl.CL - 1) / cl.CL;
@@ -810,6 +810,7 @@ __device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int co
             for (int q = 0; q < cl.CL; q++) s2 += cx.Sp0[q * cx.sp_stride + (size_t)ldA * ldA + o];
             s -= s2;
         }
+        if (a == b && a >= diag_from && a < diag_to) s += diag_add;
         cx.Sfin[o] = s;
     }
     if (extra_row && cl.rank == cl.CL - 1) {
@@ -840,11 +841,15 @@ __device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int co
 // row mm-1 as right-hand side:  S = sum_r wt[r] V[r][a] V[r][b];  S[0:mm-1, 0:mm-1] x = S[mm-1, 0:mm-1].
 // out (shared memory of every CTA) <- x.
 __device__ void gram_solve(const ChainCtx &cx, Clu &cl, const double *V, int ldv, int mm, const double *wt, double *out,
-                           const FitSmem &sm)
+                           const FitSmem &sm, double diag_add = 0.0, int diag_from = 0)
 {
     cl.pt.mark(PH_OTHER);
     if (cl.CL == 1) {
         gram(V, ldv, cx.rb, cx.re, mm, wt, cx.S, cx.lds, sm);
+        if (diag_add != 0.0) {  // ridge term on the unknowns [diag_from, mm - 1)
+            for (int a = diag_from + threadIdx.x; a < mm - 1; a += FIT_NT) cx.S[(size_t)a * cx.lds + a] += diag_add;
+            __syncthreads();
+        }
         cl.pt.mark(PH_SYRK);
         solve_broadcast(cx, cl, cx.S, cx.lds, mm - 1, out, sm);
         return;
@@ -853,7 +858,7 @@ __device__ void gram_solve(const ChainCtx &cx, Clu &cl, const double *V, int ldv
     clu_sync(cl);
     cl.pt.mark(PH_SYRK);
     int lds;
-    double *S = reduce_partials(cx, cl, mm, mm, 1, false, &lds, sm);
+    double *S = reduce_partials(cx, cl, mm, mm, 1, false, &lds, sm, diag_add, diag_from, mm - 1);
     cl.pt.mark(PH_REDUCE);
     solve_broadcast(cx, cl, S, lds, mm - 1, out, sm);
 }
@@ -866,12 +871,12 @@ __device__ __forceinline__ double row_dot(const double *row, const double *b, in
 }
 
 // ---- gaussian: Algorithm.h:1131-1135
-__device__ void fit_lm(const ChainCtx &cx, Clu &cl, const FitSmem &sm, double *beta_out)
+__device__ void fit_lm(const ChainCtx &cx, Clu &cl, const FitSmem &sm, double *beta_out, double lambda)
 {
     const int T = cx.T, ldA = cx.ldA;
     for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) cx.XA[(size_t)r * ldA + T] = cx.y[r];
     __syncthreads();
-    gram_solve(cx, cl, cx.XA, ldA, T + 1, nullptr, beta_out, sm);
+    gram_solve(cx, cl, cx.XA, ldA, T + 1, nullptr, beta_out, sm, lambda, 0);  // X'X + lambda*I (Algorithm.h:1134)
 }
 
 // ---- binomial: Algorithm.h:1148-1204.  Design columns: [1 | X_A | z]
@@ -901,7 +906,7 @@ __device__ void logit_wz(const ChainCtx &cx, bool floor_w)
     }
     __syncthreads();
 }
-__device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm)
+__device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm, double lambda)
 {
     double *b0 = sm.b0, *b1 = sm.b1;
     for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = 0.0;
@@ -909,7 +914,7 @@ __device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm)
     double ll0 = logit_eval(cx, cl, b0, sm);
     logit_wz(cx, false);
     cl.pt.mark(PH_WZ);
-    gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm);
+    gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm, 2.0 * lambda, 1);  // + 2*lambda*lambdamat, intercept free
     for (int j = 0; j < 30; j++) {
         const double ll1 = logit_eval(cx, cl, b1, sm);
         if (fabs(ll0 - ll1) / (0.1 + fabs(ll1)) < 1e-6) break;
@@ -918,13 +923,13 @@ __device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm)
         __syncthreads();
         logit_wz(cx, true);
         cl.pt.mark(PH_WZ);
-        gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm);
+        gram_solve(cx, cl, cx.XA, cx.ldA, cx.m + 1, cx.v[2], b1, sm, 2.0 * lambda, 1);  // + 2*lambda*lambdamat, intercept free
     }
     // result: b0 (the iterate before the last solve)
 }
 
 // ---- poisson: Algorithm.h:1273-1322
-__device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const FitSmem &sm)
+__device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const FitSmem &sm, double lambda)
 {
     double *b0 = sm.b0;
     const int ldA = cx.ldA;
@@ -944,7 +949,7 @@ __device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const 
             cx.XA[(size_t)r * ldA + cx.m] = cx.v[0][r] + (cx.y[r] - e) / e;
         }
         __syncthreads();
-        gram_solve(cx, cl, cx.XA, ldA, cx.m + 1, cx.v[2], b0, sm);
+        gram_solve(cx, cl, cx.XA, ldA, cx.m + 1, cx.v[2], b0, sm, 2.0 * lambda, 1);
         double ll = 0.0;
         for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
             const double eta = clampd(row_dot(cx.XA + (size_t)r * ldA, b0, cx.m), 30.0);
@@ -1059,7 +1064,7 @@ __device__ void cox_riskset_means(const ChainCtx &cx, Clu &cl, double *XB, const
     __syncthreads();
 }
 __device__ int g_dbg_cox_iters = 30;  // debug knob (bess_b200_debug_set key 1); 30 = reference behaviour
-__device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &sm)
+__device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &sm, double lambda)
 {
     const int max_newton = g_dbg_cox_iters;
     const int m = cx.m, ldA = cx.ldA;
@@ -1111,6 +1116,8 @@ __device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &
                 double s = 0.0;
                 for (int sl = 0; sl < nsl; sl++)
                     if (a + sl * m < m * nsl) s += sm.scratch[sl * m + a];
+                // + 2*lambda*beta0 (Algorithm.h:1429); in cluster mode rank 0's share carries it
+                if (cl.rank == 0) s += 2.0 * lambda * b0[a];
                 gdst[a] = s;  // CL == 1: row m of the bordered system
             }
             __syncthreads();
@@ -1121,13 +1128,15 @@ __device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &
             for (int it = threadIdx.x; it < m * m; it += FIT_NT) {
                 const int a = it / m, bcol = it % m;
                 cx.S[(size_t)a * cx.lds + bcol] -= P2[(size_t)a * ldA + bcol];
+                // h + 2*lambda*I on the reference's negative-definite h (Algorithm.h:1472)  <=>  P - 2*lambda*I here
+                if (a == bcol) cx.S[(size_t)a * cx.lds + bcol] -= 2.0 * lambda;
             }
             __syncthreads();
             S = cx.S;
             lds = cx.lds;
         } else {
             clu_sync(cl);
-            S = reduce_partials(cx, cl, m, m, 2, true, &lds, sm);
+            S = reduce_partials(cx, cl, m, m, 2, true, &lds, sm, -2.0 * lambda, 0, m);
         }
         // P d' = g  (d' = -d of Algorithm.h:1472)
         solve_broadcast(cx, cl, S, lds, m, sm.rhs, sm);
@@ -1362,18 +1371,18 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     double coef0 = coef0_in;
     const double *slopes;
     if (d.family == FAM_LM) {
-        fit_lm(cx, cl, sm, sm.b0);
+        fit_lm(cx, cl, sm, sm.b0, d.lambda);
         slopes = sm.b0;
     } else if (d.family == FAM_LOGIT) {
-        fit_logistic(cx, cl, sm);
+        fit_logistic(cx, cl, sm, d.lambda);
         coef0 = sm.b0[0];
         slopes = sm.b0 + 1;
     } else if (d.family == FAM_POISSON) {
-        fit_poisson(cx, cl, coef0_in, sm);
+        fit_poisson(cx, cl, coef0_in, sm, d.lambda);
         coef0 = sm.b0[0];
         slopes = sm.b0 + 1;
     } else {
-        fit_cox(cx, cl, d.XB + (size_t)c * d.n * ldA, sm);
+        fit_cox(cx, cl, d.XB + (size_t)c * d.n * ldA, sm, d.lambda);
         slopes = sm.b0;
     }
     __syncthreads();

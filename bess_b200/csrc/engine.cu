@@ -862,7 +862,7 @@ static inline int sweep_epi(int family)
 }
 
 void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out,
-                       const std::vector<LossJob> *jobs, std::vector<double> *loss_out)
+                       const std::vector<LossJob> *jobs, std::vector<double> *loss_out, double lambda)
 {
     Impl &m = *d_;
     if (!m.chains_ready) throw EngineError{"run_batch before setup_chains"};
@@ -893,6 +893,8 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         }
     }
     d.ldXr = T;
+    if (!(lambda >= 0.0)) throw EngineError{"lambda must be >= 0"};
+    d.lambda = lambda;
     const int mode = sweep_mode(family_), epi = sweep_epi(family_);
     const double vec_bytes = 8.0 * d.n * b.nch * (mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 4)) + 8.0 * d.p * b.nch;
 

@@ -94,8 +94,9 @@ public:
     // ---- one sparsity level for a set of chains (ascending chain ids).  with_full: the batch starts a new
     // path step (update_coef0_init, path.cpp:57) -- chain 0 must then be in the set.
     // jobs/loss_out: optional Metric losses evaluated right behind the fits (same stream, one host synchronisation).
+    // lambda: ridge level of the fits (Algorithm::lambda_level, the L0L2 / "bsrr" penalty); 0 = best-subset selection.
     void run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out,
-                   const std::vector<LossJob> *jobs = nullptr, std::vector<double> *loss_out = nullptr);
+                   const std::vector<LossJob> *jobs = nullptr, std::vector<double> *loss_out = nullptr, double lambda = 0.0);
 
     // ---- Metric::train_loss / fold test losses for the chains' current beta.
     void losses(const std::vector<LossJob> &jobs, std::vector<double> &out);

@@ -306,19 +306,20 @@ __global__ void __launch_bounds__(256) finish_kernel(const Dev d, int mode, cons
         out = bq * bq;
     } else {
         const double beta = d.betaD[(size_t)c * d.pstride + j];
+        const double lam2 = 2.0 * d.lambda;  // L0L2 ridge term (Algorithm.h:1109, 1236/1246, 1341/1350, 1629-1630)
         if (EPI == EPI_SACR_LM) {
-            // Phi = sqrt(x_j.x_j / n) (utilities.cpp:142-151), invPhi = 1/Phi (:167-177); Algorithm.h:1116-1122
-            const double phi = sqrt(d.xtx[(size_t)c * d.pstride + j] / (double)d.ntrain[c]);
-            const double t = phi * beta + (1.0 / phi) * dsum;
+            // Phi = sqrt(2*lambda + x_j.x_j / n) (utilities.cpp:142-151), invPhi = 1/Phi (:167-177); Algorithm.h:1116-1122
+            const double phi = sqrt(lam2 + d.xtx[(size_t)c * d.pstride + j] / (double)d.ntrain[c]);
+            const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
             out = t * t;
         } else if (EPI == EPI_SACR_GLM) {
-            const double phi = sqrt(hsum);  // Algorithm.h:1238-1257 / 1342-1361
-            const double t = phi * beta + (1.0 / phi) * dsum;
+            const double phi = sqrt(hsum + lam2);  // Algorithm.h:1238-1257 / 1342-1361
+            const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
             out = t * t;
         } else {
-            // Algorithm.h:1626-1634: l1 = -dsum, l2 = hsum - R, d = -l1/l2, bd = |beta + d| * sqrt(l2)
-            const double l2 = hsum - R;
-            out = fabs(beta + dsum / l2) * sqrt(l2);
+            // Algorithm.h:1626-1634: l1 = -dsum + 2*lambda*beta, l2 = hsum - R + 2*lambda, d = -l1/l2, bd = |beta + d| * sqrt(l2)
+            const double l2 = hsum - R + lam2;
+            out = fabs(beta + (dsum - lam2 * beta) / l2) * sqrt(l2);
         }
     }
     d.bd[(size_t)c * d.pstride + j] = out;

@@ -31,6 +31,7 @@ struct Dev {
     int ldA;     // leading dim of gathered active columns: kcap + 2 rounded to even
     int max_iter;
     int warm;
+    double lambda;      // ridge level of the running batch (Algorithm::lambda_level; 0 for best-subset selection)
     // per-chain tables (index with chain id c)
     int *rows;          // [MAXC][n] train rows (ascending) of the chain's mask
     int *ntrain;        // [MAXC]

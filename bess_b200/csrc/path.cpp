@@ -35,7 +35,7 @@ struct Eval {
     int T = 0, l = 0;
     std::vector<int> A;
     std::vector<double> bA;
-    double coef0 = 0.0, train_loss = 0.0, ic = 0.0;
+    double coef0 = 0.0, train_loss = 0.0, ic = 0.0, lambda = 0.0;
 };
 
 struct Driver {
@@ -81,7 +81,7 @@ struct Driver {
     // fold fits of Metric::test_loss run in the same batch as the full fit (they never read its result; their
     // coef0_init is the one the path set BEFORE this step).
     // last_fold: also return the last fold's beta and ITS full-data loss (gs_path final sweep, path.cpp:314-319).
-    Eval step(int T, Eval *last_fold = nullptr)
+    Eval step(int T, Eval *last_fold = nullptr, double lambda = 0.0)
     {
         BatchResult br;
         std::vector<LossJob> jobs;
@@ -89,9 +89,10 @@ struct Driver {
         for (int k = 0; k < K; k++) jobs.push_back({1 + k, 1, k});
         if (last_fold && K > 0) jobs.push_back({K, 0, 0});
         std::vector<double> v;
-        eng.run_batch(T, all_chains, /*new_path_step=*/true, br, &jobs, &v);
+        eng.run_batch(T, all_chains, /*new_path_step=*/true, br, &jobs, &v, lambda);
         Eval e;
         e.T = T;
+        e.lambda = lambda;
         e.l = br.l[0];
         e.A = br.A[0];
         e.bA = br.bA[0];
@@ -149,15 +150,27 @@ struct Driver {
 
 void sequential_path(Driver &dr, BessResult &out, Eval &best)
 {
+    // path.cpp:48-74: for every sparsity level the lambda grid is walked zig-zag (:50), the warm start follows the walk.
     const BessArgs &a = dr.a;
-    std::vector<Eval> evs;
-    for (int s : a.sequence) evs.push_back(dr.step(s));
-    // ic_sequence.minCoeff: first minimum (path.cpp:113)
+    std::vector<double> lams = a.lambda_seq.empty() ? std::vector<double>{0.0} : a.lambda_seq;
+    const int S = (int)a.sequence.size(), L = (int)lams.size();
+    std::vector<Eval> evs((size_t)S * L);  // [lambda][s]
+    std::vector<int> order;
+    for (int i = 0; i < S; i++) {
+        for (int q = 0; q < L; q++) {
+            const int j = (i % 2 == 0) ? q : L - 1 - q;
+            evs[(size_t)j * S + i] = dr.step(a.sequence[(size_t)i], nullptr, lams[(size_t)j]);
+            order.push_back(j * S + i);
+        }
+    }
+    // ic_sequence.minCoeff (path.cpp:113): Eigen visits the column-major matrix ic(s, lambda) column by column, i.e.
+    // lambda outer / s inner, and keeps the first minimum
     size_t bi = 0;
     for (size_t i = 1; i < evs.size(); i++)
         if (evs[i].ic < evs[bi].ic) bi = i;
     best = evs[bi];
-    for (const Eval &e : evs) {
+    for (int idx : order) {  // trace in evaluation order
+        const Eval &e = evs[(size_t)idx];
         std::vector<double> b;
         double c0;
         dr.denormalise(e, b, c0);
@@ -168,6 +181,7 @@ void sequential_path(Driver &dr, BessResult &out, Eval &best)
         out.ic_all.push_back(e.ic);
         out.s_all.push_back(e.T);
         out.l_all.push_back(e.l);
+        out.lambda_all.push_back(e.lambda);
     }
 }
 
@@ -253,8 +267,11 @@ void bess_run(const BessArgs &a, BessResult &out)
     if (a.data_type < 1 || a.data_type > 3) throw EngineError{"data_type must be 1..3"};
     if (a.path_type != 1 && (a.algorithm_type == 5 || a.algorithm_type == 3))
         throw EngineError{"pgs_path (bsrr, algorithm_type 3/5 with path_type 2) is outside this build's scope"};
-    for (double l : a.lambda_seq)
-        if (l != 0.0) throw EngineError{"lambda != 0 (bsrr) is outside this build's scope"};
+    for (double l : a.lambda_seq) {
+        if (!(l >= 0.0)) throw EngineError{"lambda_seq entries must be >= 0"};
+        if (l != 0.0 && a.path_type != 1)
+            throw EngineError{"lambda != 0 is supported on the sequential path only (gs_path ignores lambda, path.cpp:134)"};
+    }
     if (!a.g_index.empty()) {
         if ((int)a.g_index.size() != a.p) throw EngineError{"group selection (gsize > 1) is outside this build's scope"};
         for (int j = 0; j < a.p; j++)
@@ -316,7 +333,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     out.coef0 = coef0;
     out.train_loss = best.train_loss;
     out.ic = best.ic;
-    out.lambda = 0.0;
+    out.lambda = best.lambda;
     out.chosen_s = best.T;
     // scatter to the ORIGINAL column numbering (un-screen: bess.cpp:186-209)
     out.beta.assign((size_t)p_all, 0.0);

@@ -62,6 +62,7 @@ struct BessResult {
     std::vector<std::vector<double>> bA_all;
     std::vector<double> coef0_all, train_loss_all, ic_all;
     std::vector<int> s_all, l_all;
+    std::vector<double> lambda_all;
     EngineStats stats;
     double prof_ms[PROF_NCAT] = {};
     long long prof_n[PROF_NCAT] = {};

@@ -76,6 +76,7 @@ typedef struct bess_b200_ext {
     int world, rank;
     long long col_lo, p_total;
     const void *nccl_unique_id; /* 128 bytes from bess_b200_nccl_unique_id() on rank 0, broadcast by the caller       */
+    double *chosen_lambda_out;  /* ridge level of the returned model (List key "lambda", path.cpp:129)                 */
 } bess_b200_ext;
 
 /* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's
@@ -96,6 +97,8 @@ int bess_b200_trace(int *s_all, int *l_all, double *coef0_all, double *train_los
                     int p);
 
 /* Metric.h:49-106 with the seed pinned: fold index of every row. */
+/* lambda of every evaluated (s, lambda) pair of the last call, in evaluation order (same order as bess_b200_trace). */
+int bess_b200_trace_lambda(double *lambda_all);
 int bess_b200_cv_fold_ids(int n, int K, unsigned seed, int *fold_of_row_out);
 
 /* ncclGetUniqueId through the library's run-time-loaded NCCL: call on rank 0, broadcast the 128 bytes to all ranks. */

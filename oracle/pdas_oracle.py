@@ -139,9 +139,9 @@ def loglik_poiss(x, y, coef, weights):
 # --------------------------------------------------------------------------------------
 # primary_model_fit x4: Algorithm.h:1131-1135, 1148-1204, 1273-1322, 1377-1490
 # --------------------------------------------------------------------------------------
-def fit_lm(XA, y, w, coef0):
-    """Algorithm.h:1131-1135.  coef0 untouched."""
-    G = XA.T @ XA
+def fit_lm(XA, y, w, coef0, lam=0.0):
+    """Algorithm.h:1131-1135.  coef0 untouched.  lam: X'X + lambda*I (:1134, not 2*lambda, not scaled by n)."""
+    G = XA.T @ XA + lam * np.eye(XA.shape[1])
     beta = np.linalg.solve(G, XA.T @ y)
     return beta, coef0
 
@@ -153,18 +153,20 @@ def _pi(X1, coef):
     return e / (1.0 + e)
 
 
-def fit_logistic(XA, y, w, coef0, floor_w=True):
+def fit_logistic(XA, y, w, coef0, floor_w=True, lam=0.0):
     """Algorithm.h:1148-1204 (floor_w=True) and logistic.cpp:61-157 ``logit_fit`` (floor_w=False).
     Starts from 0, returns the iterate *before* the last solve."""
     n, k = XA.shape
     X = np.hstack([np.ones((n, 1)), XA])
     beta0 = np.zeros(k + 1)
+    lmat = 2.0 * lam * np.eye(k + 1)  # 2*lambda*lambdamat, lambdamat(0,0) = 0 (:1158-1159, :1171)
+    lmat[0, 0] = 0.0
     Pi = _pi(X, beta0)
     ll0 = float((y * np.log(Pi) + (1 - y) * np.log(1 - Pi)) @ w)
     W = Pi * (1 - Pi)
     Z = X @ beta0 + (y - Pi) / W
     W = W * w
-    beta1 = np.linalg.solve((X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
+    beta1 = np.linalg.solve(lmat + (X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
     for _ in range(30):
         Pi = _pi(X, beta1)
         ll1 = float((y * np.log(Pi) + (1 - y) * np.log(1 - Pi)) @ w)
@@ -177,16 +179,18 @@ def fit_logistic(XA, y, w, coef0, floor_w=True):
             W = np.maximum(W, 0.001)
         Z = X @ beta0 + (y - Pi) / W
         W = W * w
-        beta1 = np.linalg.solve((X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
+        beta1 = np.linalg.solve(lmat + (X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
     return beta0[1:].copy(), float(beta0[0])
 
 
-def fit_poisson(XA, y, w, coef0):
+def fit_poisson(XA, y, w, coef0, lam=0.0):
     """Algorithm.h:1273-1322.  Intercept warm-started from coef0, slopes from 0."""
     n, k = XA.shape
     X = np.hstack([np.ones((n, 1)), XA])
     beta0 = np.zeros(k + 1)
     beta0[0] = coef0
+    lmat = 2.0 * lam * np.eye(k + 1)  # :1299
+    lmat[0, 0] = 0.0
     eta = X @ beta0
     expeta = np.exp(eta)
     ll0 = 1e5
@@ -194,7 +198,7 @@ def fit_poisson(XA, y, w, coef0):
         ww = expeta * w
         z = eta + (y - expeta) / expeta
         XtW = (X * ww[:, None]).T
-        beta0 = np.linalg.solve(XtW @ X, XtW @ z)
+        beta0 = np.linalg.solve(lmat + XtW @ X, XtW @ z)
         eta = _clip(X @ beta0, 30.0)
         expeta = np.maximum(np.exp(eta), 0.001)
         ll1 = float((y * eta - expeta) @ w)
@@ -204,7 +208,7 @@ def fit_poisson(XA, y, w, coef0):
     return beta0[1:].copy(), float(beta0[0])
 
 
-def fit_cox(XA, status, w, coef0, clamp=30.0):
+def fit_cox(XA, status, w, coef0, clamp=30.0, lam=0.0):
     """Algorithm.h:1377-1490 (clamp 30) and coxph.cpp:42-109 ``cox_fit`` (clamp 50).
     theta has NO weights here; first Newton step is always d/32 (ll0 starts at 1e5)."""
     n, k = XA.shape
@@ -215,12 +219,13 @@ def fit_cox(XA, status, w, coef0, clamp=30.0):
         theta = np.exp(_clip(XA @ beta0, clamp))
         cum = np.cumsum(theta[::-1])[::-1]
         xt = np.cumsum((XA * theta[:, None])[::-1], axis=0)[::-1] / cum[:, None]
-        g = (XA - xt).T @ ws
+        g = (XA - xt).T @ ws + 2.0 * lam * beta0  # :1429
         h = np.empty((k, k))
         for a in range(k):
             for b in range(a, k):
                 s = np.cumsum((theta * XA[:, a] * XA[:, b])[::-1])[::-1]
                 h[a, b] = h[b, a] = -float((s / cum - xt[:, a] * xt[:, b]) @ ws)
+        h = h + 2.0 * lam * np.eye(k)  # :1472 (added to the NEGATIVE-definite h, as the reference does)
         d = np.linalg.solve(h, g)
         m = 1
         beta1 = beta0 - 0.5 ** m * d
@@ -239,35 +244,35 @@ def fit_cox(XA, status, w, coef0, clamp=30.0):
 # --------------------------------------------------------------------------------------
 # get_A x4 (sacrifices): Algorithm.h:1097-1129, 1206-1263, 1324-1367, 1569-1640
 # --------------------------------------------------------------------------------------
-def sacrifice_lm(X, y, w, beta, coef0, xtx):
+def sacrifice_lm(X, y, w, beta, coef0, xtx, lam=0.0):
     n = X.shape[0]
-    d = X.T @ (y - X @ beta - coef0) / float(n)  # :1109
-    phi = np.sqrt(xtx / float(n))  # utilities.cpp:142-151 (1x1 sqrt)
+    d = X.T @ (y - X @ beta - coef0) / float(n) - 2.0 * lam * beta  # :1109
+    phi = np.sqrt(2.0 * lam + xtx / float(n))  # utilities.cpp:142-151 (1x1 sqrt)
     inv = 1.0 / phi  # utilities.cpp:167-177 (1x1 ldlt inverse)
     return (phi * beta + inv * d) ** 2  # :1116-1122
 
 
-def sacrifice_logistic(X, y, w, beta, coef0, xtx=None):
+def sacrifice_logistic(X, y, w, beta, coef0, xtx=None, lam=0.0):
     eta = _clip(X @ beta + coef0, 30.0)  # :1223-1231
     e = np.exp(eta)
     pr = e / (e + 1.0)
     g = w * (y - pr)
     h = w * pr * (1 - pr)
-    d = X.T @ g  # :1236
-    phi = np.sqrt((X * X).T @ h)  # :1238-1250
+    d = X.T @ g - 2.0 * lam * beta  # :1236
+    phi = np.sqrt((X * X).T @ h + 2.0 * lam)  # :1238-1250
     return (phi * beta + d / phi) ** 2
 
 
-def sacrifice_poisson(X, y, w, beta, coef0, xtx=None):
+def sacrifice_poisson(X, y, w, beta, coef0, xtx=None, lam=0.0):
     eta = X @ beta + coef0  # :1338 (NOT clamped)
     e = np.exp(eta)
     g = (y - e) * w
-    d = X.T @ g
-    phi = np.sqrt((X * X).T @ (e * w))  # :1342-1350
+    d = X.T @ g - 2.0 * lam * beta  # :1341
+    phi = np.sqrt((X * X).T @ (e * w) + 2.0 * lam)  # :1342-1350
     return (phi * beta + d / phi) ** 2
 
 
-def sacrifice_cox(X, y, w, beta, coef0=0.0, xtx=None):
+def sacrifice_cox(X, y, w, beta, coef0=0.0, xtx=None, lam=0.0):
     """Algorithm.h:1569-1640 (algorithm_type 1 branch).  y is the 0/1 status, rows time-sorted."""
     theta = w * np.exp(_clip(X @ beta, 30.0))  # :1579-1587
     cum = np.cumsum(theta[::-1])[::-1]
@@ -276,8 +281,8 @@ def sacrifice_cox(X, y, w, beta, coef0=0.0, xtx=None):
     x2th = x2th - xth ** 2
     xth = X - xth
     ev = (y != 0.0)  # :1618-1625 rows with status 0 are zeroed
-    l1 = -(xth[ev].T @ w[ev])
-    l2 = x2th[ev].T @ w[ev]
+    l1 = -(xth[ev].T @ w[ev]) + 2.0 * lam * beta  # :1629
+    l2 = x2th[ev].T @ w[ev] + 2.0 * lam  # :1630
     d = -l1 / l2
     return np.abs(beta + d) * np.sqrt(l2)  # :1631-1634 (not squared)
 
@@ -299,7 +304,8 @@ class FitResult:
     min_gap: float = np.inf
 
 
-def pdas_fit(data: Data, model_type, T0, beta_init, coef0_init, train_mask, xtx, max_iter=20, always_select=()):
+def pdas_fit(data: Data, model_type, T0, beta_init, coef0_init, train_mask, xtx, max_iter=20, always_select=(),
+             lam=0.0):
     X = data.x[train_mask] if len(train_mask) != data.n else data.x
     y = data.y[train_mask] if len(train_mask) != data.n else data.y
     w = data.weight[train_mask] if len(train_mask) != data.n else data.weight
@@ -309,12 +315,12 @@ def pdas_fit(data: Data, model_type, T0, beta_init, coef0_init, train_mask, xtx,
     seen = [np.zeros(T0, dtype=np.int32)]  # A_list.col(0) = 0  (:142-143)
     res = FitResult(beta, coef0, 0, seen[0])
     for l in range(1, max_iter + 1):
-        bd = _SACRIFICE[model_type](X, y, w, beta, coef0, xtx)
+        bd = _SACRIFICE[model_type](X, y, w, beta, coef0, xtx, lam=lam)
         if len(always_select):
             bd[np.asarray(always_select)] = DBL_MAX  # slice_assignment, utilities.cpp:190-199
         res.min_gap = min(res.min_gap, boundary_gap(bd, T0))
         A = max_k(bd, T0)
-        beta_A, coef0 = _FIT[model_type](X[:, A], y, w, coef0)  # beta_A reset to 0 before the fit (:157)
+        beta_A, coef0 = _FIT[model_type](X[:, A], y, w, coef0, lam=lam)  # beta_A reset to 0 before the fit (:157)
         beta = np.zeros(p)
         beta[A] = beta_A
         res.A_hist.append(A)
@@ -378,6 +384,7 @@ class PathState:
         self.full_mask = np.arange(n)
         self.xtx_full = (data.x * data.x).sum(axis=0) if model_type == 1 else None  # utilities.cpp:153-165
         self.alg_coef0_init = 0.0
+        self.lam = 0.0  # Algorithm::lambda_level
         self.alg_beta = np.zeros(p)
         self.alg_coef0 = 0.0
         self.T = 0
@@ -393,7 +400,8 @@ class PathState:
                               if model_type == 1 else [None] * K)  # Metric.h:108-129
 
     def _fit(self, T, beta_init, coef0_init, mask, xtx):
-        r = pdas_fit(self.data, self.model_type, T, beta_init, coef0_init, mask, xtx, self.max_iter, self.always)
+        r = pdas_fit(self.data, self.model_type, T, beta_init, coef0_init, mask, xtx, self.max_iter, self.always,
+                     lam=self.lam)
         self.n_fits += 1
         self.n_iters += min(r.l, self.max_iter)
         self.min_gap = min(self.min_gap, r.min_gap)
@@ -444,25 +452,37 @@ def _denormalise(data: Data, beta, coef0, gs):
     return beta, coef0
 
 
-def sequential_path(st: PathState, sequence):
-    """path.cpp:25-132 (lambda_seq = [0])."""
+def sequential_path(st: PathState, sequence, lambda_seq=(0.0,)):
+    """path.cpp:25-132: for every sparsity level the lambda grid is walked zig-zag (:50), warm starts follow the walk,
+    the criterion matrix ic[s][lambda] is minimised with Eigen's minCoeff (column-major visit: lambda outer, s inner)."""
     p = st.data.p
+    S, L = len(sequence), len(lambda_seq)
     beta_init, coef0_init = np.zeros(p), 0.0
-    betas, coef0s, losses, ics, ls = [], [], [], [], []
-    for s in sequence:
-        r = st.full_fit(int(s), beta_init, coef0_init)
-        if st.warm:
-            beta_init, coef0_init = r.beta.copy(), r.coef0
-        betas.append(r.beta.copy())
-        coef0s.append(r.coef0)
-        ls.append(r.l)
-        losses.append(st.train_loss())
-        ics.append(st.ic())
-    best = int(np.argmin(np.array(ics)))  # first minimum, path.cpp:113
-    beta, coef0 = _denormalise(st.data, betas[best], coef0s[best], gs=False)
-    return dict(beta=beta, coef0=coef0, train_loss=losses[best], ic=ics[best], best=best, s=int(sequence[best]),
-                beta_all=np.array(betas), coef0_all=np.array(coef0s), loss_all=np.array(losses),
-                ic_all=np.array(ics), l_all=np.array(ls))
+    betas = np.zeros((L, S, p))
+    coef0s, losses, ics = np.zeros((L, S)), np.zeros((L, S)), np.zeros((L, S))
+    ls = np.zeros((L, S), dtype=np.int64)
+    for i, s in enumerate(sequence):
+        js = range(L) if i % 2 == 0 else range(L - 1, -1, -1)
+        for j in js:
+            st.lam = float(lambda_seq[j])
+            r = st.full_fit(int(s), beta_init, coef0_init)
+            if st.warm:
+                beta_init, coef0_init = r.beta.copy(), r.coef0
+            betas[j, i] = r.beta
+            coef0s[j, i] = r.coef0
+            ls[j, i] = r.l
+            losses[j, i] = st.train_loss()
+            ics[j, i] = st.ic()
+    flat = int(np.argmin(ics.reshape(-1)))  # [lambda][s] row-major == Eigen column-major visit of ic(s, lambda)
+    bj, bi = divmod(flat, S)
+    beta, coef0 = _denormalise(st.data, betas[bj, bi], coef0s[bj, bi], gs=False)
+    out = dict(beta=beta, coef0=coef0, train_loss=float(losses[bj, bi]), ic=float(ics[bj, bi]), best=bi,
+               s=int(sequence[bi]), lam=float(lambda_seq[bj]))
+    if L == 1:
+        out.update(beta_all=betas[0], coef0_all=coef0s[0], loss_all=losses[0], ic_all=ics[0], l_all=ls[0])
+    else:
+        out.update(beta_all=betas, coef0_all=coef0s, loss_all=losses, ic_all=ics, l_all=ls)
+    return out
 
 
 def gs_path(st: PathState, s_min, s_max):
@@ -579,7 +599,8 @@ def screening(x, y, w, model_type, screening_size, always_select=()):
 # bessCpp: bess.cpp:37-214
 # --------------------------------------------------------------------------------------
 def bess_cpp(x, y, data_type, weight, is_normal, model_type, max_iter, path_type, is_warm_start, ic_type, is_cv, K,
-             sequence, s_min, s_max, is_screening, screening_size, always_select=(), fold_of_row=None):
+             sequence, s_min, s_max, is_screening, screening_size, always_select=(), fold_of_row=None,
+             lambda_seq=(0.0,)):
     x = np.asarray(x, dtype=np.float64)
     p0 = x.shape[1]
     always = np.asarray(always_select, dtype=np.int64)
@@ -590,7 +611,7 @@ def bess_cpp(x, y, data_type, weight, is_normal, model_type, max_iter, path_type
         always = np.searchsorted(scr, always) if len(always) else always  # screening.cpp:91-102
     data = make_data(x, y, weight, data_type, is_normal, model_type)
     st = PathState(data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, is_warm_start, always)
-    out = sequential_path(st, sequence) if path_type == 1 else gs_path(st, s_min, s_max)
+    out = sequential_path(st, sequence, lambda_seq) if path_type == 1 else gs_path(st, s_min, s_max)
     if is_screening:
         b = np.zeros(p0)
         b[scr] = out["beta"]

@@ -44,7 +44,7 @@ def cv_fold_ids(n: int, K: int, seed: int = 123) -> np.ndarray:
 
 def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
                 is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size,
-                always_select=(), cv_seed=123):
+                always_select=(), cv_seed=123, lambda_seq=(0.0,)):
     """Calls the reference's pywrap_bess (bess.cpp:218).  Returns dict(beta, coef0, train_loss, ic)."""
     os.environ["BESS_CV_SEED"] = str(cv_seed)
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -54,7 +54,7 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
     g = np.arange(p, dtype=np.int32)
     state = np.zeros(1)
     seq = np.ascontiguousarray(sequence, dtype=np.int32)
-    lam = np.zeros(1)
+    lam = np.ascontiguousarray(lambda_seq, dtype=np.float64)
     alw = np.ascontiguousarray(always_select, dtype=np.int32)
     beta = np.zeros(p)
     s1 = [np.zeros(1) for _ in range(7)]
@@ -66,8 +66,8 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
     lib().ref_pywrap_bess(
         _d(x), i(n), i(p), _d(y), i(n), i(data_type), _d(w), i(n), b(is_normal), i(algorithm_type), i(model_type),
         i(max_iter), i(exchange_num), i(path_type), b(is_warm_start), i(ic_type), b(is_cv), i(K), _i(g), i(p),
-        _d(state), i(1), _i(seq), i(len(seq)), _d(lam), i(1), i(s_min), i(s_max), i(10), dbl(10.0), dbl(0.0), dbl(0.0),
-        i(1), b(is_screening), i(screening_size), i(1), _i(alw), i(len(alw)), dbl(1.1),
+        _d(state), i(1), _i(seq), i(len(seq)), _d(lam), i(len(lam)), i(s_min), i(s_max), i(10), dbl(10.0), dbl(0.0), dbl(0.0),
+        i(len(lam)), b(is_screening), i(screening_size), i(1), _i(alw), i(len(alw)), dbl(1.1),
         _d(beta), i(p), _d(s1[0]), i(1), _d(s1[1]), i(1), _d(s1[2]), i(1), _d(s1[3]), _d(s1[4]), i(1), _d(s1[5]), i(1),
         _d(s1[6]), i(1), _i(A_out), i(p), _i(l_out))
     return dict(beta=beta, coef0=float(s1[0][0]), train_loss=float(s1[1][0]), ic=float(s1[2][0]))

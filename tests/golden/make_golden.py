@@ -33,10 +33,22 @@ CASES = [
     ("poisson_seq_screen", "poisson", 150, 300, 3, 1, False, 5, 3, 6, 50, False, 33),
     ("cox_seq_screen", "cox", 120, 300, 3, 1, False, 5, 3, 6, 50, False, 43),
 ]
+# L0L2 ("bsrr", Algorithm::lambda_level) on the sequential path: lambda grid walked zig-zag per level (path.cpp:50)
+LAMBDA_CASES = {
+    "lm_seq_l0l2": ("gaussian", 150, 300, 5, 1, False, 5, 3, 8, 0, False, 51, [0.0, 0.05, 0.5]),
+    "lm_seq_l0l2_cv": ("gaussian", 150, 300, 5, 1, True, 3, 1, 6, 0, True, 52, [0.3, 0.01]),
+    "logit_seq_l0l2_cv": ("binomial", 200, 250, 4, 1, True, 3, 1, 5, 0, False, 53, [0.02, 0.2]),
+    "poisson_seq_l0l2": ("poisson", 200, 250, 4, 1, False, 5, 3, 6, 0, False, 54, [0.01, 0.1]),
+    "cox_seq_l0l2": ("cox", 160, 200, 4, 1, False, 5, 3, 6, 0, False, 55, [0.0, 0.01, 0.05]),
+}
 
 
 def main():
-    for (name, fam, n, p, k, path_type, is_cv, K, ic_type, smax, scr, weighted, seed) in CASES:
+    only = set(sys.argv[1:])
+    cases = [c + ([0.0],) for c in CASES] + [(nm,) + v for nm, v in LAMBDA_CASES.items()]
+    for (name, fam, n, p, k, path_type, is_cv, K, ic_type, smax, scr, weighted, seed, lams) in cases:
+        if only and name not in only:
+            continue
         model_type, data_type = FAM[fam]
         d = gen_data(n, p, fam, k, seed=seed)
         rng = np.random.Generator(np.random.PCG64(1000 + seed))
@@ -44,13 +56,15 @@ def main():
         seq = np.arange(1, smax + 1, dtype=np.int32)
         fold = ref.cv_fold_ids(n, K) if is_cv else np.zeros(n, dtype=np.int32)
         r = ref.pywrap_bess(d.x, d.y, data_type, w, True, 1, model_type, 20, 2, path_type, True, ic_type, is_cv, K,
-                            seq, 1, smax, scr > 0, scr if scr > 0 else 1)
+                            seq, 1, smax, scr > 0, scr if scr > 0 else 1, lambda_seq=lams)
         out = dict(x=d.x, y=d.y, weight=w, fold_of_row=fold, beta=r["beta"], coef0=r["coef0"],
                    train_loss=r["train_loss"], ic=r["ic"],
                    meta=np.array([model_type, data_type, path_type, int(is_cv), K, ic_type, smax, scr], dtype=np.int64))
+        if len(lams) > 1 or lams[0] != 0.0:
+            out["lambda_seq"] = np.asarray(lams, dtype=np.float64)
         if scr > 0:
             out["screening_A"] = ref.screening(d.x, d.y, w, model_type, scr)
-        elif path_type == 1:
+        elif path_type == 1 and "lambda_seq" not in out:
             t = ref.seq_trace(d.x, d.y, w, data_type, True, model_type, 20, True, ic_type, is_cv, K, seq)
             out.update({k2: v for k2, v in t.items()})
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)

@@ -17,6 +17,7 @@ def load_golden(name):
     m = g["meta"]
     g["model_type"], g["data_type"], g["path_type"], g["is_cv"], g["K"], g["ic_type"], g["smax"], g["scr"] = (
         int(m[0]), int(m[1]), int(m[2]), bool(m[3]), int(m[4]), int(m[5]), int(m[6]), int(m[7]))
+    g["lambda_seq"] = g.get("lambda_seq", np.zeros(1))
     return g
 
 

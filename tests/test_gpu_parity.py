@@ -42,7 +42,7 @@ def test_golden_end_to_end(name):
     seq = np.arange(1, g["smax"] + 1)
     out = cbess.fit(g["x"], g["y"], g["data_type"], g["weight"], True, 1, g["model_type"], 20, 2, g["path_type"], True,
                     g["ic_type"], g["is_cv"], g["K"], seq, 1, g["smax"], g["scr"] > 0, max(g["scr"], 1),
-                    fold_of_row=g["fold_of_row"] if g["is_cv"] else None)
+                    fold_of_row=g["fold_of_row"] if g["is_cv"] else None, lambda_seq=g["lambda_seq"])
     _check_final(out, g)
     assert out["stats"]["n_boundary_ties"] == 0
     if "screening_A" in g:
@@ -180,6 +180,35 @@ def test_path_parity_with_oracle(fam, path_type, is_cv):
     assert out["s"] == exp["s"]
     assert out["stats"]["n_fits"] == exp["n_fits"]
     assert out["stats"]["n_pdas_iters"] == exp["n_iters"]
+
+
+@pytest.mark.parametrize("fam,is_cv", [("gaussian", True), ("binomial", False), ("poisson", True), ("cox", False)])
+def test_l0l2_lambda_grid_parity_with_oracle(fam, is_cv):
+    """L0L2 ("bsrr") on the sequential path: the lambda grid is walked zig-zag per sparsity level with warm starts
+    following the walk (path.cpp:48-74); chosen (s, lambda), supports and the criterion of EVERY evaluation must match."""
+    from bess_b200 import cbess
+    from bess_b200.gen_data import gen_data
+    model_type, data_type = FAM[fam]
+    n, p, k, K, smax = 300, 900, 5, 3, 7
+    lams = [0.0, 0.01, 0.1, 0.6]
+    d = gen_data(n, p, fam, k, seed=61)
+    w = np.random.default_rng(61).uniform(0.5, 1.5, n)
+    fold = cbess.cv_fold_ids(n, K, 9)
+    seq = np.arange(1, smax + 1)
+    exp = orc.bess_cpp(d.x, d.y, data_type, w, True, model_type, 20, 1, True, 2, is_cv, K, seq, 1, smax, False, 1,
+                       fold_of_row=fold, lambda_seq=lams)
+    out = cbess.fit(d.x, d.y, data_type, w, True, 5, model_type, 20, 2, 1, True, 2, is_cv, K, seq, 1, smax, False, 1,
+                    fold_of_row=fold, lambda_seq=lams)
+    _check_final(out, exp)
+    assert out["s"] == exp["s"] and out["lam"] == exp["lam"]
+    # evaluation order: level i walks the grid forwards when i is even, backwards when odd
+    order = [(j if i % 2 == 0 else len(lams) - 1 - j, i) for i in range(smax) for j in range(len(lams))]
+    assert out["lambda_all"].tolist() == [lams[j] for j, _ in order]
+    assert out["s_all"].tolist() == [int(seq[i]) for _, i in order]
+    assert rel_err(out["ic_all"], np.array([exp["ic_all"][j, i] for j, i in order])) < RTOL
+    assert rel_err(out["loss_all"], np.array([exp["loss_all"][j, i] for j, i in order])) < RTOL
+    assert out["l_all"].tolist() == [int(exp["l_all"][j, i]) for j, i in order]
+    assert out["stats"]["n_boundary_ties"] == 0
 
 
 @pytest.mark.parametrize("variant", ["no_normal", "cold_start", "always", "max_iter1", "k_equals_p", "weights_gs"])

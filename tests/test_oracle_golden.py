@@ -12,7 +12,7 @@ def test_oracle_matches_reference_golden(name):
     seq = np.arange(1, g["smax"] + 1)
     out = orc.bess_cpp(g["x"], g["y"], g["data_type"], g["weight"], True, g["model_type"], 20, g["path_type"], True,
                        g["ic_type"], g["is_cv"], g["K"], seq, 1, g["smax"], g["scr"] > 0, max(g["scr"], 1),
-                       fold_of_row=g["fold_of_row"])
+                       fold_of_row=g["fold_of_row"], lambda_seq=g["lambda_seq"])
     assert_same_support(out["beta"], g["beta"])
     assert rel_err(out["beta"], g["beta"]) < RTOL
     assert abs(out["coef0"] - g["coef0"]) <= RTOL * max(1.0, abs(g["coef0"]))
