@@ -257,10 +257,15 @@ def run_ours(args):
         eng.run_batch(5, list(range(NFOLDS + 1)), True)
         pms, pbytes = eng.time_dual_sweep(20)
         eng.close()
-        probe = {"what": "dual_sweep_kernel<FT=12,MODE_D>: X^T r for 11 chains (full fit + 10 folds) in ONE pass over the "
+        probe = {"what": "dual_sweep_tma_kernel<FT=12,MODE_D> (bulk-TMA pipeline): X^T r for 11 chains (full fit + 10 folds) in ONE pass over the "
                          "normalised 1000 x 500000 design (config 5 without screening)",
                  "ms_per_launch": pms, "achieved": pbytes / (pms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                  "frac": pbytes / (pms * 1e-3) / 1e9 / peak, "algorithmic_bytes": pbytes}
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["tma_sweep_F12_4GB"]
+            probe["traffic"], probe["traffic_source"] = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        except Exception:
+            pass
 
     # ---- C5b: config 5 WITHOUT screening -- every PDAS dual sweep is p=500k-sized; at N > 1 each iteration is sharded by
     # columns (local sweep + local top-k, NCCL all-gather of candidates, all-reduce of the k active columns).  This is the

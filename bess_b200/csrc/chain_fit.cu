@@ -578,28 +578,20 @@ __device__ void chol_packed_smem(const double *Sg, int lds, int mm, double *x, c
     for (int j0 = jlast; j0 >= 0; j0 -= NB) {
         const int nb = min(NB, mm - j0);
         const int t0 = j0 + nb;
-        double acc[NB];
-#pragma unroll
-        for (int q = 0; q < NB; q++) acc[q] = 0.0;
-        for (int i = t0 + tid; i < mm; i += FIT_NT) {
-            const double xi = x[i];
-            const double *Li = Lp + tri(i) + j0;
-#pragma unroll
-            for (int q = 0; q < NB; q++)
-                if (q < nb) acc[q] = fma(Li[q], xi, acc[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < NB; q++) acc[q] = warp_sum(acc[q]);
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < NB; q++) red[wid * NB + q] = acc[q];
+        // v[q] = sum_{i in [t0, mm)} L[i][j0+q] x[i]: thread (q = tid & 15, g = tid >> 4) sums the rows i == g (mod 32)
+        {
+            const int q = tid & (NB - 1), g = tid >> 4;
+            double acc = 0.0;
+            if (q < nb)
+                for (int i = t0 + g; i < mm; i += FIT_NT / NB) acc = fma(Lp[tri(i) + j0 + q], x[i], acc);
+            red[g * NB + q] = acc;
         }
         __syncthreads();
         if (wid == 0) {
             double t = 0.0;
             if (lane < nb) {
                 double vsum = 0.0;
-                for (int w2 = 0; w2 < FIT_NT / 32; w2++) vsum += red[w2 * NB + lane];
+                for (int g2 = 0; g2 < FIT_NT / NB; g2++) vsum += red[g2 * NB + lane];
                 t = x[j0 + lane] - vsum;
             }
             for (int q = nb - 1; q >= 0; q--) {
@@ -720,23 +712,14 @@ __device__ __noinline__ void chol_blocked_cluster(double *S, int lds, int mm, do
     for (int j0 = jlast; j0 >= 0; j0 -= NB) {
         const int nb = min(NB, mm - j0);
         const int t0 = j0 + nb;
-        // v[q] = sum_{i in [t0, mm)} L[i][j0+q] * x[i]
-        double acc[NB];
-#pragma unroll
-        for (int q = 0; q < NB; q++) acc[q] = 0.0;
-        for (int i = t0 + tid; i < mm; i += FIT_NT) {
-            const double xi = x[i];
-            const double *Li = S + (size_t)i * lds + j0;
-#pragma unroll
-            for (int q = 0; q < NB; q++)
-                if (q < nb) acc[q] = fma(Li[q], xi, acc[q]);
-        }
-#pragma unroll
-        for (int q = 0; q < NB; q++) acc[q] = warp_sum(acc[q]);
+        // v[q] = sum_{i in [t0, mm)} L[i][j0+q] x[i]: thread (q = tid & 15, g = tid >> 4) sums the rows i == g (mod 32)
         __syncthreads();
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < NB; q++) sm.scratch[wid * NB + q] = acc[q];
+        {
+            const int q = tid & (NB - 1), g = tid >> 4;
+            double acc = 0.0;
+            if (q < nb)
+                for (int i = t0 + g; i < mm; i += FIT_NT / NB) acc = fma(S[(size_t)i * lds + j0 + q], x[i], acc);
+            sm.scratch[g * NB + q] = acc;
         }
         // diagonal block to smem
         for (int e = tid; e < nb * nb; e += FIT_NT) {
@@ -748,7 +731,7 @@ __device__ __noinline__ void chol_blocked_cluster(double *S, int lds, int mm, do
             double t = 0.0;
             if (lane < nb) {
                 double vsum = 0.0;
-                for (int w2 = 0; w2 < FIT_NT / 32; w2++) vsum += sm.scratch[w2 * NB + lane];
+                for (int g2 = 0; g2 < FIT_NT / NB; g2++) vsum += sm.scratch[g2 * NB + lane];
                 t = x[j0 + lane] - vsum;
             }
             for (int q = nb - 1; q >= 0; q--) {

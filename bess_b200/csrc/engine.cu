@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -905,6 +906,11 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
     // PDAS iterations are enqueued speculatively: the kernels of an iteration return at once when every chain of the
     // batch has already met the stopping rule (Dev::gate), so the host only synchronises once per group.  PDAS needs
     // 2-4 iterations per warm-started fit; the first group covers that, later groups are shorter.
+    static const bool fuse_topk = [] {
+        const char *e = std::getenv("BESS_B200_FUSE_TOPK");
+        return !(e && e[0] == '0');
+    }();
+    const bool fused_mode = fuse_topk && !sharded_ && d.p <= TOPK_LMAX;
     d.gate = d.n_active;
     int enq = 0;
     bool all = false;
@@ -914,13 +920,18 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
             sp = m.span_begin(1);
             launch_dual_sweep(d, mode, m.st);
             m.span_end(sp);
-            sp = m.span_begin(2);
-            launch_finish(d, mode, epi, b, nullptr, m.st);
-            m.span_end(sp);
-            if (m.n_always)
-                launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
+            const bool fused = fuse_topk && !sharded_ && d.p <= TOPK_LMAX;
+            if (!fused) {
+                sp = m.span_begin(2);
+                launch_finish(d, mode, epi, b, nullptr, m.st);
+                m.span_end(sp);
+                if (m.n_always)
+                    launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
+            }
             sp = m.span_begin(3);
-            if (!sharded_) {
+            if (fused) {
+                launch_topk_fused(d, mode, epi, cmin, cmax - cmin + 1, T, m.always, m.n_always, m.st);
+            } else if (!sharded_) {
                 launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1,
                             d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride,
                             m.st, d.gate);
@@ -987,7 +998,7 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         stats_.n_boundary_ties += m.h_tie[c];
         executed = std::max(executed, iters);
     }
-    launches += (long long)executed * (4 + (m.n_always ? 1 : 0) + (sharded_ ? 4 : 0)) + (jobs ? 1 : 0);
+    launches += (long long)executed * (fused_mode ? 3 : 4 + (m.n_always ? 1 : 0) + (sharded_ ? 4 : 0)) + (jobs ? 1 : 0);
     stats_.n_sweeps += executed;
     stats_.sweep_bytes += executed * (8.0 * d.n * d.p + vec_bytes);
     stats_.kernel_launches += launches;  // launches that did work; gated no-op launches are not counted

@@ -268,13 +268,11 @@ void launch_dual_sweep(const Dev &d, int mode, cudaStream_t st)
 // =====================================================================================================
 // finish: reduce row-split partials, apply the sacrifice
 // =====================================================================================================
+// value of the finish epilogue EPI for chain c, column j: reduces the row-split partials in a fixed order and applies the
+// sacrifice / screening formula.  EPI_RAW writes the reduced sums to raw_out and returns 0.
 template <int EPI>
-__global__ void __launch_bounds__(256) finish_kernel(const Dev d, int mode, const BatchDesc b, double *raw_out)
+__device__ __forceinline__ double finish_value(const Dev &d, int mode, int c, long long j, double *raw_out)
 {
-    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (j >= d.p) return;
-    if (d.gate && *d.gate == 0) return;
-    const int c = b.chain[blockIdx.y];  // chain id == slot in the sweep vectors
     const int NQ = mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 5);
     const int FT = d.FS;
     double dsum = 0.0, hsum = 0.0, R = 0.0;
@@ -298,7 +296,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const Dev d, int mode, cons
     if (EPI == EPI_RAW) {
         raw_out[(size_t)(0 * FT + c) * d.pstride + j] = dsum;
         if (mode >= MODE_DH) raw_out[(size_t)(1 * FT + c) * d.pstride + j] = hsum;
-        return;
+        return 0.0;
     }
     double out;
     if (EPI == EPI_SCREEN_LM) {
@@ -322,7 +320,18 @@ __global__ void __launch_bounds__(256) finish_kernel(const Dev d, int mode, cons
             out = fabs(beta + (dsum - lam2 * beta) / l2) * sqrt(l2);
         }
     }
-    d.bd[(size_t)c * d.pstride + j] = out;
+    return out;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256) finish_kernel(const Dev d, int mode, const BatchDesc b, double *raw_out)
+{
+    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (j >= d.p) return;
+    if (d.gate && *d.gate == 0) return;
+    const int c = b.chain[blockIdx.y];  // chain id == slot in the sweep vectors
+    const double out = finish_value<EPI>(d, mode, c, j, raw_out);
+    if (EPI != EPI_RAW) d.bd[(size_t)c * d.pstride + j] = out;
 }
 
 void launch_finish(const Dev &d, int mode, int epi, const BatchDesc &b, double *raw_out, cudaStream_t st)
@@ -360,36 +369,26 @@ void launch_pin(const Dev &d, double *vals, long long stride, int nch, const int
 // One CTA selects the top min(k, len) keys of its slice and writes them IN INPUT ORDER (so candidate lists stay
 // index-ascending through every stage and the final list needs no sort).  Total order: larger key first, then
 // lower index first.  grid = (nslices, nchains).
-__global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__restrict__ keys_in,
-                                                              const int *__restrict__ idx_in, long long in_stride,
-                                                              int n_in, int k, int slice_len, double *keys_out,
-                                                              int *idx_out, long long out_stride, int *final_out,
-                                                              int final_ld, int *tie, const int *gate)
+__device__ __forceinline__ unsigned long long topk_key(double v)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
-    if (gate && *gate == 0) return;
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    if (!(v == v) || v < 0.0) u = 0ull;  // NaN / negative never happen for a sacrifice; rank them last
+    return u;
+}
+
+// Select + ordered compaction over `len` keys already in shared memory (block-synchronised by the caller's first barrier
+// inside).  Outputs as in topk_slices_kernel.
+__device__ __forceinline__ void topk_body(unsigned long long *keys, int len, int k, int slice_len, const int *iin, int b0, int s,
+                                          int f, double *keys_out, int *idx_out, long long out_stride, int *final_out,
+                                          int final_ld, int *tie)
+{
     __shared__ int hist[256];
     __shared__ unsigned long long sh_prefix;
     __shared__ int sh_krem, sh_neq;
     __shared__ unsigned long long scan_sh[34];
-
     const int tid = threadIdx.x;
-    const int s = blockIdx.x, f = blockIdx.y;
-    const int b0 = s * slice_len;
-    const int len = min(slice_len, n_in - b0);
-    if (len <= 0) return;
     const int kk = min(k, len);
-    const double *kin = keys_in + (size_t)f * in_stride + b0;
-    const int *iin = idx_in ? idx_in + (size_t)f * in_stride + b0 : nullptr;
     const int out_per_slice = min(k, slice_len);
-
-    for (int i = tid; i < len; i += TOPK_NT) {
-        const double v = kin[i];
-        unsigned long long u = (unsigned long long)__double_as_longlong(v);
-        if (!(v == v) || v < 0.0) u = 0ull;  // NaN / negative never happen for a sacrifice; rank them last
-        keys[i] = u;
-    }
     unsigned long long thr = 0ull;
     int krem = kk, neq = len;
     if (kk < len) {
@@ -512,6 +511,72 @@ __global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__re
         }
     }
     if (final_out && tie && tid == 0) tie[f] = (kk < len && neq > krem) ? 1 : 0;
+}
+
+
+// One CTA selects the top min(k, len) keys of its slice and writes them IN INPUT ORDER (so candidate lists stay
+// index-ascending through every stage and the final list needs no sort).  Total order: larger key first, then
+// lower index first.  grid = (nslices, nchains).
+__global__ void __launch_bounds__(TOPK_NT) topk_slices_kernel(const double *__restrict__ keys_in,
+                                                              const int *__restrict__ idx_in, long long in_stride,
+                                                              int n_in, int k, int slice_len, double *keys_out,
+                                                              int *idx_out, long long out_stride, int *final_out,
+                                                              int final_ld, int *tie, const int *gate)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    if (gate && *gate == 0) return;
+    const int tid = threadIdx.x;
+    const int s = blockIdx.x, f = blockIdx.y;
+    const int b0 = s * slice_len;
+    const int len = min(slice_len, n_in - b0);
+    if (len <= 0) return;
+    const double *kin = keys_in + (size_t)f * in_stride + b0;
+    const int *iin = idx_in ? idx_in + (size_t)f * in_stride + b0 : nullptr;
+    for (int i = tid; i < len; i += TOPK_NT) keys[i] = topk_key(kin[i]);
+    topk_body(keys, len, k, slice_len, iin, b0, s, f, keys_out, idx_out, out_stride, final_out, final_ld, tie);
+}
+
+// Fused finish + pin + top-k for designs of at most TOPK_LMAX columns: the CTA of chain c reduces the sweep partials and
+// applies the sacrifice itself (finish_value), pins the always-include columns to DBL_MAX (utilities.cpp:190-199) and
+// selects -- the sacrifice vector never goes to memory.  grid = (1, chains cmin..cmax); chains that already met the
+// stopping rule are skipped.
+template <int EPI>
+__global__ void __launch_bounds__(TOPK_NT) topk_fused_kernel(const Dev d, int mode, int cmin, int k, const int *always,
+                                                             int n_always)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    if (d.gate && *d.gate == 0) return;
+    const int tid = threadIdx.x;
+    const int c = cmin + blockIdx.y;
+    if (d.done[c]) return;
+    const int len = d.p;
+    for (int i = tid; i < len; i += TOPK_NT) keys[i] = topk_key(finish_value<EPI>(d, mode, c, i, nullptr));
+    if (n_always > 0) {
+        __syncthreads();
+        for (int q = tid; q < n_always; q += TOPK_NT) keys[always[q]] = (unsigned long long)__double_as_longlong(DBL_MAX);
+    }
+    topk_body(keys, len, k, len, nullptr, 0, 0, 0, nullptr, nullptr, 0, d.Anew + (size_t)c * d.kcap, d.kcap, d.tie + c);
+}
+void launch_topk_fused(const Dev &d, int mode, int epi, int cmin, int nspan, int k, const int *always, int n_always,
+                       cudaStream_t st)
+{
+    if (k > d.p) throw EngineError{"top-k: k > number of candidates"};
+    if (d.p > TOPK_LMAX) throw EngineError{"fused top-k: too many columns"};
+    const size_t smem = (size_t)d.p * 8;
+    dim3 grid(1, nspan);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(topk_fused_kernel<EPI_SACR_LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_LMAX * 8));
+        CUDA_CHECK(cudaFuncSetAttribute(topk_fused_kernel<EPI_SACR_GLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_LMAX * 8));
+        CUDA_CHECK(cudaFuncSetAttribute(topk_fused_kernel<EPI_SACR_COX>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_LMAX * 8));
+        configured = true;
+    }
+    if (epi == EPI_SACR_LM) topk_fused_kernel<EPI_SACR_LM><<<grid, TOPK_NT, smem, st>>>(d, mode, cmin, k, always, n_always);
+    else if (epi == EPI_SACR_GLM) topk_fused_kernel<EPI_SACR_GLM><<<grid, TOPK_NT, smem, st>>>(d, mode, cmin, k, always, n_always);
+    else topk_fused_kernel<EPI_SACR_COX><<<grid, TOPK_NT, smem, st>>>(d, mode, cmin, k, always, n_always);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_topk(const double *vals, long long stride, int n_in, int k, int nch, int *out_idx, int out_ld, int *tie,

@@ -107,6 +107,10 @@ void launch_pin(const Dev &d, double *vals, long long stride, int nch, const int
 void launch_topk(const double *vals, long long stride, int n_in, int k, int nch, int *out_idx, int out_ld, int *tie,
                  double *ck0, int *ci0, double *ck1, int *ci1, long long cstride, cudaStream_t st,
                  const int *gate = nullptr, const int *idx0 = nullptr);
+// finish + pin + top-k in one kernel (p <= TOPK_LMAX): reads the sweep partials, writes d.Anew / d.tie for chains
+// cmin .. cmin + nspan - 1 that have not met the stopping rule
+void launch_topk_fused(const Dev &d, int mode, int epi, int cmin, int nspan, int k, const int *always, int n_always,
+                       cudaStream_t st);
 // ---- column-sharded mode
 struct Cand {
     double v;
