@@ -70,12 +70,16 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
 def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
         fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
-        world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,)):
+        world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,), lambda_min=0.0, lambda_max=0.0,
+        n_lambda=None, powell_path=1):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
     ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``.
     ``world > 1``: column-sharded multi-GPU call -- ``x`` is this rank's column shard ``[col_lo, col_lo + p)`` of a
     ``p_total``-column design, ``nccl_id`` the job's 128-byte NCCL unique id (``bess_b200.dist.nccl_unique_id``); beta
-    and always_select use global column numbers."""
+    and always_select use global column numbers.
+    ``path_type == 2`` with ``algorithm_type`` 5 / 3 runs the Powell search over (s, lambda) in
+    ``[s_min, s_max] x [lambda_min, lambda_max]`` (pgs_path, path.cpp:1138); ``powell_path`` 1 = golden-section line
+    searches, 2 = walks on an ``n_lambda``-point log grid."""
     lib = _lib.load()
     if x_device_ptr is None:
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -121,8 +125,9 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     rc = lib.bess_b200_fit(xptr, n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal),
                            int(algorithm_type), int(model_type), int(max_iter), int(exchange_num), int(path_type),
                            bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g), g.size, _d(st), 1, _i(seq),
-                           seq.size, _d(lam), lam.size, int(s_min), int(s_max), 10, 10.0, 0.0, 0.0, lam.size, bool(is_screening),
-                           int(screening_size), 1, _i(alw), alw.size, 1.1, _d(beta), p_all, C.byref(c0), C.byref(tl),
+                           seq.size, _d(lam), lam.size, int(s_min), int(s_max), 10, 10.0, float(lambda_min), float(lambda_max),
+                           int(n_lambda) if n_lambda is not None else lam.size, bool(is_screening),
+                           int(screening_size), int(powell_path), _i(alw), alw.size, 1.1, _d(beta), p_all, C.byref(c0), C.byref(tl),
                            C.byref(ic), C.byref(ext))
     _lib.check(rc)
     out = dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, s=chosen.value, lam=chosen_lam.value,
@@ -138,8 +143,9 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     if want_trace and L > 0:
         s_all, l_all = np.zeros(L, dtype=np.int32), np.zeros(L, dtype=np.int32)
         c_all, t_all, i_all = np.zeros(L), np.zeros(L), np.zeros(L)
-        b_all = np.zeros((L, p)) if path_type == 1 else None
-        lib.bess_b200_trace(_i(s_all), _i(l_all), _d(c_all) if path_type == 1 else None, _d(t_all), _d(i_all),
+        full = path_type == 1 or algorithm_type in (3, 5)  # sequential_path and pgs_path keep every evaluated model
+        b_all = np.zeros((L, p)) if full else None
+        lib.bess_b200_trace(_i(s_all), _i(l_all), _d(c_all) if full else None, _d(t_all), _d(i_all),
                             _d(b_all) if b_all is not None else None, p)
         lam_all = np.zeros(L)
         lib.bess_b200_trace_lambda(_d(lam_all))

@@ -1405,6 +1405,75 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     cl.pt.mark(PH_GRAD);
 }
 
+// ---- explicit chain state (see kernels.cuh).  One CTA rewrites the small tables; a second, wide launch re-gathers the
+// active columns of the restored support for the chain's train rows (chain_begin_kernel computes the linear predictor
+// from XA and never re-gathers).
+__global__ void __launch_bounds__(FIT_NT, 1)
+chain_state_kernel(const Dev d, int c, int op, int slot_beta, int slot_coef0, const StateSlots s)
+{
+    int *A = d.A + (size_t)c * d.kcap;
+    double *bA = d.bA + (size_t)c * d.kcap;
+    double *bD = d.betaD + (size_t)c * d.pstride;
+    if (op == STATE_SAVE) {
+        if (slot_beta >= 0) {
+            const int ks = d.ks[c];
+            for (int a = threadIdx.x; a < ks; a += FIT_NT) {
+                s.A[(size_t)slot_beta * d.kcap + a] = A[a];
+                s.bA[(size_t)slot_beta * d.kcap + a] = bA[a];
+            }
+            if (threadIdx.x == 0) s.ks[slot_beta] = ks;
+        }
+        if (slot_coef0 >= 0 && threadIdx.x == 0) s.coef0[slot_coef0] = d.coef0[c];
+        return;
+    }
+    if (op == STATE_ZERO || slot_beta >= 0) {
+        const int ks_old = d.ks[c];
+        for (int a = threadIdx.x; a < ks_old; a += FIT_NT) {
+            const int j = A[a] - d.col_lo;
+            if (j >= 0 && j < d.p) bD[j] = 0.0;
+        }
+        __syncthreads();
+        const int ks_new = op == STATE_LOAD ? s.ks[slot_beta] : 0;
+        for (int a = threadIdx.x; a < ks_new; a += FIT_NT) {
+            const int j = s.A[(size_t)slot_beta * d.kcap + a];
+            const double v = s.bA[(size_t)slot_beta * d.kcap + a];
+            A[a] = j;
+            bA[a] = v;
+            const int jl = j - d.col_lo;
+            if (jl >= 0 && jl < d.p) bD[jl] = v;
+        }
+        if (threadIdx.x == 0) d.ks[c] = ks_new;
+    }
+    if (threadIdx.x == 0) {
+        if (op == STATE_ZERO) d.coef0[c] = 0.0;
+        else if (slot_coef0 >= 0) d.coef0[c] = s.coef0[slot_coef0];
+    }
+}
+__global__ void __launch_bounds__(256) chain_state_gather_kernel(const Dev d, int c)
+{
+    const int ks = d.ks[c], nt = d.ntrain[c];
+    const int off = (d.family == FAM_LOGIT || d.family == FAM_POISSON) ? 1 : 0;
+    const int *rows = d.rows + (size_t)c * d.n;
+    const int *A = d.A + (size_t)c * d.kcap;
+    double *XA = d.XA + (size_t)c * d.n * d.ldA;
+    const long long tot = (long long)nt * ks;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / ks), a = (int)(e - (long long)r * ks);
+        XA[(size_t)r * d.ldA + off + a] = __ldg(d.X + (size_t)rows[r] * d.ldx + A[a]);
+    }
+    if (off)
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nt; r += gridDim.x * blockDim.x) XA[(size_t)r * d.ldA] = 1.0;
+}
+void launch_chain_state(const Dev &d, int chain, int op, int slot_beta, int slot_coef0, const StateSlots &s, cudaStream_t st)
+{
+    chain_state_kernel<<<1, FIT_NT, 0, st>>>(d, chain, op, slot_beta, slot_coef0, s);
+    CUDA_CHECK(cudaGetLastError());
+    if (op == STATE_LOAD && slot_beta >= 0) {
+        chain_state_gather_kernel<<<148, 256, 0, st>>>(d, chain);
+        CUDA_CHECK(cudaGetLastError());
+    }
+}
+
 void debug_set(int key, int val)
 {
     if (key == 1) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_cox_iters, &val, sizeof(int)));

@@ -136,6 +136,7 @@ struct Engine::Impl {
     double *loss_scratch = nullptr, *loss_out = nullptr;
     int *always = nullptr;
     int n_always = 0;
+    StateSlots slots{};
     double *ck0 = nullptr, *ck1 = nullptr;
     int *ci0 = nullptr, *ci1 = nullptr;
     long long cstride = 0;
@@ -211,6 +212,7 @@ struct Engine::Impl {
         dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
         dfree(m.st, cand_s); dfree(m.st, cand_r); dfree(m.st, mv); dfree(m.st, mi); dfree(m.st, Aloc); dfree(m.st, AXs);
         dfree(m.st, d.AXr); dfree(m.st, d.AXk);
+        dfree(m.st, slots.A); dfree(m.st, slots.bA); dfree(m.st, slots.ks); dfree(m.st, slots.coef0);
         chains_ready = false;
     }
     // (re)allocate the sweep vectors / partial buffers for FS chain slots over the current (n, p)
@@ -756,6 +758,12 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     d.CLcap = CLMAX;
     d.CLcap = chain_cluster_size(d, kcap, 1);  // the largest cluster any batch of this problem can ask for
     d.Spart = d.CLcap > 1 ? dalloc<double>(m.st, (size_t)C * d.CLcap * d.nmat * d.ldA * d.ldA) : nullptr;
+    m.slots.A = dalloc<int>(m.st, (size_t)NSLOT * kcap);
+    m.slots.bA = dalloc<double>(m.st, (size_t)NSLOT * kcap);
+    m.slots.ks = dalloc<int>(m.st, NSLOT);
+    m.slots.coef0 = dalloc<double>(m.st, NSLOT);
+    CUDA_CHECK(cudaMemsetAsync(m.slots.ks, 0, NSLOT * 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(m.slots.coef0, 0, NSLOT * 8, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.ks, 0, MAXC * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.A, 0, (size_t)MAXC * kcap * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.bA, 0, (size_t)MAXC * kcap * 8, m.st));
@@ -1005,6 +1013,19 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
     stats_.n_fits += b.nch;
     stats_.n_batches++;
     if (jobs && loss_out) loss_out->assign(m.h_loss, m.h_loss + ld.njobs);
+}
+
+void Engine::chain_state(int chain, int op, int slot_beta, int slot_coef0)
+{
+    Impl &m = *d_;
+    if (!m.chains_ready) throw EngineError{"chain_state before setup_chains"};
+    if (sharded_) throw EngineError{"chain_state is not available in column-sharded mode"};
+    if (chain < 0 || chain >= m.nchains || slot_beta >= NSLOT || slot_coef0 >= NSLOT) throw EngineError{"bad chain_state call"};
+    if (op != STATE_ZERO && op != STATE_SAVE && op != STATE_LOAD) throw EngineError{"bad chain_state op"};
+    const int sp = m.span_begin(5);
+    launch_chain_state(m.d, chain, op, slot_beta, slot_coef0, m.slots, m.st);
+    m.span_end(sp);
+    stats_.kernel_launches += (op == STATE_LOAD && slot_beta >= 0) ? 2 : 1;
 }
 
 void Engine::losses(const std::vector<LossJob> &jobs, std::vector<double> &out)

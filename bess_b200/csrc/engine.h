@@ -19,6 +19,8 @@ namespace bess {
 constexpr int MAXC = 16;      // max chains = 1 + K folds
 constexpr int PROF_NCAT = 8;
 constexpr int MAX_HIST = 66;  // max_iter + 2 columns of A_list (Algorithm.h:142)
+constexpr int NSLOT = 4;      // snapshot slots of Engine::chain_state
+enum { STATE_ZERO = 0, STATE_SAVE = 1, STATE_LOAD = 2 };
 
 enum Family { FAM_LM = 1, FAM_LOGIT = 2, FAM_POISSON = 3, FAM_COX = 4 };
 
@@ -97,6 +99,10 @@ public:
     // lambda: ridge level of the fits (Algorithm::lambda_level, the L0L2 / "bsrr" penalty); 0 = best-subset selection.
     void run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out,
                    const std::vector<LossJob> *jobs = nullptr, std::vector<double> *loss_out = nullptr, double lambda = 0.0);
+
+    // ---- explicit warm-start state of a chain (STATE_ZERO / STATE_SAVE / STATE_LOAD on NSLOT slots; the
+    // (A, beta_A) half and the coef0 half are addressed separately, a negative slot skips that half).  Used by pgs_path.
+    void chain_state(int chain, int op, int slot_beta, int slot_coef0);
 
     // ---- Metric::train_loss / fold test losses for the chains' current beta.
     void losses(const std::vector<LossJob> &jobs, std::vector<double> &out);

@@ -128,6 +128,19 @@ void launch_gather_active(const Dev &d, const BatchDesc &b, double *AXs, cudaStr
 void launch_gather_owned_cols(const double *X, long long ldx, int n, int p_local, long long col_lo, const int *sel, int m,
                               double *Xn, long long ldn, cudaStream_t st);
 void launch_chain_begin(const Dev &d, const BatchDesc &b, cudaStream_t st);
+// ---- explicit warm-start state of a chain.  pgs_path re-seeds Algorithm::beta_init / coef0_init by hand (zeros at the
+// start of every line search, path.cpp:590-592; the snapshot after the first fit for the backward walk of seq_search,
+// path.cpp:1040-1041, 1084-1085; a stale value for its last fit, path.cpp:1212-1217), so the driver needs to save,
+// restore and clear what a chain would otherwise simply carry forward.
+struct StateSlots {
+    int *A;         // [NSLOT][kcap]
+    double *bA;     // [NSLOT][kcap]
+    int *ks;        // [NSLOT]
+    double *coef0;  // [NSLOT]
+};
+// SAVE: slot_beta <- (A, beta_A, ks) and slot_coef0 <- coef0 of `chain`.  LOAD: the reverse (also rewrites the dense beta
+// and re-gathers X_A).  ZERO: beta = 0, coef0 = 0.  A negative slot leaves that half untouched.
+void launch_chain_state(const Dev &d, int chain, int op, int slot_beta, int slot_coef0, const StateSlots &s, cudaStream_t st);
 void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st);
 void launch_losses(const Dev &d, const LossDesc &jobs, const int *testrows, const int *ntest, const double *y,
                    const double *w, const double *lfact, double *scratch, double *out, cudaStream_t st);

@@ -42,6 +42,7 @@ struct Driver {
     Engine &eng;
     const BessArgs &a;
     int n, p, K;  // p: columns after screening; K: folds (0 when !is_cv)
+    int kcap = 0;  // largest sparsity level the chain workspaces were sized for
     std::vector<int> all_chains, fold_chains;
 
     Driver(Engine &e, const BessArgs &args) : eng(e), a(args)
@@ -253,6 +254,368 @@ void gs_path(Driver &dr, BessResult &out, Eval &best)
     if (!have) throw EngineError{"gs_path: no finite criterion value in the final sweep"};
 }
 
+// ======================================================================================================================
+// pgs_path (path.cpp:1138-1309): Powell's conjugate-direction search over (sparsity level, log lambda) -- the default
+// method of R's type = "bsrr" and of the Python L0L2* classes with path_type = "pgs".  Line searches are either
+// golden-section (powell_path == 1, path.cpp:579-935) or exhaustive walks on the lambda grid (seq_search, :954-1137).
+// Everything below is control flow on scalars; each evaluation is one Driver::step on the device.  The reference's
+// statefulness is kept literally (stale "temp" records after a bracket swap, the warm start of the closing fit, ...):
+// those decide which model is returned.
+// ======================================================================================================================
+enum { SLOT_WARM = 0, SLOT_PREV = 1, SLOT_PREV_FOLD = 2 };
+
+struct Pgs {
+    Driver &dr;
+    BessResult &out;
+    int s_min, s_max;
+    double lmin, lmax;  // log(lambda) bounds (bess.cpp:171-172)
+    bool warm;
+
+    static int sign(double a) { return a > 0 ? 1 : (a < 0 ? -1 : 0); }  // path.cpp:391-405
+    static double det(const double a[2], const double b[2]) { return a[0] * b[1] - a[1] * b[0]; }
+
+    // path.cpp:414-440
+    static void line_intersection(double l1[2][2], double l2[2][2], double x[2], bool &need)
+    {
+        double xdiff[2] = {l1[0][0] - l1[1][0], l2[0][0] - l2[1][0]};
+        double ydiff[2] = {l1[0][1] - l1[1][1], l2[0][1] - l2[1][1]};
+        const double div = det(xdiff, ydiff);
+        if (div == 0) {
+            need = false;
+            return;
+        }
+        double d[2] = {det(l1[0], l1[1]), det(l2[0], l2[1])};
+        x[0] = det(d, xdiff) / div;
+        x[1] = det(d, ydiff) / div;
+        need = true;
+    }
+
+    // path.cpp:445-577: the two points where the line p + t*u leaves the box [s_min, s_max] x [lmin, lmax]
+    void cal_intersections(const double p[2], const double u[2], double a[2], double b[2]) const
+    {
+        double line0[2][2] = {{p[0], p[1]}, {p[0] + u[0], p[1] + u[1]}};
+        double ls[4][2][2] = {{{(double)s_min, lmin}, {(double)s_min, lmax}},
+                              {{(double)s_max, lmin}, {(double)s_max, lmax}},
+                              {{(double)s_min, lmin}, {(double)s_max, lmin}},
+                              {{(double)s_min, lmax}, {(double)s_max, lmax}}};
+        double x[4][2] = {};
+        bool need[4];
+        for (int i = 0; i < 4; i++) line_intersection(line0, ls[i], x[i], need[i]);
+        for (int i = 0; i < 4; i++)
+            if (need[i] && ((x[i][0] < s_min - 0.0001) | (x[i][0] > s_max + 0.0001) | (x[i][1] < lmin - 0.001) |
+                            (x[i][1] > lmax + 0.001)))
+                need[i] = false;
+        for (int i = 0; i < 4; i++)
+            if (need[i])
+                for (int j = i + 1; j < 4; j++)
+                    if (need[j] && std::fabs(x[i][0] - x[j][0]) < 0.0001 && std::fabs(x[i][1] - x[j][1]) < 0.0001)
+                        need[j] = false;
+        int j = 0;
+        for (int i = 0; i < 4; i++)
+            if (need[i]) {
+                if (j == 2) j += 1;
+                if (j == 1) {
+                    b[0] = x[i][0];
+                    b[1] = x[i][1];
+                    j += 1;
+                }
+                if (j == 0) {
+                    a[0] = x[i][0];
+                    a[1] = x[i][1];
+                    j += 1;
+                }
+            }
+        // the reference prints a diagnostic and carries on with uninitialised end points (path.cpp:539-574)
+        if (j < 2) throw EngineError{"pgs_path: search line does not cross the (s, lambda) box twice"};
+    }
+
+    // One evaluation: full-data fit at (T, exp(loglam)) then metric->ic() and metric->train_loss() in the order every
+    // call site uses (path.cpp:633-650).  Under CV the recorded model is what Algorithm holds AFTER ic(): the last
+    // fold's fit, with that beta's full-data loss.
+    Eval eval(double Td, double loglam)
+    {
+        const int T = (int)Td;  // update_sparsity_level(int) truncates
+        if (T < 1 || T > dr.kcap) throw EngineError{"pgs_path: sparsity level left [1, s_max]"};
+        if (warm) {
+            dr.eng.chain_state(0, STATE_SAVE, SLOT_PREV, SLOT_PREV);
+            if (dr.K > 0) dr.eng.chain_state(dr.K, STATE_SAVE, SLOT_PREV_FOLD, -1);
+        }
+        Eval lf;
+        Eval e = dr.step(T, &lf, std::exp(loglam));
+        std::vector<double> b;
+        double c0;
+        dr.denormalise(lf, b, c0);
+        out.A_all.push_back(lf.A);
+        out.bA_all.push_back(std::move(b));
+        out.coef0_all.push_back(c0);
+        out.train_loss_all.push_back(lf.train_loss);
+        out.ic_all.push_back(lf.ic);
+        out.s_all.push_back(T);
+        out.l_all.push_back(e.l);
+        out.lambda_all.push_back(e.lambda);
+        lf.lambda = e.lambda;
+        return lf;
+    }
+    void zero_start()
+    {
+        if (warm) dr.eng.chain_state(0, STATE_ZERO, -1, -1);  // beta_init = 0, coef0_init = 0 (path.cpp:590-592, 966-967)
+    }
+
+    // path.cpp:579-935.  p may alias best_arg (P[0] -> P[0]).
+    void golden_section_search(const double p[2], const double u[2], double best_arg[2], Eval &best)
+    {
+        zero_start();
+        const double s_tol = 2;
+        const double log_lambda_tol = (lmax - lmin) / 200;
+        const double invphi = (std::pow(5.0, 0.5) - 1.0) / 2.0;
+        const double invphi2 = (3.0 - std::pow(5.0, 0.5)) / 2.0;
+        double a[2], b[2], c[2], d[2], h[2];
+        cal_intersections(p, u, a, b);
+        h[0] = b[0] - a[0];
+        h[1] = b[1] - a[1];
+        c[0] = a[0] + invphi2 * h[0];
+        c[1] = a[1] + invphi2 * h[1];
+        d[0] = a[0] + invphi * h[0];
+        d[1] = a[1] + invphi * h[1];
+        if (h[0] > 0.0001) {
+            c[0] = (int)c[0];
+            d[0] = std::ceil(d[0]);
+        } else if (h[0] < -0.0001) {
+            c[0] = std::ceil(c[0]);
+            d[0] = (int)d[0];
+        } else {
+            c[0] = std::round(c[0]);
+            d[0] = std::round(d[0]);
+        }
+        // temp1 / temp2 are only refreshed when c / d is EVALUATED; a bracket swap moves closs / dloss but not them
+        Eval temp1 = eval(c[0], c[1]);
+        double closs = temp1.ic;
+        Eval temp2 = eval(d[0], d[1]);
+        double dloss = temp2.ic;
+        auto small = [&] {
+            return std::fabs((invphi2 - invphi) * h[0]) <= s_tol && std::fabs((invphi2 - invphi) * h[1]) < log_lambda_tol;
+        };
+        auto finish = [&] {
+            double min_loss;
+            const double c0 = c[0], c1 = c[1];
+            if (closs < dloss) {
+                best_arg[0] = c[0];
+                best_arg[1] = c[1];
+                min_loss = closs;
+                best = temp1;
+                best.ic = closs;
+            } else {
+                best_arg[0] = d[0];
+                best_arg[1] = d[1];
+                min_loss = dloss;
+                best = temp2;
+                best.ic = dloss;
+            }
+            for (int i = 1; i < std::fabs((invphi2 - invphi) * h[0]); i++) {
+                Eval e = eval((double)(int)(c0 + sign(h[0]) * i), c1);
+                if (e.ic < min_loss) {
+                    best_arg[0] = c0 + sign(h[0]) * i;
+                    best_arg[1] = c1;
+                    min_loss = e.ic;
+                    best = e;
+                }
+            }
+        };
+        if (small()) {
+            finish();
+            return;
+        }
+        int tt = 0;
+        while (tt < 100) {
+            tt++;
+            if (closs < dloss) {
+                b[0] = d[0];
+                b[1] = d[1];
+                d[0] = c[0];
+                d[1] = c[1];
+                dloss = closs;
+                h[0] = b[0] - a[0];
+                h[1] = b[1] - a[1];
+                c[0] = a[0] + invphi2 * h[0];
+                c[1] = a[1] + invphi2 * h[1];
+                if (h[0] > 0.0001) c[0] = (int)c[0];
+                else if (h[0] < -0.0001) c[0] = std::ceil(c[0]);
+                else c[0] = std::round(c[0]);
+                temp1 = eval(c[0], c[1]);
+                closs = temp1.ic;
+            } else {
+                a[0] = c[0];
+                a[1] = c[1];
+                c[0] = d[0];
+                c[1] = d[1];
+                closs = dloss;
+                h[0] = b[0] - a[0];
+                h[1] = b[1] - a[1];
+                d[0] = a[0] + invphi * h[0];
+                d[1] = a[1] + invphi * h[1];
+                if (h[0] > 0.0001) d[0] = std::ceil(d[0]);
+                else if (h[0] < -0.0001) d[0] = (int)d[0];
+                else d[0] = std::round(d[0]);
+                temp2 = eval(d[0], d[1]);
+                dloss = temp2.ic;
+            }
+            if (small() || tt == 50) {
+                finish();
+                return;
+            }
+        }
+    }
+
+    static int GDC(int a, int b)  // path.cpp:937-953
+    {
+        int Max = a > b ? a : b;
+        int Min = (a == Max) ? b : a;
+        if (Min == 0) throw EngineError{"pgs_path: degenerate search direction (the reference divides by zero here)"};
+        int z = Min;
+        while (Max % Min != 0) {
+            z = Max % Min;
+            Max = Min;
+            Min = z;
+        }
+        return z;
+    }
+
+    // path.cpp:954-1137.  u is rescaled IN PLACE to a primitive grid step; p may alias best_arg.
+    void seq_search(const double p[2], double u[2], double best_arg[2], Eval &best, int nlambda)
+    {
+        zero_start();
+        const double d_lambda = (lmax - lmin) / (nlambda - 1);
+        const int k_lambda = (int)std::fabs(std::round(u[1] / d_lambda));
+        if (std::fabs(u[0]) != 1 && k_lambda != 1) {
+            if (k_lambda == 0 && u[0] != 0) {
+                u[0] = u[0] / std::fabs(u[0]);
+            } else if (u[0] == 0 && k_lambda != 0) {
+                u[1] = u[1] / k_lambda;
+            } else {
+                const int gdc = GDC(k_lambda, std::abs((int)u[0]));
+                if (gdc) {
+                    u[0] = std::round(u[0] / gdc);
+                    u[1] = u[1] / gdc;
+                }
+            }
+        }
+        const double p0 = p[0], p1 = p[1];
+        auto inside = [&](double s, double l) {
+            return (s <= s_max) && (l <= lmax + d_lambda * 1e-4) && (s >= s_min) && (l >= lmin - d_lambda * 1e-4);
+        };
+        std::vector<Eval> fwd, bwd;
+        fwd.push_back(eval(p0, p1));
+        bwd.push_back(fwd[0]);
+        if (warm) dr.eng.chain_state(0, STATE_SAVE, SLOT_WARM, SLOT_WARM);  // beta_warm / coef0_warm (:1040-1041)
+        const size_t cap = (size_t)(s_max - s_min + 1) * (size_t)nlambda;    // rows of beta_all_1 / _2 (:999-1006)
+        for (int i = 1; inside(p0 + i * u[0], p1 + i * u[1]); i++) {
+            if (fwd.size() >= cap) throw EngineError{"pgs_path: seq_search walk longer than the (s, lambda) grid"};
+            fwd.push_back(eval(p0 + i * u[0], p1 + i * u[1]));
+        }
+        if (warm) dr.eng.chain_state(0, STATE_LOAD, SLOT_WARM, SLOT_WARM);  // :1084-1085
+        for (int j = 1; inside(p0 - j * u[0], p1 - j * u[1]); j++) {
+            if (bwd.size() >= cap) throw EngineError{"pgs_path: seq_search walk longer than the (s, lambda) grid"};
+            bwd.push_back(eval(p0 - j * u[0], p1 - j * u[1]));
+        }
+        size_t m1 = 0, m2 = 0;  // Eigen minCoeff: first minimum
+        for (size_t i = 1; i < fwd.size(); i++)
+            if (fwd[i].ic < fwd[m1].ic) m1 = i;
+        for (size_t j = 1; j < bwd.size(); j++)
+            if (bwd[j].ic < bwd[m2].ic) m2 = j;
+        int min_position;
+        if (fwd[m1].ic < bwd[m2].ic) {
+            min_position = (int)m1;
+            best = fwd[m1];
+        } else {
+            min_position = -(int)m2;
+            best = bwd[m2];
+        }
+        best_arg[0] = p0 + min_position * u[0];
+        best_arg[1] = p1 + min_position * u[1];
+    }
+
+    void run(Eval &best, double &best_lambda)
+    {
+        const BessArgs &a = dr.a;
+        const int powell_path = a.powell_path;
+        const int nlambda = powell_path == 1 ? 100 : a.nlambda;
+        if (nlambda < 2) throw EngineError{"pgs_path: nlambda must be >= 2"};
+        double P[3][2], U[2][2];
+        P[0][0] = (double)s_min;
+        P[0][1] = lmin;
+        U[1][0] = 1.;
+        U[1][1] = 0.;
+        U[0][0] = 0.;
+        U[0][1] = (lmax - lmin) / (nlambda - 1);
+        std::vector<Eval> rec(16);
+        std::vector<double> lam(16, 0.0);
+        auto search = [&](double *p, double *u, double *arg, Eval &e) {
+            if (powell_path == 1) golden_section_search(p, u, arg, e);
+            else seq_search(p, u, arg, e, nlambda);
+        };
+        int ttt = 0;
+        search(P[0], U[1], P[0], rec[0]);
+        lam[0] = std::exp(P[0][1]);
+        while (ttt < 11) {
+            ttt++;
+            for (int i = 0; i < 2; i++) {
+                search(P[i], U[i], P[i + 1], rec[(size_t)ttt]);
+                lam[(size_t)ttt] = std::exp(P[i + 1][1]);
+                ttt++;
+            }
+            U[0][0] = U[1][0];
+            U[0][1] = U[1][1];
+            U[1][0] = P[2][0] - P[0][0];
+            U[1][1] = P[2][1] - P[0][1];
+            if ((!(std::fabs(U[1][0]) <= 0.0001 && std::fabs(U[1][1]) <= 0.0001)) && ttt < 11) {
+                search(P[0], U[1], P[0], rec[(size_t)ttt]);
+                lam[(size_t)ttt] = std::exp(P[0][1]);
+            } else {
+                // the closing fit at P[0] (:1212-1225).  Neither update_beta_init nor update_coef0_init is called, so it
+                // starts from whatever Algorithm was last handed: coef0_init of the search's last fit, and beta_init of
+                // that fit -- or, under CV, of the last fold fitted by the ic() behind it (Metric.h:179).
+                const int T = (int)P[0][0];
+                if (T < 1 || T > dr.kcap) throw EngineError{"pgs_path: sparsity level left [1, s_max]"};
+                if (warm) dr.eng.chain_state(0, STATE_LOAD, dr.K > 0 ? SLOT_PREV_FOLD : SLOT_PREV, SLOT_PREV);
+                Eval e = dr.step(T, nullptr, std::exp(P[0][1]));
+                rec[(size_t)ttt] = e;
+                lam[(size_t)ttt] = std::exp(P[0][1]);
+                std::vector<double> b;
+                double c0;
+                dr.denormalise(e, b, c0);
+                out.A_all.push_back(e.A);
+                out.bA_all.push_back(std::move(b));
+                out.coef0_all.push_back(c0);
+                out.train_loss_all.push_back(e.train_loss);
+                out.ic_all.push_back(e.ic);
+                out.s_all.push_back(T);
+                out.l_all.push_back(e.l);
+                out.lambda_all.push_back(e.lambda);
+                ttt++;
+                size_t mi = 0;  // ic_all.minCoeff (:1262), ties go to the closing fit (:1263-1266)
+                for (size_t i = 1; i < (size_t)ttt; i++)
+                    if (rec[i].ic < rec[mi].ic) mi = i;
+                if (rec[mi].ic == rec[(size_t)ttt - 1].ic) mi = (size_t)ttt - 1;
+                best = rec[mi];
+                best_lambda = lam[mi];
+                return;
+            }
+        }
+        throw EngineError{"pgs_path: no result (the reference returns an empty list here)"};
+    }
+};
+
+void pgs_path(Driver &dr, BessResult &out, Eval &best)
+{
+    const BessArgs &a = dr.a;
+    Pgs g{dr, out, a.s_min, a.s_max, std::log(std::max(a.lambda_min, 1e-5)), std::log(std::max(a.lambda_max, 1e-5)),
+          a.is_warm_start};
+    if (!(g.lmax > g.lmin)) throw EngineError{"pgs_path needs lambda_max > max(lambda_min, 1e-5)"};
+    double lam = 0.0;
+    g.run(best, lam);
+    best.lambda = lam;  // lambda_chosen (:1176, 1192, 1207): the line search's end point, not the record's own level
+}
+
 }  // namespace
 
 void bess_run(const BessArgs &a, BessResult &out)
@@ -265,13 +628,14 @@ void bess_run(const BessArgs &a, BessResult &out)
         throw EngineError{"algorithm_type must be 1 (PDAS), 2, 3 or 5 (bess.cpp:93)"};
     if (a.model_type < 1 || a.model_type > 4) throw EngineError{"model_type must be 1..4"};
     if (a.data_type < 1 || a.data_type > 3) throw EngineError{"data_type must be 1..3"};
-    if (a.path_type != 1 && (a.algorithm_type == 5 || a.algorithm_type == 3))
-        throw EngineError{"pgs_path (bsrr, algorithm_type 3/5 with path_type 2) is outside this build's scope"};
-    for (double l : a.lambda_seq) {
-        if (!(l >= 0.0)) throw EngineError{"lambda_seq entries must be >= 0"};
-        if (l != 0.0 && a.path_type != 1)
-            throw EngineError{"lambda != 0 is supported on the sequential path only (gs_path ignores lambda, path.cpp:134)"};
-    }
+    // bess.cpp:167-180: path_type != 1 runs pgs_path for the L0L2 algorithm types and gs_path otherwise
+    const bool pgs = a.path_type != 1 && (a.algorithm_type == 5 || a.algorithm_type == 3);
+    if (pgs && a.world > 1) throw EngineError{"pgs_path is not available in column-sharded mode"};
+    if (pgs && !(a.lambda_min >= 0.0 && a.lambda_max >= 0.0)) throw EngineError{"lambda_min / lambda_max must be >= 0"};
+    if (pgs && a.powell_path != 1 && a.powell_path != 2) throw EngineError{"powell_path must be 1 (golden section) or 2 (sequential)"};
+    if (a.path_type == 1)
+        for (double l : a.lambda_seq)
+            if (!(l >= 0.0)) throw EngineError{"lambda_seq entries must be >= 0"};
     if (!a.g_index.empty()) {
         if ((int)a.g_index.size() != a.p) throw EngineError{"group selection (gsize > 1) is outside this build's scope"};
         for (int j = 0; j < a.p; j++)
@@ -323,8 +687,10 @@ void bess_run(const BessArgs &a, BessResult &out)
     eng.setup_chains(a.is_cv ? a.K : 0, folds.data(), kcap, a.max_iter, a.is_warm_start, always);
 
     Driver dr(eng, a);
+    dr.kcap = kcap;
     Eval best;
     if (a.path_type == 1) sequential_path(dr, out, best);
+    else if (pgs) pgs_path(dr, out, best);
     else gs_path(dr, out, best);
 
     std::vector<double> bA;

@@ -406,6 +406,7 @@ class PathState:
         self.n_iters += min(r.l, self.max_iter)
         self.min_gap = min(self.min_gap, r.min_gap)
         self.alg_beta, self.alg_coef0, self.last = r.beta, r.coef0, r
+        self.alg_beta_init = beta_init  # what update_beta_init was last handed (path.cpp:56 / Metric.h:179)
         return r
 
     def full_fit(self, T, beta_init, coef0_init):
@@ -538,6 +539,239 @@ def gs_path(st: PathState, s_min, s_max):
 
 
 # --------------------------------------------------------------------------------------
+# pgs_path: path.cpp:391-1309 (Powell search over (s, log lambda); "bsrr")
+# --------------------------------------------------------------------------------------
+def _c_round(v):
+    return math.floor(v + 0.5) if v >= 0 else -math.floor(-v + 0.5)
+
+
+def _sign(a):
+    return 1 if a > 0 else (-1 if a < 0 else 0)
+
+
+def _det(a, b):
+    return a[0] * b[1] - a[1] * b[0]
+
+
+def _line_intersection(l1, l2):
+    """path.cpp:414-440; None when parallel."""
+    xdiff = (l1[0][0] - l1[1][0], l2[0][0] - l2[1][0])
+    ydiff = (l1[0][1] - l1[1][1], l2[0][1] - l2[1][1])
+    div = _det(xdiff, ydiff)
+    if div == 0:
+        return None
+    d = (_det(l1[0], l1[1]), _det(l2[0], l2[1]))
+    return [_det(d, xdiff) / div, _det(d, ydiff) / div]
+
+
+def _cal_intersections(p, u, s_min, s_max, lmin, lmax):
+    """path.cpp:445-577."""
+    line0 = ((p[0], p[1]), (p[0] + u[0], p[1] + u[1]))
+    ls = [((s_min, lmin), (s_min, lmax)), ((s_max, lmin), (s_max, lmax)), ((s_min, lmin), (s_max, lmin)),
+          ((s_min, lmax), (s_max, lmax))]
+    ls = [tuple(tuple(float(v) for v in pt) for pt in ln) for ln in ls]
+    xs = [_line_intersection(line0, ln) for ln in ls]
+    need = [x is not None for x in xs]
+    for i in range(4):
+        if need[i] and (xs[i][0] < s_min - 0.0001 or xs[i][0] > s_max + 0.0001 or xs[i][1] < lmin - 0.001
+                        or xs[i][1] > lmax + 0.001):
+            need[i] = False
+    for i in range(4):
+        if need[i]:
+            for j in range(i + 1, 4):
+                if need[j] and abs(xs[i][0] - xs[j][0]) < 0.0001 and abs(xs[i][1] - xs[j][1]) < 0.0001:
+                    need[j] = False
+    pts = [xs[i] for i in range(4) if need[i]]
+    if len(pts) < 2:
+        raise ValueError("pgs_path: search line does not cross the box twice (uninitialised end points in the reference)")
+    return list(pts[0]), list(pts[1])
+
+
+class _PgsRec:
+    __slots__ = ("beta", "coef0", "train_loss", "ic", "T", "lam")
+
+
+def pgs_path(st: PathState, s_min, s_max, lmin, lmax, powell_path, nlambda):
+    """path.cpp:1138-1309.  lmin/lmax are LOG lambda bounds (bess.cpp:171-172).  Returns the de-normalised winner, the
+    chosen lambda and the (T, lambda) trace of the full-data fits."""
+    p_cols = st.data.p
+    trace = []
+    state = dict(beta_init=np.zeros(p_cols), coef0_init=0.0)
+
+    def ev(Td, loglam):
+        """fit + ic() + get_beta()/train_loss() AFTER ic() (path.cpp:633-650)."""
+        T = int(Td)
+        st.lam = math.exp(loglam)
+        r = st.full_fit(T, state["beta_init"], state["coef0_init"])
+        if st.warm:
+            state["beta_init"], state["coef0_init"] = r.beta.copy(), r.coef0
+        trace.append((T, st.lam))
+        rec = _PgsRec()
+        rec.ic = st.ic()
+        rec.beta, rec.coef0, rec.train_loss, rec.T, rec.lam = st.alg_beta.copy(), st.alg_coef0, st.train_loss(), T, st.lam
+        return rec
+
+    def golden(p, u):
+        state["beta_init"], state["coef0_init"] = np.zeros(p_cols), 0.0
+        s_tol, tol = 2, (lmax - lmin) / 200
+        invphi, invphi2 = (5 ** 0.5 - 1.0) / 2.0, (3.0 - 5 ** 0.5) / 2.0
+        a, b = _cal_intersections(p, u, s_min, s_max, lmin, lmax)
+        h = [b[0] - a[0], b[1] - a[1]]
+        c = [a[0] + invphi2 * h[0], a[1] + invphi2 * h[1]]
+        d = [a[0] + invphi * h[0], a[1] + invphi * h[1]]
+        if h[0] > 0.0001:
+            c[0], d[0] = float(int(c[0])), float(math.ceil(d[0]))
+        elif h[0] < -0.0001:
+            c[0], d[0] = float(math.ceil(c[0])), float(int(d[0]))
+        else:
+            c[0], d[0] = float(_c_round(c[0])), float(_c_round(d[0]))
+        t1 = ev(c[0], c[1]); closs = t1.ic
+        t2 = ev(d[0], d[1]); dloss = t2.ic
+
+        def small():
+            return abs((invphi2 - invphi) * h[0]) <= s_tol and abs((invphi2 - invphi) * h[1]) < tol
+
+        def finish():
+            if closs < dloss:
+                arg, best, min_loss = [c[0], c[1]], t1, closs
+            else:
+                arg, best, min_loss = [d[0], d[1]], t2, dloss
+            best = _copy_rec(best, min_loss)
+            i = 1
+            while i < abs((invphi2 - invphi) * h[0]):
+                e = ev(float(int(c[0] + _sign(h[0]) * i)), c[1])
+                if e.ic < min_loss:
+                    arg, min_loss, best = [c[0] + _sign(h[0]) * i, c[1]], e.ic, e
+                i += 1
+            return arg, best
+
+        if small():
+            return finish()
+        tt = 0
+        while tt < 100:
+            tt += 1
+            if closs < dloss:
+                b = [d[0], d[1]]
+                d = [c[0], c[1]]
+                dloss = closs
+                h = [b[0] - a[0], b[1] - a[1]]
+                c = [a[0] + invphi2 * h[0], a[1] + invphi2 * h[1]]
+                c[0] = float(int(c[0])) if h[0] > 0.0001 else (float(math.ceil(c[0])) if h[0] < -0.0001 else float(_c_round(c[0])))
+                t1 = ev(c[0], c[1]); closs = t1.ic
+            else:
+                a = [c[0], c[1]]
+                c = [d[0], d[1]]
+                closs = dloss
+                h = [b[0] - a[0], b[1] - a[1]]
+                d = [a[0] + invphi * h[0], a[1] + invphi * h[1]]
+                d[0] = float(math.ceil(d[0])) if h[0] > 0.0001 else (float(int(d[0])) if h[0] < -0.0001 else float(_c_round(d[0])))
+                t2 = ev(d[0], d[1]); dloss = t2.ic
+            if small() or tt == 50:
+                return finish()
+        raise AssertionError("unreachable")
+
+    def gdc(a, b):
+        mx = max(a, b)
+        mn = b if a == mx else a
+        if mn == 0:
+            raise ValueError("pgs_path: degenerate direction (integer division by zero in the reference)")
+        z = mn
+        while mx % mn != 0:
+            z = mx % mn
+            mx, mn = mn, z
+        return z
+
+    def seqs(p, u):
+        """u is rescaled in place (the caller's U row changes, path.cpp:971-992)."""
+        state["beta_init"], state["coef0_init"] = np.zeros(p_cols), 0.0
+        dl = (lmax - lmin) / (nlambda - 1)
+        k_lambda = int(abs(_c_round(u[1] / dl)))
+        if abs(u[0]) != 1 and k_lambda != 1:
+            if k_lambda == 0 and u[0] != 0:
+                u[0] = u[0] / abs(u[0])
+            elif u[0] == 0 and k_lambda != 0:
+                u[1] = u[1] / k_lambda
+            else:
+                g = gdc(k_lambda, abs(int(u[0])))
+                if g:
+                    u[0] = float(_c_round(u[0] / g))
+                    u[1] = u[1] / g
+        p0, p1 = p[0], p[1]
+
+        def inside(s, l):
+            return s <= s_max and l <= lmax + dl * 1e-4 and s >= s_min and l >= lmin - dl * 1e-4
+
+        fwd = [ev(p0, p1)]
+        bwd = [fwd[0]]
+        warm = (state["beta_init"].copy(), state["coef0_init"])
+        i = 1
+        while inside(p0 + i * u[0], p1 + i * u[1]):
+            fwd.append(ev(p0 + i * u[0], p1 + i * u[1]))
+            i += 1
+        state["beta_init"], state["coef0_init"] = warm[0].copy(), warm[1]
+        j = 1
+        while inside(p0 - j * u[0], p1 - j * u[1]):
+            bwd.append(ev(p0 - j * u[0], p1 - j * u[1]))
+            j += 1
+        m1 = int(np.argmin([e.ic for e in fwd]))
+        m2 = int(np.argmin([e.ic for e in bwd]))
+        if fwd[m1].ic < bwd[m2].ic:
+            pos, best = m1, fwd[m1]
+        else:
+            pos, best = -m2, bwd[m2]
+        return [p0 + pos * u[0], p1 + pos * u[1]], best
+
+    if powell_path == 1:
+        nlambda = 100
+    search = golden if powell_path == 1 else seqs
+    P = [[float(s_min), lmin], [0.0, 0.0], [0.0, 0.0]]
+    U = [[0.0, (lmax - lmin) / (nlambda - 1)], [1.0, 0.0]]
+    recs, lams = {}, {}
+    ttt = 0
+    P[0], recs[0] = search(P[0], U[1])
+    lams[0] = math.exp(P[0][1])
+    while ttt < 11:
+        ttt += 1
+        for i in range(2):
+            P[i + 1], recs[ttt] = search(P[i], U[i])
+            lams[ttt] = math.exp(P[i + 1][1])
+            ttt += 1
+        U[0] = [U[1][0], U[1][1]]
+        U[1] = [P[2][0] - P[0][0], P[2][1] - P[0][1]]
+        if not (abs(U[1][0]) <= 0.0001 and abs(U[1][1]) <= 0.0001) and ttt < 11:
+            P[0], recs[ttt] = search(P[0], U[1])
+            lams[ttt] = math.exp(P[0][1])
+        else:
+            # closing fit: no update_beta_init / update_coef0_init (path.cpp:1212-1217)
+            T = int(P[0][0])
+            st.lam = math.exp(P[0][1])
+            st.T = T
+            r = st._fit(T, st.alg_beta_init, st.alg_coef0_init, st.full_mask, st.xtx_full)
+            trace.append((T, st.lam))
+            rec = _PgsRec()
+            rec.beta, rec.coef0, rec.train_loss, rec.T, rec.lam = r.beta.copy(), r.coef0, st.train_loss(), T, st.lam
+            rec.ic = st.ic()
+            recs[ttt] = rec
+            lams[ttt] = math.exp(P[0][1])
+            ttt += 1
+            ics = [recs[i].ic for i in range(ttt)]
+            mi = int(np.argmin(ics))
+            if ics[mi] == ics[ttt - 1]:
+                mi = ttt - 1
+            best = recs[mi]
+            beta, coef0 = _denormalise(st.data, best.beta, best.coef0, gs=False)
+            return dict(beta=beta, coef0=coef0, train_loss=best.train_loss, ic=best.ic, lam=lams[mi], trace=trace,
+                        s=int(np.count_nonzero(best.beta)))
+    raise ValueError("pgs_path: no result (empty list in the reference)")
+
+
+def _copy_rec(r, ic):
+    o = _PgsRec()
+    o.beta, o.coef0, o.train_loss, o.T, o.lam, o.ic = r.beta, r.coef0, r.train_loss, r.T, r.lam, ic
+    return o
+
+
+# --------------------------------------------------------------------------------------
 # Screening: screening.cpp:26-105 + marginal fits
 # --------------------------------------------------------------------------------------
 def poisson_fit_marginal(xj, y, w):
@@ -600,7 +834,7 @@ def screening(x, y, w, model_type, screening_size, always_select=()):
 # --------------------------------------------------------------------------------------
 def bess_cpp(x, y, data_type, weight, is_normal, model_type, max_iter, path_type, is_warm_start, ic_type, is_cv, K,
              sequence, s_min, s_max, is_screening, screening_size, always_select=(), fold_of_row=None,
-             lambda_seq=(0.0,)):
+             lambda_seq=(0.0,), algorithm_type=1, lambda_min=0.0, lambda_max=0.0, n_lambda=100, powell_path=1):
     x = np.asarray(x, dtype=np.float64)
     p0 = x.shape[1]
     always = np.asarray(always_select, dtype=np.int64)
@@ -611,7 +845,13 @@ def bess_cpp(x, y, data_type, weight, is_normal, model_type, max_iter, path_type
         always = np.searchsorted(scr, always) if len(always) else always  # screening.cpp:91-102
     data = make_data(x, y, weight, data_type, is_normal, model_type)
     st = PathState(data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, is_warm_start, always)
-    out = sequential_path(st, sequence, lambda_seq) if path_type == 1 else gs_path(st, s_min, s_max)
+    if path_type == 1:
+        out = sequential_path(st, sequence, lambda_seq)
+    elif algorithm_type in (5, 3):  # bess.cpp:167-175
+        out = pgs_path(st, s_min, s_max, math.log(max(lambda_min, 1e-5)), math.log(max(lambda_max, 1e-5)), powell_path,
+                       n_lambda)
+    else:
+        out = gs_path(st, s_min, s_max)
     if is_screening:
         b = np.zeros(p0)
         b[scr] = out["beta"]

@@ -10,6 +10,9 @@
 //   ref_seq_trace     -> re-drives /root/reference/src/path.cpp:48-74 with the reference's own
 //                        fit()/train_loss()/ic() and records every level (what the R build
 //                        returns as beta_all / ic_all, path.cpp:116-123)
+//   ref_bess_lambda   -> /root/reference/src/bess.cpp:37 bessCpp, result list incl. "lambda" (sequential_path with a
+//                        lambda grid, path.cpp:25-132; pgs_path Powell search, path.cpp:1138-1309)
+//   ref_pgs_trace     -> /root/reference/src/path.cpp:1138 pgs_path driven directly, every Algorithm::fit() logged
 #include <Eigen/Eigen>
 #include "List.h"
 #include "Data.h"
@@ -154,6 +157,103 @@ void ref_seq_trace(double *x, int n, int p, double *y, double *weight, int data_
     }
     delete alg;
     delete metric;
+}
+
+// bessCpp (/root/reference/src/bess.cpp:37) with the "lambda" key of the result list surfaced as well (pywrap_bess
+// drops it, bess.cpp:270-280): the ridge level chosen by sequential_path (path.cpp:127) / pgs_path (path.cpp:1290).
+void ref_bess_lambda(double *x, int n, int p, double *y, int data_type, double *weight, bool is_normal, int algorithm_type,
+                     int model_type, int max_iter, int path_type, bool is_warm_start, int ic_type, bool is_cv, int K,
+                     int *sequence, int sequence_len, double *lambda_sequence, int lambda_sequence_len, int s_min,
+                     int s_max, double lambda_min, double lambda_max, int n_lambda, bool is_screening, int screening_size,
+                     int powell_path, int *always_select, int always_select_len, double *beta_out, double *coef0_out,
+                     double *train_loss_out, double *ic_out, double *lambda_out)
+{
+    Eigen::VectorXd state = Eigen::VectorXd::Zero(1);
+    Eigen::VectorXi g_index = Eigen::VectorXi::LinSpaced(p, 0, p - 1);
+    List res = bessCpp(Pointer2MatrixXd(x, n, p), Pointer2VectorXd(y, n), data_type, Pointer2VectorXd(weight, n), is_normal,
+                       algorithm_type, model_type, max_iter, 2, path_type, is_warm_start, ic_type, is_cv, K, state,
+                       Pointer2VectorXi(sequence, sequence_len), Pointer2VectorXd(lambda_sequence, lambda_sequence_len),
+                       s_min, s_max, 10, 10.0, lambda_min, lambda_max, n_lambda, is_screening, screening_size, powell_path,
+                       g_index, Pointer2VectorXi(always_select, always_select_len), 1.1);
+    Eigen::VectorXd beta;
+    double lam = 0.0;
+    res.get_value_by_name("beta", beta);
+    res.get_value_by_name("coef0", *coef0_out);
+    res.get_value_by_name("train_loss", *train_loss_out);
+    res.get_value_by_name("ic", *ic_out);
+    res.get_value_by_name("lambda", lam);
+    *lambda_out = lam;
+    for (int j = 0; j < p; j++) beta_out[j] = beta(j);
+}
+
+// ---- pgs_path with every Algorithm::fit() logged.  The reference classes are used as they are; a derived class only
+// overrides the virtual get_A (Algorithm.h:228) to note (sparsity_level, lambda_level, #train rows, coef0_init,
+// nnz(beta_init)) on the first PDAS iteration of each fit (Algorithm::l == 1, Algorithm.h:151) before delegating.
+}  // extern "C"
+
+struct FitLog {
+    std::vector<double> rec;  // 5 doubles per fit
+};
+template <class Base>
+struct Traced : Base {
+    FitLog *log;
+    Traced(Data &data, int algorithm_type, int max_iter, FitLog *lg) : Base(data, algorithm_type, max_iter), log(lg) {}
+    void get_A(Eigen::MatrixXd X, Eigen::VectorXd y, Eigen::VectorXd beta, double coef0, int T0, Eigen::VectorXd weights,
+               Eigen::VectorXi index, Eigen::VectorXi gsize, int N, Eigen::VectorXi &A_out)
+    {
+        if (this->l == 1) {
+            int nnz = 0;
+            for (int j = 0; j < this->beta_init.size(); j++) nnz += this->beta_init(j) != 0.0;
+            const double r[5] = {(double)this->sparsity_level, this->lambda_level, (double)X.rows(), this->coef0_init, (double)nnz};
+            log->rec.insert(log->rec.end(), r, r + 5);
+        }
+        Base::get_A(X, y, beta, coef0, T0, weights, index, gsize, N, A_out);
+    }
+};
+
+extern "C" {
+
+// returns the number of fits; rec_out receives min(nfits, max_rec) records of 5 doubles
+int ref_pgs_trace(double *x, int n, int p, double *y, double *weight, int data_type, bool is_normal, int algorithm_type,
+                  int model_type, int max_iter, bool is_warm_start, int ic_type, bool is_cv, int K, int s_min, int s_max,
+                  double lambda_min, double lambda_max, int n_lambda, int powell_path, double *beta_out, double *coef0_out,
+                  double *train_loss_out, double *ic_out, double *lambda_out, double *rec_out, int max_rec)
+{
+    Eigen::MatrixXd X = Pointer2MatrixXd(x, n, p);
+    Eigen::VectorXd Y = Pointer2VectorXd(y, n);
+    Eigen::VectorXd W = Pointer2VectorXd(weight, n);
+    Eigen::VectorXi g_index = Eigen::VectorXi::LinSpaced(p, 0, p - 1);
+    srand(123);  // bess.cpp:53
+    Data data(X, Y, data_type, W, is_normal, g_index);
+    FitLog flog;
+    Algorithm *alg;
+    if (model_type == 1) { data.add_weight(); alg = new Traced<GroupPdasLm>(data, algorithm_type, max_iter, &flog); }
+    else if (model_type == 2) alg = new Traced<GroupPdasLogistic>(data, algorithm_type, max_iter, &flog);
+    else if (model_type == 3) alg = new Traced<GroupPdasPoisson>(data, algorithm_type, max_iter, &flog);
+    else alg = new Traced<GroupPdasCox>(data, algorithm_type, max_iter, &flog);
+    alg->set_warm_start(is_warm_start);
+    alg->always_select = Eigen::VectorXi(0);
+    alg->tao = 1.1;
+    Metric *metric = make_metric(model_type, ic_type, is_cv, K);
+    if (is_cv) {
+        metric->set_cv_train_test_mask(data.get_n());
+        metric->set_cv_initial_model_param(K, data.get_p());
+        if (model_type == 1) metric->cal_cv_group_XTX(data);
+    }
+    List res = pgs_path(data, alg, metric, s_min, s_max, log(std::max(lambda_min, 1e-5)), log(std::max(lambda_max, 1e-5)),
+                        powell_path, n_lambda);  // bess.cpp:171-174
+    Eigen::VectorXd beta;
+    res.get_value_by_name("beta", beta);
+    res.get_value_by_name("coef0", *coef0_out);
+    res.get_value_by_name("train_loss", *train_loss_out);
+    res.get_value_by_name("ic", *ic_out);
+    res.get_value_by_name("lambda", *lambda_out);
+    for (int j = 0; j < p; j++) beta_out[j] = beta(j);
+    const int nfits = (int)(flog.rec.size() / 5);
+    for (int i = 0; i < std::min(nfits, max_rec) * 5; i++) rec_out[i] = flog.rec[(size_t)i];
+    delete alg;
+    delete metric;
+    return nfits;
 }
 
 }  // extern "C"

@@ -54,3 +54,22 @@ def full_checksum(d):
 def load_full_golden(name):
     path = os.path.join(GOLDEN_DIR, "full", name + ".npz")
     return dict(np.load(path)) if os.path.exists(path) else None
+
+
+PGS_DIR = os.path.join(GOLDEN_DIR, "pgs")
+
+
+def pgs_golden_names():
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(PGS_DIR, "*.npz")))
+
+
+def load_pgs_golden(name):
+    """tests/golden/pgs/*.npz (made by tests/golden/pgs/make_pgs.py from the real reference's pgs_path)."""
+    g = dict(np.load(os.path.join(PGS_DIR, name + ".npz")))
+    (g["model_type"], g["data_type"], g["powell_path"], g["is_cv"], g["K"], g["ic_type"], g["s_min"], g["s_max"],
+     g["n_lambda"], g["warm"]) = (int(v) for v in g["meta"])
+    g["is_cv"], g["warm"] = bool(g["is_cv"]), bool(g["warm"])
+    g["lambda_min"], g["lambda_max"] = (float(v) for v in g["lambda_range"])
+    n = g["x"].shape[0]
+    g["full_fits"] = g["fits"][g["fits"][:, 2] == n][:, :2]  # (sparsity level, lambda) of the full-data fits, in order
+    return g

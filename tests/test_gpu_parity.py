@@ -10,7 +10,7 @@ import pytest
 from oracle import pdas_oracle as orc
 from oracle import ref as refso
 from tests.helpers import (FULL_CONFIGS, RTOL, assert_same_support, full_checksum, golden_names, load_full_golden,
-                           load_golden, rel_err)
+                           load_golden, load_pgs_golden, pgs_golden_names, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -380,3 +380,39 @@ def test_dual_sweep_roofline_probe_runs():
     ms, nbytes = eng.time_dual_sweep(5)
     assert ms > 0 and nbytes == 8.0 * n * p
     eng.close()
+
+
+@pytest.mark.parametrize("name", pgs_golden_names())
+def test_pgs_path_golden(name):
+    """bsrr / L0L2 with path_type 2: the Powell search of pgs_path (path.cpp:1138-1309) over (s, lambda), golden-section
+    and grid-walk line searches, IC and CV, warm and cold, all four families -- final model, chosen lambda and the order
+    of every evaluated (s, lambda) point against the real reference."""
+    from bess_b200 import cbess
+    g = load_pgs_golden(name)
+    out = cbess.fit(g["x"], g["y"], g["data_type"], g["weight"], True, 5, g["model_type"], 20, 2, 2, g["warm"], g["ic_type"],
+                    g["is_cv"], g["K"], [1], g["s_min"], g["s_max"], False, 1,
+                    fold_of_row=g["fold_of_row"] if g["is_cv"] else None, lambda_min=g["lambda_min"],
+                    lambda_max=g["lambda_max"], n_lambda=g["n_lambda"], powell_path=g["powell_path"])
+    assert out["s_all"].tolist() == g["full_fits"][:, 0].astype(int).tolist()
+    assert rel_err(out["lambda_all"], g["full_fits"][:, 1]) < 1e-12
+    _check_final(out, g)
+    assert abs(out["lam"] - g["lam"]) <= 1e-12 * abs(g["lam"])
+    assert out["stats"]["n_boundary_ties"] == 0
+
+
+def test_pgs_path_against_live_reference():
+    """Same, on a fresh seeded problem against the reference library itself (when oracle/_ref travelled)."""
+    if not refso.available():
+        pytest.skip("oracle/_ref/libbess_ref.so not built")
+    from bess_b200 import cbess
+    from bess_b200.gen_data import gen_data
+    for fam, pp, is_cv, seed in (("gaussian", 1, True, 91), ("binomial", 2, False, 92)):
+        model_type, data_type = FAM[fam]
+        d = gen_data(220, 300, fam, 5, seed=seed)
+        w = np.ones(220)
+        r = refso.bess_lambda(d.x, d.y, data_type, w, True, 5, model_type, 20, 2, True, 3, is_cv, 4, [1], 1, 10,
+                              lambda_min=0.001, lambda_max=1.0, n_lambda=6, powell_path=pp)
+        out = cbess.fit(d.x, d.y, data_type, w, True, 5, model_type, 20, 2, 2, True, 3, is_cv, 4, [1], 1, 10, False, 1,
+                        cv_seed=123, lambda_min=0.001, lambda_max=1.0, n_lambda=6, powell_path=pp)
+        _check_final(out, r)
+        assert abs(out["lam"] - r["lambda_"]) <= 1e-12 * abs(r["lambda_"])

@@ -3,7 +3,8 @@ import numpy as np
 import pytest
 
 from oracle import pdas_oracle as orc
-from tests.helpers import RTOL, assert_same_support, golden_names, load_golden, rel_err
+from tests.helpers import (RTOL, assert_same_support, golden_names, load_golden, load_pgs_golden, pgs_golden_names,
+                           rel_err)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -28,3 +29,24 @@ def test_oracle_matches_reference_golden(name):
         assert rel_err(out["loss_all"], g["loss_all"]) < RTOL
         assert out["l_all"].tolist() == g["l_all"].tolist()
     assert out["min_gap"] > 1e-9, "a top-k decision sits inside rounding noise"
+
+
+# poisson_seq_gic is left to the GPU suite: its IRLS fits run away to huge counts and take a minute in numpy
+@pytest.mark.parametrize("name", [n for n in pgs_golden_names() if n != "poisson_seq_gic"])
+def test_oracle_pgs_path_matches_reference(name):
+    """pgs_path (path.cpp:1138-1309): Powell search over (s, lambda).  The order of the evaluated (s, lambda) points is
+    checked too -- the search is stateful (warm starts, stale records), so a wrong turn cannot cancel out."""
+    g = load_pgs_golden(name)
+    out = orc.bess_cpp(g["x"], g["y"], g["data_type"], g["weight"], True, g["model_type"], 20, 2, g["warm"], g["ic_type"],
+                       g["is_cv"], g["K"], [1], g["s_min"], g["s_max"], False, 1, fold_of_row=g["fold_of_row"],
+                       algorithm_type=5, lambda_min=g["lambda_min"], lambda_max=g["lambda_max"], n_lambda=g["n_lambda"],
+                       powell_path=g["powell_path"])
+    tr = np.array(out["trace"])
+    assert tr[:, 0].tolist() == g["full_fits"][:, 0].tolist()
+    assert rel_err(tr[:, 1], g["full_fits"][:, 1]) < 1e-12
+    assert_same_support(out["beta"], g["beta"])
+    assert rel_err(out["beta"], g["beta"]) < RTOL
+    assert abs(out["coef0"] - g["coef0"]) <= RTOL * max(1.0, abs(g["coef0"]))
+    assert abs(out["train_loss"] - g["train_loss"]) <= RTOL * abs(g["train_loss"])
+    assert abs(out["ic"] - g["ic"]) <= RTOL * abs(g["ic"])
+    assert abs(out["lam"] - g["lam"]) <= 1e-12 * abs(g["lam"])
