@@ -7,8 +7,21 @@ Workload ("C5"): gaussian gen.data-shaped design n=1000, p=500000, true s=10, sc
 sequential s.list=1..20  => one step = one full bessCpp call = 220 PDAS fits (20 levels x (1 full fit + 10 folds)).
 
   python bench.py --gpus 1 --steps K --warmup W            our arm, one GPU
-  torchrun ... bench.py --gpus N ...                        our arm, columns of X sharded over N ranks (NCCL)
+  torchrun ... bench.py --gpus N ...                        our arm, N ranks: REPEATED 10-fold CV, one repetition per
+                                                            rank (weak scaling, see below)
   python bench.py --impl reference ...                      the reference's own CPU code (oracle/_ref) on host cores
+
+N > 1.  A single C5 call is 7 ms of which only the 0.6 ms screening sweep is p-sized; the 220 fits behind it run on a
+40 MB screened design and are a chain of ~60 dependent PDAS iterations, so one call cannot be made shorter by more GPUs
+(measured: columns sharded over 2 GPUs, 28.2k -> 30.1k fits/s).  What does shard is what north_star names first: "CV folds
+and sparsity levels shard embarrassingly, with only per-fold losses reduced".  The N-GPU job is therefore repeated 10-fold
+CV with N repetitions (rank r draws its folds from cv_seed + r): the columns of X are sharded over the ranks for the joint
+screening sweep (local top-k + NCCL all-gather of candidates + all-reduce of the kept columns, inside the library), each
+rank then runs its own repetition's 200 fold fits + the full-data chain on the replicated screened design, and one NCCL
+all-reduce per step averages the per-level CV losses so every rank chooses the same sparsity level.  Per-GPU work is fixed
+as N grows => "scaling": "weak".  `value` counts UNIQUE fits only: the full-data chain is identical on every rank and is
+counted once (20*(1 + 10*N) fits per step).  The strong-scaling numbers of the column-sharded path itself (C5 call and the
+no-screening variant C5b, where every PDAS sweep is p = 500k wide) are reported next to it under "column_sharded".
 
 `value`  : whole-job fits/s with X already resident in HBM when the timed region starts.
 `e2e`    : same metric through the reference-facing C-ABI call with X in pinned HOST memory (H2D inside the region).
@@ -88,25 +101,55 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline():
-    """The reference's own C++ (oracle/_ref, single thread as shipped) on a bounded slice of the workload."""
+def _ref_sample(levels):
+    """A proportional slice of C5 for the CPU arm: same n, folds and screening.num (=> same per-fit cost), `levels` of the
+    20 sparsity levels and the same share of the 500000 columns (=> same screening-to-fit ratio as the full call)."""
     from bess_b200.gen_data import gen_data
+    p = CPU_P * levels // CPU_SMAX
+    d = gen_data(N_ROWS, p, "gaussian", K_TRUE, seed=5)
+    return d, p
+
+
+def _ref_call(d, levels):
+    from oracle import ref
+    w = np.ones(N_ROWS)
+    seq = np.arange(1, levels + 1)
+    t0 = time.perf_counter()
+    ref.pywrap_bess(d.x, d.y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, levels, True, SCREEN, cv_seed=123)
+    return time.perf_counter() - t0
+
+
+def _sample_text(p, levels, procs):
+    return (f"oracle/_ref (reference src/*.cpp, -O2, single-threaded as shipped) on a {100 * levels // 20}% slice of C5: "
+            f"n=1000, p={p}, screening.num=5000, 10-fold CV, s.list=1..{levels} ({levels * (1 + NFOLDS)} fits per call)"
+            + (f"; {procs} independent calls side by side, one per process" if procs > 1 else ""))
+
+
+def cpu_baseline(levels=CPU_SMAX):
+    """The reference's own C++ (oracle/_ref, single thread as shipped) on a bounded slice of the workload."""
     from oracle import ref
     if not ref.available():
         return None
-    d = gen_data(N_ROWS, CPU_P, "gaussian", K_TRUE, seed=5)
-    w = np.ones(N_ROWS)
-    seq = np.arange(1, CPU_SMAX + 1)
-    t0 = time.perf_counter()
-    ref.pywrap_bess(d.x, d.y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, CPU_SMAX, True, SCREEN, cv_seed=123)
-    dt = time.perf_counter() - t0
-    fits = CPU_SMAX * (1 + NFOLDS)
+    d, p = _ref_sample(levels)
+    dt = _ref_call(d, levels)
+    fits = levels * (1 + NFOLDS)
     return {"value": fits / dt, "unit": "fits/s", "cores": 1, "kind": "reference", "seconds": dt,
-            "sample": f"oracle/_ref (reference src/*.cpp, -O2, 1 thread) on a 15% slice of C5: n=1000, p={CPU_P}, "
-                      f"screening.num=5000, 10-fold CV, s.list=1..{CPU_SMAX} ({fits} fits)"}
+            "sample": _sample_text(p, levels, 1)}
+
+
+def _ref_worker(d, levels, nsteps, barrier, q):
+    times = []
+    for _ in range(nsteps):
+        barrier.wait()
+        times.append(_ref_call(d, levels))
+    q.put(times)
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation on the box's host cores.  The library is single-threaded
+    (python/setup.py:38-40: no OpenMP), so "all the host threads it can use" = independent calls side by side, one
+    process per core (capped at 16: every call copies its 0.2-0.6 GB design several times over, Algorithm.h:133-138, 228).
+    A step = every process makes one call on the sample, all released together; the step time is the slowest process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -114,19 +157,28 @@ def run_reference(args):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbess_ref.so was not built"}))
         return
-    times = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_baseline()
-        if i >= args.warmup:
-            times.append(base["seconds"])
-    dt = float(np.mean(times))
-    fits = CPU_SMAX * (1 + NFOLDS)
+    import multiprocessing as mp
+    total = args.warmup + args.steps
+    levels = int(max(1, min(CPU_SMAX, 150.0 / (max(total, 1) * 3.5))))  # keep the whole run within a few minutes
+    procs = max(1, min(os.cpu_count() or 1, 16))
+    d, p = _ref_sample(levels)
+    ctx = mp.get_context("fork")
+    barrier, q = ctx.Barrier(procs), ctx.Queue()
+    ws = [ctx.Process(target=_ref_worker, args=(d, levels, total, barrier, q)) for _ in range(procs)]
+    for pr in ws:
+        pr.start()
+    per_proc = [q.get() for _ in ws]
+    for pr in ws:
+        pr.join()
+    step_s = np.max(np.array(per_proc), axis=0)[args.warmup:]  # slowest process of every timed step
+    dt = float(np.mean(step_s))
+    fits = levels * (1 + NFOLDS) * procs
     val = fits / dt
-    base["value"] = val
+    base = {"value": val, "unit": "fits/s", "cores": procs, "kind": "reference", "seconds": dt,
+            "sample": _sample_text(p, levels, procs)}
     print(json.dumps({"impl": "reference", "metric": "pdas_path_cv_fits_per_sec", "value": val, "unit": "fits/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                       "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": base["sample"]},
                       "cpu_baseline": base,
                       "e2e": {"value": val, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -153,7 +205,17 @@ def run_ours(args):
     del X
     torch.cuda.empty_cache()
 
-    def step(host_x=None, profile=False):
+    curve_dev = torch.zeros(SMAX, dtype=torch.float64, device=dev)
+
+    def reduce_curve(o):
+        # repeated CV: average the per-level CV losses over the repetitions (one 160-byte NCCL all-reduce per step)
+        curve_dev.copy_(torch.from_numpy(o["ic_all"]), non_blocking=False)
+        dist.all_reduce(curve_dev)
+        mean = (curve_dev / world).cpu().numpy()
+        o["cv_curve_mean"], o["s_joint"] = mean, int(o["s_all"][int(np.argmin(mean))])
+        return o
+
+    def step(host_x=None, profile=False, seed_shift=True):
         if world == 1:
             if host_x is None:
                 return cbess.fit(None, y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, SMAX, True, SCREEN,
@@ -161,14 +223,17 @@ def run_ours(args):
                                  want_trace=False, profile=profile)
             return cbess.fit(host_x, y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, SMAX, True, SCREEN,
                              cv_seed=123, device=local_rank, want_trace=False, profile=profile)
+        seed = 123 + (rank if seed_shift else 0)
         if host_x is None:
-            return bdist.fit_column_sharded(None, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
-                                            SCREEN, cv_seed=123, device=local_rank, x_shard_device_ptr=Xs.data_ptr(),
-                                            n=N_ROWS, p_local=hi - lo, profile=profile)
-        return bdist.fit_column_sharded(host_x, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
-                                        SCREEN, cv_seed=123, device=local_rank, profile=profile)
+            o = bdist.fit_column_sharded(None, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
+                                         SCREEN, cv_seed=seed, device=local_rank, x_shard_device_ptr=Xs.data_ptr(),
+                                         n=N_ROWS, p_local=hi - lo, profile=profile, want_curve=seed_shift)
+        else:
+            o = bdist.fit_column_sharded(host_x, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
+                                         SCREEN, cv_seed=seed, device=local_rank, profile=profile, want_curve=seed_shift)
+        return reduce_curve(o) if seed_shift else o
 
-    def timed(nsteps, host_x=None):
+    def timed(nsteps, host_x=None, **kw):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -176,7 +241,7 @@ def run_ours(args):
         e0.record()
         out = None
         for _ in range(nsteps):
-            out = step(host_x)
+            out = step(host_x, **kw)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -194,7 +259,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     ms, out = timed(args.steps)
-    fits_per_step = 220
+    # unique fits per step: 20 levels x (the full-data chain once + 10 folds per CV repetition)
+    fits_per_step = bdist.unique_fits_repeated_cv(world, SMAX, NFOLDS)
     value = fits_per_step * args.steps / (ms / 1e3)
 
     # ---- e2e: X in pinned host memory, H2D inside the timed region, results (beta, coef0, losses) read back
@@ -302,18 +368,37 @@ def run_ours(args):
                "parallelism": "single GPU" if world == 1 else f"columns sharded over {world} ranks, NCCL all-gather of "
                               "top-k candidates + all-reduce of active columns every PDAS iteration"}
 
+    # ---- strong scaling of ONE C5 call with the columns sharded (same folds on every rank, no repetition): what the
+    # column axis alone buys at config 5 (only the screening sweep is p-sized)
+    col_sharded = None
+    if world > 1:
+        for _ in range(2):
+            step(seed_shift=False)
+        ns = max(3, min(args.steps, 20))
+        ms_s, out_s = timed(ns, seed_shift=False)
+        col_sharded = {"c5_one_call_strong": {"ms_per_call": ms_s / ns, "fits_per_s": 220 * ns / (ms_s * 1e-3),
+                                              "chosen_s": int(out_s["s"]),
+                                              "note": "one C5 call, columns sharded for the screening sweep, same folds on "
+                                                      "every rank; the PDAS path on the screened design is replicated"},
+                       "c5b_no_screening_strong": c5b}
+
     base = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     if rank == 0:
         line = {
             "metric": "pdas_path_cv_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": "single GPU" if world == 1 else
-                       f"columns of X sharded over {world} ranks for the screening sweep (local top-k + NCCL all-gather "
-                       f"of candidates + all-reduce of the kept columns); PDAS path on the 1000 x 5000 screened design "
-                       f"replicated",
-                       "l2_policy": "inputs larger than L2 (4 GB design streamed from HBM every step)",
-                       "cv_seed": 123, "chosen_s": int(out["s"]), "support_recovered": int(np.isin(nz, np.nonzero(out["beta"])[0]).sum())},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if world == 1 else WORKLOAD + f" x {world} CV repetitions (repeated 10-fold CV, "
+                       f"one repetition per rank; {fits_per_step} unique fits per step)",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"{world} ranks: columns of X sharded for the joint screening sweep (local top-k + NCCL all-gather of "
+                       f"candidates + all-reduce of the kept columns), CV repetitions sharded over the ranks (rank r: folds "
+                       f"from cv_seed 123 + r) on the replicated 1000 x 5000 screened design, one NCCL all-reduce of the "
+                       f"per-level CV losses per step",
+                       "l2_policy": ("inputs larger than L2 (4 GB design streamed from HBM every step)" if world == 1 else
+                                     f"inputs larger than L2 ({4.0 / world:.2f} GB column shard per rank streamed from HBM every step)"),
+                       "cv_seed": 123, "chosen_s": int(out["s"]) if world == 1 else int(out["s_joint"]),
+                       "support_recovered": int(np.isin(nz, np.nonzero(out["beta"])[0]).sum())},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
@@ -330,7 +415,7 @@ def run_ours(args):
                          "kernel_ms_per_step": {k: float(v / args.steps) for k, v in zip(cbess.PROF_CATS, prof_ms)},
                          "kernel_share_of_step": float(total_kernel_ms / args.steps / (ms / args.steps)),
                          "p500k_pdas_sweep": probe},
-            "cpu_baseline": base, "c5b_no_screening": c5b,
+            "cpu_baseline": base, "c5b_no_screening": c5b if world == 1 else None, "column_sharded": col_sharded,
             "fits_per_step": fits_per_step, "n_boundary_ties": int(st["n_boundary_ties"]),
         }
     if world > 1:

@@ -71,7 +71,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
         fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
         world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,), lambda_min=0.0, lambda_max=0.0,
-        n_lambda=None, powell_path=1):
+        n_lambda=None, powell_path=1, want_curve=False):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
     ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``.
     ``world > 1``: column-sharded multi-GPU call -- ``x`` is this rank's column shard ``[col_lo, col_lo + p)`` of a
@@ -140,6 +140,10 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     if is_screening:
         out["screening_A"] = scrA[:int(screening_size)].copy()
     L = int(stats[7])
+    if want_curve and L > 0 and not want_trace:  # criterion per evaluated level only (cheap)
+        s_all, i_all = np.zeros(L, dtype=np.int32), np.zeros(L)
+        lib.bess_b200_trace(_i(s_all), None, None, None, _d(i_all), None, 0)
+        out.update(s_all=s_all, ic_all=i_all)
     if want_trace and L > 0:
         s_all, l_all = np.zeros(L, dtype=np.int32), np.zeros(L, dtype=np.int32)
         c_all, t_all, i_all = np.zeros(L), np.zeros(L), np.zeros(L)

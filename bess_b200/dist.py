@@ -6,6 +6,9 @@ The path shards along two axes:
   B. columns -- for very large p, rank r owns the contiguous column range ``shard_range(p, world, r)``; every PDAS
                 iteration each rank runs the dual sweep + exact local top-k on its columns, the (value, index)
                 candidates are all-gathered and merged identically on every rank (``global_topk_from_local``).
+On top of both sits the embarrassingly parallel axis the bench scales on: repeated K-fold CV -- rank r runs the CV path with
+its own fold assignment (``cv_seed + r``), the per-level CV losses are averaged over ranks (``repeated_cv_reduce``), every
+rank picks the same sparsity level from the averaged curve.
 The merge rule is the library's total order (larger value first, lower index first), implemented once in the C ABI
 (``bess_b200_merge_candidates``) so host and device paths agree."""
 from __future__ import annotations
@@ -71,7 +74,7 @@ def allreduce_sum(x: np.ndarray) -> np.ndarray:
     import torch
     dist = _dist()
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    t = torch.from_numpy(np.array(x, dtype=np.float64, copy=True)).to(dev)  # never reduce into the caller's array
     dist.all_reduce(t)
     return t.cpu().numpy()
 
@@ -98,7 +101,7 @@ def nccl_unique_id() -> bytes:
 def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal, model_type, max_iter, path_type,
                        is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, screening_size, cv_seed=123,
                        fold_of_row=None, device=None, x_shard_device_ptr=None, n=None, p_local=None, profile=False,
-                       always_select=()):
+                       always_select=(), want_curve=False):
     """Multi-GPU fit with the columns of X sharded across the ranks of the current process group (one ``bess_b200_fit``
     call per rank, the library talks NCCL itself).
 
@@ -109,7 +112,9 @@ def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal
         replicated on the n x screening_size design.
       * ``screening_size == 0``: every PDAS iteration is sharded -- local dual sweep + local top-k, all-gather of the
         candidates, all-reduce of the k active columns, replicated active-set fit.
-    Returns the same dict as ``cbess.fit`` (beta has length p_total), identical on every rank."""
+    Returns the same dict as ``cbess.fit`` (beta has length p_total), identical on every rank -- unless the ranks pass
+    different ``cv_seed`` / ``fold_of_row`` with ``screening_size > 0``: the screening is then still joint, and each rank
+    runs its own CV repetition on the replicated screened design (repeated CV, see ``repeated_cv_reduce``)."""
     import torch
     from . import cbess
     dist = _dist()
@@ -120,4 +125,19 @@ def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal
                      ic_type, is_cv, K, sequence, s_min, s_max, scr > 0, max(scr, 1), always_select=always_select,
                      fold_of_row=fold_of_row, cv_seed=cv_seed, device=device, x_device_ptr=x_shard_device_ptr, n=n,
                      p=p_local, want_trace=False, profile=profile, world=dist.get_world_size(), rank=dist.get_rank(),
-                     col_lo=col_lo, p_total=p_total, nccl_id=nccl_unique_id())
+                     col_lo=col_lo, p_total=p_total, nccl_id=nccl_unique_id(), want_curve=want_curve)
+
+
+def repeated_cv_reduce(cv_curve: np.ndarray):
+    """Repeated K-fold CV over the ranks of the current process group: ``cv_curve[i]`` is this rank's mean fold loss at
+    the i-th sparsity level (its own fold assignment); returns (curve averaged over the ranks, index of its first
+    minimum) -- identical on every rank, so all ranks choose the same level.  One small all-reduce per path."""
+    dist = _dist()
+    mean = allreduce_sum(np.asarray(cv_curve, dtype=np.float64)) / dist.get_world_size()
+    return mean, int(np.argmin(mean))
+
+
+def unique_fits_repeated_cv(world: int, n_levels: int, K: int) -> int:
+    """PDAS fits of a ``world``-repetition repeated-CV job that are not duplicates of one another: the full-data chain
+    is the same on every rank (counted once), the K fold chains differ per repetition."""
+    return n_levels * (1 + world * K)

@@ -5,7 +5,9 @@ through ``bess_b200.cbess.pywrap_bess`` (the SWIG-compatible entry over the C AB
 Mapping (linear.py:138-202): algorithm_type "Pdas"->1 / "GroupPdas"->2 / "L0L2"->5; model_type "Lm","Logistic",
 "Poisson","Cox" -> 1..4; path_type "seq"->1 / "pgs"->2; ic_type "aic","bic","gic","ebic" -> 1..4;
 data_type 1 (Lm) / 2 (Logistic, Poisson) / 3 (Cox) (linear.py:475,517,559,597).
-Only the PDAS estimators (algorithm_type 1, lambda = 0, no groups) are inside this build's scope."""
+All twelve estimator classes of the reference are here: Pdas* (best-subset selection), L0L2* (best-subset ridge, "bsrr":
+sequential lambda grids and the Powell search path_type="pgs") and GroupPdas* (accepted when every group is a single
+variable -- group selection with gsize > 1 is the one branch outside this build's scope, and is refused, not approximated)."""
 from __future__ import annotations
 
 import math
@@ -62,9 +64,22 @@ class bess_base:
             raise ValueError("There is NAN value in y")
         n, p = X.shape
         self.p = p
-        if self.algorithm_type_int == 2:
-            raise ValueError("GroupPdas (gsize > 1) is outside the scope of this build")
-        g_index = np.arange(p, dtype=np.int32)
+        if self.algorithm_type_int == 2:  # linear.py:238-254
+            if group is None:
+                raise ValueError("When you choose GroupPdas algorithm, the group information should be given")
+            if len(group) != p:
+                raise ValueError("The length of group should be equal to the number of variables")
+            group = sorted(group)  # the reference sorts the caller's list in place; a copy is sorted here
+            g_index, j = [], 0
+            for i in list(set(group)):
+                while group[j] != i:
+                    j += 1
+                g_index.append(j)
+            if len(g_index) != p:
+                raise ValueError("group selection (groups of more than one variable) is outside the scope of this build")
+            g_index = np.asarray(g_index, dtype=np.int32)
+        else:
+            g_index = np.arange(p, dtype=np.int32)
         if self.model_type_int == 4:
             order = y[:, 0].argsort()  # linear.py:257-263: rows sorted by time, y <- status
             X = X[order]
@@ -137,21 +152,23 @@ class bess_base:
         return None  # the reference defines no prediction for Cox (linear.py:389-430)
 
 
-def _make(name, model, data_type):
+def _make(name, algorithm, model, data_type):
     def __init__(self, max_iter=20, exchange_num=0, path_type="seq", is_warm_start=True, sequence=None,
                  lambda_sequence=None, s_min=None, s_max=None, K_max=None, epsilon=0.0001, lambda_min=None,
                  lambda_max=None, ic_type="ebic", is_cv=False, K=5, is_screening=False, screening_size=None,
                  powell_path=1, always_select=(), tao=0.):
-        bess_base.__init__(self, "Pdas", model, path_type, max_iter, exchange_num, is_warm_start, sequence,
+        bess_base.__init__(self, algorithm, model, path_type, max_iter, exchange_num, is_warm_start, sequence,
                            lambda_sequence, s_min, s_max, K_max, epsilon, lambda_min, lambda_max, ic_type, is_cv, K,
                            is_screening, screening_size, powell_path, always_select, tao)
         self.data_type = data_type
     return type(name, (bess_base,), {"__init__": __init__,
-                                     "__doc__": f"PDAS best-subset selection, model {model} "
+                                     "__doc__": f"{algorithm} estimator, model {model} "
                                                 f"(reference: python/bess/linear.py class {name})."})
 
 
-PdasLm = _make("PdasLm", "Lm", 1)
-PdasLogistic = _make("PdasLogistic", "Logistic", 2)
-PdasPoisson = _make("PdasPoisson", "Poisson", 2)
-PdasCox = _make("PdasCox", "Cox", 3)
+_DATA_TYPE = {"Lm": 1, "Logistic": 2, "Poisson": 2, "Cox": 3}  # linear.py:475,517,559,597
+for _alg in ("Pdas", "L0L2", "GroupPdas"):
+    for _model, _dt in _DATA_TYPE.items():
+        globals()[_alg + _model] = _make(_alg + _model, _alg, _model, _dt)
+del _alg, _model, _dt
+__all__ = ["bess_base"] + [a + m for a in ("Pdas", "L0L2", "GroupPdas") for m in _DATA_TYPE]

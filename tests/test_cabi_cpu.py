@@ -120,3 +120,25 @@ def test_frontend_argument_surface(monkeypatch):
         linear.PdasLm(is_screening=True, screening_size=2, sequence=[1, 2, 3]).fit(x, x[:, 0])
     with pytest.raises(ValueError):
         linear.bess_base("Nope", "Lm", "seq")
+    # the twelve estimator classes of the reference (linear.py:434-925) and their codes
+    for alg, code in (("Pdas", 1), ("L0L2", 5), ("GroupPdas", 2)):
+        for model, (mt, dt) in {"Lm": (1, 1), "Logistic": (2, 2), "Poisson": (3, 2), "Cox": (4, 3)}.items():
+            est = getattr(linear, alg + model)()
+            assert (est.algorithm_type_int, est.model_type_int, est.data_type) == (code, mt, dt)
+    # bsrr: Powell search arguments travel unchanged (linear.py:360-372)
+    m = linear.L0L2Lm(path_type="pgs", s_min=2, s_max=9, lambda_min=0.01, lambda_max=10, powell_path=2)
+    m.fit(x, x[:, 0])
+    a = seen["args"]
+    assert a[5] == 5 and a[9] == 2 and (a[18], a[19]) == (2, 9) and (a[22], a[23], a[24]) == (0.01, 10, 100) and a[27] == 2
+    # sequential lambda grid
+    m = linear.L0L2Poisson(sequence=[1, 2], lambda_sequence=[0.1, 1.0])
+    m.fit(x, np.ones(50))
+    assert list(seen["args"][17]) == [0.1, 1.0] and list(seen["args"][16]) == [1, 2]
+    # GroupPdas: group labels -> first column of each group (linear.py:238-254); singleton groups pass, wider ones are refused
+    m = linear.GroupPdasLm(sequence=[1, 2])
+    with pytest.raises(ValueError):
+        m.fit(x, x[:, 0])
+    m.fit(x, x[:, 0], group=list(range(30)))
+    assert list(seen["args"][14]) == list(range(30)) and seen["args"][5] == 2
+    with pytest.raises(ValueError):
+        m.fit(x, x[:, 0], group=[i // 2 for i in range(30)])

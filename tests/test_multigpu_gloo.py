@@ -36,7 +36,12 @@ def _worker(rank, world, port, q):
         mine = np.array([fold_losses[c] if bdist.chain_owner(1 + c, world) == rank else 0.0 for c in range(K)])
         red = bdist.allreduce_sum(mine)
         ok_red = np.allclose(red, fold_losses)
-        q.put((rank, ok_topk, ok_red))
+        # repeated CV: every rank holds its own CV curve; all ranks must agree on the averaged curve and the chosen level
+        curves = np.array([[5.0, 3.0, 2.5, 2.6, 4.0], [5.5, 2.0, 2.9, 2.7, 4.5]])
+        mean, best = bdist.repeated_cv_reduce(curves[rank])
+        ok_rep = np.allclose(mean, curves.mean(axis=0)) and best == int(np.argmin(curves.mean(axis=0)))
+        ok_rep = ok_rep and bdist.unique_fits_repeated_cv(world, 20, 10) == 20 * (1 + 2 * 10)
+        q.put((rank, ok_topk, ok_red and ok_rep))
     finally:
         dist.destroy_process_group()
 
