@@ -292,6 +292,75 @@ _FIT = {1: fit_lm, 2: fit_logistic, 3: fit_poisson, 4: fit_cox}
 
 
 # --------------------------------------------------------------------------------------
+# Group selection (gsize > 1; R: bess(..., group.index=), Python: GroupPdas*): the same get_A functions with real
+# k_g x k_g Phi / invPhi blocks.  Algorithm.h:1097-1129 (lm), :1206-1263 (logistic), :1324-1367 (poisson),
+# :1497-1568 (cox, dense n x n Hessian branch of algorithm_type 2 / 3); utilities.cpp:113-177.
+# --------------------------------------------------------------------------------------
+def group_layout(g_index, p):
+    """Data ctor, Data.h:53-61: g_index holds the first column of every group (ascending), sizes by difference."""
+    g_index = np.asarray(g_index, dtype=np.int64)
+    g_size = np.diff(np.append(g_index, p))
+    return g_index, g_size
+
+
+def _sqrtm_spd(M):
+    """Principal square root of a symmetric positive-definite block (the reference calls Eigen's Schur-based
+    MatrixBase::sqrt(), utilities.cpp:147; for an SPD argument that is U diag(sqrt(ev)) U^T)."""
+    ev, U = np.linalg.eigh(M)
+    return (U * np.sqrt(ev)) @ U.T
+
+
+def group_gram_lm(X, g_index, g_size):
+    """utilities.cpp:153-165 group_XTX: X_g^T X_g per group (over the rows handed in)."""
+    return [X[:, a:a + k].T @ X[:, a:a + k] for a, k in zip(g_index, g_size)]
+
+
+def find_ind(A, g_index, g_size, p):
+    """utilities.cpp:113-130."""
+    if len(A) == len(g_index):
+        return np.arange(p)
+    return np.concatenate([np.arange(g_index[g], g_index[g] + g_size[g]) for g in A]).astype(np.int64)
+
+
+def group_sacrifice(model_type, X, y, w, beta, coef0, xtx, lam, g_index, g_size):
+    n = X.shape[0]
+    N = len(g_index)
+    if model_type == 1:
+        d = X.T @ (y - X @ beta - coef0) / float(n) - 2.0 * lam * beta
+        blocks = [2.0 * lam * np.eye(k) + xtx[i] / float(n) for i, k in enumerate(g_size)]
+    elif model_type in (2, 3):
+        if model_type == 2:
+            e = np.exp(_clip(X @ beta + coef0, 30.0))
+            pr = e / (e + 1.0)
+            g, h = w * (y - pr), w * pr * (1 - pr)
+        else:
+            e = np.exp(X @ beta + coef0)
+            g, h = (y - e) * w, e * w
+        d = X.T @ g - 2.0 * lam * beta
+        blocks = []
+        for a, k in zip(g_index, g_size):
+            XG = X[:, a:a + k]
+            blocks.append((XG * h[:, None]).T @ XG + 2.0 * lam * np.eye(k))
+    else:
+        theta = w * np.exp(_clip(X @ beta, 30.0))
+        cum = np.cumsum(theta[::-1])[::-1]
+        c2 = np.cumsum(y * w / cum)
+        c3 = np.cumsum(y * w / cum ** 2)
+        idx = np.minimum.outer(np.arange(n), np.arange(n))
+        H = -c3[idx] * np.outer(theta, theta)  # :1535-1545: upper triangle mirrored
+        H[np.diag_indices(n)] += c2 * theta
+        g = w * y - c2 * theta
+        d = X.T @ g - 2.0 * lam * beta
+        blocks = [X[:, a:a + k].T @ H @ X[:, a:a + k] + 2.0 * lam * np.eye(k) for a, k in zip(g_index, g_size)]
+    bd = np.zeros(N)
+    for i, (a, k) in enumerate(zip(g_index, g_size)):
+        phi = _sqrtm_spd(blocks[i])
+        t = phi @ beta[a:a + k] + np.linalg.solve(phi, d[a:a + k])
+        bd[i] = float(t @ t) / k
+    return bd
+
+
+# --------------------------------------------------------------------------------------
 # Algorithm::fit  (Algorithm.h:113-171)
 # --------------------------------------------------------------------------------------
 @dataclass
@@ -302,10 +371,13 @@ class FitResult:
     A: np.ndarray
     A_hist: list = field(default_factory=list)
     min_gap: float = np.inf
+    G: np.ndarray = None  # selected groups (== A without group structure)
 
 
 def pdas_fit(data: Data, model_type, T0, beta_init, coef0_init, train_mask, xtx, max_iter=20, always_select=(),
-             lam=0.0):
+             lam=0.0, groups=None):
+    """groups: None, or (g_index, g_size) -- then T0 counts GROUPS, xtx is the list of per-group Grams (lm) and
+    FitResult.A holds the selected columns (find_ind), FitResult.G the selected groups."""
     X = data.x[train_mask] if len(train_mask) != data.n else data.x
     y = data.y[train_mask] if len(train_mask) != data.n else data.y
     w = data.weight[train_mask] if len(train_mask) != data.n else data.weight
@@ -315,14 +387,18 @@ def pdas_fit(data: Data, model_type, T0, beta_init, coef0_init, train_mask, xtx,
     seen = [np.zeros(T0, dtype=np.int32)]  # A_list.col(0) = 0  (:142-143)
     res = FitResult(beta, coef0, 0, seen[0])
     for l in range(1, max_iter + 1):
-        bd = _SACRIFICE[model_type](X, y, w, beta, coef0, xtx, lam=lam)
+        if groups is None:
+            bd = _SACRIFICE[model_type](X, y, w, beta, coef0, xtx, lam=lam)
+        else:
+            bd = group_sacrifice(model_type, X, y, w, beta, coef0, xtx, lam, groups[0], groups[1])
         if len(always_select):
             bd[np.asarray(always_select)] = DBL_MAX  # slice_assignment, utilities.cpp:190-199
         res.min_gap = min(res.min_gap, boundary_gap(bd, T0))
         A = max_k(bd, T0)
-        beta_A, coef0 = _FIT[model_type](X[:, A], y, w, coef0, lam=lam)  # beta_A reset to 0 before the fit (:157)
+        ind = A if groups is None else find_ind(A, groups[0], groups[1], p)
+        beta_A, coef0 = _FIT[model_type](X[:, ind], y, w, coef0, lam=lam)  # beta_A reset to 0 before the fit (:157)
         beta = np.zeros(p)
-        beta[A] = beta_A
+        beta[ind] = beta_A
         res.A_hist.append(A)
         res.l = l
         if any(np.array_equal(A, s) for s in seen):  # :164-170
@@ -330,7 +406,8 @@ def pdas_fit(data: Data, model_type, T0, beta_init, coef0_init, train_mask, xtx,
         seen.append(A)
     else:
         res.l = max_iter + 1  # loop variable after a non-returning for (:151)
-    res.beta, res.coef0, res.A = beta, coef0, A
+    res.beta, res.coef0, res.A = beta, coef0, ind
+    res.G = A
     return res
 
 
@@ -377,12 +454,23 @@ def ic_penalty(ic_type, n, p, s):
 class PathState:
     """The mutable state the reference keeps in Algorithm + Metric between calls."""
 
-    def __init__(self, data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, warm_start, always_select=()):
+    def __init__(self, data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, warm_start, always_select=(),
+                 g_index=None, algorithm_type=1):
         self.data, self.model_type, self.ic_type, self.is_cv, self.K = data, model_type, ic_type, is_cv, K
         self.max_iter, self.warm, self.always = max_iter, warm_start, tuple(always_select)
         n, p = data.n, data.p
+        self.algorithm_type = algorithm_type
+        self.groups = None
+        if g_index is not None and len(g_index) != p:
+            self.groups = group_layout(g_index, p)
+        self.g_num = p if self.groups is None else len(self.groups[0])
         self.full_mask = np.arange(n)
-        self.xtx_full = (data.x * data.x).sum(axis=0) if model_type == 1 else None  # utilities.cpp:153-165
+        if model_type != 1:
+            self.xtx_full = None
+        elif self.groups is None:
+            self.xtx_full = (data.x * data.x).sum(axis=0)  # utilities.cpp:153-165
+        else:
+            self.xtx_full = group_gram_lm(data.x, *self.groups)
         self.alg_coef0_init = 0.0
         self.lam = 0.0  # Algorithm::lambda_level
         self.alg_beta = np.zeros(p)
@@ -396,12 +484,16 @@ class PathState:
             self.test_masks = [np.nonzero(fold_of_row == k)[0] for k in range(K)]
             self.train_masks = [np.nonzero(fold_of_row != k)[0] for k in range(K)]
             self.cv_param = np.zeros((K, p))  # Metric.h:39-42
-            self.xtx_folds = ([(data.x[m] ** 2).sum(axis=0) for m in self.train_masks]
-                              if model_type == 1 else [None] * K)  # Metric.h:108-129
+            if model_type != 1:
+                self.xtx_folds = [None] * K
+            elif self.groups is None:
+                self.xtx_folds = [(data.x[m] ** 2).sum(axis=0) for m in self.train_masks]  # Metric.h:108-129
+            else:
+                self.xtx_folds = [group_gram_lm(data.x[m], *self.groups) for m in self.train_masks]
 
     def _fit(self, T, beta_init, coef0_init, mask, xtx):
         r = pdas_fit(self.data, self.model_type, T, beta_init, coef0_init, mask, xtx, self.max_iter, self.always,
-                     lam=self.lam)
+                     lam=self.lam, groups=self.groups)
         self.n_fits += 1
         self.n_iters += min(r.l, self.max_iter)
         self.min_gap = min(self.min_gap, r.min_gap)
@@ -431,7 +523,8 @@ class PathState:
                 losses.append(fold_loss(self.data, self.model_type, r.beta, r.coef0, self.test_masks[k]))
             return float(np.mean(losses))
         tl = self.train_loss()
-        pen = ic_penalty(self.ic_type, self.data.n, self.data.p, self.T)
+        # algorithm_type 2 / 3 (GPDAS / GL0L2): g_num and group_df (= sparsity level) replace p and s (Metric.h:230-254)
+        pen = ic_penalty(self.ic_type, self.data.n, self.g_num if self.algorithm_type in (2, 3) else self.data.p, self.T)
         if pen is None:
             return 0.0
         if self.model_type == 1:
@@ -834,7 +927,8 @@ def screening(x, y, w, model_type, screening_size, always_select=()):
 # --------------------------------------------------------------------------------------
 def bess_cpp(x, y, data_type, weight, is_normal, model_type, max_iter, path_type, is_warm_start, ic_type, is_cv, K,
              sequence, s_min, s_max, is_screening, screening_size, always_select=(), fold_of_row=None,
-             lambda_seq=(0.0,), algorithm_type=1, lambda_min=0.0, lambda_max=0.0, n_lambda=100, powell_path=1):
+             lambda_seq=(0.0,), algorithm_type=1, lambda_min=0.0, lambda_max=0.0, n_lambda=100, powell_path=1,
+             g_index=None):
     x = np.asarray(x, dtype=np.float64)
     p0 = x.shape[1]
     always = np.asarray(always_select, dtype=np.int64)
@@ -844,7 +938,10 @@ def bess_cpp(x, y, data_type, weight, is_normal, model_type, max_iter, path_type
         x = x[:, scr]
         always = np.searchsorted(scr, always) if len(always) else always  # screening.cpp:91-102
     data = make_data(x, y, weight, data_type, is_normal, model_type)
-    st = PathState(data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, is_warm_start, always)
+    if g_index is not None and len(g_index) != x.shape[1] and is_screening:
+        raise ValueError("screening with groups un-screens by group id in the reference (bess.cpp:186-209): not restated")
+    st = PathState(data, model_type, ic_type, is_cv, K, fold_of_row, max_iter, is_warm_start, always, g_index=g_index,
+                   algorithm_type=algorithm_type)
     if path_type == 1:
         out = sequential_path(st, sequence, lambda_seq)
     elif algorithm_type in (5, 3):  # bess.cpp:167-175

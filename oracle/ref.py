@@ -120,7 +120,7 @@ def seq_trace(x, y, weight, data_type, is_normal, model_type, max_iter, is_warm_
 
 def bess_lambda(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, path_type, is_warm_start, ic_type,
                 is_cv, K, sequence, s_min, s_max, lambda_seq=(0.0,), lambda_min=0.0, lambda_max=0.0, n_lambda=100,
-                powell_path=1, is_screening=False, screening_size=1, always_select=(), cv_seed=123):
+                powell_path=1, is_screening=False, screening_size=1, always_select=(), cv_seed=123, g_index=None):
     """bessCpp (bess.cpp:37) incl. the chosen ridge level: sequential lambda grids and the pgs_path Powell search
     (path.cpp:1138-1309; taken when path_type == 2 and algorithm_type is 5 or 3, bess.cpp:169-176)."""
     os.environ["BESS_CV_SEED"] = str(cv_seed)
@@ -131,14 +131,15 @@ def bess_lambda(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
     seq = np.ascontiguousarray(sequence, dtype=np.int32)
     lam = np.ascontiguousarray(lambda_seq, dtype=np.float64)
     alw = np.ascontiguousarray(always_select, dtype=np.int32)
+    gi = np.ascontiguousarray(np.arange(p) if g_index is None else g_index, dtype=np.int32)
     beta = np.zeros(p)
     c0, tl, ic, lo = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
     i, b, dbl = C.c_int, C.c_bool, C.c_double
     lib().ref_bess_lambda(_d(x), i(n), i(p), _d(y), i(data_type), _d(w), b(is_normal), i(algorithm_type), i(model_type),
                           i(max_iter), i(path_type), b(is_warm_start), i(ic_type), b(is_cv), i(K), _i(seq), i(len(seq)),
                           _d(lam), i(len(lam)), i(s_min), i(s_max), dbl(lambda_min), dbl(lambda_max), i(n_lambda),
-                          b(is_screening), i(screening_size), i(powell_path), _i(alw), i(len(alw)), _d(beta),
-                          C.byref(c0), C.byref(tl), C.byref(ic), C.byref(lo))
+                          b(is_screening), i(screening_size), i(powell_path), _i(alw), i(len(alw)), _i(gi), i(len(gi)),
+                          _d(beta), C.byref(c0), C.byref(tl), C.byref(ic), C.byref(lo))
     return dict(beta=beta, coef0=c0.value, train_loss=tl.value, ic=ic.value, lambda_=lo.value)
 
 

@@ -165,11 +165,11 @@ void ref_bess_lambda(double *x, int n, int p, double *y, int data_type, double *
                      int model_type, int max_iter, int path_type, bool is_warm_start, int ic_type, bool is_cv, int K,
                      int *sequence, int sequence_len, double *lambda_sequence, int lambda_sequence_len, int s_min,
                      int s_max, double lambda_min, double lambda_max, int n_lambda, bool is_screening, int screening_size,
-                     int powell_path, int *always_select, int always_select_len, double *beta_out, double *coef0_out,
-                     double *train_loss_out, double *ic_out, double *lambda_out)
+                     int powell_path, int *always_select, int always_select_len, int *gindex, int gindex_len,
+                     double *beta_out, double *coef0_out, double *train_loss_out, double *ic_out, double *lambda_out)
 {
     Eigen::VectorXd state = Eigen::VectorXd::Zero(1);
-    Eigen::VectorXi g_index = Eigen::VectorXi::LinSpaced(p, 0, p - 1);
+    Eigen::VectorXi g_index = Pointer2VectorXi(gindex, gindex_len);  // first column of every group (bess.R:540)
     List res = bessCpp(Pointer2MatrixXd(x, n, p), Pointer2VectorXd(y, n), data_type, Pointer2VectorXd(weight, n), is_normal,
                        algorithm_type, model_type, max_iter, 2, path_type, is_warm_start, ic_type, is_cv, K, state,
                        Pointer2VectorXi(sequence, sequence_len), Pointer2VectorXd(lambda_sequence, lambda_sequence_len),
