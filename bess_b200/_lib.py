@@ -59,6 +59,9 @@ def load():
     lib.bessgpu_gather_columns.argtypes = [C.c_void_p, ip, ip, C.c_int, C.c_void_p, C.c_longlong]
     lib.bessgpu_normalize.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bessgpu_get_norm.argtypes = [C.c_void_p, dp, dp, dp]
+    lib.bessgpu_set_groups.argtypes = [C.c_void_p, ip, C.c_int]
+    lib.bessgpu_run_batch_groups.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, C.c_int, C.c_double, ip, dp, ip, ip, dp,
+                                             C.c_int]
     lib.bessgpu_setup_chains.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, C.c_int, C.c_int, ip, C.c_int]
     lib.bessgpu_run_batch.argtypes = [C.c_void_p, C.c_int, ip, C.c_int, C.c_int, ip, dp, ip, dp]
     lib.bessgpu_losses.argtypes = [C.c_void_p, ip, ip, ip, C.c_int, dp]

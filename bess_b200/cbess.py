@@ -71,7 +71,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
         fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
         world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,), lambda_min=0.0, lambda_max=0.0,
-        n_lambda=None, powell_path=1, want_curve=False):
+        n_lambda=None, powell_path=1, want_curve=False, g_index=None):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
     ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``.
     ``world > 1``: column-sharded multi-GPU call -- ``x`` is this rank's column shard ``[col_lo, col_lo + p)`` of a
@@ -89,7 +89,8 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
         xptr = C.cast(C.c_void_p(int(x_device_ptr)), dp)
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     w = np.ascontiguousarray(weight, dtype=np.float64).ravel()
-    g = np.arange(p, dtype=np.int32)
+    # group selection: first column of every group (linear.py:238-254); None = no group structure
+    g = np.arange(p, dtype=np.int32) if g_index is None else np.ascontiguousarray(g_index, dtype=np.int32).ravel()
     st = np.zeros(1)
     lam = np.ascontiguousarray(lambda_seq, dtype=np.float64).ravel()
     seq = np.ascontiguousarray(sequence, dtype=np.int32).ravel()

@@ -296,6 +296,10 @@ int bessgpu_gather_columns(bessgpu_handle *h, const int *cols, const int *pos, i
 {
     return guarded([&] { h->eng->gather_columns(cols, pos, m, dst_dev, ld); });
 }
+int bessgpu_set_groups(bessgpu_handle *h, const int *g_index, int n_groups)
+{
+    return guarded([&] { h->eng->set_groups(std::vector<int>(g_index, g_index + n_groups)); });
+}
 int bessgpu_normalize(bessgpu_handle *h, int data_type, int is_normal)
 {
     return guarded([&] { h->eng->normalize(data_type, is_normal != 0); });
@@ -328,6 +332,23 @@ int bessgpu_run_batch(bessgpu_handle *h, int T, const int *chains, int nch, int 
             if (coef0_out) coef0_out[i] = br.coef0[i];
             if (A_out) std::copy(br.A[i].begin(), br.A[i].end(), A_out + (size_t)i * T);
             if (bA_out) std::copy(br.bA[i].begin(), br.bA[i].end(), bA_out + (size_t)i * T);
+        }
+    });
+}
+int bessgpu_run_batch_groups(bessgpu_handle *h, int T, const int *chains, int nch, int new_path_step, double lambda,
+                             int *l_out, double *coef0_out, int *ks_out, int *A_out, double *bA_out, int ld)
+{
+    return guarded([&] {
+        std::vector<int> ch(chains, chains + nch);
+        BatchResult br;
+        h->eng->run_batch(T, ch, new_path_step != 0, br, nullptr, nullptr, lambda);
+        for (int i = 0; i < nch; i++) {
+            if ((int)br.A[i].size() > ld) throw EngineError{"run_batch_groups: ld is smaller than a support"};
+            if (l_out) l_out[i] = br.l[i];
+            if (coef0_out) coef0_out[i] = br.coef0[i];
+            if (ks_out) ks_out[i] = (int)br.A[i].size();
+            if (A_out) std::copy(br.A[i].begin(), br.A[i].end(), A_out + (size_t)i * ld);
+            if (bA_out) std::copy(br.bA[i].begin(), br.bA[i].end(), bA_out + (size_t)i * ld);
         }
     });
 }

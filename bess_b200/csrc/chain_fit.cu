@@ -1297,10 +1297,13 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     if (d.done[c]) return;  // uniform over the cluster
     Clu cl = make_clu(sm, CL);
     if (CL > 1) cg::this_cluster().sync();  // every CTA of the cluster is running before any DSMEM traffic
-    const int T = b.T;
+    // group selection: the top-k chose T0 GROUPS (Ag), the fit works on their T columns (Anew); without groups they coincide
+    const int T0 = b.T;
+    const int T = d.grouped ? d.Tc[c] : T0;
+    const int *Ag = d.Anew + (size_t)c * d.kcap;
     ChainCtx cx = make_ctx(d, c, T, cl, sm);
     const int ldA = d.ldA;
-    const int *Anew = d.Anew + (size_t)c * d.kcap;
+    const int *Anew = d.grouped ? d.AnewCols + (size_t)c * d.kcap : Ag;
     const int *rows = d.rows + (size_t)c * d.n;
     int *Acur = d.A + (size_t)c * d.kcap;
     const int ks_old = d.ks[c];
@@ -1374,7 +1377,7 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     for (int ll = 0; ll < l && !seen; ll++) {
         const int *hp = d.hist + ((size_t)c * MAX_HIST + ll) * d.kcap;
         int same = 1;
-        for (int a = threadIdx.x; a < T; a += FIT_NT) same &= (hp[a] == Anew[a]);
+        for (int a = threadIdx.x; a < T0; a += FIT_NT) same &= (hp[a] == Ag[a]);
         seen = __syncthreads_and(same);
     }
     const int finished = seen || l >= d.max_iter;
@@ -1383,10 +1386,10 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     // scatter (Algorithm.h:159-163), record A
     if (cl.rank == 0) {
         int *hl = d.hist + ((size_t)c * MAX_HIST + l) * d.kcap;
+        for (int a = threadIdx.x; a < T0; a += FIT_NT) hl[a] = Ag[a];
         for (int a = threadIdx.x; a < T; a += FIT_NT) {
             const int j = Anew[a];
             Acur[a] = j;
-            hl[a] = j;
             d.bA[(size_t)c * d.kcap + a] = slopes[a];
             const int jl = j - d.col_lo;
             if (jl >= 0 && jl < d.p) d.betaD[(size_t)c * d.pstride + jl] = slopes[a];

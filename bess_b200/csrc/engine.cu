@@ -141,7 +141,9 @@ struct Engine::Impl {
     int *ci0 = nullptr, *ci1 = nullptr;
     long long cstride = 0;
     // pinned host mirrors (owned by the DeviceContext)
-    int *h_done = nullptr, *h_l = nullptr, *h_tie = nullptr, *h_A = nullptr;
+    int *h_done = nullptr, *h_l = nullptr, *h_tie = nullptr, *h_ks = nullptr, *h_A = nullptr;
+    int *gidx = nullptr, *gsz = nullptr;  // group selection: device copies of Engine::g_index_ / g_size_
+    int Tmax = 0;                          // largest sparsity level (in groups when grouped) the workspaces hold
     double *h_coef0 = nullptr, *h_bA = nullptr, *h_loss = nullptr;
     bool chains_ready = false;
     bool x_owned = true;
@@ -213,6 +215,7 @@ struct Engine::Impl {
         dfree(m.st, cand_s); dfree(m.st, cand_r); dfree(m.st, mv); dfree(m.st, mi); dfree(m.st, Aloc); dfree(m.st, AXs);
         dfree(m.st, d.AXr); dfree(m.st, d.AXk);
         dfree(m.st, slots.A); dfree(m.st, slots.bA); dfree(m.st, slots.ks); dfree(m.st, slots.coef0);
+        dfree(m.st, d.Tc); dfree(m.st, d.AnewCols);
         chains_ready = false;
     }
     // (re)allocate the sweep vectors / partial buffers for FS chain slots over the current (n, p)
@@ -289,6 +292,7 @@ Engine::Engine(int device)
     d_->h_done = c->h_int;
     d_->h_l = c->h_int + MAXC;
     d_->h_tie = c->h_int + 2 * MAXC;
+    d_->h_ks = c->h_int + 3 * MAXC;
     d_->h_coef0 = c->h_dbl;
     d_->h_loss = c->h_dbl + MAXC;
 }
@@ -305,6 +309,7 @@ Engine::~Engine()
     m.free_sweep_buffers();
     if (m.x_owned) dfree(m.st, m.X);
     dfree(m.st, m.y); dfree(m.st, m.w);
+    dfree(m.st, m.gidx); dfree(m.st, m.gsz);
     cudaStreamSynchronize(m.st);
     release_context(m.ctx);
     delete d_;
@@ -681,6 +686,31 @@ void Engine::normalize(int data_type, bool is_normal)
     }
 }
 
+void Engine::set_groups(const std::vector<int> &g_index)
+{
+    Impl &m = *d_;
+    if (sharded_) throw EngineError{"group selection is not available in column-sharded mode"};
+    const int p = m.p, N = (int)g_index.size();
+    if (N < 1 || N > p) throw EngineError{"g_index must hold between 1 and p group starts"};
+    if (g_index[0] != 0) throw EngineError{"g_index must start at column 0"};
+    g_index_ = g_index;
+    g_size_.assign((size_t)N, 0);
+    for (int g = 0; g < N; g++) {
+        const int next = g + 1 < N ? g_index[(size_t)g + 1] : p;  // Data.h:53-61
+        if (next <= g_index[(size_t)g]) throw EngineError{"g_index must be strictly ascending"};
+        g_size_[(size_t)g] = next - g_index[(size_t)g];
+        if (g_size_[(size_t)g] > GMAX) throw EngineError{"groups of more than 8 variables are not supported"};
+    }
+    n_groups_ = N;
+    dfree(m.st, m.gidx);
+    dfree(m.st, m.gsz);
+    m.gidx = dalloc<int>(m.st, (size_t)N);
+    m.gsz = dalloc<int>(m.st, (size_t)N);
+    CUDA_CHECK(cudaMemcpyAsync(m.gidx, g_index_.data(), (size_t)N * 4, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.gsz, g_size_.data(), (size_t)N * 4, cudaMemcpyHostToDevice, m.st));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+}
+
 void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter, bool warm_start,
                           const std::vector<int> &always_select)
 {
@@ -688,7 +718,19 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     const int n = m.n, p = m.p;
     if (K < 0 || K > MAXC - 1) throw EngineError{"K (nfolds) must be in [0, 15]"};
     if (max_iter < 1 || max_iter > MAX_HIST - 2) throw EngineError{"max_iter must be in [1, 64]"};
-    if (kcap < 1 || kcap > p_model()) throw EngineError{"support size must be in [1, p]"};
+    const bool grp = grouped();
+    if (kcap < 1 || kcap > (grp ? n_groups_ : p_model())) throw EngineError{"support size must be in [1, p]"};
+    m.Tmax = kcap;
+    if (grp) {
+        // sparsity levels count groups; the column capacity of a support is the size of the kcap widest groups
+        std::vector<int> sz = g_size_;
+        std::sort(sz.begin(), sz.end(), [](int a, int b) { return a > b; });
+        int cols = 0;
+        for (int g = 0; g < kcap; g++) cols += sz[(size_t)g];
+        kcap = cols;
+        for (int j : always_select)
+            if (j < 0 || j >= n_groups_) throw EngineError{"always_select must hold group numbers in [0, number of groups)"};
+    }
     m.free_chain_buffers();
     m.K = K;
     m.nchains = 1 + K;
@@ -758,6 +800,16 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     d.CLcap = CLMAX;
     d.CLcap = chain_cluster_size(d, kcap, 1);  // the largest cluster any batch of this problem can ask for
     d.Spart = d.CLcap > 1 ? dalloc<double>(m.st, (size_t)C * d.CLcap * d.nmat * d.ldA * d.ldA) : nullptr;
+    d.grouped = grp ? 1 : 0;
+    d.N = n_groups_;
+    d.gidx = m.gidx;
+    d.gsz = m.gsz;
+    if (grp) {
+        d.Tc = dalloc<int>(m.st, MAXC);
+        d.AnewCols = dalloc<int>(m.st, (size_t)MAXC * kcap);
+        CUDA_CHECK(cudaMemsetAsync(d.Tc, 0, MAXC * 4, m.st));
+        CUDA_CHECK(cudaMemsetAsync(d.AnewCols, 0, (size_t)MAXC * kcap * 4, m.st));
+    }
     m.slots.A = dalloc<int>(m.st, (size_t)NSLOT * kcap);
     m.slots.bA = dalloc<double>(m.st, (size_t)NSLOT * kcap);
     m.slots.ks = dalloc<int>(m.st, NSLOT);
@@ -778,7 +830,14 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     CUDA_CHECK(cudaMemsetAsync(d.XA, 0, (size_t)C * n * d.ldA * 8, m.st));
 
     // ---- x_j.x_j over each chain's train rows (utilities.cpp:153-165, Metric.h:108-129); gaussian only
-    if (family_ == FAM_LM) {
+    if (family_ == FAM_LM && grp) {
+        // group blocks X_g^T X_g / n are accumulated by group_sacrifice_kernel itself: W = 1/n on the chain's train rows
+        std::vector<double> ind((size_t)m.npad * d.FS, 0.0);
+        for (int c = 0; c < C; c++)
+            for (int r = 0; r < ntrain[c]; r++) ind[(size_t)rows[(size_t)c * n + r] * d.FS + c] = 1.0 / (double)ntrain[c];
+        CUDA_CHECK(cudaMemcpyAsync(d.W, ind.data(), ind.size() * 8, cudaMemcpyHostToDevice, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));  // `ind` must outlive the copy
+    } else if (family_ == FAM_LM) {
         d.xtx = dalloc<double>(m.st, (size_t)C * d.pstride);
         std::vector<double> ind((size_t)m.npad * d.FS, 0.0);
         for (int c = 0; c < C; c++)
@@ -876,13 +935,13 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
     Impl &m = *d_;
     if (!m.chains_ready) throw EngineError{"run_batch before setup_chains"};
     Dev &d = m.d;
-    if (T < 1 || T > d.kcap) throw EngineError{"sparsity level outside [1, kcap]"};
+    if (T < 1 || T > m.Tmax) throw EngineError{"sparsity level outside [1, kcap]"};
     if (chains.empty() || (int)chains.size() > m.nchains) throw EngineError{"bad chain set"};
     BatchDesc b{};
     b.nch = (int)chains.size();
     b.T = T;
     b.new_path_step = new_path_step ? 1 : 0;
-    b.CL = chain_cluster_size(d, T, b.nch);
+    b.CL = chain_cluster_size(d, d.grouped ? std::min(d.kcap, T * GMAX) : T, b.nch);
     int cmin = MAXC, cmax = -1;
     for (int i = 0; i < b.nch; i++) {
         if (chains[i] < 0 || chains[i] >= m.nchains) throw EngineError{"chain id out of range"};
@@ -918,13 +977,31 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         const char *e = std::getenv("BESS_B200_FUSE_TOPK");
         return !(e && e[0] == '0');
     }();
-    const bool fused_mode = fuse_topk && !sharded_ && d.p <= TOPK_LMAX;
+    const bool fused_mode = fuse_topk && !sharded_ && !d.grouped && d.p <= TOPK_LMAX;
     d.gate = d.n_active;
     int enq = 0;
     bool all = false;
     while (!all && enq < d.max_iter) {
         const int group = std::min(enq == 0 ? 3 : 2, d.max_iter - enq);
         for (int q = 0; q < group; q++) {
+            if (d.grouped) {
+                // group selection: sweep + group sacrifice in one kernel, top-k over the groups, groups -> columns
+                sp = m.span_begin(1);
+                launch_group_sacrifice(d, b, m.st);
+                m.span_end(sp);
+                if (m.n_always)
+                    launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
+                sp = m.span_begin(3);
+                launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.N, T, cmax - cmin + 1,
+                            d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride,
+                            m.st, d.gate);
+                launch_group_expand(d, b, m.st);
+                m.span_end(sp);
+                sp = m.span_begin(4);
+                launch_chain_fit(d, b, m.st);
+                m.span_end(sp);
+                continue;
+            }
             sp = m.span_begin(1);
             launch_dual_sweep(d, mode, m.st);
             m.span_end(sp);
@@ -981,6 +1058,7 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         }
         CUDA_CHECK(cudaMemcpyAsync(m.h_done, d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
         CUDA_CHECK(cudaMemcpyAsync(m.h_l, d.l, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        if (d.grouped) CUDA_CHECK(cudaMemcpyAsync(m.h_ks, d.ks, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
         CUDA_CHECK(cudaMemcpyAsync(m.h_tie, d.tie_acc, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
         CUDA_CHECK(cudaMemcpyAsync(m.h_coef0, d.coef0, MAXC * sizeof(double), cudaMemcpyDeviceToHost, m.st));
         CUDA_CHECK(cudaMemcpyAsync(m.h_A, d.A, (size_t)MAXC * d.kcap * sizeof(int), cudaMemcpyDeviceToHost, m.st));
@@ -999,8 +1077,9 @@ void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step
         out.chain_ids[i] = c;
         out.l[i] = m.h_l[c];
         out.coef0[i] = m.h_coef0[c];
-        out.A[i].assign(m.h_A + (size_t)c * d.kcap, m.h_A + (size_t)c * d.kcap + T);
-        out.bA[i].assign(m.h_bA + (size_t)c * d.kcap, m.h_bA + (size_t)c * d.kcap + T);
+        const int ks = d.grouped ? m.h_ks[c] : T;  // columns in the support (== T without group structure)
+        out.A[i].assign(m.h_A + (size_t)c * d.kcap, m.h_A + (size_t)c * d.kcap + ks);
+        out.bA[i].assign(m.h_bA + (size_t)c * d.kcap, m.h_bA + (size_t)c * d.kcap + ks);
         const int iters = std::min(m.h_l[c], d.max_iter);
         stats_.n_pdas_iters += iters;
         stats_.n_boundary_ties += m.h_tie[c];

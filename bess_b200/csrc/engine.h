@@ -19,6 +19,7 @@ namespace bess {
 constexpr int MAXC = 16;      // max chains = 1 + K folds
 constexpr int PROF_NCAT = 8;
 constexpr int MAX_HIST = 66;  // max_iter + 2 columns of A_list (Algorithm.h:142)
+constexpr int GMAX = 8;       // widest group of variables in group selection (gsize > 1)
 constexpr int NSLOT = 4;      // snapshot slots of Engine::chain_state
 enum { STATE_ZERO = 0, STATE_SAVE = 1, STATE_LOAD = 2 };
 
@@ -88,6 +89,12 @@ public:
     // ---- Data ctor normalisation (Data.h:41-68, normalize.cpp) + add_weight for gaussian (Data.h:70-77).
     void normalize(int data_type, bool is_normal);
 
+    // ---- group selection (R: group.index, Python: GroupPdas*).  g_index: first column of every group, ascending from 0
+    // (Data.h:53-61); call after normalize() and before setup_chains().  From then on sparsity levels, top-k results and
+    // always_select count GROUPS; supports / coefficients reported by run_batch are still per column.
+    void set_groups(const std::vector<int> &g_index);
+    int n_groups() const { return n_groups_; }
+
     // ---- CV folds (Metric.h:49-129).  fold_of_row[i] in [0,K) or K == 0 for no CV.  Also (re)allocates all
     // chain workspaces for supports up to kcap.
     void setup_chains(int K, const int *fold_of_row, int kcap, int max_iter, bool warm_start,
@@ -114,6 +121,7 @@ public:
 
     int n() const { return n_; }
     int p() const { return p_; }
+    bool grouped() const { return n_groups_ > 0; }
     int family() const { return family_; }
     const std::vector<double> &x_mean() const { return h_xmean_; }
     const std::vector<double> &x_norm() const { return h_xnorm_; }
@@ -126,6 +134,8 @@ private:
     Impl *d_ = nullptr;
     int n_ = 0, p_ = 0, family_ = 0;
     int S_ = 1;
+    int n_groups_ = 0;
+    std::vector<int> g_index_, g_size_;
     std::vector<double> h_xmean_, h_xnorm_;
     double y_mean_ = 0.0;
     // sharded mode

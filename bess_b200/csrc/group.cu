@@ -1,0 +1,177 @@
+// Group selection (gsize > 1): R bess(..., group.index =), Python GroupPdas* -- algorithm_type 2 (GPDAS) / 3 (GL0L2).
+//
+// A sparsity level counts GROUPS.  get_A (Algorithm.h:1097-1129 lm, :1206-1263 logistic, :1324-1367 poisson,
+// :1497-1568 cox) scores group g by
+//     bd_g = || Phi_g beta_g + Phi_g^{-1} d_g ||^2 / gsize_g,   Phi_g = (M_g + 2 lambda I)^{1/2},
+// with d = X^T (gradient vector) - 2 lambda beta and M_g the k_g x k_g block of the model's curvature on the group's
+// columns:  lm  X_g^T X_g / n  (utilities.cpp:142-165);  logistic / poisson  X_g^T diag(h) X_g;  cox  X_g^T H X_g with the
+// dense n x n partial-likelihood Hessian H, which in risk-set form is
+//     sum_i omega_i x_ia x_ib  -  sum_{k: event} (e_k / S_k^2) s_a(k) s_b(k),    s_a(k) = sum_{i >= k} theta_i x_ia.
+// The matrix square root (Eigen's Schur-based sqrt(), utilities.cpp:147) of an SPD block is U diag(sqrt(ev)) U^T, so with
+// M_g + 2 lambda I = U diag(ev) U^T:   bd_g = sum_i ( sqrt(ev_i) (U^T beta_g)_i + (U^T d_g)_i / sqrt(ev_i) )^2 / gsize_g.
+//
+// group_sacrifice_kernel fuses sweep and epilogue: one thread per (group, chain) walks all rows once (neighbouring
+// threads own neighbouring column ranges of the row-major design, so the loads coalesce), accumulating d_g, the packed
+// block M_g and -- for cox, walking the rows from the last to the first -- the running risk-set sums, then diagonalises
+// the block with cyclic Jacobi rotations.  The gradient vectors (G, W, TH, C2; zero on rows outside the chain's train
+// mask) are the ones chain_begin / chain_fit already publish for the column-wise sweep.
+// group_expand_kernel turns the T selected groups into the column list the active-set fit works on (find_ind,
+// utilities.cpp:113-130).
+#include <cfloat>
+#include <cmath>
+
+#include "device_utils.cuh"
+#include "kernels.cuh"
+
+namespace bess {
+
+constexpr int GS_NT = 128;
+
+// cyclic Jacobi on a symmetric g x g matrix (g <= GMAX): A -> diag(ev), U = eigenvectors in columns
+__device__ void jacobi_eig(double (*A)[GMAX], double (*U)[GMAX], int g)
+{
+    for (int i = 0; i < g; i++)
+        for (int j = 0; j < g; j++) U[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rotated = 0;
+        for (int p = 0; p < g - 1; p++)
+            for (int q = p + 1; q < g; q++) {
+                const double apq = A[p][q];
+                // a rotation that cannot change the diagonal any more is skipped
+                if (fabs(apq) <= 1e-18 * sqrt(fabs(A[p][p] * A[q][q])) || apq == 0.0) continue;
+                rotated = 1;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < g; k++) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - s * akq;
+                    A[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < g; k++) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - s * aqk;
+                    A[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < g; k++) {
+                    const double ukp = U[k][p], ukq = U[k][q];
+                    U[k][p] = c * ukp - s * ukq;
+                    U[k][q] = s * ukp + c * ukq;
+                }
+            }
+        if (!rotated) break;
+    }
+}
+
+template <bool COX>
+__global__ void __launch_bounds__(GS_NT) group_sacrifice_kernel(const Dev d, const BatchDesc b)
+{
+    if (d.gate && *d.gate == 0) return;
+    const int c = b.chain[blockIdx.y];
+    if (d.done[c]) return;
+    const int g = blockIdx.x * GS_NT + threadIdx.x;
+    if (g >= d.N) return;
+    const int j0 = d.gidx[g], gs = d.gsz[g];
+    const int FS = d.FS;
+    double dv[GMAX], sv[GMAX], M[GMAX * (GMAX + 1) / 2];
+#pragma unroll
+    for (int a = 0; a < GMAX; a++) dv[a] = 0.0, sv[a] = 0.0;
+#pragma unroll
+    for (int e = 0; e < GMAX * (GMAX + 1) / 2; e++) M[e] = 0.0;
+    for (int ii = 0; ii < d.n; ii++) {
+        const int i = COX ? d.n - 1 - ii : ii;
+        const double gi = d.G[(size_t)i * FS + c], wi = d.W[(size_t)i * FS + c];
+        double th = 0.0, c2 = 0.0;
+        if (COX) {
+            th = d.TH[(size_t)i * FS + c];
+            c2 = d.C2[(size_t)i * FS + c];
+        }
+        if (gi == 0.0 && wi == 0.0 && th == 0.0) continue;  // row outside the chain's train mask
+        const double *xr = d.X + (size_t)i * d.ldx + j0;
+        double x[GMAX];
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) x[a] = a < gs ? __ldg(xr + a) : 0.0;
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) {
+            dv[a] = fma(x[a], gi, dv[a]);
+            if (COX) sv[a] = fma(x[a], th, sv[a]);
+        }
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) {
+            const double wa = wi * x[a];
+#pragma unroll
+            for (int bb = a; bb < GMAX; bb++, e++) {
+                double v = fma(wa, x[bb], M[e]);
+                if (COX) v = fma(-c2 * sv[a], sv[bb], v);
+                M[e] = v;
+            }
+        }
+    }
+    // M_g + 2 lambda I, d_g - 2 lambda beta_g
+    double A[GMAX][GMAX], U[GMAX][GMAX], bg[GMAX];
+    {
+        int e = 0;
+        for (int a = 0; a < GMAX; a++)
+            for (int bb = a; bb < GMAX; bb++, e++)
+                if (bb < gs) A[a][bb] = A[bb][a] = M[e] + (a == bb ? 2.0 * d.lambda : 0.0);
+    }
+    for (int a = 0; a < gs; a++) {
+        bg[a] = d.betaD[(size_t)c * d.pstride + j0 + a];
+        dv[a] -= 2.0 * d.lambda * bg[a];
+    }
+    double bd;
+    if (gs == 1) {
+        const double phi = sqrt(A[0][0]);
+        const double t = phi * bg[0] + dv[0] / phi;
+        bd = t * t;
+    } else {
+        jacobi_eig(A, U, gs);
+        bd = 0.0;
+        for (int q = 0; q < gs; q++) {
+            double ub = 0.0, ud = 0.0;
+            for (int a = 0; a < gs; a++) {
+                ub = fma(U[a][q], bg[a], ub);
+                ud = fma(U[a][q], dv[a], ud);
+            }
+            const double r = sqrt(A[q][q]);
+            const double t = r * ub + ud / r;
+            bd = fma(t, t, bd);
+        }
+        bd /= (double)gs;
+    }
+    d.bd[(size_t)c * d.pstride + g] = bd;
+}
+
+// find_ind (utilities.cpp:113-130): the T selected groups (ascending) -> their columns, in order
+__global__ void group_expand_kernel(const Dev d, const BatchDesc b)
+{
+    if (d.gate && *d.gate == 0) return;
+    const int c = b.chain[blockIdx.x];
+    if (d.done[c]) return;
+    if (threadIdx.x != 0) return;
+    const int *An = d.Anew + (size_t)c * d.kcap;
+    int *out = d.AnewCols + (size_t)c * d.kcap;
+    int cnt = 0;
+    for (int a = 0; a < b.T; a++) {
+        const int g = An[a];
+        const int j0 = d.gidx[g], gs = d.gsz[g];
+        for (int q = 0; q < gs && cnt < d.kcap; q++) out[cnt++] = j0 + q;
+    }
+    d.Tc[c] = cnt;
+}
+
+void launch_group_sacrifice(const Dev &d, const BatchDesc &b, cudaStream_t st)
+{
+    const dim3 grid((unsigned)((d.N + GS_NT - 1) / GS_NT), (unsigned)b.nch);
+    if (d.family == FAM_COX) group_sacrifice_kernel<true><<<grid, GS_NT, 0, st>>>(d, b);
+    else group_sacrifice_kernel<false><<<grid, GS_NT, 0, st>>>(d, b);
+    CUDA_CHECK(cudaGetLastError());
+}
+void launch_group_expand(const Dev &d, const BatchDesc &b, cudaStream_t st)
+{
+    group_expand_kernel<<<b.nch, 32, 0, st>>>(d, b);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace bess

@@ -59,6 +59,14 @@ struct Dev {
     double *cw;         // [MAXC][CLMAX][4][ldA] cluster exchange vectors
     // column-sharded mode (multi-GPU axis B): X holds columns [col_lo, col_lo + p) of a wider design; supports (A, Anew,
     // hist) carry GLOBAL column indices, betaD / bd / xtx are local
+    // group selection (group.cu): columns [gidx[g], gidx[g] + gsz[g]) form group g.  Anew / hist / the top-k work on
+    // group ids, A / bA / ks / AnewCols on columns; kcap is the COLUMN capacity of a support.
+    int grouped;        // 0: every column is its own group, the fields below are unused
+    int N;              // number of groups
+    const int *gidx;    // [N]
+    const int *gsz;     // [N]
+    int *Tc;            // [MAXC] number of columns of the groups chosen by the last top-k
+    int *AnewCols;      // [MAXC][kcap] those columns (find_ind, utilities.cpp:113-130)
     int sharded;
     int col_lo;
     double *AXr;        // [MAXC][n][ldXr] active columns of this iteration for ALL rows, summed over ranks (ldXr = T)
@@ -128,6 +136,9 @@ void launch_gather_active(const Dev &d, const BatchDesc &b, double *AXs, cudaStr
 void launch_gather_owned_cols(const double *X, long long ldx, int n, int p_local, long long col_lo, const int *sel, int m,
                               double *Xn, long long ldn, cudaStream_t st);
 void launch_chain_begin(const Dev &d, const BatchDesc &b, cudaStream_t st);
+// ---- group selection (group.cu): sweep + group sacrifice in one kernel -> d.bd[chain][group]; selected groups -> columns
+void launch_group_sacrifice(const Dev &d, const BatchDesc &b, cudaStream_t st);
+void launch_group_expand(const Dev &d, const BatchDesc &b, cudaStream_t st);
 // ---- explicit warm-start state of a chain.  pgs_path re-seeds Algorithm::beta_init / coef0_init by hand (zeros at the
 // start of every line search, path.cpp:590-592; the snapshot after the first fit for the backward walk of seq_search,
 // path.cpp:1040-1041, 1084-1085; a stale value for its last fit, path.cpp:1212-1217), so the driver needs to save,

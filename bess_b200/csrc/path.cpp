@@ -59,7 +59,8 @@ struct Driver {
     double ic_formula(double train_loss, int T) const
     {
         double pen;
-        const double dn = (double)n, dp = (double)p;
+        // algorithm_type 2 / 3: log(g_num) and group_df = sparsity level (Metric.h:230-254); equal to p and s without groups
+        const double dn = (double)n, dp = (double)((a.algorithm_type == 2 || a.algorithm_type == 3) && eng.grouped() ? eng.n_groups() : p);
         switch (a.ic_type) {
             case 1: pen = 2.0 * T; break;
             case 2: pen = std::log(dn) * T; break;
@@ -636,17 +637,26 @@ void bess_run(const BessArgs &a, BessResult &out)
     if (a.path_type == 1)
         for (double l : a.lambda_seq)
             if (!(l >= 0.0)) throw EngineError{"lambda_seq entries must be >= 0"};
-    if (!a.g_index.empty()) {
-        if ((int)a.g_index.size() != a.p) throw EngineError{"group selection (gsize > 1) is outside this build's scope"};
+    // g_index: first column of every group (bess.R:540, linear.py:238-254).  p entries = no group structure.
+    const bool grouped = !a.g_index.empty() && (int)a.g_index.size() != a.p;
+    if (!a.g_index.empty() && !grouped)
         for (int j = 0; j < a.p; j++)
-            if (a.g_index[(size_t)j] != j) throw EngineError{"g_index must be 0..p-1 (no groups)"};
+            if (a.g_index[(size_t)j] != j) throw EngineError{"g_index with p entries must be 0..p-1"};
+    if (grouped) {
+        if (a.algorithm_type != 2 && a.algorithm_type != 3)
+            throw EngineError{"group selection needs algorithm_type 2 (GPDAS) or 3 (GL0L2)"};
+        // the reference un-screens a grouped fit by group number (bess.cpp:186-209 writes beta(screening_A(i))), which
+        // scrambles the coefficients; there is no defined behaviour to reproduce
+        if (a.is_screening) throw EngineError{"screening together with group selection is not supported"};
+        if (a.world > 1) throw EngineError{"group selection is not available in column-sharded mode"};
     }
     if (a.is_cv && (a.K < 2 || a.K > MAXC - 1)) throw EngineError{"K (nfolds) must be in [2, 15]"};
     const bool shard = a.world > 1;
     const long long p_all = shard ? a.p_total : a.p;
     if (shard && a.x_on_device == false && a.x == nullptr) throw EngineError{"sharded fit: x shard is null"};
+    const long long n_units = grouped ? (long long)a.g_index.size() : p_all;  // what s.list / always_select count
     for (int j : a.always_select)
-        if (j < 0 || j >= p_all) throw EngineError{"always_select index out of range"};
+        if (j < 0 || j >= n_units) throw EngineError{"always_select index out of range"};
 
     Engine eng(a.device);
     eng.set_profiling(a.profile);
@@ -666,8 +676,9 @@ void bess_run(const BessArgs &a, BessResult &out)
         }
     }
     eng.normalize(a.data_type, a.is_normal);
+    if (grouped) eng.set_groups(a.g_index);
 
-    const long long p = eng.p_model();
+    const long long p = grouped ? (long long)eng.n_groups() : eng.p_model();
     int kcap;
     if (a.path_type == 1) {
         if (a.sequence.empty()) throw EngineError{"sequence (s.list) is empty"};
@@ -677,7 +688,7 @@ void bess_run(const BessArgs &a, BessResult &out)
         if (a.s_min < 1 || a.s_max < a.s_min) throw EngineError{"need 1 <= s_min <= s_max"};
         kcap = a.s_max;
     }
-    if (kcap > p) throw EngineError{"sparsity level exceeds the number of (screened) columns"};
+    if (kcap > p) throw EngineError{"sparsity level exceeds the number of (screened) columns / groups"};
 
     std::vector<int> folds;
     if (a.is_cv) {

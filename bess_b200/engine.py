@@ -80,6 +80,26 @@ class GpuEngine:
         _lib.check(self._lib.bessgpu_get_norm(self._h, _d(xm), _d(xn), C.byref(ym)))
         return xm, xn, ym.value
 
+    def set_groups(self, g_index):
+        """Group selection: g_index = first column of every group; levels / kcap / always_select then count groups."""
+        g = np.ascontiguousarray(g_index, dtype=np.int32)
+        _lib.check(self._lib.bessgpu_set_groups(self._h, _i(g), g.size))
+        self._group_sizes = np.diff(np.append(g, self.p))
+
+    def run_batch_groups(self, T, chains, new_path_step=True, lam=0.0):
+        """run_batch for grouped designs (and / or a ridge level): supports come back as per-chain lists."""
+        ch = np.ascontiguousarray(chains, dtype=np.int32)
+        nch = ch.size
+        sizes = getattr(self, "_group_sizes", np.ones(self.p, dtype=np.int64))
+        ld = int(np.sort(sizes)[::-1][:T].sum())
+        l, ks = np.zeros(nch, dtype=np.int32), np.zeros(nch, dtype=np.int32)
+        c0 = np.zeros(nch)
+        A = np.zeros((nch, ld), dtype=np.int32)
+        bA = np.zeros((nch, ld))
+        _lib.check(self._lib.bessgpu_run_batch_groups(self._h, T, _i(ch), nch, int(new_path_step), float(lam), _i(l),
+                                                      _d(c0), _i(ks), _i(A), _d(bA), ld))
+        return dict(l=l, coef0=c0, A=[A[i, :ks[i]].copy() for i in range(nch)], bA=[bA[i, :ks[i]].copy() for i in range(nch)])
+
     def setup_chains(self, K, fold_of_row, kcap, max_iter=20, warm_start=True, always_select=()):
         f = np.ascontiguousarray(fold_of_row if fold_of_row is not None else np.zeros(self.n), dtype=np.int32)
         alw = np.ascontiguousarray(list(always_select), dtype=np.int32)

@@ -127,6 +127,10 @@ int bessgpu_screen_local(bessgpu_handle *h, int screening_size, const int *alway
 int bessgpu_gather_columns(bessgpu_handle *h, const int *cols, const int *pos, int m, double *dst_dev, long long ld);
 /* Data.h:41-77 + normalize.cpp:20-86 */
 int bessgpu_normalize(bessgpu_handle *h, int data_type, int is_normal);
+/* group selection (Data.h:53-61: g_index = first column of every group, ascending from 0; at most 8 variables per
+ * group).  Call after bessgpu_normalize and before bessgpu_setup_chains; sparsity levels, kcap and always_select then
+ * count groups (Algorithm.h:1097-1129, 1206-1263, 1324-1367, 1497-1568; utilities.cpp:113-177). */
+int bessgpu_set_groups(bessgpu_handle *h, const int *g_index, int n_groups);
 int bessgpu_get_norm(bessgpu_handle *h, double *x_mean_out, double *x_norm_out, double *y_mean_out);
 /* Metric.h:49-129 (fold row lists, per-fold x_j.x_j) + workspace for supports up to kcap */
 int bessgpu_setup_chains(bessgpu_handle *h, int K, const int *fold_of_row, int kcap, int max_iter, int warm_start,
@@ -134,6 +138,10 @@ int bessgpu_setup_chains(bessgpu_handle *h, int K, const int *fold_of_row, int k
 /* Algorithm::fit (Algorithm.h:113-171) for `nch` chains at sparsity T in lock-step.  Outputs are [nch] / [nch][T]. */
 int bessgpu_run_batch(bessgpu_handle *h, int T, const int *chains, int nch, int new_path_step, int *l_out,
                       double *coef0_out, int *A_out, double *beta_A_out);
+/* the same with a ridge level and supports of different width per chain (group selection): ks_out[i] columns of chain
+ * i's support are written to A_out / beta_A_out rows of leading dimension ld */
+int bessgpu_run_batch_groups(bessgpu_handle *h, int T, const int *chains, int nch, int new_path_step, double lambda,
+                             int *l_out, double *coef0_out, int *ks_out, int *A_out, double *beta_A_out, int ld);
 /* Metric::train_loss (kind 0) / fold test loss (kind 1) of a chain's current model */
 int bessgpu_losses(bessgpu_handle *h, const int *chain, const int *kind, const int *fold, int njobs, double *out);
 /* roofline probe: mean device time (ms) of one dual-sweep launch over all chain slots and its algorithmic bytes */

@@ -73,3 +73,25 @@ def load_pgs_golden(name):
     n = g["x"].shape[0]
     g["full_fits"] = g["fits"][g["fits"][:, 2] == n][:, :2]  # (sparsity level, lambda) of the full-data fits, in order
     return g
+
+
+GROUP_DIR = os.path.join(GOLDEN_DIR, "group")
+
+
+def group_golden_names():
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GROUP_DIR, "*.npz")))
+
+
+def load_group_golden(name):
+    """tests/golden/group/*.npz (made by tests/golden/group/make_group.py from the real reference, gsize > 1)."""
+    g = dict(np.load(os.path.join(GROUP_DIR, name + ".npz")))
+    (g["model_type"], g["data_type"], g["algorithm_type"], g["path_type"], g["is_cv"], g["K"], g["ic_type"], g["s_min"],
+     g["s_max"], g["pgs"], g["n_lambda"], g["powell_path"]) = (int(v) for v in g["meta"])
+    g["is_cv"], g["pgs"] = bool(g["is_cv"]), bool(g["pgs"])
+    g["seq"] = np.arange(g["s_min"], g["s_max"] + 1)
+    if g["pgs"]:
+        g["kw"] = dict(lambda_min=float(g["lambdas"][0]), lambda_max=float(g["lambdas"][1]), n_lambda=g["n_lambda"],
+                       powell_path=g["powell_path"])
+    else:
+        g["kw"] = dict(lambda_seq=g["lambdas"])
+    return g

@@ -9,8 +9,8 @@ import pytest
 
 from oracle import pdas_oracle as orc
 from oracle import ref as refso
-from tests.helpers import (FULL_CONFIGS, RTOL, assert_same_support, full_checksum, golden_names, load_full_golden,
-                           load_golden, load_pgs_golden, pgs_golden_names, rel_err)
+from tests.helpers import (FULL_CONFIGS, RTOL, assert_same_support, full_checksum, golden_names, group_golden_names,
+                           load_full_golden, load_golden, load_group_golden, load_pgs_golden, pgs_golden_names, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -416,3 +416,66 @@ def test_pgs_path_against_live_reference():
                         cv_seed=123, lambda_min=0.001, lambda_max=1.0, n_lambda=6, powell_path=pp)
         _check_final(out, r)
         assert abs(out["lam"] - r["lambda_"]) <= 1e-12 * abs(r["lambda_"])
+
+
+@pytest.mark.parametrize("name", group_golden_names())
+def test_group_selection_golden(name):
+    """Group selection (gsize > 1; R group.index, Python GroupPdas*, algorithm_type 2 / 3): all four families, sequential /
+    golden-section / Powell paths, CV, weights, always-include, ridge levels -- against the real reference."""
+    from bess_b200 import cbess
+    g = load_group_golden(name)
+    out = cbess.fit(g["x"], g["y"], g["data_type"], g["weight"], True, g["algorithm_type"], g["model_type"], 20, 2,
+                    g["path_type"], True, g["ic_type"], g["is_cv"], g["K"], g["seq"], g["s_min"], g["s_max"], False, 1,
+                    always_select=g["always"], fold_of_row=g["fold_of_row"] if g["is_cv"] else None, g_index=g["g_index"],
+                    **g["kw"])
+    _check_final(out, g)
+    assert abs(out["lam"] - float(g["lam"])) <= 1e-12 * max(abs(float(g["lam"])), 1e-300)
+    assert out["stats"]["n_boundary_ties"] == 0
+
+
+@pytest.mark.parametrize("fam", ["gaussian", "binomial", "poisson", "cox"])
+def test_group_fit_level_parity_with_oracle(fam):
+    """Algorithm::fit granularity with groups: every chain of a batch (full data + folds), warm-started over three
+    levels and a ridge level, against oracle.pdas_fit -- selected columns, iteration counts, coefficients."""
+    from bess_b200 import cbess
+    from bess_b200.engine import GpuEngine
+    from bess_b200.gen_data import gen_data
+    model_type, data_type = FAM[fam]
+    n, p, K = 260, 402, 2
+    d = gen_data(n, p, fam, 5, seed=17)
+    w = np.random.default_rng(17).uniform(0.5, 1.5, n)
+    gi, sizes, k = [0], [3, 1, 8, 2, 5], 0
+    while gi[-1] + sizes[k % 5] < p:
+        gi.append(gi[-1] + sizes[k % 5])
+        k += 1
+    gi = np.array(gi, dtype=np.int32)
+    fold = cbess.cv_fold_ids(n, K, 123)
+    eng = GpuEngine()
+    eng.load(d.x, d.y, w, model_type)
+    eng.normalize(data_type, True)
+    eng.set_groups(gi)
+    data = orc.make_data(d.x, d.y, w, data_type, True, model_type)
+    Ts = [1, 2, 4]
+    eng.setup_chains(K, fold, max(Ts), 20, True)
+    st = orc.PathState(data, model_type, 3, True, K, fold, 20, True, g_index=gi, algorithm_type=2)
+    chains = list(range(K + 1))
+    masks = [st.full_mask] + st.train_masks
+    xtxs = [st.xtx_full] + st.xtx_folds
+    binit = [np.zeros(p) for _ in chains]
+    c0_full = 0.0
+    lam = 0.0 if fam == "cox" else 0.02
+    for T in Ts:
+        r = eng.run_batch_groups(T, chains, True, lam)
+        c0_level = c0_full
+        for ci in chains:
+            o = orc.pdas_fit(data, model_type, T, binit[ci], c0_level, masks[ci], xtxs[ci], 20, lam=lam, groups=st.groups)
+            assert o.min_gap > 1e-9
+            assert r["A"][ci].tolist() == o.A.tolist()
+            assert int(r["l"][ci]) == o.l
+            assert rel_err(r["bA"][ci], o.beta[o.A]) < RTOL
+            assert abs(r["coef0"][ci] - o.coef0) <= RTOL * max(1.0, abs(o.coef0))
+            binit[ci] = o.beta
+            if ci == 0:
+                c0_full = o.coef0
+    assert eng.stats()["n_boundary_ties"] == 0
+    eng.close()

@@ -3,8 +3,8 @@ import numpy as np
 import pytest
 
 from oracle import pdas_oracle as orc
-from tests.helpers import (RTOL, assert_same_support, golden_names, load_golden, load_pgs_golden, pgs_golden_names,
-                           rel_err)
+from tests.helpers import (RTOL, assert_same_support, golden_names, group_golden_names, load_golden, load_group_golden,
+                           load_pgs_golden, pgs_golden_names, rel_err)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -50,3 +50,20 @@ def test_oracle_pgs_path_matches_reference(name):
     assert abs(out["train_loss"] - g["train_loss"]) <= RTOL * abs(g["train_loss"])
     assert abs(out["ic"] - g["ic"]) <= RTOL * abs(g["ic"])
     assert abs(out["lam"] - g["lam"]) <= 1e-12 * abs(g["lam"])
+
+
+@pytest.mark.parametrize("name", group_golden_names())
+def test_oracle_group_selection_matches_reference(name):
+    """Group selection (gsize > 1, algorithm_type 2 / 3): k_g x k_g Phi blocks, group top-k, find_ind, group IC."""
+    g = load_group_golden(name)
+    out = orc.bess_cpp(g["x"], g["y"], g["data_type"], g["weight"], True, g["model_type"], 20, g["path_type"], True,
+                       g["ic_type"], g["is_cv"], g["K"], g["seq"], g["s_min"], g["s_max"], False, 1,
+                       always_select=g["always"], fold_of_row=g["fold_of_row"], algorithm_type=g["algorithm_type"],
+                       g_index=g["g_index"], **g["kw"])
+    assert_same_support(out["beta"], g["beta"])
+    assert rel_err(out["beta"], g["beta"]) < RTOL
+    assert abs(out["coef0"] - g["coef0"]) <= RTOL * max(1.0, abs(g["coef0"]))
+    assert abs(out["train_loss"] - g["train_loss"]) <= RTOL * abs(g["train_loss"])
+    assert abs(out["ic"] - g["ic"]) <= RTOL * abs(g["ic"])
+    assert abs(out["lam"] - g["lam"]) <= 1e-12 * max(abs(g["lam"]), 1e-300) if "lam" in out else True
+    assert out["min_gap"] > 1e-9, "a top-k decision sits inside rounding noise"
