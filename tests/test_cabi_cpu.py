@@ -134,11 +134,13 @@ def test_frontend_argument_surface(monkeypatch):
     m = linear.L0L2Poisson(sequence=[1, 2], lambda_sequence=[0.1, 1.0])
     m.fit(x, np.ones(50))
     assert list(seen["args"][17]) == [0.1, 1.0] and list(seen["args"][16]) == [1, 2]
-    # GroupPdas: group labels -> first column of each group (linear.py:238-254); singleton groups pass, wider ones are refused
+    # GroupPdas: group labels -> first column of each group (linear.py:238-254)
     m = linear.GroupPdasLm(sequence=[1, 2])
     with pytest.raises(ValueError):
         m.fit(x, x[:, 0])
     m.fit(x, x[:, 0], group=list(range(30)))
     assert list(seen["args"][14]) == list(range(30)) and seen["args"][5] == 2
+    m.fit(x, x[:, 0], group=[i // 3 for i in range(30)])
+    assert list(seen["args"][14]) == list(range(0, 30, 3))
     with pytest.raises(ValueError):
-        m.fit(x, x[:, 0], group=[i // 2 for i in range(30)])
+        m.fit(x, x[:, 0], group=[0, 1])

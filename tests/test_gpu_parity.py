@@ -479,3 +479,19 @@ def test_group_fit_level_parity_with_oracle(fam):
                 c0_full = o.coef0
     assert eng.stats()["n_boundary_ties"] == 0
     eng.close()
+
+
+def test_frontend_group_and_bsrr_estimators():
+    """GroupPdasLm (group labels -> g_index) and L0L2Lm with the Powell path, through the estimator classes."""
+    from bess_b200.linear import GroupPdasLm, L0L2Lm
+    g = load_group_golden("lm_seq_gic")
+    p = g["x"].shape[1]
+    labels = np.searchsorted(g["g_index"], np.arange(p), side="right") - 1  # group label of every column
+    m = GroupPdasLm(path_type="seq", sequence=list(g["seq"]), ic_type="gic")
+    m.fit(g["x"], g["y"], group=labels.tolist())
+    assert rel_err(m.beta, g["beta"]) < RTOL and _close(m.ic, g["ic"])
+    q = load_pgs_golden("lm_gs_gic")
+    m = L0L2Lm(path_type="pgs", s_min=q["s_min"], s_max=q["s_max"], lambda_min=q["lambda_min"], lambda_max=q["lambda_max"],
+               ic_type="gic", powell_path=1)
+    m.fit(q["x"], q["y"])
+    assert rel_err(m.beta, q["beta"]) < RTOL and _close(m.ic, q["ic"])
