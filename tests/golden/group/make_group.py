@@ -42,6 +42,11 @@ CASES = {
     "cox_seq_gic": ("cox", 180, 150, 4, [3, 1, 4, 2], 2, 1, False, 5, 3, 1, 6, [0.0], False, (), 112),
     "cox_seq_cv": ("cox", 180, 150, 4, [2, 3], 2, 1, True, 3, 1, 1, 5, [0.0], False, (), 113),
     "cox_l0l2_seq": ("cox", 180, 150, 4, [3, 1, 4, 2], 3, 1, False, 5, 2, 1, 5, [0.0, 0.01], False, (3,), 114),
+    # every group a single variable (GroupPdas* with group = 0..p-1): algorithm_type 2 / 3 take the group code paths of the
+    # reference -- for cox the dense-Hessian branch, Algorithm.h:1497-1568 -- which must agree with the plain PDAS build
+    "single_cox_seq_cv": ("cox", 160, 120, 4, [1], 2, 1, True, 3, 1, 1, 6, [0.0], False, (), 115),
+    "single_lm_gs_cv": ("gaussian", 150, 200, 5, [1], 2, 2, True, 3, 1, 1, 12, [0.0], False, (), 116),
+    "single_logit_l0l2_seq": ("binomial", 200, 150, 4, [1], 3, 1, False, 5, 3, 1, 6, [0.01, 0.1], False, (), 117),
 }
 
 
