@@ -1249,6 +1249,11 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, con
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FitSmem sm = carve_fit_smem(smem_raw, d.ldA, d.fit_smem_doubles);
+    if (d.prev_active && *d.prev_active != 0) {
+        // speculatively enqueued behind a batch that has not finished: close this batch's gate, touch nothing
+        if (blockIdx.x == 0 && threadIdx.x == 0) *d.n_active = 0;
+        return;
+    }
     const int c = b.chain[blockIdx.x];
     // Algorithm::coef0_init is only refreshed when the path starts a new step (path.cpp:57); CV folds of the same
     // step inherit it.

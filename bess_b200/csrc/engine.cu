@@ -46,9 +46,10 @@ struct DeviceContext {
     int device = 0;
     int sm_count = 148;
     cudaStream_t st = nullptr;
-    int *h_int = nullptr;        // pinned: [4][MAXC] done, l, ks, tie
-    double *h_dbl = nullptr;     // pinned: [MAXC] coef0 + [2*MAXC] losses
-    int *h_A = nullptr;          // pinned, grow-only: [MAXC][kcap]
+    // pinned result mirrors, two of each (one per batch slot, Engine::Impl::Mirror)
+    int *h_int = nullptr;        // [2][5][MAXC] done, l, tie, ks, gate
+    double *h_dbl = nullptr;     // [2]([MAXC] coef0 + [2*MAXC] losses)
+    int *h_A = nullptr;          // grow-only: [2][MAXC][kcap]
     double *h_bA = nullptr;
     size_t cap_A = 0;
     bool in_use = false;
@@ -62,8 +63,8 @@ struct DeviceContext {
         if (h_A) cudaFreeHost(h_A);
         if (h_bA) cudaFreeHost(h_bA);
         h_A = nullptr; h_bA = nullptr; cap_A = 0;
-        CUDA_CHECK(cudaMallocHost(&h_A, count * sizeof(int)));
-        CUDA_CHECK(cudaMallocHost(&h_bA, count * sizeof(double)));
+        CUDA_CHECK(cudaMallocHost(&h_A, 2 * count * sizeof(int)));
+        CUDA_CHECK(cudaMallocHost(&h_bA, 2 * count * sizeof(double)));
         cap_A = count;
     }
 };
@@ -94,8 +95,8 @@ DeviceContext *acquire_context(int device)
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
     unsigned long long keep = ~0ULL;
     CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    CUDA_CHECK(cudaMallocHost(&c->h_int, 4 * MAXC * sizeof(int)));
-    CUDA_CHECK(cudaMallocHost(&c->h_dbl, 3 * MAXC * sizeof(double)));
+    CUDA_CHECK(cudaMallocHost(&c->h_int, 2 * 5 * MAXC * sizeof(int)));
+    CUDA_CHECK(cudaMallocHost(&c->h_dbl, 2 * 3 * MAXC * sizeof(double)));
     configure_kernels();
     c->in_use = true;
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -137,14 +138,34 @@ struct Engine::Impl {
     int *always = nullptr;
     int n_always = 0;
     StateSlots slots{};
+    // ---- batches in flight.  Two slots alternate: a batch's kernels carry a private copy of the descriptor (ridge level,
+    // gate counter), its results land in the slot's pinned mirror, so the next path step can be enqueued before the
+    // host has read the current one.
+    struct Ticket {
+        Dev d{};
+        BatchDesc b{};
+        LossDesc ld{};
+        bool has_jobs = false, fused = false, pending = false;
+        int T = 0, slot = 0, enq = 0, cmin = 0, cmax = 0;
+        long long launches = 0;
+        cudaEvent_t ev = nullptr;
+    };
+    struct Mirror {
+        int *done = nullptr, *l = nullptr, *tie = nullptr, *ks = nullptr, *gate = nullptr, *A = nullptr;
+        double *coef0 = nullptr, *loss = nullptr, *bA = nullptr;
+    };
+    Ticket tk[2];
+    Mirror mir[2];
+    unsigned long long seq = 0;
+    int *n_active2 = nullptr;  // device [2]: the alternating gate counters (Dev::n_active / Dev::prev_active)
     double *ck0 = nullptr, *ck1 = nullptr;
     int *ci0 = nullptr, *ci1 = nullptr;
     long long cstride = 0;
     // pinned host mirrors (owned by the DeviceContext)
-    int *h_done = nullptr, *h_l = nullptr, *h_tie = nullptr, *h_ks = nullptr, *h_A = nullptr;
+    int *h_A = nullptr;
     int *gidx = nullptr, *gsz = nullptr;  // group selection: device copies of Engine::g_index_ / g_size_
     int Tmax = 0;                          // largest sparsity level (in groups when grouped) the workspaces hold
-    double *h_coef0 = nullptr, *h_bA = nullptr, *h_loss = nullptr;
+    double *h_bA = nullptr;
     bool chains_ready = false;
     bool x_owned = true;
     // column-sharded mode
@@ -208,7 +229,8 @@ struct Engine::Impl {
         Impl &m = *this;
         dfree(m.st, d.rows); dfree(m.st, d.ntrain); dfree(m.st, d.ytr); dfree(m.st, d.wtr); dfree(m.st, d.ks); dfree(m.st, d.A); dfree(m.st, d.bA);
         dfree(m.st, d.coef0); dfree(m.st, d.coef0_level); dfree(m.st, d.Anew); dfree(m.st, d.hist); dfree(m.st, d.l); dfree(m.st, d.done); dfree(m.st, d.tie);
-        dfree(m.st, d.tie_acc); dfree(m.st, d.n_active);
+        dfree(m.st, d.tie_acc); dfree(m.st, n_active2);
+        d.n_active = nullptr;
         dfree(m.st, d.betaD); dfree(m.st, d.XA); dfree(m.st, d.XB); dfree(m.st, d.vec); dfree(m.st, d.Smat); dfree(m.st, d.Spart); dfree(m.st, d.cw); dfree(m.st, d.xtx);
         dfree(m.st, testrows); dfree(m.st, ntest); dfree(m.st, lfact); dfree(m.st, loss_scratch); dfree(m.st, loss_out); dfree(m.st, always);
         dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
@@ -289,12 +311,17 @@ Engine::Engine(int device)
     DeviceContext *c = d_->ctx;
     d_->st = c->st;
     d_->sm_count = c->sm_count;
-    d_->h_done = c->h_int;
-    d_->h_l = c->h_int + MAXC;
-    d_->h_tie = c->h_int + 2 * MAXC;
-    d_->h_ks = c->h_int + 3 * MAXC;
-    d_->h_coef0 = c->h_dbl;
-    d_->h_loss = c->h_dbl + MAXC;
+    for (int q = 0; q < 2; q++) {
+        Impl::Mirror &h = d_->mir[q];
+        int *hi = c->h_int + (size_t)q * 5 * MAXC;
+        h.done = hi;
+        h.l = hi + MAXC;
+        h.tie = hi + 2 * MAXC;
+        h.ks = hi + 3 * MAXC;
+        h.gate = hi + 4 * MAXC;
+        h.coef0 = c->h_dbl + (size_t)q * 3 * MAXC;
+        h.loss = h.coef0 + MAXC;
+    }
 }
 
 Engine::~Engine()
@@ -353,6 +380,10 @@ void Engine::init_shard(int world, int rank, const void *unique_id, long long co
 }
 void Engine::profile(double *ms_out, long long *n_out) const
 {
+    if (d_->prof && !d_->spans.empty()) {  // pipelined batches leave their spans for the end of the path
+        cudaStreamSynchronize(d_->st);
+        d_->collect_spans();
+    }
     for (int i = 0; i < PROF_NCAT; i++) {
         ms_out[i] = d_->cat_ms[i];
         n_out[i] = d_->cat_n[i];
@@ -789,7 +820,9 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     d.done = dalloc<int>(m.st, MAXC);
     d.tie = dalloc<int>(m.st, MAXC);
     d.tie_acc = dalloc<int>(m.st, MAXC);
-    d.n_active = dalloc<int>(m.st, 1);
+    m.n_active2 = dalloc<int>(m.st, 2);
+    d.n_active = m.n_active2;
+    d.prev_active = nullptr;
     d.betaD = dalloc<double>(m.st, (size_t)C * d.pstride);
     d.XA = dalloc<double>(m.st, (size_t)C * n * d.ldA);
     d.XB = family_ == FAM_COX ? dalloc<double>(m.st, (size_t)C * n * d.ldA) : nullptr;
@@ -825,7 +858,7 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     CUDA_CHECK(cudaMemsetAsync(d.done, 0, MAXC * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.tie, 0, MAXC * 4, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.tie_acc, 0, MAXC * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.n_active, 0, 4, m.st));
+    CUDA_CHECK(cudaMemsetAsync(m.n_active2, 0, 8, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.betaD, 0, (size_t)C * d.pstride * 8, m.st));
     CUDA_CHECK(cudaMemsetAsync(d.XA, 0, (size_t)C * n * d.ldA * 8, m.st));
 
@@ -916,8 +949,11 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     m.ci0 = dalloc<int>(m.st, (size_t)C * m.cstride);
     m.ci1 = dalloc<int>(m.st, (size_t)C * m.cstride);
     m.ctx->reserve_support((size_t)MAXC * kcap);
-    m.h_A = m.ctx->h_A;
-    m.h_bA = m.ctx->h_bA;
+    for (int q = 0; q < 2; q++) {
+        m.mir[q].A = m.ctx->h_A + (size_t)q * MAXC * kcap;
+        m.mir[q].bA = m.ctx->h_bA + (size_t)q * MAXC * kcap;
+        m.tk[q].pending = false;
+    }
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     S_ = d.S;
     m.chains_ready = true;
@@ -929,169 +965,234 @@ static inline int sweep_epi(int family)
     return family == FAM_LM ? EPI_SACR_LM : (family == FAM_COX ? EPI_SACR_COX : EPI_SACR_GLM);
 }
 
-void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out,
-                       const std::vector<LossJob> *jobs, std::vector<double> *loss_out, double lambda)
+// One group of PDAS iterations for the batch described by ticket `t` (enqueue only).
+static void enqueue_iterations(Engine::Impl &m, Engine::Impl::Ticket &t, int count, bool sharded, long long col_lo);
+
+int Engine::run_batch_enqueue(int T, const std::vector<int> &chains, bool new_path_step, const std::vector<LossJob> *jobs,
+                              double lambda)
 {
     Impl &m = *d_;
     if (!m.chains_ready) throw EngineError{"run_batch before setup_chains"};
     Dev &d = m.d;
     if (T < 1 || T > m.Tmax) throw EngineError{"sparsity level outside [1, kcap]"};
     if (chains.empty() || (int)chains.size() > m.nchains) throw EngineError{"bad chain set"};
-    BatchDesc b{};
+    if (!(lambda >= 0.0)) throw EngineError{"lambda must be >= 0"};
+    const int slot = (int)(m.seq++ & 1);
+    Impl::Ticket &t = m.tk[slot];
+    if (t.pending) throw EngineError{"run_batch_enqueue: the ticket of this slot has not been collected"};
+    BatchDesc &b = t.b;
+    b = BatchDesc{};
     b.nch = (int)chains.size();
     b.T = T;
     b.new_path_step = new_path_step ? 1 : 0;
     b.CL = chain_cluster_size(d, d.grouped ? std::min(d.kcap, T * GMAX) : T, b.nch);
-    int cmin = MAXC, cmax = -1;
+    t.cmin = MAXC;
+    t.cmax = -1;
     for (int i = 0; i < b.nch; i++) {
         if (chains[i] < 0 || chains[i] >= m.nchains) throw EngineError{"chain id out of range"};
         b.chain[i] = chains[i];
-        cmin = std::min(cmin, chains[i]);
-        cmax = std::max(cmax, chains[i]);
+        t.cmin = std::min(t.cmin, chains[i]);
+        t.cmax = std::max(t.cmax, chains[i]);
     }
     if (new_path_step && chains[0] != 0) throw EngineError{"a new path step must include the full-data chain"};
-    LossDesc ld{};
+    t.ld = LossDesc{};
+    t.has_jobs = jobs != nullptr;
     if (jobs) {
         if ((int)jobs->size() > 2 * MAXC) throw EngineError{"too many loss jobs"};
-        ld.njobs = (int)jobs->size();
-        for (int i = 0; i < ld.njobs; i++) {
-            ld.chain[i] = (*jobs)[i].chain;
-            ld.kind[i] = (*jobs)[i].kind;
-            ld.fold[i] = (*jobs)[i].fold;
+        t.ld.njobs = (int)jobs->size();
+        for (int i = 0; i < t.ld.njobs; i++) {
+            t.ld.chain[i] = (*jobs)[i].chain;
+            t.ld.kind[i] = (*jobs)[i].kind;
+            t.ld.fold[i] = (*jobs)[i].fold;
         }
     }
-    d.ldXr = T;
-    if (!(lambda >= 0.0)) throw EngineError{"lambda must be >= 0"};
-    d.lambda = lambda;
-    const int mode = sweep_mode(family_), epi = sweep_epi(family_);
-    const double vec_bytes = 8.0 * d.n * b.nch * (mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 4)) + 8.0 * d.p * b.nch;
-
-    int sp = m.span_begin(4);
-    launch_chain_begin(d, b, m.st);
-    m.span_end(sp);
-    long long launches = 1;
-    // PDAS iterations are enqueued speculatively: the kernels of an iteration return at once when every chain of the
-    // batch has already met the stopping rule (Dev::gate), so the host only synchronises once per group.  PDAS needs
-    // 2-4 iterations per warm-started fit; the first group covers that, later groups are shorter.
+    // the kernels of this batch carry their own copy of the descriptor: ridge level, gate counter of this slot and the
+    // counter of the batch enqueued before it (Dev::prev_active)
+    t.d = d;
+    t.d.ldXr = T;
+    t.d.lambda = lambda;
+    t.d.n_active = m.n_active2 + slot;
+    t.d.prev_active = m.n_active2 + (slot ^ 1);
+    t.d.gate = t.d.n_active;
+    t.T = T;
+    t.slot = slot;
+    t.enq = 0;
+    t.launches = 1;
     static const bool fuse_topk = [] {
         const char *e = std::getenv("BESS_B200_FUSE_TOPK");
         return !(e && e[0] == '0');
     }();
-    const bool fused_mode = fuse_topk && !sharded_ && !d.grouped && d.p <= TOPK_LMAX;
-    d.gate = d.n_active;
-    int enq = 0;
-    bool all = false;
-    while (!all && enq < d.max_iter) {
-        const int group = std::min(enq == 0 ? 3 : 2, d.max_iter - enq);
-        for (int q = 0; q < group; q++) {
-            if (d.grouped) {
-                // group selection: sweep + group sacrifice in one kernel, top-k over the groups, groups -> columns
-                sp = m.span_begin(1);
-                launch_group_sacrifice(d, b, m.st);
-                m.span_end(sp);
-                if (m.n_always)
-                    launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
-                sp = m.span_begin(3);
-                launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.N, T, cmax - cmin + 1,
-                            d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride,
-                            m.st, d.gate);
-                launch_group_expand(d, b, m.st);
-                m.span_end(sp);
-                sp = m.span_begin(4);
-                launch_chain_fit(d, b, m.st);
-                m.span_end(sp);
-                continue;
-            }
+    t.fused = fuse_topk && !sharded_ && !d.grouped && d.p <= TOPK_LMAX;
+    if (!t.ev) CUDA_CHECK(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+
+    int sp = m.span_begin(4);
+    launch_chain_begin(t.d, b, m.st);
+    m.span_end(sp);
+    // PDAS iterations are enqueued speculatively: the kernels of an iteration return at once when every chain of the
+    // batch has already met the stopping rule (Dev::gate), so the host only synchronises once per group.  PDAS needs
+    // 2-4 iterations per warm-started fit; the first group covers that, later groups are shorter.
+    enqueue_iterations(m, t, std::min(3, d.max_iter), sharded_, col_lo_);
+    t.pending = true;
+    return slot;
+}
+
+static void enqueue_iterations(Engine::Impl &m, Engine::Impl::Ticket &t, int count, bool sharded, long long col_lo)
+{
+    const Dev &d = t.d;
+    const BatchDesc &b = t.b;
+    const int T = t.T, cmin = t.cmin, cmax = t.cmax;
+    const int mode = sweep_mode(d.family), epi = sweep_epi(d.family);
+    int sp;
+    for (int q = 0; q < count; q++) {
+        if (d.grouped) {
+            // group selection: sweep + group sacrifice in one kernel, top-k over the groups, groups -> columns
             sp = m.span_begin(1);
-            launch_dual_sweep(d, mode, m.st);
+            launch_group_sacrifice(d, b, m.st);
             m.span_end(sp);
-            const bool fused = fuse_topk && !sharded_ && d.p <= TOPK_LMAX;
-            if (!fused) {
-                sp = m.span_begin(2);
-                launch_finish(d, mode, epi, b, nullptr, m.st);
-                m.span_end(sp);
-                if (m.n_always)
-                    launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
-            }
+            if (m.n_always)
+                launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
             sp = m.span_begin(3);
-            if (fused) {
-                launch_topk_fused(d, mode, epi, cmin, cmax - cmin + 1, T, m.always, m.n_always, m.st);
-            } else if (!sharded_) {
-                launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1,
-                            d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride,
-                            m.st, d.gate);
-            } else {
-                // exact local top-k -> all-gather of (sacrifice, global index) candidates -> identical merge on every
-                // rank (rank-major concatenation of ascending lists is ascending, so the ordered compaction of the
-                // select keeps the reference's ascending-index output and the lower-index tie rule)
-                const NcclApi &api = nccl_api();
-                const int nspan = cmax - cmin + 1;
-                const int kloc = std::min(T, d.p);
-                launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, kloc, nspan, m.Aloc + (size_t)cmin * d.kcap,
-                            d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st, d.gate);
-                launch_pack_candidates(d.bd + (size_t)cmin * d.pstride, d.pstride, m.Aloc + (size_t)cmin * d.kcap, d.kcap,
-                                       kloc, T, col_lo_, nspan, m.cand_s + (size_t)cmin * d.kcap, d.kcap, d.gate, m.st);
-                NCCL_CHECK(api.AllGather(m.cand_s, m.cand_r, (size_t)m.nchains * d.kcap * sizeof(Cand), ncclChar, m.comm,
-                                         m.st));
-                launch_unpack_candidates(m.cand_r + (size_t)cmin * d.kcap, m.world, m.nchains, d.kcap, T,
-                                         m.mv + (size_t)cmin * m.mstride, m.mi + (size_t)cmin * m.mstride, m.mstride,
-                                         d.gate, m.st);
-                launch_topk(m.mv + (size_t)cmin * m.mstride, m.mstride, m.world * T, T, nspan,
-                            d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride,
-                            m.st, d.gate, m.mi + (size_t)cmin * m.mstride);
-                // the k active columns, all rows: owners write them, everybody sums (x + 0 is exact)
-                launch_gather_active(d, b, m.AXs, m.st);
-                NCCL_CHECK(api.AllReduce(m.AXs, d.AXr, (size_t)m.nchains * d.n * T, ncclDouble, ncclSum, m.comm, m.st));
-            }
+            launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.N, T, cmax - cmin + 1, d.Anew + (size_t)cmin * d.kcap,
+                        d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st, d.gate);
+            launch_group_expand(d, b, m.st);
             m.span_end(sp);
             sp = m.span_begin(4);
             launch_chain_fit(d, b, m.st);
             m.span_end(sp);
+            continue;
         }
-        enq += group;
-        // results are enqueued behind the group; they are only used if the batch turns out to be finished
-        if (jobs) {
-            sp = m.span_begin(5);
-            launch_losses(d, ld, m.testrows, m.ntest, m.y, m.w, m.lfact, m.loss_scratch, m.loss_out, m.st);
+        sp = m.span_begin(1);
+        launch_dual_sweep(d, mode, m.st);
+        m.span_end(sp);
+        if (!t.fused) {
+            sp = m.span_begin(2);
+            launch_finish(d, mode, epi, b, nullptr, m.st);
             m.span_end(sp);
-            CUDA_CHECK(cudaMemcpyAsync(m.h_loss, m.loss_out, ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+            if (m.n_always)
+                launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, cmax - cmin + 1, m.always, m.n_always, m.st);
         }
-        CUDA_CHECK(cudaMemcpyAsync(m.h_done, d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaMemcpyAsync(m.h_l, d.l, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        if (d.grouped) CUDA_CHECK(cudaMemcpyAsync(m.h_ks, d.ks, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaMemcpyAsync(m.h_tie, d.tie_acc, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaMemcpyAsync(m.h_coef0, d.coef0, MAXC * sizeof(double), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaMemcpyAsync(m.h_A, d.A, (size_t)MAXC * d.kcap * sizeof(int), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaMemcpyAsync(m.h_bA, d.bA, (size_t)MAXC * d.kcap * sizeof(double), cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));
-        all = true;
-        for (int i = 0; i < b.nch; i++) all = all && m.h_done[b.chain[i]];
+        sp = m.span_begin(3);
+        if (t.fused) {
+            launch_topk_fused(d, mode, epi, cmin, cmax - cmin + 1, T, m.always, m.n_always, m.st);
+        } else if (!sharded) {
+            launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, T, cmax - cmin + 1, d.Anew + (size_t)cmin * d.kcap,
+                        d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st, d.gate);
+        } else {
+            // exact local top-k -> all-gather of (sacrifice, global index) candidates -> identical merge on every
+            // rank (rank-major concatenation of ascending lists is ascending, so the ordered compaction of the
+            // select keeps the reference's ascending-index output and the lower-index tie rule)
+            const NcclApi &api = nccl_api();
+            const int nspan = cmax - cmin + 1;
+            const int kloc = std::min(T, d.p);
+            launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, d.p, kloc, nspan, m.Aloc + (size_t)cmin * d.kcap, d.kcap,
+                        d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st, d.gate);
+            launch_pack_candidates(d.bd + (size_t)cmin * d.pstride, d.pstride, m.Aloc + (size_t)cmin * d.kcap, d.kcap, kloc, T,
+                                   col_lo, nspan, m.cand_s + (size_t)cmin * d.kcap, d.kcap, d.gate, m.st);
+            NCCL_CHECK(api.AllGather(m.cand_s, m.cand_r, (size_t)m.nchains * d.kcap * sizeof(Cand), ncclChar, m.comm, m.st));
+            launch_unpack_candidates(m.cand_r + (size_t)cmin * d.kcap, m.world, m.nchains, d.kcap, T,
+                                     m.mv + (size_t)cmin * m.mstride, m.mi + (size_t)cmin * m.mstride, m.mstride, d.gate, m.st);
+            launch_topk(m.mv + (size_t)cmin * m.mstride, m.mstride, m.world * T, T, nspan, d.Anew + (size_t)cmin * d.kcap,
+                        d.kcap, d.tie + cmin, m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st, d.gate,
+                        m.mi + (size_t)cmin * m.mstride);
+            // the k active columns, all rows: owners write them, everybody sums (x + 0 is exact)
+            launch_gather_active(d, b, m.AXs, m.st);
+            NCCL_CHECK(api.AllReduce(m.AXs, d.AXr, (size_t)m.nchains * d.n * T, ncclDouble, ncclSum, m.comm, m.st));
+        }
+        m.span_end(sp);
+        sp = m.span_begin(4);
+        launch_chain_fit(d, b, m.st);
+        m.span_end(sp);
     }
-    d.gate = nullptr;
-    m.collect_spans();
+    t.enq += count;
+    // results are enqueued behind the group; they are only used if the batch turns out to be finished
+    Engine::Impl::Mirror &h = m.mir[t.slot];
+    if (t.has_jobs) {
+        sp = m.span_begin(5);
+        launch_losses(d, t.ld, m.testrows, m.ntest, m.y, m.w, m.lfact, m.loss_scratch, m.loss_out, m.st);
+        m.span_end(sp);
+        CUDA_CHECK(cudaMemcpyAsync(h.loss, m.loss_out, t.ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(h.done, d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(h.l, d.l, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(h.tie, d.tie_acc, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(h.ks, d.ks, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(h.gate, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(h.coef0, d.coef0, MAXC * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(h.A, d.A, (size_t)MAXC * d.kcap * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(h.bA, d.bA, (size_t)MAXC * d.kcap * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaEventRecord(t.ev, m.st));
+}
+
+bool Engine::run_batch_collect(int ticket, BatchResult &out, std::vector<double> *loss_out)
+{
+    Impl &m = *d_;
+    if (ticket < 0 || ticket > 1 || !m.tk[ticket].pending) throw EngineError{"run_batch_collect: no such pending batch"};
+    Impl::Ticket &t = m.tk[ticket];
+    Impl::Mirror &h = m.mir[t.slot];
+    const Dev &d = t.d;
+    const BatchDesc &b = t.b;
+    CUDA_CHECK(cudaEventSynchronize(t.ev));
+    auto finished = [&] {
+        bool all = true;
+        for (int i = 0; i < b.nch; i++) all = all && h.done[b.chain[i]];
+        return all;
+    };
+    const bool in_one_go = finished();
+    // a batch that was itself enqueued behind an unfinished one never started (its gate counter reads 0 while its chains
+    // are not done): the caller collects the earlier batch first, so this cannot happen here
+    while (!finished() && t.enq < d.max_iter) {
+        enqueue_iterations(m, t, std::min(2, d.max_iter - t.enq), sharded_, col_lo_);
+        CUDA_CHECK(cudaEventSynchronize(t.ev));
+    }
+    t.pending = false;
+    const int T = t.T;
     out.T = T;
     out.nchains = b.nch;
     int executed = 0;  // iterations that actually ran (the rest of the last group returned at the gate)
     for (int i = 0; i < b.nch; i++) {
         const int c = b.chain[i];
         out.chain_ids[i] = c;
-        out.l[i] = m.h_l[c];
-        out.coef0[i] = m.h_coef0[c];
-        const int ks = d.grouped ? m.h_ks[c] : T;  // columns in the support (== T without group structure)
-        out.A[i].assign(m.h_A + (size_t)c * d.kcap, m.h_A + (size_t)c * d.kcap + ks);
-        out.bA[i].assign(m.h_bA + (size_t)c * d.kcap, m.h_bA + (size_t)c * d.kcap + ks);
-        const int iters = std::min(m.h_l[c], d.max_iter);
+        out.l[i] = h.l[c];
+        out.coef0[i] = h.coef0[c];
+        const int ks = d.grouped ? h.ks[c] : T;  // columns in the support (== T without group structure)
+        out.A[i].assign(h.A + (size_t)c * d.kcap, h.A + (size_t)c * d.kcap + ks);
+        out.bA[i].assign(h.bA + (size_t)c * d.kcap, h.bA + (size_t)c * d.kcap + ks);
+        const int iters = std::min(h.l[c], d.max_iter);
         stats_.n_pdas_iters += iters;
-        stats_.n_boundary_ties += m.h_tie[c];
+        stats_.n_boundary_ties += h.tie[c];
         executed = std::max(executed, iters);
     }
-    launches += (long long)executed * (fused_mode ? 3 : 4 + (m.n_always ? 1 : 0) + (sharded_ ? 4 : 0)) + (jobs ? 1 : 0);
+    const int mode = sweep_mode(family_);
+    const double vec_bytes = 8.0 * d.n * b.nch * (mode == MODE_D ? 1 : (mode == MODE_DH ? 2 : 4)) + 8.0 * d.p * b.nch;
+    const long long per_iter = d.grouped ? 4 + (m.n_always ? 1 : 0)
+                                         : (t.fused ? 3 : 4 + (m.n_always ? 1 : 0) + (sharded_ ? 4 : 0));
     stats_.n_sweeps += executed;
-    stats_.sweep_bytes += executed * (8.0 * d.n * d.p + vec_bytes);
-    stats_.kernel_launches += launches;  // launches that did work; gated no-op launches are not counted
+    stats_.sweep_bytes += executed * (8.0 * d.n * d.p * (d.grouped ? b.nch : 1) + vec_bytes);
+    stats_.kernel_launches += 1 + (long long)executed * per_iter + (t.has_jobs ? 1 : 0);  // gated no-op launches are not counted
     stats_.n_fits += b.nch;
     stats_.n_batches++;
-    if (jobs && loss_out) loss_out->assign(m.h_loss, m.h_loss + ld.njobs);
+    if (t.has_jobs && loss_out) loss_out->assign(h.loss, h.loss + t.ld.njobs);
+    return in_one_go;
+}
+
+void Engine::run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out,
+                       const std::vector<LossJob> *jobs, std::vector<double> *loss_out, double lambda)
+{
+    const int tk = run_batch_enqueue(T, chains, new_path_step, jobs, lambda);
+    run_batch_collect(tk, out, loss_out);
+    Impl &m = *d_;
+    if (!m.tk[tk ^ 1].pending) {
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        m.collect_spans();
+    }
+}
+
+void Engine::run_batch_discard(int ticket)
+{
+    Impl &m = *d_;
+    if (ticket < 0 || ticket > 1 || !m.tk[ticket].pending) return;
+    CUDA_CHECK(cudaEventSynchronize(m.tk[ticket].ev));
+    m.tk[ticket].pending = false;
 }
 
 void Engine::chain_state(int chain, int op, int slot_beta, int slot_coef0)
@@ -1122,10 +1223,10 @@ void Engine::losses(const std::vector<LossJob> &jobs, std::vector<double> &out)
     const int sp = m.span_begin(5);
     launch_losses(m.d, ld, m.testrows, m.ntest, m.y, m.w, m.lfact, m.loss_scratch, m.loss_out, m.st);
     m.span_end(sp);
-    CUDA_CHECK(cudaMemcpyAsync(m.h_loss, m.loss_out, ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(m.mir[0].loss, m.loss_out, ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     stats_.kernel_launches++;
-    out.assign(m.h_loss, m.h_loss + ld.njobs);
+    out.assign(m.mir[0].loss, m.mir[0].loss + ld.njobs);
 }
 
 // Roofline probe: `reps` back-to-back dual sweeps (+ finish) for all chain slots; returns mean ms per sweep kernel.

@@ -107,6 +107,16 @@ public:
     void run_batch(int T, const std::vector<int> &chains, bool new_path_step, BatchResult &out,
                    const std::vector<LossJob> *jobs = nullptr, std::vector<double> *loss_out = nullptr, double lambda = 0.0);
 
+    // ---- the same in two halves, so that the NEXT path step can be enqueued while the host still waits for this one
+    // (sequential_path knows its order of evaluation in advance).  enqueue returns a ticket (two may be pending);
+    // collect waits for the batch, enqueues more PDAS iterations if the first speculative group did not finish every
+    // chain, and returns true when the first group sufficed.  When it returns false, a batch enqueued behind this one
+    // found it unfinished and skipped itself on the device (Dev::prev_active): discard that ticket and enqueue it again.
+    int run_batch_enqueue(int T, const std::vector<int> &chains, bool new_path_step, const std::vector<LossJob> *jobs,
+                          double lambda);
+    bool run_batch_collect(int ticket, BatchResult &out, std::vector<double> *loss_out);
+    void run_batch_discard(int ticket);
+
     // ---- explicit warm-start state of a chain (STATE_ZERO / STATE_SAVE / STATE_LOAD on NSLOT slots; the
     // (A, beta_A) half and the coef0 half are addressed separately, a negative slot skips that half).  Used by pgs_path.
     void chain_state(int chain, int op, int slot_beta, int slot_coef0);

@@ -47,7 +47,12 @@ struct Dev {
     int *done;          // [MAXC]
     int *tie;           // [MAXC] boundary-tie flag of the last top-k
     int *tie_acc;       // [MAXC] boundary ties consumed by the chain's fits since chain_begin
-    int *n_active;      // [1] chains of the running batch that have not met the stopping rule yet
+    int *n_active;      // chains of the running batch that have not met the stopping rule yet (one of two alternating
+                        // counters: consecutive batches use different ones)
+    const int *prev_active; // the counter of the batch enqueued before this one.  A batch may be enqueued BEHIND an
+                        // unfinished one (the next path step, speculatively, while the host still waits for the current
+                        // one): chain_begin_kernel then finds *prev_active != 0, zeroes its own counter and the whole
+                        // batch falls through its gates without touching any state; the host re-enqueues it later.
     const int *gate;    // == n_active while a batch runs: every per-iteration kernel returns at once when *gate == 0,
                         // so iterations can be enqueued speculatively without a host round trip; nullptr = no gate
     double *betaD;      // [MAXC][p] dense beta (for the sacrifice)

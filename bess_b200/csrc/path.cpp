@@ -117,6 +117,30 @@ struct Driver {
         return e;
     }
 
+    // step() in two halves for paths whose order of evaluation is known in advance (Engine::run_batch_enqueue)
+    int step_enqueue(int T, double lambda)
+    {
+        std::vector<LossJob> jobs;
+        jobs.push_back({0, 0, 0});
+        for (int k = 0; k < K; k++) jobs.push_back({1 + k, 1, k});
+        return eng.run_batch_enqueue(T, all_chains, /*new_path_step=*/true, &jobs, lambda);
+    }
+    bool step_collect(int ticket, int T, double lambda, Eval &e)
+    {
+        BatchResult br;
+        std::vector<double> v;
+        const bool in_one_go = eng.run_batch_collect(ticket, br, &v);
+        e.T = T;
+        e.lambda = lambda;
+        e.l = br.l[0];
+        e.A = br.A[0];
+        e.bA = br.bA[0];
+        e.coef0 = br.coef0[0];
+        e.train_loss = v[0];
+        e.ic = K > 0 ? mean_of(v, 1, 1 + (size_t)K) : ic_formula(e.train_loss, T);
+        return in_one_go;
+    }
+
     // A repeated metric->ic() on the same level (gs_path evaluates every fresh point twice): under CV
     // that is a second K-fold pass warm-started by the first; without CV the value is unchanged.
     double ic_again(const Eval &e)
@@ -158,11 +182,30 @@ void sequential_path(Driver &dr, BessResult &out, Eval &best)
     const int S = (int)a.sequence.size(), L = (int)lams.size();
     std::vector<Eval> evs((size_t)S * L);  // [lambda][s]
     std::vector<int> order;
-    for (int i = 0; i < S; i++) {
+    for (int i = 0; i < S; i++)
         for (int q = 0; q < L; q++) {
             const int j = (i % 2 == 0) ? q : L - 1 - q;
-            evs[(size_t)j * S + i] = dr.step(a.sequence[(size_t)i], nullptr, lams[(size_t)j]);
             order.push_back(j * S + i);
+        }
+    // The order of evaluation is fixed in advance and every warm start lives on the device, so step t+1 is enqueued
+    // before the host waits for step t: the GPU never idles through a host round trip.  If step t needs more PDAS
+    // iterations than its first speculative group, step t+1 skips itself on the device and is enqueued again.
+    auto level = [&](int idx) { return a.sequence[(size_t)(order[(size_t)idx] % S)]; };
+    auto ridge = [&](int idx) { return lams[(size_t)(order[(size_t)idx] / S)]; };
+    const int n_steps = (int)order.size();
+    const bool pipelined = !dr.eng.sharded();
+    if (!pipelined) {
+        for (int t = 0; t < n_steps; t++) evs[(size_t)order[(size_t)t]] = dr.step(level(t), nullptr, ridge(t));
+    } else {
+        int cur = dr.step_enqueue(level(0), ridge(0));
+        for (int t = 0; t < n_steps; t++) {
+            int next = t + 1 < n_steps ? dr.step_enqueue(level(t + 1), ridge(t + 1)) : -1;
+            const bool in_one_go = dr.step_collect(cur, level(t), ridge(t), evs[(size_t)order[(size_t)t]]);
+            if (!in_one_go && next >= 0) {
+                dr.eng.run_batch_discard(next);
+                next = dr.step_enqueue(level(t + 1), ridge(t + 1));
+            }
+            cur = next;
         }
     }
     // ic_sequence.minCoeff (path.cpp:113): Eigen visits the column-major matrix ic(s, lambda) column by column, i.e.

@@ -6,7 +6,7 @@ nvidia-smi > gpurun_out/nvidia_smi.txt 2>&1
 nproc > gpurun_out/nproc.txt; lscpu | head -20 >> gpurun_out/nproc.txt
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/smoke.log
-echo "== bench ref"; timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json
+echo "== bench ref"; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json
 echo "== bench"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 echo "== perf"; timeout 900 python tools/gpu_perf.py c1 c5 c4 c2 c3 > gpurun_out/perf.log 2>&1; echo "perf rc=$?"; grep -A2 "rep1\|rep2\|C5b" gpurun_out/perf.log | grep -v "^--" | cut -c1-400
 echo "== ncu launches"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-c5b > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"
