@@ -90,7 +90,8 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     w = np.ascontiguousarray(weight, dtype=np.float64).ravel()
     # group selection: first column of every group (linear.py:238-254); None = no group structure
-    g = np.arange(p, dtype=np.int32) if g_index is None else np.ascontiguousarray(g_index, dtype=np.int32).ravel()
+    # (no p-sized work on the call path when there are no groups: gindex = NULL means "every column its own group")
+    g = None if g_index is None else np.ascontiguousarray(g_index, dtype=np.int32).ravel()
     st = np.zeros(1)
     lam = np.ascontiguousarray(lambda_seq, dtype=np.float64).ravel()
     seq = np.ascontiguousarray(sequence, dtype=np.int32).ravel()
@@ -123,9 +124,11 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     stats = np.zeros(32)
     ext.stats_out = _d(stats)
     ext.profile = 1 if profile else 0
+    ext.beta_out_zeroed = 1  # `beta` comes from np.zeros (calloc): untouched pages stay untouched
     rc = lib.bess_b200_fit(xptr, n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal),
                            int(algorithm_type), int(model_type), int(max_iter), int(exchange_num), int(path_type),
-                           bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g), g.size, _d(st), 1, _i(seq),
+                           bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g) if g is not None else None,
+                           g.size if g is not None else 0, _d(st), 1, _i(seq),
                            seq.size, _d(lam), lam.size, int(s_min), int(s_max), 10, 10.0, float(lambda_min), float(lambda_max),
                            int(n_lambda) if n_lambda is not None else lam.size, bool(is_screening),
                            int(screening_size), int(powell_path), _i(alw), alw.size, 1.1, _d(beta), p_all, C.byref(c0), C.byref(tl),
@@ -136,6 +139,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
                           n_batches=int(stats[3]), n_boundary_ties=int(stats[4]), sweep_bytes=float(stats[5]),
                           kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[24]),
                           sweep_splits=int(stats[25]), norm_bytes=float(stats[26]),
+                          host_ms=dict(zip(("load", "screen", "normalize", "setup_chains", "path"), stats[27:32].tolist())),
                           prof_ms=dict(zip(PROF_CATS, stats[8:16].tolist())),
                           prof_launches=dict(zip(PROF_CATS, [int(v) for v in stats[16:24]]))))
     if is_screening:

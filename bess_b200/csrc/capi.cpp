@@ -95,7 +95,12 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
         }
         BessResult r;
         bess_run(a, r);
-        if (beta_out) std::copy(r.beta.begin(), r.beta.end(), beta_out);
+        if (beta_out) {
+            // dense beta by contract (bess.cpp:277); a caller that hands in a zero-filled buffer can say so and spare the
+            // p-sized pass (at p = 500000 zeroing 4 MB of fresh pages costs more than a PDAS iteration)
+            if (!(ext && ext->beta_out_zeroed)) std::fill(beta_out, beta_out + r.p_out, 0.0);
+            for (size_t i = 0; i < r.beta_idx.size(); i++) beta_out[r.beta_idx[i]] = r.beta_val[i];
+        }
         if (coef0_out) *coef0_out = r.coef0;
         if (train_loss_out) *train_loss_out = r.train_loss;
         if (ic_out) *ic_out = r.ic;
@@ -120,6 +125,7 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
                 ext->stats_out[24] = r.stats.big_sweep_bytes;
                 ext->stats_out[25] = (double)r.sweep_splits;
                 ext->stats_out[26] = r.stats.norm_bytes;
+                for (int q = 0; q < 5; q++) ext->stats_out[27 + q] = r.host_ms[q];
             }
         }
         g_last = std::move(r);
@@ -401,7 +407,10 @@ int bessgpu_topk(const double *vals, int n, int k, int *idx_out, int *tie_out)
 
 int bess_b200_debug_set(int key, int val)
 {
-    return guarded([&] { debug_set(key, val); });
+    return guarded([&] {
+        if (key == 3) engine_debug_first_group(val);  // size of the first speculative group of PDAS iterations (default 3)
+        else debug_set(key, val);
+    });
 }
 
 int bess_b200_debug_get(unsigned long long *out32)

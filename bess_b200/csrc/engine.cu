@@ -965,6 +965,9 @@ static inline int sweep_epi(int family)
     return family == FAM_LM ? EPI_SACR_LM : (family == FAM_COX ? EPI_SACR_COX : EPI_SACR_GLM);
 }
 
+static int g_first_group = 3;
+void engine_debug_first_group(int n) { g_first_group = n < 1 ? 1 : n; }
+
 // One group of PDAS iterations for the batch described by ticket `t` (enqueue only).
 static void enqueue_iterations(Engine::Impl &m, Engine::Impl::Ticket &t, int count, bool sharded, long long col_lo);
 
@@ -1031,7 +1034,7 @@ int Engine::run_batch_enqueue(int T, const std::vector<int> &chains, bool new_pa
     // PDAS iterations are enqueued speculatively: the kernels of an iteration return at once when every chain of the
     // batch has already met the stopping rule (Dev::gate), so the host only synchronises once per group.  PDAS needs
     // 2-4 iterations per warm-started fit; the first group covers that, later groups are shorter.
-    enqueue_iterations(m, t, std::min(3, d.max_iter), sharded_, col_lo_);
+    enqueue_iterations(m, t, std::min(g_first_group, d.max_iter), sharded_, col_lo_);
     t.pending = true;
     return slot;
 }

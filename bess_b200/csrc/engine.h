@@ -167,6 +167,10 @@ inline void shard_range(long long p, int world, int rank, long long *lo, long lo
     *hi = 2 * e < p ? 2 * e : p;
 }
 
+// test knob (bess_b200_debug_set(3, n)): how many PDAS iterations run_batch_enqueue enqueues before the host first looks.
+// 1 forces the "needs more iterations" path at almost every step, i.e. the next path step skips itself and is re-enqueued.
+void engine_debug_first_group(int n);
+
 // thrown by the engine on CUDA errors / misuse; the C-ABI turns it into an error code + message
 struct EngineError {
     std::string msg;

@@ -3,6 +3,7 @@
 #include "path.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <numeric>
@@ -701,11 +702,19 @@ void bess_run(const BessArgs &a, BessResult &out)
     for (int j : a.always_select)
         if (j < 0 || j >= n_units) throw EngineError{"always_select index out of range"};
 
+    using clk = std::chrono::steady_clock;
+    auto t_last = clk::now();
+    auto lap = [&](int phase) {
+        const auto now = clk::now();
+        out.host_ms[phase] += std::chrono::duration<double, std::milli>(now - t_last).count();
+        t_last = now;
+    };
     Engine eng(a.device);
     eng.set_profiling(a.profile);
     if (shard) eng.init_shard(a.world, a.rank, a.nccl_id, a.col_lo, a.p_total);
     eng.load(a.x, a.n, a.p, a.x_on_device, a.y, a.weight, a.model_type, /*borrow=*/a.is_screening);
 
+    lap(0);
     std::vector<int> always = a.always_select;
     std::sort(always.begin(), always.end());
     if (a.is_screening) {
@@ -718,8 +727,10 @@ void bess_run(const BessArgs &a, BessResult &out)
             j = (int)(it - out.screening_A.begin());
         }
     }
+    lap(1);
     eng.normalize(a.data_type, a.is_normal);
     if (grouped) eng.set_groups(a.g_index);
+    lap(2);
 
     const long long p = grouped ? (long long)eng.n_groups() : eng.p_model();
     int kcap;
@@ -740,6 +751,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     }
     eng.setup_chains(a.is_cv ? a.K : 0, folds.data(), kcap, a.max_iter, a.is_warm_start, always);
 
+    lap(3);
     Driver dr(eng, a);
     dr.kcap = kcap;
     Eval best;
@@ -747,6 +759,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     else if (pgs) pgs_path(dr, out, best);
     else gs_path(dr, out, best);
 
+    lap(4);
     std::vector<double> bA;
     double coef0;
     dr.denormalise(best, bA, coef0);
@@ -756,9 +769,14 @@ void bess_run(const BessArgs &a, BessResult &out)
     out.lambda = best.lambda;
     out.chosen_s = best.T;
     // scatter to the ORIGINAL column numbering (un-screen: bess.cpp:186-209)
-    out.beta.assign((size_t)p_all, 0.0);
+    out.p_out = p_all;
+    out.beta_idx.clear();
+    out.beta_val.clear();
     auto orig = [&](int j) { return a.is_screening ? out.screening_A[(size_t)j] : j; };
-    for (size_t i = 0; i < best.A.size(); i++) out.beta[(size_t)orig(best.A[i])] = bA[i];
+    for (size_t i = 0; i < best.A.size(); i++) {
+        out.beta_idx.push_back(orig(best.A[i]));
+        out.beta_val.push_back(bA[i]);
+    }
     for (auto &A : out.A_all)
         for (int &j : A) j = orig(j);
     out.stats = eng.stats();

@@ -50,7 +50,11 @@ struct BessArgs {
 };
 
 struct BessResult {
-    std::vector<double> beta;  // length p (original, un-screened), de-normalised
+    // the returned model, sparse: de-normalised coefficients on its support (ORIGINAL, un-screened column numbers,
+    // ascending); p_out = length of the dense beta vector the caller sees
+    std::vector<int> beta_idx;
+    std::vector<double> beta_val;
+    long long p_out = 0;
     double coef0 = 0.0, train_loss = 0.0, ic = 0.0, lambda = 0.0;
     std::vector<int> screening_A;
     int chosen_s = 0;
@@ -67,6 +71,9 @@ struct BessResult {
     double prof_ms[PROF_NCAT] = {};
     long long prof_n[PROF_NCAT] = {};
     int sweep_splits = 1;
+    // host wall-clock of the call by phase (ms): 0 engine + load (+ upload), 1 screening, 2 normalisation, 3 fold / chain
+    // set-up, 4 the path itself
+    double host_ms[5] = {};
 };
 
 // Metric.h:49-106 with the seed pinned (same std::mt19937 + std::shuffle + chunking)

@@ -66,7 +66,9 @@ typedef struct bess_b200_ext {
                               /*  8..15 device ms per kernel category (profile != 0): screening sweep, PDAS dual      */
                               /*  sweeps, finish, top-k, chain kernels, other, normalisation passes, H2D upload;      */
                               /*  16..23 launches per category; 24 algorithmic bytes of the screening sweep (8np);    */
-                              /*  25 sweep row splits; 26 algorithmic bytes of the normalisation / x_j.x_j passes     */
+                              /*  25 sweep row splits; 26 algorithmic bytes of the normalisation / x_j.x_j passes;    */
+                              /*  27..31 host wall-clock ms by phase: load, screening, normalisation, fold / chain    */
+                              /*  set-up, path                                                                        */
     int profile;              /* record CUDA events around every kernel category on the engine's stream               */
     /* ---- multi-GPU, columns of x sharded over `world` processes (one per GPU); world <= 1: single GPU.            */
     /* x then holds columns [col_lo, col_lo + x_col) = bess_b200_shard_range(p_total, world, rank) of the design,      */
@@ -77,6 +79,7 @@ typedef struct bess_b200_ext {
     long long col_lo, p_total;
     const void *nccl_unique_id; /* 128 bytes from bess_b200_nccl_unique_id() on rank 0, broadcast by the caller       */
     double *chosen_lambda_out;  /* ridge level of the returned model (List key "lambda", path.cpp:129)                 */
+    int beta_out_zeroed;        /* beta_out already holds zeros (e.g. calloc): only the non-zero coefficients are written */
 } bess_b200_ext;
 
 /* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's

@@ -495,3 +495,26 @@ def test_frontend_group_and_bsrr_estimators():
                ic_type="gic", powell_path=1)
     m.fit(q["x"], q["y"])
     assert rel_err(m.beta, q["beta"]) < RTOL and _close(m.ic, q["ic"])
+
+
+@pytest.mark.parametrize("first_group", [1, 2, 6])
+def test_pipelined_path_skip_and_reenqueue(first_group):
+    """sequential_path enqueues path step t+1 behind step t; when step t needs more PDAS iterations than its first
+    speculative group, step t+1 must skip itself on the device and be enqueued again.  A first group of 1 forces that at
+    (almost) every step, 6 never does: the results must not depend on it."""
+    from bess_b200 import _lib, cbess
+    lib = _lib.load()
+    try:
+        lib.bess_b200_debug_set(3, first_group)
+        for name in ("lm_seq_cv", "logit_seq_cv_w", "cox_seq_cv", "lm_seq_l0l2_cv", "poisson_seq_gic"):
+            g = load_golden(name)
+            seq = np.arange(1, g["smax"] + 1)
+            out = cbess.fit(g["x"], g["y"], g["data_type"], g["weight"], True, 1, g["model_type"], 20, 2, 1, True, g["ic_type"],
+                            g["is_cv"], g["K"], seq, 1, g["smax"], False, 1,
+                            fold_of_row=g["fold_of_row"] if g["is_cv"] else None, lambda_seq=g["lambda_seq"])
+            _check_final(out, g)
+            if "l_all" in g:
+                assert out["l_all"].tolist() == g["l_all"].tolist()
+                assert rel_err(out["ic_all"], g["ic_all"]) < RTOL
+    finally:
+        lib.bess_b200_debug_set(3, 3)

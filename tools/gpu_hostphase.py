@@ -1,0 +1,43 @@
+"""Host wall-clock of one C5 call by phase (no CUDA-event profiling), design resident in HBM: where the time outside the
+kernels goes.  Prints the mean over the timed calls."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bess_b200 import cbess  # noqa: E402
+
+
+def main():
+    n, p, k = 1000, 500000, 10
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(n, p, dtype=torch.float64, device="cuda", generator=g)
+    rng = np.random.default_rng(5)
+    nz = np.sort(rng.choice(p, k, replace=False))
+    beta = rng.uniform(1, 5, k)
+    y = (X[:, torch.as_tensor(nz, device="cuda")] @ torch.as_tensor(beta, device="cuda")).cpu().numpy() + rng.normal(0, 3, n)
+    w = np.ones(n)
+    seq = np.arange(1, 21)
+    acc, wall, reps = None, 0.0, 30
+    for r in range(reps + 3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = cbess.fit(None, y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, 10, seq, 1, 20, True, 5000,
+                        x_device_ptr=X.data_ptr(), n=n, p=p, want_trace=False)
+        dt = time.perf_counter() - t0
+        if r >= 3:
+            h = np.array(list(out["stats"]["host_ms"].values()))
+            acc = h if acc is None else acc + h
+            wall += dt
+    names = list(out["stats"]["host_ms"].keys())
+    print("C5 resident, mean of", reps, "calls: wall", round(wall / reps * 1e3, 3), "ms; host phases (ms):",
+          {nm: round(v / reps, 3) for nm, v in zip(names, acc)}, "sum", round(acc.sum() / reps, 3),
+          "| sweeps", out["stats"]["n_sweeps"], "batches", out["stats"]["n_batches"])
+
+
+if __name__ == "__main__":
+    main()

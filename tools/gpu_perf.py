@@ -20,7 +20,8 @@ def show(tag, out, dt):
     prof = {k: round(v, 3) for k, v in st["prof_ms"].items()}
     print(f"{tag}: {dt*1e3:.1f} ms  s={out['s']} support={np.nonzero(out['beta'])[0][:12].tolist()} fits={st['n_fits']} "
           f"iters={st['n_pdas_iters']} sweeps={st['n_sweeps']} launches={st['kernel_launches']} ties={st['n_boundary_ties']} "
-          f"S={st['sweep_splits']}\n    prof_ms={prof} n={st['prof_launches']}", flush=True)
+          f"S={st['sweep_splits']}\n    prof_ms={prof} n={st['prof_launches']}\n    host_ms={ {k: round(v, 3) for k, v in st['host_ms'].items()} }",
+          flush=True)
     if st["prof_ms"]["dual_sweep"] > 0:
         print(f"    PDAS sweep: {st['sweep_bytes']/st['prof_ms']['dual_sweep']/1e6:.0f} GB/s algorithmic; "
               f"screening sweep: {st['big_sweep_bytes']/max(st['prof_ms']['screen_sweep'],1e-9)/1e6:.0f} GB/s", flush=True)
