@@ -788,7 +788,8 @@ __global__ void __launch_bounds__(FIT_NT) loss_kernel(const Dev d, const LossDes
 void launch_losses(const Dev &d, const LossDesc &jobs, const int *testrows, const int *ntest, const double *y,
                    const double *w, const double *lfact, double *scratch, double *out, cudaStream_t st)
 {
-    const size_t smem = (size_t)d.kcap * (sizeof(double) + sizeof(int));
+    // + 16: nvcc reads the index list two entries at a time (LDS.64) in the loop remainder, i.e. up to one int past the end
+    const size_t smem = (size_t)d.kcap * (sizeof(double) + sizeof(int)) + 16;
     loss_kernel<<<jobs.njobs, FIT_NT, smem, st>>>(d, jobs, testrows, ntest, y, w, lfact, scratch, out);
     CUDA_CHECK(cudaGetLastError());
 }
