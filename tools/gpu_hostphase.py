@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bess_b200 import cbess  # noqa: E402
+from bess_b200 import _lib, cbess  # noqa: E402
 
 
 def main():
@@ -22,6 +22,13 @@ def main():
     y = (X[:, torch.as_tensor(nz, device="cuda")] @ torch.as_tensor(beta, device="cuda")).cpu().numpy() + rng.normal(0, 3, n)
     w = np.ones(n)
     seq = np.arange(1, 21)
+    for fg in [int(v) for v in os.environ.get("FIRST_GROUPS", "3").split(",")]:
+        _lib.load().bess_b200_debug_set(3, fg)
+        run(X, y, w, seq, n, p, fg)
+    _lib.load().bess_b200_debug_set(3, 3)
+
+
+def run(X, y, w, seq, n, p, fg):
     acc, wall, reps = None, 0.0, 30
     for r in range(reps + 3):
         torch.cuda.synchronize()
@@ -34,7 +41,7 @@ def main():
             acc = h if acc is None else acc + h
             wall += dt
     names = list(out["stats"]["host_ms"].keys())
-    print("C5 resident, mean of", reps, "calls: wall", round(wall / reps * 1e3, 3), "ms; host phases (ms):",
+    print("first group", fg, "| C5 resident, mean of", reps, "calls: wall", round(wall / reps * 1e3, 3), "ms; host phases (ms):",
           {nm: round(v / reps, 3) for nm, v in zip(names, acc)}, "sum", round(acc.sum() / reps, 3),
           "| sweeps", out["stats"]["n_sweeps"], "batches", out["stats"]["n_batches"])
 
