@@ -384,8 +384,9 @@ __device__ __forceinline__ void topk_body(unsigned long long *keys, int len, int
 {
     __shared__ int hist[256];
     __shared__ unsigned long long sh_prefix;
-    __shared__ int sh_krem, sh_neq;
+    __shared__ int sh_krem, sh_neq, sh_cnt;
     __shared__ unsigned long long scan_sh[34];
+    __shared__ unsigned long long small_bin[32];
     const int tid = threadIdx.x;
     const int kk = min(k, len);
     const int out_per_slice = min(k, slice_len);
@@ -438,6 +439,37 @@ __device__ __forceinline__ void topk_body(unsigned long long *keys, int len, int
             // every key of the boundary bin is wanted: the select is decided, the remaining digits cannot change it
             if (neq == krem && pass > 0 && prefix > 0ull) {
                 early = true;
+                break;
+            }
+            // few keys left in the boundary bin (the usual case after two digits: the largest sacrifices are spread over
+            // orders of magnitude): rank them in one warp instead of walking the remaining digits
+            if (neq <= 32 && pass > 0) {
+                if (tid == 0) sh_cnt = 0;
+                __syncthreads();
+                for (int i = tid; i < len; i += TOPK_NT) {
+                    const unsigned long long u = keys[i];
+                    if ((u & mask) == prefix) small_bin[atomicAdd(&sh_cnt, 1)] = u;
+                }
+                __syncthreads();
+                if (tid < 32 && tid < neq) {
+                    const unsigned long long u = small_bin[tid];
+                    int gt = 0, ge = 0;
+                    for (int j = 0; j < neq; j++) {
+                        const unsigned long long v = small_bin[j];
+                        gt += (v > u);
+                        ge += (v >= u);
+                    }
+                    if (gt < krem && krem <= ge) {  // u is the krem-th largest of the bin (all its duplicates agree)
+                        sh_prefix = u;
+                        sh_krem = krem - gt;
+                        sh_neq = ge - gt;
+                    }
+                }
+                __syncthreads();
+                prefix = sh_prefix;
+                krem = sh_krem;
+                neq = sh_neq;
+                __syncthreads();
                 break;
             }
         }

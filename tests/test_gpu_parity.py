@@ -263,6 +263,21 @@ def test_topk_exact_ascending_ties_and_pins():
     z = np.zeros(300)
     got, tie = topk(z, 10)
     assert got.tolist() == list(range(10)) and tie == 1
+    # the boundary bin holds few keys: the select finishes by ranking them in one warp -- near-equal keys, duplicates
+    # inside the bin, bins that are small from the first digit on
+    for n, k in [(30, 7), (31, 30), (5000, 12), (5000, 25), (20000, 40)]:
+        v = rng.random(n) * 1e-3
+        top = rng.choice(n, 28, replace=False)
+        v[top] = 1.0 + np.arange(28) * 2.0 ** -50          # same leading digits, distinct only in the last bits
+        got, tie = topk(v, k)
+        assert got.tolist() == orc.max_k(v, k).tolist() and tie == 0
+        v[top[:6]] = 1.0 + 5 * 2.0 ** -50                   # six duplicates straddling some of the boundaries
+        got, tie = topk(v, k)
+        assert got.tolist() == orc.max_k(v, k).tolist()
+    v = np.array([3.0, 5.0, 5.0, 1.0, 5.0, 3.0, 5.0, 0.0, 3.0])
+    for k in range(1, 10):
+        got, tie = topk(v, k)
+        assert got.tolist() == orc.max_k(v, k).tolist()
 
 
 def test_errors_are_loud():
