@@ -268,6 +268,35 @@ void launch_dual_sweep(const Dev &d, int mode, cudaStream_t st)
 // =====================================================================================================
 // finish: reduce row-split partials, apply the sacrifice
 // =====================================================================================================
+// sacrifice / screening utility from the reduced sums (the tail of the finish epilogue)
+template <int EPI>
+__device__ __forceinline__ double finish_epilogue(const Dev &d, int c, long long j, double dsum, double hsum, double R)
+{
+    double out;
+    if (EPI == EPI_SCREEN_LM) {
+        const double bq = dsum / hsum;  // one-column least squares (screening.cpp:46)
+        out = bq * bq;
+    } else {
+        const double beta = d.betaD[(size_t)c * d.pstride + j];
+        const double lam2 = 2.0 * d.lambda;  // L0L2 ridge term (Algorithm.h:1109, 1236/1246, 1341/1350, 1629-1630)
+        if (EPI == EPI_SACR_LM) {
+            // Phi = sqrt(2*lambda + x_j.x_j / n) (utilities.cpp:142-151), invPhi = 1/Phi (:167-177); Algorithm.h:1116-1122
+            const double phi = sqrt(lam2 + d.xtx[(size_t)c * d.pstride + j] / (double)d.ntrain[c]);
+            const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
+            out = t * t;
+        } else if (EPI == EPI_SACR_GLM) {
+            const double phi = sqrt(hsum + lam2);  // Algorithm.h:1238-1257 / 1342-1361
+            const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
+            out = t * t;
+        } else {
+            // Algorithm.h:1626-1634: l1 = -dsum + 2*lambda*beta, l2 = hsum - R + 2*lambda, d = -l1/l2, bd = |beta + d| * sqrt(l2)
+            const double l2 = hsum - R + lam2;
+            out = fabs(beta + (dsum - lam2 * beta) / l2) * sqrt(l2);
+        }
+    }
+    return out;
+}
+
 // value of the finish epilogue EPI for chain c, column j: reduces the row-split partials in a fixed order and applies the
 // sacrifice / screening formula.  EPI_RAW writes the reduced sums to raw_out and returns 0.
 template <int EPI>
@@ -298,30 +327,41 @@ __device__ __forceinline__ double finish_value(const Dev &d, int mode, int c, lo
         if (mode >= MODE_DH) raw_out[(size_t)(1 * FT + c) * d.pstride + j] = hsum;
         return 0.0;
     }
-    double out;
-    if (EPI == EPI_SCREEN_LM) {
-        const double bq = dsum / hsum;  // one-column least squares (screening.cpp:46)
-        out = bq * bq;
-    } else {
-        const double beta = d.betaD[(size_t)c * d.pstride + j];
-        const double lam2 = 2.0 * d.lambda;  // L0L2 ridge term (Algorithm.h:1109, 1236/1246, 1341/1350, 1629-1630)
-        if (EPI == EPI_SACR_LM) {
-            // Phi = sqrt(2*lambda + x_j.x_j / n) (utilities.cpp:142-151), invPhi = 1/Phi (:167-177); Algorithm.h:1116-1122
-            const double phi = sqrt(lam2 + d.xtx[(size_t)c * d.pstride + j] / (double)d.ntrain[c]);
-            const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
-            out = t * t;
-        } else if (EPI == EPI_SACR_GLM) {
-            const double phi = sqrt(hsum + lam2);  // Algorithm.h:1238-1257 / 1342-1361
-            const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
-            out = t * t;
-        } else {
-            // Algorithm.h:1626-1634: l1 = -dsum + 2*lambda*beta, l2 = hsum - R + 2*lambda, d = -l1/l2, bd = |beta + d| * sqrt(l2)
-            const double l2 = hsum - R + lam2;
-            out = fabs(beta + (dsum - lam2 * beta) / l2) * sqrt(l2);
+    return finish_epilogue<EPI>(d, c, j, dsum, hsum, R);
+}
+
+// The same for NB columns j0, j0 + jstep, ... of one thread at once (gaussian / GLM sweeps): the partials of all NB columns
+// are in flight together instead of one dependent chain of S loads per column.  Per column the partials are still added
+// in the order s = 0 .. S-1, so the result is bit-identical to finish_value.
+template <int EPI, int NB>
+__device__ __forceinline__ void finish_batch(const Dev &d, int mode, int c, long long j0, long long jstep, int nb, double (&out)[NB])
+{
+    const int NQ = mode == MODE_D ? 1 : 2;
+    const int FT = d.FS;
+    double ds[NB], hs[NB];
+#pragma unroll
+    for (int q = 0; q < NB; q++) ds[q] = 0.0, hs[q] = 0.0;
+#pragma unroll 2
+    for (int s = 0; s < d.S; s++) {
+        const double *pd = d.part + ((size_t)(s * NQ + 0) * FT + c) * d.pstride + j0;
+        const double *ph = d.part + ((size_t)(s * NQ + (NQ - 1)) * FT + c) * d.pstride + j0;
+        double vd[NB], vh[NB];
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+            vd[q] = q < nb ? pd[q * jstep] : 0.0;
+            vh[q] = (q < nb && mode == MODE_DH) ? ph[q * jstep] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+            ds[q] += vd[q];
+            hs[q] += vh[q];
         }
     }
-    return out;
+#pragma unroll
+    for (int q = 0; q < NB; q++)
+        if (q < nb) out[q] = finish_epilogue<EPI>(d, c, j0 + q * jstep, ds[q], hs[q], 0.0);
 }
+
 
 template <int EPI>
 __global__ void __launch_bounds__(256) finish_kernel(const Dev d, int mode, const BatchDesc b, double *raw_out)
@@ -584,7 +624,19 @@ __global__ void __launch_bounds__(TOPK_NT) topk_fused_kernel(const Dev d, int mo
     const int c = cmin + blockIdx.y;
     if (d.done[c]) return;
     const int len = d.p;
-    for (int i = tid; i < len; i += TOPK_NT) keys[i] = topk_key(finish_value<EPI>(d, mode, c, i, nullptr));
+    if (mode != MODE_COX) {
+        constexpr int NB = 8;
+        for (int i0 = tid; i0 < len; i0 += NB * TOPK_NT) {
+            const int nb = min(NB, (len - i0 + TOPK_NT - 1) / TOPK_NT);
+            double v[NB];
+            finish_batch<EPI, NB>(d, mode, c, i0, TOPK_NT, nb, v);
+#pragma unroll
+            for (int q = 0; q < NB; q++)
+                if (q < nb) keys[i0 + q * TOPK_NT] = topk_key(v[q]);
+        }
+    } else {
+        for (int i = tid; i < len; i += TOPK_NT) keys[i] = topk_key(finish_value<EPI>(d, mode, c, i, nullptr));
+    }
     if (n_always > 0) {
         __syncthreads();
         for (int q = tid; q < n_always; q += TOPK_NT) keys[always[q]] = (unsigned long long)__double_as_longlong(DBL_MAX);
