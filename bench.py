@@ -49,9 +49,15 @@ WORKLOAD = ("C5: gaussian gen.data n=1000 p=500000 true-s=10, screening.num=5000
 CPU_P, CPU_SMAX = 75000, 3
 
 
-def make_c5_on_device(torch, device, p=P_COLS, seed=5):
-    gen = torch.Generator(device=device).manual_seed(seed)
-    X = torch.randn(N_ROWS, p, dtype=torch.float64, device=device, generator=gen)
+def make_c5_on_device(torch, device, p=P_COLS, seed=5, torch_design=False):
+    """gen.data-shaped gaussian problem with the design born in HBM: x from the library's own generator
+    (bess_b200_gen_design: rows ~ N(0, I), gen.data.R:110-118 with rho = 0), or torch.randn with --torch-design."""
+    if torch_design:
+        gen = torch.Generator(device=device).manual_seed(seed)
+        X = torch.randn(N_ROWS, p, dtype=torch.float64, device=device, generator=gen)
+    else:
+        from bess_b200.gen_data import gen_design_device
+        X = gen_design_device(N_ROWS, p, 0.0, seed, torch.device(device).index or 0)
     rng = np.random.default_rng(seed)
     nz = np.sort(rng.choice(p, K_TRUE, replace=False))
     m = 5 * np.sqrt(2 * np.log(p) / N_ROWS)
@@ -197,7 +203,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     dev = f"cuda:{local_rank}"
-    X, y, nz = make_c5_on_device(torch, dev)
+    X, y, nz = make_c5_on_device(torch, dev, torch_design=args.torch_design)
     w = np.ones(N_ROWS)
     seq = np.arange(1, SMAX + 1)
     lo, hi = (0, P_COLS) if world == 1 else bdist.shard_range(P_COLS, world, rank)
@@ -387,7 +393,8 @@ def run_ours(args):
         line = {
             "metric": "pdas_path_cv_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (gen.data recipe; design drawn in HBM by " + ("torch.randn" if args.torch_design else "bess_b200_gen_design") + ")",
             "config": {"workload": WORKLOAD if world == 1 else WORKLOAD + f" x {world} CV repetitions (repeated 10-fold CV, "
                        f"one repetition per rank; {fits_per_step} unique fits per step)",
                        "parallelism": "single GPU" if world == 1 else
@@ -447,6 +454,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5b", action="store_true")
+    ap.add_argument("--torch-design", action="store_true", help="draw the design with torch.randn instead of the library's generator")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -237,6 +237,17 @@ int bess_b200_nccl_unique_id(void *out128)
     });
 }
 
+int bess_b200_gen_design(double *x_dev, int n, long long p, long long ld, double rho, unsigned long long seed, int device)
+{
+    return guarded([&] {
+        if (!x_dev || n < 1 || p < 1 || ld < p) throw EngineError{"gen_design: need a device buffer, n >= 1, 1 <= p <= ld"};
+        if (device >= 0 && cudaSetDevice(device) != cudaSuccess) throw EngineError{"gen_design: cudaSetDevice failed"};
+        launch_gen_design(x_dev, ld, n, p, rho, seed, nullptr);
+        const cudaError_t e = cudaStreamSynchronize(nullptr);
+        if (e != cudaSuccess) throw EngineError{std::string("gen_design: ") + cudaGetErrorString(e)};
+    });
+}
+
 const char *bess_b200_last_error(void) { return g_err.c_str(); }
 int bess_b200_version(void) { return BESS_B200_VERSION; }
 int bess_b200_device_count(void)

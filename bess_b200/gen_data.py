@@ -54,3 +54,16 @@ def gen_data(n, p, family="gaussian", k=10, seed=1, snr=10.0, scal=10.0, c=10.0,
         order = np.argsort(time, kind="stable")
         return SynthData(np.ascontiguousarray(x[order]), status[order], tbeta, time[order])
     raise ValueError("family should be 'gaussian', 'binomial', 'poisson' or 'cox'")
+
+
+def gen_design_device(n, p, rho=0.0, seed=1, device=0):
+    """The x of ``gen.data`` (R/R/gen.data.R:110-118, cortype 1: rows ~ MVN(0, Sigma), Sigma_jk = rho^|j-k|) drawn on the
+    GPU by the library's own kernel (``bess_b200_gen_design``): a row-major n x p fp64 ``torch`` tensor in HBM that can be
+    handed to ``cbess.fit(..., x_device_ptr=X.data_ptr())`` -- torch only owns the memory."""
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    _lib.require_gpu()
+    X = torch.empty((n, p), dtype=torch.float64, device=f"cuda:{device}")
+    _lib.check(lib.bess_b200_gen_design(X.data_ptr(), int(n), int(p), int(p), float(rho), int(seed), int(device)))
+    return X

@@ -107,6 +107,11 @@ int bess_b200_cv_fold_ids(int n, int K, unsigned seed, int *fold_of_row_out);
 /* ncclGetUniqueId through the library's run-time-loaded NCCL: call on rank 0, broadcast the 128 bytes to all ranks. */
 int bess_b200_nccl_unique_id(void *out128);
 
+/* Device-side design generator (R/R/gen.data.R:110-118, cortype 1): fills the DEVICE buffer x_dev (row-major n x p, leading
+ * dimension ld >= p) with rows ~ MVN(0, Sigma), Sigma_jk = rho^|j-k| (rho = 0: iid N(0,1)); counter-based (Philox4x32-10 +
+ * Box-Muller), so x[i][j] is a pure function of (seed, i, j).  For benchmarks whose design must not cross PCIe. */
+int bess_b200_gen_design(double *x_dev, int n, long long p, long long ld, double rho, unsigned long long seed, int device);
+
 const char *bess_b200_last_error(void);
 int bess_b200_version(void);
 /* number of CUDA devices visible (0 = no GPU: every compute call will fail) */
