@@ -6,7 +6,7 @@
 // z_ij is a pure function of (seed, i, j): Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3",
 // SC'11) on the counter (j as a signed 64-bit integer, i, 0) with the seed as key, two 53-bit uniforms, Box-Muller
 // (cosine branch).  R's Mersenne-Twister stream cannot be reproduced without R; what is kept is the
-// distribution, and the stream is restated in numpy (oracle/gen_design_oracle.py) for the parity test.
+// distribution; the parity tests check the stream against an independent numpy restatement (tests/test_gen_design.py).
 //
 // One warp walks one (row, column segment): 32 columns per step, the AR(1) recurrence inside the step is a 5-stage
 // decayed inclusive scan over the lanes (v_j += rho^d * v_{j-d}), the carry from the previous step enters as
