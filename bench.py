@@ -424,6 +424,7 @@ def run_ours(args):
                          "p500k_pdas_sweep": probe},
             "cpu_baseline": base, "c5b_no_screening": c5b if world == 1 else None, "column_sharded": col_sharded,
             "fits_per_step": fits_per_step, "n_boundary_ties": int(st["n_boundary_ties"]),
+            "host_ms_last_call": {k: round(float(v), 4) for k, v in st["host_ms"].items()},
         }
     if world > 1:
         dist.destroy_process_group()
