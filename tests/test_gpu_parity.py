@@ -533,3 +533,40 @@ def test_pipelined_path_skip_and_reenqueue(first_group):
                 assert rel_err(out["ic_all"], g["ic_all"]) < RTOL
     finally:
         lib.bess_b200_debug_set(3, 3)
+
+
+@pytest.mark.skipif(not refso.available(), reason="prebuilt oracle/_ref/libbess_ref.so did not travel")
+def test_widened_rows_edge_cases_against_live_reference():
+    """Corners of the bsrr / group rows against the reference library itself: every group selected (find_ind returns all
+    columns), cold starts, max_iter = 2, always-include under the Powell path, the Powell path behind a screening step,
+    a lambda grid with groups under CV."""
+    from bess_b200 import cbess
+    from bess_b200.gen_data import gen_data
+
+    def both(fam, n, p, k, seed, alg, path_type, is_cv, K, ic_type, seq, s_min, s_max, warm=True, max_iter=20, g_index=None,
+             always=(), scr=0, **kw):
+        model_type, data_type = FAM[fam]
+        d = gen_data(n, p, fam, k, seed=seed)
+        w = np.ones(n)
+        r = refso.bess_lambda(d.x, d.y, data_type, w, True, alg, model_type, max_iter, path_type, warm, ic_type, is_cv, K, seq,
+                              s_min, s_max, is_screening=scr > 0, screening_size=max(scr, 1), always_select=always,
+                              g_index=g_index, **kw)
+        out = cbess.fit(d.x, d.y, data_type, w, True, alg, model_type, max_iter, 2, path_type, warm, ic_type, is_cv, K, seq,
+                        s_min, s_max, scr > 0, max(scr, 1), always_select=always, cv_seed=123, g_index=g_index, **kw)
+        _check_final(out, r)
+        assert abs(out["lam"] - r["lambda_"]) <= 1e-12 * max(abs(r["lambda_"]), 1e-300)
+        assert out["stats"]["n_boundary_ties"] == 0
+
+    g8 = np.arange(0, 24, 3, dtype=np.int32)  # 8 groups of 3
+    both("gaussian", 120, 24, 4, 201, 2, 1, False, 5, 3, np.arange(1, 9), 1, 8, g_index=g8)              # T runs up to N
+    both("binomial", 150, 24, 3, 202, 2, 1, True, 3, 1, np.arange(1, 9), 1, 8, warm=False, g_index=g8)   # cold, CV, T = N
+    both("gaussian", 150, 90, 5, 203, 2, 1, False, 5, 2, np.arange(2, 7), 2, 6, max_iter=2,
+         g_index=np.arange(0, 90, 2, dtype=np.int32), always=(7, 30))                                    # max_iter 2 + pins
+    both("poisson", 200, 60, 3, 204, 3, 1, True, 3, 1, np.arange(1, 5), 1, 4,
+         g_index=np.arange(0, 60, 4, dtype=np.int32), lambda_seq=[0.0, 0.05])                            # GL0L2 grid, CV
+    both("gaussian", 200, 400, 5, 205, 5, 2, False, 5, 3, [1], 2, 9, always=(11, 250), lambda_min=0.01, lambda_max=10.0,
+         n_lambda=100, powell_path=1)                                                                    # Powell + pins
+    both("gaussian", 200, 600, 5, 206, 5, 2, True, 3, 1, [1], 1, 8, scr=80, lambda_min=0.01, lambda_max=10.0, n_lambda=6,
+         powell_path=2)                                                                                  # screening + Powell
+    both("cox", 160, 120, 4, 207, 5, 2, False, 5, 2, [1], 1, 6, warm=False, lambda_min=0.001, lambda_max=0.05, n_lambda=100,
+         powell_path=1)                                                                                  # cold Powell, cox
