@@ -18,7 +18,8 @@ and sparsity levels shard embarrassingly, with only per-fold losses reduced".  T
 CV with N repetitions (rank r draws its folds from cv_seed + r): the columns of X are sharded over the ranks for the joint
 screening sweep (local top-k + NCCL all-gather of candidates + all-reduce of the kept columns, inside the library), each
 rank then runs its own repetition's 200 fold fits + the full-data chain on the replicated screened design, and one NCCL
-all-reduce per step averages the per-level CV losses so every rank chooses the same sparsity level.  Per-GPU work is fixed
+all-reduce per step -- inside the library, on its own communicator (ext.cv_reduce_over_ranks) -- averages the per-level CV
+losses so every rank chooses the same sparsity level and returns the same model.  Per-GPU work is fixed
 as N grows => "scaling": "weak".  `value` counts UNIQUE fits only: the full-data chain is identical on every rank and is
 counted once (20*(1 + 10*N) fits per step).  The strong-scaling numbers of the column-sharded path itself (C5 call and the
 no-screening variant C5b, where every PDAS sweep is p = 500k wide) are reported next to it under "column_sharded".
@@ -221,6 +222,8 @@ def run_ours(args):
         o["cv_curve_mean"], o["s_joint"] = mean, int(o["s_all"][int(np.argmin(mean))])
         return o
 
+    lib_reduce = not args.torch_cv_reduce  # the library averages the CV curves itself (ext.cv_reduce_over_ranks)
+
     def step(host_x=None, profile=False, seed_shift=True):
         if world == 1:
             if host_x is None:
@@ -233,10 +236,16 @@ def run_ours(args):
         if host_x is None:
             o = bdist.fit_column_sharded(None, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
                                          SCREEN, cv_seed=seed, device=local_rank, x_shard_device_ptr=Xs.data_ptr(),
-                                         n=N_ROWS, p_local=hi - lo, profile=profile, want_curve=seed_shift)
+                                         n=N_ROWS, p_local=hi - lo, profile=profile, want_curve=seed_shift and not lib_reduce,
+                                         cv_reduce_over_ranks=seed_shift and lib_reduce)
         else:
             o = bdist.fit_column_sharded(host_x, lo, P_COLS, y, w, 1, True, 1, 20, 1, True, 1, True, NFOLDS, seq, 1, SMAX,
-                                         SCREEN, cv_seed=seed, device=local_rank, profile=profile, want_curve=seed_shift)
+                                         SCREEN, cv_seed=seed, device=local_rank, profile=profile,
+                                         want_curve=seed_shift and not lib_reduce,
+                                         cv_reduce_over_ranks=seed_shift and lib_reduce)
+        if seed_shift and lib_reduce:
+            o["s_joint"] = int(o["s"])  # chosen from the rank-averaged CV curve inside the library (one ncclAllReduce)
+            return o
         return reduce_curve(o) if seed_shift else o
 
     def timed(nsteps, host_x=None, **kw):
@@ -401,7 +410,7 @@ def run_ours(args):
                        f"{world} ranks: columns of X sharded for the joint screening sweep (local top-k + NCCL all-gather of "
                        f"candidates + all-reduce of the kept columns), CV repetitions sharded over the ranks (rank r: folds "
                        f"from cv_seed 123 + r) on the replicated 1000 x 5000 screened design, one NCCL all-reduce of the "
-                       f"per-level CV losses per step",
+                       f"per-level CV losses per step ({'inside the library' if lib_reduce else 'torch.distributed in the bench'})",
                        "l2_policy": ("inputs larger than L2 (4 GB design streamed from HBM every step)" if world == 1 else
                                      f"inputs larger than L2 ({4.0 / world:.2f} GB column shard per rank streamed from HBM every step)"),
                        "cv_seed": 123, "chosen_s": int(out["s"]) if world == 1 else int(out["s_joint"]),
@@ -455,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5b", action="store_true")
+    ap.add_argument("--torch-cv-reduce", action="store_true",
+                    help="N > 1: average the CV curves with torch.distributed in the bench instead of inside the library")
     ap.add_argument("--torch-design", action="store_true", help="draw the design with torch.randn instead of the library's generator")
     args = ap.parse_args()
     if args.impl == "reference":

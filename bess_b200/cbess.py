@@ -71,7 +71,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
         fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
         world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,), lambda_min=0.0, lambda_max=0.0,
-        n_lambda=None, powell_path=1, want_curve=False, g_index=None):
+        n_lambda=None, powell_path=1, want_curve=False, g_index=None, cv_reduce_over_ranks=False):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
     ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``.
     ``world > 1``: column-sharded multi-GPU call -- ``x`` is this rank's column shard ``[col_lo, col_lo + p)`` of a
@@ -125,6 +125,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     ext.stats_out = _d(stats)
     ext.profile = 1 if profile else 0
     ext.beta_out_zeroed = 1  # `beta` comes from np.zeros (calloc): untouched pages stay untouched
+    ext.cv_reduce_over_ranks = 1 if (cv_reduce_over_ranks and sharded) else 0
     rc = lib.bess_b200_fit(xptr, n, p, _d(y), y.size, int(data_type), _d(w), w.size, bool(is_normal),
                            int(algorithm_type), int(model_type), int(max_iter), int(exchange_num), int(path_type),
                            bool(is_warm_start), int(ic_type), bool(is_cv), int(K), _i(g) if g is not None else None,

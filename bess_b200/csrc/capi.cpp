@@ -91,6 +91,7 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
                 a.col_lo = ext->col_lo;
                 a.p_total = ext->p_total;
                 a.nccl_id = ext->nccl_unique_id;
+                a.cv_reduce_over_ranks = ext->cv_reduce_over_ranks != 0;
             }
         }
         BessResult r;

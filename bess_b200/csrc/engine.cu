@@ -344,6 +344,25 @@ Engine::~Engine()
 
 void Engine::set_profiling(bool on) { d_->prof = on; }
 
+bool Engine::has_comm() const { return d_->comm != nullptr && d_->world > 1; }
+
+void Engine::allreduce_mean(std::vector<double> &v)
+{
+    Impl &m = *d_;
+    if (!has_comm()) throw EngineError{"allreduce_mean: no communicator (call init_shard first)"};
+    if (v.empty()) return;
+    const NcclApi &api = nccl_api();
+    double *buf = dalloc<double>(m.st, v.size());
+    CUDA_CHECK(cudaMemcpyAsync(buf, v.data(), v.size() * 8, cudaMemcpyHostToDevice, m.st));
+    NCCL_CHECK(api.AllReduce(buf, buf, v.size(), ncclDouble, ncclSum, m.comm, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(v.data(), buf, v.size() * 8, cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    dfree(m.st, buf);
+    // the sum is reduced in the same order on every rank (one collective), the division is exact arithmetic on equal
+    // inputs: all ranks hold bit-identical means
+    for (double &x : v) x /= (double)m.world;
+}
+
 void Engine::init_shard(int world, int rank, const void *unique_id, long long col_lo, long long p_total)
 {
     Impl &m = *d_;

@@ -209,6 +209,13 @@ void sequential_path(Driver &dr, BessResult &out, Eval &best)
             cur = next;
         }
     }
+    if (a.cv_reduce_over_ranks && a.world > 1) {
+        // repeated CV: every rank ran its own fold assignment on the shared screened design; average the CV curves
+        std::vector<double> curve(evs.size());
+        for (size_t i = 0; i < evs.size(); i++) curve[i] = evs[i].ic;
+        dr.eng.allreduce_mean(curve);
+        for (size_t i = 0; i < evs.size(); i++) evs[i].ic = curve[i];
+    }
     // ic_sequence.minCoeff (path.cpp:113): Eigen visits the column-major matrix ic(s, lambda) column by column, i.e.
     // lambda outer / s inner, and keeps the first minimum
     size_t bi = 0;
@@ -676,6 +683,9 @@ void bess_run(const BessArgs &a, BessResult &out)
     // bess.cpp:167-180: path_type != 1 runs pgs_path for the L0L2 algorithm types and gs_path otherwise
     const bool pgs = a.path_type != 1 && (a.algorithm_type == 5 || a.algorithm_type == 3);
     if (pgs && a.world > 1) throw EngineError{"pgs_path is not available in column-sharded mode"};
+    if (a.cv_reduce_over_ranks && a.world > 1 && !(a.path_type == 1 && a.is_cv && a.is_screening))
+        throw EngineError{"cv_reduce_over_ranks needs the sequential path with CV and screening (ranks share the screened "
+                          "design and differ only in their folds)"};
     if (pgs && !(a.lambda_min >= 0.0 && a.lambda_max >= 0.0)) throw EngineError{"lambda_min / lambda_max must be >= 0"};
     if (pgs && a.powell_path != 1 && a.powell_path != 2) throw EngineError{"powell_path must be 1 (golden section) or 2 (sequential)"};
     if (a.path_type == 1)

@@ -47,6 +47,10 @@ struct BessArgs {
     int world = 1, rank = 0;
     long long col_lo = 0, p_total = 0;
     const void *nccl_id = nullptr;
+    // repeated K-fold CV over the ranks: each rank passes its own folds (cv_seed / fold_of_row); the per-level CV losses
+    // are averaged over the ranks before the level is chosen, so every rank returns the same model.  Sequential path with
+    // CV and screening only (the ranks then share the screened design but not the folds).
+    bool cv_reduce_over_ranks = false;
 };
 
 struct BessResult {

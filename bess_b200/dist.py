@@ -101,7 +101,7 @@ def nccl_unique_id() -> bytes:
 def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal, model_type, max_iter, path_type,
                        is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, screening_size, cv_seed=123,
                        fold_of_row=None, device=None, x_shard_device_ptr=None, n=None, p_local=None, profile=False,
-                       always_select=(), want_curve=False):
+                       always_select=(), want_curve=False, cv_reduce_over_ranks=False):
     """Multi-GPU fit with the columns of X sharded across the ranks of the current process group (one ``bess_b200_fit``
     call per rank, the library talks NCCL itself).
 
@@ -114,7 +114,10 @@ def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal
         candidates, all-reduce of the k active columns, replicated active-set fit.
     Returns the same dict as ``cbess.fit`` (beta has length p_total), identical on every rank -- unless the ranks pass
     different ``cv_seed`` / ``fold_of_row`` with ``screening_size > 0``: the screening is then still joint, and each rank
-    runs its own CV repetition on the replicated screened design (repeated CV, see ``repeated_cv_reduce``)."""
+    runs its own CV repetition on the replicated screened design.  With ``cv_reduce_over_ranks=True`` the library then
+    averages the per-level CV losses over the ranks itself (one NCCL all-reduce) before choosing the level, so the ranks
+    again return the same model: repeated K-fold CV, one repetition per GPU (``repeated_cv_reduce`` is the same
+    reduction done by the caller with ``torch.distributed``)."""
     import torch
     from . import cbess
     dist = _dist()
@@ -125,7 +128,8 @@ def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal
                      ic_type, is_cv, K, sequence, s_min, s_max, scr > 0, max(scr, 1), always_select=always_select,
                      fold_of_row=fold_of_row, cv_seed=cv_seed, device=device, x_device_ptr=x_shard_device_ptr, n=n,
                      p=p_local, want_trace=False, profile=profile, world=dist.get_world_size(), rank=dist.get_rank(),
-                     col_lo=col_lo, p_total=p_total, nccl_id=nccl_unique_id(), want_curve=want_curve)
+                     col_lo=col_lo, p_total=p_total, nccl_id=nccl_unique_id(), want_curve=want_curve,
+                     cv_reduce_over_ranks=cv_reduce_over_ranks)
 
 
 def repeated_cv_reduce(cv_curve: np.ndarray):

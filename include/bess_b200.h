@@ -80,6 +80,9 @@ typedef struct bess_b200_ext {
     const void *nccl_unique_id; /* 128 bytes from bess_b200_nccl_unique_id() on rank 0, broadcast by the caller       */
     double *chosen_lambda_out;  /* ridge level of the returned model (List key "lambda", path.cpp:129)                 */
     int beta_out_zeroed;        /* beta_out already holds zeros (e.g. calloc): only the non-zero coefficients are written */
+    int cv_reduce_over_ranks;   /* world > 1, sequential path, CV + screening: REPEATED K-fold CV -- every rank passes its  */
+                                /* own folds (cv_seed / fold_of_row), the per-level CV losses are averaged over the ranks   */
+                                /* (one ncclAllReduce) before the level is chosen; all ranks return the same model          */
 } bess_b200_ext;
 
 /* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's

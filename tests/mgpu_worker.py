@@ -70,6 +70,38 @@ def main():
                   f"err={err:.2e} ranks_identical={same} {'OK' if ok and same else 'FAIL'}", flush=True)
         if not (ok and same):
             failures.append(ci)
+    # ---- repeated K-fold CV over the ranks (ext.cv_reduce_over_ranks): every rank draws its own folds, the library averages
+    # the per-level CV losses with one all-reduce and all ranks must return the same model -- the one a single GPU picks
+    # from the average of the per-repetition CV curves
+    n, p, K, smax, scr = 300, 4000, 3, 8, 200
+    d = gen_data(n, p, "gaussian", 6, seed=77)
+    w = np.ones(n)
+    seq = np.arange(1, smax + 1)
+    lo, hi = bdist.shard_range(p, world, rank)
+    xs = np.ascontiguousarray(d.x[:, lo:hi])
+    out = bdist.fit_column_sharded(xs, lo, p, d.y, w, 1, True, 1, 20, 1, True, 1, True, K, seq, 1, smax, scr,
+                                   cv_seed=500 + rank, device=local, cv_reduce_over_ranks=True)
+    curves, models = [], []
+    for r in range(world):  # the same repetitions one after another on this GPU, whole design
+        o = cbess.fit(d.x, d.y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, K, seq, 1, smax, True, scr, cv_seed=500 + r,
+                      device=local, want_trace=True)
+        curves.append(o["ic_all"])
+        models.append(o)
+    mean = np.mean(np.array(curves), axis=0)
+    best = int(np.argmin(mean))
+    exp_beta = models[0]["beta_all"][best]  # the full-data chain does not depend on the folds
+    scale = max(np.abs(exp_beta).max(), 1e-300)
+    ok = (out["s"] == int(seq[best]) and np.nonzero(out["beta"])[0].tolist() == np.nonzero(exp_beta)[0].tolist()
+          and float(np.abs(out["beta"] - exp_beta).max() / scale) < 1e-9 and abs(out["ic"] - mean[best]) <= 1e-9 * abs(mean[best]))
+    t = torch.from_numpy(out["beta"]).cuda()
+    g = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(g, t)
+    same = all(torch.equal(g[0], gi) for gi in g)
+    if rank == 0:
+        print(f"repeated CV over {world} ranks: chosen s={out['s']} expected {int(seq[best])} ranks_identical={same} "
+              f"{'OK' if ok and same else 'FAIL'}", flush=True)
+    if not (ok and same):
+        failures.append("repeated_cv")
     dist.barrier()
     dist.destroy_process_group()
     if failures:
