@@ -12,8 +12,8 @@ sequential s.list=1..20  => one step = one full bessCpp call = 220 PDAS fits (20
   python bench.py --impl reference ...                      the reference's own CPU code (oracle/_ref) on host cores
 
 N > 1.  A single C5 call is 7 ms of which only the 0.6 ms screening sweep is p-sized; the 220 fits behind it run on a
-40 MB screened design and are a chain of ~60 dependent PDAS iterations, so one call cannot be made shorter by more GPUs
-(measured: columns sharded over 2 GPUs, 28.2k -> 30.1k fits/s).  What does shard is what north_star names first: "CV folds
+40 MB screened design and are a chain of ~55 dependent PDAS iterations, so one call cannot be made shorter by more GPUs
+(measured, one call with the columns sharded over 1 / 2 / 4 / 8 GPUs: 6.9 / 6.3 / 6.3 / 6.3 ms).  What does shard is what north_star names first: "CV folds
 and sparsity levels shard embarrassingly, with only per-fold losses reduced".  The N-GPU job is therefore repeated 10-fold
 CV with N repetitions (rank r draws its folds from cv_seed + r): the columns of X are sharded over the ranks for the joint
 screening sweep (local top-k + NCCL all-gather of candidates + all-reduce of the kept columns, inside the library), each
