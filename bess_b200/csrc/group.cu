@@ -19,6 +19,7 @@
 // utilities.cpp:113-130).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 #include "kernels.cuh"
@@ -61,6 +62,90 @@ __device__ void jacobi_eig(double (*A)[GMAX], double (*U)[GMAX], int g)
             }
         if (!rotated) break;
     }
+}
+
+// block + gradient of one group -> its sacrifice (shared by the two sweep kernels below)
+__device__ void group_epilogue(const Dev &d, int c, int g, int j0, int gs, double (&dv)[GMAX], const double (&M)[GMAX * (GMAX + 1) / 2])
+{
+    // M_g + 2 lambda I, d_g - 2 lambda beta_g
+    double A[GMAX][GMAX], U[GMAX][GMAX], bg[GMAX];
+    {
+        int e = 0;
+        for (int a = 0; a < GMAX; a++)
+            for (int bb = a; bb < GMAX; bb++, e++)
+                if (bb < gs) A[a][bb] = A[bb][a] = M[e] + (a == bb ? 2.0 * d.lambda : 0.0);
+    }
+    for (int a = 0; a < gs; a++) {
+        bg[a] = d.betaD[(size_t)c * d.pstride + j0 + a];
+        dv[a] -= 2.0 * d.lambda * bg[a];
+    }
+    double bd;
+    if (gs == 1) {
+        const double phi = sqrt(A[0][0]);
+        const double t = phi * bg[0] + dv[0] / phi;
+        bd = t * t;
+    } else {
+        jacobi_eig(A, U, gs);
+        bd = 0.0;
+        for (int q = 0; q < gs; q++) {
+            double ub = 0.0, ud = 0.0;
+            for (int a = 0; a < gs; a++) {
+                ub = fma(U[a][q], bg[a], ub);
+                ud = fma(U[a][q], dv[a], ud);
+            }
+            const double r = sqrt(A[q][q]);
+            const double t = r * ub + ud / r;
+            bd = fma(t, t, bd);
+        }
+        bd /= (double)gs;
+    }
+    d.bd[(size_t)c * d.pstride + g] = bd;
+}
+
+// Row-parallel variant for the gaussian / logistic / poisson blocks (no risk-set recurrence): one WARP per (group, chain),
+// lane l takes rows l, l + 32, ..., the 8 + 36 partial sums meet in a butterfly reduction (fixed lane order => bitwise
+// reproducible), lane 0 diagonalises.  32 x the threads of the serial kernel: the row walk is no longer a serial chain of
+// n dependent steps per thread.
+__global__ void __launch_bounds__(GS_NT) group_sacrifice_warp_kernel(const Dev d, const BatchDesc b)
+{
+    if (d.gate && *d.gate == 0) return;
+    const int c = b.chain[blockIdx.y];
+    if (d.done[c]) return;
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (GS_NT / 32) + (threadIdx.x >> 5);
+    if (g >= d.N) return;  // warp-uniform
+    const int j0 = d.gidx[g], gs = d.gsz[g];
+    const int FS = d.FS;
+    double dv[GMAX], M[GMAX * (GMAX + 1) / 2];
+#pragma unroll
+    for (int a = 0; a < GMAX; a++) dv[a] = 0.0;
+#pragma unroll
+    for (int e = 0; e < GMAX * (GMAX + 1) / 2; e++) M[e] = 0.0;
+    for (int i = lane; i < d.n; i += 32) {
+        const double gi = d.G[(size_t)i * FS + c], wi = d.W[(size_t)i * FS + c];
+        if (gi == 0.0 && wi == 0.0) continue;  // row outside the chain's train mask
+        const double *xr = d.X + (size_t)i * d.ldx + j0;
+        double x[GMAX];
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) x[a] = a < gs ? __ldg(xr + a) : 0.0;
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) dv[a] = fma(x[a], gi, dv[a]);
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) {
+            const double wa = wi * x[a];
+#pragma unroll
+            for (int bb = a; bb < GMAX; bb++, e++) M[e] = fma(wa, x[bb], M[e]);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) dv[a] += __shfl_xor_sync(0xffffffffu, dv[a], off);
+#pragma unroll
+        for (int e = 0; e < GMAX * (GMAX + 1) / 2; e++) M[e] += __shfl_xor_sync(0xffffffffu, M[e], off);
+    }
+    if (lane == 0) group_epilogue(d, c, g, j0, gs, dv, M);
 }
 
 template <bool COX>
@@ -108,39 +193,7 @@ __global__ void __launch_bounds__(GS_NT) group_sacrifice_kernel(const Dev d, con
             }
         }
     }
-    // M_g + 2 lambda I, d_g - 2 lambda beta_g
-    double A[GMAX][GMAX], U[GMAX][GMAX], bg[GMAX];
-    {
-        int e = 0;
-        for (int a = 0; a < GMAX; a++)
-            for (int bb = a; bb < GMAX; bb++, e++)
-                if (bb < gs) A[a][bb] = A[bb][a] = M[e] + (a == bb ? 2.0 * d.lambda : 0.0);
-    }
-    for (int a = 0; a < gs; a++) {
-        bg[a] = d.betaD[(size_t)c * d.pstride + j0 + a];
-        dv[a] -= 2.0 * d.lambda * bg[a];
-    }
-    double bd;
-    if (gs == 1) {
-        const double phi = sqrt(A[0][0]);
-        const double t = phi * bg[0] + dv[0] / phi;
-        bd = t * t;
-    } else {
-        jacobi_eig(A, U, gs);
-        bd = 0.0;
-        for (int q = 0; q < gs; q++) {
-            double ub = 0.0, ud = 0.0;
-            for (int a = 0; a < gs; a++) {
-                ub = fma(U[a][q], bg[a], ub);
-                ud = fma(U[a][q], dv[a], ud);
-            }
-            const double r = sqrt(A[q][q]);
-            const double t = r * ub + ud / r;
-            bd = fma(t, t, bd);
-        }
-        bd /= (double)gs;
-    }
-    d.bd[(size_t)c * d.pstride + g] = bd;
+    group_epilogue(d, c, g, j0, gs, dv, M);
 }
 
 // find_ind (utilities.cpp:113-130): the T selected groups (ascending) -> their columns, in order
@@ -163,9 +216,19 @@ __global__ void group_expand_kernel(const Dev d, const BatchDesc b)
 
 void launch_group_sacrifice(const Dev &d, const BatchDesc &b, cudaStream_t st)
 {
-    const dim3 grid((unsigned)((d.N + GS_NT - 1) / GS_NT), (unsigned)b.nch);
-    if (d.family == FAM_COX) group_sacrifice_kernel<true><<<grid, GS_NT, 0, st>>>(d, b);
-    else group_sacrifice_kernel<false><<<grid, GS_NT, 0, st>>>(d, b);
+    static const bool serial = [] {
+        const char *e = std::getenv("BESS_B200_GROUP_SERIAL");
+        return e && e[0] == '1';
+    }();
+    if (d.family == FAM_COX || serial) {
+        const dim3 grid((unsigned)((d.N + GS_NT - 1) / GS_NT), (unsigned)b.nch);
+        if (d.family == FAM_COX) group_sacrifice_kernel<true><<<grid, GS_NT, 0, st>>>(d, b);
+        else group_sacrifice_kernel<false><<<grid, GS_NT, 0, st>>>(d, b);
+    } else {
+        const int wpb = GS_NT / 32;
+        const dim3 grid((unsigned)((d.N + wpb - 1) / wpb), (unsigned)b.nch);
+        group_sacrifice_warp_kernel<<<grid, GS_NT, 0, st>>>(d, b);
+    }
     CUDA_CHECK(cudaGetLastError());
 }
 void launch_group_expand(const Dev &d, const BatchDesc &b, cudaStream_t st)
