@@ -74,6 +74,7 @@ def load():
     lib.bess_b200_chain_owner.argtypes = [C.c_int, C.c_int]
     lib.bess_b200_nccl_unique_id.argtypes = [C.c_void_p]
     lib.bess_b200_trace_lambda.argtypes = [dp]
+    lib.bess_b200_pgs_line_box.argtypes = [dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
     lib.bess_b200_gen_design.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_double, C.c_ulonglong, C.c_int]
     lib.bess_b200_merge_candidates.argtypes = [dp, ip, C.c_int, C.c_int, ip]
     _lib = lib

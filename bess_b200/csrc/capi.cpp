@@ -249,6 +249,12 @@ int bess_b200_gen_design(double *x_dev, int n, long long p, long long ld, double
     });
 }
 
+int bess_b200_pgs_line_box(const double *p2, const double *u2, int s_min, int s_max, double log_lambda_min, double log_lambda_max,
+                           double *a2_out, double *b2_out)
+{
+    return pgs_line_box(p2, u2, s_min, s_max, log_lambda_min, log_lambda_max, a2_out, b2_out);
+}
+
 const char *bess_b200_last_error(void) { return g_err.c_str(); }
 int bess_b200_version(void) { return BESS_B200_VERSION; }
 int bess_b200_device_count(void)

@@ -30,6 +30,59 @@ std::vector<int> cv_fold_ids(int n, int K, unsigned seed)
     return fold;
 }
 
+// path.cpp:414-577 (line_intersection + cal_intersections): the points where the line p + t*u leaves the box
+// [s_min, s_max] x [lmin, lmax]; a <- first, b <- second (in the reference's edge order); returns how many were found.
+int pgs_line_box(const double p[2], const double u[2], int s_min, int s_max, double lmin, double lmax, double a[2], double b[2])
+{
+    auto det = [](const double x[2], const double y[2]) { return x[0] * y[1] - x[1] * y[0]; };
+    auto line_intersection = [&](double l1[2][2], double l2[2][2], double x[2], bool &need) {
+        double xdiff[2] = {l1[0][0] - l1[1][0], l2[0][0] - l2[1][0]};
+        double ydiff[2] = {l1[0][1] - l1[1][1], l2[0][1] - l2[1][1]};
+        const double div = det(xdiff, ydiff);
+        if (div == 0) {
+            need = false;
+            return;
+        }
+        double d[2] = {det(l1[0], l1[1]), det(l2[0], l2[1])};
+        x[0] = det(d, xdiff) / div;
+        x[1] = det(d, ydiff) / div;
+        need = true;
+    };
+    double line0[2][2] = {{p[0], p[1]}, {p[0] + u[0], p[1] + u[1]}};
+    double ls[4][2][2] = {{{(double)s_min, lmin}, {(double)s_min, lmax}},
+                          {{(double)s_max, lmin}, {(double)s_max, lmax}},
+                          {{(double)s_min, lmin}, {(double)s_max, lmin}},
+                          {{(double)s_min, lmax}, {(double)s_max, lmax}}};
+    double x[4][2] = {};
+    bool need[4];
+    for (int i = 0; i < 4; i++) line_intersection(line0, ls[i], x[i], need[i]);
+    for (int i = 0; i < 4; i++)
+        if (need[i] && ((x[i][0] < s_min - 0.0001) | (x[i][0] > s_max + 0.0001) | (x[i][1] < lmin - 0.001) |
+                        (x[i][1] > lmax + 0.001)))
+            need[i] = false;
+    for (int i = 0; i < 4; i++)
+        if (need[i])
+            for (int j = i + 1; j < 4; j++)
+                if (need[j] && std::fabs(x[i][0] - x[j][0]) < 0.0001 && std::fabs(x[i][1] - x[j][1]) < 0.0001)
+                    need[j] = false;
+    int j = 0;
+    for (int i = 0; i < 4; i++)
+        if (need[i]) {
+            if (j == 2) j += 1;
+            if (j == 1) {
+                b[0] = x[i][0];
+                b[1] = x[i][1];
+                j += 1;
+            }
+            if (j == 0) {
+                a[0] = x[i][0];
+                a[1] = x[i][1];
+                j += 1;
+            }
+        }
+    return j;
+}
+
 namespace {
 
 struct Eval {
@@ -324,61 +377,11 @@ struct Pgs {
     bool warm;
 
     static int sign(double a) { return a > 0 ? 1 : (a < 0 ? -1 : 0); }  // path.cpp:391-405
-    static double det(const double a[2], const double b[2]) { return a[0] * b[1] - a[1] * b[0]; }
-
-    // path.cpp:414-440
-    static void line_intersection(double l1[2][2], double l2[2][2], double x[2], bool &need)
-    {
-        double xdiff[2] = {l1[0][0] - l1[1][0], l2[0][0] - l2[1][0]};
-        double ydiff[2] = {l1[0][1] - l1[1][1], l2[0][1] - l2[1][1]};
-        const double div = det(xdiff, ydiff);
-        if (div == 0) {
-            need = false;
-            return;
-        }
-        double d[2] = {det(l1[0], l1[1]), det(l2[0], l2[1])};
-        x[0] = det(d, xdiff) / div;
-        x[1] = det(d, ydiff) / div;
-        need = true;
-    }
-
-    // path.cpp:445-577: the two points where the line p + t*u leaves the box [s_min, s_max] x [lmin, lmax]
     void cal_intersections(const double p[2], const double u[2], double a[2], double b[2]) const
     {
-        double line0[2][2] = {{p[0], p[1]}, {p[0] + u[0], p[1] + u[1]}};
-        double ls[4][2][2] = {{{(double)s_min, lmin}, {(double)s_min, lmax}},
-                              {{(double)s_max, lmin}, {(double)s_max, lmax}},
-                              {{(double)s_min, lmin}, {(double)s_max, lmin}},
-                              {{(double)s_min, lmax}, {(double)s_max, lmax}}};
-        double x[4][2] = {};
-        bool need[4];
-        for (int i = 0; i < 4; i++) line_intersection(line0, ls[i], x[i], need[i]);
-        for (int i = 0; i < 4; i++)
-            if (need[i] && ((x[i][0] < s_min - 0.0001) | (x[i][0] > s_max + 0.0001) | (x[i][1] < lmin - 0.001) |
-                            (x[i][1] > lmax + 0.001)))
-                need[i] = false;
-        for (int i = 0; i < 4; i++)
-            if (need[i])
-                for (int j = i + 1; j < 4; j++)
-                    if (need[j] && std::fabs(x[i][0] - x[j][0]) < 0.0001 && std::fabs(x[i][1] - x[j][1]) < 0.0001)
-                        need[j] = false;
-        int j = 0;
-        for (int i = 0; i < 4; i++)
-            if (need[i]) {
-                if (j == 2) j += 1;
-                if (j == 1) {
-                    b[0] = x[i][0];
-                    b[1] = x[i][1];
-                    j += 1;
-                }
-                if (j == 0) {
-                    a[0] = x[i][0];
-                    a[1] = x[i][1];
-                    j += 1;
-                }
-            }
         // the reference prints a diagnostic and carries on with uninitialised end points (path.cpp:539-574)
-        if (j < 2) throw EngineError{"pgs_path: search line does not cross the (s, lambda) box twice"};
+        if (pgs_line_box(p, u, s_min, s_max, lmin, lmax, a, b) < 2)
+            throw EngineError{"pgs_path: search line does not cross the (s, lambda) box twice"};
     }
 
     // One evaluation: full-data fit at (T, exp(loglam)) then metric->ic() and metric->train_loss() in the order every

@@ -83,6 +83,9 @@ struct BessResult {
 // Metric.h:49-106 with the seed pinned (same std::mt19937 + std::shuffle + chunking)
 std::vector<int> cv_fold_ids(int n, int K, unsigned seed);
 
+// pgs_path geometry (path.cpp:414-577), host only: where the line p + t*u leaves the (s, log lambda) box
+int pgs_line_box(const double p[2], const double u[2], int s_min, int s_max, double lmin, double lmax, double a[2], double b[2]);
+
 // throws EngineError
 void bess_run(const BessArgs &a, BessResult &out);
 

@@ -162,6 +162,12 @@ int bessgpu_stats(bessgpu_handle *h, double *out8);
  * the k-th straddle the boundary */
 int bessgpu_topk(const double *vals, int n, int k, int *idx_out, int *tie_out);
 
+/* pgs_path geometry (path.cpp:414-577, pure host code): the points where the search line p + t*u leaves the box
+ * [s_min, s_max] x [log_lambda_min, log_lambda_max]; a2_out / b2_out receive the first two in the reference's edge order.
+ * Returns the number of crossings found (the Powell search needs 2). */
+int bess_b200_pgs_line_box(const double *p2, const double *u2, int s_min, int s_max, double log_lambda_min, double log_lambda_max,
+                           double *a2_out, double *b2_out);
+
 /* ---- 3. multi-GPU host helpers (pure host code, no CUDA) ------------------------------------------------------ */
 /* contiguous column shard [lo, hi) of rank r out of `world` (SURVEY 8e axis B) */
 void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi);

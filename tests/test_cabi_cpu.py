@@ -144,3 +144,29 @@ def test_frontend_argument_surface(monkeypatch):
     assert list(seen["args"][14]) == list(range(0, 30, 3))
     with pytest.raises(ValueError):
         m.fit(x, x[:, 0], group=[0, 1])
+
+
+def test_pgs_line_box_matches_the_oracle():
+    """Host logic of the Powell path (path.cpp:414-577) without a GPU: the library's line/box intersection against the
+    numpy restatement on random lines through random points of the (s, log lambda) box, incl. axis-parallel directions."""
+    import ctypes as C
+    from bess_b200._lib import dp
+    from oracle import pdas_oracle as orc
+    lib = _lib()
+    rng = np.random.default_rng(5)
+    s_min, s_max, lmin, lmax = 2, 17, float(np.log(1e-3)), float(np.log(50.0))
+    dirs = [(1.0, 0.0), (0.0, 0.1), (3.0, -0.7), (-2.0, 1.3), (5.0, 2.0)]
+    for t in range(200):
+        p = np.array([float(rng.integers(s_min, s_max + 1)), rng.uniform(lmin, lmax)])
+        u = np.array(dirs[t % len(dirs)]) if t < 100 else np.array([float(rng.integers(-6, 7)), rng.normal()])
+        if u[0] == 0.0 and abs(u[1]) < 1e-3:
+            continue
+        a, b = np.zeros(2), np.zeros(2)
+        n = lib.bess_b200_pgs_line_box(p.ctypes.data_as(dp), u.ctypes.data_as(dp), s_min, s_max, lmin, lmax,
+                                       a.ctypes.data_as(dp), b.ctypes.data_as(dp))
+        try:
+            ea, eb = orc._cal_intersections(p, u, s_min, s_max, lmin, lmax)
+        except ValueError:
+            assert n < 2
+            continue
+        assert n >= 2 and np.array_equal(a, np.array(ea)) and np.array_equal(b, np.array(eb))
