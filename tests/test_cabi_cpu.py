@@ -170,3 +170,13 @@ def test_pgs_line_box_matches_the_oracle():
             assert n < 2
             continue
         assert n >= 2 and np.array_equal(a, np.array(ea)) and np.array_equal(b, np.array(eb))
+
+
+@pytest.mark.parametrize("compiler,std,ext", [("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "cpp")])
+def test_public_header_is_self_contained(tmp_path, compiler, std, ext):
+    """include/bess_b200.h is what a maintainer binds against (cgo / Rcpp / SWIG): it must compile on its own as C and C++."""
+    src = tmp_path / f"hdr.{ext}"
+    src.write_text('#include "bess_b200.h"\nint main(void) { return 0; }\n')
+    r = subprocess.run([compiler, std, "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
