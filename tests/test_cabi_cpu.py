@@ -180,3 +180,39 @@ def test_public_header_is_self_contained(tmp_path, compiler, std, ext):
     r = subprocess.run([compiler, std, "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_program_links_and_calls_the_library(tmp_path):
+    """The boundary is a C ABI: a C99 program compiled with gcc links against libbess_b200.so and calls host-only entry
+    points (no GPU here); a compute entry fails loudly with a status code and a message instead of falling back."""
+    src = tmp_path / "client.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "bess_b200.h"
+int main(void) {
+    long long lo = -1, hi = -1;
+    double p[2] = {3.0, 0.5}, u[2] = {1.0, 0.0}, a[2], b[2];
+    if (bess_b200_version() != BESS_B200_VERSION) return 10;
+    bess_b200_shard_range(1001, 4, 3, &lo, &hi);
+    if (!(lo >= 0 && hi == 1001 && lo < hi)) return 11;
+    if (bess_b200_pgs_line_box(p, u, 1, 9, 0.0, 2.0, a, b) != 2 || a[0] != 1.0 || b[0] != 9.0) return 12;
+    if (bess_b200_device_count() == 0) {
+        double x[6] = {1, 2, 3, 4, 5, 7}, y[3] = {1, 2, 3}, w[3] = {1, 1, 1}, beta[2], c0, tl, ic;
+        int seq[1] = {1};
+        double lam[1] = {0.0}, st[1] = {0.0};
+        int rc = bess_b200_fit(x, 3, 2, y, 3, 1, w, 3, 1, 1, 1, 20, 2, 1, 1, 3, 0, 5, NULL, 0, st, 1, seq, 1, lam, 1, 1, 1, 10,
+                               10.0, 0.0, 0.0, 1, 0, 1, 1, NULL, 0, 1.1, beta, 2, &c0, &tl, &ic, NULL);
+        if (rc == 0 || strlen(bess_b200_last_error()) == 0) return 13;   /* no GPU: must fail loudly, never fall back */
+    }
+    printf("ok\n");
+    return 0;
+}
+""")
+    exe = tmp_path / "client"
+    libdir = os.path.join(ROOT, "bess_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                        "-lbess_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
