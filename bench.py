@@ -168,6 +168,9 @@ def run_reference(args):
     total = args.warmup + args.steps
     levels = int(max(1, min(CPU_SMAX, 150.0 / (max(total, 1) * 3.5))))  # keep the whole run within a few minutes
     procs = max(1, min(os.cpu_count() or 1, 16))
+    # test overrides (tests/test_bench_contract.py runs this arm on a tiny sample)
+    levels = int(os.environ.get("BESS_BENCH_REF_LEVELS", levels))
+    procs = int(os.environ.get("BESS_BENCH_REF_PROCS", procs))
     d, p = _ref_sample(levels)
     ctx = mp.get_context("fork")
     barrier, q = ctx.Barrier(procs), ctx.Queue()
