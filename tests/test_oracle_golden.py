@@ -67,3 +67,29 @@ def test_oracle_group_selection_matches_reference(name):
     assert abs(out["ic"] - g["ic"]) <= RTOL * abs(g["ic"])
     assert abs(out["lam"] - g["lam"]) <= 1e-12 * max(abs(g["lam"]), 1e-300) if "lam" in out else True
     assert out["min_gap"] > 1e-9, "a top-k decision sits inside rounding noise"
+
+
+@pytest.mark.parametrize("model_type,data_type,fam", [(1, 1, "gaussian"), (2, 2, "binomial"), (3, 2, "poisson"), (4, 3, "cox")])
+def test_group_sacrifice_with_singleton_groups_is_the_column_sacrifice(model_type, data_type, fam):
+    """Self-consistency of the restatement: with every column its own group the k_g x k_g blocks are 1 x 1 and the group
+    sacrifice (Algorithm.h:1097-1129, 1206-1263, 1324-1367, 1497-1568) must equal the per-column one -- for cox the dense
+    n x n Hessian branch of algorithm_type 2/3 against the suffix-sum branch of algorithm_type 1 (:1569-1640), whose value
+    is the square root of the former."""
+    from bess_b200.gen_data import gen_data
+    n, p = 120, 40
+    d = gen_data(n, p, fam, 4, seed=301)
+    w = np.random.default_rng(1).uniform(0.5, 1.5, n)
+    data = orc.make_data(d.x, d.y, w, data_type, True, model_type)
+    rng = np.random.default_rng(2)
+    beta = np.zeros(p)
+    beta[rng.choice(p, 5, replace=False)] = rng.normal(0, 0.3, 5)
+    coef0 = 0.1 if model_type in (2, 3) else 0.0
+    gi, gs = orc.group_layout(np.arange(p), p)
+    for lam in (0.0, 0.05):
+        xtx_cols = (data.x * data.x).sum(axis=0)
+        col = orc._SACRIFICE[model_type](data.x, data.y, data.weight, beta, coef0, xtx_cols, lam=lam)
+        grp = orc.group_sacrifice(model_type, data.x, data.y, data.weight, beta, coef0, orc.group_gram_lm(data.x, gi, gs), lam,
+                                  gi, gs)
+        want = col ** 2 if model_type == 4 else col
+        assert rel_err(grp, want) < 1e-10
+        assert orc.max_k(grp, 6).tolist() == orc.max_k(col, 6).tolist()
