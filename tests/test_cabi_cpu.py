@@ -216,3 +216,27 @@ int main(void) {
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_reference_module_names_resolve_to_this_library():
+    """bess_b200.compat.install_as_bess(): `from bess.linear import PdasLm` / `from bess.cbess import pywrap_bess` of
+    unmodified user code land in this package (python/bess/linear.py:434-925, python/bess/cbess.py:65-66)."""
+    import importlib
+    import sys
+    from bess_b200 import compat
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "bess" or k.startswith("bess.")}
+    try:
+        compat.install_as_bess()
+        lin = importlib.import_module("bess.linear")
+        from bess.cbess import pywrap_bess  # noqa: F401
+        from bess.linear import GroupPdasCox, L0L2Logistic, PdasLm
+        import bess_b200.linear
+        assert lin is bess_b200.linear and PdasLm is bess_b200.linear.PdasLm
+        assert L0L2Logistic().algorithm_type_int == 5 and GroupPdasCox().model_type_int == 4
+        sys.modules["bess"] = type(sys)("bess")  # somebody else's bess
+        with pytest.raises(ImportError):
+            compat.install_as_bess()
+    finally:
+        for k in [k for k in sys.modules if k == "bess" or k.startswith("bess.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
