@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libbess_b200.so")
-SOURCES = ["kernels.cu", "sweep_tma.cu", "chain_fit.cu", "group.cu", "gen_design.cu", "engine.cu", "path.cpp", "capi.cpp", "pywrap_cxx.cpp", "nccl_dl.cpp"]
+SOURCES = ["kernels.cu", "sweep_tma.cu", "chain_fit.cu", "lm_path.cu", "group.cu", "gen_design.cu", "engine.cu", "path.cpp", "capi.cpp", "pywrap_cxx.cpp", "nccl_dl.cpp"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-diag-suppress", "550"]
 

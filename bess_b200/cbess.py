@@ -123,6 +123,8 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     ext.chosen_lambda_out = C.pointer(chosen_lam)
     stats = np.zeros(32)
     ext.stats_out = _d(stats)
+    resident = np.zeros(24)
+    ext.resident_out = _d(resident)
     ext.profile = 1 if profile else 0
     ext.beta_out_zeroed = 1  # `beta` comes from np.zeros (calloc): untouched pages stay untouched
     ext.cv_reduce_over_ranks = 1 if (cv_reduce_over_ranks and sharded) else 0
@@ -141,6 +143,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
                           kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[24]),
                           sweep_splits=int(stats[25]), norm_bytes=float(stats[26]),
                           host_ms=dict(zip(("load", "screen", "normalize", "setup_chains", "path"), stats[27:32].tolist())),
+                          resident=resident.tolist(),
                           prof_ms=dict(zip(PROF_CATS, stats[8:16].tolist())),
                           prof_launches=dict(zip(PROF_CATS, [int(v) for v in stats[16:24]]))))
     if is_screening:

@@ -1,6 +1,7 @@
 // Device engine: owns the design matrix and all chain state in HBM and drives the kernels of kernels.cu.
 // See engine.h for the vocabulary.  All compute is on the GPU; there is no CPU fallback anywhere in this file.
 #include "kernels.cuh"
+#include "lm_path.cuh"
 #include "device_utils.cuh"
 #include "nccl_dl.h"
 
@@ -52,11 +53,31 @@ struct DeviceContext {
     int *h_A = nullptr;          // grow-only: [2][MAXC][kcap]
     double *h_bA = nullptr;
     size_t cap_A = 0;
+    // resident path (lm_path.cu): result mirrors, two slots each, grow-only
+    int *h_lp_i = nullptr;
+    double *h_lp_d = nullptr;
+    unsigned *h_lp_sync = nullptr;           // [2][LP_SYNC_WORDS]
+    unsigned long long *h_lp_dbg = nullptr;  // [2][LP_NDBG]
+    size_t cap_lp = 0;                        // entries per slot
     bool in_use = false;
     // NCCL communicator of the column-sharded mode, created once per (world, rank, unique id)
     ncclComm_t comm = nullptr;
     int comm_world = 0, comm_rank = -1;
     char comm_id[NCCL_UNIQUE_ID_BYTES] = {};
+    void reserve_resident(size_t count)
+    {
+        if (!h_lp_sync) {
+            CUDA_CHECK(cudaMallocHost(&h_lp_sync, 2 * LP_SYNC_WORDS * sizeof(unsigned)));
+            CUDA_CHECK(cudaMallocHost(&h_lp_dbg, 2 * LP_NDBG * sizeof(unsigned long long)));
+        }
+        if (count <= cap_lp) return;
+        if (h_lp_i) cudaFreeHost(h_lp_i);
+        if (h_lp_d) cudaFreeHost(h_lp_d);
+        h_lp_i = nullptr; h_lp_d = nullptr; cap_lp = 0;
+        CUDA_CHECK(cudaMallocHost(&h_lp_i, 2 * count * sizeof(int)));
+        CUDA_CHECK(cudaMallocHost(&h_lp_d, 2 * count * sizeof(double)));
+        cap_lp = count;
+    }
     void reserve_support(size_t count)
     {
         if (count <= cap_A) return;
@@ -146,6 +167,8 @@ struct Engine::Impl {
         BatchDesc b{};
         LossDesc ld{};
         bool has_jobs = false, fused = false, pending = false;
+        bool resident = false, loss_kernel = false;  // resident: one lm_path launch; loss_kernel: jobs it cannot express
+        LpDesc lp{};
         int T = 0, slot = 0, enq = 0, cmin = 0, cmax = 0;
         long long launches = 0;
         cudaEvent_t ev = nullptr;
@@ -177,6 +200,19 @@ struct Engine::Impl {
     long long mstride = 0;
     int *Aloc = nullptr;                         // [C][kcap] local top-k (local column indices)
     double *AXs = nullptr;                       // [C][n][T] this rank's contribution to the active columns
+    // ---- resident path (lm_path.cu)
+    bool lp_ok = false;
+    std::string lp_why = "chains not set up";
+    int lp_ns = 0;
+    size_t lp_res_count = 0;               // result entries per slot
+    unsigned *lp_sync = nullptr;           // device [2][LP_SYNC_WORDS]
+    LpCand *lp_cand = nullptr;
+    int *lp_ncand = nullptr;
+    double *lp_pub = nullptr, *lp_tau = nullptr;
+    int *lp_res_i = nullptr;               // device [2][lp_res_count]
+    double *lp_res_d = nullptr;
+    unsigned long long *lp_dbg = nullptr;  // device [LP_NDBG]
+    double lp_counters[24] = {};
     // ---- per-category device timing (CUDA events on the engine stream), enabled by Engine::set_profiling
     bool prof = false;
     struct Span { cudaEvent_t a, b; int cat; };
@@ -238,6 +274,9 @@ struct Engine::Impl {
         dfree(m.st, d.AXr); dfree(m.st, d.AXk);
         dfree(m.st, slots.A); dfree(m.st, slots.bA); dfree(m.st, slots.ks); dfree(m.st, slots.coef0);
         dfree(m.st, d.Tc); dfree(m.st, d.AnewCols);
+        dfree(m.st, lp_sync); dfree(m.st, lp_cand); dfree(m.st, lp_ncand); dfree(m.st, lp_pub); dfree(m.st, lp_tau);
+        dfree(m.st, lp_res_i); dfree(m.st, lp_res_d); dfree(m.st, lp_dbg);
+        lp_ok = false;
         chains_ready = false;
     }
     // (re)allocate the sweep vectors / partial buffers for FS chain slots over the current (n, p)
@@ -973,9 +1012,170 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
         m.mir[q].bA = m.ctx->h_bA + (size_t)q * MAXC * kcap;
         m.tk[q].pending = false;
     }
+    // ---- resident path (lm_path.cu): one cooperative launch per path segment when the problem fits
+    m.lp_why.clear();
+    m.lp_ok = lm_path_eligible(d, max_iter, m.sm_count, &m.lp_why);
+    if (m.lp_ok) {
+        int coop = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m.ctx->device));
+        if (!coop) {
+            m.lp_ok = false;
+            m.lp_why = "device without cooperative launch";
+        }
+    }
+    if (m.lp_ok) {
+        m.lp_ns = lm_path_slots(d, max_iter);
+        m.lp_res_count = (size_t)LP_MAXSTEP * MAXC * (2 + kcap);
+        m.lp_sync = dalloc<unsigned>(m.st, 2 * LP_SYNC_WORDS);
+        m.lp_cand = dalloc<LpCand>(m.st, (size_t)MAXC * LP_CAP);
+        m.lp_ncand = dalloc<int>(m.st, MAXC);
+        m.lp_pub = dalloc<double>(m.st, 2 * MAXC);
+        m.lp_tau = dalloc<double>(m.st, MAXC);
+        m.lp_res_i = dalloc<int>(m.st, 2 * m.lp_res_count);
+        m.lp_res_d = dalloc<double>(m.st, 2 * m.lp_res_count);
+        m.lp_dbg = dalloc<unsigned long long>(m.st, LP_NDBG);
+        std::vector<double> inf(MAXC, INFINITY);  // no candidate threshold yet: the first select reads the whole vector
+        CUDA_CHECK(cudaMemcpyAsync(m.lp_tau, inf.data(), MAXC * 8, cudaMemcpyHostToDevice, m.st));
+        CUDA_CHECK(cudaMemsetAsync(m.lp_pub, 0, 2 * MAXC * 8, m.st));
+        CUDA_CHECK(cudaMemsetAsync(m.lp_dbg, 0, LP_NDBG * 8, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));  // `inf` must outlive the copy
+        m.ctx->reserve_resident(m.lp_res_count);
+    }
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     S_ = d.S;
     m.chains_ready = true;
+}
+
+bool Engine::resident_path() const { return d_->lp_ok; }
+const std::string &Engine::resident_path_why() const { return d_->lp_why; }
+void Engine::resident_counters(double *out24) const
+{
+    for (int i = 0; i < 24; i++) out24[i] = d_->lp_counters[i];
+}
+
+// Enqueue one launch of the resident kernel for the batch in t.b: memsets, kernel, result copies into the slot's pinned
+// mirrors.  The caller records the ticket's event.
+static void lp_launch(Engine::Impl &m, Engine::Impl::Ticket &t, const PathStep *steps, int nsteps)
+{
+    const Dev &d = t.d;
+    if (nsteps < 1 || nsteps > LP_MAXSTEP) throw EngineError{"resident path: bad step count"};
+    LpDesc &L = t.lp;
+    L = LpDesc{};
+    L.nsteps = nsteps;
+    L.nch = t.b.nch;
+    L.n_always = m.n_always;
+    L.nsweep = m.sm_count - t.b.nch;
+    L.ns = m.lp_ns;
+    L.hist_rows = d.max_iter + 2;
+    for (int q = 0; q < nsteps; q++) {
+        if (steps[q].T < 1 || steps[q].T > m.Tmax) throw EngineError{"sparsity level outside [1, kcap]"};
+        if (!(steps[q].lambda >= 0.0)) throw EngineError{"lambda must be >= 0"};
+        L.T[q] = steps[q].T;
+        L.lam[q] = steps[q].lambda;
+    }
+    for (int i = 0; i < t.b.nch; i++) L.chain[i] = t.b.chain[i];
+    L.always = m.always;
+    L.y = m.y;
+    L.sync = m.lp_sync + (size_t)t.slot * LP_SYNC_WORDS;
+    L.cand = m.lp_cand;
+    L.ncand = m.lp_ncand;
+    L.pub = m.lp_pub;
+    L.tau = m.lp_tau;
+    L.res_i = m.lp_res_i + (size_t)t.slot * m.lp_res_count;
+    L.res_d = m.lp_res_d + (size_t)t.slot * m.lp_res_count;
+    L.dbg = m.lp_dbg;
+    CUDA_CHECK(cudaMemsetAsync(L.sync, 0, LP_SYNC_WORDS * sizeof(unsigned), m.st));
+    CUDA_CHECK(cudaMemsetAsync(m.lp_ncand, 0, MAXC * sizeof(int), m.st));
+    const int sp = m.span_begin(4);
+    launch_lm_path(d, L, m.sm_count, d.max_iter, m.st);
+    m.span_end(sp);
+    const size_t cnt = (size_t)nsteps * t.b.nch * (2 + d.kcap);
+    DeviceContext *c = m.ctx;
+    CUDA_CHECK(cudaMemcpyAsync(c->h_lp_i + (size_t)t.slot * c->cap_lp, L.res_i, cnt * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(c->h_lp_d + (size_t)t.slot * c->cap_lp, L.res_d, cnt * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(c->h_lp_sync + (size_t)t.slot * LP_SYNC_WORDS, L.sync, LP_SYNC_WORDS * sizeof(unsigned),
+                               cudaMemcpyDeviceToHost, m.st));
+    CUDA_CHECK(cudaMemcpyAsync(c->h_lp_dbg + (size_t)t.slot * LP_NDBG, m.lp_dbg, LP_NDBG * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, m.st));
+}
+
+// After the ticket's event: unpack the slot's mirrors.  outs[q] <- batch result of step q; la / lt [q * nch + i].
+static void lp_parse(Engine::Impl &m, const Engine::Impl::Ticket &t, EngineStats &stats, BatchResult *outs, double *la, double *lt)
+{
+    const Dev &d = t.d;
+    const LpDesc &L = t.lp;
+    DeviceContext *c = m.ctx;
+    const unsigned *sy = c->h_lp_sync + (size_t)t.slot * LP_SYNC_WORDS;
+    if (sy[LP_SYNC_ABORT] != 0u || sy[LP_SYNC_TERM] == 0u)
+        throw EngineError{"resident path: the kernel did not finish (phase barrier watchdog)"};
+    const int *ri0 = c->h_lp_i + (size_t)t.slot * c->cap_lp;
+    const double *rd0 = c->h_lp_d + (size_t)t.slot * c->cap_lp;
+    const int nch = L.nch, kc = d.kcap;
+    for (int q = 0; q < L.nsteps; q++) {
+        BatchResult &o = outs[q];
+        o.T = L.T[q];
+        o.nchains = nch;
+        for (int i = 0; i < nch; i++) {
+            const int *ri = ri0 + ((size_t)q * nch + i) * (2 + kc);
+            const double *rd = rd0 + ((size_t)q * nch + i) * (2 + kc);
+            o.chain_ids[i] = L.chain[i];
+            o.l[i] = ri[0];
+            o.coef0[i] = 0.0;  // the gaussian fit leaves coef0 at coef0_init = 0 (Algorithm.h:1131-1135)
+            o.A[i].assign(ri + 2, ri + 2 + L.T[q]);
+            o.bA[i].assign(rd + 2, rd + 2 + L.T[q]);
+            la[(size_t)q * nch + i] = rd[0];
+            lt[(size_t)q * nch + i] = rd[1];
+            stats.n_pdas_iters += std::min(ri[0], d.max_iter);
+            stats.n_boundary_ties += ri[1];
+        }
+    }
+    const double iters = (double)sy[LP_SYNC_ITERS];
+    stats.n_sweeps += (long long)iters;
+    stats.sweep_bytes += iters * (8.0 * d.n * d.p + 8.0 * d.n * nch + 8.0 * d.p * nch);
+    stats.kernel_launches += 1;
+    stats.n_fits += (long long)nch * L.nsteps;
+    stats.n_batches += L.nsteps;
+    m.lp_counters[0] += 1.0;
+    m.lp_counters[1] += iters;
+    m.lp_counters[2] += (double)sy[LP_SYNC_FALLBACKS];
+    m.lp_counters[3] += (double)L.nsteps;
+    const unsigned long long *dbg = c->h_lp_dbg + (size_t)t.slot * LP_NDBG;  // cumulative since setup_chains
+    for (int q = 0; q < 8; q++) m.lp_counters[8 + q] = (double)dbg[q];
+    for (int q = 0; q < 3; q++) m.lp_counters[16 + q] = (double)dbg[16 + q];
+}
+
+void Engine::run_steps(const std::vector<PathStep> &steps, const std::vector<int> &chains, std::vector<BatchResult> &out,
+                       std::vector<double> &loss_all, std::vector<double> &loss_test)
+{
+    Impl &m = *d_;
+    if (!m.chains_ready || !m.lp_ok) throw EngineError{"run_steps: the resident path is not available (" + m.lp_why + ")"};
+    if (m.tk[0].pending || m.tk[1].pending) throw EngineError{"run_steps: a batch is still pending"};
+    if (chains.empty() || (int)chains.size() > m.nchains) throw EngineError{"bad chain set"};
+    const int nch = (int)chains.size();
+    out.assign(steps.size(), BatchResult{});
+    loss_all.assign(steps.size() * nch, 0.0);
+    loss_test.assign(steps.size() * nch, 0.0);
+    for (size_t s0 = 0; s0 < steps.size(); s0 += LP_MAXSTEP) {
+        const int cnt = (int)std::min<size_t>(LP_MAXSTEP, steps.size() - s0);
+        const int slot = (int)(m.seq++ & 1);
+        Impl::Ticket &t = m.tk[slot];
+        t.b = BatchDesc{};
+        t.b.nch = nch;
+        for (int i = 0; i < nch; i++) {
+            if (chains[i] < 0 || chains[i] >= m.nchains) throw EngineError{"chain id out of range"};
+            t.b.chain[i] = chains[i];
+        }
+        t.d = m.d;
+        t.slot = slot;
+        t.resident = true;
+        if (!t.ev) CUDA_CHECK(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+        lp_launch(m, t, steps.data() + s0, cnt);
+        CUDA_CHECK(cudaEventRecord(t.ev, m.st));
+        CUDA_CHECK(cudaEventSynchronize(t.ev));
+        lp_parse(m, t, stats_, out.data() + s0, loss_all.data() + s0 * nch, loss_test.data() + s0 * nch);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    m.collect_spans();
 }
 
 static inline int sweep_mode(int family) { return family == FAM_LM ? MODE_D : (family == FAM_COX ? MODE_COX : MODE_DH); }
@@ -1046,6 +1246,29 @@ int Engine::run_batch_enqueue(int T, const std::vector<int> &chains, bool new_pa
     }();
     t.fused = fuse_topk && !sharded_ && !d.grouped && d.p <= TOPK_LMAX;
     if (!t.ev) CUDA_CHECK(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+    t.resident = m.lp_ok;
+    if (t.resident) {
+        // gaussian family, L2-resident design: the whole batch (prologue, every PDAS iteration, losses) is one launch
+        const PathStep st1{T, lambda};
+        lp_launch(m, t, &st1, 1);
+        t.loss_kernel = false;
+        for (int i = 0; i < t.ld.njobs; i++) {
+            bool in_batch = false;
+            for (int q = 0; q < b.nch; q++) in_batch = in_batch || b.chain[q] == t.ld.chain[i];
+            const bool ok = in_batch && (t.ld.kind[i] == 0 || (t.ld.kind[i] == 1 && t.ld.fold[i] == t.ld.chain[i] - 1));
+            if (!ok) t.loss_kernel = true;
+        }
+        if (t.loss_kernel) {
+            Engine::Impl::Mirror &h = m.mir[t.slot];
+            const int sp2 = m.span_begin(5);
+            launch_losses(t.d, t.ld, m.testrows, m.ntest, m.y, m.w, m.lfact, m.loss_scratch, m.loss_out, m.st);
+            m.span_end(sp2);
+            CUDA_CHECK(cudaMemcpyAsync(h.loss, m.loss_out, t.ld.njobs * sizeof(double), cudaMemcpyDeviceToHost, m.st));
+        }
+        CUDA_CHECK(cudaEventRecord(t.ev, m.st));
+        t.pending = true;
+        return slot;
+    }
 
     int sp = m.span_begin(4);
     launch_chain_begin(t.d, b, m.st);
@@ -1154,6 +1377,25 @@ bool Engine::run_batch_collect(int ticket, BatchResult &out, std::vector<double>
     const Dev &d = t.d;
     const BatchDesc &b = t.b;
     CUDA_CHECK(cudaEventSynchronize(t.ev));
+    if (t.resident) {
+        t.pending = false;
+        double la[MAXC], lt[MAXC];
+        lp_parse(m, t, stats_, &out, la, lt);
+        if (t.has_jobs && loss_out) {
+            if (t.loss_kernel) {
+                stats_.kernel_launches++;
+                loss_out->assign(h.loss, h.loss + t.ld.njobs);
+            } else {
+                loss_out->resize((size_t)t.ld.njobs);
+                for (int i = 0; i < t.ld.njobs; i++) {
+                    int q = 0;
+                    while (b.chain[q] != t.ld.chain[i]) q++;
+                    (*loss_out)[(size_t)i] = t.ld.kind[i] == 0 ? la[q] : lt[q];
+                }
+            }
+        }
+        return true;
+    }
     auto finished = [&] {
         bool all = true;
         for (int i = 0; i < b.nch; i++) all = all && h.done[b.chain[i]];

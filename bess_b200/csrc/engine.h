@@ -35,6 +35,12 @@ struct BatchResult {
     std::vector<double> bA[MAXC]; // coefficients on the support (normalised scale)
 };
 
+// one step of a path segment: sparsity level + ridge level (path.cpp:48-74 walks these in a fixed order)
+struct PathStep {
+    int T;
+    double lambda;
+};
+
 struct LossJob {
     int chain;   // whose beta/coef0
     int kind;    // 0 = train_loss formula on ALL rows (Metric::train_loss); 1 = fold test loss on fold `fold`
@@ -121,6 +127,21 @@ public:
                           double lambda);
     bool run_batch_collect(int ticket, BatchResult &out, std::vector<double> *loss_out);
     void run_batch_discard(int ticket);
+
+    // ---- resident path (gaussian family, lm_path.cu): a whole path segment -- `steps` in evaluation order, every chain of
+    // `chains` fitted at every step, warm-started from its own previous step -- in ONE cooperative launch with the PDAS
+    // iteration loop on the device.  out[t] = the batch result of step t; loss_all / loss_test [t * chains.size() + i] =
+    // the Lm train-loss formula over all rows (Metric.h:145-148) / the fold loss over chain i's held-out rows (:190).
+    // Only when resident_path() (decided by setup_chains: family, shapes, shared-memory budget); run_batch uses the same
+    // kernel for single steps.
+    bool resident_path() const;
+    const std::string &resident_path_why() const;
+    void run_steps(const std::vector<PathStep> &steps, const std::vector<int> &chains, std::vector<BatchResult> &out,
+                   std::vector<double> &loss_all, std::vector<double> &loss_test);
+    // counters of the resident kernel since load(): 0 launches, 1 PDAS iterations (sweeps), 2 full-vector select fallbacks,
+    // 3 path steps, 8..15 clock ticks by phase of chain owner 0 (begin, wait, select, load columns, gram, solve, residual +
+    // cycle test, publish), 16..18 of sweeper 0 (wait, stream X, reduce + sacrifice)
+    void resident_counters(double *out24) const;
 
     // ---- explicit warm-start state of a chain (STATE_ZERO / STATE_SAVE / STATE_LOAD on NSLOT slots; the
     // (A, beta_A) half and the coef0 half are addressed separately, a negative slot skips that half).  Used by pgs_path.

@@ -1,0 +1,1024 @@
+// Resident PDAS path for the gaussian family: Algorithm::fit (/root/reference/src/Algorithm.h:113-171) with
+// GroupPdasLm::get_A / primary_model_fit (:1097-1135), max_k (utilities.cpp:179-199), the warm-started level loop of
+// sequential_path (path.cpp:48-74) and the Lm losses of Metric.h:145-148 / 190 -- for ALL chains of a batch (full-data
+// fit + CV folds) and ALL steps of a path segment in ONE cooperative launch.
+//
+// Why: after screening (BASELINE config 5: 1000 x 5000, 11 chains, s = 1..20) the design is L2-resident and a PDAS
+// iteration is a few microseconds of work; launched as sweep / top-k / fit kernels the path was ~55 dependent iterations
+// of three 11-to-300-CTA launches each (profiles/r01g_small_kernels_full.md: 1-2 % SM throughput).  Here the iteration
+// loop lives on the device:
+//
+//   * SWEEPER CTAs (all but one CTA per chain) each own a slice of ~p/137 adjacent columns for the whole launch.  Per
+//     iteration a sweeper stages the residual vectors of all chains ([n][FT], one bulk-TMA copy into shared memory), walks
+//     all n rows of its slice once (16-byte loads of X from L2, 2*FT fp64 FMAs per load), reduces its row phases in a
+//     fixed order, applies the splicing sacrifice (Algorithm.h:1112-1123) and writes bd; values above the chain's
+//     published threshold are appended to a short candidate list.  No row splits, no partial vectors in memory.
+//   * one OWNER CTA per chain keeps the chain's state in shared memory for the whole launch: the active columns X_A (all
+//     n rows, column-major, in reusable slots), their Gram matrix and X_A^T y (cached per slot pair -- a PDAS iteration
+//     typically exchanges 0-3 columns, only those rows of the Gram are recomputed), the response, the fold mask and
+//     A_list.  Per iteration it ranks the candidates (exact top-k: larger value first, lower index first; falls back to a
+//     radix select over the whole bd vector when the list is short or overflows), loads the new columns, solves the
+//     bordered normal equations by Cholesky, publishes the residual of the next sweep and runs the cycle test
+//     (Algorithm.h:164-170).  A chain that has met the stopping rule writes its result (support, coefficients, l, train /
+//     held-out loss) and moves on to ITS next path step at once -- the chains of a batch are independent lineages
+//     (SURVEY 7.2), so nobody waits for the slowest chain of a level.
+//   * two counters in global memory order the phases: sweepers arrive at B1, owners wait for it; owners arrive at B2,
+//     everybody waits for it.  The launch is cooperative (all CTAs co-resident), a watchdog turns a lost arrival into an
+//     error instead of a hang.
+//
+// The results are bitwise reproducible from run to run (fixed summation orders; the candidate list is unordered but its
+// ranking is a total order) and equal to the multi-kernel path up to fp64 re-association (supports identical).
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+
+#include "device_utils.cuh"
+#include "lm_path.cuh"
+
+namespace bess {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lp_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lp_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lp_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void lp_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lp_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     lp_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(lp_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool lp_mbar_try(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(lp_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void lp_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!lp_mbar_try(bar, parity)) {
+    }
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double2 ldg_stream_v2(const double *p)
+{
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream(const double *p)
+{
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long lp_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// phase barriers: monotonic counters in global memory
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long LP_WATCHDOG_NS = 4000000000ull;  // a lost arrival becomes an error after 4 s
+
+__device__ __forceinline__ void cta_arrive(unsigned *ctr)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_release_add_u32(ctr, 1u);
+    }
+}
+// returns false when the launch was aborted (by this or another CTA's watchdog)
+__device__ __forceinline__ bool cta_wait(unsigned *sync, int which, unsigned target, int *flag_sh)
+{
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while (ld_acquire_u32(sync + which) < target) {
+            if ((++spins & 0x3ffu) == 0u) {
+                if (t0 == 0) t0 = lp_globaltimer();
+                if (ld_acquire_u32(sync + LP_SYNC_ABORT) != 0u || lp_globaltimer() - t0 > LP_WATCHDOG_NS) {
+                    atomicExch(sync + LP_SYNC_ABORT, 1u);
+                    ok = 0;
+                    break;
+                }
+            }
+        }
+        if (ok && ld_acquire_u32(sync + LP_SYNC_ABORT) != 0u) ok = 0;
+        __threadfence();
+        *flag_sh = ok;
+    }
+    __syncthreads();
+    const bool ok = *flag_sh != 0;
+    __syncthreads();
+    return ok;
+}
+
+struct Timer {
+    long long t;
+    bool on;
+    unsigned long long *dst;
+    __device__ __forceinline__ void start(bool enable, unsigned long long *d)
+    {
+        on = enable;
+        dst = d;
+        if (on) t = clock64();
+    }
+    __device__ __forceinline__ void mark(int id)
+    {
+        if (on) {
+            const long long now = clock64();
+            dst[id] += (unsigned long long)(now - t);
+            t = now;
+        }
+    }
+};
+
+// =====================================================================================================================
+// SWEEPER
+// =====================================================================================================================
+struct SweepSm {
+    double *R;        // [npad][FT] residual vectors of all chain slots; aliased by the row-phase scratch [RP][FT][W2]
+    double *tau;      // [16]
+    double *lam;      // [16]
+    uint64_t *mbar;
+    int *flag;
+};
+
+__host__ __device__ inline size_t sweeper_smem_doubles(int npad, int FT)
+{
+    const size_t r = (size_t)npad * FT;
+    const size_t scr = (size_t)2 * LP_NT * FT;  // RP * Wp <= LP_NT
+    return (r > scr ? r : scr) + 16 + 16 + 2 + 2;
+}
+
+template <int FT>
+__device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
+{
+    SweepSm sm;
+    {
+        double *p = reinterpret_cast<double *>(raw);
+        const size_t r = (size_t)((d.n + 1) & ~1) * FT, scr = (size_t)2 * LP_NT * FT;
+        sm.R = p;
+        p += (r > scr ? r : scr);
+        sm.tau = p;
+        p += 16;
+        sm.lam = p;
+        p += 16;
+        sm.mbar = reinterpret_cast<uint64_t *>(p);
+        p += 2;
+        sm.flag = reinterpret_cast<int *>(p);
+    }
+    const int tid = threadIdx.x;
+    const int n = d.n, npad = (n + 1) & ~1;
+    const int sidx = (int)blockIdx.x - L.nch;
+    const int P2 = (d.p + 1) >> 1;
+    const int WpA = (P2 + L.nsweep - 1) / L.nsweep;
+    const int q0 = min(P2, sidx * WpA), q1 = min(P2, q0 + WpA);
+    const int Wp = q1 - q0;
+    const int RP = Wp > 0 ? min(LP_NT / Wp, LP_RPMAX) : 0;
+    const int cp = Wp > 0 ? tid % Wp : 0, rp = Wp > 0 ? tid / Wp : 0;
+    const bool active = Wp > 0 && rp < RP;
+    const int W2 = 2 * Wp, nout = W2 * FT;
+    unsigned inbatch = 0;
+    for (int i = 0; i < L.nch; i++) inbatch |= 1u << L.chain[i];
+    const uint32_t rbytes = (uint32_t)((size_t)npad * FT * sizeof(double));
+    if (tid == 0) {
+        lp_mbar_init(sm.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    Timer tm;
+    tm.start(tid == 0 && sidx == 0, L.dbg + 16);
+    uint32_t parity = 0;
+    for (unsigned it = 1;; it++) {
+        if (!cta_wait(L.sync, LP_SYNC_B2, (unsigned)L.nch * it, sm.flag)) return;
+        {
+            const unsigned term = ld_acquire_u32(L.sync + LP_SYNC_TERM);
+            if (term != 0u && term <= it) return;  // the last chain finished its last step in owner phase term - 1 <= it - 1
+        }
+        tm.mark(0);
+        if (Wp > 0) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                lp_mbar_expect_tx(sm.mbar, rbytes);
+                uint32_t off = 0;
+                while (off < rbytes) {
+                    const uint32_t chunk = min(rbytes - off, 32768u);
+                    lp_bulk_g2s(reinterpret_cast<unsigned char *>(sm.R) + off, reinterpret_cast<const unsigned char *>(d.G) + off,
+                                chunk, sm.mbar);
+                    off += chunk;
+                }
+            }
+            if (tid < 16) {
+                sm.tau[tid] = tid < FT ? __ldcg(L.pub + 2 * tid) : 0.0;
+                sm.lam[tid] = tid < FT ? __ldcg(L.pub + 2 * tid + 1) : 0.0;
+            }
+            double a0[FT], a1[FT];
+#pragma unroll
+            for (int f = 0; f < FT; f++) a0[f] = a1[f] = 0.0;
+            if (active) {
+                constexpr int U = FT >= 16 ? 4 : 8;  // x loads in flight per thread (register budget: 128 at 512 threads)
+                const double *xp = d.X + 2 * (size_t)(q0 + cp);
+                bool first = true;
+                for (int i0 = rp; i0 < n; i0 += RP * U) {
+                    double2 xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = i0 + u * RP;
+                        xv[u] = i < n ? ldg_stream_v2(xp + (size_t)i * d.ldx) : make_double2(0.0, 0.0);
+                    }
+                    if (first) {
+                        lp_mbar_wait(sm.mbar, parity);
+                        first = false;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = i0 + u * RP;
+                        if (i < n) {
+                            const double *r = sm.R + (size_t)i * FT;
+                            if constexpr (FT == 1) {
+                                const double g = r[0];
+                                a0[0] = fma(xv[u].x, g, a0[0]);
+                                a1[0] = fma(xv[u].y, g, a1[0]);
+                            } else {
+#pragma unroll
+                                for (int f = 0; f < FT; f += 2) {
+                                    const double2 g = *reinterpret_cast<const double2 *>(r + f);
+                                    a0[f] = fma(xv[u].x, g.x, a0[f]);
+                                    a1[f] = fma(xv[u].y, g.x, a1[f]);
+                                    a0[f + 1] = fma(xv[u].x, g.y, a0[f + 1]);
+                                    a1[f + 1] = fma(xv[u].y, g.y, a1[f + 1]);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (first) lp_mbar_wait(sm.mbar, parity);
+            } else {
+                lp_mbar_wait(sm.mbar, parity);
+            }
+            parity ^= 1u;
+            tm.mark(1);
+            __syncthreads();  // every thread is done with R: the scratch may overwrite it
+            double *scr = sm.R;
+            if (active) {
+#pragma unroll
+                for (int f = 0; f < FT; f++)
+                    *reinterpret_cast<double2 *>(scr + ((size_t)rp * FT + f) * W2 + 2 * cp) = make_double2(a0[f], a1[f]);
+            }
+            __syncthreads();
+            for (int o = tid; o < nout; o += LP_NT) {
+                const int f = o / W2, col = o - f * W2;
+                const long long j = 2LL * q0 + col;
+                if (!((inbatch >> f) & 1u) || j >= d.p) continue;
+                double dsum = 0.0;
+                for (int r = 0; r < RP; r++) dsum += scr[((size_t)r * FT + f) * W2 + col];
+                // splicing sacrifice, Algorithm.h:1112-1123 with the L0L2 ridge term (:1109) -- same formula as
+                // finish_epilogue<EPI_SACR_LM> of the multi-kernel path
+                const double beta = __ldcg(d.betaD + (size_t)f * d.pstride + j);
+                const double lam2 = 2.0 * sm.lam[f];
+                const double phi = sqrt(lam2 + __ldg(d.xtx + (size_t)f * d.pstride + j) / (double)__ldg(d.ntrain + f));
+                const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
+                double v = t * t;
+                if (!(v == v)) v = 0.0;  // a NaN sacrifice ranks last (topk_key of the multi-kernel path)
+                for (int q = 0; q < L.n_always; q++)
+                    if (__ldg(L.always + q) == (int)j) v = DBL_MAX;  // utilities.cpp:190-199
+                __stcg(d.bd + (size_t)f * d.pstride + j, v);
+                if (v >= sm.tau[f]) {
+                    const int pos = atomicAdd(L.ncand + f, 1);
+                    if (pos < LP_CAP) {
+                        LpCand cnd;
+                        cnd.v = v;
+                        cnd.idx = (int)j;
+                        cnd.pad = 0;
+                        __stcg(reinterpret_cast<int4 *>(L.cand + (size_t)f * LP_CAP + pos), *reinterpret_cast<int4 *>(&cnd));
+                    }
+                }
+            }
+            tm.mark(2);
+        }
+        cta_arrive(L.sync + LP_SYNC_B1);  // its leading __syncthreads also protects the scratch from the next TMA copy
+    }
+}
+
+// =====================================================================================================================
+// OWNER
+// =====================================================================================================================
+struct OwnSm {
+    double *XA;    // [ns][npad] active columns, one per slot, all n rows
+    double *y, *m, *my;  // [npad] response, train mask (1/0), their product
+    double *Gc;    // [ns][ns] sum_i m_i x_s x_t per slot pair
+    double *bc;    // [ns] sum_i m_i y_i x_s
+    double *S;     // [(kcap+1)][ldS] bordered normal equations
+    double *beta;  // [kcap]
+    double *dg;    // [kcap+1]
+    double *cv;    // [LP_CAP] candidate values
+    double *selv;  // [kcap+1] values by rank
+    double *red;   // [40]
+    int *ci;       // [LP_CAP]
+    int *A, *slotA, *Anew, *slotNew, *newlist;  // [kcap]
+    int *seli;     // [kcap+1] indices by rank
+    int *slot_col, *keep;  // [ns]
+    int *hist;     // [hist_rows][kcap]
+    int *hbin;     // [256]
+    int *misc;     // [16]
+    int ldS;
+};
+enum { MI_FLAG = 0, MI_CNT = 1, MI_NNEW = 2, MI_SEEN = 3, MI_TIE = 4, MI_KREM = 5, MI_NEQ = 6, MI_COUNT = 7 };
+
+__host__ __device__ inline size_t owner_smem_bytes(int npad, int kcap, int ns, int hist_rows)
+{
+    const int ldS = (kcap + 2) | 1;
+    size_t dbl = (size_t)ns * npad + 3 * (size_t)npad + (size_t)ns * ns + ns + (size_t)(kcap + 1) * ldS + kcap + (kcap + 1) +
+                 LP_CAP + (kcap + 1) + 40 + 2 /* prefix/scratch */;
+    size_t ints = LP_CAP + 5 * (size_t)kcap + (kcap + 1) + 2 * (size_t)ns + (size_t)hist_rows * kcap + 256 + 16 + 64 /* scan */;
+    return dbl * 8 + ((ints + 1) & ~(size_t)1) * 4;
+}
+
+__device__ __forceinline__ OwnSm carve_owner(unsigned char *raw, int npad, int kcap, int ns, int hist_rows, double **pre_out,
+                                             int **scan_out)
+{
+    OwnSm s;
+    double *p = reinterpret_cast<double *>(raw);
+    s.ldS = (kcap + 2) | 1;
+    s.XA = p; p += (size_t)ns * npad;
+    s.y = p; p += npad;
+    s.m = p; p += npad;
+    s.my = p; p += npad;
+    s.Gc = p; p += (size_t)ns * ns;
+    s.bc = p; p += ns;
+    s.S = p; p += (size_t)(kcap + 1) * s.ldS;
+    s.beta = p; p += kcap;
+    s.dg = p; p += kcap + 1;
+    s.cv = p; p += LP_CAP;
+    s.selv = p; p += kcap + 1;
+    s.red = p; p += 40;
+    *pre_out = p; p += 2;
+    int *q = reinterpret_cast<int *>(p);
+    s.ci = q; q += LP_CAP;
+    s.A = q; q += kcap;
+    s.slotA = q; q += kcap;
+    s.Anew = q; q += kcap;
+    s.slotNew = q; q += kcap;
+    s.newlist = q; q += kcap;
+    s.seli = q; q += kcap + 1;
+    s.slot_col = q; q += ns;
+    s.keep = q; q += ns;
+    s.hist = q; q += (size_t)hist_rows * kcap;
+    s.hbin = q; q += 256;
+    s.misc = q; q += 16;
+    *scan_out = q;
+    return s;
+}
+
+// exclusive block scan of one int per thread; scan_sh: 64 ints
+__device__ __forceinline__ int block_excl_scan_int(int v, int *scan_sh, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) scan_sh[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const int w = lane < LP_NT / 32 ? scan_sh[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < LP_NT / 32) scan_sh[lane] = winc - w;
+        if (lane == 31) scan_sh[32] = winc;
+    }
+    __syncthreads();
+    const int r = scan_sh[wid] + inc - v;
+    *total = scan_sh[32];
+    __syncthreads();
+    return r;
+}
+
+// Exact top-k of the whole sacrifice vector bd[0..p) (global memory, L2-resident), for the iterations whose candidate
+// list is unusable: MSB-first radix select on the fp64 bit patterns (values are >= 0), then the k winners -- every key
+// above the threshold plus the lowest-index keys equal to it -- go to (cv, ci) in any order.  *vk <- (a lower bound of)
+// the k-th largest value, MI_TIE <- boundary tie.
+__device__ void fallback_select(const double *bd, int p, int k, OwnSm &s, int *scan_sh, double *vk)
+{
+    const int tid = threadIdx.x;
+    unsigned long long prefix = 0ull, mask = 0ull;
+    int krem = k, neq = p;
+    unsigned long long *pre_sh = reinterpret_cast<unsigned long long *>(s.red);  // red[0] as a 64-bit scratch word
+    if (k < p) {
+        for (int pass = 7; pass >= 0; pass--) {
+            const int shift = pass * 8;
+            if (tid < 256) s.hbin[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < p; i += LP_NT) {
+                const unsigned long long u = (unsigned long long)__double_as_longlong(__ldcg(bd + i));
+                if ((u & mask) == prefix) atomicAdd(&s.hbin[(int)((u >> shift) & 255ull)], 1);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                int loc[8], tot = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    loc[q] = s.hbin[tid * 8 + q];
+                    tot += loc[q];
+                }
+                int suf = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (tid + o < 32) suf += t;
+                }
+                const int above = suf - tot;
+                if (above < krem && suf >= krem) {
+                    int acc = above;
+                    for (int q = 7; q >= 0; q--) {
+                        if (acc + loc[q] >= krem) {
+                            *pre_sh = prefix | ((unsigned long long)(tid * 8 + q) << shift);
+                            s.misc[MI_KREM] = krem - acc;
+                            s.misc[MI_NEQ] = loc[q];
+                            break;
+                        }
+                        acc += loc[q];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = *pre_sh;
+            krem = s.misc[MI_KREM];
+            neq = s.misc[MI_NEQ];
+            mask |= 255ull << shift;
+            __syncthreads();
+            if (neq == krem) break;  // every key of the boundary bin is wanted: lower digits cannot change the set
+        }
+    } else {
+        mask = 0ull;  // k == p: everything matches the empty prefix and is taken
+        krem = p;
+        neq = p;
+    }
+    // collect: keys above the boundary bin, and the first krem keys of the bin in index order (contiguous chunk per thread)
+    const int per = (p + LP_NT - 1) / LP_NT;
+    const int cb = min(p, tid * per), ce = min(p, cb + per);
+    int ceq = 0;
+    for (int i = cb; i < ce; i++) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(__ldcg(bd + i));
+        ceq += ((u & mask) == prefix);
+    }
+    int tot_eq;
+    int eq_before = block_excl_scan_int(ceq, scan_sh, &tot_eq);
+    if (tid == 0) s.misc[MI_CNT] = 0;
+    __syncthreads();
+    for (int i = cb; i < ce; i++) {
+        const double v = __ldcg(bd + i);
+        const unsigned long long u = (unsigned long long)__double_as_longlong(v), mu = u & mask;
+        bool take = mu > prefix;
+        if (mu == prefix) {
+            take = eq_before < krem;
+            eq_before++;
+        }
+        if (take) {
+            const int pos = atomicAdd(&s.misc[MI_CNT], 1);
+            if (pos < LP_CAP) {
+                s.cv[pos] = v;
+                s.ci[pos] = i;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) s.misc[MI_TIE] = (k < p && mask == ~0ull && neq > krem) ? 1 : 0;
+    *vk = __longlong_as_double((long long)prefix);
+    __syncthreads();
+}
+
+// Rank `count` <= LP_CAP candidates (larger value first, lower index first -- a total order) and write the k best to
+// Anew in ascending index order.  tie_known: MI_TIE was set by the caller (the list holds exactly the k winners).
+__device__ void rank_select(OwnSm &s, int count, int k, bool tie_known, double *vk)
+{
+    const int tid = threadIdx.x;
+    if (tid < count) {
+        const double v = s.cv[tid];
+        const int id = s.ci[tid];
+        int r = 0;
+        for (int u = 0; u < count; u++) {
+            const double vu = s.cv[u];
+            const int iu = s.ci[u];
+            r += (vu > v) || (vu == v && iu < id);
+        }
+        if (r <= k) {
+            s.seli[r] = id;
+            s.selv[r] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < k) {
+        const int id = s.seli[tid];
+        int pos = 0;
+        for (int u = 0; u < k; u++) pos += (s.seli[u] < id);
+        s.Anew[pos] = id;
+    }
+    if (tid == 0 && !tie_known) s.misc[MI_TIE] = (count > k && s.selv[k] == s.selv[k - 1]) ? 1 : 0;
+    if (!tie_known) *vk = s.selv[k - 1];
+    __syncthreads();
+}
+
+// XA[slot][i] = X[i][slot_col[slot]] for the nnew slots of newlist, all n rows
+__device__ void gather_new(const Dev &d, OwnSm &s, int nnew, int npad)
+{
+    const int n = d.n;
+    const int tot = nnew * n;
+    for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * LP_NT) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * LP_NT;
+            if (e < tot) {
+                const int q = e / n, i = e - q * n;
+                v[u] = ldg_stream(d.X + (size_t)i * d.ldx + s.slot_col[s.newlist[q]]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * LP_NT;
+            if (e < tot) {
+                const int q = e / n, i = e - q * n;
+                s.XA[(size_t)s.newlist[q] * npad + i] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// sum_i a_i * b_i * w_i, lanes stride the rows, four running sums per lane, fixed combination order
+__device__ __forceinline__ double warp_dot3(const double *a, const double *b, const double *w, int n)
+{
+    const int lane = threadIdx.x & 31;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int i = lane;
+    for (; i + 96 < n; i += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] = fma(a[i + 32 * u] * w[i + 32 * u], b[i + 32 * u], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+        if (i + 32 * u < n) acc[u] = fma(a[i + 32 * u] * w[i + 32 * u], b[i + 32 * u], acc[u]);
+    return warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+}
+__device__ __forceinline__ double warp_dot2(const double *a, const double *b, int n)
+{
+    const int lane = threadIdx.x & 31;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int i = lane;
+    for (; i + 96 < n; i += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[u] = fma(a[i + 32 * u], b[i + 32 * u], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+        if (i + 32 * u < n) acc[u] = fma(a[i + 32 * u], b[i + 32 * u], acc[u]);
+    return warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+}
+
+// Gram rows / columns and X^T y entries of the freshly loaded slots against every occupied slot
+__device__ void gram_new(const Dev &d, OwnSm &s, int nnew, int ns, int npad)
+{
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = nnew * (ns + 1);
+    for (int item = wid; item < items; item += LP_NT / 32) {
+        const int q = item / (ns + 1), o = item - q * (ns + 1);
+        const int sn = s.newlist[q];
+        if (o == ns) {
+            const double v = warp_dot2(s.XA + (size_t)sn * npad, s.my, d.n);
+            if (lane == 0) s.bc[sn] = v;
+        } else if (s.slot_col[o] >= 0) {
+            const int lo = min(sn, o), hi = max(sn, o);
+            const double v = warp_dot3(s.XA + (size_t)lo * npad, s.XA + (size_t)hi * npad, s.m, d.n);
+            if (lane == 0) {
+                s.Gc[(size_t)sn * ns + o] = v;
+                s.Gc[(size_t)o * ns + sn] = v;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Bordered Cholesky solve in shared memory: rows 0..k-1 of S hold the SPD matrix (lower triangle used), row k the
+// right-hand side; beta <- S^{-1} rhs.  (The reference solves with colPivHouseholderQr, Algorithm.h:1134; on these SPD
+// systems the solutions agree to ~1e-13.)
+__device__ void chol_solve(OwnSm &s, int k)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ldS = s.ldS;
+    double *S = s.S;
+    if (k + 1 <= 32) {
+        if (wid == 0) {
+            for (int j = 0; j < k; j++) {
+                const double inv = rsqrt(S[j * ldS + j]);
+                double lij = 0.0;
+                if (lane > j && lane <= k) {
+                    lij = S[lane * ldS + j] * inv;
+                    S[lane * ldS + j] = lij;
+                }
+                if (lane == j) s.dg[j] = inv;
+                __syncwarp();
+                if (lane > j && lane <= k) {
+                    const int cend = min(lane, k - 1);
+                    for (int c = j + 1; c <= cend; c++) S[lane * ldS + c] -= lij * S[c * ldS + j];
+                }
+                __syncwarp();
+            }
+            double z = lane < k ? S[k * ldS + lane] : 0.0;
+            for (int j = k - 1; j >= 0; j--) {
+                const double xj = __shfl_sync(0xffffffffu, z, j) * s.dg[j];
+                if (lane == j) z = xj;
+                if (lane < j) z -= S[j * ldS + lane] * xj;
+            }
+            if (lane < k) s.beta[lane] = z;
+        }
+        __syncthreads();
+        return;
+    }
+    for (int j = 0; j < k; j++) {
+        __syncthreads();
+        const double inv = rsqrt(S[j * ldS + j]);
+        if (tid == 0) s.dg[j] = inv;
+        for (int i = j + 1 + tid; i <= k; i += LP_NT) S[i * ldS + j] *= inv;
+        __syncthreads();
+        for (int i = j + 1 + wid; i <= k; i += LP_NT / 32) {
+            const double lij = S[i * ldS + j];
+            const int cend = min(i, k - 1);
+            for (int c = j + 1 + lane; c <= cend; c += 32) S[i * ldS + c] -= lij * S[c * ldS + j];
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        for (int c = lane; c < k; c += 32) s.beta[c] = S[k * ldS + c];
+        __syncwarp();
+        for (int j = k - 1; j >= 0; j--) {
+            const double xj = s.beta[j] * s.dg[j];
+            __syncwarp();
+            if (lane == 0) s.beta[j] = xj;
+            for (int c = lane; c < j; c += 32) s.beta[c] -= S[j * ldS + c] * xj;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+// Residual of the next sweep, G[i][c] = (y_i - x_i,A beta_A) / n_train on the chain's train rows, 0 elsewhere
+// (Algorithm.h:1109), and on request the Lm losses of Metric.h:145-148 (all rows, / n) and :190 (held-out rows, / 2 n_t).
+__device__ void residual(const Dev &d, OwnSm &s, int c, int ks, int nt, int npad, bool want_loss, double *loss_all,
+                         double *loss_test)
+{
+    const int n = d.n;
+    double sa = 0.0, st = 0.0;
+    for (int i = threadIdx.x; i < n; i += LP_NT) {
+        double eta = 0.0;
+        for (int a = 0; a < ks; a++) eta = fma(s.XA[(size_t)s.slotA[a] * npad + i], s.beta[a], eta);
+        const double e = s.y[i] - eta;
+        const bool train = s.m[i] != 0.0;
+        __stcg(d.G + (size_t)i * d.FS + c, train ? e / (double)nt : 0.0);
+        sa += e * e;
+        if (!train) st += e * e;
+    }
+    if (want_loss) {
+        const double ta = block_sum<LP_NT>(sa, s.red);
+        const double tt = block_sum<LP_NT>(st, s.red);
+        *loss_all = ta / (double)n;
+        *loss_test = n > nt ? tt / (double)(2 * (n - nt)) : 0.0;
+    }
+    __syncthreads();
+}
+
+__device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ci = blockIdx.x, c = L.chain[ci];
+    const int n = d.n, npad = (n + 1) & ~1, kcap = d.kcap, ns = L.ns, p = d.p;
+    double *pre_sh;
+    int *scan_sh;
+    OwnSm s = carve_owner(raw, npad, kcap, ns, L.hist_rows, &pre_sh, &scan_sh);
+    (void)pre_sh;
+    const int nt = d.ntrain[c];
+    const int *rows = d.rows + (size_t)c * n;
+    double *bD = d.betaD + (size_t)c * d.pstride;
+    Timer tm;
+    tm.start(tid == 0 && ci == 0, L.dbg);
+
+    // ---- phase O(0): Algorithm::fit prologue from the chain's stored state (Algorithm.h:141-148)
+    for (int i = tid; i < npad; i += LP_NT) {
+        s.m[i] = 0.0;
+        s.y[i] = i < n ? L.y[i] : 0.0;
+    }
+    for (int q = tid; q < ns; q += LP_NT) s.slot_col[q] = -1;
+    __syncthreads();
+    for (int r = tid; r < nt; r += LP_NT) s.m[rows[r]] = 1.0;
+    __syncthreads();
+    for (int i = tid; i < npad; i += LP_NT) s.my[i] = s.m[i] * s.y[i];
+    int ks = d.ks[c];
+    if (!d.warm) {  // cold start: beta_init = 0
+        for (int a = tid; a < ks; a += LP_NT) __stcg(bD + d.A[(size_t)c * kcap + a], 0.0);
+        ks = 0;
+    }
+    for (int a = tid; a < ks; a += LP_NT) {
+        s.A[a] = d.A[(size_t)c * kcap + a];
+        s.beta[a] = d.bA[(size_t)c * kcap + a];
+        s.slotA[a] = a;
+        s.slot_col[a] = s.A[a];
+        s.newlist[a] = a;
+    }
+    __syncthreads();
+    gather_new(d, s, ks, npad);
+    gram_new(d, s, ks, ns, npad);
+    int step = 0, T = L.T[0], l = 0, tie_acc = 0;
+    double lam = L.lam[0];
+    for (int a = tid; a < T; a += LP_NT) s.hist[a] = 0;  // A_list.col(0) = 0 (Algorithm.h:143)
+    double la = 0.0, lt = 0.0;
+    residual(d, s, c, ks, nt, npad, false, &la, &lt);
+    double tau = L.tau[c];
+    if (tid == 0) {
+        __stcg(L.pub + 2 * c, tau);
+        __stcg(L.pub + 2 * c + 1, lam);
+    }
+    bool complete = false;
+    tm.mark(0);
+    cta_arrive(L.sync + LP_SYNC_B2);
+
+    for (unsigned it = 1;; it++) {
+        if (!cta_wait(L.sync, LP_SYNC_B2, (unsigned)L.nch * it, &s.misc[MI_FLAG])) return;
+        {
+            const unsigned term = ld_acquire_u32(L.sync + LP_SYNC_TERM);
+            if (term != 0u && term <= it) return;
+        }
+        if (!cta_wait(L.sync, LP_SYNC_B1, (unsigned)L.nsweep * it, &s.misc[MI_FLAG])) return;
+        tm.mark(1);
+        if (!complete) {
+            const int k = T;
+            // ---- exact top-k (max_k, utilities.cpp:179-188): candidates published by the sweepers, else the whole vector
+            if (tid == 0) s.misc[MI_COUNT] = __ldcg(L.ncand + c);
+            __syncthreads();
+            int count = s.misc[MI_COUNT];
+            double vk = 0.0;
+            bool tie_known = false;
+            if (count >= k && count <= LP_CAP) {
+                if (tid < count) {
+                    const int4 raw4 = __ldcg(reinterpret_cast<const int4 *>(L.cand + (size_t)c * LP_CAP + tid));
+                    const LpCand cnd = *reinterpret_cast<const LpCand *>(&raw4);
+                    s.cv[tid] = cnd.v;
+                    s.ci[tid] = cnd.idx;
+                }
+                __syncthreads();
+            } else {
+                fallback_select(d.bd + (size_t)c * d.pstride, p, k, s, scan_sh, &vk);
+                count = k;
+                tie_known = true;
+                if (tid == 0) atomicAdd(L.sync + LP_SYNC_FALLBACKS, 1u);
+            }
+            rank_select(s, count, k, tie_known, &vk);
+            tau = 0.7 * vk;
+            tm.mark(2);
+            // ---- which of the selected columns are already resident; the others take the slots of columns not selected
+            for (int q = tid; q < ns; q += LP_NT) s.keep[q] = 0;
+            __syncthreads();
+            if (tid < k) {
+                const int j = s.Anew[tid];
+                int sl = -1;
+                for (int q = 0; q < ns; q++)
+                    if (s.slot_col[q] == j) sl = q;
+                s.slotNew[tid] = sl;
+                if (sl >= 0) s.keep[sl] = 1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int nnew = 0, q = 0;
+                // empty slots first, then the slots of columns that are not selected now
+                for (int pass = 0; pass < 2; pass++) {
+                    q = 0;
+                    for (int a = 0; a < k; a++) {
+                        if (s.slotNew[a] >= 0) continue;
+                        while (q < ns && (s.keep[q] || (pass == 0 && s.slot_col[q] >= 0))) q++;
+                        if (q >= ns) break;
+                        s.slotNew[a] = q;
+                        s.slot_col[q] = s.Anew[a];
+                        s.keep[q] = 1;
+                        s.newlist[nnew++] = q;
+                    }
+                }
+                s.misc[MI_NNEW] = nnew;
+            }
+            __syncthreads();
+            const int nnew = s.misc[MI_NNEW];
+            gather_new(d, s, nnew, npad);
+            tm.mark(3);
+            gram_new(d, s, nnew, ns, npad);
+            tm.mark(4);
+            // ---- X_A^T X_A + lambda I | X_A^T y  (Algorithm.h:1134), solve
+            for (int e = tid; e < (k + 1) * k; e += LP_NT) {
+                const int a = e / k, b = e - a * k;
+                s.S[a * s.ldS + b] =
+                    a < k ? s.Gc[(size_t)s.slotNew[a] * ns + s.slotNew[b]] + (a == b ? lam : 0.0) : s.bc[s.slotNew[b]];
+            }
+            __syncthreads();
+            chol_solve(s, k);
+            tm.mark(5);
+            // ---- scatter (Algorithm.h:159-163), cycle test against A_list[0..l] (Algorithm.h:164-170)
+            for (int a = tid; a < ks; a += LP_NT) __stcg(bD + s.A[a], 0.0);
+            if (tid == 0) s.misc[MI_SEEN] = 0;
+            __syncthreads();
+            for (int a = tid; a < k; a += LP_NT) {
+                s.A[a] = s.Anew[a];
+                s.slotA[a] = s.slotNew[a];
+                __stcg(bD + s.Anew[a], s.beta[a]);
+            }
+            ks = k;
+            l += 1;
+            for (int ll = wid; ll < l; ll += LP_NT / 32) {
+                const int *hp = s.hist + (size_t)ll * kcap;
+                int same = 1;
+                for (int a = lane; a < k; a += 32) same &= (hp[a] == s.Anew[a]);
+                if (__all_sync(0xffffffffu, same) && lane == 0) s.misc[MI_SEEN] = 1;
+            }
+            __syncthreads();
+            const bool seen = s.misc[MI_SEEN] != 0;
+            tie_acc += s.misc[MI_TIE];
+            if (l < L.hist_rows)
+                for (int a = tid; a < k; a += LP_NT) s.hist[(size_t)l * kcap + a] = s.Anew[a];
+            const bool finished = seen || l >= d.max_iter;
+            residual(d, s, c, ks, nt, npad, finished, &la, &lt);
+            tm.mark(6);
+            if (finished) {
+                int *ri = L.res_i + ((size_t)step * L.nch + ci) * (2 + kcap);
+                double *rd = L.res_d + ((size_t)step * L.nch + ci) * (2 + kcap);
+                const int l_out = seen ? l : d.max_iter + 1;
+                if (tid == 0) {
+                    ri[0] = l_out;
+                    ri[1] = tie_acc;
+                    rd[0] = la;
+                    rd[1] = lt;
+                }
+                for (int a = tid; a < k; a += LP_NT) {
+                    ri[2 + a] = s.A[a];
+                    rd[2 + a] = s.beta[a];
+                }
+                step += 1;
+                if (step == L.nsteps) {
+                    complete = true;
+                    // hand the chain back to the engine's tables (chain_state / the multi-kernel path read them)
+                    for (int a = tid; a < k; a += LP_NT) {
+                        d.A[(size_t)c * kcap + a] = s.A[a];
+                        d.bA[(size_t)c * kcap + a] = s.beta[a];
+                    }
+                    if (tid == 0) {
+                        d.ks[c] = ks;
+                        d.l[c] = l_out;
+                        d.done[c] = 1;
+                        d.coef0[c] = 0.0;
+                        d.tie_acc[c] = tie_acc;
+                        L.tau[c] = tau;
+                        const unsigned old = atomicAdd(L.sync + LP_SYNC_NCOMPLETE, 1u);
+                        if (old + 1u == (unsigned)L.nch) {
+                            atomicExch(L.sync + LP_SYNC_TERM, it + 1u);
+                            atomicExch(L.sync + LP_SYNC_ITERS, it);
+                        }
+                    }
+                } else {
+                    T = L.T[step];
+                    lam = L.lam[step];
+                    l = 0;
+                    tie_acc = 0;
+                    __syncthreads();
+                    for (int a = tid; a < T; a += LP_NT) s.hist[a] = 0;
+                    if (!d.warm) {
+                        for (int a = tid; a < ks; a += LP_NT) __stcg(bD + s.A[a], 0.0);
+                        ks = 0;
+                        residual(d, s, c, 0, nt, npad, false, &la, &lt);
+                    }
+                }
+            }
+            if (tid == 0) {
+                __stcg(L.pub + 2 * c, complete ? (double)INFINITY : tau);
+                __stcg(L.pub + 2 * c + 1, lam);
+                __stcg(L.ncand + c, 0);
+            }
+            tm.mark(7);
+        }
+        cta_arrive(L.sync + LP_SYNC_B2);
+    }
+}
+
+template <int FT>
+__global__ void __launch_bounds__(LP_NT, 1) lm_path_kernel(const Dev d, const LpDesc L)
+{
+    extern __shared__ __align__(128) unsigned char lp_smem[];
+    if ((int)blockIdx.x < L.nch) owner_main(d, L, lp_smem);
+    else sweeper_main<FT>(d, L, lp_smem);
+}
+
+bool env_enabled()
+{
+    static const bool on = [] {
+        const char *e = std::getenv("BESS_B200_RESIDENT");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+}  // namespace
+
+int lm_path_slots(const Dev &d, int max_iter)
+{
+    const int npad = (d.n + 1) & ~1;
+    const size_t budget = 232448 - 2048;
+    int ns = d.kcap + 8;
+    while (ns > d.kcap && owner_smem_bytes(npad, d.kcap, ns, max_iter + 2) > budget) ns--;
+    return ns;
+}
+
+size_t lm_path_smem_bytes(const Dev &d, int max_iter, int sm_count)
+{
+    (void)sm_count;
+    const int npad = (d.n + 1) & ~1;
+    const size_t own = owner_smem_bytes(npad, d.kcap, lm_path_slots(d, max_iter), max_iter + 2);
+    const size_t swp = sweeper_smem_doubles(npad, d.FS) * 8;
+    return ((own > swp ? own : swp) + 127) & ~(size_t)127;
+}
+
+bool lm_path_eligible(const Dev &d, int max_iter, int sm_count, std::string *why)
+{
+    auto no = [&](const char *m) {
+        if (why) *why = m;
+        return false;
+    };
+    if (!env_enabled()) return no("disabled by BESS_B200_RESIDENT=0");
+    if (d.family != FAM_LM) return no("family is not gaussian");
+    if (d.grouped) return no("group selection");
+    if (d.sharded) return no("column-sharded mode");
+    if (d.kcap > LP_KMAX) return no("support larger than 64");
+    if (d.kcap > d.p) return no("support larger than p");
+    if (sm_count < MAXC + 8) return no("too few SMs");
+    const int nsweep = sm_count - MAXC;  // the fewest sweepers any batch of this problem can have
+    const int P2 = (d.p + 1) >> 1;
+    if ((P2 + nsweep - 1) / nsweep > LP_WPMAX) return no("too many columns per sweeper CTA");
+    if (lm_path_smem_bytes(d, max_iter, sm_count) > 232448 - 2048) return no("shared-memory budget");
+    if (owner_smem_bytes((d.n + 1) & ~1, d.kcap, d.kcap, max_iter + 2) > 232448 - 2048) return no("shared-memory budget");
+    return true;
+}
+
+void launch_lm_path(const Dev &d, const LpDesc &desc, int sm_count, int max_iter, cudaStream_t st)
+{
+    const size_t smem = lm_path_smem_bytes(d, max_iter, sm_count);
+    void (*fn)(const Dev, const LpDesc) = nullptr;
+    switch (d.FS) {
+        case 1: fn = lm_path_kernel<1>; break;
+        case 2: fn = lm_path_kernel<2>; break;
+        case 4: fn = lm_path_kernel<4>; break;
+        case 6: fn = lm_path_kernel<6>; break;
+        case 8: fn = lm_path_kernel<8>; break;
+        case 12: fn = lm_path_kernel<12>; break;
+        case 16: fn = lm_path_kernel<16>; break;
+        default: throw EngineError{"resident path: unsupported chain-slot count"};
+    }
+    CUDA_CHECK(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[2] = {(void *)&d, (void *)&desc};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)fn, dim3((unsigned)(desc.nch + desc.nsweep)), dim3(LP_NT), args, smem, st));
+}
+
+}  // namespace bess

@@ -248,7 +248,29 @@ void sequential_path(Driver &dr, BessResult &out, Eval &best)
     auto ridge = [&](int idx) { return lams[(size_t)(order[(size_t)idx] / S)]; };
     const int n_steps = (int)order.size();
     const bool pipelined = !dr.eng.sharded();
-    if (!pipelined) {
+    if (dr.eng.resident_path()) {
+        // gaussian family on an L2-resident design: the whole walk is one cooperative launch (Engine::run_steps); every
+        // chain advances from step to step on the device, the host only reads the per-step results
+        std::vector<PathStep> steps;
+        for (int t = 0; t < n_steps; t++) steps.push_back({level(t), ridge(t)});
+        std::vector<BatchResult> brs;
+        std::vector<double> la, lt;
+        dr.eng.run_steps(steps, dr.all_chains, brs, la, lt);
+        const size_t nch = dr.all_chains.size();
+        for (int t = 0; t < n_steps; t++) {
+            Eval &e = evs[(size_t)order[(size_t)t]];
+            const BatchResult &br = brs[(size_t)t];
+            e.T = level(t);
+            e.lambda = ridge(t);
+            e.l = br.l[0];
+            e.A = br.A[0];
+            e.bA = br.bA[0];
+            e.coef0 = br.coef0[0];
+            e.train_loss = la[(size_t)t * nch];
+            e.ic = dr.K > 0 ? Driver::mean_of(lt, (size_t)t * nch + 1, (size_t)t * nch + 1 + (size_t)dr.K)
+                            : dr.ic_formula(e.train_loss, e.T);
+        }
+    } else if (!pipelined) {
         for (int t = 0; t < n_steps; t++) evs[(size_t)order[(size_t)t]] = dr.step(level(t), nullptr, ridge(t));
     } else {
         int cur = dr.step_enqueue(level(0), ridge(0));
@@ -795,6 +817,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     out.stats = eng.stats();
     eng.profile(out.prof_ms, out.prof_n);
     out.sweep_splits = eng.sweep_splits();
+    eng.resident_counters(out.resident);
 }
 
 }  // namespace bess

@@ -43,7 +43,14 @@ def run(X, y, w, seq, n, p, fg):
     names = list(out["stats"]["host_ms"].keys())
     print("first group", fg, "| C5 resident, mean of", reps, "calls: wall", round(wall / reps * 1e3, 3), "ms; host phases (ms):",
           {nm: round(v / reps, 3) for nm, v in zip(names, acc)}, "sum", round(acc.sum() / reps, 3),
-          "| sweeps", out["stats"]["n_sweeps"], "batches", out["stats"]["n_batches"])
+          "| sweeps", out["stats"]["n_sweeps"], "batches", out["stats"]["n_batches"], "launches", out["stats"]["kernel_launches"])
+    r = out["stats"]["resident"]
+    if r[0] > 0:
+        mhz = 1965.0
+        own = dict(zip(("begin", "wait", "select", "load_cols", "gram", "solve", "resid_cycle", "publish"), [round(v / mhz, 1) for v in r[8:16]]))
+        swp = dict(zip(("wait", "stream_x", "reduce_sacrifice"), [round(v / mhz, 1) for v in r[16:19]]))
+        print("  resident kernel (last call): launches", r[0], "iterations", r[1], "fallback selects", r[2], "steps", r[3],
+              "| owner 0 us by phase", own, "| sweeper 0 us", swp)
 
 
 if __name__ == "__main__":
