@@ -123,7 +123,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     ext.chosen_lambda_out = C.pointer(chosen_lam)
     stats = np.zeros(32)
     ext.stats_out = _d(stats)
-    resident = np.zeros(24)
+    resident = np.zeros(88)
     ext.resident_out = _d(resident)
     ext.profile = 1 if profile else 0
     ext.beta_out_zeroed = 1  # `beta` comes from np.zeros (calloc): untouched pages stay untouched

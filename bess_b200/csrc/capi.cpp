@@ -110,7 +110,7 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
                 std::copy(r.screening_A.begin(), r.screening_A.end(), ext->screening_A_out);
             if (ext->chosen_s_out) *ext->chosen_s_out = r.chosen_s;
             if (ext->chosen_lambda_out) *ext->chosen_lambda_out = r.lambda;
-            if (ext->resident_out) std::copy(r.resident, r.resident + 24, ext->resident_out);
+            if (ext->resident_out) std::copy(r.resident, r.resident + 88, ext->resident_out);
             if (ext->stats_out) {
                 ext->stats_out[0] = (double)r.stats.n_fits;
                 ext->stats_out[1] = (double)r.stats.n_pdas_iters;

@@ -212,7 +212,9 @@ struct Engine::Impl {
     int *lp_res_i = nullptr;               // device [2][lp_res_count]
     double *lp_res_d = nullptr;
     unsigned long long *lp_dbg = nullptr;  // device [LP_NDBG]
+    double *lp_R = nullptr;                // device [2][npad][MAXC] residual matrices of the two chain groups
     double lp_counters[24] = {};
+    double lp_owner[4 * MAXC] = {};
     // ---- per-category device timing (CUDA events on the engine stream), enabled by Engine::set_profiling
     bool prof = false;
     struct Span { cudaEvent_t a, b; int cat; };
@@ -275,7 +277,7 @@ struct Engine::Impl {
         dfree(m.st, slots.A); dfree(m.st, slots.bA); dfree(m.st, slots.ks); dfree(m.st, slots.coef0);
         dfree(m.st, d.Tc); dfree(m.st, d.AnewCols);
         dfree(m.st, lp_sync); dfree(m.st, lp_cand); dfree(m.st, lp_ncand); dfree(m.st, lp_pub); dfree(m.st, lp_tau);
-        dfree(m.st, lp_res_i); dfree(m.st, lp_res_d); dfree(m.st, lp_dbg);
+        dfree(m.st, lp_res_i); dfree(m.st, lp_res_d); dfree(m.st, lp_dbg); dfree(m.st, lp_R);
         lp_ok = false;
         chains_ready = false;
     }
@@ -1034,6 +1036,8 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
         m.lp_res_i = dalloc<int>(m.st, 2 * m.lp_res_count);
         m.lp_res_d = dalloc<double>(m.st, 2 * m.lp_res_count);
         m.lp_dbg = dalloc<unsigned long long>(m.st, LP_NDBG);
+        m.lp_R = dalloc<double>(m.st, (size_t)2 * m.npad * MAXC);
+        CUDA_CHECK(cudaMemsetAsync(m.lp_R, 0, (size_t)2 * m.npad * MAXC * 8, m.st));
         std::vector<double> inf(MAXC, INFINITY);  // no candidate threshold yet: the first select reads the whole vector
         CUDA_CHECK(cudaMemcpyAsync(m.lp_tau, inf.data(), MAXC * 8, cudaMemcpyHostToDevice, m.st));
         CUDA_CHECK(cudaMemsetAsync(m.lp_pub, 0, 2 * MAXC * 8, m.st));
@@ -1051,6 +1055,10 @@ const std::string &Engine::resident_path_why() const { return d_->lp_why; }
 void Engine::resident_counters(double *out24) const
 {
     for (int i = 0; i < 24; i++) out24[i] = d_->lp_counters[i];
+}
+void Engine::resident_owner_counters(double *out64) const
+{
+    for (int i = 0; i < 4 * MAXC; i++) out64[i] = d_->lp_owner[i];
 }
 
 // Enqueue one launch of the resident kernel for the batch in t.b: memsets, kernel, result copies into the slot's pinned
@@ -1074,6 +1082,19 @@ static void lp_launch(Engine::Impl &m, Engine::Impl::Ticket &t, const PathStep *
         L.lam[q] = steps[q].lambda;
     }
     for (int i = 0; i < t.b.nch; i++) L.chain[i] = t.b.chain[i];
+    // two chain groups (alternate chains, so the full-data chain and the folds spread evenly): one group's owners work
+    // while the other group is swept
+    L.ng = lm_path_groups(L.nch);
+    L.gcount[0] = L.gcount[1] = 0;
+    for (int i = 0; i < L.nch; i++) {
+        const int g = L.ng == 2 ? (i & 1) : 0;
+        L.ogroup[i] = g;
+        L.oslot[i] = L.gcount[g];
+        L.gchain[g][L.gcount[g]++] = L.chain[i];
+    }
+    L.fh = lm_path_fh(L.nch, L.ng);
+    L.Rg[0] = m.lp_R;
+    L.Rg[1] = m.lp_R + (size_t)m.npad * MAXC;
     L.always = m.always;
     L.y = m.y;
     L.sync = m.lp_sync + (size_t)t.slot * LP_SYNC_WORDS;
@@ -1139,9 +1160,12 @@ static void lp_parse(Engine::Impl &m, const Engine::Impl::Ticket &t, EngineStats
     m.lp_counters[1] += iters;
     m.lp_counters[2] += (double)sy[LP_SYNC_FALLBACKS];
     m.lp_counters[3] += (double)L.nsteps;
+    m.lp_counters[4] += (double)sy[LP_SYNC_MERGED];
     const unsigned long long *dbg = c->h_lp_dbg + (size_t)t.slot * LP_NDBG;  // cumulative since setup_chains
     for (int q = 0; q < 8; q++) m.lp_counters[8 + q] = (double)dbg[q];
     for (int q = 0; q < 3; q++) m.lp_counters[16 + q] = (double)dbg[16 + q];
+    m.lp_counters[19] = (double)dbg[8];
+    for (int q = 0; q < 4 * MAXC; q++) m.lp_owner[q] = (double)dbg[32 + q];  // assembling the normal equations (part of `solve` when added to slot 13)
 }
 
 void Engine::run_steps(const std::vector<PathStep> &steps, const std::vector<int> &chains, std::vector<BatchResult> &out,

@@ -142,6 +142,9 @@ public:
     // 3 path steps, 8..15 clock ticks by phase of chain owner 0 (begin, wait, select, load columns, gram, solve, residual +
     // cycle test, publish), 16..18 of sweeper 0 (wait, stream X, reduce + sacrifice)
     void resident_counters(double *out24) const;
+    // per chain owner i (position in the batch): [4 * i + 0] busy ticks, [1] longest phase, [2] ticks in fallback selects,
+    // [3] fits actually solved
+    void resident_owner_counters(double *out64) const;
 
     // ---- explicit warm-start state of a chain (STATE_ZERO / STATE_SAVE / STATE_LOAD on NSLOT slots; the
     // (A, beta_A) half and the coef0 half are addressed separately, a negative slot skips that half).  Used by pgs_path.

@@ -205,15 +205,16 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     const int n = d.n, npad = (n + 1) & ~1;
     const int sidx = (int)blockIdx.x - L.nch;
     const int P2 = (d.p + 1) >> 1;
-    const int WpA = (P2 + L.nsweep - 1) / L.nsweep;
+    // slice width in column pairs, rounded to even: a row segment of an even number of pairs is a whole number of 32-byte
+    // sectors (measured: 18-pair slices stream 15 % faster than 17- or 19-pair ones)
+    int WpA = (P2 + L.nsweep - 1) / L.nsweep;
+    if (WpA > 1 && (WpA & 1) && WpA < LP_WPMAX) WpA++;
     const int q0 = min(P2, sidx * WpA), q1 = min(P2, q0 + WpA);
     const int Wp = q1 - q0;
     const int RP = Wp > 0 ? min(LP_NT / Wp, LP_RPMAX) : 0;
     const int cp = Wp > 0 ? tid % Wp : 0, rp = Wp > 0 ? tid / Wp : 0;
     const bool active = Wp > 0 && rp < RP;
     const int W2 = 2 * Wp, nout = W2 * FT;
-    unsigned inbatch = 0;
-    for (int i = 0; i < L.nch; i++) inbatch |= 1u << L.chain[i];
     const uint32_t rbytes = (uint32_t)((size_t)npad * FT * sizeof(double));
     if (tid == 0) {
         lp_mbar_init(sm.mbar, 1);
@@ -223,13 +224,20 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     Timer tm;
     tm.start(tid == 0 && sidx == 0, L.dbg + 16);
     uint32_t parity = 0;
-    for (unsigned it = 1;; it++) {
-        if (!cta_wait(L.sync, LP_SYNC_B2, (unsigned)L.nch * it, sm.flag)) return;
+    // step s sweeps group g = s % ng for the r-th time (r = s / ng + 1) once that group's owners have finished their
+    // phase r - 1.  Owner phase O_g(r) has index ng * r + g; LP_SYNC_TERM holds 1 + the index of the phase in which the
+    // last chain finished its last step, and everybody leaves at the first decision point at or past it.
+    for (unsigned st = 0;; st++) {
+        const int g = (int)(st % (unsigned)L.ng);
+        const unsigned r = st / (unsigned)L.ng + 1u;
+        if (!cta_wait(L.sync, LP_SYNC_B2 + g, (unsigned)L.gcount[g] * r, sm.flag)) return;
         {
             const unsigned term = ld_acquire_u32(L.sync + LP_SYNC_TERM);
-            if (term != 0u && term <= it) return;  // the last chain finished its last step in owner phase term - 1 <= it - 1
+            if (term != 0u && term - 1u <= st) return;
         }
         tm.mark(0);
+        const double *Rsrc = L.Rg[g];
+        const int nslot = L.gcount[g];
         if (Wp > 0) {
             if (tid == 0) {
                 asm volatile("fence.proxy.async;" ::: "memory");
@@ -237,32 +245,38 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                 uint32_t off = 0;
                 while (off < rbytes) {
                     const uint32_t chunk = min(rbytes - off, 32768u);
-                    lp_bulk_g2s(reinterpret_cast<unsigned char *>(sm.R) + off, reinterpret_cast<const unsigned char *>(d.G) + off,
+                    lp_bulk_g2s(reinterpret_cast<unsigned char *>(sm.R) + off, reinterpret_cast<const unsigned char *>(Rsrc) + off,
                                 chunk, sm.mbar);
                     off += chunk;
                 }
             }
             if (tid < 16) {
-                sm.tau[tid] = tid < FT ? __ldcg(L.pub + 2 * tid) : 0.0;
-                sm.lam[tid] = tid < FT ? __ldcg(L.pub + 2 * tid + 1) : 0.0;
+                const int cc = tid < nslot ? L.gchain[g][tid] : 0;
+                sm.tau[tid] = tid < nslot ? __ldcg(L.pub + 2 * cc) : 0.0;
+                sm.lam[tid] = tid < nslot ? __ldcg(L.pub + 2 * cc + 1) : 0.0;
             }
             double a0[FT], a1[FT];
 #pragma unroll
             for (int f = 0; f < FT; f++) a0[f] = a1[f] = 0.0;
             if (active) {
-                constexpr int U = FT >= 16 ? 4 : 8;  // x loads in flight per thread (register budget: 128 at 512 threads)
+                // software pipeline: the x loads of row group g + 1 are in flight while group g is multiplied
+                constexpr int U = 4;
                 const double *xp = d.X + 2 * (size_t)(q0 + cp);
-                bool first = true;
+                double2 xn[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = rp + u * RP;
+                    xn[u] = i < n ? ldg_stream_v2(xp + (size_t)i * d.ldx) : make_double2(0.0, 0.0);
+                }
+                lp_mbar_wait(sm.mbar, parity);
                 for (int i0 = rp; i0 < n; i0 += RP * U) {
                     double2 xv[U];
 #pragma unroll
+                    for (int u = 0; u < U; u++) xv[u] = xn[u];
+#pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const int i = i0 + u * RP;
-                        xv[u] = i < n ? ldg_stream_v2(xp + (size_t)i * d.ldx) : make_double2(0.0, 0.0);
-                    }
-                    if (first) {
-                        lp_mbar_wait(sm.mbar, parity);
-                        first = false;
+                        const int i = i0 + (U + u) * RP;
+                        xn[u] = i < n ? ldg_stream_v2(xp + (size_t)i * d.ldx) : make_double2(0.0, 0.0);
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
@@ -286,7 +300,6 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                         }
                     }
                 }
-                if (first) lp_mbar_wait(sm.mbar, parity);
             } else {
                 lp_mbar_wait(sm.mbar, parity);
             }
@@ -303,34 +316,35 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
             for (int o = tid; o < nout; o += LP_NT) {
                 const int f = o / W2, col = o - f * W2;
                 const long long j = 2LL * q0 + col;
-                if (!((inbatch >> f) & 1u) || j >= d.p) continue;
+                if (f >= nslot || j >= d.p) continue;
+                const int cc = L.gchain[g][f];  // chain id: row of betaD / xtx / bd, candidate list
                 double dsum = 0.0;
-                for (int r = 0; r < RP; r++) dsum += scr[((size_t)r * FT + f) * W2 + col];
+                for (int r2 = 0; r2 < RP; r2++) dsum += scr[((size_t)r2 * FT + f) * W2 + col];
                 // splicing sacrifice, Algorithm.h:1112-1123 with the L0L2 ridge term (:1109) -- same formula as
                 // finish_epilogue<EPI_SACR_LM> of the multi-kernel path
-                const double beta = __ldcg(d.betaD + (size_t)f * d.pstride + j);
+                const double beta = __ldcg(d.betaD + (size_t)cc * d.pstride + j);
                 const double lam2 = 2.0 * sm.lam[f];
-                const double phi = sqrt(lam2 + __ldg(d.xtx + (size_t)f * d.pstride + j) / (double)__ldg(d.ntrain + f));
+                const double phi = sqrt(lam2 + __ldg(d.xtx + (size_t)cc * d.pstride + j) / (double)__ldg(d.ntrain + cc));
                 const double t = phi * beta + (1.0 / phi) * (dsum - lam2 * beta);
                 double v = t * t;
                 if (!(v == v)) v = 0.0;  // a NaN sacrifice ranks last (topk_key of the multi-kernel path)
                 for (int q = 0; q < L.n_always; q++)
                     if (__ldg(L.always + q) == (int)j) v = DBL_MAX;  // utilities.cpp:190-199
-                __stcg(d.bd + (size_t)f * d.pstride + j, v);
+                __stcg(d.bd + (size_t)cc * d.pstride + j, v);
                 if (v >= sm.tau[f]) {
-                    const int pos = atomicAdd(L.ncand + f, 1);
+                    const int pos = atomicAdd(L.ncand + cc, 1);
                     if (pos < LP_CAP) {
                         LpCand cnd;
                         cnd.v = v;
                         cnd.idx = (int)j;
                         cnd.pad = 0;
-                        __stcg(reinterpret_cast<int4 *>(L.cand + (size_t)f * LP_CAP + pos), *reinterpret_cast<int4 *>(&cnd));
+                        __stcg(reinterpret_cast<int4 *>(L.cand + (size_t)cc * LP_CAP + pos), *reinterpret_cast<int4 *>(&cnd));
                     }
                 }
             }
             tm.mark(2);
         }
-        cta_arrive(L.sync + LP_SYNC_B1);  // its leading __syncthreads also protects the scratch from the next TMA copy
+        cta_arrive(L.sync + LP_SYNC_B1 + g);  // its leading __syncthreads also protects the scratch from the next TMA copy
     }
 }
 
@@ -435,24 +449,40 @@ __device__ __forceinline__ int block_excl_scan_int(int v, int *scan_sh, int *tot
     return r;
 }
 
-// Exact top-k of the whole sacrifice vector bd[0..p) (global memory, L2-resident), for the iterations whose candidate
-// list is unusable: MSB-first radix select on the fp64 bit patterns (values are >= 0), then the k winners -- every key
-// above the threshold plus the lowest-index keys equal to it -- go to (cv, ci) in any order.  *vk <- (a lower bound of)
-// the k-th largest value, MI_TIE <- boundary tie.
-__device__ void fallback_select(const double *bd, int p, int k, OwnSm &s, int *scan_sh, double *vk)
+// Exact top-kk of the whole sacrifice vector bd[0..p) (global memory, L2-resident), for the iterations whose candidate
+// list is unusable: MSB-first radix select on the fp64 bit patterns (values are >= 0), then the kk winners -- every key
+// above the boundary bin plus the lowest-index keys of the bin -- go to (cv, ci) in any order; rank_select orders them.
+// p <= LP_NT * FB_PER: the keys stay in registers between the passes (strided, coalesced), else they are re-read from L2.
+constexpr int FB_PER = 12;
+__device__ void fallback_select(const double *bd, int p, int kk, OwnSm &s, int *scan_sh)
 {
     const int tid = threadIdx.x;
     unsigned long long prefix = 0ull, mask = 0ull;
-    int krem = k, neq = p;
+    int krem = kk, neq = p;
     unsigned long long *pre_sh = reinterpret_cast<unsigned long long *>(s.red);  // red[0] as a 64-bit scratch word
-    if (k < p) {
+    const bool inreg = p <= LP_NT * FB_PER;
+    unsigned long long key[FB_PER];
+    if (inreg) {
+#pragma unroll
+        for (int q = 0; q < FB_PER; q++) {
+            const int i = tid + q * LP_NT;
+            key[q] = i < p ? (unsigned long long)__double_as_longlong(__ldcg(bd + i)) : 0ull;
+        }
+    }
+    if (kk < p) {
         for (int pass = 7; pass >= 0; pass--) {
             const int shift = pass * 8;
             if (tid < 256) s.hbin[tid] = 0;
             __syncthreads();
-            for (int i = tid; i < p; i += LP_NT) {
-                const unsigned long long u = (unsigned long long)__double_as_longlong(__ldcg(bd + i));
-                if ((u & mask) == prefix) atomicAdd(&s.hbin[(int)((u >> shift) & 255ull)], 1);
+            if (inreg) {
+#pragma unroll
+                for (int q = 0; q < FB_PER; q++)
+                    if (tid + q * LP_NT < p && (key[q] & mask) == prefix) atomicAdd(&s.hbin[(int)((key[q] >> shift) & 255ull)], 1);
+            } else {
+                for (int i = tid; i < p; i += LP_NT) {
+                    const unsigned long long u = (unsigned long long)__double_as_longlong(__ldcg(bd + i));
+                    if ((u & mask) == prefix) atomicAdd(&s.hbin[(int)((u >> shift) & 255ull)], 1);
+                }
             }
             __syncthreads();
             if (tid < 32) {
@@ -491,11 +521,28 @@ __device__ void fallback_select(const double *bd, int p, int k, OwnSm &s, int *s
             if (neq == krem) break;  // every key of the boundary bin is wanted: lower digits cannot change the set
         }
     } else {
-        mask = 0ull;  // k == p: everything matches the empty prefix and is taken
-        krem = p;
+        krem = p;  // kk == p: everything matches the empty prefix and is taken
         neq = p;
     }
-    // collect: keys above the boundary bin, and the first krem keys of the bin in index order (contiguous chunk per thread)
+    if (tid == 0) s.misc[MI_CNT] = 0;
+    __syncthreads();
+    if (inreg && neq == krem) {
+        // the usual case: the boundary bin is wanted as a whole
+#pragma unroll
+        for (int q = 0; q < FB_PER; q++) {
+            const int i = tid + q * LP_NT;
+            if (i < p && (key[q] & mask) >= prefix) {
+                const int pos = atomicAdd(&s.misc[MI_CNT], 1);
+                if (pos < LP_CAP) {
+                    s.cv[pos] = __longlong_as_double((long long)key[q]);
+                    s.ci[pos] = i;
+                }
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    // keys above the boundary bin, and the first krem keys of the bin in index order (contiguous chunk per thread)
     const int per = (p + LP_NT - 1) / LP_NT;
     const int cb = min(p, tid * per), ce = min(p, cb + per);
     int ceq = 0;
@@ -505,8 +552,6 @@ __device__ void fallback_select(const double *bd, int p, int k, OwnSm &s, int *s
     }
     int tot_eq;
     int eq_before = block_excl_scan_int(ceq, scan_sh, &tot_eq);
-    if (tid == 0) s.misc[MI_CNT] = 0;
-    __syncthreads();
     for (int i = cb; i < ce; i++) {
         const double v = __ldcg(bd + i);
         const unsigned long long u = (unsigned long long)__double_as_longlong(v), mu = u & mask;
@@ -524,16 +569,15 @@ __device__ void fallback_select(const double *bd, int p, int k, OwnSm &s, int *s
         }
     }
     __syncthreads();
-    if (tid == 0) s.misc[MI_TIE] = (k < p && mask == ~0ull && neq > krem) ? 1 : 0;
-    *vk = __longlong_as_double((long long)prefix);
-    __syncthreads();
 }
 
 // Rank `count` <= LP_CAP candidates (larger value first, lower index first -- a total order) and write the k best to
-// Anew in ascending index order.  tie_known: MI_TIE was set by the caller (the list holds exactly the k winners).
-__device__ void rank_select(OwnSm &s, int count, int k, bool tie_known, double *vk)
+// Anew in ascending index order.  MI_TIE <- the k-th and (k+1)-th values are equal (a boundary tie, utilities.cpp:179-188
+// leaves its resolution to std::nth_element).  *vk <- k-th value, *vdeep <- value of rank min(count, deep).
+__device__ void rank_select(OwnSm &s, int count, int k, int deep, double *vk, double *vdeep)
 {
     const int tid = threadIdx.x;
+    const int dd = min(count, deep);
     if (tid < count) {
         const double v = s.cv[tid];
         const int id = s.ci[tid];
@@ -547,6 +591,7 @@ __device__ void rank_select(OwnSm &s, int count, int k, bool tie_known, double *
             s.seli[r] = id;
             s.selv[r] = v;
         }
+        if (r == dd - 1) s.red[1] = v;
     }
     __syncthreads();
     if (tid < k) {
@@ -555,32 +600,41 @@ __device__ void rank_select(OwnSm &s, int count, int k, bool tie_known, double *
         for (int u = 0; u < k; u++) pos += (s.seli[u] < id);
         s.Anew[pos] = id;
     }
-    if (tid == 0 && !tie_known) s.misc[MI_TIE] = (count > k && s.selv[k] == s.selv[k - 1]) ? 1 : 0;
-    if (!tie_known) *vk = s.selv[k - 1];
+    if (tid == 0) s.misc[MI_TIE] = (count > k && s.selv[k] == s.selv[k - 1]) ? 1 : 0;
+    *vk = s.selv[k - 1];
+    *vdeep = s.red[1];
     __syncthreads();
 }
 
-// XA[slot][i] = X[i][slot_col[slot]] for the nnew slots of newlist, all n rows
+// XA[slot][i] = X[i][slot_col[slot]] for the nnew slots of newlist, all n rows; up to 8 loads in flight per thread
 __device__ void gather_new(const Dev &d, OwnSm &s, int nnew, int npad)
 {
     const int n = d.n;
-    const int tot = nnew * n;
-    for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * LP_NT) {
-        double v[4];
+    if (nnew == 0) return;
+    for (int q0 = 0; q0 < nnew; q0 += 4) {
+        for (int i0 = threadIdx.x; i0 < n; i0 += 2 * LP_NT) {
+            double v[4][2];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int e = e0 + u * LP_NT;
-            if (e < tot) {
-                const int q = e / n, i = e - q * n;
-                v[u] = ldg_stream(d.X + (size_t)i * d.ldx + s.slot_col[s.newlist[q]]);
+            for (int u = 0; u < 4; u++) {
+                if (q0 + u < nnew) {
+                    const double *col = d.X + s.slot_col[s.newlist[q0 + u]];
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int i = i0 + r * LP_NT;
+                        if (i < n) v[u][r] = ldg_stream(col + (size_t)i * d.ldx);
+                    }
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int e = e0 + u * LP_NT;
-            if (e < tot) {
-                const int q = e / n, i = e - q * n;
-                s.XA[(size_t)s.newlist[q] * npad + i] = v[u];
+            for (int u = 0; u < 4; u++) {
+                if (q0 + u < nnew) {
+                    double *dst = s.XA + (size_t)s.newlist[q0 + u] * npad;
+#pragma unroll
+                    for (int r = 0; r < 2; r++) {
+                        const int i = i0 + r * LP_NT;
+                        if (i < n) dst[i] = v[u][r];
+                    }
+                }
             }
         }
     }
@@ -640,38 +694,62 @@ __device__ void gram_new(const Dev &d, OwnSm &s, int nnew, int ns, int npad)
     __syncthreads();
 }
 
-// Bordered Cholesky solve in shared memory: rows 0..k-1 of S hold the SPD matrix (lower triangle used), row k the
-// right-hand side; beta <- S^{-1} rhs.  (The reference solves with colPivHouseholderQr, Algorithm.h:1134; on these SPD
-// systems the solutions agree to ~1e-13.)
+// Bordered Cholesky solve: rows 0..k-1 of S hold the SPD matrix (lower triangle used), row k the right-hand side;
+// beta <- S^{-1} rhs.  (The reference solves with colPivHouseholderQr, Algorithm.h:1134; on these SPD systems the
+// solutions agree to ~1e-13.)
+// k + 1 <= KB <= 24: one warp, lane i keeps row i in registers (statically indexed: the loops are fully unrolled), the
+// pivot and the column entries travel by shuffle -- no shared-memory round trip inside the factorisation.
+template <int KB>
+__device__ __noinline__ void chol_warp_reg(double *S, int ldS, double *dg, double *beta, int k)
+{
+    const int lane = threadIdx.x & 31;
+    double row[KB];
+#pragma unroll
+    for (int c = 0; c < KB; c++) row[c] = (lane <= k && c < k && c <= lane) ? S[lane * ldS + c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < KB; j++) {
+        if (j < k) {
+            const double piv = __shfl_sync(0xffffffffu, row[j], j);
+            const double inv = rsqrt(piv);
+            if (lane == 0) dg[j] = inv;
+            const double lij = row[j] * inv;  // lanes above j hold zeros here and stay zero
+            row[j] = lij;
+#pragma unroll
+            for (int c = 0; c < KB; c++) {  // constant bounds + guard: the unroller sees static register indices
+                if (c > j) {
+                    const double lcj = __shfl_sync(0xffffffffu, lij, c);
+                    if (c < k) row[c] = fma(-lij, lcj, row[c]);
+                }
+            }
+        }
+    }
+    // L back to shared memory for the back substitution (lane c needs column c of L, i.e. another lane's registers)
+#pragma unroll
+    for (int c = 0; c < KB; c++)
+        if (lane <= k && c < k && c <= lane) S[lane * ldS + c] = row[c];
+    __syncwarp();
+    double z = lane < k ? S[k * ldS + lane] : 0.0;
+#pragma unroll
+    for (int j = KB - 1; j >= 0; j--) {
+        if (j < k) {
+            const double xj = __shfl_sync(0xffffffffu, z, j) * dg[j];
+            if (lane == j) z = xj;
+            if (lane < j) z = fma(-S[j * ldS + lane], xj, z);
+        }
+    }
+    if (lane < k) beta[lane] = z;
+}
+
 __device__ void chol_solve(OwnSm &s, int k)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ldS = s.ldS;
     double *S = s.S;
-    if (k + 1 <= 32) {
+    if (k + 1 <= 24) {  // (a 32-row instance does not fit the 128-register budget of a 512-thread CTA)
         if (wid == 0) {
-            for (int j = 0; j < k; j++) {
-                const double inv = rsqrt(S[j * ldS + j]);
-                double lij = 0.0;
-                if (lane > j && lane <= k) {
-                    lij = S[lane * ldS + j] * inv;
-                    S[lane * ldS + j] = lij;
-                }
-                if (lane == j) s.dg[j] = inv;
-                __syncwarp();
-                if (lane > j && lane <= k) {
-                    const int cend = min(lane, k - 1);
-                    for (int c = j + 1; c <= cend; c++) S[lane * ldS + c] -= lij * S[c * ldS + j];
-                }
-                __syncwarp();
-            }
-            double z = lane < k ? S[k * ldS + lane] : 0.0;
-            for (int j = k - 1; j >= 0; j--) {
-                const double xj = __shfl_sync(0xffffffffu, z, j) * s.dg[j];
-                if (lane == j) z = xj;
-                if (lane < j) z -= S[j * ldS + lane] * xj;
-            }
-            if (lane < k) s.beta[lane] = z;
+            if (k + 1 <= 8) chol_warp_reg<8>(S, ldS, s.dg, s.beta, k);
+            else if (k + 1 <= 16) chol_warp_reg<16>(S, ldS, s.dg, s.beta, k);
+            else chol_warp_reg<24>(S, ldS, s.dg, s.beta, k);
         }
         __syncthreads();
         return;
@@ -705,23 +783,58 @@ __device__ void chol_solve(OwnSm &s, int k)
 
 // Residual of the next sweep, G[i][c] = (y_i - x_i,A beta_A) / n_train on the chain's train rows, 0 elsewhere
 // (Algorithm.h:1109), and on request the Lm losses of Metric.h:145-148 (all rows, / n) and :190 (held-out rows, / 2 n_t).
-__device__ void residual(const Dev &d, OwnSm &s, int c, int ks, int nt, int npad, bool want_loss, double *loss_all,
-                         double *loss_test)
+__device__ void residual(const Dev &d, OwnSm &s, int c, double *Rcol, int fh, int ks, int nt, int npad, bool want_loss,
+                         double *loss_all, double *loss_test)
 {
+    // Rcol: this chain's column of its group's residual matrix [npad][fh] (what the sweepers stage); d.G gets the same
+    // values so that the multi-kernel helpers (debug_sacrifice, time_dual_sweep) see the chain's current state
     const int n = d.n;
     double sa = 0.0, st = 0.0;
-    for (int i = threadIdx.x; i < n; i += LP_NT) {
-        double eta = 0.0;
-        for (int a = 0; a < ks; a++) eta = fma(s.XA[(size_t)s.slotA[a] * npad + i], s.beta[a], eta);
-        const double e = s.y[i] - eta;
-        const bool train = s.m[i] != 0.0;
-        __stcg(d.G + (size_t)i * d.FS + c, train ? e / (double)nt : 0.0);
-        sa += e * e;
-        if (!train) st += e * e;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 2 * LP_NT) {
+        const int i1 = i0 + LP_NT;
+        const bool two = i1 < n;
+        double eta0 = 0.0, eta1 = 0.0;
+        for (int a = 0; a < ks; a++) {
+            const double *col = s.XA + (size_t)s.slotA[a] * npad;
+            const double b = s.beta[a];
+            eta0 = fma(col[i0], b, eta0);
+            if (two) eta1 = fma(col[i1], b, eta1);
+        }
+        {
+            const double e = s.y[i0] - eta0;
+            const bool train = s.m[i0] != 0.0;
+            const double gv = train ? e / (double)nt : 0.0;
+            __stcg(Rcol + (size_t)i0 * fh, gv);
+            d.G[(size_t)i0 * d.FS + c] = gv;
+            sa += e * e;
+            if (!train) st += e * e;
+        }
+        if (two) {
+            const double e = s.y[i1] - eta1;
+            const bool train = s.m[i1] != 0.0;
+            const double gv = train ? e / (double)nt : 0.0;
+            __stcg(Rcol + (size_t)i1 * fh, gv);
+            d.G[(size_t)i1 * d.FS + c] = gv;
+            sa += e * e;
+            if (!train) st += e * e;
+        }
     }
     if (want_loss) {
-        const double ta = block_sum<LP_NT>(sa, s.red);
-        const double tt = block_sum<LP_NT>(st, s.red);
+        // both sums through one deterministic block reduction
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        sa = warp_sum(sa);
+        st = warp_sum(st);
+        __syncthreads();
+        if (lane == 0) {
+            s.red[2 + wid] = sa;
+            s.red[20 + wid] = st;
+        }
+        __syncthreads();
+        double ta = 0.0, tt = 0.0;
+        for (int w = 0; w < LP_NT / 32; w++) {
+            ta += s.red[2 + w];
+            tt += s.red[20 + w];
+        }
         *loss_all = ta / (double)n;
         *loss_test = n > nt ? tt / (double)(2 * (n - nt)) : 0.0;
     }
@@ -738,6 +851,8 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     OwnSm s = carve_owner(raw, npad, kcap, ns, L.hist_rows, &pre_sh, &scan_sh);
     (void)pre_sh;
     const int nt = d.ntrain[c];
+    const int g = L.ogroup[ci], og = 1 - g;
+    double *Rcol = L.Rg[g] + L.oslot[ci];
     const int *rows = d.rows + (size_t)c * n;
     double *bD = d.betaD + (size_t)c * d.pstride;
     Timer tm;
@@ -772,7 +887,7 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     double lam = L.lam[0];
     for (int a = tid; a < T; a += LP_NT) s.hist[a] = 0;  // A_list.col(0) = 0 (Algorithm.h:143)
     double la = 0.0, lt = 0.0;
-    residual(d, s, c, ks, nt, npad, false, &la, &lt);
+    residual(d, s, c, Rcol, L.fh, ks, nt, npad, false, &la, &lt);
     double tau = L.tau[c];
     if (tid == 0) {
         __stcg(L.pub + 2 * c, tau);
@@ -780,156 +895,195 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     }
     bool complete = false;
     tm.mark(0);
-    cta_arrive(L.sync + LP_SYNC_B2);
+    cta_arrive(L.sync + LP_SYNC_B2 + g);
 
+    // Owner phase O_g(it) has index ng * it + g (see sweeper_main).  Before reading the termination word the owner has
+    // seen every owner phase up to its decision index complete (its own group's phase it - 1 and the other group's phase
+    // just before it), so the word can no longer change below that index: every CTA leaves at the same point.
     for (unsigned it = 1;; it++) {
-        if (!cta_wait(L.sync, LP_SYNC_B2, (unsigned)L.nch * it, &s.misc[MI_FLAG])) return;
+        if (!cta_wait(L.sync, LP_SYNC_B2 + g, (unsigned)L.gcount[g] * it, &s.misc[MI_FLAG])) return;
+        if (L.ng == 2 && !cta_wait(L.sync, LP_SYNC_B2 + og, (unsigned)L.gcount[og] * (g == 0 ? it - 1u : it), &s.misc[MI_FLAG]))
+            return;
         {
             const unsigned term = ld_acquire_u32(L.sync + LP_SYNC_TERM);
-            if (term != 0u && term <= it) return;
+            if (term != 0u && term - 1u <= (unsigned)L.ng * (it - 1u) + (unsigned)g) return;
         }
-        if (!cta_wait(L.sync, LP_SYNC_B1, (unsigned)L.nsweep * it, &s.misc[MI_FLAG])) return;
+        if (!cta_wait(L.sync, LP_SYNC_B1 + g, (unsigned)L.nsweep * it, &s.misc[MI_FLAG])) return;
         tm.mark(1);
+        const long long t_phase = clock64();
         if (!complete) {
-            const int k = T;
-            // ---- exact top-k (max_k, utilities.cpp:179-188): candidates published by the sweepers, else the whole vector
-            if (tid == 0) s.misc[MI_COUNT] = __ldcg(L.ncand + c);
-            __syncthreads();
-            int count = s.misc[MI_COUNT];
-            double vk = 0.0;
-            bool tie_known = false;
-            if (count >= k && count <= LP_CAP) {
-                if (tid < count) {
-                    const int4 raw4 = __ldcg(reinterpret_cast<const int4 *>(L.cand + (size_t)c * LP_CAP + tid));
-                    const LpCand cnd = *reinterpret_cast<const LpCand *>(&raw4);
+            // ---- the candidates the sweepers published for this chain; the count and the (possibly stale) slots are
+            // fetched together: one L2 round trip
+            {
+                int4 raw4 = make_int4(0, 0, 0, 0);
+                if (tid < LP_CAP) raw4 = __ldcg(reinterpret_cast<const int4 *>(L.cand + (size_t)c * LP_CAP + tid));
+                if (tid == 0) s.misc[MI_COUNT] = __ldcg(L.ncand + c);
+                const LpCand cnd = *reinterpret_cast<const LpCand *>(&raw4);
+                if (tid < LP_CAP) {
                     s.cv[tid] = cnd.v;
                     s.ci[tid] = cnd.idx;
                 }
-                __syncthreads();
-            } else {
-                fallback_select(d.bd + (size_t)c * d.pstride, p, k, s, scan_sh, &vk);
-                count = k;
-                tie_known = true;
-                if (tid == 0) atomicAdd(L.sync + LP_SYNC_FALLBACKS, 1u);
-            }
-            rank_select(s, count, k, tie_known, &vk);
-            tau = 0.7 * vk;
-            tm.mark(2);
-            // ---- which of the selected columns are already resident; the others take the slots of columns not selected
-            for (int q = tid; q < ns; q += LP_NT) s.keep[q] = 0;
-            __syncthreads();
-            if (tid < k) {
-                const int j = s.Anew[tid];
-                int sl = -1;
-                for (int q = 0; q < ns; q++)
-                    if (s.slot_col[q] == j) sl = q;
-                s.slotNew[tid] = sl;
-                if (sl >= 0) s.keep[sl] = 1;
             }
             __syncthreads();
-            if (tid == 0) {
-                int nnew = 0, q = 0;
-                // empty slots first, then the slots of columns that are not selected now
-                for (int pass = 0; pass < 2; pass++) {
-                    q = 0;
-                    for (int a = 0; a < k; a++) {
-                        if (s.slotNew[a] >= 0) continue;
-                        while (q < ns && (s.keep[q] || (pass == 0 && s.slot_col[q] >= 0))) q++;
-                        if (q >= ns) break;
-                        s.slotNew[a] = q;
-                        s.slot_col[q] = s.Anew[a];
-                        s.keep[q] = 1;
-                        s.newlist[nnew++] = q;
-                    }
-                }
-                s.misc[MI_NNEW] = nnew;
-            }
-            __syncthreads();
-            const int nnew = s.misc[MI_NNEW];
-            gather_new(d, s, nnew, npad);
-            tm.mark(3);
-            gram_new(d, s, nnew, ns, npad);
-            tm.mark(4);
-            // ---- X_A^T X_A + lambda I | X_A^T y  (Algorithm.h:1134), solve
-            for (int e = tid; e < (k + 1) * k; e += LP_NT) {
-                const int a = e / k, b = e - a * k;
-                s.S[a * s.ldS + b] =
-                    a < k ? s.Gc[(size_t)s.slotNew[a] * ns + s.slotNew[b]] + (a == b ? lam : 0.0) : s.bc[s.slotNew[b]];
-            }
-            __syncthreads();
-            chol_solve(s, k);
-            tm.mark(5);
-            // ---- scatter (Algorithm.h:159-163), cycle test against A_list[0..l] (Algorithm.h:164-170)
-            for (int a = tid; a < ks; a += LP_NT) __stcg(bD + s.A[a], 0.0);
-            if (tid == 0) s.misc[MI_SEEN] = 0;
-            __syncthreads();
-            for (int a = tid; a < k; a += LP_NT) {
-                s.A[a] = s.Anew[a];
-                s.slotA[a] = s.slotNew[a];
-                __stcg(bD + s.Anew[a], s.beta[a]);
-            }
-            ks = k;
-            l += 1;
-            for (int ll = wid; ll < l; ll += LP_NT / 32) {
-                const int *hp = s.hist + (size_t)ll * kcap;
-                int same = 1;
-                for (int a = lane; a < k; a += 32) same &= (hp[a] == s.Anew[a]);
-                if (__all_sync(0xffffffffu, same) && lane == 0) s.misc[MI_SEEN] = 1;
-            }
-            __syncthreads();
-            const bool seen = s.misc[MI_SEEN] != 0;
-            tie_acc += s.misc[MI_TIE];
-            if (l < L.hist_rows)
-                for (int a = tid; a < k; a += LP_NT) s.hist[(size_t)l * kcap + a] = s.Anew[a];
-            const bool finished = seen || l >= d.max_iter;
-            residual(d, s, c, ks, nt, npad, finished, &la, &lt);
-            tm.mark(6);
-            if (finished) {
-                int *ri = L.res_i + ((size_t)step * L.nch + ci) * (2 + kcap);
-                double *rd = L.res_d + ((size_t)step * L.nch + ci) * (2 + kcap);
-                const int l_out = seen ? l : d.max_iter + 1;
-                if (tid == 0) {
-                    ri[0] = l_out;
-                    ri[1] = tie_acc;
-                    rd[0] = la;
-                    rd[1] = lt;
-                }
-                for (int a = tid; a < k; a += LP_NT) {
-                    ri[2 + a] = s.A[a];
-                    rd[2 + a] = s.beta[a];
-                }
-                step += 1;
-                if (step == L.nsteps) {
-                    complete = true;
-                    // hand the chain back to the engine's tables (chain_state / the multi-kernel path read them)
-                    for (int a = tid; a < k; a += LP_NT) {
-                        d.A[(size_t)c * kcap + a] = s.A[a];
-                        d.bA[(size_t)c * kcap + a] = s.beta[a];
-                    }
-                    if (tid == 0) {
-                        d.ks[c] = ks;
-                        d.l[c] = l_out;
-                        d.done[c] = 1;
-                        d.coef0[c] = 0.0;
-                        d.tie_acc[c] = tie_acc;
-                        L.tau[c] = tau;
-                        const unsigned old = atomicAdd(L.sync + LP_SYNC_NCOMPLETE, 1u);
-                        if (old + 1u == (unsigned)L.nch) {
-                            atomicExch(L.sync + LP_SYNC_TERM, it + 1u);
-                            atomicExch(L.sync + LP_SYNC_ITERS, it);
-                        }
-                    }
-                } else {
-                    T = L.T[step];
-                    lam = L.lam[step];
-                    l = 0;
-                    tie_acc = 0;
+            int count = s.misc[MI_COUNT];
+            // One sweep can serve two fits: when a fit ends because its active set repeats the previous one, beta has not
+            // moved since the sweep, and the first get_A of the NEXT path step (warm start, same ridge level) would
+            // recompute exactly this sacrifice vector -- the owner selects again from the same candidates at once.
+            bool again = true;
+            while (again) {
+                again = false;
+                const int k = T;
+                // ---- exact top-k (max_k, utilities.cpp:179-188)
+                const int deep = min(p, 2 * k + 4);  // how far down the order statistics the next threshold looks
+                if (count < k || count > LP_CAP) {
                     __syncthreads();
-                    for (int a = tid; a < T; a += LP_NT) s.hist[a] = 0;
-                    if (!d.warm) {
-                        for (int a = tid; a < ks; a += LP_NT) __stcg(bD + s.A[a], 0.0);
-                        ks = 0;
-                        residual(d, s, c, 0, nt, npad, false, &la, &lt);
+                    const long long t_fb = clock64();
+                    fallback_select(d.bd + (size_t)c * d.pstride, p, deep, s, scan_sh);
+                    count = min(s.misc[MI_CNT], LP_CAP);
+                    if (tid == 0) {
+                        atomicAdd(L.sync + LP_SYNC_FALLBACKS, 1u);
+                        L.dbg[32 + 4 * ci + 2] += (unsigned long long)(clock64() - t_fb);
+                    }
+                }
+                double vk = 0.0, vdeep = 0.0;
+                rank_select(s, count, k, deep, &vk, &vdeep);
+                // candidate threshold of the next iteration: well below the `deep`-th largest sacrifice, so that the next
+                // level (k + 1) and moderately changed sacrifices still find their k winners in the list
+                tau = 0.7 * vdeep;
+                tm.mark(2);
+                // ---- same active set as the previous iteration of this fit: the fit would reproduce beta bit for bit
+                // and the cycle test (Algorithm.h:164-170) ends the fit -- nothing to recompute
+                int same = (l >= 1 && ks == k) ? 1 : 0;
+                if (same)
+                    for (int a2 = tid; a2 < k; a2 += LP_NT) same &= (s.A[a2] == s.Anew[a2]);
+                same = __syncthreads_and(same);
+                bool seen = same != 0;
+                if (!same) {
+                    // ---- which of the selected columns are already resident; the others take the slots of columns not selected
+                    for (int q = tid; q < ns; q += LP_NT) s.keep[q] = 0;
+                    __syncthreads();
+                    if (tid < k) {
+                        const int j = s.Anew[tid];
+                        int sl = -1;
+                        for (int q = 0; q < ns; q++)
+                            if (s.slot_col[q] == j) sl = q;
+                        s.slotNew[tid] = sl;
+                        if (sl >= 0) s.keep[sl] = 1;
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        int nnew = 0, q = 0;
+                        // empty slots first, then the slots of columns that are not selected now
+                        for (int pass = 0; pass < 2; pass++) {
+                            q = 0;
+                            for (int a2 = 0; a2 < k; a2++) {
+                                if (s.slotNew[a2] >= 0) continue;
+                                while (q < ns && (s.keep[q] || (pass == 0 && s.slot_col[q] >= 0))) q++;
+                                if (q >= ns) break;
+                                s.slotNew[a2] = q;
+                                s.slot_col[q] = s.Anew[a2];
+                                s.keep[q] = 1;
+                                s.newlist[nnew++] = q;
+                            }
+                        }
+                        s.misc[MI_NNEW] = nnew;
+                    }
+                    __syncthreads();
+                    const int nnew = s.misc[MI_NNEW];
+                    gather_new(d, s, nnew, npad);
+                    tm.mark(3);
+                    gram_new(d, s, nnew, ns, npad);
+                    tm.mark(4);
+                    // ---- X_A^T X_A + lambda I | X_A^T y  (Algorithm.h:1134), solve
+                    for (int e = tid; e < (k + 1) * k; e += LP_NT) {
+                        const int a2 = e / k, b2 = e - a2 * k;
+                        s.S[a2 * s.ldS + b2] = a2 < k ? s.Gc[(size_t)s.slotNew[a2] * ns + s.slotNew[b2]] + (a2 == b2 ? lam : 0.0)
+                                                      : s.bc[s.slotNew[b2]];
+                    }
+                    __syncthreads();
+                    tm.mark(8);
+                    chol_solve(s, k);
+                    tm.mark(5);
+                    // ---- scatter (Algorithm.h:159-163), cycle test against A_list[0..l] (Algorithm.h:164-170)
+                    for (int a2 = tid; a2 < ks; a2 += LP_NT) __stcg(bD + s.A[a2], 0.0);
+                    if (tid == 0) s.misc[MI_SEEN] = 0;
+                    __syncthreads();
+                    for (int a2 = tid; a2 < k; a2 += LP_NT) {
+                        s.A[a2] = s.Anew[a2];
+                        s.slotA[a2] = s.slotNew[a2];
+                        __stcg(bD + s.Anew[a2], s.beta[a2]);
+                    }
+                    ks = k;
+                    for (int ll = wid; ll <= l; ll += LP_NT / 32) {
+                        const int *hp = s.hist + (size_t)ll * kcap;
+                        int eq = 1;
+                        for (int a2 = lane; a2 < k; a2 += 32) eq &= (hp[a2] == s.Anew[a2]);
+                        if (__all_sync(0xffffffffu, eq) && lane == 0) s.misc[MI_SEEN] = 1;
+                    }
+                    __syncthreads();
+                    seen = s.misc[MI_SEEN] != 0;
+                    // the losses ride along with every residual: a fit that ends on a repeated set needs them without a pass
+                    residual(d, s, c, Rcol, L.fh, ks, nt, npad, true, &la, &lt);
+                    tm.mark(6);
+                    if (tid == 0) L.dbg[32 + 4 * ci + 3] += 1ull;
+                }
+                l += 1;
+                tie_acc += s.misc[MI_TIE];
+                if (l < L.hist_rows)
+                    for (int a2 = tid; a2 < k; a2 += LP_NT) s.hist[(size_t)l * kcap + a2] = s.Anew[a2];
+                const bool finished = seen || l >= d.max_iter;
+                if (finished) {
+                    int *ri = L.res_i + ((size_t)step * L.nch + ci) * (2 + kcap);
+                    double *rd = L.res_d + ((size_t)step * L.nch + ci) * (2 + kcap);
+                    const int l_out = seen ? l : d.max_iter + 1;
+                    if (tid == 0) {
+                        ri[0] = l_out;
+                        ri[1] = tie_acc;
+                        rd[0] = la;
+                        rd[1] = lt;
+                    }
+                    for (int a2 = tid; a2 < k; a2 += LP_NT) {
+                        ri[2 + a2] = s.A[a2];
+                        rd[2 + a2] = s.beta[a2];
+                    }
+                    step += 1;
+                    if (step == L.nsteps) {
+                        complete = true;
+                        // hand the chain back to the engine's tables (chain_state / the multi-kernel path read them)
+                        for (int a2 = tid; a2 < k; a2 += LP_NT) {
+                            d.A[(size_t)c * kcap + a2] = s.A[a2];
+                            d.bA[(size_t)c * kcap + a2] = s.beta[a2];
+                        }
+                        if (tid == 0) {
+                            d.ks[c] = ks;
+                            d.l[c] = l_out;
+                            d.done[c] = 1;
+                            d.coef0[c] = 0.0;
+                            d.tie_acc[c] = tie_acc;
+                            L.tau[c] = tau;
+                            const unsigned old = atomicAdd(L.sync + LP_SYNC_NCOMPLETE, 1u);
+                            if (old + 1u == (unsigned)L.nch) {
+                                atomicExch(L.sync + LP_SYNC_TERM, (unsigned)L.ng * it + (unsigned)g + 1u);
+                                atomicExch(L.sync + LP_SYNC_ITERS, (unsigned)L.ng * (it - 1u) + (unsigned)g + 1u);  // sweeps that fed a fit
+                            }
+                        }
+                    } else {
+                        const double lam_prev = lam;
+                        T = L.T[step];
+                        lam = L.lam[step];
+                        l = 0;
+                        tie_acc = 0;
+                        __syncthreads();
+                        for (int a2 = tid; a2 < T; a2 += LP_NT) s.hist[a2] = 0;
+                        if (!d.warm) {
+                            for (int a2 = tid; a2 < ks; a2 += LP_NT) __stcg(bD + s.A[a2], 0.0);
+                            ks = 0;
+                            residual(d, s, c, Rcol, L.fh, 0, nt, npad, true, &la, &lt);
+                        } else if (same && lam == lam_prev) {
+                            again = true;  // the sweep this phase consumed was computed from exactly the state the next step starts in
+                            if (tid == 0) atomicAdd(L.sync + LP_SYNC_MERGED, 1u);
+                        }
+                        __syncthreads();
                     }
                 }
             }
@@ -940,7 +1094,13 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
             }
             tm.mark(7);
         }
-        cta_arrive(L.sync + LP_SYNC_B2);
+        if (tid == 0) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t_phase);
+            unsigned long long *od = L.dbg + 32 + 4 * ci;
+            od[0] += dt;
+            if (dt > od[1]) od[1] = dt;
+        }
+        cta_arrive(L.sync + LP_SYNC_B2 + g);
     }
 }
 
@@ -972,12 +1132,22 @@ int lm_path_slots(const Dev &d, int max_iter)
     return ns;
 }
 
+int lm_path_groups(int nch) { return nch >= 4 ? 2 : 1; }
+int lm_path_fh(int nch, int ng)
+{
+    const int per = (nch + ng - 1) / ng;
+    const int opts[] = {1, 2, 4, 6, 8, 12, 16};
+    for (int o : opts)
+        if (o >= per) return o;
+    return 16;
+}
+
 size_t lm_path_smem_bytes(const Dev &d, int max_iter, int sm_count)
 {
     (void)sm_count;
     const int npad = (d.n + 1) & ~1;
     const size_t own = owner_smem_bytes(npad, d.kcap, lm_path_slots(d, max_iter), max_iter + 2);
-    const size_t swp = sweeper_smem_doubles(npad, d.FS) * 8;
+    const size_t swp = sweeper_smem_doubles(npad, d.FS) * 8;  // d.FS >= the slots of any group of any batch
     return ((own > swp ? own : swp) + 127) & ~(size_t)127;
 }
 
@@ -1006,7 +1176,7 @@ void launch_lm_path(const Dev &d, const LpDesc &desc, int sm_count, int max_iter
 {
     const size_t smem = lm_path_smem_bytes(d, max_iter, sm_count);
     void (*fn)(const Dev, const LpDesc) = nullptr;
-    switch (d.FS) {
+    switch (desc.fh) {
         case 1: fn = lm_path_kernel<1>; break;
         case 2: fn = lm_path_kernel<2>; break;
         case 4: fn = lm_path_kernel<4>; break;

@@ -12,7 +12,7 @@ constexpr int LP_MAXSTEP = 64;    // path steps (sparsity level, ridge level) pe
 constexpr int LP_WPMAX = 128;     // widest column slice of a sweeper CTA, in column pairs
 constexpr int LP_RPMAX = 32;      // most row phases of a sweeper CTA (bounds its serial partial reduction)
 constexpr int LP_KMAX = 64;       // largest support the in-kernel solver handles
-constexpr int LP_NDBG = 32;
+constexpr int LP_NDBG = 32 + 4 * MAXC;  // 0..15 owner 0 phases, 16..31 sweeper 0 phases, then 4 words per chain owner
 
 struct LpCand {
     double v;
@@ -20,8 +20,9 @@ struct LpCand {
     int pad;
 };
 
-enum { LP_SYNC_B1 = 0, LP_SYNC_B2 = 1, LP_SYNC_NCOMPLETE = 2, LP_SYNC_TERM = 3, LP_SYNC_ITERS = 4, LP_SYNC_ABORT = 5,
-       LP_SYNC_FALLBACKS = 6, LP_SYNC_WORDS = 8 };
+// words of LpDesc::sync.  B1 / B2 have one counter per chain group.
+enum { LP_SYNC_B1 = 0, LP_SYNC_B2 = 2, LP_SYNC_NCOMPLETE = 4, LP_SYNC_TERM = 5, LP_SYNC_ITERS = 6, LP_SYNC_ABORT = 7,
+       LP_SYNC_FALLBACKS = 8, LP_SYNC_MERGED = 9, LP_SYNC_WORDS = 16 };
 
 // One launch = `nsteps` path steps for the chains of one batch.  Passed by value.
 struct LpDesc {
@@ -31,6 +32,15 @@ struct LpDesc {
     int T[LP_MAXSTEP];
     double lam[LP_MAXSTEP];
     int chain[MAXC];
+    // chain groups: the sweepers alternate between the groups, so that the owners of one group work on their active sets
+    // while the other group's sacrifices are swept (one group: plain alternation of sweep and owner phases)
+    int ng;                // 1 or 2
+    int gcount[2];         // chains per group
+    int gchain[2][MAXC];   // chain id of slot f of group g
+    int ogroup[MAXC];      // group / slot of the chain at position i of chain[]
+    int oslot[MAXC];
+    int fh;                // chain slots of a group's residual matrix (the sweeper's FT)
+    double *Rg[2];         // [npad][fh] residual vectors of each group
     const int *always;     // [n_always] pinned columns (always_select)
     const double *y;       // [n] response after normalisation
     unsigned *sync;        // [LP_SYNC_WORDS], zeroed before every launch
@@ -48,5 +58,8 @@ bool lm_path_eligible(const Dev &d, int max_iter, int sm_count, std::string *why
 size_t lm_path_smem_bytes(const Dev &d, int max_iter, int sm_count);
 int lm_path_slots(const Dev &d, int max_iter);
 void launch_lm_path(const Dev &d, const LpDesc &desc, int sm_count, int max_iter, cudaStream_t st);
+// chain slots per group for a batch of nch chains split into ng groups (a supported sweeper instantiation)
+int lm_path_fh(int nch, int ng);
+int lm_path_groups(int nch);
 
 }  // namespace bess

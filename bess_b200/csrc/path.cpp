@@ -818,6 +818,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     eng.profile(out.prof_ms, out.prof_n);
     out.sweep_splits = eng.sweep_splits();
     eng.resident_counters(out.resident);
+    eng.resident_owner_counters(out.resident + 24);
 }
 
 }  // namespace bess

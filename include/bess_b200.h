@@ -83,10 +83,11 @@ typedef struct bess_b200_ext {
     int cv_reduce_over_ranks;   /* world > 1, sequential path, CV + screening: REPEATED K-fold CV -- every rank passes its  */
                                 /* own folds (cv_seed / fold_of_row), the per-level CV losses are averaged over the ranks   */
                                 /* (one ncclAllReduce) before the level is chosen; all ranks return the same model          */
-    double *resident_out;       /* [24] counters of the resident-path kernel (gaussian family, design resident in L2: the   */
+    double *resident_out;       /* [88] counters of the resident-path kernel (gaussian family, design resident in L2: the   */
                                 /* whole PDAS path is ONE cooperative launch): 0 launches, 1 PDAS iterations, 2 full-vector */
                                 /* select fallbacks, 3 path steps, 8..15 clock ticks by phase of chain owner 0, 16..18 of    */
-                                /* sweeper 0; all zero when the multi-kernel path ran                                        */
+                                /* sweeper 0; 24 + 4 i ..: chain owner i: busy ticks, longest phase, ticks in fallback        */
+                                /* selects, fits solved; all zero when the multi-kernel path ran                             */
 } bess_b200_ext;
 
 /* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's
