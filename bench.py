@@ -152,11 +152,29 @@ def _ref_worker(d, levels, nsteps, barrier, q):
     q.put(times)
 
 
+def _mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return float(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+# one reference call on C5 holds its row-major input (shared with the parent, copy-on-write), the column-major copy of
+# Pointer2MatrixXd (utilities.cpp:13-25) and the by-value copy of bessCpp (bess.h:20) until screening shrinks it: ~9-12 GB
+REF_GB_PER_PROC, REF_GB_PARENT = 13.0, 6.0
+
+
 def run_reference(args):
-    """The reference arm: the reference's own CPU implementation on the box's host cores.  The library is single-threaded
-    (python/setup.py:38-40: no OpenMP), so "all the host threads it can use" = independent calls side by side, one
-    process per core (capped at 16: every call copies its 0.2-0.6 GB design several times over, Algorithm.h:133-138, 228).
-    A step = every process makes one call on the sample, all released together; the step time is the slowest process."""
+    """The reference arm: the reference's own CPU implementation (oracle/_ref = /root/reference/src compiled as shipped) on
+    the box's host cores, ON CONFIG 5 ITSELF -- n=1000, p=500000, screening.num=5000, 10-fold CV, s.list=1..20, 220 fits per
+    call, ~50-150 s per call.  The library is single-threaded (python/setup.py:38-40: no OpenMP), so "all the host threads it
+    can use" = independent calls side by side, one process per core, as many as the host memory holds (~13 GB each).
+    Every process makes ONE timed call (no warm-up: --steps/--warmup would cost tens of minutes and a CPU library has nothing
+    to warm), all released together; the step time is the slowest process.  If the host cannot hold even one full call
+    the arm falls back to the proportional slice of round 1 and says so in `reference_sample`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -164,14 +182,24 @@ def run_reference(args):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbess_ref.so was not built"}))
         return
+    ref.lib()  # mapped in THIS process before forking, so the loaded .so is visible to whoever inspects the arm
     import multiprocessing as mp
-    total = args.warmup + args.steps
-    levels = int(max(1, min(CPU_SMAX, 150.0 / (max(total, 1) * 3.5))))  # keep the whole run within a few minutes
-    procs = max(1, min(os.cpu_count() or 1, 16))
+    cores = os.cpu_count() or 1
+    avail = _mem_available_gb()
+    procs_full = int(min(cores, 16, (avail - REF_GB_PARENT) // REF_GB_PER_PROC))
     # test overrides (tests/test_bench_contract.py runs this arm on a tiny sample)
-    levels = int(os.environ.get("BESS_BENCH_REF_LEVELS", levels))
-    procs = int(os.environ.get("BESS_BENCH_REF_PROCS", procs))
-    d, p = _ref_sample(levels)
+    force_levels = os.environ.get("BESS_BENCH_REF_LEVELS")
+    full = procs_full >= 1 and force_levels is None
+    if full:
+        levels, procs, total, warm = SMAX, procs_full, 1, 0
+        from bess_b200.gen_data import gen_data
+        d, p = gen_data(N_ROWS, P_COLS, "gaussian", K_TRUE, seed=5), P_COLS
+    else:
+        total, warm = args.warmup + args.steps, args.warmup
+        levels = int(max(1, min(CPU_SMAX, 150.0 / (max(total, 1) * 3.5))))  # keep the whole run within a few minutes
+        levels = int(force_levels) if force_levels is not None else levels
+        procs = int(os.environ.get("BESS_BENCH_REF_PROCS", max(1, min(cores, 16))))
+        d, p = _ref_sample(levels)
     ctx = mp.get_context("fork")
     barrier, q = ctx.Barrier(procs), ctx.Queue()
     ws = [ctx.Process(target=_ref_worker, args=(d, levels, total, barrier, q)) for _ in range(procs)]
@@ -180,16 +208,25 @@ def run_reference(args):
     per_proc = [q.get() for _ in ws]
     for pr in ws:
         pr.join()
-    step_s = np.max(np.array(per_proc), axis=0)[args.warmup:]  # slowest process of every timed step
+    step_s = np.max(np.array(per_proc), axis=0)[warm:]  # slowest process of every timed step
     dt = float(np.mean(step_s))
     fits = levels * (1 + NFOLDS) * procs
     val = fits / dt
-    base = {"value": val, "unit": "fits/s", "cores": procs, "kind": "reference", "seconds": dt,
-            "sample": _sample_text(p, levels, procs)}
+    if full:
+        sample = (f"oracle/_ref (reference src/*.cpp, -O2, single-threaded as shipped) on config 5 ITSELF: n=1000, p=500000, "
+                  f"screening.num=5000, 10-fold CV, s.list=1..20 (220 fits per call); {procs} independent calls side by side, one "
+                  f"per process ({cores} cores, {avail:.0f} GB available, ~{REF_GB_PER_PROC:.0f} GB per call); one timed call per "
+                  f"process, no warm-up (per-process call times {min(min(t) for t in per_proc):.1f}-{max(max(t) for t in per_proc):.1f} s)")
+    else:
+        sample = _sample_text(p, levels, procs) + (f" [fallback: {avail:.0f} GB of host memory cannot hold one full config-5 call]"
+                                                   if force_levels is None else "")
+    base = {"value": val, "unit": "fits/s", "cores": procs, "kind": "reference", "seconds": dt, "sample": sample}
     print(json.dumps({"impl": "reference", "metric": "pdas_path_cv_fits_per_sec", "value": val, "unit": "fits/s",
-                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                      "n_gpus": args.gpus, "steps": len(step_s), "warmup": warm, "steps_requested": args.steps,
+                      "warmup_requested": args.warmup, "ms_per_step": dt * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                      "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": base["sample"]},
+                      "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": sample,
+                                                      "same_config_as_gpu_arm": bool(full)},
                       "cpu_baseline": base,
                       "e2e": {"value": val, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

@@ -69,7 +69,7 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
 
 def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, exchange_num, path_type,
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
-        fold_of_row=None, cv_seed=0, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
+        fold_of_row=None, cv_seed=None, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
         world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,), lambda_min=0.0, lambda_max=0.0,
         n_lambda=None, powell_path=1, want_curve=False, g_index=None, cv_reduce_over_ranks=False):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
@@ -112,7 +112,8 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     if fold_of_row is not None:
         fold = np.ascontiguousarray(fold_of_row, dtype=np.int32)
         ext.fold_of_row = _i(fold)
-    ext.cv_seed = int(cv_seed)
+    ext.cv_seed = int(cv_seed) if cv_seed is not None else 0  # None: $BESS_CV_SEED or 123
+    ext.cv_seed_set = 1 if cv_seed is not None else 0
     ext.x_on_device = 1 if x_device_ptr is not None else 0
     ext.device = int(device)
     scrA = np.zeros(max(int(screening_size), 1), dtype=np.int32)
@@ -123,7 +124,9 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     ext.chosen_lambda_out = C.pointer(chosen_lam)
     stats = np.zeros(32)
     ext.stats_out = _d(stats)
-    resident = np.zeros(88)
+    resident = np.zeros(152)
+    tie_exact = C.c_int(0)
+    ext.tie_exact_out = C.pointer(tie_exact)
     ext.resident_out = _d(resident)
     ext.profile = 1 if profile else 0
     ext.beta_out_zeroed = 1  # `beta` comes from np.zeros (calloc): untouched pages stay untouched
@@ -143,7 +146,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
                           kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[24]),
                           sweep_splits=int(stats[25]), norm_bytes=float(stats[26]),
                           host_ms=dict(zip(("load", "screen", "normalize", "setup_chains", "path"), stats[27:32].tolist())),
-                          resident=resident.tolist(),
+                          resident=resident.tolist(), tie_exact_pass=bool(tie_exact.value),
                           prof_ms=dict(zip(PROF_CATS, stats[8:16].tolist())),
                           prof_launches=dict(zip(PROF_CATS, [int(v) for v in stats[16:24]]))))
     if is_screening:

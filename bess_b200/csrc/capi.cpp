@@ -75,13 +75,15 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
         a.s_min = s_min; a.s_max = s_max; a.K_max = K_max; a.epsilon = epsilon; a.lambda_min = lambda_min;
         a.lambda_max = lambda_max; a.nlambda = n_lambda; a.is_screening = is_screening;
         a.screening_size = screening_size; a.powell_path = powell_path;
-        if (gindex && gindex_len > 0 && !shard) a.g_index.assign(gindex, gindex + gindex_len);
+        // (in column-sharded mode a real group structure is refused by bess_run; a trivial gindex -- one entry per local
+        // column, 0..x_col-1 -- carries no information and is dropped)
+        if (gindex && gindex_len > 0 && !(shard && gindex_len == x_col)) a.g_index.assign(gindex, gindex + gindex_len);
         if (always_select && always_select_len > 0) a.always_select.assign(always_select, always_select + always_select_len);
         a.tao = tao;
         a.cv_seed = env_seed();
         if (ext) {
             a.fold_of_row = ext->fold_of_row;
-            if (ext->cv_seed) a.cv_seed = ext->cv_seed;
+            if (ext->cv_seed || ext->cv_seed_set) a.cv_seed = ext->cv_seed;
             a.x_on_device = ext->x_on_device != 0;
             a.device = ext->device;
             a.profile = ext->profile != 0;
@@ -110,7 +112,8 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
                 std::copy(r.screening_A.begin(), r.screening_A.end(), ext->screening_A_out);
             if (ext->chosen_s_out) *ext->chosen_s_out = r.chosen_s;
             if (ext->chosen_lambda_out) *ext->chosen_lambda_out = r.lambda;
-            if (ext->resident_out) std::copy(r.resident, r.resident + 88, ext->resident_out);
+            if (ext->resident_out) std::copy(r.resident, r.resident + 24 + 4 * MAXC, ext->resident_out);
+            if (ext->tie_exact_out) *ext->tie_exact_out = r.tie_exact_pass ? 1 : 0;
             if (ext->stats_out) {
                 ext->stats_out[0] = (double)r.stats.n_fits;
                 ext->stats_out[1] = (double)r.stats.n_pdas_iters;

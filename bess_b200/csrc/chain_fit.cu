@@ -1281,7 +1281,7 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_begin_kernel(const Dev d, con
         d.l[c] = 0;
         d.done[c] = 0;
     }
-    int *h0 = d.hist + (size_t)c * MAX_HIST * d.kcap;
+    int *h0 = d.hist + (size_t)c * d.hist_rows * d.kcap;
     for (int a = threadIdx.x; a < b.T; a += FIT_NT) h0[a] = 0;
     for (int a = threadIdx.x; a < ks; a += FIT_NT) sm.b0[a] = d.bA[(size_t)c * d.kcap + a];
     __syncthreads();
@@ -1380,7 +1380,7 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     // cycle test (Algorithm.h:164-170) against A_list[0..l-1]; every CTA of the cluster evaluates it identically
     int seen = 0;
     for (int ll = 0; ll < l && !seen; ll++) {
-        const int *hp = d.hist + ((size_t)c * MAX_HIST + ll) * d.kcap;
+        const int *hp = d.hist + ((size_t)c * d.hist_rows + ll) * d.kcap;
         int same = 1;
         for (int a = threadIdx.x; a < T0; a += FIT_NT) same &= (hp[a] == Ag[a]);
         seen = __syncthreads_and(same);
@@ -1390,7 +1390,7 @@ __global__ void __launch_bounds__(FIT_NT, 1) chain_fit_kernel(const Dev d, const
     cl.pt.mark(PH_CYCLE);
     // scatter (Algorithm.h:159-163), record A
     if (cl.rank == 0) {
-        int *hl = d.hist + ((size_t)c * MAX_HIST + l) * d.kcap;
+        int *hl = d.hist + ((size_t)c * d.hist_rows + l) * d.kcap;
         for (int a = threadIdx.x; a < T0; a += FIT_NT) hl[a] = Ag[a];
         for (int a = threadIdx.x; a < T; a += FIT_NT) {
             const int j = Anew[a];

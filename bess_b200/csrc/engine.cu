@@ -41,9 +41,183 @@ void dfree(cudaStream_t st, T *&p)
     p = nullptr;
 }
 
+// Workspaces cached per device for the life of the process.  A call on a 1000 x 5000 screened design is a few hundred
+// microseconds of kernels; dozens of cudaMallocAsync / cudaMemsetAsync / pageable cudaMemcpyAsync calls (3-20 us of host
+// time each) used to cost more than the kernels.  All small buffers are therefore bump-allocated from chunks that are
+// created once and reused by every later call:
+//   * DevArena     device-only scratch and state (stack discipline: mark / release; one stream, so stream order == program
+//                  order and a released block can be handed out again at once);
+//   * MirrorArena  host-to-device payloads: a pinned chunk and its device twin; the host fills the pinned side, flush()
+//                  moves everything filled since the last flush with ONE truly asynchronous copy;
+//   * pinned read-back blocks for results that the host only needs at the end of the call.
+// Chunks never move, so pointers stay valid; a chunk that is too small is left in place and a larger one is appended
+// (cudaMalloc -- only while the process warms up).
+struct DevArena {
+    struct Chunk {
+        char *base = nullptr;
+        size_t cap = 0, used = 0;
+    };
+    struct Mark {
+        size_t chunk = 0, used = 0;
+    };
+    std::vector<Chunk> chunks;
+    size_t cur = 0;
+    void *alloc_bytes(size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        for (;;) {
+            if (cur < chunks.size()) {
+                Chunk &c = chunks[cur];
+                if (c.used + bytes <= c.cap) {
+                    void *p = c.base + c.used;
+                    c.used += bytes;
+                    return p;
+                }
+                if (cur + 1 < chunks.size()) {
+                    cur++;
+                    chunks[cur].used = 0;
+                    continue;
+                }
+            }
+            Chunk c;
+            c.cap = std::max<size_t>(bytes, (size_t)32 << 20);
+            CUDA_CHECK(cudaMalloc((void **)&c.base, c.cap));
+            chunks.push_back(c);
+            cur = chunks.size() - 1;
+        }
+    }
+    template <class T>
+    T *alloc(size_t count)
+    {
+        return reinterpret_cast<T *>(alloc_bytes(count * sizeof(T)));
+    }
+    Mark mark() const { return Mark{cur, cur < chunks.size() ? chunks[cur].used : 0}; }
+    void release(const Mark &mk)
+    {
+        if (chunks.empty()) return;
+        cur = std::min(mk.chunk, chunks.size() - 1);
+        chunks[cur].used = std::min(mk.used, chunks[cur].cap);
+    }
+    void reset()
+    {
+        cur = 0;
+        if (!chunks.empty()) chunks[0].used = 0;
+    }
+};
+
+struct MirrorArena {
+    struct Chunk {
+        char *pin = nullptr, *dev = nullptr;
+        size_t cap = 0, used = 0, flushed = 0;
+    };
+    std::vector<Chunk> chunks;
+    size_t cur = 0;
+    // host <- where to write, returns the device address the bytes will have after flush()
+    void *alloc_bytes(size_t bytes, void **host)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        for (;;) {
+            if (cur < chunks.size()) {
+                Chunk &c = chunks[cur];
+                if (c.used + bytes <= c.cap) {
+                    *host = c.pin + c.used;
+                    void *p = c.dev + c.used;
+                    c.used += bytes;
+                    return p;
+                }
+                if (cur + 1 < chunks.size()) {
+                    cur++;
+                    chunks[cur].used = chunks[cur].flushed = 0;
+                    continue;
+                }
+            }
+            Chunk c;
+            c.cap = std::max<size_t>(bytes, (size_t)4 << 20);
+            CUDA_CHECK(cudaMallocHost((void **)&c.pin, c.cap));
+            CUDA_CHECK(cudaMalloc((void **)&c.dev, c.cap));
+            chunks.push_back(c);
+            cur = chunks.size() - 1;
+        }
+    }
+    template <class T>
+    T *alloc(size_t count, T **host)
+    {
+        void *h = nullptr;
+        T *d = reinterpret_cast<T *>(alloc_bytes(count * sizeof(T), &h));
+        *host = reinterpret_cast<T *>(h);
+        return d;
+    }
+    void flush(cudaStream_t st)
+    {
+        for (size_t i = 0; i <= cur && i < chunks.size(); i++) {
+            Chunk &c = chunks[i];
+            if (c.used > c.flushed) {
+                CUDA_CHECK(cudaMemcpyAsync(c.dev + c.flushed, c.pin + c.flushed, c.used - c.flushed, cudaMemcpyHostToDevice, st));
+                c.flushed = c.used;
+            }
+        }
+    }
+    void reset()
+    {
+        cur = 0;
+        if (!chunks.empty()) chunks[0].used = chunks[0].flushed = 0;
+    }
+};
+
+// pinned host blocks for deferred read-backs (bump, reset per load())
+struct PinnedArena {
+    struct Chunk {
+        char *pin = nullptr;
+        size_t cap = 0, used = 0;
+    };
+    std::vector<Chunk> chunks;
+    size_t cur = 0;
+    void *alloc_bytes(size_t bytes)
+    {
+        bytes = (bytes + 63) & ~(size_t)63;
+        if (bytes == 0) bytes = 64;
+        for (;;) {
+            if (cur < chunks.size()) {
+                Chunk &c = chunks[cur];
+                if (c.used + bytes <= c.cap) {
+                    void *p = c.pin + c.used;
+                    c.used += bytes;
+                    return p;
+                }
+                if (cur + 1 < chunks.size()) {
+                    cur++;
+                    chunks[cur].used = 0;
+                    continue;
+                }
+            }
+            Chunk c;
+            c.cap = std::max<size_t>(bytes, (size_t)1 << 20);
+            CUDA_CHECK(cudaMallocHost((void **)&c.pin, c.cap));
+            chunks.push_back(c);
+            cur = chunks.size() - 1;
+        }
+    }
+    template <class T>
+    T *alloc(size_t count)
+    {
+        return reinterpret_cast<T *>(alloc_bytes(count * sizeof(T)));
+    }
+    void reset()
+    {
+        cur = 0;
+        if (!chunks.empty()) chunks[0].used = 0;
+    }
+};
+
 // Per-device resources that are expensive to create (stream, pinned mirrors) are cached for the life of the process
 // and lent to one Engine at a time.
 struct DeviceContext {
+    DevArena ar;
+    MirrorArena mir;
+    PinnedArena rb;
+    int coop_launch = -1;  // cudaDevAttrCooperativeLaunch, queried once
     int device = 0;
     int sm_count = 148;
     cudaStream_t st = nullptr;
@@ -131,10 +305,10 @@ void release_context(DeviceContext *c)
 }
 int pick_fs(int nch)
 {
-    const int opts[] = {1, 2, 4, 6, 8, 12, 16};
+    const int opts[] = {1, 2, 4, 6, 8, 12, 16, 24, 32};
     for (int o : opts)
         if (o >= nch) return o;
-    throw EngineError{"too many chains (K must be <= 15)"};
+    throw EngineError{"too many chains (K must be <= 31)"};
 }
 }  // namespace
 
@@ -191,6 +365,7 @@ struct Engine::Impl {
     double *h_bA = nullptr;
     bool chains_ready = false;
     bool x_owned = true;
+    bool tie_exact = false;  // Engine::set_tie_exact
     // column-sharded mode
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -256,28 +431,45 @@ struct Engine::Impl {
         spans.clear();
     }
 
+    // ---- workspace bookkeeping (DeviceContext arenas).  Stack order in the device arena: [load] [sweep buffers]
+    // [phase scratch | chain state].  config_sweep releases everything above the load mark, so it ends the life of the
+    // chain state as well (setup_chains re-creates it right afterwards).
+    DevArena::Mark mk_load{}, mk_sweep_end{};
+    bool have_sweep = false;
+    // read-backs that are only awaited when somebody asks for them
+    int *h_sel = nullptr;          // pinned: kept columns of the last screening
+    int *h_sel_tie = nullptr;
+    int sel_count = 0;
+    bool sel_pending = false;
+    double *h_mean = nullptr, *h_norm = nullptr;  // pinned: column statistics of the last normalisation
+    bool stats_pending = false;
+    bool stats_have_mean = false;
+
     void free_sweep_buffers()
     {
-        Impl &m = *this;
-        dfree(m.st, d.G); dfree(m.st, d.W); dfree(m.st, d.TH); dfree(m.st, d.C2);
-        dfree(m.st, d.part); dfree(m.st, d.c2sum); dfree(m.st, d.bd); dfree(m.st, raw);
+        d.G = d.W = d.TH = d.C2 = nullptr;
+        d.part = d.c2sum = d.bd = nullptr;
+        raw = nullptr;
+        have_sweep = false;
     }
     void free_chain_buffers()
     {
         Impl &m = *this;
-        dfree(m.st, d.rows); dfree(m.st, d.ntrain); dfree(m.st, d.ytr); dfree(m.st, d.wtr); dfree(m.st, d.ks); dfree(m.st, d.A); dfree(m.st, d.bA);
-        dfree(m.st, d.coef0); dfree(m.st, d.coef0_level); dfree(m.st, d.Anew); dfree(m.st, d.hist); dfree(m.st, d.l); dfree(m.st, d.done); dfree(m.st, d.tie);
-        dfree(m.st, d.tie_acc); dfree(m.st, n_active2);
+        // everything of the chain state lives in the arenas and dies with the next config_sweep / load; only the
+        // column-sharded exchange buffers are stream-ordered allocations
+        d.rows = nullptr; d.ntrain = nullptr; d.ytr = d.wtr = nullptr; d.ks = nullptr; d.A = nullptr; d.bA = nullptr;
+        d.coef0 = d.coef0_level = nullptr; d.Anew = nullptr; d.hist = nullptr; d.l = d.done = d.tie = d.tie_acc = nullptr;
+        n_active2 = nullptr;
         d.n_active = nullptr;
-        dfree(m.st, d.betaD); dfree(m.st, d.XA); dfree(m.st, d.XB); dfree(m.st, d.vec); dfree(m.st, d.Smat); dfree(m.st, d.Spart); dfree(m.st, d.cw); dfree(m.st, d.xtx);
-        dfree(m.st, testrows); dfree(m.st, ntest); dfree(m.st, lfact); dfree(m.st, loss_scratch); dfree(m.st, loss_out); dfree(m.st, always);
-        dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
+        d.betaD = d.XA = d.XB = d.vec = d.Smat = d.Spart = d.cw = d.xtx = nullptr;
+        testrows = ntest = nullptr; lfact = loss_scratch = loss_out = nullptr; always = nullptr;
+        ck0 = ck1 = nullptr; ci0 = ci1 = nullptr;
         dfree(m.st, cand_s); dfree(m.st, cand_r); dfree(m.st, mv); dfree(m.st, mi); dfree(m.st, Aloc); dfree(m.st, AXs);
         dfree(m.st, d.AXr); dfree(m.st, d.AXk);
-        dfree(m.st, slots.A); dfree(m.st, slots.bA); dfree(m.st, slots.ks); dfree(m.st, slots.coef0);
-        dfree(m.st, d.Tc); dfree(m.st, d.AnewCols);
-        dfree(m.st, lp_sync); dfree(m.st, lp_cand); dfree(m.st, lp_ncand); dfree(m.st, lp_pub); dfree(m.st, lp_tau);
-        dfree(m.st, lp_res_i); dfree(m.st, lp_res_d); dfree(m.st, lp_dbg); dfree(m.st, lp_R);
+        slots = StateSlots{};
+        d.Tc = nullptr; d.AnewCols = nullptr;
+        lp_sync = nullptr; lp_cand = nullptr; lp_ncand = nullptr; lp_pub = lp_tau = nullptr;
+        lp_res_i = nullptr; lp_res_d = nullptr; lp_dbg = nullptr; lp_R = nullptr;
         lp_ok = false;
         chains_ready = false;
     }
@@ -285,7 +477,9 @@ struct Engine::Impl {
     void config_sweep(int FS)
     {
         Impl &m = *this;
+        free_chain_buffers();
         free_sweep_buffers();
+        ctx->ar.release(mk_load);
         d.gate = nullptr;
         d.X = X; d.ldx = ldx; d.n = n; d.p = p; d.FS = FS;
         d.pstride = (p + 1) & ~1LL;
@@ -321,22 +515,40 @@ struct Engine::Impl {
         rps = (rps + 1) & ~1;
         d.rows_per_split = rps;
         d.S = (n + rps - 1) / rps;
-        const size_t vsz = (size_t)npad * FS;
-        d.G = dalloc<double>(m.st, vsz); d.W = dalloc<double>(m.st, vsz); d.TH = dalloc<double>(m.st, vsz); d.C2 = dalloc<double>(m.st, vsz);
-        CUDA_CHECK(cudaMemsetAsync(d.G, 0, vsz * 8, st));
-        CUDA_CHECK(cudaMemsetAsync(d.W, 0, vsz * 8, st));
-        CUDA_CHECK(cudaMemsetAsync(d.TH, 0, vsz * 8, st));
-        CUDA_CHECK(cudaMemsetAsync(d.C2, 0, vsz * 8, st));
-        d.part = dalloc<double>(m.st, (size_t)d.S * 5 * FS * d.pstride);
-        d.c2sum = dalloc<double>(m.st, (size_t)d.S * FS);
-        d.bd = dalloc<double>(m.st, (size_t)FS * d.pstride);
-        raw = dalloc<double>(m.st, (size_t)2 * FS * d.pstride);
+        const size_t vsz = ((size_t)npad * FS + 31) & ~(size_t)31;  // keeps the four vectors 256-byte aligned
+        double *vecs = ctx->ar.alloc<double>(4 * vsz);  // one block, one memset
+        d.G = vecs; d.W = vecs + vsz; d.TH = vecs + 2 * vsz; d.C2 = vecs + 3 * vsz;
+        CUDA_CHECK(cudaMemsetAsync(vecs, 0, 4 * vsz * 8, st));
+        d.part = ctx->ar.alloc<double>((size_t)d.S * 5 * FS * d.pstride);
+        d.c2sum = ctx->ar.alloc<double>((size_t)d.S * FS);
+        d.bd = ctx->ar.alloc<double>((size_t)FS * d.pstride);
+        raw = ctx->ar.alloc<double>((size_t)2 * FS * d.pstride);
+        mk_sweep_end = ctx->ar.mark();
+        have_sweep = true;
     }
-    // upload a host vector into slot f of a [npad][FS] sweep vector
-    void put_vec(double *dst, int f, const std::vector<double> &v)
+    // Stage a host vector for the device: the returned device pointer is valid after the next mirror flush.
+    // pad: number of doubles of the device block (>= v.size(), the tail is zero)
+    double *stage_vec(const double *v, size_t count, size_t pad)
     {
-        CUDA_CHECK(cudaMemcpy2DAsync(dst + f, (size_t)d.FS * 8, v.data(), 8, 8, v.size(), cudaMemcpyHostToDevice, st));
+        double *h = nullptr;
+        double *dv = ctx->mir.alloc<double>(pad, &h);
+        std::memcpy(h, v, count * 8);
+        if (pad > count) std::memset(h + count, 0, (pad - count) * 8);
+        return dv;
     }
+    // slot f of a [npad][FS] sweep vector <- host vector (FS == 1: the staged block itself becomes the vector)
+    void put_vec(double *&dst, int f, const std::vector<double> &v)
+    {
+        if (d.FS == 1 && f == 0) {
+            dst = stage_vec(v.data(), v.size(), (size_t)npad);
+            ctx->mir.flush(st);
+            return;
+        }
+        double *sv = stage_vec(v.data(), v.size(), v.size());
+        ctx->mir.flush(st);
+        CUDA_CHECK(cudaMemcpy2DAsync(dst + f, (size_t)d.FS * 8, sv, 8, 8, v.size(), cudaMemcpyDeviceToDevice, st));
+    }
+    void await_stream() { CUDA_CHECK(cudaStreamSynchronize(st)); }
 };
 
 Engine::Engine(int device)
@@ -376,14 +588,31 @@ Engine::~Engine()
     m.free_chain_buffers();
     m.free_sweep_buffers();
     if (m.x_owned) dfree(m.st, m.X);
-    dfree(m.st, m.y); dfree(m.st, m.w);
     dfree(m.st, m.gidx); dfree(m.st, m.gsz);
     cudaStreamSynchronize(m.st);
+    m.ctx->ar.reset();
+    m.ctx->mir.reset();
+    m.ctx->rb.reset();
     release_context(m.ctx);
     delete d_;
 }
 
 void Engine::set_profiling(bool on) { d_->prof = on; }
+void Engine::set_tie_exact(bool on) { d_->tie_exact = on; }
+bool Engine::tie_exact() const { return d_->tie_exact; }
+
+// max_k of the reference, statement for statement (utilities.cpp:179-188): an index array 0..N-1, std::nth_element with
+// the comparator vec(i) > vec(j), std::sort of the first k.  Which of several equal values at the boundary survive is
+// whatever libstdc++'s introselect leaves in front -- reproduced by running the same algorithm on the same ordering.
+static void host_max_k(const double *vec, int N, int k, int *out)
+{
+    std::vector<int> ind((size_t)N);
+    std::iota(ind.begin(), ind.end(), 0);
+    auto rule = [vec](int i, int j) -> bool { return vec[i] > vec[j]; };
+    std::nth_element(ind.data(), ind.data() + k, ind.data() + ind.size(), rule);
+    std::sort(ind.data(), ind.data() + k);
+    std::copy(ind.data(), ind.data() + k, out);
+}
 
 bool Engine::has_comm() const { return d_->comm != nullptr && d_->world > 1; }
 
@@ -464,7 +693,12 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     m.free_chain_buffers();
     m.free_sweep_buffers();
     if (m.x_owned) dfree(m.st, m.X);
-    dfree(m.st, m.y); dfree(m.st, m.w);
+    // a new problem: every arena block of the previous one is dead once the stream has drained
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    m.ctx->ar.reset();
+    m.ctx->mir.reset();
+    m.ctx->rb.reset();
+    m.sel_pending = m.stats_pending = false;
     n_ = n; p_ = p; family_ = family;
     m.n = n; m.p = p; m.npad = (n + 1) & ~1;
     m.ldx = (p + 1) & ~1LL;
@@ -484,44 +718,62 @@ void Engine::load(const double *x, int n, int p, bool x_on_device, const double 
     }
     m.hy.assign(y, y + n);
     m.hw.assign(weight, weight + n);
-    m.y = dalloc<double>(m.st, m.npad);
-    m.w = dalloc<double>(m.st, m.npad);
-    CUDA_CHECK(cudaMemsetAsync(m.y, 0, m.npad * 8, m.st));
-    CUDA_CHECK(cudaMemsetAsync(m.w, 0, m.npad * 8, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(m.y, y, n * 8, cudaMemcpyHostToDevice, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(m.w, weight, n * 8, cudaMemcpyHostToDevice, m.st));
+    m.y = m.stage_vec(y, (size_t)n, (size_t)m.npad);
+    m.w = m.stage_vec(weight, (size_t)n, (size_t)m.npad);
+    m.ctx->mir.flush(m.st);
+    m.mk_load = m.ctx->ar.mark();
     m.d = Dev{};
     m.d.family = family;
     m.d.sharded = sharded_ ? 1 : 0;
     m.d.col_lo = sharded_ ? (int)col_lo_ : 0;
-    h_xmean_.assign(p, 0.0);
-    h_xnorm_.assign(p, 0.0);
+    // (the column statistics are p-sized host vectors: at p = 500000 zero-filling them costs more than the whole path of
+    // a screened call, so they are only materialised when somebody reads them -- ensure_stats)
+    h_xmean_.clear();
+    h_xnorm_.clear();
     y_mean_ = 0.0;
-    CUDA_CHECK(cudaStreamSynchronize(m.st));
 }
 
-// screening.cpp:26-61: marginal utility of every column on RAW x -> m.d.bd (device), always_select pinned.
-// Selects the top `size` (ascending indices) into d_sel; if vals_out != nullptr also returns their utilities.
-static void screen_select(Engine::Impl &m, EngineStats &st, int family, int size, const std::vector<int> &always_select,
-                          int *d_sel, std::vector<double> *vals_out, std::vector<int> *sel_out);
+static int *screen_select(Engine::Impl &m, EngineStats &st, int family, int size, const std::vector<int> &always_select,
+                          std::vector<double> *vals_out, std::vector<int> *sel_out, bool to_pinned);
 
 std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
 {
+    screen_enqueue(size, always_select);
+    return screen_result();
+}
+
+// The kept columns of the last screen_enqueue(), ascending (waits for the device only here).
+std::vector<int> Engine::screen_result()
+{
+    Impl &m = *d_;
+    if (!m.h_sel) throw EngineError{"screen_result: no screening has run"};
+    if (m.sel_pending) {
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        m.sel_pending = false;
+        stats_.n_boundary_ties += *m.h_sel_tie;
+    }
+    return std::vector<int>(m.h_sel, m.h_sel + m.sel_count);
+}
+
+void Engine::screen_enqueue(int size, const std::vector<int> &always_select)
+{
     Impl &m = *d_;
     if (size < 1 || size > p_model()) throw EngineError{"screening_size must be in [1, p]"};
-    std::vector<int> sel;
     const long long ldn = (size + 1) & ~1LL;
     double *Xn = dalloc<double>(m.st, (size_t)m.n * ldn);
     if (ldn != size) CUDA_CHECK(cudaMemsetAsync(Xn, 0, (size_t)m.n * ldn * 8, m.st));
+    m.h_sel = m.ctx->rb.alloc<int>((size_t)size);
+    m.h_sel_tie = m.ctx->rb.alloc<int>(1);
+    *m.h_sel_tie = 0;
+    m.sel_count = size;
     if (!sharded_) {
-        int *d_sel = dalloc<int>(m.st, size);
-        screen_select(m, stats_, family_, size, always_select, d_sel, nullptr, &sel);
+        const int *d_sel = screen_select(m, stats_, family_, size, always_select, nullptr, nullptr, /*to_pinned=*/true);
         // X <- X[:, sel]  (screening.cpp:83-88)
         const int spk = m.span_begin(5);
         launch_gather_cols(m.X, m.ldx, m.n, d_sel, size, Xn, ldn, m.st);
         m.span_end(spk);
         stats_.kernel_launches += 1;
-        dfree(m.st, d_sel);
+        m.sel_pending = true;  // the index list and the tie flag are on their way to the pinned block
     } else {
         // Column-sharded screening (SURVEY 8e axis B): marginal utilities of the local columns, exact local top-`size`,
         // NCCL all-gather of the (utility, global index) candidates, identical merge on every rank, then every rank
@@ -532,8 +784,7 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
         std::vector<int> alw_local;
         for (int j : always_select)
             if (j >= col_lo_ && j < col_lo_ + m.p) alw_local.push_back((int)(j - col_lo_));
-        int *d_sel = dalloc<int>(m.st, size);
-        screen_select(m, stats_, family_, kloc, alw_local, d_sel, nullptr, nullptr);
+        const int *d_sel = screen_select(m, stats_, family_, kloc, alw_local, nullptr, nullptr, /*to_pinned=*/false);
         Cand *cs = dalloc<Cand>(m.st, size), *cr = dalloc<Cand>(m.st, (size_t)m.world * size);
         const long long n_in = (long long)m.world * size;
         double *mv = dalloc<double>(m.st, n_in);
@@ -549,22 +800,17 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
         launch_gather_owned_cols(m.X, m.ldx, m.n, m.p, col_lo_, d_gsel, size, Xn, ldn, m.st);
         NCCL_CHECK(api.AllReduce(Xn, Xn, (size_t)m.n * ldn, ncclDouble, ncclSum, m.comm, m.st));
         m.span_end(spx);
-        sel.resize(size);
-        int tie = 0;
-        CUDA_CHECK(cudaMemcpyAsync(sel.data(), d_gsel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));
-        stats_.n_boundary_ties += tie;
+        CUDA_CHECK(cudaMemcpyAsync(m.h_sel, d_gsel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_sel_tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
+        m.sel_pending = true;
         stats_.kernel_launches += 4;
-        dfree(m.st, d_sel); dfree(m.st, cs); dfree(m.st, cr); dfree(m.st, mv); dfree(m.st, mi); dfree(m.st, d_gsel);
+        dfree(m.st, cs); dfree(m.st, cr); dfree(m.st, mv); dfree(m.st, mi); dfree(m.st, d_gsel);
         dfree(m.st, d_tie); dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1);
         // from here on every rank holds the whole (screened) design: the path runs replicated
         sharded_ = false;
         col_lo_ = 0;
     }
-    CUDA_CHECK(cudaStreamSynchronize(m.st));
-    m.collect_spans();
-    if (m.x_owned) dfree(m.st, m.X);
+    if (m.x_owned) dfree(m.st, m.X);  // stream-ordered: the gather above has the old design until it is done
     m.x_owned = true;
     m.X = Xn;
     m.ldx = ldn;
@@ -573,9 +819,8 @@ std::vector<int> Engine::screen(int size, const std::vector<int> &always_select)
     m.free_sweep_buffers();
     m.d.sharded = 0;
     m.d.col_lo = 0;
-    h_xmean_.assign(size, 0.0);
-    h_xnorm_.assign(size, 0.0);
-    return sel;
+    h_xmean_.clear();
+    h_xnorm_.clear();
 }
 
 // Column-sharded screening (SURVEY 8e axis B): the local top-`size` candidates (utility, local column index) of this
@@ -585,9 +830,7 @@ void Engine::screen_local(int size, const std::vector<int> &always_select, std::
 {
     Impl &m = *d_;
     size = std::min(size, m.p);
-    int *d_sel = dalloc<int>(m.st, size);
-    screen_select(m, stats_, family_, size, always_select, d_sel, &vals, &idx);
-    dfree(m.st, d_sel);
+    screen_select(m, stats_, family_, size, always_select, &vals, &idx, /*to_pinned=*/false);
     m.free_sweep_buffers();
 }
 
@@ -606,11 +849,16 @@ void Engine::gather_columns(const int *cols, const int *pos, int mcols, double *
     dfree(m.st, d_pos);
 }
 
-static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int size,
-                          const std::vector<int> &always_select, int *d_sel, std::vector<double> *vals_out,
-                          std::vector<int> *sel_out)
+// Marginal utilities (screening.cpp:26-61) on RAW x -> m.d.bd, always_select pinned, exact top-`size` (ascending) into a
+// device list that is returned (arena memory, alive until the next config_sweep).  Host copies:
+//   sel_out / vals_out   synchronous (screen_local);
+//   to_pinned            the list and the boundary-tie flag go to m.h_sel / m.h_sel_tie asynchronously.
+static int *screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int size,
+                          const std::vector<int> &always_select, std::vector<double> *vals_out,
+                          std::vector<int> *sel_out, bool to_pinned)
 {
     m.config_sweep(1);
+    DevArena &ar = m.ctx->ar;
     BatchDesc b{};
     b.nch = 1;
     b.chain[0] = 0;
@@ -635,37 +883,56 @@ static void screen_select(Engine::Impl &m, EngineStats &stats_, int family_, int
         stats_.big_sweep_bytes += 8.0 * m.n * m.p;  // algorithmic: one pass (the marginal fits re-read the column from L2)
         stats_.kernel_launches += 1;
     }
-    int *d_alw = nullptr;
     if (!always_select.empty()) {
-        d_alw = dalloc<int>(m.st, always_select.size());
-        CUDA_CHECK(cudaMemcpyAsync(d_alw, always_select.data(), always_select.size() * 4, cudaMemcpyHostToDevice, m.st));
+        int *h_alw = nullptr;
+        int *d_alw = m.ctx->mir.alloc<int>(always_select.size(), &h_alw);
+        std::copy(always_select.begin(), always_select.end(), h_alw);
+        m.ctx->mir.flush(m.st);
         launch_pin(m.d, m.d.bd, m.d.pstride, 1, d_alw, (int)always_select.size(), m.st);
     }
+    int *d_sel = ar.alloc<int>((size_t)size);
     const long long cstride = std::max<long long>(2LL * size + 16, ((long long)m.p / 8192 + 2) * std::min(size, TOPK_LMAX));
-    double *ck0 = dalloc<double>(m.st, cstride), *ck1 = dalloc<double>(m.st, cstride);
-    int *ci0 = dalloc<int>(m.st, cstride), *ci1 = dalloc<int>(m.st, cstride);
-    int *d_tie = dalloc<int>(m.st, 1);
+    double *ck0 = ar.alloc<double>((size_t)cstride), *ck1 = ar.alloc<double>((size_t)cstride);
+    int *ci0 = ar.alloc<int>((size_t)cstride), *ci1 = ar.alloc<int>((size_t)cstride);
+    int *d_tie = ar.alloc<int>(1);
     const int spk = m.span_begin(3);
     launch_topk(m.d.bd, m.d.pstride, m.p, size, 1, d_sel, size, d_tie, ck0, ci0, ck1, ci1, cstride, m.st);
     m.span_end(spk);
-    int tie = 0;
+    stats_.kernel_launches += 2;
+    if (m.tie_exact && !m.d.sharded) {
+        int tie = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        if (tie) {  // the reference's own resolution of the tie (max_k on the utilities, screening.cpp:66)
+            std::vector<double> all((size_t)m.p);
+            std::vector<int> hs((size_t)size);
+            CUDA_CHECK(cudaMemcpyAsync(all.data(), m.d.bd, (size_t)m.p * 8, cudaMemcpyDeviceToHost, m.st));
+            CUDA_CHECK(cudaStreamSynchronize(m.st));
+            host_max_k(all.data(), m.p, size, hs.data());
+            CUDA_CHECK(cudaMemcpyAsync(d_sel, hs.data(), (size_t)size * 4, cudaMemcpyHostToDevice, m.st));
+            CUDA_CHECK(cudaStreamSynchronize(m.st));
+        }
+    }
+    if (to_pinned) {
+        CUDA_CHECK(cudaMemcpyAsync(m.h_sel, d_sel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_sel_tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));
+    }
     if (sel_out) {
+        int tie = 0;
         sel_out->resize(size);
         CUDA_CHECK(cudaMemcpyAsync(sel_out->data(), d_sel, (size_t)size * 4, cudaMemcpyDeviceToHost, m.st));
         CUDA_CHECK(cudaMemcpyAsync(&tie, d_tie, 4, cudaMemcpyDeviceToHost, m.st));  // a LOCAL boundary tie only matters
-    }                                                                               // when the local list is the result
-    CUDA_CHECK(cudaStreamSynchronize(m.st));
-    if (vals_out) {
-        std::vector<double> all((size_t)m.p);
-        CUDA_CHECK(cudaMemcpyAsync(all.data(), m.d.bd, (size_t)m.p * 8, cudaMemcpyDeviceToHost, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));
-        vals_out->resize(size);
-        for (int q = 0; q < size; q++) (*vals_out)[q] = all[(size_t)(*sel_out)[q]];
+        CUDA_CHECK(cudaStreamSynchronize(m.st));                                    // when the local list is the result
+        stats_.n_boundary_ties += tie;
+        if (vals_out) {
+            std::vector<double> all((size_t)m.p);
+            CUDA_CHECK(cudaMemcpyAsync(all.data(), m.d.bd, (size_t)m.p * 8, cudaMemcpyDeviceToHost, m.st));
+            CUDA_CHECK(cudaStreamSynchronize(m.st));
+            vals_out->resize(size);
+            for (int q = 0; q < size; q++) (*vals_out)[q] = all[(size_t)(*sel_out)[q]];
+        }
     }
-    m.collect_spans();
-    stats_.n_boundary_ties += tie;
-    stats_.kernel_launches += 2;
-    dfree(m.st, ck0); dfree(m.st, ck1); dfree(m.st, ci0); dfree(m.st, ci1); dfree(m.st, d_tie); dfree(m.st, d_alw);
+    return d_sel;
 }
 
 // Data ctor (Data.h:41-68) + normalize.cpp + add_weight (Data.h:70-77, bess.cpp:97)
@@ -680,12 +947,19 @@ void Engine::normalize(int data_type, bool is_normal)
         m.x_owned = true;
     }
     m.config_sweep(1);
+    DevArena &ar = m.ctx->ar;
     BatchDesc b{};
     b.nch = 1;
     b.chain[0] = 0;
-    double *d_mean = nullptr, *d_mul = nullptr, *d_rowmul = nullptr;
+    double *d_mul = nullptr, *d_rowmul = nullptr;
+    m.stats_have_mean = false;
+    m.stats_pending = false;
     const int sp_all = m.span_begin(6);
+    // No host round trip in here: the column statistics stay on the device (the scale factors are derived there) and
+    // travel to pinned memory for the de-normalisation at the end of the call (ensure_stats).
     if (is_normal) {
+        m.h_mean = m.ctx->rb.alloc<double>((size_t)p);
+        m.h_norm = m.ctx->rb.alloc<double>((size_t)p);
         if (data_type == 1 || data_type == 2) {
             // meanx_j = w.x_j / n  (normalize.cpp:25-28, 52-55)
             std::vector<double> g(n);
@@ -693,10 +967,11 @@ void Engine::normalize(int data_type, bool is_normal)
             m.put_vec(m.d.G, 0, g);
             launch_dual_sweep(m.d, MODE_D, m.st);
             launch_finish(m.d, MODE_D, EPI_RAW, b, m.raw, m.st);
-            d_mean = dalloc<double>(m.st, m.d.pstride);
+            double *d_mean = ar.alloc<double>((size_t)m.d.pstride);
             CUDA_CHECK(cudaMemcpyAsync(d_mean, m.raw, (size_t)p * 8, cudaMemcpyDeviceToDevice, m.st));
-            CUDA_CHECK(cudaMemcpyAsync(h_xmean_.data(), m.raw, (size_t)p * 8, cudaMemcpyDeviceToHost, m.st));
+            CUDA_CHECK(cudaMemcpyAsync(m.h_mean, m.raw, (size_t)p * 8, cudaMemcpyDeviceToHost, m.st));
             launch_center_scale(m.X, m.ldx, n, p, d_mean, nullptr, nullptr, m.st);
+            m.stats_have_mean = true;
             stats_.kernel_launches += 3;
         }
         if (data_type == 1) {
@@ -711,19 +986,13 @@ void Engine::normalize(int data_type, bool is_normal)
         m.put_vec(m.d.W, 0, m.hw);
         launch_dual_sweep(m.d, MODE_DH, m.st);
         launch_finish(m.d, MODE_DH, EPI_RAW, b, m.raw, m.st);
-        std::vector<double> h(p);
-        CUDA_CHECK(cudaMemcpyAsync(h.data(), m.raw + (size_t)m.d.FS * m.d.pstride, (size_t)p * 8, cudaMemcpyDeviceToHost,
-                                   m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));
-        std::vector<double> mul(p);
-        const double sn = std::sqrt((double)n);
-        for (int j = 0; j < p; j++) {
-            h_xnorm_[j] = std::sqrt(h[j]);
-            mul[j] = sn / h_xnorm_[j];  // normalize.cpp:42-45
-        }
-        d_mul = dalloc<double>(m.st, m.d.pstride);
-        CUDA_CHECK(cudaMemcpyAsync(d_mul, mul.data(), (size_t)p * 8, cudaMemcpyHostToDevice, m.st));
-        stats_.kernel_launches += 2;
+        // x_j <- sqrt(n) * x_j / normx_j  (normalize.cpp:42-45): norms and factors from the sums, on the device
+        d_mul = ar.alloc<double>((size_t)m.d.pstride);
+        double *d_norm = ar.alloc<double>((size_t)m.d.pstride);
+        launch_norm_factors(m.raw + (size_t)m.d.FS * m.d.pstride, p, std::sqrt((double)n), d_norm, d_mul, m.st);
+        CUDA_CHECK(cudaMemcpyAsync(m.h_norm, d_norm, (size_t)p * 8, cudaMemcpyDeviceToHost, m.st));
+        m.stats_pending = true;
+        stats_.kernel_launches += 3;
         stats_.n_sweeps += 2;
     }
     if (family_ == FAM_LM) {
@@ -733,25 +1002,23 @@ void Engine::normalize(int data_type, bool is_normal)
             rm[i] = std::sqrt(m.hw[i]);
             m.hy[i] *= rm[i];
         }
-        d_rowmul = dalloc<double>(m.st, n);
-        CUDA_CHECK(cudaMemcpyAsync(d_rowmul, rm.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
+        d_rowmul = m.stage_vec(rm.data(), (size_t)n, (size_t)n);
     }
+    m.y = m.stage_vec(m.hy.data(), (size_t)n, (size_t)m.npad);  // the response as the fits see it
+    m.ctx->mir.flush(m.st);
     if (d_mul || d_rowmul) {
         launch_center_scale(m.X, m.ldx, n, p, nullptr, d_mul, d_rowmul, m.st);
         stats_.kernel_launches += 1;
     }
     m.span_end(sp_all);
-    CUDA_CHECK(cudaMemcpyAsync(m.y, m.hy.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
-    CUDA_CHECK(cudaStreamSynchronize(m.st));
-    m.collect_spans();
     // passes over X: [mean sweep 8np + centre 16np] (data_type 1,2) + norm sweep 8np + scale 16np
     if (is_normal) stats_.norm_bytes += (data_type == 3 ? 24.0 : 48.0) * n * p;
     else if (family_ == FAM_LM) stats_.norm_bytes += 16.0 * n * p;
-    dfree(m.st, d_mean); dfree(m.st, d_mul); dfree(m.st, d_rowmul);
     m.free_sweep_buffers();
     if (sharded_) {
         // column statistics are shard-local; de-normalisation (path.cpp:76-110) needs those of the selected columns,
         // whoever owns them: all-gather both vectors once (2 * p_total doubles)
+        ensure_stats();
         const NcclApi &api = nccl_api();
         long long lo0, hi0;
         shard_range(p_total_, world_, 0, &lo0, &hi0);
@@ -775,6 +1042,22 @@ void Engine::normalize(int data_type, bool is_normal)
             std::copy(blk + pmax, blk + pmax + (hi - lo), g_xnorm_.begin() + lo);
         }
     }
+}
+
+// The column statistics of the last normalize() on the host (h_xmean_, h_xnorm_): waits for the device only here.
+void Engine::ensure_stats() const
+{
+    Impl &m = *d_;
+    Engine *self = const_cast<Engine *>(this);
+    if ((int)h_xmean_.size() != m.p) {
+        self->h_xmean_.assign((size_t)m.p, 0.0);
+        self->h_xnorm_.assign((size_t)m.p, 0.0);
+    }
+    if (!m.stats_pending) return;
+    CUDA_CHECK(cudaStreamSynchronize(m.st));
+    if (m.stats_have_mean) std::copy(m.h_mean, m.h_mean + m.p, self->h_xmean_.begin());
+    std::copy(m.h_norm, m.h_norm + m.p, self->h_xnorm_.begin());
+    m.stats_pending = false;
 }
 
 void Engine::set_groups(const std::vector<int> &g_index)
@@ -807,8 +1090,8 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
 {
     Impl &m = *d_;
     const int n = m.n, p = m.p;
-    if (K < 0 || K > MAXC - 1) throw EngineError{"K (nfolds) must be in [0, 15]"};
-    if (max_iter < 1 || max_iter > MAX_HIST - 2) throw EngineError{"max_iter must be in [1, 64]"};
+    if (K < 0 || K > MAXC - 1) throw EngineError{"K (nfolds) must be in [0, 31]"};
+    if (max_iter < 1 || max_iter > MAX_ITER_CAP) throw EngineError{"max_iter must be in [1, 100000]"};
     const bool grp = grouped();
     if (kcap < 1 || kcap > (grp ? n_groups_ : p_model())) throw EngineError{"support size must be in [1, p]"};
     m.Tmax = kcap;
@@ -827,115 +1110,187 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     m.nchains = 1 + K;
     const int C = m.nchains;
     m.config_sweep(pick_fs(C));
+    DevArena &ar = m.ctx->ar;
+    MirrorArena &mir = m.ctx->mir;
     Dev &d = m.d;
     d.kcap = kcap;
     d.ldA = (kcap + 2 + 1) & ~1;
     d.fit_smem_doubles = fit_smem_doubles(d.ldA, kcap);
     d.max_iter = max_iter;
     d.warm = warm_start ? 1 : 0;
-
-    // ---- row lists (Metric.h:80-103: train masks are the sorted complement of each fold)
-    std::vector<int> rows((size_t)MAXC * n, 0), ntrain(MAXC, 0), testrows((size_t)MAXC * n, 0), ntest(MAXC, 0);
-    for (int i = 0; i < n; i++) rows[i] = i;
-    ntrain[0] = n;
-    for (int k = 0; k < K; k++) {
-        int a = 0, t = 0;
-        for (int i = 0; i < n; i++) {
-            if (fold_of_row[i] < 0 || fold_of_row[i] >= K) throw EngineError{"fold_of_row out of range"};
-            if (fold_of_row[i] == k) testrows[(size_t)k * n + t++] = i;
-            else rows[(size_t)(1 + k) * n + a++] = i;
-        }
-        ntrain[1 + k] = a;
-        ntest[k] = t;
-        if (a < 2) throw EngineError{"a CV fold leaves fewer than 2 training rows"};
-    }
-    std::vector<double> ytr((size_t)MAXC * n, 0.0), wtr((size_t)MAXC * n, 0.0);
-    for (int c = 0; c < C; c++)
-        for (int r = 0; r < ntrain[c]; r++) {
-            ytr[(size_t)c * n + r] = m.hy[rows[(size_t)c * n + r]];
-            wtr[(size_t)c * n + r] = m.hw[rows[(size_t)c * n + r]];
-        }
-    d.rows = dalloc<int>(m.st, (size_t)MAXC * n);
-    d.ntrain = dalloc<int>(m.st, MAXC);
-    d.ytr = dalloc<double>(m.st, (size_t)MAXC * n);
-    d.wtr = dalloc<double>(m.st, (size_t)MAXC * n);
-    m.testrows = dalloc<int>(m.st, (size_t)MAXC * n);
-    m.ntest = dalloc<int>(m.st, MAXC);
-    CUDA_CHECK(cudaMemcpyAsync(d.rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(d.ntrain, ntrain.data(), MAXC * 4, cudaMemcpyHostToDevice, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(d.ytr, ytr.data(), ytr.size() * 8, cudaMemcpyHostToDevice, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(d.wtr, wtr.data(), wtr.size() * 8, cudaMemcpyHostToDevice, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(m.testrows, testrows.data(), testrows.size() * 4, cudaMemcpyHostToDevice, m.st));
-    CUDA_CHECK(cudaMemcpyAsync(m.ntest, ntest.data(), MAXC * 4, cudaMemcpyHostToDevice, m.st));
-
-    // ---- chain tables
-    d.ks = dalloc<int>(m.st, MAXC);
-    d.A = dalloc<int>(m.st, (size_t)MAXC * kcap);
-    d.bA = dalloc<double>(m.st, (size_t)MAXC * kcap);
-    d.coef0 = dalloc<double>(m.st, MAXC);
-    d.coef0_level = dalloc<double>(m.st, 1);
-    d.Anew = dalloc<int>(m.st, (size_t)MAXC * kcap);
-    d.hist = dalloc<int>(m.st, (size_t)MAXC * MAX_HIST * kcap);
-    d.l = dalloc<int>(m.st, MAXC);
-    d.done = dalloc<int>(m.st, MAXC);
-    d.tie = dalloc<int>(m.st, MAXC);
-    d.tie_acc = dalloc<int>(m.st, MAXC);
-    m.n_active2 = dalloc<int>(m.st, 2);
-    d.n_active = m.n_active2;
-    d.prev_active = nullptr;
-    d.betaD = dalloc<double>(m.st, (size_t)C * d.pstride);
-    d.XA = dalloc<double>(m.st, (size_t)C * n * d.ldA);
-    d.XB = family_ == FAM_COX ? dalloc<double>(m.st, (size_t)C * n * d.ldA) : nullptr;
-    d.vec = dalloc<double>(m.st, (size_t)C * NVEC * n);
-    d.Smat = dalloc<double>(m.st, (size_t)C * 2 * d.ldA * d.ldA);
-    d.cw = dalloc<double>(m.st, (size_t)C * CLMAX * 4 * d.ldA);
+    d.sharded = sharded_ ? 1 : 0;
+    d.col_lo = sharded_ ? (int)col_lo_ : 0;
     d.nmat = family_ == FAM_COX ? 2 : 1;
-    d.CLcap = CLMAX;
-    d.CLcap = chain_cluster_size(d, kcap, 1);  // the largest cluster any batch of this problem can ask for
-    d.Spart = d.CLcap > 1 ? dalloc<double>(m.st, (size_t)C * d.CLcap * d.nmat * d.ldA * d.ldA) : nullptr;
     d.grouped = grp ? 1 : 0;
     d.N = n_groups_;
     d.gidx = m.gidx;
     d.gsz = m.gsz;
-    if (grp) {
-        d.Tc = dalloc<int>(m.st, MAXC);
-        d.AnewCols = dalloc<int>(m.st, (size_t)MAXC * kcap);
-        CUDA_CHECK(cudaMemsetAsync(d.Tc, 0, MAXC * 4, m.st));
-        CUDA_CHECK(cudaMemsetAsync(d.AnewCols, 0, (size_t)MAXC * kcap * 4, m.st));
-    }
-    m.slots.A = dalloc<int>(m.st, (size_t)NSLOT * kcap);
-    m.slots.bA = dalloc<double>(m.st, (size_t)NSLOT * kcap);
-    m.slots.ks = dalloc<int>(m.st, NSLOT);
-    m.slots.coef0 = dalloc<double>(m.st, NSLOT);
-    CUDA_CHECK(cudaMemsetAsync(m.slots.ks, 0, NSLOT * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(m.slots.coef0, 0, NSLOT * 8, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.ks, 0, MAXC * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.A, 0, (size_t)MAXC * kcap * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.bA, 0, (size_t)MAXC * kcap * 8, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.coef0, 0, MAXC * 8, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.coef0_level, 0, 8, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.l, 0, MAXC * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.done, 0, MAXC * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.tie, 0, MAXC * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.tie_acc, 0, MAXC * 4, m.st));
-    CUDA_CHECK(cudaMemsetAsync(m.n_active2, 0, 8, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.betaD, 0, (size_t)C * d.pstride * 8, m.st));
-    CUDA_CHECK(cudaMemsetAsync(d.XA, 0, (size_t)C * n * d.ldA * 8, m.st));
 
-    // ---- x_j.x_j over each chain's train rows (utilities.cpp:153-165, Metric.h:108-129); gaussian only
+    // ---- host tables, written straight into the pinned half of the mirror arena: ONE copy moves them all.
+    // Row lists (Metric.h:80-103: train masks are the sorted complement of each fold), compacted response / weights.
+    int *h_rows, *h_ntrain, *h_testrows, *h_ntest;
+    double *h_ytr, *h_wtr, *h_lfact;
+    d.rows = mir.alloc<int>((size_t)MAXC * n, &h_rows);
+    d.ntrain = mir.alloc<int>(MAXC, &h_ntrain);
+    m.testrows = mir.alloc<int>((size_t)MAXC * n, &h_testrows);
+    m.ntest = mir.alloc<int>(MAXC, &h_ntest);
+    d.ytr = mir.alloc<double>((size_t)MAXC * n, &h_ytr);
+    d.wtr = mir.alloc<double>((size_t)MAXC * n, &h_wtr);
+    m.lfact = mir.alloc<double>((size_t)n, &h_lfact);
+    std::memset(h_ntrain, 0, MAXC * sizeof(int));
+    std::memset(h_ntest, 0, MAXC * sizeof(int));
+    for (int i = 0; i < n; i++) h_rows[i] = i;
+    h_ntrain[0] = n;
+    for (int k = 0; k < K; k++) {
+        int a = 0, t = 0;
+        for (int i = 0; i < n; i++) {
+            if (fold_of_row[i] < 0 || fold_of_row[i] >= K) throw EngineError{"fold_of_row out of range"};
+            if (fold_of_row[i] == k) h_testrows[(size_t)k * n + t++] = i;
+            else h_rows[(size_t)(1 + k) * n + a++] = i;
+        }
+        h_ntrain[1 + k] = a;
+        h_ntest[k] = t;
+        if (a < 2) throw EngineError{"a CV fold leaves fewer than 2 training rows"};
+    }
+    for (int c = 0; c < C; c++)
+        for (int r = 0; r < h_ntrain[c]; r++) {
+            h_ytr[(size_t)c * n + r] = m.hy[h_rows[(size_t)c * n + r]];
+            h_wtr[(size_t)c * n + r] = m.hw[h_rows[(size_t)c * n + r]];
+        }
+    // poisson: sum_{j<=y} log j (poisson.cpp:29-44), same summation order as the reference
+    std::memset(h_lfact, 0, (size_t)n * 8);
+    if (family_ == FAM_POISSON) {
+        double ymax = 0.0;
+        for (int i = 0; i < n; i++) ymax = std::max(ymax, m.hy[i]);
+        if (ymax <= 5.0e7) {
+            std::vector<double> cum((size_t)ymax + 2, 0.0);
+            for (size_t j = 1; j < cum.size(); j++) cum[j] = cum[j - 1] + std::log((double)j);
+            for (int i = 0; i < n; i++) {
+                const double yi = m.hy[i];
+                h_lfact[i] = (yi == 1.0 || yi < 1.0) ? 0.0 : cum[(size_t)std::floor(yi)];
+            }
+        } else {
+            for (int i = 0; i < n; i++) h_lfact[i] = m.hy[i] < 1.0 ? 0.0 : std::lgamma(std::floor(m.hy[i]) + 1.0);
+        }
+    }
+    std::vector<int> alw_local;  // pins are applied to the local sacrifice vector
+    for (int j : always_select)
+        if (!sharded_) alw_local.push_back(j);
+        else if (j >= col_lo_ && j < col_lo_ + p) alw_local.push_back((int)(j - col_lo_));
+    m.n_always = (int)alw_local.size();
+    if (m.n_always) {
+        int *h_alw;
+        m.always = mir.alloc<int>((size_t)m.n_always, &h_alw);
+        std::copy(alw_local.begin(), alw_local.end(), h_alw);
+    }
+    // the train-row indicators of every chain as a [npad][FS] sweep vector: x_j.x_j over each chain's train rows in one
+    // pass (utilities.cpp:153-165, Metric.h:108-129; gaussian only).  With groups the blocks X_g^T X_g / n are
+    // accumulated by group_sacrifice_kernel itself: W = 1/n_train on the chain's train rows, for the life of the chains.
+    double *d_ind = nullptr;
+    const size_t vsz = (size_t)m.npad * d.FS;
+    if (family_ == FAM_LM) {
+        double *h_ind;
+        d_ind = mir.alloc<double>(vsz, &h_ind);
+        std::memset(h_ind, 0, vsz * 8);
+        for (int c = 0; c < C; c++) {
+            const double v = grp ? 1.0 / (double)h_ntrain[c] : 1.0;
+            for (int r = 0; r < h_ntrain[c]; r++) h_ind[(size_t)h_rows[(size_t)c * n + r] * d.FS + c] = v;
+        }
+    }
+    // resident path (lm_path.cu): one cooperative launch per path segment when the problem fits
+    m.lp_why.clear();
+    m.lp_ok = lm_path_eligible(d, max_iter, m.sm_count, &m.lp_why);
+    if (m.lp_ok && m.tie_exact) {
+        m.lp_ok = false;
+        m.lp_why = "exact boundary-tie mode (selections may need the host)";
+    }
+    if (m.lp_ok) {
+        if (m.ctx->coop_launch < 0) CUDA_CHECK(cudaDeviceGetAttribute(&m.ctx->coop_launch, cudaDevAttrCooperativeLaunch, m.ctx->device));
+        if (!m.ctx->coop_launch) {
+            m.lp_ok = false;
+            m.lp_why = "device without cooperative launch";
+        }
+    }
+    if (m.lp_ok) {
+        double *h_tau;
+        m.lp_tau = mir.alloc<double>(MAXC, &h_tau);
+        for (int q = 0; q < MAXC; q++) h_tau[q] = INFINITY;  // no candidate threshold yet: the first select reads the whole vector
+    }
+    mir.flush(m.st);
+
+    // ---- chain state that starts from zero: one block, one memset
+    auto z_bytes = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t zb_ks = z_bytes(MAXC * 4), zb_A = z_bytes((size_t)MAXC * kcap * 4), zb_bA = z_bytes((size_t)MAXC * kcap * 8),
+                 zb_c0 = z_bytes(MAXC * 8), zb_lvl = z_bytes(8), zb_act = z_bytes(8), zb_slot = z_bytes(NSLOT * 8),
+                 zb_beta = z_bytes((size_t)C * d.pstride * 8), zb_XA = z_bytes((size_t)C * n * d.ldA * 8),
+                 zb_grp = grp ? z_bytes((size_t)MAXC * kcap * 4) : 0,
+                 zb_lp = m.lp_ok ? z_bytes(2 * MAXC * 8) + z_bytes(LP_NDBG * 8) + z_bytes((size_t)2 * m.npad * MAXC * 8) : 0;
+    const size_t ztotal = 5 * zb_ks + zb_A + zb_bA + zb_c0 + zb_lvl + zb_act + 2 * zb_slot + zb_beta + zb_XA +
+                          (grp ? zb_ks + zb_grp : 0) + zb_lp;
+    char *zp = ar.alloc<char>(ztotal);
+    CUDA_CHECK(cudaMemsetAsync(zp, 0, ztotal, m.st));
+    auto take = [&](size_t b) {
+        char *r = zp;
+        zp += b;
+        return r;
+    };
+    d.ks = (int *)take(zb_ks);
+    d.l = (int *)take(zb_ks);
+    d.done = (int *)take(zb_ks);
+    d.tie = (int *)take(zb_ks);
+    d.tie_acc = (int *)take(zb_ks);
+    d.A = (int *)take(zb_A);
+    d.bA = (double *)take(zb_bA);
+    d.coef0 = (double *)take(zb_c0);
+    d.coef0_level = (double *)take(zb_lvl);
+    m.n_active2 = (int *)take(zb_act);
+    m.slots.ks = (int *)take(zb_slot);
+    m.slots.coef0 = (double *)take(zb_slot);
+    d.betaD = (double *)take(zb_beta);
+    d.XA = (double *)take(zb_XA);
+    if (grp) {
+        d.Tc = (int *)take(zb_ks);
+        d.AnewCols = (int *)take(zb_grp);
+    }
+    if (m.lp_ok) {
+        m.lp_pub = (double *)take(z_bytes(2 * MAXC * 8));
+        m.lp_dbg = (unsigned long long *)take(z_bytes(LP_NDBG * 8));
+        m.lp_R = (double *)take(z_bytes((size_t)2 * m.npad * MAXC * 8));
+    }
+    d.n_active = m.n_active2;
+    d.prev_active = nullptr;
+    // ---- the rest needs no initial value
+    d.Anew = ar.alloc<int>((size_t)MAXC * kcap);
+    d.hist_rows = max_iter + 2;
+    d.hist = ar.alloc<int>((size_t)C * d.hist_rows * kcap);
+    d.XB = family_ == FAM_COX ? ar.alloc<double>((size_t)C * n * d.ldA) : nullptr;
+    d.vec = ar.alloc<double>((size_t)C * NVEC * n);
+    d.Smat = ar.alloc<double>((size_t)C * 2 * d.ldA * d.ldA);
+    d.cw = ar.alloc<double>((size_t)C * CLMAX * 4 * d.ldA);
+    d.CLcap = CLMAX;
+    d.CLcap = chain_cluster_size(d, kcap, 1);  // the largest cluster any batch of this problem can ask for
+    d.Spart = d.CLcap > 1 ? ar.alloc<double>((size_t)C * d.CLcap * d.nmat * d.ldA * d.ldA) : nullptr;
+    m.slots.A = ar.alloc<int>((size_t)NSLOT * kcap);
+    m.slots.bA = ar.alloc<double>((size_t)NSLOT * kcap);
+    m.loss_scratch = ar.alloc<double>((size_t)2 * MAXC * 2 * n);
+    m.loss_out = ar.alloc<double>(2 * MAXC);
+    if (m.lp_ok) {
+        m.lp_ns = lm_path_slots(d, max_iter);
+        m.lp_res_count = (size_t)LP_MAXSTEP * MAXC * (2 + kcap);
+        m.lp_sync = ar.alloc<unsigned>(2 * LP_SYNC_WORDS);
+        m.lp_cand = ar.alloc<LpCand>((size_t)MAXC * LP_CAP);
+        m.lp_ncand = ar.alloc<int>(MAXC);
+        m.lp_res_i = ar.alloc<int>(2 * m.lp_res_count);
+        m.lp_res_d = ar.alloc<double>(2 * m.lp_res_count);
+        m.ctx->reserve_resident(m.lp_res_count);
+    }
+
+    // ---- x_j.x_j over each chain's train rows
     if (family_ == FAM_LM && grp) {
-        // group blocks X_g^T X_g / n are accumulated by group_sacrifice_kernel itself: W = 1/n on the chain's train rows
-        std::vector<double> ind((size_t)m.npad * d.FS, 0.0);
-        for (int c = 0; c < C; c++)
-            for (int r = 0; r < ntrain[c]; r++) ind[(size_t)rows[(size_t)c * n + r] * d.FS + c] = 1.0 / (double)ntrain[c];
-        CUDA_CHECK(cudaMemcpyAsync(d.W, ind.data(), ind.size() * 8, cudaMemcpyHostToDevice, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));  // `ind` must outlive the copy
+        CUDA_CHECK(cudaMemcpyAsync(d.W, d_ind, vsz * 8, cudaMemcpyDeviceToDevice, m.st));
     } else if (family_ == FAM_LM) {
-        d.xtx = dalloc<double>(m.st, (size_t)C * d.pstride);
-        std::vector<double> ind((size_t)m.npad * d.FS, 0.0);
-        for (int c = 0; c < C; c++)
-            for (int r = 0; r < ntrain[c]; r++) ind[(size_t)rows[(size_t)c * n + r] * d.FS + c] = 1.0;
-        CUDA_CHECK(cudaMemcpyAsync(d.W, ind.data(), ind.size() * 8, cudaMemcpyHostToDevice, m.st));
+        double *Wkeep = d.W;
+        d.W = d_ind;  // the staged indicators ARE the weight vector of this one pass
         BatchDesc b{};
         b.nch = C;
         for (int c = 0; c < C; c++) b.chain[c] = c;
@@ -943,50 +1298,14 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
         launch_dual_sweep(d, MODE_DH, m.st);
         launch_finish(d, MODE_DH, EPI_RAW, b, m.raw, m.st);
         m.span_end(spx);
-        for (int c = 0; c < C; c++)
-            CUDA_CHECK(cudaMemcpyAsync(d.xtx + (size_t)c * d.pstride, m.raw + ((size_t)d.FS + c) * d.pstride,
-                                       (size_t)d.pstride * 8, cudaMemcpyDeviceToDevice, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));  // `ind` must outlive the copy
-        CUDA_CHECK(cudaMemsetAsync(d.W, 0, ind.size() * 8, m.st));
+        d.W = Wkeep;
+        // finish wrote the reduced sums as raw[1][chain][pstride]: exactly the layout of xtx (raw is not used again while
+        // these chains live)
+        d.xtx = m.raw + (size_t)d.FS * d.pstride;
         stats_.n_sweeps++;
         stats_.norm_bytes += 8.0 * n * p;
         stats_.kernel_launches += 2;
     }
-    // ---- poisson: sum_{j<=y} log j (poisson.cpp:29-44), same summation order as the reference
-    {
-        std::vector<double> lf(n, 0.0);
-        if (family_ == FAM_POISSON) {
-            double ymax = 0.0;
-            for (int i = 0; i < n; i++) ymax = std::max(ymax, m.hy[i]);
-            if (ymax <= 5.0e7) {
-                std::vector<double> cum((size_t)ymax + 2, 0.0);
-                for (size_t j = 1; j < cum.size(); j++) cum[j] = cum[j - 1] + std::log((double)j);
-                for (int i = 0; i < n; i++) {
-                    const double yi = m.hy[i];
-                    lf[i] = (yi == 1.0 || yi < 1.0) ? 0.0 : cum[(size_t)std::floor(yi)];
-                }
-            } else {
-                for (int i = 0; i < n; i++) lf[i] = m.hy[i] < 1.0 ? 0.0 : std::lgamma(std::floor(m.hy[i]) + 1.0);
-            }
-        }
-        m.lfact = dalloc<double>(m.st, n);
-        CUDA_CHECK(cudaMemcpyAsync(m.lfact, lf.data(), (size_t)n * 8, cudaMemcpyHostToDevice, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));
-    }
-    m.loss_scratch = dalloc<double>(m.st, (size_t)2 * MAXC * 2 * n);
-    m.loss_out = dalloc<double>(m.st, 2 * MAXC);
-    std::vector<int> alw_local;  // pins are applied to the local sacrifice vector
-    for (int j : always_select)
-        if (!sharded_) alw_local.push_back(j);
-        else if (j >= col_lo_ && j < col_lo_ + p) alw_local.push_back((int)(j - col_lo_));
-    m.n_always = (int)alw_local.size();
-    if (m.n_always) {
-        m.always = dalloc<int>(m.st, m.n_always);
-        CUDA_CHECK(cudaMemcpyAsync(m.always, alw_local.data(), (size_t)m.n_always * 4, cudaMemcpyHostToDevice, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));
-    }
-    d.sharded = sharded_ ? 1 : 0;
-    d.col_lo = sharded_ ? (int)col_lo_ : 0;
     if (sharded_) {
         m.cand_s = dalloc<Cand>(m.st, (size_t)C * kcap);
         m.cand_r = dalloc<Cand>(m.st, (size_t)m.world * C * kcap);
@@ -1004,48 +1323,16 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     }
     m.cstride = std::max<long long>(2LL * kcap + 16, ((long long)p / 8192 + 2) * std::min(kcap, TOPK_LMAX));
     if (sharded_) m.cstride = std::max<long long>(m.cstride, (long long)m.world * kcap + 16);
-    m.ck0 = dalloc<double>(m.st, (size_t)C * m.cstride);
-    m.ck1 = dalloc<double>(m.st, (size_t)C * m.cstride);
-    m.ci0 = dalloc<int>(m.st, (size_t)C * m.cstride);
-    m.ci1 = dalloc<int>(m.st, (size_t)C * m.cstride);
+    m.ck0 = ar.alloc<double>((size_t)C * m.cstride);
+    m.ck1 = ar.alloc<double>((size_t)C * m.cstride);
+    m.ci0 = ar.alloc<int>((size_t)C * m.cstride);
+    m.ci1 = ar.alloc<int>((size_t)C * m.cstride);
     m.ctx->reserve_support((size_t)MAXC * kcap);
     for (int q = 0; q < 2; q++) {
         m.mir[q].A = m.ctx->h_A + (size_t)q * MAXC * kcap;
         m.mir[q].bA = m.ctx->h_bA + (size_t)q * MAXC * kcap;
         m.tk[q].pending = false;
     }
-    // ---- resident path (lm_path.cu): one cooperative launch per path segment when the problem fits
-    m.lp_why.clear();
-    m.lp_ok = lm_path_eligible(d, max_iter, m.sm_count, &m.lp_why);
-    if (m.lp_ok) {
-        int coop = 0;
-        CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m.ctx->device));
-        if (!coop) {
-            m.lp_ok = false;
-            m.lp_why = "device without cooperative launch";
-        }
-    }
-    if (m.lp_ok) {
-        m.lp_ns = lm_path_slots(d, max_iter);
-        m.lp_res_count = (size_t)LP_MAXSTEP * MAXC * (2 + kcap);
-        m.lp_sync = dalloc<unsigned>(m.st, 2 * LP_SYNC_WORDS);
-        m.lp_cand = dalloc<LpCand>(m.st, (size_t)MAXC * LP_CAP);
-        m.lp_ncand = dalloc<int>(m.st, MAXC);
-        m.lp_pub = dalloc<double>(m.st, 2 * MAXC);
-        m.lp_tau = dalloc<double>(m.st, MAXC);
-        m.lp_res_i = dalloc<int>(m.st, 2 * m.lp_res_count);
-        m.lp_res_d = dalloc<double>(m.st, 2 * m.lp_res_count);
-        m.lp_dbg = dalloc<unsigned long long>(m.st, LP_NDBG);
-        m.lp_R = dalloc<double>(m.st, (size_t)2 * m.npad * MAXC);
-        CUDA_CHECK(cudaMemsetAsync(m.lp_R, 0, (size_t)2 * m.npad * MAXC * 8, m.st));
-        std::vector<double> inf(MAXC, INFINITY);  // no candidate threshold yet: the first select reads the whole vector
-        CUDA_CHECK(cudaMemcpyAsync(m.lp_tau, inf.data(), MAXC * 8, cudaMemcpyHostToDevice, m.st));
-        CUDA_CHECK(cudaMemsetAsync(m.lp_pub, 0, 2 * MAXC * 8, m.st));
-        CUDA_CHECK(cudaMemsetAsync(m.lp_dbg, 0, LP_NDBG * 8, m.st));
-        CUDA_CHECK(cudaStreamSynchronize(m.st));  // `inf` must outlive the copy
-        m.ctx->reserve_resident(m.lp_res_count);
-    }
-    CUDA_CHECK(cudaStreamSynchronize(m.st));
     S_ = d.S;
     m.chains_ready = true;
 }
@@ -1056,9 +1343,9 @@ void Engine::resident_counters(double *out24) const
 {
     for (int i = 0; i < 24; i++) out24[i] = d_->lp_counters[i];
 }
-void Engine::resident_owner_counters(double *out64) const
+void Engine::resident_owner_counters(double *out4c) const
 {
-    for (int i = 0; i < 4 * MAXC; i++) out64[i] = d_->lp_owner[i];
+    for (int i = 0; i < 4 * MAXC; i++) out4c[i] = d_->lp_owner[i];
 }
 
 // Enqueue one launch of the resident kernel for the batch in t.b: memsets, kernel, result copies into the slot's pinned
@@ -1164,7 +1451,7 @@ static void lp_parse(Engine::Impl &m, const Engine::Impl::Ticket &t, EngineStats
     const unsigned long long *dbg = c->h_lp_dbg + (size_t)t.slot * LP_NDBG;  // cumulative since setup_chains
     for (int q = 0; q < 8; q++) m.lp_counters[8 + q] = (double)dbg[q];
     for (int q = 0; q < 3; q++) m.lp_counters[16 + q] = (double)dbg[16 + q];
-    m.lp_counters[19] = (double)dbg[8];
+    for (int q = 0; q < 5; q++) m.lp_counters[19 + q] = (double)dbg[8 + q];  // assemble, candidate load, slot assignment, scatter + cycle test, level bookkeeping
     for (int q = 0; q < 4 * MAXC; q++) m.lp_owner[q] = (double)dbg[32 + q];  // assembling the normal equations (part of `solve` when added to slot 13)
 }
 
@@ -1213,6 +1500,57 @@ void engine_debug_first_group(int n) { g_first_group = n < 1 ? 1 : n; }
 
 // One group of PDAS iterations for the batch described by ticket `t` (enqueue only).
 static void enqueue_iterations(Engine::Impl &m, Engine::Impl::Ticket &t, int count, bool sharded, long long col_lo);
+
+static void enqueue_results(Engine::Impl &m, Engine::Impl::Ticket &t);
+
+// One batch in exact boundary-tie mode (Engine::set_tie_exact): the PDAS iterations run one at a time; after every device
+// select the host reads the tie flags and repeats the selection of a tied chain with the reference's max_k on the chain's
+// sacrifice vector.  Synchronous: the batch is finished when this returns.
+static void run_batch_exact(Engine::Impl &m, Engine::Impl::Ticket &t, EngineStats &stats)
+{
+    Dev &d = t.d;
+    const BatchDesc &b = t.b;
+    d.prev_active = nullptr;  // no speculative batch behind this one
+    t.fused = false;
+    const int T = t.T, cmin = t.cmin, cmax = t.cmax, nspan = cmax - cmin + 1;
+    const int mode = sweep_mode(d.family), epi = sweep_epi(d.family);
+    const int N = d.grouped ? d.N : d.p;
+    launch_chain_begin(d, b, m.st);
+    std::vector<int> tie(MAXC), done(MAXC), hsel((size_t)T);
+    std::vector<double> row((size_t)N);
+    for (int it = 0; it <= d.max_iter; it++) {
+        int active = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&active, d.n_active, sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        if (active == 0) break;
+        if (d.grouped) {
+            launch_group_sacrifice(d, b, m.st);
+        } else {
+            launch_dual_sweep(d, mode, m.st);
+            launch_finish(d, mode, epi, b, nullptr, m.st);
+        }
+        if (m.n_always) launch_pin(d, d.bd + (size_t)cmin * d.pstride, d.pstride, nspan, m.always, m.n_always, m.st);
+        launch_topk(d.bd + (size_t)cmin * d.pstride, d.pstride, N, T, nspan, d.Anew + (size_t)cmin * d.kcap, d.kcap, d.tie + cmin,
+                    m.ck0, m.ci0, m.ck1, m.ci1, m.cstride, m.st, d.gate);
+        CUDA_CHECK(cudaMemcpyAsync(tie.data(), d.tie, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(done.data(), d.done, MAXC * sizeof(int), cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaStreamSynchronize(m.st));
+        for (int i = 0; i < b.nch; i++) {
+            const int c = b.chain[i];
+            if (done[c] || !tie[c]) continue;
+            CUDA_CHECK(cudaMemcpyAsync(row.data(), d.bd + (size_t)c * d.pstride, (size_t)N * 8, cudaMemcpyDeviceToHost, m.st));
+            CUDA_CHECK(cudaStreamSynchronize(m.st));
+            host_max_k(row.data(), N, T, hsel.data());
+            CUDA_CHECK(cudaMemcpyAsync(d.Anew + (size_t)c * d.kcap, hsel.data(), (size_t)T * sizeof(int), cudaMemcpyHostToDevice, m.st));
+            CUDA_CHECK(cudaStreamSynchronize(m.st));  // hsel is reused
+        }
+        if (d.grouped) launch_group_expand(d, b, m.st);
+        launch_chain_fit(d, b, m.st);
+        t.enq++;
+        stats.kernel_launches += d.grouped ? 4 : 5;
+    }
+    enqueue_results(m, t);
+}
 
 int Engine::run_batch_enqueue(int T, const std::vector<int> &chains, bool new_path_step, const std::vector<LossJob> *jobs,
                               double lambda)
@@ -1294,6 +1632,11 @@ int Engine::run_batch_enqueue(int T, const std::vector<int> &chains, bool new_pa
         return slot;
     }
 
+    if (m.tie_exact && !sharded_) {
+        run_batch_exact(m, t, stats_);
+        t.pending = true;
+        return slot;
+    }
     int sp = m.span_begin(4);
     launch_chain_begin(t.d, b, m.st);
     m.span_end(sp);
@@ -1373,7 +1716,14 @@ static void enqueue_iterations(Engine::Impl &m, Engine::Impl::Ticket &t, int cou
         m.span_end(sp);
     }
     t.enq += count;
-    // results are enqueued behind the group; they are only used if the batch turns out to be finished
+    enqueue_results(m, t);
+}
+
+// results are enqueued behind a group of iterations; they are only used if the batch turns out to be finished
+static void enqueue_results(Engine::Impl &m, Engine::Impl::Ticket &t)
+{
+    const Dev &d = t.d;
+    int sp;
     Engine::Impl::Mirror &h = m.mir[t.slot];
     if (t.has_jobs) {
         sp = m.span_begin(5);

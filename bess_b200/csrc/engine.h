@@ -16,9 +16,9 @@
 
 namespace bess {
 
-constexpr int MAXC = 16;      // max chains = 1 + K folds
+constexpr int MAXC = 32;      // max chains = 1 + K folds (K <= 31)
 constexpr int PROF_NCAT = 8;
-constexpr int MAX_HIST = 66;  // max_iter + 2 columns of A_list (Algorithm.h:142)
+constexpr int MAX_ITER_CAP = 100000;  // A_list (Algorithm.h:142) is sized max_iter + 2 per problem; this only bounds the argument
 constexpr int GMAX = 8;       // widest group of variables in group selection (gsize > 1)
 constexpr int NSLOT = 4;      // snapshot slots of Engine::chain_state
 enum { STATE_ZERO = 0, STATE_SAVE = 1, STATE_LOAD = 2 };
@@ -73,8 +73,16 @@ public:
     bool has_comm() const;
     // column count the model sees (IC penalties, validation): p_total while sharded, else p
     long long p_model() const { return sharded_ ? p_total_ : p_; }
-    double x_mean_at(long long j) const { return sharded_ ? g_xmean_[(size_t)j] : h_xmean_[(size_t)j]; }
-    double x_norm_at(long long j) const { return sharded_ ? g_xnorm_[(size_t)j] : h_xnorm_[(size_t)j]; }
+    double x_mean_at(long long j) const { ensure_stats(); return sharded_ ? g_xmean_[(size_t)j] : h_xmean_[(size_t)j]; }
+    double x_norm_at(long long j) const { ensure_stats(); return sharded_ ? g_xnorm_[(size_t)j] : h_xnorm_[(size_t)j]; }
+    // ---- boundary ties of the top-k selections.  max_k (utilities.cpp:179-188) leaves a tie between the k-th and the
+    // (k+1)-th value to std::nth_element; the device select takes the lower index and only COUNTS such ties
+    // (stats().n_boundary_ties).  In exact mode every selection that meets a boundary tie is repeated on the host with the
+    // reference's own index-array nth_element + sort, at the price of one host round trip per PDAS iteration (no
+    // speculative iterations, no resident path).  bess_run repeats a call in this mode when the fast pass saw a tie.
+    // Call before load().  Not available in column-sharded mode (ties are then only counted).
+    void set_tie_exact(bool on);
+    bool tie_exact() const;
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;
 
@@ -91,6 +99,10 @@ public:
 
     // ---- screening.cpp:26-105: marginal utilities on RAW x, top `size`, X <- X[:, A].  Returns A ascending.
     std::vector<int> screen(int size, const std::vector<int> &always_select);
+    // the same in two halves: screen_enqueue only enqueues device work (the path can start behind it), screen_result waits
+    // for the kept-column list
+    void screen_enqueue(int size, const std::vector<int> &always_select);
+    std::vector<int> screen_result();
 
     // ---- column-sharded screening (multi-GPU axis B): local top-`size` candidates, X untouched
     void screen_local(int size, const std::vector<int> &always_select, std::vector<double> &vals, std::vector<int> &idx);
@@ -144,7 +156,7 @@ public:
     void resident_counters(double *out24) const;
     // per chain owner i (position in the batch): [4 * i + 0] busy ticks, [1] longest phase, [2] ticks in fallback selects,
     // [3] fits actually solved
-    void resident_owner_counters(double *out64) const;
+    void resident_owner_counters(double *out4c) const;  // [4 * MAXC]
 
     // ---- explicit warm-start state of a chain (STATE_ZERO / STATE_SAVE / STATE_LOAD on NSLOT slots; the
     // (A, beta_A) half and the coef0 half are addressed separately, a negative slot skips that half).  Used by pgs_path.
@@ -162,8 +174,10 @@ public:
     int p() const { return p_; }
     bool grouped() const { return n_groups_ > 0; }
     int family() const { return family_; }
-    const std::vector<double> &x_mean() const { return h_xmean_; }
-    const std::vector<double> &x_norm() const { return h_xnorm_; }
+    const std::vector<double> &x_mean() const { ensure_stats(); return h_xmean_; }
+    const std::vector<double> &x_norm() const { ensure_stats(); return h_xnorm_; }
+    // the column statistics travel to the host asynchronously; the first reader waits for them
+    void ensure_stats() const;
     double y_mean() const { return y_mean_; }
     EngineStats &stats() { return stats_; }
     int sweep_splits() const { return S_; }

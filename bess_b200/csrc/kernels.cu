@@ -250,6 +250,8 @@ static void launch_sweep_m(const Dev &d, cudaStream_t st)
         case 8: launch_sweep_t<8, MODE, MODE == MODE_D ? 2 : 1>(d, st); break;
         case 12: launch_sweep_t<12, MODE, MODE == MODE_D ? 2 : 1>(d, st); break;
         case 16: launch_sweep_t<16, MODE, 1>(d, st); break;
+        case 24: launch_sweep_t<24, MODE, 1>(d, st); break;
+        case 32: launch_sweep_t<32, MODE, 1>(d, st); break;
         default: throw EngineError{"dual sweep: unsupported chain tile FS=" + std::to_string(d.FS)};
     }
 }
@@ -900,6 +902,21 @@ __global__ void center_scale_kernel(double *X, long long ldx, int n, int p, cons
         *ptr = v;
     }
 }
+// normx_j = sqrt(h_j), mul_j = sqrt(n) / normx_j  (normalize.cpp:36-45; IEEE sqrt and division: the same bits as the host)
+__global__ void norm_factors_kernel(const double *h, int p, double sn, double *norm_out, double *mul_out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    const double nx = sqrt(h[j]);
+    norm_out[j] = nx;
+    mul_out[j] = sn / nx;
+}
+void launch_norm_factors(const double *h, int p, double sn, double *norm_out, double *mul_out, cudaStream_t st)
+{
+    norm_factors_kernel<<<(p + 255) / 256, 256, 0, st>>>(h, p, sn, norm_out, mul_out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_center_scale(double *X, long long ldx, int n, int p, const double *sub, const double *mul,
                          const double *rowmul, cudaStream_t st)
 {

@@ -42,7 +42,8 @@ struct Dev {
     double *coef0;      // [MAXC]
     double *coef0_level;// [1]  Algorithm::coef0_init of the current path step (path.cpp:57)
     int *Anew;          // [MAXC][kcap] output of top-k
-    int *hist;          // [MAXC][MAX_HIST][kcap]  A_list (Algorithm.h:141-143)
+    int *hist;          // [MAXC][hist_rows][kcap]  A_list (Algorithm.h:141-143)
+    int hist_rows;      // max_iter + 2
     int *l;             // [MAXC]
     int *done;          // [MAXC]
     int *tie;           // [MAXC] boundary-tie flag of the last top-k
@@ -160,6 +161,7 @@ void launch_chain_state(const Dev &d, int chain, int op, int slot_beta, int slot
 void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st);
 void launch_losses(const Dev &d, const LossDesc &jobs, const int *testrows, const int *ntest, const double *y,
                    const double *w, const double *lfact, double *scratch, double *out, cudaStream_t st);
+void launch_norm_factors(const double *h, int p, double sn, double *norm_out, double *mul_out, cudaStream_t st);
 void launch_center_scale(double *X, long long ldx, int n, int p, const double *sub, const double *mul,
                          const double *rowmul, cudaStream_t st);
 void launch_gather_cols(const double *X, long long ldx, int n, const int *cols, int pnew, double *Xn, long long ldn,

@@ -28,6 +28,7 @@
 //
 // The results are bitwise reproducible from run to run (fixed summation orders; the candidate list is unordered but its
 // ranking is a total order) and equal to the multi-kernel path up to fp64 re-association (supports identical).
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -926,6 +927,7 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
             }
             __syncthreads();
             int count = s.misc[MI_COUNT];
+            tm.mark(9);
             // One sweep can serve two fits: when a fit ends because its active set repeats the previous one, beta has not
             // moved since the sweep, and the first get_A of the NEXT path step (warm start, same ridge level) would
             // recompute exactly this sacrifice vector -- the owner selects again from the same candidates at once.
@@ -990,6 +992,7 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                     }
                     __syncthreads();
                     const int nnew = s.misc[MI_NNEW];
+                    tm.mark(10);
                     gather_new(d, s, nnew, npad);
                     tm.mark(3);
                     gram_new(d, s, nnew, ns, npad);
@@ -1022,6 +1025,7 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                     }
                     __syncthreads();
                     seen = s.misc[MI_SEEN] != 0;
+                    tm.mark(11);
                     // the losses ride along with every residual: a fit that ends on a repeated set needs them without a pass
                     residual(d, s, c, Rcol, L.fh, ks, nt, npad, true, &la, &lt);
                     tm.mark(6);
@@ -1087,6 +1091,7 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                     }
                 }
             }
+            tm.mark(12);
             if (tid == 0) {
                 __stcg(L.pub + 2 * c, complete ? (double)INFINITY : tau);
                 __stcg(L.pub + 2 * c + 1, lam);
@@ -1147,7 +1152,9 @@ size_t lm_path_smem_bytes(const Dev &d, int max_iter, int sm_count)
     (void)sm_count;
     const int npad = (d.n + 1) & ~1;
     const size_t own = owner_smem_bytes(npad, d.kcap, lm_path_slots(d, max_iter), max_iter + 2);
-    const size_t swp = sweeper_smem_doubles(npad, d.FS) * 8;  // d.FS >= the slots of any group of any batch
+    int fhmax = 1;  // the widest chain group any batch of this problem (at most d.FS chains) can have
+    for (int nch = 1; nch <= d.FS; nch++) fhmax = std::max(fhmax, lm_path_fh(nch, lm_path_groups(nch)));
+    const size_t swp = sweeper_smem_doubles(npad, fhmax) * 8;
     return ((own > swp ? own : swp) + 127) & ~(size_t)127;
 }
 

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <random>
 
@@ -695,7 +696,7 @@ void pgs_path(Driver &dr, BessResult &out, Eval &best)
 
 }  // namespace
 
-void bess_run(const BessArgs &a, BessResult &out)
+static void bess_run_once(const BessArgs &a, BessResult &out, bool tie_exact)
 {
     // ---- argument validation (the reference validates in its R/Python front-ends and dereferences null otherwise,
     // SURVEY Q19; here bad arguments are reported)
@@ -729,7 +730,7 @@ void bess_run(const BessArgs &a, BessResult &out)
         if (a.is_screening) throw EngineError{"screening together with group selection is not supported"};
         if (a.world > 1) throw EngineError{"group selection is not available in column-sharded mode"};
     }
-    if (a.is_cv && (a.K < 2 || a.K > MAXC - 1)) throw EngineError{"K (nfolds) must be in [2, 15]"};
+    if (a.is_cv && (a.K < 2 || a.K > MAXC - 1)) throw EngineError{"K (nfolds) must be in [2, 31]"};
     const bool shard = a.world > 1;
     const long long p_all = shard ? a.p_total : a.p;
     if (shard && a.x_on_device == false && a.x == nullptr) throw EngineError{"sharded fit: x shard is null"};
@@ -745,6 +746,7 @@ void bess_run(const BessArgs &a, BessResult &out)
         t_last = now;
     };
     Engine eng(a.device);
+    eng.set_tie_exact(tie_exact);
     eng.set_profiling(a.profile);
     if (shard) eng.init_shard(a.world, a.rank, a.nccl_id, a.col_lo, a.p_total);
     eng.load(a.x, a.n, a.p, a.x_on_device, a.y, a.weight, a.model_type, /*borrow=*/a.is_screening);
@@ -754,7 +756,10 @@ void bess_run(const BessArgs &a, BessResult &out)
     std::sort(always.begin(), always.end());
     if (a.is_screening) {
         if (a.screening_size < 1 || a.screening_size > p_all) throw EngineError{"screening_size must be in [1, p]"};
-        out.screening_A = eng.screen(a.screening_size, always);
+        // only device work is enqueued here; the kept-column list is read when it is first needed -- for the remap of
+        // always_select right away, else at the end of the call (the normalisation and the path queue up behind it)
+        eng.screen_enqueue(a.screening_size, always);
+        if (!always.empty()) out.screening_A = eng.screen_result();
         // screening.cpp:91-102: always_select -> positions inside the screened matrix
         for (int &j : always) {
             auto it = std::lower_bound(out.screening_A.begin(), out.screening_A.end(), j);
@@ -795,6 +800,7 @@ void bess_run(const BessArgs &a, BessResult &out)
     else gs_path(dr, out, best);
 
     lap(4);
+    if (a.is_screening && out.screening_A.empty()) out.screening_A = eng.screen_result();
     std::vector<double> bA;
     double coef0;
     dr.denormalise(best, bA, coef0);
@@ -819,6 +825,26 @@ void bess_run(const BessArgs &a, BessResult &out)
     out.sweep_splits = eng.sweep_splits();
     eng.resident_counters(out.resident);
     eng.resident_owner_counters(out.resident + 24);
+}
+
+// bessCpp (bess.cpp:37-214) on the device.  The fast pass resolves a boundary tie of a top-k selection -- the k-th and the
+// (k+1)-th sacrifice / screening utility exactly equal, e.g. duplicated columns -- towards the lower index and counts it;
+// the reference leaves such a tie to std::nth_element (utilities.cpp:179-188, SURVEY a-5).  When the fast pass met one,
+// the whole call is repeated in exact mode, where every tied selection is redone on the host with the reference's own
+// index-array nth_element + sort (Engine::set_tie_exact).  Continuous designs never take the second pass.
+void bess_run(const BessArgs &a, BessResult &out)
+{
+    bess_run_once(a, out, false);
+    static const bool redo = [] {
+        const char *e = std::getenv("BESS_B200_TIE_EXACT");
+        return !(e && e[0] == '0');
+    }();
+    if (redo && out.stats.n_boundary_ties > 0 && a.world <= 1) {
+        BessResult exact;
+        bess_run_once(a, exact, true);
+        out = std::move(exact);
+        out.tie_exact_pass = true;
+    }
 }
 
 }  // namespace bess

@@ -75,7 +75,8 @@ struct BessResult {
     double prof_ms[PROF_NCAT] = {};
     long long prof_n[PROF_NCAT] = {};
     int sweep_splits = 1;
-    double resident[88] = {};  // Engine::resident_counters (24) + resident_owner_counters (64)
+    bool tie_exact_pass = false;  // the call met a boundary tie and was repeated with host-resolved selections
+    double resident[24 + 4 * MAXC] = {};  // Engine::resident_counters (24) + resident_owner_counters (4 per chain)
     // host wall-clock of the call by phase (ms): 0 engine + load (+ upload), 1 screening, 2 normalisation, 3 fold / chain
     // set-up, 4 the path itself
     double host_ms[5] = {};

@@ -262,6 +262,8 @@ void launch_tma_m(const Dev &d, cudaStream_t st)
         case 8: launch_tma_t<8, MODE, MODE == MODE_COX ? 1 : 2>(d, st); break;
         case 12: launch_tma_t<12, MODE, MODE == MODE_COX ? 1 : 2>(d, st); break;
         case 16: launch_tma_t<16, MODE, MODE == MODE_D ? 2 : 1>(d, st); break;
+        case 24: launch_tma_t<24, MODE, 1>(d, st); break;
+        case 32: launch_tma_t<32, MODE, 1>(d, st); break;
         default: throw EngineError{"dual sweep: unsupported chain tile FS=" + std::to_string(d.FS)};
     }
 }

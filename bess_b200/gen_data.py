@@ -39,7 +39,7 @@ def gen_data(n, p, family="gaussian", k=10, seed=1, snr=10.0, scal=10.0, c=10.0,
         y = rng.binomial(1, pr).astype(np.float64)
         return SynthData(x, y, tbeta)
     if family == "poisson":
-        x /= 16.0
+        x = x / 16.0  # not in place: a caller-supplied design stays untouched
         tbeta[nonzero] = rng.uniform(2 * m, 10 * m, k)
         sigma = np.sqrt((tbeta @ tbeta) / snr)
         eta = np.clip(x[:, nonzero] @ tbeta[nonzero] + rng.normal(0.0, sigma, n), -30, 30)
@@ -54,6 +54,61 @@ def gen_data(n, p, family="gaussian", k=10, seed=1, snr=10.0, scal=10.0, c=10.0,
         order = np.argsort(time, kind="stable")
         return SynthData(np.ascontiguousarray(x[order]), status[order], tbeta, time[order])
     raise ValueError("family should be 'gaussian', 'binomial', 'poisson' or 'cox'")
+
+
+class data:
+    """Result record of the reference's ``gen_data`` (python/bess/gen_data.py:4-8)."""
+
+    def __init__(self, x, y, beta):
+        self.x = x
+        self.y = y
+        self.beta = beta
+
+
+def gen_data_reference(n, p, family, k, rho=0, sigma=1, beta=None, censoring=True, c=1, scal=10):
+    """The reference's Python generator, argument for argument (python/bess/gen_data.py:22-102): the banded design
+    x = X + rho * (left shift + right shift) of the centred, sqrt(n)-normalised iid normal X (``gen.data`` cortype 3,
+    R/R/gen.data.R:167-245), draws from numpy's GLOBAL random state like the reference, ``y`` of a cox problem is the
+    unsorted n x 2 array [time, status] that ``PdasCox.fit`` sorts itself (linear.py:257-263).  Served as
+    ``bess.gen_data.gen_data`` by ``bess_b200.compat.install_as_bess``; ``gen_data`` above (seeded PCG64 streams,
+    cortype 1, rows pre-sorted for cox) is what the parity tests and the bench use."""
+    X = np.random.normal(0, 1, n * p).reshape(n, p)
+    X = X - X.mean(axis=0, keepdims=True)
+    X = np.sqrt(n) * X / np.sqrt((X ** 2).sum(axis=0, keepdims=True))
+    zero = np.zeros((n, 1))
+    x = X + rho * (np.hstack((zero, X[:, 0:(p - 2)], zero)) + np.hstack((zero, X[:, 2:p], zero)))
+    full, nonzero = np.arange(p), np.zeros(k, int)
+    for i in range(k):  # sampling without replacement, one draw at a time (gen_data.py:11-19)
+        z = np.random.choice(full, 1)
+        nonzero[i] = z[0]
+        full = np.delete(full, np.where(full == z))
+    tbeta = np.zeros(p)
+    m = 5 * (1 if family == "gaussian" else sigma) * np.sqrt(2 * np.log(p) / n)
+    if beta is None:
+        tbeta[nonzero] = np.random.uniform(m, 100 * m, k) if family == "gaussian" else np.random.uniform(2 * m, 10 * m, k)
+    else:
+        tbeta = beta
+    if family == "gaussian":
+        return data(x, np.matmul(x, tbeta) + sigma * np.random.normal(0, 1, n), tbeta)
+    if family == "binomial":
+        xb = np.clip(np.matmul(x, tbeta), -30, 30)
+        return data(x, np.random.binomial(1, np.exp(xb) / (1 + np.exp(xb))), tbeta)
+    if family == "poisson":
+        x = x / 16
+        xb = np.clip(np.matmul(x, tbeta), -30, 30)
+        return data(x, np.random.poisson(lam=np.exp(xb)), tbeta)
+    if family == "cox":
+        time = np.power(-np.log(np.random.uniform(0, 1, n)) / np.exp(np.matmul(x, tbeta)), 1 / scal)
+        if censoring:
+            ctime = c * np.random.uniform(0, 1, n)
+            status = (time < ctime) * 1
+            print("censoring rate:" + str(1 - sum(status) / n))
+            time = np.minimum(time, ctime)
+        else:
+            status = np.ones(n)
+            print("no censoring")
+        return data(x, np.hstack((time.reshape((-1, 1)), status.reshape((-1, 1)))), tbeta)
+    raise ValueError("Family should be 'gaussian', 'binomial', 'possion', or 'cox'")
 
 
 def gen_design_device(n, p, rho=0.0, seed=1, device=0):

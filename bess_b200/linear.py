@@ -69,12 +69,9 @@ class bess_base:
             if len(group) != p:
                 raise ValueError("The length of group should be equal to the number of variables")
             group = sorted(group)  # the reference sorts the caller's list in place; a copy is sorted here
-            g_index, j = [], 0
-            for i in list(set(group)):
-                while group[j] != i:
-                    j += 1
-                g_index.append(j)
-            g_index = np.asarray(g_index, dtype=np.int32)
+            # first position of every distinct label of the sorted list (the reference walks `list(set(group))`, whose
+            # order is hash order: labels other than small non-negative ints run it off the end of the list)
+            g_index = np.unique(np.asarray(group), return_index=True)[1].astype(np.int32)
         else:
             g_index = np.arange(p, dtype=np.int32)
         if self.model_type_int == 4:

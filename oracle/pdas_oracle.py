@@ -77,11 +77,22 @@ def make_data(x, y, weight, data_type, is_normal, model_type):
 # --------------------------------------------------------------------------------------
 # Selection: utilities.cpp:179-199
 # --------------------------------------------------------------------------------------
+TIES = {"count": 0, "unresolved": 0}  # boundary ties met by max_k since import (tests reset and read it)
+
+
 def max_k(vec, k):
     """Indices of the k largest entries, returned ascending (utilities.cpp:179-188).
     Tie rule at the boundary: see module docstring."""
     p = vec.shape[0]
     order = np.lexsort((np.arange(p), -vec))  # primary: value desc; secondary: index asc
+    if k < p and vec[order[k - 1]] == vec[order[k]]:
+        # a boundary tie: the reference leaves its resolution to std::nth_element over an index array (libstdc++
+        # introselect) -- no closed-form rule exists, so the compiled reference itself is asked (oracle/_ref)
+        TIES["count"] += 1
+        from . import ref
+        if ref.available():
+            return ref.max_k(vec, k)
+        TIES["unresolved"] += 1
     return np.sort(order[:k]).astype(np.int32)
 
 

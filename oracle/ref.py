@@ -73,6 +73,15 @@ def pywrap_bess(x, y, data_type, weight, is_normal, algorithm_type, model_type, 
     return dict(beta=beta, coef0=float(s1[0][0]), train_loss=float(s1[1][0]), ic=float(s1[2][0]))
 
 
+def max_k(vec, k):
+    """The reference's max_k (utilities.cpp:179-188) on `vec`: k largest, ascending, boundary ties as std::nth_element
+    leaves them."""
+    v = np.ascontiguousarray(vec, dtype=np.float64)
+    out = np.zeros(k, dtype=np.int32)
+    lib().ref_max_k(_d(v), C.c_int(v.size), C.c_int(int(k)), _i(out))
+    return out
+
+
 def screening(x, y, weight, model_type, screening_size):
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(y, dtype=np.float64)

@@ -256,4 +256,13 @@ int ref_pgs_trace(double *x, int n, int p, double *y, double *weight, int data_t
     return nfits;
 }
 
+// max_k itself (utilities.cpp:179-188): the reference's resolution of boundary ties (std::nth_element over an index array)
+void ref_max_k(const double *v, int n, int k, int *out)
+{
+    Eigen::VectorXd vec = Eigen::Map<const Eigen::VectorXd>(v, n);
+    Eigen::VectorXi res;
+    max_k(vec, k, res);
+    for (int i = 0; i < k; i++) out[i] = res(i);
+}
+
 }  // extern "C"

@@ -95,3 +95,21 @@ def load_group_golden(name):
     else:
         g["kw"] = dict(lambda_seq=g["lambdas"])
     return g
+
+
+HARD_DIR = os.path.join(GOLDEN_DIR, "hard")
+
+
+def hard_golden_names():
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(HARD_DIR, "*.npz")))
+
+
+def load_hard_golden(name):
+    """tests/golden/hard/*.npz (made by tests/golden/hard/make_hard.py from the real reference): boundary ties from
+    duplicated columns, correlated designs (rho = 0.5 / 0.9, banded), 20 folds, max_iter = 100."""
+    g = dict(np.load(os.path.join(HARD_DIR, name + ".npz")))
+    m = g["meta"]
+    g["model_type"], g["data_type"], g["path_type"], g["is_cv"], g["K"], g["ic_type"], g["smax"], g["scr"] = (
+        int(m[0]), int(m[1]), int(m[2]), bool(m[3]), int(m[4]), int(m[5]), int(m[6]), int(m[7]))
+    g["max_iter"] = int(g["max_iter"])
+    return g

@@ -240,3 +240,61 @@ def test_reference_module_names_resolve_to_this_library():
         for k in [k for k in sys.modules if k == "bess" or k.startswith("bess.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_compat_gen_data_has_the_reference_signature_and_shapes():
+    """`bess.gen_data.gen_data` served by install_as_bess takes the reference's arguments (python/bess/gen_data.py:22:
+    rho=, sigma=, beta=, censoring=, c=, scal=) and returns its `data` record; cox y is the unsorted [time, status] array
+    PdasCox.fit sorts itself (linear.py:257-263)."""
+    import importlib
+    import inspect
+    import sys
+    from bess_b200 import compat
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "bess" or k.startswith("bess.")}
+    try:
+        compat.install_as_bess()
+        gd = importlib.import_module("bess.gen_data")
+        assert list(inspect.signature(gd.gen_data).parameters) == ["n", "p", "family", "k", "rho", "sigma", "beta", "censoring",
+                                                                   "c", "scal"]
+        np.random.seed(3)
+        d = gd.gen_data(60, 20, "gaussian", 3, rho=0.3, sigma=0.5)
+        assert isinstance(d, gd.data) and d.x.shape == (60, 20) and d.y.shape == (60,) and np.count_nonzero(d.beta) == 3
+        # banded design: column j is X_j + rho (X_{j-1} + X_{j+1}) of a centred, sqrt(n)-normalised X => neighbours correlate
+        c01 = np.corrcoef(d.x[:, 5], d.x[:, 6])[0, 1]
+        assert 0.2 < c01 < 0.8
+        dc = gd.gen_data(50, 10, "cox", 2, 0, 1, None, True, 10, 10)  # positional, as the reference's docs call it
+        assert dc.y.shape == (50, 2) and set(np.unique(dc.y[:, 1])) <= {0.0, 1.0}
+        assert not np.all(np.diff(dc.y[:, 0]) >= 0)  # rows are NOT time-sorted: the estimator sorts
+        dp = gd.gen_data(40, 8, "poisson", 2)
+        assert dp.y.dtype.kind in "iu" or np.all(dp.y == np.round(dp.y))
+    finally:
+        for k in [k for k in sys.modules if k == "bess" or k.startswith("bess.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_gen_data_does_not_modify_a_supplied_design():
+    from bess_b200.gen_data import gen_data
+    x = np.random.default_rng(0).standard_normal((30, 12))
+    x0 = x.copy()
+    gen_data(30, 12, "poisson", 3, seed=2, x=x)
+    gen_data(30, 12, "poisson", 3, seed=2, x=x)
+    assert np.array_equal(x, x0)
+
+
+def test_group_index_accepts_any_sortable_labels(monkeypatch):
+    """linear.py:238-254 builds g_index by walking list(set(group)) in hash order, which runs off the list for string,
+    float or large labels; here the first position of every distinct label of the sorted list is taken."""
+    import bess_b200.linear as lin
+    seen = {}
+
+    def fake(*args):
+        seen["g"] = list(args[14])
+        return [np.zeros(args[0].shape[1]), 0.0, 0.0, 0.0, 0.0, None, None, None, None, 0]
+
+    monkeypatch.setattr(lin, "pywrap_bess", fake)
+    x = np.random.default_rng(1).standard_normal((20, 6))
+    y = x[:, 0] + 0.1
+    for labels in (["b", "a", "a", "c", "c", "b"], [1000003, 7, 7, -5, -5, 1000003], [0.5, 0.25, 0.25, 2.0, 2.0, 0.5]):
+        lin.GroupPdasLm(sequence=[1]).fit(x, y, group=list(labels))
+        assert seen["g"] == [0, 2, 4]

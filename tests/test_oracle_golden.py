@@ -3,8 +3,8 @@ import numpy as np
 import pytest
 
 from oracle import pdas_oracle as orc
-from tests.helpers import (RTOL, assert_same_support, golden_names, group_golden_names, load_golden, load_group_golden,
-                           load_pgs_golden, pgs_golden_names, rel_err)
+from tests.helpers import (RTOL, assert_same_support, golden_names, group_golden_names, hard_golden_names, load_golden,
+                           load_group_golden, load_hard_golden, load_pgs_golden, pgs_golden_names, rel_err)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -29,6 +29,34 @@ def test_oracle_matches_reference_golden(name):
         assert rel_err(out["loss_all"], g["loss_all"]) < RTOL
         assert out["l_all"].tolist() == g["l_all"].tolist()
     assert out["min_gap"] > 1e-9, "a top-k decision sits inside rounding noise"
+
+
+@pytest.mark.parametrize("name", hard_golden_names())
+def test_oracle_matches_reference_on_ties_and_correlated_designs(name):
+    """Duplicated columns (boundary ties at the first level past the true support and at the screening cut: the oracle
+    asks the compiled reference's max_k, utilities.cpp:179-188), rho = 0.5 / 0.9 and banded designs, 20 folds, max_iter 100."""
+    g = load_hard_golden(name)
+    seq = np.arange(1, g["smax"] + 1)
+    orc.TIES["count"] = orc.TIES["unresolved"] = 0
+    out = orc.bess_cpp(g["x"], g["y"], g["data_type"], g["weight"], True, g["model_type"], g["max_iter"], g["path_type"], True,
+                       g["ic_type"], g["is_cv"], g["K"], seq, 1, g["smax"], g["scr"] > 0, max(g["scr"], 1),
+                       fold_of_row=g["fold_of_row"])
+    assert_same_support(out["beta"], g["beta"])
+    assert rel_err(out["beta"], g["beta"]) < RTOL
+    assert abs(out["coef0"] - g["coef0"]) <= RTOL * max(1.0, abs(g["coef0"]))
+    assert abs(out["train_loss"] - g["train_loss"]) <= RTOL * abs(g["train_loss"])
+    assert abs(out["ic"] - g["ic"]) <= RTOL * abs(g["ic"])
+    if "screening_A" in g:
+        assert out["screening_A"].tolist() == g["screening_A"].tolist()
+    if "beta_all" in g:
+        for lvl in range(len(seq)):
+            assert_same_support(out["beta_all"][lvl], g["beta_all"][lvl])
+        assert rel_err(out["beta_all"], g["beta_all"]) < RTOL
+        assert out["l_all"].tolist() == g["l_all"].tolist()
+    if name.startswith("ties_"):
+        assert orc.TIES["count"] > 0 and orc.TIES["unresolved"] == 0  # the case does exercise the reference's tie rule
+    else:
+        assert orc.TIES["count"] == 0
 
 
 # poisson_seq_gic is left to the GPU suite: its IRLS fits run away to huge counts and take a minute in numpy

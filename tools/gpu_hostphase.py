@@ -49,9 +49,9 @@ def run(X, y, w, seq, n, p, fg):
         mhz = 1965.0
         own = dict(zip(("begin", "wait", "select", "load_cols", "gram", "solve", "resid_cycle", "publish"), [round(v / mhz, 1) for v in r[8:16]]))
         swp = dict(zip(("wait", "stream_x", "reduce_sacrifice"), [round(v / mhz, 1) for v in r[16:19]]))
-        print("  resident kernel (last call): launches", r[0], "iterations", r[1], "fallback selects", r[2], "steps", r[3], "merged level starts", r[4], "assemble us", round(r[19] / mhz, 1),
+        print("  resident kernel (last call): launches", r[0], "iterations", r[1], "fallback selects", r[2], "steps", r[3], "merged level starts", r[4], "| assemble, cand load, slots, scatter+cycle, bookkeeping us", [round(v / mhz, 1) for v in r[19:24]],
               "| owner 0 us by phase", own, "| sweeper 0 us", swp)
-        ow = np.array(r[24:88]).reshape(16, 4) / mhz
+        ow = np.array(r[24:152]).reshape(32, 4) / mhz
         print("  per owner: busy us", ow[:11, 0].round(0).tolist(), "| longest phase us", ow[:11, 1].round(1).tolist(),
               "| fallback us", ow[:11, 2].round(0).tolist(), "| fits solved", (ow[:11, 3] * mhz).round(0).tolist())
 
