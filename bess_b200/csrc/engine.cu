@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -388,6 +389,7 @@ struct Engine::Impl {
     double *lp_res_d = nullptr;
     unsigned long long *lp_dbg = nullptr;  // device [LP_NDBG]
     double *lp_R = nullptr;                // device [2][npad][MAXC] residual matrices of the two chain groups
+    unsigned long long *lp_trace = nullptr;  // device, only with $BESS_B200_TRACE: phase time stamps of the resident kernel
     double lp_counters[24] = {};
     double lp_owner[4 * MAXC] = {};
     // ---- per-category device timing (CUDA events on the engine stream), enabled by Engine::set_profiling
@@ -1275,6 +1277,12 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     m.loss_scratch = ar.alloc<double>((size_t)2 * MAXC * 2 * n);
     m.loss_out = ar.alloc<double>(2 * MAXC);
     if (m.lp_ok) {
+        if (std::getenv("BESS_B200_TRACE")) {
+            m.lp_trace = ar.alloc<unsigned long long>((size_t)(MAXC + 1) * LP_TRACE * 2);
+            CUDA_CHECK(cudaMemsetAsync(m.lp_trace, 0, (size_t)(MAXC + 1) * LP_TRACE * 2 * 8, m.st));
+        } else {
+            m.lp_trace = nullptr;
+        }
         m.lp_ns = lm_path_slots(d, max_iter);
         m.lp_res_count = (size_t)LP_MAXSTEP * MAXC * (2 + kcap);
         m.lp_sync = ar.alloc<unsigned>(2 * LP_SYNC_WORDS);
@@ -1392,6 +1400,7 @@ static void lp_launch(Engine::Impl &m, Engine::Impl::Ticket &t, const PathStep *
     L.res_i = m.lp_res_i + (size_t)t.slot * m.lp_res_count;
     L.res_d = m.lp_res_d + (size_t)t.slot * m.lp_res_count;
     L.dbg = m.lp_dbg;
+    L.trace = m.lp_trace;
     CUDA_CHECK(cudaMemsetAsync(L.sync, 0, LP_SYNC_WORDS * sizeof(unsigned), m.st));
     CUDA_CHECK(cudaMemsetAsync(m.lp_ncand, 0, MAXC * sizeof(int), m.st));
     const int sp = m.span_begin(4);
@@ -1437,6 +1446,19 @@ static void lp_parse(Engine::Impl &m, const Engine::Impl::Ticket &t, EngineStats
             stats.n_boundary_ties += ri[1];
         }
     }
+    if (m.lp_trace) {  // developer aid: time line of the owner phases and of sweeper 0 ($BESS_B200_TRACE = output file)
+        std::vector<unsigned long long> tr((size_t)(MAXC + 1) * LP_TRACE * 2);
+        CUDA_CHECK(cudaMemcpy(tr.data(), m.lp_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE *f = std::fopen(std::getenv("BESS_B200_TRACE"), "w")) {
+            for (int c2 = 0; c2 <= MAXC; c2++)
+                for (int q = 0; q < LP_TRACE; q++) {
+                    const unsigned long long a = tr[((size_t)c2 * LP_TRACE + q) * 2], b2 = tr[((size_t)c2 * LP_TRACE + q) * 2 + 1];
+                    if (a || b2) std::fprintf(f, "%d %d %llu %llu\n", c2, q, a, b2);
+                }
+            std::fclose(f);
+        }
+        CUDA_CHECK(cudaMemset(m.lp_trace, 0, tr.size() * 8));
+    }
     const double iters = (double)sy[LP_SYNC_ITERS];
     stats.n_sweeps += (long long)iters;
     stats.sweep_bytes += iters * (8.0 * d.n * d.p + 8.0 * d.n * nch + 8.0 * d.p * nch);
@@ -1451,7 +1473,8 @@ static void lp_parse(Engine::Impl &m, const Engine::Impl::Ticket &t, EngineStats
     const unsigned long long *dbg = c->h_lp_dbg + (size_t)t.slot * LP_NDBG;  // cumulative since setup_chains
     for (int q = 0; q < 8; q++) m.lp_counters[8 + q] = (double)dbg[q];
     for (int q = 0; q < 3; q++) m.lp_counters[16 + q] = (double)dbg[16 + q];
-    for (int q = 0; q < 5; q++) m.lp_counters[19 + q] = (double)dbg[8 + q];  // assemble, candidate load, slot assignment, scatter + cycle test, level bookkeeping
+    for (int q = 0; q < 5; q++) m.lp_counters[19 + q] = (double)dbg[8 + q];
+    for (int q = 0; q < 3; q++) m.lp_counters[5 + q] = (double)dbg[13 + q];  // DEBUG chol  // assemble, candidate load, slot assignment, scatter + cycle test, level bookkeeping
     for (int q = 0; q < 4 * MAXC; q++) m.lp_owner[q] = (double)dbg[32 + q];  // assembling the normal equations (part of `solve` when added to slot 13)
 }
 

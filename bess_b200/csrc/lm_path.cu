@@ -112,33 +112,46 @@ __device__ __forceinline__ unsigned long long lp_globaltimer()
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr unsigned long long LP_WATCHDOG_NS = 4000000000ull;  // a lost arrival becomes an error after 4 s
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// The CTA's writes so far (ordered before thread 0's release by the block barrier) become visible to whoever acquires
+// the counter afterwards.
 __device__ __forceinline__ void cta_arrive(unsigned *ctr)
 {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        red_release_add_u32(ctr, 1u);
-    }
+    if (threadIdx.x == 0) red_release_add_u32(ctr, 1u);
 }
-// returns false when the launch was aborted (by this or another CTA's watchdog)
-__device__ __forceinline__ bool cta_wait(unsigned *sync, int which, unsigned target, int *flag_sh)
+// Thread 0 polls up to three counters with RELAXED loads (an acquire load invalidates the L1 on every poll) and fences
+// once when all have reached their targets.  Returns false when the launch was aborted (by this or another CTA's watchdog).
+__device__ __forceinline__ bool cta_wait3(unsigned *sync, int w0, unsigned t0, int w1, unsigned t1, int w2, unsigned t2,
+                                          int *flag_sh)
 {
     if (threadIdx.x == 0) {
         int ok = 1;
         unsigned spins = 0;
-        unsigned long long t0 = 0;
-        while (ld_acquire_u32(sync + which) < target) {
+        unsigned long long ts = 0;
+        for (;;) {
+            const bool r0 = ld_relaxed_u32(sync + w0) >= t0;
+            const bool r1 = w1 < 0 || ld_relaxed_u32(sync + w1) >= t1;
+            const bool r2 = w2 < 0 || ld_relaxed_u32(sync + w2) >= t2;
+            if (r0 && r1 && r2) break;
             if ((++spins & 0x3ffu) == 0u) {
-                if (t0 == 0) t0 = lp_globaltimer();
-                if (ld_acquire_u32(sync + LP_SYNC_ABORT) != 0u || lp_globaltimer() - t0 > LP_WATCHDOG_NS) {
+                if (ts == 0) ts = lp_globaltimer();
+                if (ld_relaxed_u32(sync + LP_SYNC_ABORT) != 0u || lp_globaltimer() - ts > LP_WATCHDOG_NS) {
                     atomicExch(sync + LP_SYNC_ABORT, 1u);
                     ok = 0;
                     break;
                 }
             }
         }
-        if (ok && ld_acquire_u32(sync + LP_SYNC_ABORT) != 0u) ok = 0;
-        __threadfence();
+        if (ok && ld_relaxed_u32(sync + LP_SYNC_ABORT) != 0u) ok = 0;
+        fence_acq_rel_gpu();
         *flag_sh = ok;
     }
     __syncthreads();
@@ -146,23 +159,42 @@ __device__ __forceinline__ bool cta_wait(unsigned *sync, int which, unsigned tar
     __syncthreads();
     return ok;
 }
+__device__ __forceinline__ bool cta_wait(unsigned *sync, int which, unsigned target, int *flag_sh)
+{
+    return cta_wait3(sync, which, target, -1, 0u, -1, 0u, flag_sh);
+}
 
+// Phase timers of ONE thread (clock ticks).  The sums stay in that thread's registers and are flushed to global memory
+// once, when the CTA leaves -- a read-modify-write of global memory per mark stalls the timing warp (and everybody
+// behind the next barrier) for an L2 round trip, which at 13 marks per fit distorted what it measured.
+template <int NSLOT>
 struct Timer {
     long long t;
     bool on;
-    unsigned long long *dst;
-    __device__ __forceinline__ void start(bool enable, unsigned long long *d)
+    unsigned long long acc[NSLOT];
+    __device__ __forceinline__ void start(bool enable)
     {
         on = enable;
-        dst = d;
+#pragma unroll
+        for (int q = 0; q < NSLOT; q++) acc[q] = 0ull;
         if (on) t = clock64();
     }
     __device__ __forceinline__ void mark(int id)
     {
         if (on) {
             const long long now = clock64();
-            dst[id] += (unsigned long long)(now - t);
+            const unsigned long long dt = (unsigned long long)(now - t);
+#pragma unroll
+            for (int q = 0; q < NSLOT; q++)
+                if (q == id) acc[q] += dt;
             t = now;
+        }
+    }
+    __device__ __forceinline__ void flush(unsigned long long *dst)
+    {
+        if (on) {
+#pragma unroll
+            for (int q = 0; q < NSLOT; q++) dst[q] += acc[q];
         }
     }
 };
@@ -222,8 +254,8 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    Timer tm;
-    tm.start(tid == 0 && sidx == 0, L.dbg + 16);
+    Timer<3> tm;
+    tm.start(tid == 0 && sidx == 0);
     uint32_t parity = 0;
     // step s sweeps group g = s % ng for the r-th time (r = s / ng + 1) once that group's owners have finished their
     // phase r - 1.  Owner phase O_g(r) has index ng * r + g; LP_SYNC_TERM holds 1 + the index of the phase in which the
@@ -231,12 +263,13 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     for (unsigned st = 0;; st++) {
         const int g = (int)(st % (unsigned)L.ng);
         const unsigned r = st / (unsigned)L.ng + 1u;
-        if (!cta_wait(L.sync, LP_SYNC_B2 + g, (unsigned)L.gcount[g] * r, sm.flag)) return;
+        if (!cta_wait(L.sync, LP_SYNC_B2 + g, (unsigned)L.gcount[g] * r, sm.flag)) break;
         {
             const unsigned term = ld_acquire_u32(L.sync + LP_SYNC_TERM);
-            if (term != 0u && term - 1u <= st) return;
+            if (term != 0u && term - 1u <= st) break;
         }
         tm.mark(0);
+        if (L.trace && tid == 0 && sidx == 0 && st < LP_TRACE) L.trace[((size_t)MAXC * LP_TRACE + st) * 2] = lp_globaltimer();
         const double *Rsrc = L.Rg[g];
         const int nslot = L.gcount[g];
         if (Wp > 0) {
@@ -345,8 +378,10 @@ __device__ void sweeper_main(const Dev &d, const LpDesc &L, unsigned char *raw)
             }
             tm.mark(2);
         }
+        if (L.trace && tid == 0 && sidx == 0 && st < LP_TRACE) L.trace[((size_t)MAXC * LP_TRACE + st) * 2 + 1] = lp_globaltimer();
         cta_arrive(L.sync + LP_SYNC_B1 + g);  // its leading __syncthreads also protects the scratch from the next TMA copy
     }
+    tm.flush(L.dbg + 16);
 }
 
 // =====================================================================================================================
@@ -361,25 +396,29 @@ struct OwnSm {
     double *beta;  // [kcap]
     double *dg;    // [kcap+1]
     double *cv;    // [LP_CAP] candidate values
-    double *selv;  // [kcap+1] values by rank
+    double *selv;  // [2*kcap+8] candidate values by rank
+    double *bage;  // [kcap+1] solution in factor (age) order
     double *red;   // [40]
     int *ci;       // [LP_CAP]
     int *A, *slotA, *Anew, *slotNew, *newlist;  // [kcap]
-    int *seli;     // [kcap+1] indices by rank
+    int *seli;     // [2*kcap+8] candidate indices by rank
+    int *ord, *ordNew;  // [kcap] slot of the t-th column of the Cholesky factor (columns are kept in order of arrival)
+    int *pos;      // [ns] position of a slot's column in that order, -1 when the column is not part of the factor
+    int *freel;    // [ns] scratch: free slots
     int *slot_col, *keep;  // [ns]
     int *hist;     // [hist_rows][kcap]
     int *hbin;     // [256]
     int *misc;     // [16]
     int ldS;
 };
-enum { MI_FLAG = 0, MI_CNT = 1, MI_NNEW = 2, MI_SEEN = 3, MI_TIE = 4, MI_KREM = 5, MI_NEQ = 6, MI_COUNT = 7 };
+enum { MI_FLAG = 0, MI_CNT = 1, MI_NNEW = 2, MI_SEEN = 3, MI_TIE = 4, MI_KREM = 5, MI_NEQ = 6, MI_COUNT = 7, MI_Q = 8 };
 
 __host__ __device__ inline size_t owner_smem_bytes(int npad, int kcap, int ns, int hist_rows)
 {
     const int ldS = (kcap + 2) | 1;
     size_t dbl = (size_t)ns * npad + 3 * (size_t)npad + (size_t)ns * ns + ns + (size_t)(kcap + 1) * ldS + kcap + (kcap + 1) +
-                 LP_CAP + (kcap + 1) + 40 + 2 /* prefix/scratch */;
-    size_t ints = LP_CAP + 5 * (size_t)kcap + (kcap + 1) + 2 * (size_t)ns + (size_t)hist_rows * kcap + 256 + 16 + 64 /* scan */;
+                 LP_CAP + (2 * kcap + 8) + (kcap + 1) + 40 + 2 /* prefix/scratch */;
+    size_t ints = LP_CAP + 7 * (size_t)kcap + (2 * kcap + 8) + 4 * (size_t)ns + (size_t)hist_rows * kcap + 256 + 16 + 64 /* scan */;
     return dbl * 8 + ((ints + 1) & ~(size_t)1) * 4;
 }
 
@@ -399,7 +438,8 @@ __device__ __forceinline__ OwnSm carve_owner(unsigned char *raw, int npad, int k
     s.beta = p; p += kcap;
     s.dg = p; p += kcap + 1;
     s.cv = p; p += LP_CAP;
-    s.selv = p; p += kcap + 1;
+    s.selv = p; p += 2 * kcap + 8;
+    s.bage = p; p += kcap + 1;
     s.red = p; p += 40;
     *pre_out = p; p += 2;
     int *q = reinterpret_cast<int *>(p);
@@ -409,7 +449,11 @@ __device__ __forceinline__ OwnSm carve_owner(unsigned char *raw, int npad, int k
     s.Anew = q; q += kcap;
     s.slotNew = q; q += kcap;
     s.newlist = q; q += kcap;
-    s.seli = q; q += kcap + 1;
+    s.seli = q; q += 2 * kcap + 8;
+    s.ord = q; q += kcap;
+    s.ordNew = q; q += kcap;
+    s.pos = q; q += ns;
+    s.freel = q; q += ns;
     s.slot_col = q; q += ns;
     s.keep = q; q += ns;
     s.hist = q; q += (size_t)hist_rows * kcap;
@@ -460,6 +504,7 @@ __device__ void fallback_select(const double *bd, int p, int kk, OwnSm &s, int *
     const int tid = threadIdx.x;
     unsigned long long prefix = 0ull, mask = 0ull;
     int krem = kk, neq = p;
+    bool whole_bin = false;
     unsigned long long *pre_sh = reinterpret_cast<unsigned long long *>(s.red);  // red[0] as a 64-bit scratch word
     const bool inreg = p <= LP_NT * FB_PER;
     unsigned long long key[FB_PER];
@@ -520,6 +565,12 @@ __device__ void fallback_select(const double *bd, int p, int kk, OwnSm &s, int *
             mask |= 255ull << shift;
             __syncthreads();
             if (neq == krem) break;  // every key of the boundary bin is wanted: lower digits cannot change the set
+            if ((kk - krem) + neq <= LP_CAP / 2) {
+                // the keys above the bin plus the WHOLE bin fit the candidate list: hand them all over, the ranking that
+                // follows picks the exact winners (usually after two or three digits instead of eight)
+                whole_bin = true;
+                break;
+            }
         }
     } else {
         krem = p;  // kk == p: everything matches the empty prefix and is taken
@@ -527,6 +578,7 @@ __device__ void fallback_select(const double *bd, int p, int kk, OwnSm &s, int *
     }
     if (tid == 0) s.misc[MI_CNT] = 0;
     __syncthreads();
+    if (whole_bin) krem = neq;
     if (inreg && neq == krem) {
         // the usual case: the boundary bin is wanted as a whole
 #pragma unroll
@@ -572,29 +624,43 @@ __device__ void fallback_select(const double *bd, int p, int kk, OwnSm &s, int *
     __syncthreads();
 }
 
-// Rank `count` <= LP_CAP candidates (larger value first, lower index first -- a total order) and write the k best to
-// Anew in ascending index order.  MI_TIE <- the k-th and (k+1)-th values are equal (a boundary tie, utilities.cpp:179-188
-// leaves its resolution to std::nth_element).  *vk <- k-th value, *vdeep <- value of rank min(count, deep).
-__device__ void rank_select(OwnSm &s, int count, int k, int deep, double *vk, double *vdeep)
+// Rank the `count` <= LP_CAP candidates once (larger value first, lower index first -- a total order; the values are
+// non-negative doubles, so their bit patterns order like the values and the comparisons stay off the FP64 pipe) and file
+// the best 2 * kcap + 8 of them by rank: every select of this phase (the closing cycle test of a fit, then the first
+// iteration of the next path step) reads its winners, its boundary and its next threshold from that table.
+__device__ void rank_candidates(OwnSm &s, int count, int rmax)
 {
     const int tid = threadIdx.x;
-    const int dd = min(count, deep);
-    if (tid < count) {
-        const double v = s.cv[tid];
-        const int id = s.ci[tid];
-        int r = 0;
-        for (int u = 0; u < count; u++) {
-            const double vu = s.cv[u];
+    // P threads per candidate split the comparison loop (P = 4 while 4 * count fits the CTA): the loop is a chain of
+    // shared-memory loads and integer compares that a thread cannot overlap with anything, so its length is the cost
+    const int P = count * 4 <= LP_NT ? 4 : (count * 2 <= LP_NT ? 2 : 1);
+    const int t = tid / P, h = tid - t * P;
+    int r = 0;
+    unsigned long long v = 0ull;
+    int id = 0;
+    if (t < count) {
+        v = (unsigned long long)__double_as_longlong(s.cv[t]);
+        id = s.ci[t];
+        for (int u = h; u < count; u += P) {
+            const unsigned long long vu = (unsigned long long)__double_as_longlong(s.cv[u]);
             const int iu = s.ci[u];
             r += (vu > v) || (vu == v && iu < id);
         }
-        if (r <= k) {
-            s.seli[r] = id;
-            s.selv[r] = v;
-        }
-        if (r == dd - 1) s.red[1] = v;
+    }
+    // the P partial counts of a candidate sit in adjacent lanes of one warp (P divides 32)
+    if (P >= 2) r += __shfl_xor_sync(0xffffffffu, r, 1);
+    if (P >= 4) r += __shfl_xor_sync(0xffffffffu, r, 2);
+    if (t < count && h == 0 && r < rmax) {
+        s.seli[r] = id;
+        s.selv[r] = s.cv[t];
     }
     __syncthreads();
+}
+// The k best of the ranked candidates in ascending index order -> Anew.  MI_TIE <- the k-th and (k+1)-th values are equal
+// (a boundary tie: utilities.cpp:179-188 leaves its resolution to std::nth_element).  *vdeep <- value of rank min(count, deep).
+__device__ void pick_topk(OwnSm &s, int count, int k, int deep, double *vdeep)
+{
+    const int tid = threadIdx.x;
     if (tid < k) {
         const int id = s.seli[tid];
         int pos = 0;
@@ -602,8 +668,7 @@ __device__ void rank_select(OwnSm &s, int count, int k, int deep, double *vk, do
         s.Anew[pos] = id;
     }
     if (tid == 0) s.misc[MI_TIE] = (count > k && s.selv[k] == s.selv[k - 1]) ? 1 : 0;
-    *vk = s.selv[k - 1];
-    *vdeep = s.red[1];
+    *vdeep = s.selv[min(count, deep) - 1];
     __syncthreads();
 }
 
@@ -695,70 +760,156 @@ __device__ void gram_new(const Dev &d, OwnSm &s, int nnew, int ns, int npad)
     __syncthreads();
 }
 
-// Bordered Cholesky solve: rows 0..k-1 of S hold the SPD matrix (lower triangle used), row k the right-hand side;
-// beta <- S^{-1} rhs.  (The reference solves with colPivHouseholderQr, Algorithm.h:1134; on these SPD systems the
-// solutions agree to ~1e-13.)
-// k + 1 <= KB <= 24: one warp, lane i keeps row i in registers (statically indexed: the loops are fully unrolled), the
-// pivot and the column entries travel by shuffle -- no shared-memory round trip inside the factorisation.
-template <int KB>
-__device__ __noinline__ void chol_warp_reg(double *S, int ldS, double *dg, double *beta, int k)
+// Bordered Cholesky solve, incremental.  S (shared memory, row-major, leading dimension ldS) keeps the factor of the
+// previous fit: rows 0..q-1 (columns in order of arrival; a PDAS iteration typically appends or exchanges the youngest
+// columns) are still valid, dg[j] = 1 / L_jj.  Rows q..k-1 hold fresh Gram rows (lower triangle) and row k the right-hand
+// side X_A^T y; on return rows q..k hold L (row k: L^{-1} rhs) and out[0..k) the solution of the normal equations.
+// (The reference solves with colPivHouseholderQr, Algorithm.h:1134; on these SPD systems the solutions agree to ~1e-13.)
+//
+// All variants are compact rolled loops: a fully unrolled register version (one lane per row) was tried and lost -- 40 KB
+// of straight-line code executed once per fit by one warp is bound by instruction fetch, not by its dependency chain.
+__device__ unsigned long long g_dbg_chol[8];
+constexpr int CHOL_NR = 4;  // new rows (incl. the right-hand side) the append variant carries in registers
+
+// k <= 32 and k - q + 1 == NR <= CHOL_NR.  Lane c owns COLUMN c of the NR new rows (the last one is the right-hand side).
+// Per column j: the entries of the new rows at column j travel by shuffle, are scaled by 1 / L_jj (stored for an old
+// column, one rsqrt for a new one) and eliminated from the lanes to the right -- L_cj of an old row c comes from shared
+// memory, of a new row from the scaled values.  One warp runs this alone, so what counts is the number of dependent
+// instructions per column: NR is a template parameter (no run-time row selects), the old and the new columns have their
+// own loops, all addresses are hoisted.
+template <int NR>
+__device__ __forceinline__ void chol_append_warp(double *S, int ldS, double *dg, int k, int q)
 {
     const int lane = threadIdx.x & 31;
-    double row[KB];
+    double row[NR];
 #pragma unroll
-    for (int c = 0; c < KB; c++) row[c] = (lane <= k && c < k && c <= lane) ? S[lane * ldS + c] : 0.0;
+    for (int r = 0; r < NR; r++) row[r] = (lane < k && lane <= q + r) ? S[(q + r) * ldS + lane] : 0.0;
+    // ---- old columns: every new row lies below them
+    const double *Lc = S + lane * ldS;  // row `lane` of the old factor (lanes < q)
+    const bool old_lane = lane < q;
+    const int rl = lane - q;            // lanes >= q: the new row that sits at this column
+    for (int j = 0; j < q; j++) {
+        const double inv = dg[j];
+        double l[NR];
 #pragma unroll
-    for (int j = 0; j < KB; j++) {
-        if (j < k) {
-            const double piv = __shfl_sync(0xffffffffu, row[j], j);
-            const double inv = rsqrt(piv);
-            if (lane == 0) dg[j] = inv;
-            const double lij = row[j] * inv;  // lanes above j hold zeros here and stay zero
-            row[j] = lij;
+        for (int r = 0; r < NR; r++) l[r] = __shfl_sync(0xffffffffu, row[r], j) * inv;
+        double lcj = old_lane ? Lc[j] : 0.0;
 #pragma unroll
-            for (int c = 0; c < KB; c++) {  // constant bounds + guard: the unroller sees static register indices
-                if (c > j) {
-                    const double lcj = __shfl_sync(0xffffffffu, lij, c);
-                    if (c < k) row[c] = fma(-lij, lcj, row[c]);
-                }
-            }
+        for (int r = 0; r < NR - 1; r++)
+            if (rl == r) lcj = l[r];
+        if (lane == j) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) row[r] = l[r];
+        } else if (lane > j) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) row[r] = fma(-l[r], lcj, row[r]);
         }
     }
-    // L back to shared memory for the back substitution (lane c needs column c of L, i.e. another lane's registers)
+    // ---- new columns j = q + rj: pivot = diagonal entry of new row rj
 #pragma unroll
-    for (int c = 0; c < KB; c++)
-        if (lane <= k && c < k && c <= lane) S[lane * ldS + c] = row[c];
+    for (int rj = 0; rj < NR - 1; rj++) {
+        const int j = q + rj;
+        double l[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) l[r] = __shfl_sync(0xffffffffu, row[r], j);
+        const double inv = rsqrt(l[rj]);
+        if (lane == 0) dg[j] = inv;
+#pragma unroll
+        for (int r = 0; r < NR; r++) l[r] = r < rj ? 0.0 : l[r] * inv;  // rows above the diagonal are not part of L
+        double lcj = 0.0;
+#pragma unroll
+        for (int r = 0; r < NR - 1; r++)
+            if (rl == r) lcj = l[r];
+        if (lane == j) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) row[r] = l[r];
+        } else if (lane > j) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) row[r] = fma(-l[r], lcj, row[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+        if (lane < k && lane <= q + r) S[(q + r) * ldS + lane] = row[r];
     __syncwarp();
-    double z = lane < k ? S[k * ldS + lane] : 0.0;
-#pragma unroll
-    for (int j = KB - 1; j >= 0; j--) {
-        if (j < k) {
-            const double xj = __shfl_sync(0xffffffffu, z, j) * dg[j];
-            if (lane == j) z = xj;
-            if (lane < j) z = fma(-S[j * ldS + lane], xj, z);
-        }
-    }
-    if (lane < k) beta[lane] = z;
 }
 
-__device__ void chol_solve(OwnSm &s, int k)
+// k + 1 <= 32 rows: one warp, lane t owns ROW t (in shared memory), every row from q on is factored
+__device__ __forceinline__ void chol_rows_warp(double *S, int ldS, double *dg, int k, int q)
+{
+    const int lane = threadIdx.x & 31;
+    const bool mine = lane >= q && lane <= k;
+    for (int j = 0; j < k; j++) {
+        double inv;
+        if (j < q) {
+            inv = dg[j];
+        } else {
+            inv = rsqrt(S[j * ldS + j]);
+            if (lane == 0) dg[j] = inv;
+        }
+        double lij = 0.0;
+        if (mine && lane >= j) {
+            lij = S[lane * ldS + j] * inv;
+            S[lane * ldS + j] = lij;
+        }
+        __syncwarp();
+        if (mine && lane > j) {
+            const int cend = min(lane, k - 1);
+            for (int c = j + 1; c <= cend; c++) S[lane * ldS + c] = fma(-lij, S[c * ldS + j], S[lane * ldS + c]);
+        }
+        __syncwarp();
+    }
+}
+
+// L^T x = z (z = row k of S), lane c owns x_c; k <= 32
+__device__ __forceinline__ void chol_backsub_warp(const double *S, int ldS, const double *dg, double *out, int k)
+{
+    const int lane = threadIdx.x & 31;
+    double z = lane < k ? S[k * ldS + lane] : 0.0;
+    const double *Lj = S + (k - 1) * ldS + lane;  // L_jc for j = k-1, c = lane; one row up per step
+    for (int j = k - 1; j >= 0; j--, Lj -= ldS) {
+        const double xj = __shfl_sync(0xffffffffu, z, j) * dg[j];
+        const double ljc = lane < j ? *Lj : 0.0;
+        z = lane == j ? xj : fma(-ljc, xj, z);
+    }
+    if (lane < k) out[lane] = z;
+}
+
+__device__ void chol_solve(OwnSm &s, int k, int q)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ldS = s.ldS;
     double *S = s.S;
-    if (k + 1 <= 24) {  // (a 32-row instance does not fit the 128-register budget of a 512-thread CTA)
+    if (k <= 31) {
         if (wid == 0) {
-            if (k + 1 <= 8) chol_warp_reg<8>(S, ldS, s.dg, s.beta, k);
-            else if (k + 1 <= 16) chol_warp_reg<16>(S, ldS, s.dg, s.beta, k);
-            else chol_warp_reg<24>(S, ldS, s.dg, s.beta, k);
+            const long long t0 = clock64();
+            const int nr = k - q + 1;
+            if (nr == 2) chol_append_warp<2>(S, ldS, s.dg, k, q);
+            else if (nr == 3) chol_append_warp<3>(S, ldS, s.dg, k, q);
+            else if (nr == 4) chol_append_warp<4>(S, ldS, s.dg, k, q);
+            else chol_rows_warp(S, ldS, s.dg, k, q);
+            const long long t1 = clock64();
+            chol_backsub_warp(S, ldS, s.dg, s.bage, k);
+            const long long t2 = clock64();
+            if (lane == 0 && blockIdx.x == 0) {
+                g_dbg_chol[0] += (unsigned long long)(t1 - t0);
+                g_dbg_chol[1] += (unsigned long long)(t2 - t1);
+                g_dbg_chol[2] += 1ull;
+                g_dbg_chol[3] += (unsigned long long)k;
+            }
         }
         __syncthreads();
         return;
     }
+    // q == 0 here (the caller assembles every row for systems this large)
     for (int j = 0; j < k; j++) {
         __syncthreads();
         const double inv = rsqrt(S[j * ldS + j]);
-        if (tid == 0) s.dg[j] = inv;
+        __syncthreads();
+        if (tid == 0) {
+            s.dg[j] = inv;
+            S[j * ldS + j] *= inv;
+        }
         for (int i = j + 1 + tid; i <= k; i += LP_NT) S[i * ldS + j] *= inv;
         __syncthreads();
         for (int i = j + 1 + wid; i <= k; i += LP_NT / 32) {
@@ -769,13 +920,13 @@ __device__ void chol_solve(OwnSm &s, int k)
     }
     __syncthreads();
     if (wid == 0) {
-        for (int c = lane; c < k; c += 32) s.beta[c] = S[k * ldS + c];
+        for (int c = lane; c < k; c += 32) s.bage[c] = S[k * ldS + c];
         __syncwarp();
         for (int j = k - 1; j >= 0; j--) {
-            const double xj = s.beta[j] * s.dg[j];
+            const double xj = s.bage[j] * s.dg[j];
             __syncwarp();
-            if (lane == 0) s.beta[j] = xj;
-            for (int c = lane; c < j; c += 32) s.beta[c] -= S[j * ldS + c] * xj;
+            if (lane == 0) s.bage[j] = xj;
+            for (int c = lane; c < j; c += 32) s.bage[c] -= S[j * ldS + c] * xj;
             __syncwarp();
         }
     }
@@ -856,15 +1007,19 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     double *Rcol = L.Rg[g] + L.oslot[ci];
     const int *rows = d.rows + (size_t)c * n;
     double *bD = d.betaD + (size_t)c * d.pstride;
-    Timer tm;
-    tm.start(tid == 0 && ci == 0, L.dbg);
+    Timer<13> tm;
+    tm.start(tid == 0 && ci == 0);
+    unsigned long long own_busy = 0ull, own_max = 0ull, own_fb = 0ull, own_fits = 0ull;  // thread 0: flushed at exit
 
     // ---- phase O(0): Algorithm::fit prologue from the chain's stored state (Algorithm.h:141-148)
     for (int i = tid; i < npad; i += LP_NT) {
         s.m[i] = 0.0;
         s.y[i] = i < n ? L.y[i] : 0.0;
     }
-    for (int q = tid; q < ns; q += LP_NT) s.slot_col[q] = -1;
+    for (int q = tid; q < ns; q += LP_NT) {
+        s.slot_col[q] = -1;
+        s.pos[q] = -1;
+    }
     __syncthreads();
     for (int r = tid; r < nt; r += LP_NT) s.m[rows[r]] = 1.0;
     __syncthreads();
@@ -885,7 +1040,8 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     gather_new(d, s, ks, npad);
     gram_new(d, s, ks, ns, npad);
     int step = 0, T = L.T[0], l = 0, tie_acc = 0;
-    double lam = L.lam[0];
+    int kfac = 0;  // columns of the Cholesky factor in s.S that are valid (in the order s.ord)
+    double lam = L.lam[0], lam_fact = L.lam[0];
     for (int a = tid; a < T; a += LP_NT) s.hist[a] = 0;  // A_list.col(0) = 0 (Algorithm.h:143)
     double la = 0.0, lt = 0.0;
     residual(d, s, c, Rcol, L.fh, ks, nt, npad, false, &la, &lt);
@@ -902,16 +1058,18 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
     // seen every owner phase up to its decision index complete (its own group's phase it - 1 and the other group's phase
     // just before it), so the word can no longer change below that index: every CTA leaves at the same point.
     for (unsigned it = 1;; it++) {
-        if (!cta_wait(L.sync, LP_SYNC_B2 + g, (unsigned)L.gcount[g] * it, &s.misc[MI_FLAG])) return;
-        if (L.ng == 2 && !cta_wait(L.sync, LP_SYNC_B2 + og, (unsigned)L.gcount[og] * (g == 0 ? it - 1u : it), &s.misc[MI_FLAG]))
-            return;
+        if (!cta_wait3(L.sync, LP_SYNC_B2 + g, (unsigned)L.gcount[g] * it, L.ng == 2 ? LP_SYNC_B2 + og : -1,
+                       (unsigned)L.gcount[og] * (g == 0 ? it - 1u : it), -1, 0u, &s.misc[MI_FLAG]))
+            break;
         {
             const unsigned term = ld_acquire_u32(L.sync + LP_SYNC_TERM);
-            if (term != 0u && term - 1u <= (unsigned)L.ng * (it - 1u) + (unsigned)g) return;
+            if (term != 0u && term - 1u <= (unsigned)L.ng * (it - 1u) + (unsigned)g) break;
         }
-        if (!cta_wait(L.sync, LP_SYNC_B1 + g, (unsigned)L.nsweep * it, &s.misc[MI_FLAG])) return;
+        // (only now: once the last chain has finished, the sweepers leave and this counter never moves again)
+        if (!cta_wait(L.sync, LP_SYNC_B1 + g, (unsigned)L.nsweep * it, &s.misc[MI_FLAG])) break;
         tm.mark(1);
         const long long t_phase = clock64();
+        if (L.trace && tid == 0 && it < LP_TRACE) L.trace[((size_t)ci * LP_TRACE + it) * 2] = lp_globaltimer();
         if (!complete) {
             // ---- the candidates the sweepers published for this chain; the count and the (possibly stale) slots are
             // fetched together: one L2 round trip
@@ -931,7 +1089,8 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
             // One sweep can serve two fits: when a fit ends because its active set repeats the previous one, beta has not
             // moved since the sweep, and the first get_A of the NEXT path step (warm start, same ridge level) would
             // recompute exactly this sacrifice vector -- the owner selects again from the same candidates at once.
-            bool again = true;
+            bool again = true, ranked = false;
+            const int rmax = 2 * kcap + 8;
             while (again) {
                 again = false;
                 const int k = T;
@@ -942,13 +1101,18 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                     const long long t_fb = clock64();
                     fallback_select(d.bd + (size_t)c * d.pstride, p, deep, s, scan_sh);
                     count = min(s.misc[MI_CNT], LP_CAP);
+                    ranked = false;
                     if (tid == 0) {
                         atomicAdd(L.sync + LP_SYNC_FALLBACKS, 1u);
-                        L.dbg[32 + 4 * ci + 2] += (unsigned long long)(clock64() - t_fb);
+                        (void)t_fb;
                     }
                 }
-                double vk = 0.0, vdeep = 0.0;
-                rank_select(s, count, k, deep, &vk, &vdeep);
+                if (!ranked) {
+                    rank_candidates(s, count, rmax);
+                    ranked = true;
+                }
+                double vdeep = 0.0;
+                pick_topk(s, count, k, deep, &vdeep);
                 // candidate threshold of the next iteration: well below the `deep`-th largest sacrifice, so that the next
                 // level (k + 1) and moderately changed sacrifices still find their k winners in the list
                 tau = 0.7 * vdeep;
@@ -961,51 +1125,116 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                 same = __syncthreads_and(same);
                 bool seen = same != 0;
                 if (!same) {
-                    // ---- which of the selected columns are already resident; the others take the slots of columns not selected
-                    for (int q = tid; q < ns; q += LP_NT) s.keep[q] = 0;
+                    // ---- which of the selected columns are already resident
+                    for (int q2 = tid; q2 < ns; q2 += LP_NT) s.keep[q2] = 0;
                     __syncthreads();
                     if (tid < k) {
                         const int j = s.Anew[tid];
                         int sl = -1;
-                        for (int q = 0; q < ns; q++)
-                            if (s.slot_col[q] == j) sl = q;
+                        for (int q2 = 0; q2 < ns; q2++)
+                            if (s.slot_col[q2] == j) sl = q2;
                         s.slotNew[tid] = sl;
                         if (sl >= 0) s.keep[sl] = 1;
                     }
                     __syncthreads();
-                    if (tid == 0) {
-                        int nnew = 0, q = 0;
-                        // empty slots first, then the slots of columns that are not selected now
-                        for (int pass = 0; pass < 2; pass++) {
-                            q = 0;
-                            for (int a2 = 0; a2 < k; a2++) {
-                                if (s.slotNew[a2] >= 0) continue;
-                                while (q < ns && (s.keep[q] || (pass == 0 && s.slot_col[q] >= 0))) q++;
-                                if (q >= ns) break;
-                                s.slotNew[a2] = q;
-                                s.slot_col[q] = s.Anew[a2];
-                                s.keep[q] = 1;
-                                s.newlist[nnew++] = q;
+                    // ---- one warp, ballots instead of serial loops: (a) how much of the Cholesky factor survives -- its
+                    // columns are kept in order of arrival, the longest prefix whose columns are all still selected stays
+                    // valid; (b) the new column order: that prefix, the other survivors, the newcomers; (c) the newcomers
+                    // take free slots, empty ones first, then slots of columns that are not selected now
+                    if (wid == 0) {
+                        const unsigned lt = (1u << lane) - 1u;
+                        int q = kfac;
+                        for (int t0 = 0; t0 < kfac; t0 += 32) {
+                            const int t = t0 + lane;
+                            const bool okk = t < kfac && s.keep[s.ord[t]] != 0;
+                            const unsigned mk = __ballot_sync(0xffffffffu, okk || t >= kfac);
+                            if (mk != 0xffffffffu) {
+                                q = t0 + __ffs(~mk) - 1;
+                                break;
                             }
                         }
-                        s.misc[MI_NNEW] = nnew;
+                        if (lam != lam_fact || k > 31) q = 0;  // another ridge level / a system the CTA refactors as a whole
+                        for (int t = lane; t < q; t += 32) s.ordNew[t] = s.ord[t];
+                        int n_out = q;
+                        for (int t0 = q; t0 < kfac; t0 += 32) {
+                            const int t = t0 + lane;
+                            const bool okk = t < kfac && s.keep[s.ord[t]] != 0;
+                            const unsigned mk = __ballot_sync(0xffffffffu, okk);
+                            if (okk) s.ordNew[n_out + __popc(mk & lt)] = s.ord[t];
+                            n_out += __popc(mk);
+                        }
+                        // selected columns that are resident but not part of the factor (loaded by the prologue, or
+                        // dropped by an earlier fit and still cached in their slot)
+                        for (int a0 = 0; a0 < k; a0 += 32) {
+                            const int a2 = a0 + lane;
+                            const int sl = a2 < k ? s.slotNew[a2] : -1;
+                            const bool okk = sl >= 0 && (s.pos[sl] < 0 || s.pos[sl] >= kfac);
+                            const unsigned mk = __ballot_sync(0xffffffffu, okk);
+                            if (okk) s.ordNew[n_out + __popc(mk & lt)] = sl;
+                            n_out += __popc(mk);
+                        }
+                        int nfree = 0;
+                        for (int pass = 0; pass < 2; pass++)
+                            for (int q0 = 0; q0 < ns; q0 += 32) {
+                                const int sl = q0 + lane;
+                                const bool okk = sl < ns && s.keep[sl] == 0 && ((s.slot_col[sl] < 0) == (pass == 0));
+                                const unsigned mk = __ballot_sync(0xffffffffu, okk);
+                                if (okk) s.freel[nfree + __popc(mk & lt)] = sl;
+                                nfree += __popc(mk);
+                            }
+                        __syncwarp();
+                        int nnew = 0;
+                        for (int a0 = 0; a0 < k; a0 += 32) {
+                            const int a2 = a0 + lane;
+                            const bool need = a2 < k && s.slotNew[a2] < 0;
+                            const unsigned mk = __ballot_sync(0xffffffffu, need);
+                            if (need) {
+                                const int r2 = nnew + __popc(mk & lt);
+                                const int sl = s.freel[r2];
+                                s.slotNew[a2] = sl;
+                                s.slot_col[sl] = s.Anew[a2];
+                                s.newlist[r2] = sl;
+                                s.ordNew[n_out + r2] = sl;
+                            }
+                            nnew += __popc(mk);
+                        }
+                        __syncwarp();
+                        for (int sl = lane; sl < ns; sl += 32) s.pos[sl] = -1;
+                        __syncwarp();
+                        for (int t = lane; t < k; t += 32) {
+                            const int sl = s.ordNew[t];
+                            s.ord[t] = sl;
+                            s.pos[sl] = t;
+                        }
+                        if (lane == 0) {
+                            s.misc[MI_NNEW] = nnew;
+                            s.misc[MI_Q] = q;
+                        }
                     }
                     __syncthreads();
-                    const int nnew = s.misc[MI_NNEW];
+                    const int nnew = s.misc[MI_NNEW], q = s.misc[MI_Q];
                     tm.mark(10);
                     gather_new(d, s, nnew, npad);
                     tm.mark(3);
                     gram_new(d, s, nnew, ns, npad);
                     tm.mark(4);
-                    // ---- X_A^T X_A + lambda I | X_A^T y  (Algorithm.h:1134), solve
-                    for (int e = tid; e < (k + 1) * k; e += LP_NT) {
-                        const int a2 = e / k, b2 = e - a2 * k;
-                        s.S[a2 * s.ldS + b2] = a2 < k ? s.Gc[(size_t)s.slotNew[a2] * ns + s.slotNew[b2]] + (a2 == b2 ? lam : 0.0)
-                                                      : s.bc[s.slotNew[b2]];
+                    // ---- rows q..k-1 of X_A^T X_A + lambda I (Algorithm.h:1134) in factor order, X_A^T y as row k
+                    for (int e = tid; e < (k + 1 - q) * k; e += LP_NT) {
+                        const int t = q + e / k, u = e - (t - q) * k;
+                        if (t < k) {
+                            if (u <= t) s.S[t * s.ldS + u] = s.Gc[(size_t)s.ord[t] * ns + s.ord[u]] + (t == u ? lam : 0.0);
+                        } else {
+                            s.S[k * s.ldS + u] = s.bc[s.ord[u]];
+                        }
                     }
                     __syncthreads();
                     tm.mark(8);
-                    chol_solve(s, k);
+                    own_fb += (unsigned long long)(k - q) * 1965ull;  // DEBUG: new rows per fit (x1965 so the us conversion shows the count)
+                    chol_solve(s, k, q);
+                    kfac = k;
+                    lam_fact = lam;
+                    for (int a2 = tid; a2 < k; a2 += LP_NT) s.beta[a2] = s.bage[s.pos[s.slotNew[a2]]];  // back to ascending column order
+                    __syncthreads();
                     tm.mark(5);
                     // ---- scatter (Algorithm.h:159-163), cycle test against A_list[0..l] (Algorithm.h:164-170)
                     for (int a2 = tid; a2 < ks; a2 += LP_NT) __stcg(bD + s.A[a2], 0.0);
@@ -1029,7 +1258,7 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                     // the losses ride along with every residual: a fit that ends on a repeated set needs them without a pass
                     residual(d, s, c, Rcol, L.fh, ks, nt, npad, true, &la, &lt);
                     tm.mark(6);
-                    if (tid == 0) L.dbg[32 + 4 * ci + 3] += 1ull;
+                    own_fits += 1ull;
                 }
                 l += 1;
                 tie_acc += s.misc[MI_TIE];
@@ -1081,7 +1310,7 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                         for (int a2 = tid; a2 < T; a2 += LP_NT) s.hist[a2] = 0;
                         if (!d.warm) {
                             for (int a2 = tid; a2 < ks; a2 += LP_NT) __stcg(bD + s.A[a2], 0.0);
-                            ks = 0;
+                            ks = 0;  // (the factor stays: its leading columns are reused if the next fit selects them again)
                             residual(d, s, c, Rcol, L.fh, 0, nt, npad, true, &la, &lt);
                         } else if (same && lam == lam_prev) {
                             again = true;  // the sweep this phase consumed was computed from exactly the state the next step starts in
@@ -1101,11 +1330,24 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
         }
         if (tid == 0) {
             const unsigned long long dt = (unsigned long long)(clock64() - t_phase);
-            unsigned long long *od = L.dbg + 32 + 4 * ci;
-            od[0] += dt;
-            if (dt > od[1]) od[1] = dt;
+            own_busy += dt;
+            if (dt > own_max) own_max = dt;
+            if (L.trace && it < LP_TRACE) L.trace[((size_t)ci * LP_TRACE + it) * 2 + 1] = lp_globaltimer();
         }
         cta_arrive(L.sync + LP_SYNC_B2 + g);
+    }
+    tm.flush(L.dbg);
+    if (tid == 0 && ci == 0) {
+        L.dbg[13] = g_dbg_chol[0];
+        L.dbg[14] = g_dbg_chol[1];
+        L.dbg[15] = g_dbg_chol[3] * 1965ull / (g_dbg_chol[2] ? g_dbg_chol[2] : 1ull);
+    }
+    if (tid == 0) {
+        unsigned long long *od = L.dbg + 32 + 4 * ci;
+        od[0] += own_busy;
+        if (own_max > od[1]) od[1] = own_max;
+        od[2] += own_fb;
+        od[3] += own_fits;
     }
 }
 

@@ -11,6 +11,7 @@ constexpr int LP_CAP = 512;       // capacity of a chain's candidate list (== LP
 constexpr int LP_MAXSTEP = 64;    // path steps (sparsity level, ridge level) per launch
 constexpr int LP_WPMAX = 128;     // widest column slice of a sweeper CTA, in column pairs
 constexpr int LP_RPMAX = 32;      // most row phases of a sweeper CTA (bounds its serial partial reduction)
+constexpr int LP_TRACE = 128;     // phases recorded per CTA in LpDesc::trace
 constexpr int LP_KMAX = 64;       // largest support the in-kernel solver handles
 constexpr int LP_NDBG = 32 + 4 * MAXC;  // 0..15 owner 0 phases, 16..31 sweeper 0 phases, then 4 words per chain owner
 
@@ -51,6 +52,7 @@ struct LpDesc {
     int *res_i;            // [nsteps][nch][2 + kcap]: l, boundary ties, support
     double *res_d;         // [nsteps][nch][2 + kcap]: loss over all rows, loss over the chain's held-out rows, coefficients
     unsigned long long *dbg;  // [LP_NDBG] phase timers (clock ticks) of owner 0 and sweeper 0
+    unsigned long long *trace;  // optional [MAXC + 1][LP_TRACE][2] globaltimer stamps (start, end) of every owner phase / sweeper-0 step
 };
 
 // Can the resident kernel run this problem (family, shapes, shared-memory budget)?  `why` <- reason when not.

@@ -51,6 +51,7 @@ def run(X, y, w, seq, n, p, fg):
         swp = dict(zip(("wait", "stream_x", "reduce_sacrifice"), [round(v / mhz, 1) for v in r[16:19]]))
         print("  resident kernel (last call): launches", r[0], "iterations", r[1], "fallback selects", r[2], "steps", r[3], "merged level starts", r[4], "| assemble, cand load, slots, scatter+cycle, bookkeeping us", [round(v / mhz, 1) for v in r[19:24]],
               "| owner 0 us by phase", own, "| sweeper 0 us", swp)
+        print("  DEBUG chol: factor us (cumulative over calls)", round(r[5] / mhz, 1), "backsub us", round(r[6] / mhz, 1), "avg k", round(r[7] / mhz, 2))
         ow = np.array(r[24:152]).reshape(32, 4) / mhz
         print("  per owner: busy us", ow[:11, 0].round(0).tolist(), "| longest phase us", ow[:11, 1].round(1).tolist(),
               "| fallback us", ow[:11, 2].round(0).tolist(), "| fits solved", (ow[:11, 3] * mhz).round(0).tolist())
