@@ -28,7 +28,7 @@ def _check_common(j):
 
 
 def test_our_bench_line_single_gpu():
-    j = _latest("r01*_bench.json")
+    j = _latest("r0*_bench.json")
     _check_common(j)
     assert j["n_gpus"] == 1 and j["warmup"] >= 3 and j["gpu_launches"] > 0
     assert abs(j["value"] - 220 * 1e3 / j["ms_per_step"]) < 1e-6 * j["value"]  # 220 fits per step
@@ -46,7 +46,7 @@ def test_our_bench_line_single_gpu():
 
 def test_our_bench_lines_multi_gpu_are_weak_scaling_on_unique_fits():
     for n in (2, 4, 8):
-        j = _latest(f"r01*_bench_n{n}.json")
+        j = _latest(f"r0*_bench_n{n}.json")
         _check_common(j)
         assert j["n_gpus"] == n and j["scaling"] == "weak"
         assert j["fits_per_step"] == 20 * (1 + 10 * n)  # the full-data chain is counted once, not once per rank
@@ -65,3 +65,14 @@ def test_reference_arm_runs_here_and_keeps_the_contract():
     _check_common(j)
     assert j["impl"] == "reference" and j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
     assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1 and j["e2e"]["value"] == j["value"]
+
+
+def test_committed_reference_arm_line_ran_config_5_itself():
+    """The reference arm of the last GPU-box run (profiles/r0*_bench_ref.json): from round 2 on it times the reference on
+    config 5 itself (n=1000, p=500000, 220 fits per call), one call per process, not a proportional slice."""
+    j = _latest("r0*_bench_ref.json")
+    _check_common(j)
+    assert j["impl"] == "reference" and j["config"]["same_config_as_gpu_arm"] is True
+    assert "p=500000" in j["config"]["reference_sample"] and "s.list=1..20" in j["config"]["reference_sample"]
+    assert j["steps"] >= 1 and j["cpu_baseline"]["cores"] >= 1
+    assert abs(j["value"] - 220 * j["cpu_baseline"]["cores"] / j["cpu_baseline"]["seconds"]) < 1e-6 * j["value"]

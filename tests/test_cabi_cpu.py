@@ -298,3 +298,49 @@ def test_group_index_accepts_any_sortable_labels(monkeypatch):
     for labels in (["b", "a", "a", "c", "c", "b"], [1000003, 7, 7, -5, -5, 1000003], [0.5, 0.25, 0.25, 2.0, 2.0, 0.5]):
         lin.GroupPdasLm(sequence=[1]).fit(x, y, group=list(labels))
         assert seen["g"] == [0, 2, 4]
+
+
+EIGEN_INC = "/root/reference/python/include"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(EIGEN_INC, "Eigen")), reason="vendored Eigen of the reference not present")
+def test_bessCpp_eigen_adaptor_compiles_and_links_against_the_vendored_eigen(tmp_path):
+    """include/bess_b200_eigen.hpp: `bessCpp` with the reference's thirty by-value arguments (src/bess.h:20-33) and a
+    List-shaped result (src/List.h), header-only over bess_b200_fit.  Compiled here as C++11 against the reference's own
+    Eigen 3.3.4, linked against the library and run: without a GPU the call must fail loudly (std::runtime_error carrying
+    the library's message), never fall back to a CPU path."""
+    src = tmp_path / "client.cpp"
+    src.write_text(r'''
+#include <bess_b200_eigen.hpp>
+#include <cstdio>
+int main() {
+    const int n = 40, p = 12;
+    Eigen::MatrixXd x = Eigen::MatrixXd::Random(n, p);
+    Eigen::VectorXd y = x.col(0) * 2.0 + Eigen::VectorXd::Random(n) * 0.01, w = Eigen::VectorXd::Ones(n), state = Eigen::VectorXd::Ones(n);
+    Eigen::VectorXi seq(3); seq << 1, 2, 3;
+    Eigen::VectorXd lam(1); lam << 0.0;
+    Eigen::VectorXi g = Eigen::VectorXi::LinSpaced(p, 0, p - 1), always(0);
+    bess_b200::List r0;
+    Eigen::VectorXd z3 = Eigen::VectorXd::Zero(3), o2 = Eigen::VectorXd::Ones(2);
+    r0.add("beta", z3); r0.add("beta", o2); r0.add("ic", 1.5);
+    Eigen::VectorXd b; double ic = 0; r0.get_value_by_name("beta", b); r0.get_value_by_name("ic", ic);
+    if (b.size() != 2 || ic != 1.5 || r0.has("nope")) return 3;
+    try {
+        bess_b200::List r = bess_b200::bessCpp(x, y, 1, w, true, 1, 1, 20, 2, 1, true, 3, false, 5, state, seq, lam, 1, 3, 10, 10.0,
+                                               0.0, 0.0, 1, false, 1, 1, g, always, 1.1);
+        Eigen::VectorXd beta; r.get_value_by_name("beta", beta);
+        std::printf("fit ok nnz=%d\n", (int)(beta.array() != 0.0).count());
+    } catch (const std::runtime_error &e) {
+        std::printf("loud failure: %s\n", e.what());
+    }
+    return 0;
+}
+''')
+    exe = tmp_path / "client"
+    so_dir = os.path.join(ROOT, "bess_b200")
+    r = subprocess.run(["g++", "-std=c++11", "-O1", "-w", "-I", os.path.join(ROOT, "include"), "-I", EIGEN_INC, str(src), "-o", str(exe),
+                        "-L", so_dir, "-l:libbess_b200.so", "-Wl,-rpath," + so_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert ("fit ok" in run.stdout) or ("loud failure" in run.stdout and "bess_b200" in run.stdout), run.stdout
