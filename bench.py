@@ -248,6 +248,13 @@ def run_ours(args):
     w = np.ones(N_ROWS)
     seq = np.arange(1, SMAX + 1)
     lo, hi = (0, P_COLS) if world == 1 else bdist.shard_range(P_COLS, world, rank)
+    # N > 1: rank 0 first runs the SAME calls on the whole design on its own GPU -- the answers the column-sharded calls
+    # must reproduce (checked on the box, reported as parity_vs_single_gpu)
+    single = None
+    if world > 1 and rank == 0:
+        one = lambda scr: cbess.fit(None, y, 1, w, True, 1, 1, 20, 2, 1, True, 1, True, NFOLDS, seq, 1, SMAX, scr > 0, max(scr, 1),
+                                    cv_seed=123, device=local_rank, x_device_ptr=X.data_ptr(), n=N_ROWS, p=P_COLS, want_trace=False)
+        single = {"c5": one(SCREEN), "c5b": None if args.no_c5b else one(0)}
     Xs = X if world == 1 else X[:, lo:hi].contiguous()
     del X
     torch.cuda.empty_cache()
@@ -459,6 +466,20 @@ def run_ours(args):
                                                       "every rank; the PDAS path on the screened design is replicated"},
                        "c5b_no_screening_strong": c5b}
 
+    parity = None
+    if world > 1 and rank == 0:
+        def cmp(a, b):
+            sa, sb = np.nonzero(a["beta"])[0], np.nonzero(b["beta"])[0]
+            same = sa.tolist() == sb.tolist()
+            rel = float(np.max(np.abs(a["beta"][sb] - b["beta"][sb]) / np.abs(b["beta"][sb]))) if same and sb.size else None
+            return {"support_equal": bool(same), "chosen_s_equal": int(a["s"]) == int(b["s"]), "beta_max_rel_diff": rel,
+                    "ic_rel_diff": abs(a["ic"] - b["ic"]) / abs(b["ic"])}
+        parity = {"what": f"the column-sharded call on {world} GPUs against the same call on ONE GPU holding the whole design "
+                          "(same folds, cv_seed 123), computed on this box in this run",
+                  "c5_one_call": cmp(out_s, single["c5"]),
+                  "c5b_no_screening": cmp(ob, single["c5b"]) if (single["c5b"] is not None and c5b is not None) else None}
+        parity["ok"] = all(v is None or (v["support_equal"] and v["chosen_s_equal"] and v["beta_max_rel_diff"] <= 1e-9)
+                           for k2, v in parity.items() if k2 in ("c5_one_call", "c5b_no_screening"))
     base = cpu_baseline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     if rank == 0:
         line = {
@@ -496,6 +517,11 @@ def run_ours(args):
                          "kernel_share_of_step": float(total_kernel_ms / args.steps / (ms / args.steps)),
                          "p500k_pdas_sweep": probe},
             "cpu_baseline": base, "c5b_no_screening": c5b if world == 1 else None, "column_sharded": col_sharded,
+            # the strong-scaling curve of ONE call (columns sharded) starts here: N = 1 of column_sharded.c5_one_call_strong /
+            # c5b_no_screening_strong in the N > 1 lines
+            "strong_scaling_n1": {"c5_one_call_ms": ms / args.steps, "c5b_no_screening_ms": c5b["ms_per_call"] if c5b else None}
+            if world == 1 else None,
+            "parity_vs_single_gpu": parity,
             "fits_per_step": fits_per_step, "n_boundary_ties": int(st["n_boundary_ties"]),
             "host_ms_last_call": {k: round(float(v), 4) for k, v in st["host_ms"].items()},
         }

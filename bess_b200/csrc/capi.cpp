@@ -253,6 +253,27 @@ int bess_b200_gen_design(double *x_dev, int n, long long p, long long ld, double
     });
 }
 
+int bess_b200_gen_design_cortype(double *x_dev, int n, long long p, long long ld, double rho, unsigned long long seed, int cortype,
+                                 int device)
+{
+    return guarded([&] {
+        if (!x_dev || n < 1 || p < 1 || ld < p) throw EngineError{"gen_design: need a device buffer, n >= 1, 1 <= p <= ld"};
+        if (device >= 0 && cudaSetDevice(device) != cudaSuccess) throw EngineError{"gen_design: cudaSetDevice failed"};
+        double *scratch = nullptr;
+        if (cortype == 3 && cudaMalloc((void **)&scratch, (size_t)2 * p * sizeof(double)) != cudaSuccess)
+            throw EngineError{"gen_design: out of device memory"};
+        try {
+            launch_gen_design_cortype(x_dev, ld, n, p, rho, seed, cortype, scratch, nullptr);
+        } catch (...) {
+            cudaFree(scratch);
+            throw;
+        }
+        const cudaError_t e = cudaStreamSynchronize(nullptr);
+        cudaFree(scratch);
+        if (e != cudaSuccess) throw EngineError{std::string("gen_design: ") + cudaGetErrorString(e)};
+    });
+}
+
 int bess_b200_pgs_line_box(const double *p2, const double *u2, int s_min, int s_max, double log_lambda_min, double log_lambda_max,
                            double *a2_out, double *b2_out)
 {

@@ -1,4 +1,5 @@
-// Device-side design generator: the x of the reference's gen.data (R/R/gen.data.R:110-118, cortype 1) drawn directly
+// Device-side design generator: the x of the reference's gen.data (R/R/gen.data.R:110-118, cortype 1; cortype 2 and 3 at
+// the end of the file) drawn directly
 // in HBM, row-major n x p fp64 -- the layout pywrap_bess takes -- so a benchmark design never crosses PCIe.
 //   x_i ~ MVN(0, Sigma),  Sigma_jk = rho^|j-k|          (rho = 0, the default of gen.data: iid N(0,1))
 // A stationary AR(1) process along the columns has exactly that covariance:
@@ -97,6 +98,84 @@ void launch_gen_design(double *X, long long ld, int n, long long p, double rho, 
     const long long warps = (long long)n * nseg;
     gen_design_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(X, ld, n, p, rho, seed, seg, kwarm, nseg);
     CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- cortype 2 (R/R/gen.data.R:114-116): Sigma = rho + (1 - rho) I, i.e. one common factor per row:
+//   x_ij = sqrt(rho) * f_i + sqrt(1 - rho) * z_ij,  f_i = z_i,-1 (a column index no design column uses)
+__global__ void gen_design_exch_kernel(double *X, long long ld, int n, long long p, double rho, unsigned long long seed)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= p) return;
+    const double f = normal_at(seed, i, -1);
+    X[(size_t)i * ld + j] = sqrt(rho) * f + sqrt(1.0 - rho) * normal_at(seed, i, j);
+}
+
+// ---- cortype 3 (R/R/gen.data.R:167-181; the design of python/bess/gen_data.py:25-30): X iid N(0,1), columns centred and
+// scaled to norm sqrt(n), then x_j = X_j + rho (X_{j-1} + X_{j+1}) for 1 <= j <= p-2 and x_j = X_j at both ends.
+// Pass 1 (column statistics; thread per column, the rows of a warp's 32 columns are coalesced): mean, then the norm of
+// the centred column.  Pass 2 (one CTA per row, tiles left to right, IN PLACE): the left neighbour of a tile's first
+// column has already been overwritten by this CTA, so its normalised value is carried over; the right halo has not.
+__global__ void band_stats_kernel(const double *X, long long ld, int n, long long p, double *mean, double *scale)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += X[(size_t)i * ld + j];
+    const double mu = s / (double)n;
+    double q = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double t = X[(size_t)i * ld + j] - mu;
+        q = fma(t, t, q);
+    }
+    mean[j] = mu;
+    scale[j] = sqrt((double)n) / sqrt(q);
+}
+constexpr int BAND_TB = 1024;
+__global__ void __launch_bounds__(BAND_TB) band_mix_kernel(double *X, long long ld, long long p, double rho, const double *mean,
+                                                           const double *scale)
+{
+    __shared__ double t[BAND_TB + 2];
+    double *row = X + (size_t)blockIdx.x * ld;
+    const int tid = threadIdx.x;
+    double carry = 0.0;  // normalised value of the column left of the tile
+    for (long long j0 = 0; j0 < p; j0 += BAND_TB) {
+        const long long j = j0 + tid;
+        const double xn = j < p ? (row[j] - mean[j]) * scale[j] : 0.0;
+        t[tid + 1] = xn;
+        if (tid == 0) {
+            t[0] = carry;
+            const long long jr = j0 + BAND_TB;
+            t[BAND_TB + 1] = jr < p ? (row[jr] - mean[jr]) * scale[jr] : 0.0;
+        }
+        __syncthreads();
+        carry = t[BAND_TB];  // last column of this tile, before it is overwritten
+        if (j < p) row[j] = (j >= 1 && j <= p - 2) ? xn + rho * (t[tid] + t[tid + 2]) : xn;
+        __syncthreads();
+    }
+}
+
+// cortype 1: AR(1) covariance rho^|j-k| (launch_gen_design); 2: exchangeable; 3: banded.  scratch: 2 * p doubles (cortype 3).
+void launch_gen_design_cortype(double *X, long long ld, int n, long long p, double rho, unsigned long long seed, int cortype,
+                               double *scratch, cudaStream_t st)
+{
+    if (cortype == 1) {
+        launch_gen_design(X, ld, n, p, rho, seed, st);
+    } else if (cortype == 2) {
+        if (!(rho >= 0.0 && rho < 1.0)) throw EngineError{"gen_design: cortype 2 needs rho in [0, 1)"};
+        dim3 grid((unsigned)((p + 255) / 256), (unsigned)n);
+        gen_design_exch_kernel<<<grid, 256, 0, st>>>(X, ld, n, p, rho, seed);
+        CUDA_CHECK(cudaGetLastError());
+    } else if (cortype == 3) {
+        if (p < 3) throw EngineError{"gen_design: cortype 3 needs p >= 3"};
+        launch_gen_design(X, ld, n, p, 0.0, seed, st);
+        band_stats_kernel<<<(unsigned)((p + 127) / 128), 128, 0, st>>>(X, ld, n, p, scratch, scratch + p);
+        CUDA_CHECK(cudaGetLastError());
+        band_mix_kernel<<<(unsigned)n, BAND_TB, 0, st>>>(X, ld, p, rho, scratch, scratch + p);
+        CUDA_CHECK(cudaGetLastError());
+    } else {
+        throw EngineError{"gen_design: cortype must be 1, 2 or 3"};
+    }
 }
 
 }  // namespace bess

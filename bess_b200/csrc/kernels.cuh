@@ -172,6 +172,8 @@ void launch_screen_glm(const double *X, long long ldx, int n, int p, const doubl
                        double *util, cudaStream_t st);
 // device-side gen.data design (gen_design.cu): X[i][j], row-major n x p with leading dimension ld
 void launch_gen_design(double *X, long long ld, int n, long long p, double rho, unsigned long long seed, cudaStream_t st);
+void launch_gen_design_cortype(double *X, long long ld, int n, long long p, double rho, unsigned long long seed, int cortype,
+                               double *scratch, cudaStream_t st);
 size_t fit_smem_bytes(const Dev &d);
 int fit_smem_doubles(int ldA, int kcap);
 int chain_cluster_size(const Dev &d, int T, int nch);

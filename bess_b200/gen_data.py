@@ -111,7 +111,36 @@ def gen_data_reference(n, p, family, k, rho=0, sigma=1, beta=None, censoring=Tru
     raise ValueError("Family should be 'gaussian', 'binomial', 'possion', or 'cox'")
 
 
-def gen_design_device(n, p, rho=0.0, seed=1, device=0):
+def gen_response_device(X, family, k, seed=1, snr=10.0, scal=10.0, c=10.0):
+    """The y of ``gen.data`` for a design that lives in HBM (a ``torch`` tensor from ``gen_design_device``): only the k
+    active columns are touched -- gathered and multiplied on the device (``X[:, nonzero] @ beta``), n numbers come back --,
+    the draws of the noise / the response (n numbers) are numpy's.  Same recipe as ``gen_data`` above; for cox the caller
+    gets (time, status) and must sort the rows of X by time itself (a 4 GB row permutation is the caller's call).
+    Returns (y, beta_true, nonzero) and for cox ((time, status), beta_true, nonzero)."""
+    import torch
+    n, p = X.shape
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nonzero = np.sort(rng.choice(p, size=k, replace=False))
+    m = 5.0 * np.sqrt(2.0 * np.log(p) / n)
+    tb = rng.uniform(m, 100.0 * m, k) if family == "gaussian" else rng.uniform(2 * m, 10 * m, k)
+    eta = (X[:, torch.as_tensor(nonzero, device=X.device)] @ torch.as_tensor(tb, device=X.device)).cpu().numpy()
+    sigma = np.sqrt((tb @ tb) / snr)
+    if family == "gaussian":
+        return eta + rng.normal(0.0, sigma, n), tb, nonzero
+    if family == "binomial":
+        e = np.clip(eta + rng.normal(0.0, sigma, n), -30, 30)
+        return rng.binomial(1, np.exp(e) / (1 + np.exp(e))).astype(np.float64), tb, nonzero
+    if family == "poisson":
+        e = np.clip(eta + rng.normal(0.0, sigma, n), -30, 30)
+        return rng.poisson(np.exp(e)).astype(np.float64), tb, nonzero
+    if family == "cox":
+        time = (-np.log(rng.uniform(size=n)) / np.exp(eta)) ** (1.0 / scal)
+        ctime = c * rng.uniform(size=n)
+        return (np.minimum(time, ctime), (time < ctime).astype(np.float64)), tb, nonzero
+    raise ValueError("family should be 'gaussian', 'binomial', 'poisson' or 'cox'")
+
+
+def gen_design_device(n, p, rho=0.0, seed=1, device=0, cortype=1):
     """The x of ``gen.data`` (R/R/gen.data.R:110-118, cortype 1: rows ~ MVN(0, Sigma), Sigma_jk = rho^|j-k|) drawn on the
     GPU by the library's own kernel (``bess_b200_gen_design``): a row-major n x p fp64 ``torch`` tensor in HBM that can be
     handed to ``cbess.fit(..., x_device_ptr=X.data_ptr())`` -- torch only owns the memory."""
@@ -120,5 +149,8 @@ def gen_design_device(n, p, rho=0.0, seed=1, device=0):
     lib = _lib.load()
     _lib.require_gpu()
     X = torch.empty((n, p), dtype=torch.float64, device=f"cuda:{device}")
-    _lib.check(lib.bess_b200_gen_design(X.data_ptr(), int(n), int(p), int(p), float(rho), int(seed), int(device)))
+    # cortype 1: Sigma_jk = rho^|j-k|; 2: exchangeable rho + (1 - rho) I; 3: the banded design (gen.data cortype 3, the
+    # Python generator of the reference)
+    _lib.check(lib.bess_b200_gen_design_cortype(X.data_ptr(), int(n), int(p), int(p), float(rho), int(seed), int(cortype),
+                                                int(device)))
     return X

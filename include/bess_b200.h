@@ -123,6 +123,13 @@ int bess_b200_nccl_unique_id(void *out128);
  * Box-Muller), so x[i][j] is a pure function of (seed, i, j).  For benchmarks whose design must not cross PCIe. */
 int bess_b200_gen_design(double *x_dev, int n, long long p, long long ld, double rho, unsigned long long seed, int device);
 
+/* The same for every correlation type of gen.data (R/R/gen.data.R:110-118, 167-181): cortype 1 = the call above; 2 =
+ * exchangeable, Sigma = rho + (1 - rho) I (one common factor per row, rho in [0, 1)); 3 = the banded design of gen.data
+ * cortype 3 and of python/bess/gen_data.py:25-30 (iid columns centred and scaled to norm sqrt(n), then
+ * x_j = X_j + rho (X_{j-1} + X_{j+1}) inside, x_j = X_j at both ends). */
+int bess_b200_gen_design_cortype(double *x_dev, int n, long long p, long long ld, double rho, unsigned long long seed, int cortype,
+                                 int device);
+
 const char *bess_b200_last_error(void);
 int bess_b200_version(void);
 /* number of CUDA devices visible (0 = no GPU: every compute call will fail) */

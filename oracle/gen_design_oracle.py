@@ -55,3 +55,19 @@ def design(n, p, rho=0.0, seed=1):
         prev = rho * prev + s * z[:, t]
         x[:, t] = prev
     return x[:, warm:]
+
+
+def design_cortype(n, p, rho, seed, cortype):
+    """gen_design.cu launch_gen_design_cortype: 1 = design(); 2 = exchangeable (R/R/gen.data.R:114-116), common factor
+    z_i,-1; 3 = the banded design (gen.data.R:167-181, python/bess/gen_data.py:25-30) on the iid stream."""
+    if cortype == 1:
+        return design(n, p, rho, seed)
+    ii = np.arange(n, dtype=np.int64)[:, None]
+    if cortype == 2:
+        f = normal_at(seed, ii, np.full((1, 1), -1, dtype=np.int64))
+        return math.sqrt(rho) * f + math.sqrt(1.0 - rho) * normal_at(seed, ii, np.arange(p, dtype=np.int64)[None, :])
+    X = design(n, p, 0.0, seed)
+    X = X - X.mean(axis=0, keepdims=True)
+    X = math.sqrt(n) * X / np.sqrt((X ** 2).sum(axis=0, keepdims=True))
+    zero = np.zeros((n, 1))
+    return X + rho * (np.hstack((zero, X[:, 0:(p - 2)], zero)) + np.hstack((zero, X[:, 2:p], zero)))

@@ -61,3 +61,44 @@ def test_device_design_distribution_and_use():
     out = cbess.fit(None, y, 1, np.ones(n), True, 1, 1, 20, 2, 1, True, 3, False, 5, [1, 2, 3, 4], 1, 4, True, 2000,
                     x_device_ptr=X.data_ptr(), n=n, p=p, want_trace=False)
     assert set(nz.tolist()) <= set(np.nonzero(out["beta"])[0].tolist())
+
+
+@pytest.mark.parametrize("cortype,rho", [(2, 0.4), (3, 0.5)])
+def test_oracle_cortype_2_and_3_have_the_gen_data_structure(cortype, rho):
+    """cortype 2 (R/R/gen.data.R:114-116): every pair of columns correlates rho.  cortype 3 (gen.data.R:167-181,
+    python/bess/gen_data.py:25-30): neighbours 2 rho / (1 + 2 rho^2), second neighbours rho^2 / (1 + 2 rho^2), none beyond."""
+    x = gd.design_cortype(400, 1500, rho, 7, cortype)
+    c = np.corrcoef(x, rowvar=False)
+    if cortype == 2:
+        off = c[np.triu_indices(1500, 1)]
+        assert abs(off.mean() - rho) < 0.05 and abs(x.std() - 1.0) < 0.05  # 400 draws of the common factor
+    else:
+        d1, d2, d3 = np.diag(c, 1)[1:-1], np.diag(c, 2)[1:-1], np.diag(c, 3)
+        assert abs(d1.mean() - 2 * rho / (1 + 2 * rho ** 2)) < 0.02
+        assert abs(d2.mean() - rho ** 2 / (1 + 2 * rho ** 2)) < 0.02 and abs(d3.mean()) < 0.02
+        assert np.allclose(x[:, 0].std(), 1.0, atol=1e-9)  # the edge columns are the normalised X itself
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p,rho,cortype", [(40, 3000, 0.3, 2), (33, 2500, 0.5, 3), (17, 5, 0.25, 3), (64, 1025, 0.5, 3)])
+def test_device_cortype_2_and_3_match_the_restatement(n, p, rho, cortype):
+    from bess_b200.gen_data import gen_design_device
+    x = gen_design_device(n, p, rho, seed=99, cortype=cortype).cpu().numpy()
+    ref = gd.design_cortype(n, p, rho, 99, cortype)
+    assert np.max(np.abs(x - ref)) < 1e-10
+
+
+@pytest.mark.gpu
+def test_device_response_recipe_feeds_a_fit():
+    """gen_response_device: the y of gen.data from a design that never leaves HBM (only the k active columns are read)."""
+    from bess_b200 import cbess
+    from bess_b200.gen_data import gen_design_device, gen_response_device
+    n, p = 400, 60000
+    X = gen_design_device(n, p, 0.5, seed=3, cortype=3)
+    for fam, (mt, dt) in {"gaussian": (1, 1), "binomial": (2, 2), "poisson": (3, 2)}.items():
+        Xf = X / 16.0 if fam == "poisson" else X
+        y, tb, nz = gen_response_device(Xf, fam, 5, seed=17)
+        out = cbess.fit(None, y, dt, np.ones(n), True, 1, mt, 20, 2, 1, True, 3, False, 5, [1, 2, 3, 4, 5, 6], 1, 6, True, 3000,
+                        x_device_ptr=Xf.data_ptr(), n=n, p=p, want_trace=False)
+        got = set(np.nonzero(out["beta"])[0].tolist())
+        assert len(got & set(nz.tolist())) >= 3, (fam, sorted(got), nz.tolist())
