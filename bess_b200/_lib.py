@@ -77,6 +77,8 @@ def load():
     lib.bess_b200_trace_lambda.argtypes = [dp]
     lib.bess_b200_pgs_line_box.argtypes = [dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
     lib.bess_b200_gen_design.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_double, C.c_ulonglong, C.c_int]
+    lib.bess_b200_gen_design_cortype.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_double, C.c_ulonglong, C.c_int,
+                                                 C.c_int]
     lib.bess_b200_merge_candidates.argtypes = [dp, ip, C.c_int, C.c_int, ip]
     _lib = lib
     return lib
