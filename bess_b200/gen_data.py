@@ -127,11 +127,13 @@ def gen_response_device(X, family, k, seed=1, snr=10.0, scal=10.0, c=10.0):
     sigma = np.sqrt((tb @ tb) / snr)
     if family == "gaussian":
         return eta + rng.normal(0.0, sigma, n), tb, nonzero
+    # binomial / poisson: the linear predictor carries no noise term (python/bess/gen_data.py:44-73); the caller scales a
+    # poisson design by 1/16 first, as the reference does
     if family == "binomial":
-        e = np.clip(eta + rng.normal(0.0, sigma, n), -30, 30)
+        e = np.clip(eta, -30, 30)
         return rng.binomial(1, np.exp(e) / (1 + np.exp(e))).astype(np.float64), tb, nonzero
     if family == "poisson":
-        e = np.clip(eta + rng.normal(0.0, sigma, n), -30, 30)
+        e = np.clip(eta, -30, 30)
         return rng.poisson(np.exp(e)).astype(np.float64), tb, nonzero
     if family == "cox":
         time = (-np.log(rng.uniform(size=n)) / np.exp(eta)) ** (1.0 / scal)
