@@ -460,6 +460,16 @@ int bess_b200_debug_get(unsigned long long *out32)
 {
     return guarded([&] { debug_get(out32); });
 }
+// probes of the chain kernels' building blocks (tools / tests; not part of the public header)
+int bess_b200_debug_gram(const double *V, int ldv, int nrows, int mm, const double *wt, double *S_out, int impl, int reps,
+                         double *ticks_out)
+{
+    return guarded([&] { debug_gram(V, ldv, nrows, mm, wt, S_out, impl, reps, ticks_out); });
+}
+int bess_b200_debug_solve(const double *S, int lds, int mm, double *x_out, int impl, int reps, double *ticks_out)
+{
+    return guarded([&] { debug_solve(S, lds, mm, x_out, impl, reps, ticks_out); });
+}
 
 // ---- multi-GPU host helpers ------------------------------------------------------------------------------------------
 void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi)

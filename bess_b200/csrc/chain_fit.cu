@@ -42,6 +42,30 @@ struct FitSmem {
     int arena_len;    // doubles from `tile` to the end of the dynamic shared memory
 };
 constexpr int FIT_ARENA_MIN = FIT_TILE_DOUBLES + FIT_NT * 16 + FIT_SMEM_MS * FIT_SMEM_MS;
+// The FitSmem pointers travel through structs, references and (for the big solvers) real calls, where the compiler's
+// address-space inference loses track of them and falls back to GENERIC loads / stores (LD.E / ST.E, 64-bit address
+// arithmetic, no LDS.128) -- the hot loops re-derive them from the kernel's dynamic shared array with as_shared().
+__device__ __forceinline__ double *as_shared(const double *p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *const sbase = reinterpret_cast<double *>(smem_raw);
+    return sbase + (p - sbase);
+}
+__device__ __forceinline__ FitSmem sm_shared(const FitSmem &a)
+{
+    FitSmem s;
+    s.b0 = as_shared(a.b0);
+    s.b1 = as_shared(a.b1);
+    s.rhs = as_shared(a.rhs);
+    s.dg = as_shared(a.dg);
+    s.red = as_shared(a.red);
+    s.xch = as_shared(a.xch);
+    s.tile = as_shared(a.tile);
+    s.scratch = as_shared(a.scratch);
+    s.Ssm = as_shared(a.Ssm);
+    s.arena_len = a.arena_len;
+    return s;
+}
 __device__ __forceinline__ FitSmem carve_fit_smem(unsigned char *raw, int ldA, int total_doubles)
 {
     FitSmem s;
@@ -164,15 +188,17 @@ __device__ __forceinline__ double *cw_slot(const ChainCtx &cx, int rank, int s) 
 // Gram: S (mm x mm, both triangles) = sum_{r in [r0,r1)} wt[r] * V[r][a] * V[r][b]; V row-major, ld ldv, global memory
 // =====================================================================================================
 __device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
-                           const FitSmem &sm)
+                           const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
     const int tid = threadIdx.x;
     const int mb = (mm + 3) >> 2, mp = mb * 4;
     const int nblk = mb * (mb + 1) / 2;
     int R = FIT_TILE_DOUBLES / (mp + 1);
     if (R > 512) R = 512;
-    double *tile = sm.tile;
-    double *tw = sm.tile + (size_t)R * mp;
+    double *tile = as_shared(sm.tile);
+    double *tw = tile + (size_t)R * mp;
+    double *scratch = as_shared(sm.scratch);
     const int nsl = nblk >= FIT_NT ? 1 : FIT_NT / nblk;
     const int nbatch = nsl > 1 ? 1 : (nblk + FIT_NT - 1) / FIT_NT;
     for (int batch = 0; batch < nbatch; batch++) {
@@ -219,13 +245,13 @@ __device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, con
             // and the staging of tile t+1 (cp.async, 16-byte chunks, no register round trip) overlaps the FMAs of tile t.
             // Columns in [mm, mp) receive whatever follows in the row (or stale shared memory past the row end): they only
             // feed accumulators that are never stored.
-            double *buf[2] = {sm.tile, sm.scratch};
+            double *const buf0 = as_shared(sm.tile), *const buf1 = as_shared(sm.scratch);
             const int ntile = (r1 - r0 + R - 1) / R;
             const int cpr = mp >> 1;  // 16-byte chunks per row
             auto issue = [&](int t) {
                 const int rb = r0 + t * R;
                 const int rc = min(R, r1 - rb);
-                double *dst = buf[t & 1];
+                double *dst = (t & 1) ? buf1 : buf0;
                 for (int e = tid; e < rc * cpr; e += FIT_NT) {
                     const int r = e / cpr, cidx = (e - r * cpr) * 2;
                     if (cidx < ldv) __pipeline_memcpy_async(dst + r * mp + cidx, V + (size_t)(rb + r) * ldv + cidx, 16);
@@ -244,7 +270,7 @@ __device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, con
                     __pipeline_wait_prior(0);
                 }
                 __syncthreads();
-                if (valid) fma_rows(buf[t & 1], buf[t & 1] + (size_t)R * mp, min(R, r1 - (r0 + t * R)));
+                if (valid) fma_rows((t & 1) ? buf1 : buf0, ((t & 1) ? buf1 : buf0) + (size_t)R * mp, min(R, r1 - (r0 + t * R)));
                 __syncthreads();
             }
         } else {
@@ -279,13 +305,13 @@ __device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, con
             __syncthreads();
             if (valid) {
 #pragma unroll
-                for (int e = 0; e < 16; e++) sm.scratch[(size_t)(sl * nblk + blk) * 16 + e] = acc[e];
+                for (int e = 0; e < 16; e++) scratch[(size_t)(sl * nblk + blk) * 16 + e] = acc[e];
             }
             __syncthreads();
             for (int idx = tid; idx < nblk * 16; idx += FIT_NT) {
                 const int bk = idx >> 4, e = idx & 15;
                 double v = 0.0;
-                for (int q = 0; q < nsl; q++) v += sm.scratch[(size_t)(q * nblk + bk) * 16 + e];
+                for (int q = 0; q < nsl; q++) v += scratch[(size_t)(q * nblk + bk) * 16 + e];
                 int ci = (int)((sqrt(8.0 * (double)bk + 1.0) - 1.0) * 0.5);
                 while ((ci + 1) * (ci + 2) / 2 <= bk) ci++;
                 while (ci * (ci + 1) / 2 > bk) ci--;
@@ -325,8 +351,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
                  : "d"(a), "d"(b));
 }
 __device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
-                                const FitSmem &sm)
+                                const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
     constexpr int NTN = 2;  // warp block = 32 rows x 16 columns: 4 x 2 mma tiles, 16 accumulators per thread
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int mp = ((mm + 3) >> 2) << 2;
@@ -334,7 +361,7 @@ __device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm
     const int nb = (mm + 31) >> 5;                // 32-row block rows; block row bi has 2*bi + 2 column blocks of 16
     const int nblk = nb * (nb + 1);
     const int R = (FIT_TILE_DOUBLES / (ts + 1)) & ~3;  // rows per tile, multiple of the mma k
-    double *buf[2] = {sm.tile, sm.scratch};
+    double *const buf0 = as_shared(sm.tile), *const buf1 = as_shared(sm.scratch);
     const int ntile = (r1 - r0 + R - 1) / R;
     const int cpr = mp >> 1;  // 16-byte chunks per row
     const int g = lane >> 2, t4 = lane & 3;
@@ -358,7 +385,7 @@ __device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm
             if (t < ntile) {  // stage tile t (cp.async, 16-byte chunks) into buf[t & 1]
                 const int rb = r0 + t * R;
                 const int rc = min(R, r1 - rb);
-                double *dst = buf[t & 1];
+                double *dst = (t & 1) ? buf1 : buf0;
                 for (int e = tid; e < rc * cpr; e += FIT_NT) {
                     const int r = e / cpr, cidx = (e - r * cpr) * 2;
                     if (cidx < ldv) __pipeline_memcpy_async(dst + r * ts + cidx, V + (size_t)(rb + r) * ldv + cidx, 16);
@@ -375,7 +402,7 @@ __device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm
             __pipeline_wait_prior(1);
             __syncthreads();
             if (valid) {
-                const double *tl = buf[(t - 1) & 1];
+                const double *tl = ((t - 1) & 1) ? buf1 : buf0;
                 const double *twt = tl + (size_t)R * ts;
                 const int rc4 = (min(R, r1 - (r0 + (t - 1) * R)) + 3) & ~3;
                 const double *pa = tl + t4 * ts + bi * 32 + g;
@@ -414,8 +441,9 @@ __device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm
 }
 // dispatcher: tensor cores when the system is wide, register-blocked FMAs otherwise
 __device__ __forceinline__ void gram(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
-                                     const FitSmem &sm)
+                                     const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
     if (mm > 96) block_syrk_dmma(V, ldv, r0, r1, mm, wt, S, lds, sm);
     else block_syrk(V, ldv, r0, r1, mm, wt, S, lds, sm);
 }
@@ -500,8 +528,9 @@ __device__ __forceinline__ void panel_factor(RowPtr rowp, int mr, int nb, double
 // panels (panel_factor + register-blocked 4x4 trailing update) and back-substituted in place.  x (smem) <- solution.
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 __device__ __forceinline__ bool packed_fits(int mm, int arena_len) { return tri(mm + 1) + FIT_NT <= arena_len; }
-__device__ void chol_packed_smem(const double *Sg, int lds, int mm, double *x, const FitSmem &sm, PhaseTimer &pt)
+__device__ void chol_packed_smem(const double *Sg, int lds, int mm, double *x, const FitSmem &sm_, PhaseTimer &pt)
 {
+    const FitSmem sm = sm_shared(sm_);
     constexpr int NB = CHOL_NB;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *Lp = sm.tile;                 // packed: row i at tri(i), columns 0..min(i, mm-1)
@@ -606,6 +635,366 @@ __device__ void chol_packed_smem(const double *Sg, int lds, int mm, double *x, c
     pt.mark(12);
 }
 
+// =====================================================================================================
+// Panel-major Cholesky: the solver of the wide systems (65 .. 511 unknowns; C2: every IRLS step factors a ~200 x 200
+// Hessian).  One CTA, the matrix in shared memory in PANEL-MAJOR storage: panel pb holds columns [16 pb, 16 pb + 16) for
+// the rows from its own first column down to the border row mm, COLUMN-major inside the panel with a leading dimension
+// == 4 (mod 8) doubles.  That layout makes every access of the factorisation conflict-free:
+//   * panel factor: thread i owns panel row i, a column is contiguous over the threads;
+//   * trailing update on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA): an A / B fragment is 8 consecutive rows
+//     x 4 consecutive panel columns -- 8 contiguous doubles per column, the four columns 4 (mod 8) doubles apart, i.e.
+//     two shared-memory wavefronts, the minimum for 256 bytes; a warp owns a 32 x 16 block of the trailing matrix
+//     (8 accumulator tiles), 6 loads per 8 DMMAs.  (The packed row-major layout this replaces had every lane of a warp
+//     in a different row at an irregular offset: 4-8-way bank conflicts, 137 us per factorisation at 200 unknowns.)
+//   * back substitution: warp q reduces panel column q against x with contiguous loads.
+// Systems that do not fit the arena (~225 unknowns at 227 KB) run in STAGES: as many leading panels as fit are factored in
+// shared memory at their full height, the Schur complement of the remaining columns is updated in place in the global
+// matrix by DMMA blocks with the stage as the k dimension, the factored panels are written back, and the next stage loads
+// what is left; the back substitution reloads the stages in reverse order.
+// =====================================================================================================
+constexpr int PNB = 16;
+constexpr int PM_MAX_STAGES = 12;
+__device__ int g_dbg_solver = 0;  // debug knob (bess_b200_debug_set key 4): 1 = the round-1 solvers (packed / cluster-blocked)
+__device__ __forceinline__ int pm_ld(int h) { return (((h + 3) >> 3) << 3) + 4; }  // >= h and == 4 (mod 8)
+// number of 16-column panels from column c0 on (at their full height mm + 1 - c) that fit `cap` doubles
+__device__ __forceinline__ int pm_plan(int c0, int mm, int cap)
+{
+    int used = 0, np = 0;
+    for (int c = c0; c < mm; c += PNB) {
+        const int need = PNB * pm_ld(mm + 1 - c);
+        if (used + need > cap) break;
+        used += need;
+        np++;
+    }
+    return np;
+}
+__device__ __forceinline__ int pm_capacity(int arena_len) { return arena_len - 64; }  // panel offsets in front, slack behind
+__device__ __forceinline__ int pm_stage_count(int mm, int arena_len)
+{
+    const int cap = pm_capacity(arena_len);
+    int ns = 0;
+    for (int c0 = 0; c0 < mm;) {
+        const int np = pm_plan(c0, mm, cap);
+        if (np == 0) return PM_MAX_STAGES + 1;
+        c0 += np * PNB;
+        ns++;
+    }
+    return ns;
+}
+// poff[pb] = offset of panel pb of the stage that starts at column c0
+__device__ __forceinline__ void pm_offsets(int *poff, int mm, int c0, int np)
+{
+    __syncthreads();
+    if ((int)threadIdx.x < np) {
+        int off = 0;
+        for (int q = 0; q < (int)threadIdx.x; q++) off += PNB * pm_ld(mm + 1 - (c0 + q * PNB));
+        poff[threadIdx.x] = off;
+    }
+    __syncthreads();
+}
+// global (row-major, lower triangle) -> panels.  A warp moves 4-row x 8-column patches: 64-byte row segments on the
+// global side, 16 distinct banks x 2 on the shared side.  Columns past the last one are zero-filled.
+template <bool TO_GLOBAL>
+__device__ void pm_copy(double *L, const int *poff, double *Sg, int lds, int mm, int c0, int np)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int il = lane >> 3, cl = lane & 7;
+    constexpr int NW = FIT_NT / 32;
+    for (int pb = 0; pb < np; pb++) {
+        const int r0 = c0 + pb * PNB;
+        const int h = mm + 1 - r0, ld = pm_ld(h);
+        const int nb = min(PNB, mm - r0);
+        double *P = L + poff[pb];
+        const int npatch = 2 * ((h + 3) >> 2);
+        if (TO_GLOBAL) {
+            for (int pa = wid; pa < npatch; pa += NW) {
+                const int i = (pa >> 1) * 4 + il, c = (pa & 1) * 8 + cl;
+                if (i < h && c < nb && c <= i) Sg[(size_t)(r0 + i) * lds + r0 + c] = P[c * ld + i];
+            }
+        } else {
+            for (int pa0 = wid; pa0 < npatch; pa0 += 4 * NW) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int pa = pa0 + u * NW;
+                    const int i = (pa >> 1) * 4 + il, c = (pa & 1) * 8 + cl;
+                    v[u] = (pa < npatch && i < h && c < nb) ? Sg[(size_t)(r0 + i) * lds + r0 + c] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int pa = pa0 + u * NW;
+                    const int i = (pa >> 1) * 4 + il, c = (pa & 1) * 8 + cl;
+                    if (pa < npatch && i < h) P[c * ld + i] = v[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+// Diagonal block of a panel (nb x nb, in place), ONE warp: lane r holds row r in registers, the pivot column travels by
+// shuffles -- no block barrier in the serial part of the factorisation.  dinv[q] <- 1 / L[q][q] (the rsqrt itself: neither
+// the row solve below nor the back substitution ever divides).
+__device__ __forceinline__ void pm_diag_factor(double *P, int ld, int nb, double *dinv)
+{
+    const int lane = threadIdx.x & 31, r = lane & 15;
+    double a[PNB];
+#pragma unroll
+    for (int c = 0; c < PNB; c++) a[c] = (r < nb && c <= r) ? P[c * ld + r] : (c == r ? 1.0 : 0.0);
+#pragma unroll
+    for (int q = 0; q < PNB; q++) {
+        const double d = __shfl_sync(0xffffffffu, a[q], q);
+        const double inv = rsqrt(d);
+        const double lq = (r == q) ? d * inv : a[q] * inv;
+        a[q] = lq;
+        if (lane == q && q < nb) dinv[q] = inv;
+#pragma unroll
+        for (int c = q + 1; c < PNB; c++) a[c] = fma(-lq, __shfl_sync(0xffffffffu, lq, c), a[c]);
+    }
+    if (lane < nb) {
+#pragma unroll
+        for (int c = 0; c < PNB; c++)
+            if (c <= lane) P[c * ld + lane] = a[c];
+    }
+}
+// Rows below the diagonal block: thread i solves its own row against L11 (x L11^T = a, forward substitution in registers,
+// L11 broadcast from shared memory): 136 fp64 instructions per row, no barrier, no rsqrt.
+template <bool FULL>
+__device__ __forceinline__ void pm_row_solve(double *P, int ld, int h, int nb, const double *dinv)
+{
+    const int i = nb + threadIdx.x;
+    if (i < h) {
+        double a[PNB];
+#pragma unroll
+        for (int c = 0; c < PNB; c++) a[c] = (FULL || c < nb) ? P[c * ld + i] : 0.0;
+#pragma unroll
+        for (int c = 0; c < PNB; c++) {
+            if (FULL || c < nb) {
+                const double xc = a[c] * dinv[c];
+                a[c] = xc;
+#pragma unroll
+                for (int q = c + 1; q < PNB; q++)
+                    if (FULL || q < nb) a[q] = fma(-xc, P[c * ld + q], a[q]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < PNB; c++)
+            if (FULL || c < nb) P[c * ld + i] = a[c];
+    }
+    __syncthreads();
+}
+// acc (32 rows from a0 x 16 rows from b0, as 4 x 2 mma tiles) += L[a][q] L[b][q] over the 16 columns q of panel Pq
+// (first row / column cq, leading dimension ldq).  Rows past the border read whatever follows in shared memory: they
+// only reach accumulators that are never stored.
+__device__ __forceinline__ void pm_mma_panel(double (&acc)[4][2][2], const double *Pq, int ldq, int cq, int a0, int b0, int g,
+                                             int t4)
+{
+    const double *pa = Pq + t4 * ldq + (a0 - cq) + g;
+    const double *pb = Pq + t4 * ldq + (b0 - cq) + g;
+#pragma unroll
+    for (int q0 = 0; q0 < PNB; q0 += 4) {
+        double a[4], b[2];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) a[mt] = pa[q0 * ldq + 8 * mt];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) b[nt] = pb[q0 * ldq + 8 * nt];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) dmma_m8n8k4(acc[mt][nt], a[mt], b[nt]);
+    }
+}
+// Right-looking update of the stage's later panels with factored panel pb: S[a][b] -= sum_q L[a][q] L[b][q].
+// Work units (target panel, 32-row block) are dealt round robin to warps 1 .. 15; warp 0 takes the unit that holds the
+// diagonal block of the NEXT panel and factors that block right away (look-ahead), so the serial part of the next panel
+// step runs underneath this update.
+__device__ void pm_trailing(double *L, const int *poff, int mm, int c0, int np, int pb, double *dinv_stage)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    constexpr int NW = FIT_NT / 32 - 1;
+    const int cq = c0 + pb * PNB;
+    const int ldq = pm_ld(mm + 1 - cq);
+    const double *Pq = L + poff[pb];
+    int u = 0;  // units before this panel, not counting unit 0
+    for (int pj = pb + 1; pj < np; pj++) {
+        const int cj = c0 + pj * PNB;
+        const int hj = mm + 1 - cj, ldj = pm_ld(hj);
+        const int nbj = min(PNB, mm - cj);
+        const int nrb = (hj + 31) >> 5;
+        int first, step;
+        if (pj == pb + 1) {  // row block 0 of the next panel is warp 0's; the others start at row block 1
+            first = wid == 0 ? 0 : 1 + (wid - 1 - u % NW + NW) % NW;
+            step = wid == 0 ? nrb : NW;
+        } else {
+            first = wid == 0 ? nrb : (wid - 1 - u % NW + NW) % NW;
+            step = NW;
+        }
+        double *Pj = L + poff[pj];
+        for (int rb = first; rb < nrb; rb += step) {
+            const int a0 = cj + 32 * rb;
+            double acc[4][2][2];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            pm_mma_panel(acc, Pq, ldq, cq, a0, cj, g, t4);
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                    for (int w = 0; w < 2; w++) {
+                        const int a = a0 + 8 * mt + g, bl = 8 * nt + 2 * t4 + w;
+                        if (a <= mm && bl < nbj) Pj[bl * ldj + (a - cj)] -= acc[mt][nt][w];
+                    }
+        }
+        if (pj == pb + 1) {
+            if (wid == 0) {
+                __syncwarp();
+                pm_diag_factor(Pj, ldj, nbj, dinv_stage + (pj * PNB));
+            }
+            u += nrb - 1;
+        } else {
+            u += nrb;
+        }
+    }
+    __syncthreads();
+}
+// Schur complement of the columns behind a stage, in place in the global matrix: S[a][b] -= sum over ALL columns q of the
+// stage of L[a][q] L[b][q] for b >= c1, a >= b's block.
+__device__ void pm_update_global(const double *L, const int *poff, double *Sg, int lds, int mm, int c0, int np)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    constexpr int NW = FIT_NT / 32;
+    const int c1 = c0 + np * PNB;
+    int u = 0;
+    for (int cj = c1; cj < mm; cj += PNB) {
+        const int nrb = (mm + 1 - cj + 31) >> 5;
+        const int first = (wid - u % NW + NW) % NW;
+        for (int rb = first; rb < nrb; rb += NW) {
+            const int a0 = cj + 32 * rb;
+            double acc[4][2][2];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+            for (int pb = 0; pb < np; pb++) {
+                const int cq = c0 + pb * PNB;
+                pm_mma_panel(acc, L + poff[pb], pm_ld(mm + 1 - cq), cq, a0, cj, g, t4);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    const int a = a0 + 8 * mt + g, b = cj + 8 * nt + 2 * t4;
+                    if (a <= mm) {
+                        if (b < mm) Sg[(size_t)a * lds + b] -= acc[mt][nt][0];
+                        if (b + 1 < mm) Sg[(size_t)a * lds + b + 1] -= acc[mt][nt][1];
+                    }
+                }
+        }
+        u += nrb;
+    }
+    __syncthreads();
+}
+// L^T x = z over the columns of the stage in shared memory; x[c] of the later columns is final.
+__device__ void pm_backsub(const double *L, const int *poff, int mm, int c0, int np, double *x, double *red /* PNB */,
+                           const double *dinv_stage)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ncol = min(np * PNB, mm - c0);
+    for (int e = tid; e < ncol; e += FIT_NT) {
+        const int pb = e >> 4, q = e & 15, r0 = c0 + pb * PNB;
+        x[c0 + e] = L[poff[pb] + q * pm_ld(mm + 1 - r0) + (mm - r0)];  // z = the border row
+    }
+    __syncthreads();
+    for (int pb = np - 1; pb >= 0; pb--) {
+        const int r0 = c0 + pb * PNB;
+        const int h = mm + 1 - r0, ld = pm_ld(h);
+        const int nb = min(PNB, mm - r0);
+        const double *P = L + poff[pb];
+        if (wid < nb) {  // warp q: v_q = sum_{i > block} L[i][r0 + q] x[i]
+            double acc = 0.0;
+            for (int i = nb + lane; i < h - 1; i += 32) acc = fma(P[wid * ld + i], x[r0 + i], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) red[wid] = acc;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            double t = 0.0, dinv = 0.0, lrow[PNB];  // lrow[q] = L[r0 + q][r0 + lane] (q > lane)
+#pragma unroll
+            for (int q = 0; q < PNB; q++) lrow[q] = (lane < q && q < nb) ? P[lane * ld + q] : 0.0;
+            if (lane < nb) {
+                t = x[r0 + lane] - red[lane];
+                dinv = dinv_stage[pb * PNB + lane];
+            }
+#pragma unroll
+            for (int q = PNB - 1; q >= 0; q--) {
+                const double yq = __shfl_sync(0xffffffffu, t, q) * __shfl_sync(0xffffffffu, dinv, q);
+                if (lane == q) t = yq;
+                t = fma(-lrow[q], yq, t);  // lrow[q] == 0 for lane >= q and for q >= nb (then yq == 0 as well)
+            }
+            if (lane < nb) x[r0 + lane] = t;
+        }
+        __syncthreads();
+    }
+}
+// Sg: bordered system in global memory (row-major, lower triangle + border row mm); multi-stage runs overwrite it.
+// x (shared memory) <- solution.
+__device__ __noinline__ void chol_panel_major(double *Sg, int lds, int mm, double *x, const FitSmem &sm_, PhaseTimer &pt)
+{
+    const FitSmem sm = sm_shared(sm_);
+    // Re-derive every shared-memory pointer from the kernel's dynamic shared array: behind the call boundary of this
+    // (not inlined) function the compiler would otherwise address them generically (LD.E / ST.E instead of LDS / STS,
+    // 64-bit address arithmetic) -- measured 5x slower per DMMA block.
+    int *poff = reinterpret_cast<int *>(as_shared(sm.tile));  // up to 64 panel offsets
+    double *L = as_shared(sm.tile) + 32;
+    double *dg = as_shared(sm.dg);
+    double *red = as_shared(sm.red);
+    x = as_shared(x);
+    const int cap = pm_capacity(sm.arena_len);
+    int sc0[PM_MAX_STAGES], snp[PM_MAX_STAGES], ns = 0;
+    for (int c0 = 0; c0 < mm && ns < PM_MAX_STAGES;) {
+        const int np = pm_plan(c0, mm, cap);
+        sc0[ns] = c0;
+        snp[ns] = np;
+        ns++;
+        c0 += np * PNB;
+    }
+    for (int s = 0; s < ns; s++) {
+        const int c0 = sc0[s], np = snp[s];
+        pm_offsets(poff, mm, c0, np);
+        pm_copy<false>(L, poff, Sg, lds, mm, c0, np);
+        pt.mark(10);
+        if (threadIdx.x < 32) pm_diag_factor(L + poff[0], pm_ld(mm + 1 - c0), min(PNB, mm - c0), dg + c0);
+        __syncthreads();
+        for (int pb = 0; pb < np; pb++) {
+            const int r0 = c0 + pb * PNB;
+            const int nb = min(PNB, mm - r0);
+            if (nb == PNB) pm_row_solve<true>(L + poff[pb], pm_ld(mm + 1 - r0), mm + 1 - r0, nb, dg + r0);
+            else pm_row_solve<false>(L + poff[pb], pm_ld(mm + 1 - r0), mm + 1 - r0, nb, dg + r0);
+            pt.mark(13);
+            if (pb + 1 < np) pm_trailing(L, poff, mm, c0, np, pb, dg + c0);
+            pt.mark(14);
+        }
+        if (s + 1 < ns) {
+            pm_update_global(L, poff, Sg, lds, mm, c0, np);
+            pm_copy<true>(L, poff, Sg, lds, mm, c0, np);
+            pt.mark(11);
+        }
+    }
+    for (int s = ns - 1; s >= 0; s--) {
+        const int c0 = sc0[s], np = snp[s];
+        if (s != ns - 1) {
+            pm_offsets(poff, mm, c0, np);
+            pm_copy<false>(L, poff, Sg, lds, mm, c0, np);
+        }
+        pm_backsub(L, poff, mm, c0, np, x, red, dg + c0);
+    }
+    pt.mark(12);
+}
+
 // P[i][q] = S[j0 + i][j0 + q] for i in [i0, i1), q < nb: 8 independent loads in flight per thread
 __device__ __forceinline__ void panel_load(double *P, const double *S, int lds, int j0, int i0, int i1, int nb)
 {
@@ -637,8 +1026,9 @@ __device__ __forceinline__ void panel_load(double *P, const double *S, int lds, 
 // back; after a cluster barrier every CTA loads the panel and updates its share of the trailing matrix with
 // register-blocked 4x4 tiles (read-modify-write in L2); a second barrier publishes the update.  Back substitution on
 // rank 0.  x (rank 0's shared memory) <- solution.  With CL == 1 the barriers degenerate to __syncthreads.
-__device__ __noinline__ void chol_blocked_cluster(double *S, int lds, int mm, double *x, const FitSmem &sm, Clu &cl)
+__device__ __noinline__ void chol_blocked_cluster(double *S, int lds, int mm, double *x, const FitSmem &sm_, Clu &cl)
 {
+    const FitSmem sm = sm_shared(sm_);
     constexpr int NB = CHOL_NB, PS = NB + 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *P = sm.tile;  // panel rows j0..mm, PS doubles each: (mm + 1) * 17 <= FIT_TILE_DOUBLES for mm <= 480
@@ -748,10 +1138,14 @@ __device__ __noinline__ void chol_blocked_cluster(double *S, int lds, int mm, do
 // Rank 0 holds a bordered system (nu unknowns) at S -- its own shared memory (small systems) or the chain's global matrix
 // (large systems, then every CTA of the cluster takes part in the factorisation): solve it and hand the solution to
 // every CTA of the cluster (out: smem).
-__device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds, int nu, double *out, const FitSmem &sm)
+__device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds, int nu, double *out, const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
+    out = as_shared(out);
     if (S == sm.Ssm) {
         if (cl.rank == 0) block_chol_solve_small(S, lds, nu, sm.rhs, sm.dg);
+    } else if (g_dbg_solver == 0 && nu < FIT_NT && pm_stage_count(nu, sm.arena_len) <= PM_MAX_STAGES) {
+        if (cl.rank == 0) chol_panel_major(S, lds, nu, sm.rhs, sm, cl.pt);
     } else if (packed_fits(nu, sm.arena_len)) {
         if (cl.rank == 0) chol_packed_smem(S, lds, nu, sm.rhs, sm, cl.pt);
     } else {
@@ -777,8 +1171,9 @@ __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds,
 // reducing a slab of rows, ranks summed in a fixed order; optional extra row `rows` = sum_q cw_slot(q, 1) (Cox gradient).
 // Ends with a cluster barrier; afterwards rank 0 stages the system where it will factor it and returns that pointer.
 __device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int cols, int nmat, bool extra_row, int *lds_out,
-                                   const FitSmem &sm, double diag_add = 0.0, int diag_from = 0, int diag_to = 0)
+                                   const FitSmem &sm_, double diag_add = 0.0, int diag_from = 0, int diag_to = 0)
 {
+    const FitSmem sm = sm_shared(sm_);
     const int ldA = cx.ldA;
     const int per = (rows + cl.CL - 1) / cl.CL;
     const int a0 = cl.rank * per, a1 = min(rows, a0 + per);
@@ -824,8 +1219,10 @@ __device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int co
 // row mm-1 as right-hand side:  S = sum_r wt[r] V[r][a] V[r][b];  S[0:mm-1, 0:mm-1] x = S[mm-1, 0:mm-1].
 // out (shared memory of every CTA) <- x.
 __device__ void gram_solve(const ChainCtx &cx, Clu &cl, const double *V, int ldv, int mm, const double *wt, double *out,
-                           const FitSmem &sm, double diag_add = 0.0, int diag_from = 0)
+                           const FitSmem &sm_, double diag_add = 0.0, int diag_from = 0)
 {
+    const FitSmem sm = sm_shared(sm_);
+    out = as_shared(out);
     cl.pt.mark(PH_OTHER);
     if (cl.CL == 1) {
         gram(V, ldv, cx.rb, cx.re, mm, wt, cx.S, cx.lds, sm);
@@ -854,8 +1251,10 @@ __device__ __forceinline__ double row_dot(const double *row, const double *b, in
 }
 
 // ---- gaussian: Algorithm.h:1131-1135
-__device__ void fit_lm(const ChainCtx &cx, Clu &cl, const FitSmem &sm, double *beta_out, double lambda)
+__device__ void fit_lm(const ChainCtx &cx, Clu &cl, const FitSmem &sm_, double *beta_out, double lambda)
 {
+    const FitSmem sm = sm_shared(sm_);
+    beta_out = as_shared(beta_out);
     const int T = cx.T, ldA = cx.ldA;
     for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) cx.XA[(size_t)r * ldA + T] = cx.y[r];
     __syncthreads();
@@ -863,8 +1262,10 @@ __device__ void fit_lm(const ChainCtx &cx, Clu &cl, const FitSmem &sm, double *b
 }
 
 // ---- binomial: Algorithm.h:1148-1204.  Design columns: [1 | X_A | z]
-__device__ double logit_eval(const ChainCtx &cx, Clu &cl, const double *beta, const FitSmem &sm)
+__device__ double logit_eval(const ChainCtx &cx, Clu &cl, const double *beta, const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
+    beta = as_shared(beta);
     double ll = 0.0;
     for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
         const double eu = row_dot(cx.XA + (size_t)r * cx.ldA, beta, cx.m);
@@ -889,8 +1290,9 @@ __device__ void logit_wz(const ChainCtx &cx, bool floor_w)
     }
     __syncthreads();
 }
-__device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm, double lambda)
+__device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm_, double lambda)
 {
+    const FitSmem sm = sm_shared(sm_);
     double *b0 = sm.b0, *b1 = sm.b1;
     for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = 0.0;
     __syncthreads();
@@ -912,8 +1314,9 @@ __device__ void fit_logistic(const ChainCtx &cx, Clu &cl, const FitSmem &sm, dou
 }
 
 // ---- poisson: Algorithm.h:1273-1322
-__device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const FitSmem &sm, double lambda)
+__device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const FitSmem &sm_, double lambda)
 {
+    const FitSmem sm = sm_shared(sm_);
     double *b0 = sm.b0;
     const int ldA = cx.ldA;
     for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = a == 0 ? coef0_in : 0.0;
@@ -951,8 +1354,9 @@ __device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const 
 // ---- scans over the chain's rows, cut into the cluster's contiguous slices.  v is global, indexed by absolute row.
 // suffix: v[r] <- sum_{k >= r} v[k];  prefix: v[r] <- sum_{k <= r} v[k].  The slice total is carried from rank to rank by
 // ADDITION only (risk sets span e^+-30: never subtract, see block_excl_scan).
-__device__ void clu_suffix_scan(const ChainCtx &cx, Clu &cl, double *v, const FitSmem &sm)
+__device__ void clu_suffix_scan(const ChainCtx &cx, Clu &cl, double *v, const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
     const int nr = cx.re - cx.rb;
     block_suffix_scan<FIT_NT>(v + cx.rb, nr, sm.red);
     if (cl.CL == 1) return;
@@ -965,8 +1369,9 @@ __device__ void clu_suffix_scan(const ChainCtx &cx, Clu &cl, double *v, const Fi
     for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) v[r] += carry;
     __syncthreads();
 }
-__device__ void clu_prefix_scan(const ChainCtx &cx, Clu &cl, double *v, const FitSmem &sm)
+__device__ void clu_prefix_scan(const ChainCtx &cx, Clu &cl, double *v, const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
     const int nr = cx.re - cx.rb;
     block_prefix_scan<FIT_NT>(v + cx.rb, nr, sm.red);
     if (cl.CL == 1) return;
@@ -982,8 +1387,10 @@ __device__ void clu_prefix_scan(const ChainCtx &cx, Clu &cl, double *v, const Fi
 
 // ---- cox: Algorithm.h:1377-1490 (+ loglik_cox, coxph.cpp:16-40)
 // loglik at beta: theta = exp(clip(X_A beta)), S0 = suffix(theta); sum status*w*log(theta/S0)
-__device__ double cox_loglik(const ChainCtx &cx, Clu &cl, const double *beta, double *th, double *s0, const FitSmem &sm)
+__device__ double cox_loglik(const ChainCtx &cx, Clu &cl, const double *beta, double *th, double *s0, const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
+    beta = as_shared(beta);
     for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
         const double t = exp(clampd(row_dot(cx.XA + (size_t)r * cx.ldA, beta, cx.m), 30.0));
         th[r] = t;
@@ -998,8 +1405,9 @@ __device__ double cox_loglik(const ChainCtx &cx, Clu &cl, const double *beta, do
 // XB[r][a] = suffix_r(theta * XA[.][a]) / S0[r]   (risk-set means), chunked two-pass scan over the slice's rows with the
 // column totals of the later slices carried in
 __device__ void cox_riskset_means(const ChainCtx &cx, Clu &cl, double *XB, const double *th, const double *s0,
-                                  const FitSmem &sm)
+                                  const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
     const int m = cx.m, ldA = cx.ldA;
     const int nr = cx.re - cx.rb;
     // rows per chunk: chunk sums [nch][m] must fit the scratch region (FIT_NT*16 doubles)
@@ -1047,8 +1455,9 @@ __device__ void cox_riskset_means(const ChainCtx &cx, Clu &cl, double *XB, const
     __syncthreads();
 }
 __device__ int g_dbg_cox_iters = 30;  // debug knob (bess_b200_debug_set key 1); 30 = reference behaviour
-__device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &sm, double lambda)
+__device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &sm_, double lambda)
 {
+    const FitSmem sm = sm_shared(sm_);
     const int max_newton = g_dbg_cox_iters;
     const int m = cx.m, ldA = cx.ldA;
     double *b0 = sm.b0, *b1 = sm.b1;
@@ -1147,8 +1556,10 @@ __device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &
 
 // Gradient vectors of the next dual sweep from the chain's current (A, beta_A, coef0); X_A is in cx.XA.
 __device__ void chain_gradient(const Dev &d, const ChainCtx &cx, Clu &cl, const double *bsl /*smem slopes*/, int ks,
-                               double coef0, const FitSmem &sm)
+                               double coef0, const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
+    bsl = as_shared(bsl);
     const int c = cx.c, FS = d.FS, nt = cx.nt;
     const int *rows = d.rows + (size_t)c * d.n;
     const int fam = d.family;
@@ -1201,8 +1612,9 @@ __device__ void chain_gradient(const Dev &d, const ChainCtx &cx, Clu &cl, const 
     __syncthreads();
 }
 
-__device__ __forceinline__ ChainCtx make_ctx(const Dev &d, int c, int T, const Clu &cl, const FitSmem &sm)
+__device__ __forceinline__ ChainCtx make_ctx(const Dev &d, int c, int T, const Clu &cl, const FitSmem &sm_)
 {
+    const FitSmem sm = sm_shared(sm_);
     ChainCtx cx;
     cx.c = c;
     cx.nt = d.ntrain[c];
@@ -1232,8 +1644,9 @@ __device__ __forceinline__ ChainCtx make_ctx(const Dev &d, int c, int T, const C
     return cx;
 }
 
-__device__ __forceinline__ Clu make_clu(const FitSmem &sm, int CL)
+__device__ __forceinline__ Clu make_clu(const FitSmem &sm_, int CL)
 {
+    const FitSmem sm = sm_shared(sm_);
     Clu cl;
     cl.CL = CL;
     cl.rank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
@@ -1482,9 +1895,95 @@ void launch_chain_state(const Dev &d, int chain, int op, int slot_beta, int slot
     }
 }
 
+// ---- solver probe (tools / tests): one CTA factors and solves a bordered system given in global memory, `reps` times from
+// a pristine copy; ticks[0] = clock64 ticks of the last repetition.  impl 0 = chol_panel_major, 1 = chol_packed_smem.
+__global__ void __launch_bounds__(FIT_NT, 1)
+solve_probe_kernel(const double *S0, double *Sw, int lds, int mm, double *xout, int impl, int reps, unsigned long long *ticks,
+                   int smem_doubles)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FitSmem sm = carve_fit_smem(smem_raw, lds, smem_doubles);
+    PhaseTimer pt;
+    for (int rep = 0; rep < reps; rep++) {
+        for (int e = threadIdx.x; e < (mm + 1) * lds; e += FIT_NT) Sw[e] = S0[e];
+        pt.start(threadIdx.x == 0 && rep == reps - 1);
+        __syncthreads();
+        const long long t0 = clock64();
+        if (impl != 1) chol_panel_major(Sw, lds, mm, sm.rhs, sm, pt);
+        else chol_packed_smem(Sw, lds, mm, sm.rhs, sm, pt);
+        __syncthreads();
+        if (threadIdx.x == 0) ticks[0] = (unsigned long long)(clock64() - t0);
+    }
+    for (int a = threadIdx.x; a < mm; a += FIT_NT) xout[a] = sm.rhs[a];
+}
+void debug_solve(const double *S, int lds, int mm, double *x_out, int impl, int reps, double *ticks_out)
+{
+    if (mm < 1 || mm >= FIT_NT || lds < mm || (lds & 1)) throw EngineError{"debug_solve: need 1 <= mm < 512, even lds >= mm"};
+    const int smd = fit_smem_doubles(lds, 400);
+    double *dS0, *dSw, *dx;
+    unsigned long long *dt, ht = 0;
+    const size_t nb = sizeof(double) * (size_t)(mm + 1) * lds;
+    CUDA_CHECK(cudaMalloc(&dS0, nb));
+    CUDA_CHECK(cudaMalloc(&dSw, nb));
+    CUDA_CHECK(cudaMalloc(&dx, sizeof(double) * mm));
+    CUDA_CHECK(cudaMalloc(&dt, 8));
+    CUDA_CHECK(cudaMemcpy(dS0, S, nb, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaFuncSetAttribute(solve_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smd * 8));
+    solve_probe_kernel<<<1, FIT_NT, (size_t)smd * 8>>>(dS0, dSw, lds, mm, dx, impl, reps, dt, smd);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(x_out, dx, sizeof(double) * mm, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(&ht, dt, 8, cudaMemcpyDeviceToHost));
+    if (ticks_out) *ticks_out = (double)ht;
+    cudaFree(dS0); cudaFree(dSw); cudaFree(dx); cudaFree(dt);
+}
+
+// ---- Gram probe: one CTA computes S = V^T diag(wt) V over `nrows` rows (V in global memory, as in the chain kernels).
+// impl 0 = gram() dispatcher, 1 = register-blocked FMA path, 2 = DMMA path
+__global__ void __launch_bounds__(FIT_NT, 1)
+gram_probe_kernel(const double *V, int ldv, int nrows, int mm, const double *wt, double *S, int impl, int reps,
+                  unsigned long long *ticks, int smem_doubles)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FitSmem sm = carve_fit_smem(smem_raw, ldv, smem_doubles);
+    for (int rep = 0; rep < reps; rep++) {
+        __syncthreads();
+        const long long t0 = clock64();
+        if (impl == 1) block_syrk(V, ldv, 0, nrows, mm, wt, S, ldv, sm);
+        else if (impl == 2) block_syrk_dmma(V, ldv, 0, nrows, mm, wt, S, ldv, sm);
+        else gram(V, ldv, 0, nrows, mm, wt, S, ldv, sm);
+        __syncthreads();
+        if (threadIdx.x == 0) ticks[0] = (unsigned long long)(clock64() - t0);
+    }
+}
+void debug_gram(const double *V, int ldv, int nrows, int mm, const double *wt, double *S_out, int impl, int reps,
+                double *ticks_out)
+{
+    if (mm < 1 || mm > ldv || (ldv & 1) || nrows < 1) throw EngineError{"debug_gram: need 1 <= mm <= ldv, even ldv, nrows >= 1"};
+    const int smd = fit_smem_doubles(ldv, 400);
+    double *dV, *dw, *dS;
+    unsigned long long *dt, ht = 0;
+    CUDA_CHECK(cudaMalloc(&dV, sizeof(double) * (size_t)nrows * ldv));
+    CUDA_CHECK(cudaMalloc(&dw, sizeof(double) * nrows));
+    CUDA_CHECK(cudaMalloc(&dS, sizeof(double) * (size_t)ldv * ldv));
+    CUDA_CHECK(cudaMalloc(&dt, 8));
+    CUDA_CHECK(cudaMemcpy(dV, V, sizeof(double) * (size_t)nrows * ldv, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dw, wt, sizeof(double) * nrows, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(dS, 0, sizeof(double) * (size_t)ldv * ldv));
+    CUDA_CHECK(cudaFuncSetAttribute(gram_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smd * 8));
+    gram_probe_kernel<<<1, FIT_NT, (size_t)smd * 8>>>(dV, ldv, nrows, mm, dw, dS, impl, reps, dt, smd);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(S_out, dS, sizeof(double) * (size_t)ldv * ldv, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(&ht, dt, 8, cudaMemcpyDeviceToHost));
+    if (ticks_out) *ticks_out = (double)ht;
+    cudaFree(dV); cudaFree(dw); cudaFree(dS); cudaFree(dt);
+}
+
 void debug_set(int key, int val)
 {
     if (key == 1) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_cox_iters, &val, sizeof(int)));
+    if (key == 4) CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_solver, &val, sizeof(int)));
     if (key == 2) {
         CUDA_CHECK(cudaMemcpyToSymbol(g_dbg_phase_on, &val, sizeof(int)));
         unsigned long long z[2][16] = {};

@@ -179,6 +179,10 @@ int fit_smem_doubles(int ldA, int kcap);
 int chain_cluster_size(const Dev &d, int T, int nch);
 void configure_kernels();
 void debug_set(int key, int val);
-void debug_get(unsigned long long *out32);  // chain_fit phase timers: [0][id] clock ticks, [1][id] hits
+void debug_get(unsigned long long *out32);
+void debug_solve(const double *S, int lds, int mm, double *x_out, int impl, int reps, double *ticks_out);
+void debug_gram(const double *V, int ldv, int nrows, int mm, const double *wt, double *S_out, int impl, int reps,
+                double *ticks_out);
+
 
 }  // namespace bess
