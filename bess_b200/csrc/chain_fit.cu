@@ -338,11 +338,18 @@ __device__ void block_syrk(const double *V, int ldv, int r0, int r1, int mm, con
 
 // =====================================================================================================
 // Gram on the FP64 tensor cores (DMMA, mma.sync.m8n8k4.f64) for systems wide enough to be a real dense contraction
-// (mm > 96): same contract as block_syrk.  Each warp owns a 32 x 32 block of the lower block-triangle (4 x 4 mma tiles,
-// 32 accumulators per thread); row tiles are staged with cp.async into two alternating buffers whose row stride is
-// padded to 4 (mod 8) doubles so the 4-row x 8-column fragment loads are bank-conflict free.  Per 4-row step a warp
-// issues 8 shared loads for 16 DMMAs (4096 FMAs) -- the 4x4 register-blocked FMA path needs 16x more shared-memory
-// bytes per FMA and is shared-memory bound (profiles/r01c: 168 us per Gram at m = 201, 35 % of C2's chain time).
+// (mm > 96): same contract as block_syrk.
+//   * Work: the lower triangle in 16 x 16 tiles (m = 203: 91 tiles, 13 % more entries than the triangle itself; the
+//     32 x 16 warp blocks of round 1 issued 39 % more and ran 3.5 rounds on 16 warps).  The tiles are dealt round robin
+//     to the 16 warps; a warp accumulates up to GT = 3 tiles at once (12 DMMAs per 4-row step, 24 accumulator registers),
+//     so the whole Gram is ceil(tiles / 48) passes over the row slice (2 at m = 203).
+//   * Data: rows travel global -> shared memory as 1-D bulk-TMA copies (cp.async.bulk, one per row, issued by the lanes
+//     of warp 0, completion on a `full` mbarrier per stage with expect-tx byte counts) into a 3-stage ring of row tiles
+//     whose row stride is == 4 (mod 8) doubles (fragment loads hit every bank exactly twice: the minimum for 256 bytes).
+//     A stage is released through an `empty` mbarrier (one arrival per warp) -- no block barrier and no per-thread
+//     staging instructions in the main loop (the cp.async staging of round 1 spent a fifth of the issue slots on address
+//     arithmetic with every warp staging at the same time, the tensor pipe idle meanwhile).
+//   * The weight enters through the B operand (2 multiplies per tile and 4-row step).
 // =====================================================================================================
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
 {
@@ -350,92 +357,193 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b)
                  : "+d"(c[0]), "+d"(c[1])
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ uint32_t cf_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cf_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cf_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void cf_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cf_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cf_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cf_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cf_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     cf_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(cf_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cf_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "CF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra CF_DONE;\n"
+        "bra CF_WAIT;\n"
+        "CF_DONE:\n"
+        "}" ::"r"(cf_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+constexpr int GRAM_DMMA_MIN = 56;  // systems wider than this take the tensor-core path (probe: FMA path 11 us vs 16 us at 32, 44 vs 26 at 97)
+constexpr int GRAM_NS = 3;  // ring stages
+constexpr int GRAM_GT = 3;  // 16 x 16 tiles a warp accumulates at once
 __device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
                                 const FitSmem &sm_)
 {
     const FitSmem sm = sm_shared(sm_);
-    constexpr int NTN = 2;  // warp block = 32 rows x 16 columns: 4 x 2 mma tiles, 16 accumulators per thread
+    constexpr int NW = FIT_NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int mp = ((mm + 3) >> 2) << 2;
-    const int ts = (mp & 7) == 4 ? mp : mp + 4;  // tile row stride == 4 (mod 8) doubles
-    const int nb = (mm + 31) >> 5;                // 32-row block rows; block row bi has 2*bi + 2 column blocks of 16
-    const int nblk = nb * (nb + 1);
-    const int R = (FIT_TILE_DOUBLES / (ts + 1)) & ~3;  // rows per tile, multiple of the mma k
-    double *const buf0 = as_shared(sm.tile), *const buf1 = as_shared(sm.scratch);
-    const int ntile = (r1 - r0 + R - 1) / R;
-    const int cpr = mp >> 1;  // 16-byte chunks per row
     const int g = lane >> 2, t4 = lane & 3;
-    for (int round = 0; round * (FIT_NT / 32) < nblk; round++) {
-        const int blk = round * (FIT_NT / 32) + wid;
-        const bool valid = blk < nblk;
-        int bi = 0, bj = 0;  // blk = bi * (bi + 1) + bj, bj < 2 * bi + 2
-        if (valid) {
-            bi = (int)((sqrt(4.0 * (double)blk + 1.0) - 1.0) * 0.5);
-            while ((bi + 1) * (bi + 2) <= blk) bi++;
-            while (bi * (bi + 1) > blk) bi--;
-            bj = blk - bi * (bi + 1);
+    const int mp = ((mm + 3) >> 2) << 2;
+    const int ts = (mp & 7) == 4 ? mp : mp + 4;       // tile row stride == 4 (mod 8) doubles
+    const int ncopy = min(mp, ldv);                   // doubles copied per row (even: 16-byte multiples)
+    const int nt16 = (mm + 15) >> 4;
+    const int ntiles = nt16 * (nt16 + 1) / 2;
+    const int npass = (ntiles + NW * GRAM_GT - 1) / (NW * GRAM_GT);
+    // ring: GRAM_NS stages of R rows (+ R weights each) in the arena
+    // (systems of up to FIT_SMEM_MS rows may have their output S in the Ssm region of the arena: keep the ring off it)
+    const int ring_len = mm <= FIT_SMEM_MS ? FIT_TILE_DOUBLES + FIT_NT * 16 - 16 : sm.arena_len - 16;
+    int R = (ring_len / GRAM_NS / (ts + 1)) & ~3;
+    if (R > 64) R = 64;
+    double *ring = sm.tile;
+    const int stage_len = R * (ts + 1);               // rows, then the R weights of the stage
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm.red);  // [GRAM_NS], empty = full + GRAM_NS
+    uint64_t *empty = full + GRAM_NS;
+    const int nrow = r1 - r0;
+    const int ntile = (nrow + R - 1) / R;
+    const int nstep = ntile * npass;
+    __syncthreads();  // the arena and sm.red are free
+    if (tid == 0) {
+        for (int q = 0; q < GRAM_NS; q++) {
+            cf_mbar_init(&full[q], 1);
+            cf_mbar_init(&empty[q], NW);
         }
-        double acc[4][NTN][2];
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // rows that only pad the last 4-row step of the last tile must be finite (their weight is 0): clear them in the stage
+    // that will hold the last tile if no earlier tile overwrites them with data first
+    {
+        const int rc_last = nrow - (ntile - 1) * R, rc4 = (rc_last + 3) & ~3;
+        for (int q = 0; q < GRAM_NS; q++)
+            for (int e = tid; e < (rc4 - rc_last) * ts; e += FIT_NT) ring[q * stage_len + rc_last * ts + e] = 0.0;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // producer (warp 0): tile step q -> stage q % NS
+    // weights of tile step q for rows lane, lane + 32 (R <= 64), fetched one step ahead of their use by the producer
+    double wpre[2] = {0.0, 0.0};
+    auto fetch_w = [&](int q) {
+        const int t = q % ntile;
+        const int rb = r0 + t * R, rc = min(R, r1 - rb);
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++)
+        for (int h = 0; h < 2; h++) wpre[h] = lane + 32 * h < rc ? (wt ? wt[rb + lane + 32 * h] : 1.0) : 0.0;
+    };
+    auto produce = [&](int q) {
+        const int st = q % GRAM_NS;
+        const int t = q % ntile;
+        const int rb = r0 + t * R, rc = min(R, r1 - rb);
+        double *dst = ring + st * stage_len;
+        if (q >= GRAM_NS) cf_mbar_wait(&empty[st], (uint32_t)(((q / GRAM_NS) - 1) & 1));
+        // weights of the stage (generic stores, published by the arrive below), zero for the padding rows
 #pragma unroll
-            for (int nt = 0; nt < NTN; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-        __syncthreads();
-        for (int t = 0; t <= ntile; t++) {
-            if (t < ntile) {  // stage tile t (cp.async, 16-byte chunks) into buf[t & 1]
-                const int rb = r0 + t * R;
-                const int rc = min(R, r1 - rb);
-                double *dst = (t & 1) ? buf1 : buf0;
-                for (int e = tid; e < rc * cpr; e += FIT_NT) {
-                    const int r = e / cpr, cidx = (e - r * cpr) * 2;
-                    if (cidx < ldv) __pipeline_memcpy_async(dst + r * ts + cidx, V + (size_t)(rb + r) * ldv + cidx, 16);
-                }
-                double *twd = dst + (size_t)R * ts;
-                const int rc4 = (rc + 3) & ~3;
-                for (int r = tid; r < rc4; r += FIT_NT) twd[r] = r < rc ? (wt ? wt[rb + r] : 1.0) : 0.0;
-                // rows that only pad the last k-step must be finite (their weight is 0)
-                for (int e = tid; e < (rc4 - rc) * ts; e += FIT_NT) dst[(size_t)rc * ts + e] = 0.0;
+        for (int h = 0; h < 2; h++)
+            if (lane + 32 * h < R) dst[R * ts + lane + 32 * h] = wpre[h];
+        if (q + 1 < nstep) fetch_w(q + 1);
+        __syncwarp();
+        if (lane == 0) cf_mbar_expect_tx(&full[st], (uint32_t)(rc * ncopy * 8));
+        __syncwarp();
+        for (int r = lane; r < rc; r += 32) cf_bulk_g2s(dst + r * ts, V + (size_t)(rb + r) * ldv, (uint32_t)(ncopy * 8), &full[st]);
+    };
+    if (wid == 0) {
+        fetch_w(0);
+        for (int q = 0; q < GRAM_NS - 1 && q < nstep; q++) produce(q);
+    }
+    // this warp's tiles of the current pass
+    int ti[GRAM_GT], tj[GRAM_GT];
+    bool tv[GRAM_GT];
+    double acc[GRAM_GT][2][2][2];
+    auto start_pass = [&](int pass) {
+#pragma unroll
+        for (int u = 0; u < GRAM_GT; u++) {
+            const int t = (pass * GRAM_GT + u) * NW + wid;
+            tv[u] = t < ntiles;
+            int bi = 0, bj = 0;
+            if (tv[u]) {
+                bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+                while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+                while (bi * (bi + 1) / 2 > t) bi--;
+                bj = t - bi * (bi + 1) / 2;
             }
-            __pipeline_commit();
-            if (t == 0) continue;
-            // tile t-1 is complete once all but the newest commit group have landed
-            __pipeline_wait_prior(1);
-            __syncthreads();
-            if (valid) {
-                const double *tl = ((t - 1) & 1) ? buf1 : buf0;
-                const double *twt = tl + (size_t)R * ts;
-                const int rc4 = (min(R, r1 - (r0 + (t - 1) * R)) + 3) & ~3;
-                const double *pa = tl + t4 * ts + bi * 32 + g;
-                const double *pb = tl + t4 * ts + bj * 16 + g;
-                for (int k0 = 0; k0 < rc4; k0 += 4) {
-                    const double w = twt[k0 + t4];
-                    double a[4], b[NTN];
+            ti[u] = bi;
+            tj[u] = bj;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) a[q] = pa[(size_t)k0 * ts + q * 8] * w;
+            for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                    for (int q = 0; q < NTN; q++) b[q] = pb[(size_t)k0 * ts + q * 8];
-#pragma unroll
-                    for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-                        for (int nt = 0; nt < NTN; nt++) dmma_m8n8k4(acc[mt][nt], a[mt], b[nt]);
-                }
-            }
-            __syncthreads();
+                for (int nt = 0; nt < 2; nt++) acc[u][mt][nt][0] = acc[u][mt][nt][1] = 0.0;
         }
-        if (valid) {
+    };
+    auto store_pass = [&]() {
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++)
+        for (int u = 0; u < GRAM_GT; u++) {
+            if (!tv[u]) continue;
 #pragma unroll
-                for (int nt = 0; nt < NTN; nt++)
+            for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int a = bi * 32 + mt * 8 + g, b = bj * 16 + nt * 8 + t4 * 2 + u;
+                for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                    for (int w = 0; w < 2; w++) {
+                        const int a = ti[u] * 16 + mt * 8 + g, b = tj[u] * 16 + nt * 8 + t4 * 2 + w;
                         if (a < mm && b < mm) {
-                            S[(size_t)a * lds + b] = acc[mt][nt][u];
-                            S[(size_t)b * lds + a] = acc[mt][nt][u];
+                            S[(size_t)a * lds + b] = acc[u][mt][nt][w];
+                            S[(size_t)b * lds + a] = acc[u][mt][nt][w];
                         }
                     }
         }
+    };
+    start_pass(0);
+    for (int q = 0; q < nstep; q++) {
+        const int st = q % GRAM_NS;
+        const int t = q % ntile;
+        if (wid == 0 && q + GRAM_NS - 1 < nstep) produce(q + GRAM_NS - 1);
+        cf_mbar_wait(&full[st], (uint32_t)((q / GRAM_NS) & 1));
+        const double *tl = ring + st * stage_len;
+        const double *twt = tl + R * ts;
+        const int rc4 = (min(R, nrow - t * R) + 3) & ~3;
+        const double *pk = tl + t4 * ts + g;
+#pragma unroll 2
+        for (int k0 = 0; k0 < rc4; k0 += 4) {
+            const double w = twt[k0 + t4];
+#pragma unroll
+            for (int u = 0; u < GRAM_GT; u++) {
+                if (tv[u]) {
+                    const double *pa = pk + (size_t)k0 * ts + ti[u] * 16;
+                    const double *pb = pk + (size_t)k0 * ts + tj[u] * 16;
+                    const double a0 = pa[0], a1 = pa[8];
+                    const double b0 = pb[0] * w, b1 = pb[8] * w;
+                    dmma_m8n8k4(acc[u][0][0], a0, b0);
+                    dmma_m8n8k4(acc[u][0][1], a0, b1);
+                    dmma_m8n8k4(acc[u][1][0], a1, b0);
+                    dmma_m8n8k4(acc[u][1][1], a1, b1);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) cf_mbar_arrive(&empty[st]);
+        if (t == ntile - 1) {
+            store_pass();
+            if (q + 1 < nstep) start_pass(q / ntile + 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {  // sm.red goes back to being plain scratch
+        for (int q = 0; q < 2 * GRAM_NS; q++) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(cf_smem_u32(&full[q])) : "memory");
     }
     __syncthreads();
 }
@@ -444,7 +552,7 @@ __device__ __forceinline__ void gram(const double *V, int ldv, int r0, int r1, i
                                      const FitSmem &sm_)
 {
     const FitSmem sm = sm_shared(sm_);
-    if (mm > 96) block_syrk_dmma(V, ldv, r0, r1, mm, wt, S, lds, sm);
+    if (mm > GRAM_DMMA_MIN) block_syrk_dmma(V, ldv, r0, r1, mm, wt, S, lds, sm);
     else block_syrk(V, ldv, r0, r1, mm, wt, S, lds, sm);
 }
 

@@ -16,7 +16,7 @@ def main():
     lib.bess_b200_debug_gram.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p]
     rng = np.random.default_rng(0)
-    cases = [(225, 203), (225, 103), (225, 165), (225, 265), (113, 203), (450, 203), (250, 32), (250, 97), (37, 130)]
+    cases = [(225, 203), (225, 103), (225, 165), (225, 265), (113, 203), (450, 203), (250, 32), (250, 48), (250, 57), (250, 64), (250, 80), (250, 97), (37, 130), (1800, 42), (1800, 64)]
     if os.environ.get("GRAM_CASES"):
         cases = [tuple(int(v) for v in c.split("x")) for c in os.environ["GRAM_CASES"].split(",")]
     reps = int(os.environ.get("GRAM_REPS", "3"))
