@@ -776,7 +776,7 @@ __device__ __forceinline__ int pm_plan(int c0, int mm, int cap)
     }
     return np;
 }
-__device__ __forceinline__ int pm_capacity(int arena_len) { return arena_len - 64; }  // panel offsets in front, slack behind
+__device__ __forceinline__ int pm_capacity(int arena_len) { return arena_len - 96; }  // 64-double header in front, slack behind
 __device__ __forceinline__ int pm_stage_count(int mm, int arena_len)
 {
     const int cap = pm_capacity(arena_len);
@@ -839,10 +839,25 @@ __device__ void pm_copy(double *L, const int *poff, double *Sg, int lds, int mm,
     }
     __syncthreads();
 }
-// Diagonal block of a panel (nb x nb, in place), ONE warp: lane r holds row r in registers, the pivot column travels by
-// shuffles -- no block barrier in the serial part of the factorisation.  dinv[q] <- 1 / L[q][q] (the rsqrt itself: neither
-// the row solve below nor the back substitution ever divides).
-__device__ __forceinline__ void pm_diag_factor(double *P, int ld, int nb, double *dinv)
+// 1 / sqrt(d) for the pivots: hardware approximation (2^-22) + two Newton steps (full double precision for normal d; a
+// non-positive pivot gives NaN like the library call, which is how a non-SPD system shows up).
+__device__ __forceinline__ double pm_rsqrt(double d)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const double t = d * y;
+        const double e = fma(-t, y, 1.0);
+        y = fma(0.5 * y, e, y);
+    }
+    return y;
+}
+// Diagonal block of a panel (nb x nb, in place), ONE warp: lane r holds row r in registers; per column the scaled pivot
+// column goes through a 16-double shared buffer (one store, broadcast loads) -- no block barrier in the serial part of
+// the factorisation.  dinv[q] <- 1 / L[q][q] (the rsqrt itself: neither the row solve below nor the back substitution
+// ever divides).  colbuf: 2 * PNB doubles.
+__device__ __forceinline__ void pm_diag_factor(double *P, int ld, int nb, double *dinv, double *colbuf)
 {
     const int lane = threadIdx.x & 31, r = lane & 15;
     double a[PNB];
@@ -851,12 +866,17 @@ __device__ __forceinline__ void pm_diag_factor(double *P, int ld, int nb, double
 #pragma unroll
     for (int q = 0; q < PNB; q++) {
         const double d = __shfl_sync(0xffffffffu, a[q], q);
-        const double inv = rsqrt(d);
+        const double inv = pm_rsqrt(d);
         const double lq = (r == q) ? d * inv : a[q] * inv;
         a[q] = lq;
         if (lane == q && q < nb) dinv[q] = inv;
+        if (q + 1 < PNB) {
+            double *cb = colbuf + (q & 1) * PNB;
+            if (lane < PNB) cb[lane] = lq;
+            __syncwarp();
 #pragma unroll
-        for (int c = q + 1; c < PNB; c++) a[c] = fma(-lq, __shfl_sync(0xffffffffu, lq, c), a[c]);
+            for (int c = q + 1; c < PNB; c++) a[c] = fma(-lq, cb[c], a[c]);
+        }
     }
     if (lane < nb) {
 #pragma unroll
@@ -867,27 +887,33 @@ __device__ __forceinline__ void pm_diag_factor(double *P, int ld, int nb, double
 // Rows below the diagonal block: thread i solves its own row against L11 (x L11^T = a, forward substitution in registers,
 // L11 broadcast from shared memory): 136 fp64 instructions per row, no barrier, no rsqrt.
 template <bool FULL>
+__device__ __forceinline__ void pm_row_solve_one(double *P, int ld, int i, int nb, const double *dinv)
+{
+    double a[PNB];
+#pragma unroll
+    for (int c = 0; c < PNB; c++) a[c] = (FULL || c < nb) ? P[c * ld + i] : 0.0;
+#pragma unroll
+    for (int c = 0; c < PNB; c++) {
+        if (FULL || c < nb) {
+            const double xc = a[c] * dinv[c];
+            a[c] = xc;
+#pragma unroll
+            for (int q = c + 1; q < PNB; q++)
+                if (FULL || q < nb) a[q] = fma(-xc, P[c * ld + q], a[q]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < PNB; c++)
+        if (FULL || c < nb) P[c * ld + i] = a[c];
+}
+// Phase A of a panel step: warp 0 solves the 16 rows right below the diagonal block (the rows of the NEXT diagonal block:
+// its own critical path), warps 1 .. 15 the rows beyond.
+template <bool FULL>
 __device__ __forceinline__ void pm_row_solve(double *P, int ld, int h, int nb, const double *dinv)
 {
-    const int i = nb + threadIdx.x;
-    if (i < h) {
-        double a[PNB];
-#pragma unroll
-        for (int c = 0; c < PNB; c++) a[c] = (FULL || c < nb) ? P[c * ld + i] : 0.0;
-#pragma unroll
-        for (int c = 0; c < PNB; c++) {
-            if (FULL || c < nb) {
-                const double xc = a[c] * dinv[c];
-                a[c] = xc;
-#pragma unroll
-                for (int q = c + 1; q < PNB; q++)
-                    if (FULL || q < nb) a[q] = fma(-xc, P[c * ld + q], a[q]);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < PNB; c++)
-            if (FULL || c < nb) P[c * ld + i] = a[c];
-    }
+    const int tid = threadIdx.x;
+    const int i = tid < 32 ? (tid < PNB ? nb + tid : h) : nb + PNB + (tid - 32);
+    if (i < h) pm_row_solve_one<FULL>(P, ld, i, nb, dinv);
     __syncthreads();
 }
 // acc (32 rows from a0 x 16 rows from b0, as 4 x 2 mma tiles) += L[a][q] L[b][q] over the 16 columns q of panel Pq
@@ -911,11 +937,11 @@ __device__ __forceinline__ void pm_mma_panel(double (&acc)[4][2][2], const doubl
             for (int nt = 0; nt < 2; nt++) dmma_m8n8k4(acc[mt][nt], a[mt], b[nt]);
     }
 }
-// Right-looking update of the stage's later panels with factored panel pb: S[a][b] -= sum_q L[a][q] L[b][q].
-// Work units (target panel, 32-row block) are dealt round robin to warps 1 .. 15; warp 0 takes the unit that holds the
-// diagonal block of the NEXT panel and factors that block right away (look-ahead), so the serial part of the next panel
-// step runs underneath this update.
-__device__ void pm_trailing(double *L, const int *poff, int mm, int c0, int np, int pb, double *dinv_stage)
+// Phase B of a panel step.  Warps 1 .. 15: right-looking update of the stage's later panels with factored panel pb,
+// S[a][b] -= sum_q L[a][q] L[b][q], work units (target panel, 32-row block) dealt round robin -- everything except the
+// 16 x 16 diagonal block of the NEXT panel.  Warp 0: that block (4 mma tiles), then its factorisation (look-ahead): the
+// serial part of the next panel step runs underneath the update.
+__device__ void pm_trailing(double *L, const int *poff, int mm, int c0, int np, int pb, double *dinv_stage, double *colbuf)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = lane >> 2, t4 = lane & 3;
@@ -923,46 +949,63 @@ __device__ void pm_trailing(double *L, const int *poff, int mm, int c0, int np, 
     const int cq = c0 + pb * PNB;
     const int ldq = pm_ld(mm + 1 - cq);
     const double *Pq = L + poff[pb];
-    int u = 0;  // units before this panel, not counting unit 0
-    for (int pj = pb + 1; pj < np; pj++) {
-        const int cj = c0 + pj * PNB;
-        const int hj = mm + 1 - cj, ldj = pm_ld(hj);
+    if (wid == 0) {
+        const int cj = cq + PNB;
+        const int ldj = pm_ld(mm + 1 - cj);
         const int nbj = min(PNB, mm - cj);
-        const int nrb = (hj + 31) >> 5;
-        int first, step;
-        if (pj == pb + 1) {  // row block 0 of the next panel is warp 0's; the others start at row block 1
-            first = wid == 0 ? 0 : 1 + (wid - 1 - u % NW + NW) % NW;
-            step = wid == 0 ? nrb : NW;
-        } else {
-            first = wid == 0 ? nrb : (wid - 1 - u % NW + NW) % NW;
-            step = NW;
+        double *Pj = L + poff[pb + 1];
+        double acc[2][2][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        const double *pa = Pq + t4 * ldq + PNB + g;  // rows cj + g (+ 8) of panel pb
+#pragma unroll
+        for (int q0 = 0; q0 < PNB; q0 += 4) {
+            const double f0 = pa[q0 * ldq], f1 = pa[q0 * ldq + 8];
+            dmma_m8n8k4(acc[0][0], f0, f0);
+            dmma_m8n8k4(acc[0][1], f0, f1);
+            dmma_m8n8k4(acc[1][0], f1, f0);
+            dmma_m8n8k4(acc[1][1], f1, f1);
         }
-        double *Pj = L + poff[pj];
-        for (int rb = first; rb < nrb; rb += step) {
-            const int a0 = cj + 32 * rb;
-            double acc[4][2][2];
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++)
+        for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-            pm_mma_panel(acc, Pq, ldq, cq, a0, cj, g, t4);
+            for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++)
+                for (int w = 0; w < 2; w++) {
+                    const int al = 8 * mt + g, bl = 8 * nt + 2 * t4 + w;
+                    if (al < nbj && bl <= al) Pj[bl * ldj + al] -= acc[mt][nt][w];
+                }
+        __syncwarp();
+        pm_diag_factor(Pj, ldj, nbj, dinv_stage + (pb + 1) * PNB, colbuf);
+    } else {
+        int u = 0;
+        for (int pj = pb + 1; pj < np; pj++) {
+            const int cj = c0 + pj * PNB;
+            const int hj = mm + 1 - cj, ldj = pm_ld(hj);
+            const int nbj = min(PNB, mm - cj);
+            const int nrb = (hj + 31) >> 5;
+            const int alo = pj == pb + 1 ? cj + nbj : cj;  // the next diagonal block is warp 0's
+            double *Pj = L + poff[pj];
+            for (int rb = (wid - 1 - u % NW + NW) % NW; rb < nrb; rb += NW) {
+                const int a0 = cj + 32 * rb;
+                double acc[4][2][2];
 #pragma unroll
-                for (int nt = 0; nt < 2; nt++)
+                for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                    for (int w = 0; w < 2; w++) {
-                        const int a = a0 + 8 * mt + g, bl = 8 * nt + 2 * t4 + w;
-                        if (a <= mm && bl < nbj) Pj[bl * ldj + (a - cj)] -= acc[mt][nt][w];
-                    }
-        }
-        if (pj == pb + 1) {
-            if (wid == 0) {
-                __syncwarp();
-                pm_diag_factor(Pj, ldj, nbj, dinv_stage + (pj * PNB));
+                    for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+                pm_mma_panel(acc, Pq, ldq, cq, a0, cj, g, t4);
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                        for (int w = 0; w < 2; w++) {
+                            const int a = a0 + 8 * mt + g, bl = 8 * nt + 2 * t4 + w;
+                            if (a >= alo && a <= mm && bl < nbj) Pj[bl * ldj + (a - cj)] -= acc[mt][nt][w];
+                        }
             }
-            u += nrb - 1;
-        } else {
             u += nrb;
         }
     }
@@ -1056,8 +1099,9 @@ __device__ __noinline__ void chol_panel_major(double *Sg, int lds, int mm, doubl
     // Re-derive every shared-memory pointer from the kernel's dynamic shared array: behind the call boundary of this
     // (not inlined) function the compiler would otherwise address them generically (LD.E / ST.E instead of LDS / STS,
     // 64-bit address arithmetic) -- measured 5x slower per DMMA block.
-    int *poff = reinterpret_cast<int *>(as_shared(sm.tile));  // up to 64 panel offsets
-    double *L = as_shared(sm.tile) + 32;
+    int *poff = reinterpret_cast<int *>(as_shared(sm.tile));  // header: up to 64 panel offsets | pivot-column buffer
+    double *colbuf = as_shared(sm.tile) + 32;                 // 2 * PNB doubles
+    double *L = as_shared(sm.tile) + 64;
     double *dg = as_shared(sm.dg);
     double *red = as_shared(sm.red);
     x = as_shared(x);
@@ -1075,7 +1119,7 @@ __device__ __noinline__ void chol_panel_major(double *Sg, int lds, int mm, doubl
         pm_offsets(poff, mm, c0, np);
         pm_copy<false>(L, poff, Sg, lds, mm, c0, np);
         pt.mark(10);
-        if (threadIdx.x < 32) pm_diag_factor(L + poff[0], pm_ld(mm + 1 - c0), min(PNB, mm - c0), dg + c0);
+        if (threadIdx.x < 32) pm_diag_factor(L + poff[0], pm_ld(mm + 1 - c0), min(PNB, mm - c0), dg + c0, colbuf);
         __syncthreads();
         for (int pb = 0; pb < np; pb++) {
             const int r0 = c0 + pb * PNB;
@@ -1083,7 +1127,7 @@ __device__ __noinline__ void chol_panel_major(double *Sg, int lds, int mm, doubl
             if (nb == PNB) pm_row_solve<true>(L + poff[pb], pm_ld(mm + 1 - r0), mm + 1 - r0, nb, dg + r0);
             else pm_row_solve<false>(L + poff[pb], pm_ld(mm + 1 - r0), mm + 1 - r0, nb, dg + r0);
             pt.mark(13);
-            if (pb + 1 < np) pm_trailing(L, poff, mm, c0, np, pb, dg + c0);
+            if (pb + 1 < np) pm_trailing(L, poff, mm, c0, np, pb, dg + c0, colbuf);
             pt.mark(14);
         }
         if (s + 1 < ns) {
@@ -1357,6 +1401,35 @@ __device__ __forceinline__ double row_dot(const double *row, const double *b, in
     for (int a = 0; a < m; a++) s = fma(row[a], b[a], s);
     return s;
 }
+// Linear predictor of the CTA's row slice: f(r, X_A[r] . beta) for every row r, called by the lane that owns the row.
+// A warp takes 32 rows at a time and walks each row with coalesced loads (lane = column mod 32), four rows in flight,
+// a butterfly sum per row -- the thread-per-row walk this replaces read every row as a serial chain of 32-byte sectors
+// (26 us per IRLS step at 225 rows x 203 columns; fixed summation order either way).
+template <class F>
+__device__ __forceinline__ void rows_dot(const ChainCtx &cx, const double *beta, int m, F f)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int rbase = cx.rb + wid * 32; rbase < cx.re; rbase += FIT_NT) {
+        const int nr = min(32, cx.re - rbase);
+        double mine = 0.0;
+        for (int j0 = 0; j0 < nr; j0 += 4) {
+            double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double *row = cx.XA + (size_t)(rbase + j0) * cx.ldA;
+            for (int a = lane; a < m; a += 32) {
+                const double bv = beta[a];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (j0 + u < nr) sacc[u] = fma(row[(size_t)u * cx.ldA + a], bv, sacc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double t = warp_sum(sacc[u]);
+                if (lane == j0 + u) mine = t;
+            }
+        }
+        if (lane < nr) f(rbase + lane, mine);
+    }
+}
 
 // ---- gaussian: Algorithm.h:1131-1135
 __device__ void fit_lm(const ChainCtx &cx, Clu &cl, const FitSmem &sm_, double *beta_out, double lambda)
@@ -1375,14 +1448,13 @@ __device__ double logit_eval(const ChainCtx &cx, Clu &cl, const double *beta, co
     const FitSmem sm = sm_shared(sm_);
     beta = as_shared(beta);
     double ll = 0.0;
-    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
-        const double eu = row_dot(cx.XA + (size_t)r * cx.ldA, beta, cx.m);
+    rows_dot(cx, beta, cx.m, [&](int r, double eu) {
         const double e = exp(clampd(eu, 30.0));
         const double pi = e / (1.0 + e);
         cx.v[0][r] = eu;
         cx.v[1][r] = pi;
         ll += (cx.y[r] * log(pi) + (1.0 - cx.y[r]) * log(1.0 - pi)) * cx.w[r];
-    }
+    });
     const double r = clu_allsum(cl, block_sum<FIT_NT>(ll, sm.red));
     cl.pt.mark(PH_EVAL);
     return r;
@@ -1429,11 +1501,10 @@ __device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const 
     const int ldA = cx.ldA;
     for (int a = threadIdx.x; a < cx.m; a += FIT_NT) b0[a] = a == 0 ? coef0_in : 0.0;
     __syncthreads();
-    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
-        const double eta = row_dot(cx.XA + (size_t)r * ldA, b0, cx.m);
+    rows_dot(cx, b0, cx.m, [&](int r, double eta) {
         cx.v[0][r] = eta;
         cx.v[1][r] = exp(eta);
-    }
+    });
     __syncthreads();
     double ll0 = 1e5;
     for (int j = 0; j < 50; j++) {
@@ -1445,14 +1516,14 @@ __device__ void fit_poisson(const ChainCtx &cx, Clu &cl, double coef0_in, const 
         __syncthreads();
         gram_solve(cx, cl, cx.XA, ldA, cx.m + 1, cx.v[2], b0, sm, 2.0 * lambda, 1);
         double ll = 0.0;
-        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
-            const double eta = clampd(row_dot(cx.XA + (size_t)r * ldA, b0, cx.m), 30.0);
+        rows_dot(cx, b0, cx.m, [&](int r, double dot) {
+            const double eta = clampd(dot, 30.0);
             double e = exp(eta);
             if (e < 0.001) e = 0.001;
             cx.v[0][r] = eta;
             cx.v[1][r] = e;
             ll += (cx.y[r] * eta - e) * cx.w[r];
-        }
+        });
         const double ll1 = clu_allsum(cl, block_sum<FIT_NT>(ll, sm.red));
         if (fabs(ll0 - ll1) / fabs(0.1 + ll0) < 1e-6) break;
         ll0 = ll1;
@@ -1499,11 +1570,11 @@ __device__ double cox_loglik(const ChainCtx &cx, Clu &cl, const double *beta, do
 {
     const FitSmem sm = sm_shared(sm_);
     beta = as_shared(beta);
-    for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
-        const double t = exp(clampd(row_dot(cx.XA + (size_t)r * cx.ldA, beta, cx.m), 30.0));
+    rows_dot(cx, beta, cx.m, [&](int r, double dot) {
+        const double t = exp(clampd(dot, 30.0));
         th[r] = t;
         s0[r] = t;
-    }
+    });
     __syncthreads();
     clu_suffix_scan(cx, cl, s0, sm);
     double ll = 0.0;
@@ -1575,11 +1646,11 @@ __device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &
     double ll0 = 1e5;
     for (int l = 1; l <= max_newton; l++) {
         // theta (no weights here, Algorithm.h:1423), S0
-        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) {
-            const double t = exp(clampd(row_dot(cx.XA + (size_t)r * ldA, b0, m), 30.0));
+        rows_dot(cx, b0, m, [&](int r, double dot) {
+            const double t = exp(clampd(dot, 30.0));
             th[r] = t;
             s0[r] = t;
-        }
+        });
         __syncthreads();
         clu_suffix_scan(cx, cl, s0, sm);
         // e = w*status; C = prefix(e/S0); omega = theta*C; gvec = e - omega
