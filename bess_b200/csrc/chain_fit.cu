@@ -394,7 +394,7 @@ __device__ __forceinline__ void cf_mbar_wait(uint64_t *bar, uint32_t parity)
 constexpr int GRAM_DMMA_MIN = 56;  // systems wider than this take the tensor-core path (probe: FMA path 11 us vs 16 us at 32, 44 vs 26 at 97)
 constexpr int GRAM_NS = 3;  // ring stages
 constexpr int GRAM_GT = 3;  // 16 x 16 tiles a warp accumulates at once
-__device__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
+__device__ __noinline__ void block_syrk_dmma(const double *V, int ldv, int r0, int r1, int mm, const double *wt, double *S, int lds,
                                 const FitSmem &sm_)
 {
     const FitSmem sm = sm_shared(sm_);
@@ -636,7 +636,7 @@ __device__ __forceinline__ void panel_factor(RowPtr rowp, int mr, int nb, double
 // panels (panel_factor + register-blocked 4x4 trailing update) and back-substituted in place.  x (smem) <- solution.
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 __device__ __forceinline__ bool packed_fits(int mm, int arena_len) { return tri(mm + 1) + FIT_NT <= arena_len; }
-__device__ void chol_packed_smem(const double *Sg, int lds, int mm, double *x, const FitSmem &sm_, PhaseTimer &pt)
+__device__ __noinline__ void chol_packed_smem(const double *Sg, int lds, int mm, double *x, const FitSmem &sm_, PhaseTimer &pt)
 {
     const FitSmem sm = sm_shared(sm_);
     constexpr int NB = CHOL_NB;
@@ -1402,33 +1402,51 @@ __device__ __forceinline__ double row_dot(const double *row, const double *b, in
     return s;
 }
 // Linear predictor of the CTA's row slice: f(r, X_A[r] . beta) for every row r, called by the lane that owns the row.
-// A warp takes 32 rows at a time and walks each row with coalesced loads (lane = column mod 32), four rows in flight,
-// a butterfly sum per row -- the thread-per-row walk this replaces read every row as a serial chain of 32-byte sectors
-// (26 us per IRLS step at 225 rows x 203 columns; fixed summation order either way).
+// Groups of 8 consecutive rows are dealt round robin to the 16 warps; a warp walks its 8 rows with coalesced loads
+// (lane = column mod 32, 16 loads in flight per lane), a butterfly sum per row, and parks the results on distinct lanes
+// until 32 rows are ready for f -- the thread-per-row walk this replaces read every row as a serial chain of 32-byte
+// sectors (26 us per IRLS step at 225 rows x 203 columns; fixed summation order either way).
 template <class F>
 __device__ __forceinline__ void rows_dot(const ChainCtx &cx, const double *beta, int m, F f)
 {
+    constexpr int GR = 8;
+    if (m < 64) {  // narrow supports: a thread per row, the row's few sectors stay in L1 between its loads
+        for (int r = cx.rb + threadIdx.x; r < cx.re; r += FIT_NT) f(r, row_dot(cx.XA + (size_t)r * cx.ldA, beta, m));
+        return;
+    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int rbase = cx.rb + wid * 32; rbase < cx.re; rbase += FIT_NT) {
-        const int nr = min(32, cx.re - rbase);
-        double mine = 0.0;
-        for (int j0 = 0; j0 < nr; j0 += 4) {
-            double sacc[4] = {0.0, 0.0, 0.0, 0.0};
-            const double *row = cx.XA + (size_t)(rbase + j0) * cx.ldA;
-            for (int a = lane; a < m; a += 32) {
-                const double bv = beta[a];
+    const int ngroups = (cx.re - cx.rb + GR - 1) / GR;
+    double mine = 0.0;
+    int myrow = -1, slot = 0;
+    for (int gi = wid; gi < ngroups; gi += FIT_NT / 32) {
+        const int rbase = cx.rb + gi * GR;
+        const int nr = min(GR, cx.re - rbase);
+        const double *row = cx.XA + (size_t)rbase * cx.ldA;
+        double sacc[GR];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (j0 + u < nr) sacc[u] = fma(row[(size_t)u * cx.ldA + a], bv, sacc[u]);
-            }
+        for (int u = 0; u < GR; u++) sacc[u] = 0.0;
+#pragma unroll 2
+        for (int a = lane; a < m; a += 32) {
+            const double bv = beta[a];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const double t = warp_sum(sacc[u]);
-                if (lane == j0 + u) mine = t;
+            for (int u = 0; u < GR; u++)
+                if (u < nr) sacc[u] = fma(row[(size_t)u * cx.ldA + a], bv, sacc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < GR; u++) {
+            const double t = warp_sum(sacc[u]);
+            if (lane == slot * GR + u && u < nr) {
+                mine = t;
+                myrow = rbase + u;
             }
         }
-        if (lane < nr) f(rbase + lane, mine);
+        if (++slot == 32 / GR) {
+            if (myrow >= 0) f(myrow, mine);
+            slot = 0;
+            myrow = -1;
+        }
     }
+    if (myrow >= 0) f(myrow, mine);
 }
 
 // ---- gaussian: Algorithm.h:1131-1135

@@ -14,7 +14,7 @@ from tests.helpers import FULL_CONFIGS  # noqa: E402
 
 FAM = {"gaussian": (1, 1), "binomial": (2, 2), "poisson": (3, 2), "cox": (4, 3)}
 NAMES = ["gather", "eval", "wz", "syrk", "reduce", "chol/back", "bcast", "grad", "cycle", "other", "c:load", "c:diag", "c:rows",
-         "c:wb+syncA", "c:upd+syncB", "-"]
+         "c:wb+syncA", "c:upd+syncB", "dot"]
 
 
 def main():
