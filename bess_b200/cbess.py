@@ -156,7 +156,8 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
                           kernel_launches=int(stats[6]), big_sweep_bytes=float(stats[24]),
                           sweep_splits=int(stats[25]), norm_bytes=float(stats[26]),
                           host_ms=dict(zip(("load", "screen", "normalize", "setup_chains", "path"), stats[27:32].tolist())),
-                          resident=resident.tolist(), tie_exact_pass=bool(tie_exact.value),
+                          resident=resident.tolist(), tie_exact_pass=bool(tie_exact.value & 1),
+                          robust_pass=bool(tie_exact.value & 2), rank_deficient=bool(tie_exact.value & 4),
                           prof_ms=dict(zip(PROF_CATS, stats[8:16].tolist())),
                           prof_launches=dict(zip(PROF_CATS, [int(v) for v in stats[16:24]]))))
     if is_screening:

@@ -113,7 +113,8 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
             if (ext->chosen_s_out) *ext->chosen_s_out = r.chosen_s;
             if (ext->chosen_lambda_out) *ext->chosen_lambda_out = r.lambda;
             if (ext->resident_out) std::copy(r.resident, r.resident + 24 + 4 * MAXC, ext->resident_out);
-            if (ext->tie_exact_out) *ext->tie_exact_out = r.tie_exact_pass ? 1 : 0;
+            if (ext->tie_exact_out)
+                *ext->tie_exact_out = (r.tie_exact_pass ? 1 : 0) | (r.robust_pass ? 2 : 0) | (r.stats.n_rank_deficient > 0 ? 4 : 0);
             if (ext->stats_out) {
                 ext->stats_out[0] = (double)r.stats.n_fits;
                 ext->stats_out[1] = (double)r.stats.n_pdas_iters;

@@ -564,12 +564,18 @@ __device__ __forceinline__ void gram(const double *V, int ldv, int r0, int r1, i
 //  this path the solutions agree to ~1e-13 relative.)
 // =====================================================================================================
 // unblocked, for systems resident in shared memory
-__device__ void block_chol_solve_small(double *S, int lds, int mm, double *x, double *dg)
+// A pivot at or below PIVOT_TOL times the column's own diagonal entry (its squared norm) is a numerically dependent column.
+constexpr double PIVOT_TOL = 1e-13;
+__device__ unsigned long long g_rankdef_count = 0ull;  // truncated (rank-deficient) solves since the last debug_take_rankdef()
+// S0: pristine copy of the system (same layout).  Returns false -- S is then garbage -- when a pivot fails the test above.
+__device__ bool block_chol_solve_small(double *S, int lds, int mm, double *x, double *dg, const double *S0)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int j = 0; j < mm; j++) {
         __syncthreads();
-        const double djj = sqrt(S[(size_t)j * lds + j]);
+        const double sjj = S[(size_t)j * lds + j];
+        if (!(sjj > PIVOT_TOL * S0[(size_t)j * lds + j])) return false;  // uniform over the CTA (NaN fails too)
+        const double djj = sqrt(sjj);
         if (tid == 0) dg[j] = djj;
         const double inv = 1.0 / djj;
         for (int i = j + 1 + tid; i <= mm; i += FIT_NT) S[(size_t)i * lds + j] *= inv;
@@ -591,6 +597,96 @@ __device__ void block_chol_solve_small(double *S, int lds, int mm, double *x, do
             for (int c = lane; c < j; c += 32) x[c] -= S[(size_t)j * lds + c] * xj;
             __syncwarp();
         }
+    }
+    __syncthreads();
+    return true;
+}
+
+// Rank-revealing fallback for the systems above (<= FIT_SMEM_MS unknowns, both triangles of S valid, border row mm = right-
+// hand side): LDL^T with Eigen's diagonal pivoting -- at step k the FIRST largest diagonal entry in the current positional
+// order of the remaining unknowns, swapped into position k, the unknown that sat there moving back to where the pivot came
+// from (Eigen/src/Cholesky/LDLT.h:300-330) -- that STOPS when no remaining pivot passes the PIVOT_TOL test; the unknowns
+// left over get 0.  This is what the reference's solvers return on a singular system with an exactly duplicated column:
+// the pivoted ldlt() meets an exactly zero pivot and its solve() skips it (LDLT.h:558-592), colPivHouseholderQr()
+// truncates at its rank threshold (Algorithm.h:1134) -- one copy keeps the whole coefficient, the other gets 0.  (Which
+// copy: the one met first in the positional order, as in the LDLT; the QR's own order can differ -- the two models are
+// the same function of the data.)  work: >= 3 * (mm + 1) doubles.
+__device__ void ldlt_pivoted_small(double *S, int lds, int mm, double *x, const double *S0, double *work)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *lcol = work;                                       // [mm + 1] multipliers of the running step
+    int *perm = reinterpret_cast<int *>(work + mm + 1);        // [mm] unknown at position q; then perm[mm] = step's pivot position
+    int *posof = perm + mm + 1;                                // [mm] position of unknown i
+    for (int i = tid; i < mm; i += FIT_NT) {
+        perm[i] = i;
+        posof[i] = i;
+        x[i] = 0.0;
+    }
+    __syncthreads();
+    int rank = 0;
+    for (; rank < mm; rank++) {
+        const int k = rank;
+        if (wid == 0) {
+            double best = -1.0;
+            int bpos = -1;
+            for (int pos = k + lane; pos < mm; pos += 32) {
+                const int p = perm[pos];
+                const double v = S[(size_t)p * lds + p];
+                if (v > PIVOT_TOL * S0[(size_t)p * lds + p] && v > best) {
+                    best = v;
+                    bpos = pos;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+                if (op >= 0 && (bpos < 0 || ov > best || (ov == best && op < bpos))) {
+                    best = ov;
+                    bpos = op;
+                }
+            }
+            if (lane == 0) {
+                perm[mm] = bpos;
+                if (bpos >= 0) {
+                    const int pk = perm[k], pb = perm[bpos];
+                    perm[k] = pb;
+                    perm[bpos] = pk;
+                    posof[pb] = k;
+                    posof[pk] = bpos;
+                }
+            }
+        }
+        __syncthreads();
+        if (perm[mm] < 0) break;
+        const int p = perm[k];
+        const double dinv = 1.0 / S[(size_t)p * lds + p];
+        for (int i = tid; i <= mm; i += FIT_NT)
+            if (i == mm || posof[i] > k) lcol[i] = S[(size_t)i * lds + p] * dinv;
+        __syncthreads();
+        for (int e = tid; e < (mm + 1) * mm; e += FIT_NT) {
+            const int i = e / mm, c = e - i * mm;
+            if ((i == mm || posof[i] > k) && posof[c] > k) S[(size_t)i * lds + c] -= lcol[i] * S[(size_t)p * lds + c];
+        }
+        __syncthreads();
+        for (int i = tid; i < mm; i += FIT_NT)
+            if (posof[i] > k) S[(size_t)i * lds + p] = lcol[i];  // kept for the back substitution
+        __syncthreads();
+    }
+    // back substitution in reverse pivot order: x_p = y_p / d_p - sum over later pivots q of l_qp x_q
+    if (wid == 0) {
+        for (int k = rank - 1; k >= 0; k--) {
+            const int p = perm[k];
+            double acc = 0.0;
+            for (int t = k + 1 + lane; t < rank; t += 32) {
+                const int q = perm[t];
+                acc = fma(S[(size_t)q * lds + p], x[q], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) x[p] = S[(size_t)mm * lds + p] / S[(size_t)p * lds + p] - acc;
+            __syncwarp();
+        }
+        if (lane == 0 && rank < mm) atomicAdd(&g_rankdef_count, 1ull);
     }
     __syncthreads();
 }
@@ -1295,7 +1391,20 @@ __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds,
     const FitSmem sm = sm_shared(sm_);
     out = as_shared(out);
     if (S == sm.Ssm) {
-        if (cl.rank == 0) block_chol_solve_small(S, lds, nu, sm.rhs, sm.dg);
+        if (cl.rank == 0) {
+            // pristine copy (the scratch region is free here): the pivot test of the factorisation compares against it,
+            // and a rank-deficient system is solved again from it by the rank-revealing fallback
+            double *S0 = sm.scratch;
+            __syncthreads();
+            for (int e = threadIdx.x; e < (nu + 1) * lds; e += FIT_NT) S0[e] = S[e];
+            __syncthreads();
+            if (!block_chol_solve_small(S, lds, nu, sm.rhs, sm.dg, S0)) {
+                __syncthreads();
+                for (int e = threadIdx.x; e < (nu + 1) * lds; e += FIT_NT) S[e] = S0[e];
+                __syncthreads();
+                ldlt_pivoted_small(S, lds, nu, sm.rhs, S0, sm.tile);
+            }
+        }
     } else if (g_dbg_solver == 0 && nu < FIT_NT && pm_stage_count(nu, sm.arena_len) <= PM_MAX_STAGES) {
         if (cl.rank == 0) chol_panel_major(S, lds, nu, sm.rhs, sm, cl.pt);
     } else if (packed_fits(nu, sm.arena_len)) {
@@ -2175,6 +2284,14 @@ void debug_gram(const double *V, int ldv, int nrows, int mm, const double *wt, d
     CUDA_CHECK(cudaMemcpy(&ht, dt, 8, cudaMemcpyDeviceToHost));
     if (ticks_out) *ticks_out = (double)ht;
     cudaFree(dV); cudaFree(dw); cudaFree(dS); cudaFree(dt);
+}
+
+long long debug_take_rankdef()
+{
+    unsigned long long v = 0ull, z = 0ull;
+    CUDA_CHECK(cudaMemcpyFromSymbol(&v, g_rankdef_count, sizeof(v)));
+    if (v) CUDA_CHECK(cudaMemcpyToSymbol(g_rankdef_count, &z, sizeof(z)));
+    return (long long)v;
 }
 
 void debug_set(int key, int val)

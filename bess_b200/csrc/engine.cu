@@ -1446,6 +1446,7 @@ static void lp_parse(Engine::Impl &m, const Engine::Impl::Ticket &t, EngineStats
             stats.n_boundary_ties += ri[1];
         }
     }
+    stats.n_suspect_pivots += sy[LP_SYNC_RANKDEF];
     if (m.lp_trace) {  // developer aid: time line of the owner phases and of sweeper 0 ($BESS_B200_TRACE = output file)
         std::vector<unsigned long long> tr((size_t)(MAXC + 1) * LP_TRACE * 2);
         CUDA_CHECK(cudaMemcpy(tr.data(), m.lp_trace, tr.size() * 8, cudaMemcpyDeviceToHost));

@@ -180,6 +180,8 @@ int chain_cluster_size(const Dev &d, int T, int nch);
 void configure_kernels();
 void debug_set(int key, int val);
 void debug_get(unsigned long long *out32);
+// truncated (rank-deficient) normal-equation solves of the chain kernels since the last call (synchronises the device)
+long long debug_take_rankdef();
 void debug_solve(const double *S, int lds, int mm, double *x_out, int impl, int reps, double *ticks_out);
 void debug_gram(const double *V, int ldv, int nrows, int mm, const double *wt, double *S_out, int impl, int reps,
                 double *ticks_out);

@@ -1237,6 +1237,14 @@ __device__ void owner_main(const Dev &d, const LpDesc &L, unsigned char *raw)
                     tm.mark(8);
                     own_fb += (unsigned long long)(k - q) * 1965ull;  // DEBUG: new rows per fit (x1965 so the us conversion shows the count)
                     chol_solve(s, k, q);
+                    // A pivot at or below 1e-13 of its column's own squared norm (or a NaN) is a numerically dependent
+                    // active column (e.g. an exact duplicate): this kernel's plain Cholesky has no answer for it.  Flag
+                    // the launch; the host repeats the call on the multi-kernel path, whose solver truncates the way the
+                    // reference's colPivHouseholderQr does (chain_fit.cu: ldlt_pivoted_small).
+                    for (int t2 = tid; t2 < k; t2 += LP_NT) {
+                        const double gjj = s.Gc[(size_t)s.ord[t2] * ns + s.ord[t2]] + lam, dv = s.dg[t2];
+                        if (!(dv * dv * gjj * 1e-13 < 1.0)) atomicAdd(L.sync + LP_SYNC_RANKDEF, 1u);
+                    }
                     kfac = k;
                     lam_fact = lam;
                     for (int a2 = tid; a2 < k; a2 += LP_NT) s.beta[a2] = s.bage[s.pos[s.slotNew[a2]]];  // back to ascending column order

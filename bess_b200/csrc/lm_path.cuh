@@ -23,7 +23,7 @@ struct LpCand {
 
 // words of LpDesc::sync.  B1 / B2 have one counter per chain group.
 enum { LP_SYNC_B1 = 0, LP_SYNC_B2 = 2, LP_SYNC_NCOMPLETE = 4, LP_SYNC_TERM = 5, LP_SYNC_ITERS = 6, LP_SYNC_ABORT = 7,
-       LP_SYNC_FALLBACKS = 8, LP_SYNC_MERGED = 9, LP_SYNC_WORDS = 16 };
+       LP_SYNC_FALLBACKS = 8, LP_SYNC_MERGED = 9, LP_SYNC_RANKDEF = 10, LP_SYNC_WORDS = 16 };
 
 // One launch = `nsteps` path steps for the chains of one batch.  Passed by value.
 struct LpDesc {

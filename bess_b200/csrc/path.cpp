@@ -1,6 +1,7 @@
 // Host path driver.  See path.h.  Every numerical step runs on the GPU through bess::Engine; this file only
 // decides which sparsity level to evaluate next and applies the scalar criterion / de-normalisation formulas.
 #include "path.h"
+#include "kernels.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -821,6 +822,7 @@ static void bess_run_once(const BessArgs &a, BessResult &out, bool tie_exact)
     for (auto &A : out.A_all)
         for (int &j : A) j = orig(j);
     out.stats = eng.stats();
+    out.stats.n_rank_deficient += debug_take_rankdef();
     eng.profile(out.prof_ms, out.prof_n);
     out.sweep_splits = eng.sweep_splits();
     eng.resident_counters(out.resident);
@@ -839,11 +841,20 @@ void bess_run(const BessArgs &a, BessResult &out)
         const char *e = std::getenv("BESS_B200_TIE_EXACT");
         return !(e && e[0] == '0');
     }();
-    if (redo && out.stats.n_boundary_ties > 0 && a.world <= 1) {
+    // A dependent column inside an active set (an exact duplicate both of whose copies were selected, e.g. by a cold
+    // start): the resident kernel flags it (its plain Cholesky has no answer), and a non-finite result says the same of a
+    // wide system.  The exact mode runs on the multi-kernel path, whose small-system solver falls back to a rank-revealing
+    // LDL^T that truncates like the reference's colPivHouseholderQr / pivoted ldlt (chain_fit.cu: ldlt_pivoted_small).
+    bool finite = std::isfinite(out.train_loss) && std::isfinite(out.ic) && std::isfinite(out.coef0);
+    for (double v : out.beta_val) finite = finite && std::isfinite(v);
+    const bool suspect = out.stats.n_suspect_pivots > 0 || !finite;
+    if (redo && (out.stats.n_boundary_ties > 0 || suspect) && a.world <= 1) {
+        const bool ties = out.stats.n_boundary_ties > 0;
         BessResult exact;
         bess_run_once(a, exact, true);
         out = std::move(exact);
-        out.tie_exact_pass = true;
+        out.tie_exact_pass = ties;
+        out.robust_pass = suspect;
     }
 }
 

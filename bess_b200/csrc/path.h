@@ -76,6 +76,8 @@ struct BessResult {
     long long prof_n[PROF_NCAT] = {};
     int sweep_splits = 1;
     bool tie_exact_pass = false;  // the call met a boundary tie and was repeated with host-resolved selections
+    bool robust_pass = false;     // the fast pass met a dependent active column (or a non-finite result) and the call was
+                                  // repeated on the multi-kernel path, whose solver is rank-revealing
     double resident[24 + 4 * MAXC] = {};  // Engine::resident_counters (24) + resident_owner_counters (4 per chain)
     // host wall-clock of the call by phase (ms): 0 engine + load (+ upload), 1 screening, 2 normalisation, 3 fold / chain
     // set-up, 4 the path itself

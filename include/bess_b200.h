@@ -84,8 +84,12 @@ typedef struct bess_b200_ext {
                                 /* own folds (cv_seed / fold_of_row), the per-level CV losses are averaged over the ranks   */
                                 /* (one ncclAllReduce) before the level is chosen; all ranks return the same model          */
     int cv_seed_set;            /* non-zero: cv_seed is taken as given, INCLUDING 0 (cv_seed == 0 alone means "default")     */
-    int *tie_exact_out;         /* 1 when the call met a boundary tie of a top-k selection and was repeated with the tied     */
-                                /* selections resolved by the reference's own std::nth_element (utilities.cpp:179-188)         */
+    int *tie_exact_out;         /* bit 0: the call met a boundary tie of a top-k selection and was repeated with the tied     */
+                                /* selections resolved by the reference's own std::nth_element (utilities.cpp:179-188);        */
+                                /* bit 1: the fast pass met a numerically dependent active column (or a non-finite result)     */
+                                /* and the call was repeated with the rank-revealing solver; bit 2: at least one normal-      */
+                                /* equation solve was truncated the way colPivHouseholderQr / pivoted ldlt truncate            */
+                                /* (Algorithm.h:1134, 1171; an exactly duplicated column inside the active set)                */
     double *resident_out;       /* [152] counters of the resident-path kernel (gaussian family, design resident in L2: the   */
                                 /* whole PDAS path is ONE cooperative launch): 0 launches, 1 PDAS iterations, 2 full-vector */
                                 /* select fallbacks, 3 path steps, 8..15 clock ticks by phase of chain owner 0, 16..18 of    */

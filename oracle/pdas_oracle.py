@@ -150,10 +150,62 @@ def loglik_poiss(x, y, coef, weights):
 # --------------------------------------------------------------------------------------
 # primary_model_fit x4: Algorithm.h:1131-1135, 1148-1204, 1273-1322, 1377-1490
 # --------------------------------------------------------------------------------------
+PIVOT_TOL = 1e-13
+
+
+def solve_rank_revealing(G, b):
+    """The normal-equation solve of primary_model_fit on a system that may be singular.  The reference factors with
+    colPivHouseholderQr (Algorithm.h:1134) / Eigen's pivoted ldlt (:1171, :1299); on an active set that holds an EXACTLY
+    duplicated column both drop the second copy -- the QR truncates at its rank threshold, the LDLT meets an exactly zero
+    pivot that its solve() skips (Eigen/src/Cholesky/LDLT.h:558-592) -- and the unknown gets a zero coefficient.
+    Full-rank systems take numpy's LU; a system whose Cholesky pivots fall to PIVOT_TOL of the column's own diagonal is
+    solved by LDL^T with Eigen's diagonal pivoting that stops when no remaining pivot passes that bound and leaves the
+    remaining unknowns at 0."""
+    G = np.asarray(G, dtype=np.float64)
+    dg = np.diag(G)
+    try:
+        L = np.linalg.cholesky(G)
+        if np.all(np.diag(L) ** 2 > PIVOT_TOL * dg):
+            return np.linalg.solve(G, b)
+    except np.linalg.LinAlgError:
+        pass
+    m = G.shape[0]
+    S = G.copy()
+    y = np.asarray(b, dtype=np.float64).copy()
+    # Eigen's pivoting (LDLT.h:300-330): at step k the FIRST largest diagonal entry in the current positional order of the
+    # remaining unknowns, which is then swapped into position k -- the unknown that sat at k moves back to where the
+    # pivot came from.  Which copy of a duplicated column is met first therefore depends on the swaps made so far.
+    perm = list(range(m))
+    mult = {}
+    rank = 0
+    for k in range(m):
+        best, bpos = -1.0, -1
+        for pos in range(k, m):
+            p = perm[pos]
+            if S[p, p] > PIVOT_TOL * dg[p] and S[p, p] > best:
+                best, bpos = S[p, p], pos
+        if bpos < 0:
+            break
+        perm[k], perm[bpos] = perm[bpos], perm[k]
+        p = perm[k]
+        rest = np.zeros(m, dtype=bool)
+        rest[perm[k + 1:]] = True
+        l = np.where(rest, S[:, p] / S[p, p], 0.0)
+        S[np.ix_(rest, rest)] -= np.outer(l[rest], S[p, rest])
+        y[rest] -= l[rest] * y[p]
+        mult[p] = l
+        rank += 1
+    x = np.zeros(m)
+    for k in range(rank - 1, -1, -1):
+        p = perm[k]
+        x[p] = y[p] / S[p, p] - sum(mult[p][q] * x[q] for q in perm[k + 1:rank])
+    return x
+
+
 def fit_lm(XA, y, w, coef0, lam=0.0):
     """Algorithm.h:1131-1135.  coef0 untouched.  lam: X'X + lambda*I (:1134, not 2*lambda, not scaled by n)."""
     G = XA.T @ XA + lam * np.eye(XA.shape[1])
-    beta = np.linalg.solve(G, XA.T @ y)
+    beta = solve_rank_revealing(G, XA.T @ y)
     return beta, coef0
 
 
@@ -177,7 +229,7 @@ def fit_logistic(XA, y, w, coef0, floor_w=True, lam=0.0):
     W = Pi * (1 - Pi)
     Z = X @ beta0 + (y - Pi) / W
     W = W * w
-    beta1 = np.linalg.solve(lmat + (X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
+    beta1 = solve_rank_revealing(lmat + (X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
     for _ in range(30):
         Pi = _pi(X, beta1)
         ll1 = float((y * np.log(Pi) + (1 - y) * np.log(1 - Pi)) @ w)
@@ -190,7 +242,7 @@ def fit_logistic(XA, y, w, coef0, floor_w=True, lam=0.0):
             W = np.maximum(W, 0.001)
         Z = X @ beta0 + (y - Pi) / W
         W = W * w
-        beta1 = np.linalg.solve(lmat + (X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
+        beta1 = solve_rank_revealing(lmat + (X * W[:, None]).T @ X, (X * W[:, None]).T @ Z)
     return beta0[1:].copy(), float(beta0[0])
 
 
@@ -209,7 +261,7 @@ def fit_poisson(XA, y, w, coef0, lam=0.0):
         ww = expeta * w
         z = eta + (y - expeta) / expeta
         XtW = (X * ww[:, None]).T
-        beta0 = np.linalg.solve(lmat + XtW @ X, XtW @ z)
+        beta0 = solve_rank_revealing(lmat + XtW @ X, XtW @ z)
         eta = _clip(X @ beta0, 30.0)
         expeta = np.maximum(np.exp(eta), 0.001)
         ll1 = float((y * eta - expeta) @ w)

@@ -43,6 +43,14 @@ def banded_design(n, p, rho, rng):
     return X + rho * (np.hstack((zero, X[:, 0:(p - 2)], zero)) + np.hstack((zero, X[:, 2:p], zero)))
 
 
+def dupsig_design(n, p_true, p_noise, rng):
+    """[true columns | exact copies of the true columns | noise columns]: with COLD starts every level's first selection
+    (beta = 0: the copies tie with the originals at the top of the ranking) puts both copies of a signal column into the
+    active set -- a singular Gram that the reference's colPivHouseholderQr / pivoted ldlt truncate (Algorithm.h:1134, 1171)."""
+    base = rng.standard_normal((n, p_true + p_noise))
+    return np.ascontiguousarray(np.hstack((base[:, :p_true], base[:, :p_true], base[:, p_true:])))
+
+
 def dup_design(n, p_true, p_noise, rng):
     """[true columns | noise columns | exact copies of the noise columns]"""
     base = rng.standard_normal((n, p_true + p_noise))
@@ -69,12 +77,28 @@ CASES = {
     "k20_lm_seq_cv": ("gaussian", ("ar", 0.5), 240, 200, 5, 1, True, 20, 1, 8, 0, False, 20, 131),
     "k20_logit_seq_cv": ("binomial", ("ar", 0.5), 300, 150, 4, 1, True, 20, 1, 6, 0, False, 20, 132),
     "iter_lm_seq_gic": ("gaussian", ("ar", 0.9), 150, 300, 8, 1, False, 5, 3, 14, 0, False, 100, 133),
+    # rank-deficient active sets (cold starts; see dupsig_design).  Which copy of a duplicated column a singular solve keeps
+    # follows the reference's pivot order (reproducible for these seeds: Eigen's positional LDLT pivoting; for other draws
+    # the reference's choice between the two equivalent copies rides on rounding noise -- e.g. seed 12 with 4 signal
+    # columns agrees on the chosen model but not on every level of the trace, poisson / cox not at all -- no golden there)
+    "dupsig_lm_seq_gic": ("gaussian", ("dupsig", 3, 40), 150, 46, 3, 1, False, 4, 3, 7, 0, False, 20, 7),
+    "dupsig_lm_gs_gic": ("gaussian", ("dupsig", 3, 40), 150, 46, 3, 2, False, 4, 3, 7, 0, False, 20, 7),
+    "dupsig_lm_seq_cv": ("gaussian", ("dupsig", 3, 40), 150, 46, 3, 1, True, 4, 1, 7, 0, False, 20, 7),
+    "dupsig_logit_seq_gic": ("binomial", ("dupsig", 3, 40), 150, 46, 3, 1, False, 4, 3, 7, 0, False, 20, 7),
+    "dupsig_logit_seq_cv": ("binomial", ("dupsig", 3, 40), 150, 46, 3, 1, True, 4, 1, 7, 0, False, 20, 7),
 }
+COLD = {name for name in CASES if name.startswith("dupsig_")}
 
 
 def build(name):
     fam, design, n, p, k, path_type, is_cv, K, ic_type, smax, scr, weighted, max_iter, seed = CASES[name]
     rng = np.random.Generator(np.random.PCG64(seed))
+    if design[0] == "dupsig":
+        base = rng.standard_normal((n, design[1] + design[2]))
+        x = np.ascontiguousarray(np.hstack((base[:, :design[1]], base[:, :design[1]], base[:, design[1]:])))
+        assert x.shape[1] == p
+        d = gen_data(n, design[1], fam, k, seed=seed, x=np.ascontiguousarray(base[:, :design[1]]))
+        return x, d.y
     if design[0] == "dup":
         x = dup_design(n, design[1], design[2], rng)
         assert x.shape[1] == p
@@ -109,15 +133,16 @@ def main():
         w = rng.uniform(0.5, 1.5, n) if weighted else np.ones(n)
         seq = np.arange(1, smax + 1, dtype=np.int32)
         fold = ref.cv_fold_ids(n, K) if is_cv else np.zeros(n, dtype=np.int32)
-        r = ref.pywrap_bess(x, y, data_type, w, True, 1, model_type, max_iter, 2, path_type, True, ic_type, is_cv, K,
+        warm = name not in COLD
+        r = ref.pywrap_bess(x, y, data_type, w, True, 1, model_type, max_iter, 2, path_type, warm, ic_type, is_cv, K,
                             seq, 1, smax, scr > 0, scr if scr > 0 else 1)
         out = dict(x=x, y=y, weight=w, fold_of_row=fold, beta=r["beta"], coef0=r["coef0"], train_loss=r["train_loss"], ic=r["ic"],
                    meta=np.array([model_type, data_type, path_type, int(is_cv), K, ic_type, smax, scr], dtype=np.int64),
-                   max_iter=np.int64(max_iter))
+                   max_iter=np.int64(max_iter), warm=np.int64(warm))
         if scr > 0:
             out["screening_A"] = ref.screening(x, y, w, model_type, scr)
         elif path_type == 1:
-            t = ref.seq_trace(x, y, w, data_type, True, model_type, max_iter, True, ic_type, is_cv, K, seq)
+            t = ref.seq_trace(x, y, w, data_type, True, model_type, max_iter, warm, ic_type, is_cv, K, seq)
             out.update({k2: v for k2, v in t.items()})
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
         print(name, "support", np.nonzero(r["beta"])[0].tolist(), "ic", r["ic"], flush=True)

@@ -106,10 +106,29 @@ def hard_golden_names():
 
 def load_hard_golden(name):
     """tests/golden/hard/*.npz (made by tests/golden/hard/make_hard.py from the real reference): boundary ties from
-    duplicated columns, correlated designs (rho = 0.5 / 0.9, banded), 20 folds, max_iter = 100."""
+    duplicated columns, correlated designs (rho = 0.5 / 0.9, banded), 20 folds, max_iter = 100, and dupsig_*: duplicated
+    SIGNAL columns under cold starts -- both copies enter the active set, the Gram is singular, the reference's
+    colPivHouseholderQr / pivoted ldlt truncate."""
     g = dict(np.load(os.path.join(HARD_DIR, name + ".npz")))
     m = g["meta"]
     g["model_type"], g["data_type"], g["path_type"], g["is_cv"], g["K"], g["ic_type"], g["smax"], g["scr"] = (
         int(m[0]), int(m[1]), int(m[2]), bool(m[3]), int(m[4]), int(m[5]), int(m[6]), int(m[7]))
     g["max_iter"] = int(g["max_iter"])
+    g["warm"] = bool(g["warm"]) if "warm" in g else True  # dupsig_*: cold starts (rank-deficient active sets)
     return g
+
+
+def fold_duplicates(x, beta):
+    """Coefficients summed over exactly duplicated columns of x onto the first copy (the last axis of beta indexes the
+    columns).  Two models that differ only in WHICH copy of a duplicated column carries the coefficient are the same
+    function of the data; the reference's own choice rides on its pivot order (tests/golden/hard/make_hard.py)."""
+    beta = np.array(beta, dtype=np.float64, copy=True)
+    first = {}
+    for j in range(x.shape[1]):
+        key = x[:, j].tobytes()
+        if key in first:
+            beta[..., first[key]] += beta[..., j]
+            beta[..., j] = 0.0
+        else:
+            first[key] = j
+    return beta
