@@ -1075,7 +1075,7 @@ void Engine::set_groups(const std::vector<int> &g_index)
         const int next = g + 1 < N ? g_index[(size_t)g + 1] : p;  // Data.h:53-61
         if (next <= g_index[(size_t)g]) throw EngineError{"g_index must be strictly ascending"};
         g_size_[(size_t)g] = next - g_index[(size_t)g];
-        if (g_size_[(size_t)g] > GMAX) throw EngineError{"groups of more than 8 variables are not supported"};
+        if (g_size_[(size_t)g] > GWIDE) throw EngineError{"groups of more than 64 variables are not supported"};
     }
     n_groups_ = N;
     dfree(m.st, m.gidx);
@@ -1125,6 +1125,7 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     d.nmat = family_ == FAM_COX ? 2 : 1;
     d.grouped = grp ? 1 : 0;
     d.N = n_groups_;
+    d.gmax = grp ? *std::max_element(g_size_.begin(), g_size_.end()) : 1;
     d.gidx = m.gidx;
     d.gsz = m.gsz;
 
@@ -1593,7 +1594,7 @@ int Engine::run_batch_enqueue(int T, const std::vector<int> &chains, bool new_pa
     b.nch = (int)chains.size();
     b.T = T;
     b.new_path_step = new_path_step ? 1 : 0;
-    b.CL = chain_cluster_size(d, d.grouped ? std::min(d.kcap, T * GMAX) : T, b.nch);
+    b.CL = chain_cluster_size(d, d.grouped ? std::min(d.kcap, T * d.gmax) : T, b.nch);
     t.cmin = MAXC;
     t.cmax = -1;
     for (int i = 0; i < b.nch; i++) {

@@ -19,7 +19,8 @@ namespace bess {
 constexpr int MAXC = 32;      // max chains = 1 + K folds (K <= 31)
 constexpr int PROF_NCAT = 8;
 constexpr int MAX_ITER_CAP = 100000;  // A_list (Algorithm.h:142) is sized max_iter + 2 per problem; this only bounds the argument
-constexpr int GMAX = 8;       // widest group of variables in group selection (gsize > 1)
+constexpr int GMAX = 8;       // widest group of variables the register kernels of group selection take (gsize > 1)
+constexpr int GWIDE = 64;     // widest group at all (shared-memory kernel, group.cu)
 constexpr int NSLOT = 4;      // snapshot slots of Engine::chain_state
 enum { STATE_ZERO = 0, STATE_SAVE = 1, STATE_LOAD = 2 };
 

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(GS_NT) group_sacrifice_warp_kernel(const Dev d
     const int g = blockIdx.x * (GS_NT / 32) + (threadIdx.x >> 5);
     if (g >= d.N) return;  // warp-uniform
     const int j0 = d.gidx[g], gs = d.gsz[g];
+    if (gs > GMAX) return;  // wide groups: group_sacrifice_wide_kernel
     const int FS = d.FS;
     double dv[GMAX], M[GMAX * (GMAX + 1) / 2];
 #pragma unroll
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(GS_NT) group_sacrifice_kernel(const Dev d, con
     const int g = blockIdx.x * GS_NT + threadIdx.x;
     if (g >= d.N) return;
     const int j0 = d.gidx[g], gs = d.gsz[g];
+    if (gs > GMAX) return;  // wide groups: group_sacrifice_wide_kernel
     const int FS = d.FS;
     double dv[GMAX], sv[GMAX], M[GMAX * (GMAX + 1) / 2];
 #pragma unroll
@@ -196,6 +198,140 @@ __global__ void __launch_bounds__(GS_NT) group_sacrifice_kernel(const Dev d, con
     group_epilogue(d, c, g, j0, gs, dv, M);
 }
 
+// Groups of GMAX + 1 .. GWIDE variables: one CTA per (group, chain), the k_g x k_g block in shared memory.  Rows travel
+// in tiles of GW_RT (for cox from the last row to the first: the risk-set sums s_a(k) of a tile are formed first, one
+// thread per column, then the block update is a tile contraction like the weighted one); thread t owns the block entries
+// t, t + GW_NT, ...  No eigen-decomposition here: with A = M_g + 2 lambda I = Phi^2,
+//     || Phi beta + Phi^{-1} d ||^2 = beta' A beta + 2 beta' d + d' A^{-1} d,
+// and d' A^{-1} d = || L^{-1} d ||^2 with the Cholesky factor A = L L' (an in-place unblocked factorisation by the CTA and
+// one forward substitution) -- the same number as the reference's Schur-based sqrt() / inverse route (utilities.cpp:147,
+// Algorithm.h:1112-1123) up to rounding.
+constexpr int GW_NT = 256;
+constexpr int GW_RT = 32;
+constexpr int GW_EPT = (GWIDE * GWIDE + GW_NT - 1) / GW_NT;  // block entries per thread
+template <bool COX>
+__global__ void __launch_bounds__(GW_NT) group_sacrifice_wide_kernel(const Dev d, const BatchDesc b)
+{
+    extern __shared__ __align__(16) double gw_smem[];
+    if (d.gate && *d.gate == 0) return;
+    const int c = b.chain[blockIdx.y];
+    if (d.done[c]) return;
+    const int g = blockIdx.x;
+    const int gs = d.gsz[g];
+    if (gs <= GMAX) return;  // CTA-uniform: the register kernels own the narrow groups
+    const int j0 = d.gidx[g], FS = d.FS, tid = threadIdx.x;
+    double *A = gw_smem;                 // [gs][gs]
+    double *xt = A + GWIDE * GWIDE;      // [GW_RT][gs] x tile
+    double *stl = xt + GW_RT * GWIDE;    // [GW_RT][gs] cox: risk-set sums after each row of the tile
+    double *rv = stl + GW_RT * GWIDE;    // [4][GW_RT] g, w, theta, c2 of the tile's rows
+    double *vec = rv + 4 * GW_RT;        // [4][GWIDE] d, beta, L^{-1} d, scratch
+    double *red = vec + 4 * GWIDE;       // [40] block_sum scratch
+    double macc[GW_EPT];
+#pragma unroll
+    for (int q = 0; q < GW_EPT; q++) macc[q] = 0.0;
+    double dacc = 0.0, sacc = 0.0;  // threads < gs: d_a, running risk-set sum s_a
+    const int ne = gs * gs;
+    for (int t0 = 0; t0 < d.n; t0 += GW_RT) {
+        const int rc = min(GW_RT, d.n - t0);
+        // tile row r is design row i(r): ascending, or for cox descending from the last row
+        __syncthreads();
+        for (int e = tid; e < rc * gs; e += GW_NT) {
+            const int r = e / gs, a = e - r * gs;
+            const int i = COX ? d.n - 1 - (t0 + r) : t0 + r;
+            xt[r * GWIDE + a] = __ldg(d.X + (size_t)i * d.ldx + j0 + a);
+        }
+        if (tid < rc) {
+            const int i = COX ? d.n - 1 - (t0 + tid) : t0 + tid;
+            const double gi = d.G[(size_t)i * FS + c], wi = d.W[(size_t)i * FS + c];
+            const double th = COX ? d.TH[(size_t)i * FS + c] : 0.0;
+            const bool off = gi == 0.0 && wi == 0.0 && th == 0.0;  // row outside the chain's train mask
+            rv[tid] = gi;
+            rv[GW_RT + tid] = wi;
+            rv[2 * GW_RT + tid] = th;
+            rv[3 * GW_RT + tid] = (COX && !off) ? d.C2[(size_t)i * FS + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid < gs) {
+            for (int r = 0; r < rc; r++) {
+                const double x = xt[r * GWIDE + tid];
+                dacc = fma(x, rv[r], dacc);
+                if (COX) {
+                    sacc = fma(x, rv[2 * GW_RT + r], sacc);
+                    stl[r * GWIDE + tid] = sacc;
+                }
+            }
+        }
+        if (COX) __syncthreads();
+#pragma unroll
+        for (int q = 0; q < GW_EPT; q++) {
+            const int e = tid + q * GW_NT;
+            if (e < ne) {
+                const int a = e / gs, bb = e - a * gs;
+                double m = macc[q];
+                for (int r = 0; r < rc; r++) {
+                    m = fma(rv[GW_RT + r] * xt[r * GWIDE + a], xt[r * GWIDE + bb], m);
+                    if (COX) m = fma(-rv[3 * GW_RT + r] * stl[r * GWIDE + a], stl[r * GWIDE + bb], m);
+                }
+                macc[q] = m;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < GW_EPT; q++) {
+        const int e = tid + q * GW_NT;
+        if (e < ne) {
+            const int a = e / gs, bb = e - a * gs;
+            A[a * GWIDE + bb] = macc[q] + (a == bb ? 2.0 * d.lambda : 0.0);
+        }
+    }
+    if (tid < gs) {
+        const double bg = d.betaD[(size_t)c * d.pstride + j0 + tid];
+        vec[tid] = dacc - 2.0 * d.lambda * bg;  // d_g - 2 lambda beta_g
+        vec[GWIDE + tid] = bg;
+    }
+    __syncthreads();
+    // beta' A beta + 2 beta' d
+    double part = 0.0;
+    for (int e = tid; e < ne; e += GW_NT) {
+        const int a = e / gs, bb = e - a * gs;
+        part = fma(vec[GWIDE + a] * A[a * GWIDE + bb], vec[GWIDE + bb], part);
+    }
+    if (tid < gs) part = fma(2.0 * vec[GWIDE + tid], vec[tid], part);
+    const double quad = block_sum<GW_NT>(part, red);
+    // A = L L' in place (lower triangle), then y = L^{-1} d
+    for (int j = 0; j < gs; j++) {
+        __syncthreads();
+        const double djj = sqrt(A[j * GWIDE + j]);
+        __syncthreads();
+        if (tid == 0) A[j * GWIDE + j] = djj;
+        for (int i = j + 1 + tid; i < gs; i += GW_NT) A[i * GWIDE + j] /= djj;
+        __syncthreads();
+        const int rem = gs - j - 1;
+        for (int e = tid; e < rem * rem; e += GW_NT) {
+            const int i = j + 1 + e / rem, cc = j + 1 + e % rem;
+            if (cc <= i) A[i * GWIDE + cc] -= A[i * GWIDE + j] * A[cc * GWIDE + j];
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        for (int a = tid; a < gs; a += 32) vec[2 * GWIDE + a] = vec[a];
+        __syncwarp();
+        for (int j = 0; j < gs; j++) {
+            const double yj = vec[2 * GWIDE + j] / A[j * GWIDE + j];
+            __syncwarp();
+            if (tid == 0) vec[2 * GWIDE + j] = yj;
+            for (int i = j + 1 + tid; i < gs; i += 32) vec[2 * GWIDE + i] -= A[i * GWIDE + j] * yj;
+            __syncwarp();
+        }
+        double s2 = 0.0;
+        for (int a = tid; a < gs; a += 32) s2 = fma(vec[2 * GWIDE + a], vec[2 * GWIDE + a], s2);
+        s2 = warp_sum(s2);
+        if (tid == 0) d.bd[(size_t)c * d.pstride + g] = (quad + s2) / (double)gs;
+    }
+}
+static size_t gw_smem_bytes() { return sizeof(double) * (size_t)(GWIDE * GWIDE + 2 * GW_RT * GWIDE + 4 * GW_RT + 4 * GWIDE + 40); }
+
 // find_ind (utilities.cpp:113-130): the T selected groups (ascending) -> their columns, in order
 __global__ void group_expand_kernel(const Dev d, const BatchDesc b)
 {
@@ -230,6 +366,18 @@ void launch_group_sacrifice(const Dev &d, const BatchDesc &b, cudaStream_t st)
         group_sacrifice_warp_kernel<<<grid, GS_NT, 0, st>>>(d, b);
     }
     CUDA_CHECK(cudaGetLastError());
+    if (d.gmax > GMAX) {  // some groups are wider than the register kernels take
+        const dim3 grid((unsigned)d.N, (unsigned)b.nch);
+        const size_t smem = gw_smem_bytes();
+        if (d.family == FAM_COX) {
+            CUDA_CHECK(cudaFuncSetAttribute(group_sacrifice_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            group_sacrifice_wide_kernel<true><<<grid, GW_NT, smem, st>>>(d, b);
+        } else {
+            CUDA_CHECK(cudaFuncSetAttribute(group_sacrifice_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            group_sacrifice_wide_kernel<false><<<grid, GW_NT, smem, st>>>(d, b);
+        }
+        CUDA_CHECK(cudaGetLastError());
+    }
 }
 void launch_group_expand(const Dev &d, const BatchDesc &b, cudaStream_t st)
 {

@@ -69,6 +69,7 @@ struct Dev {
     // group ids, A / bA / ks / AnewCols on columns; kcap is the COLUMN capacity of a support.
     int grouped;        // 0: every column is its own group, the fields below are unused
     int N;              // number of groups
+    int gmax;           // widest group
     const int *gidx;    // [N]
     const int *gsz;     // [N]
     int *Tc;            // [MAXC] number of columns of the groups chosen by the last top-k

@@ -6,7 +6,7 @@ Mapping (linear.py:138-202): algorithm_type "Pdas"->1 / "GroupPdas"->2 / "L0L2"-
 "Poisson","Cox" -> 1..4; path_type "seq"->1 / "pgs"->2; ic_type "aic","bic","gic","ebic" -> 1..4;
 data_type 1 (Lm) / 2 (Logistic, Poisson) / 3 (Cox) (linear.py:475,517,559,597).
 All twelve estimator classes of the reference are here: Pdas* (best-subset selection), L0L2* (best-subset ridge, "bsrr":
-sequential lambda grids and the Powell search path_type="pgs") and GroupPdas* (group selection: sparsity levels count groups of up to 8 variables)."""
+sequential lambda grids and the Powell search path_type="pgs") and GroupPdas* (group selection: sparsity levels count groups of up to 64 variables)."""
 from __future__ import annotations
 
 import math

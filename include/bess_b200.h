@@ -157,7 +157,7 @@ int bessgpu_screen_local(bessgpu_handle *h, int screening_size, const int *alway
 int bessgpu_gather_columns(bessgpu_handle *h, const int *cols, const int *pos, int m, double *dst_dev, long long ld);
 /* Data.h:41-77 + normalize.cpp:20-86 */
 int bessgpu_normalize(bessgpu_handle *h, int data_type, int is_normal);
-/* group selection (Data.h:53-61: g_index = first column of every group, ascending from 0; at most 8 variables per
+/* group selection (Data.h:53-61: g_index = first column of every group, ascending from 0; at most 64 variables per
  * group).  Call after bessgpu_normalize and before bessgpu_setup_chains; sparsity levels, kcap and always_select then
  * count groups (Algorithm.h:1097-1129, 1206-1263, 1324-1367, 1497-1568; utilities.cpp:113-177). */
 int bessgpu_set_groups(bessgpu_handle *h, const int *g_index, int n_groups);

@@ -17,7 +17,7 @@ FAM = {"gaussian": (1, 1), "binomial": (2, 2), "poisson": (3, 2), "cox": (4, 3)}
 
 
 def layout(p, sizes):
-    """first column of every group, group sizes cycling through `sizes`; the last group takes what is left (<= 8)."""
+    """first column of every group, group sizes cycling through `sizes`; the last group takes what is left."""
     gi, k = [0], 0
     while gi[-1] + sizes[k % len(sizes)] < p:
         gi.append(gi[-1] + sizes[k % len(sizes)])
@@ -47,6 +47,13 @@ CASES = {
     "single_cox_seq_cv": ("cox", 160, 120, 4, [1], 2, 1, True, 3, 1, 1, 6, [0.0], False, (), 115),
     "single_lm_gs_cv": ("gaussian", 150, 200, 5, [1], 2, 2, True, 3, 1, 1, 12, [0.0], False, (), 116),
     "single_logit_l0l2_seq": ("binomial", 200, 150, 4, [1], 3, 1, False, 5, 3, 1, 6, [0.01, 0.1], False, (), 117),
+    # groups wider than 8 variables (the shared-memory sacrifice kernel; utilities.cpp:142-177 takes any size)
+    "wide_lm_seq_gic": ("gaussian", 200, 240, 6, [12, 3, 1, 17, 5], 2, 1, False, 5, 3, 1, 5, [0.0], False, (), 121),
+    "wide_lm_l0l2_cv": ("gaussian", 220, 200, 5, [9, 2, 20, 4], 3, 1, True, 3, 1, 1, 4, [0.0, 0.1], True, (), 122),
+    "wide_logit_seq_gic": ("binomial", 400, 160, 4, [10, 2, 13, 1], 2, 1, False, 5, 3, 1, 4, [0.0], False, (), 123),
+    "wide_poisson_seq_cv": ("poisson", 400, 150, 4, [11, 3, 2], 2, 1, True, 3, 1, 1, 4, [0.0], False, (), 124),
+    "wide_cox_seq_gic": ("cox", 300, 150, 4, [12, 1, 9, 3], 2, 1, False, 5, 3, 1, 4, [0.0], False, (), 125),
+    "wide_cox_l0l2_cv": ("cox", 300, 140, 4, [10, 4, 16], 3, 1, True, 3, 1, 1, 3, [0.0, 0.01], False, (1,), 126),
 }
 
 
