@@ -1189,7 +1189,8 @@ __device__ void pm_backsub(const double *L, const int *poff, int mm, int c0, int
 }
 // Sg: bordered system in global memory (row-major, lower triangle + border row mm); multi-stage runs overwrite it.
 // x (shared memory) <- solution.
-__device__ __noinline__ void chol_panel_major(double *Sg, int lds, int mm, double *x, const FitSmem &sm_, PhaseTimer &pt)
+__device__ __noinline__ void chol_panel_major(double *Sg, int lds, int mm, double *x, const FitSmem &sm_, PhaseTimer &pt,
+                                              bool preloaded = false)
 {
     const FitSmem sm = sm_shared(sm_);
     // Re-derive every shared-memory pointer from the kernel's dynamic shared array: behind the call boundary of this
@@ -1213,7 +1214,7 @@ __device__ __noinline__ void chol_panel_major(double *Sg, int lds, int mm, doubl
     for (int s = 0; s < ns; s++) {
         const int c0 = sc0[s], np = snp[s];
         pm_offsets(poff, mm, c0, np);
-        pm_copy<false>(L, poff, Sg, lds, mm, c0, np);
+        if (!(preloaded && s == 0)) pm_copy<false>(L, poff, Sg, lds, mm, c0, np);  // (reduce_to_panels filled stage 0)
         pt.mark(10);
         if (threadIdx.x < 32) pm_diag_factor(L + poff[0], pm_ld(mm + 1 - c0), min(PNB, mm - c0), dg + c0, colbuf);
         __syncthreads();
@@ -1386,7 +1387,8 @@ __device__ __noinline__ void chol_blocked_cluster(double *S, int lds, int mm, do
 // Rank 0 holds a bordered system (nu unknowns) at S -- its own shared memory (small systems) or the chain's global matrix
 // (large systems, then every CTA of the cluster takes part in the factorisation): solve it and hand the solution to
 // every CTA of the cluster (out: smem).
-__device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds, int nu, double *out, const FitSmem &sm_)
+__device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds, int nu, double *out, const FitSmem &sm_,
+                                bool preloaded = false)
 {
     const FitSmem sm = sm_shared(sm_);
     out = as_shared(out);
@@ -1406,7 +1408,7 @@ __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds,
             }
         }
     } else if (g_dbg_solver == 0 && nu < FIT_NT && pm_stage_count(nu, sm.arena_len) <= PM_MAX_STAGES) {
-        if (cl.rank == 0) chol_panel_major(S, lds, nu, sm.rhs, sm, cl.pt);
+        if (cl.rank == 0) chol_panel_major(S, lds, nu, sm.rhs, sm, cl.pt, preloaded);
     } else if (packed_fits(nu, sm.arena_len)) {
         if (cl.rank == 0) chol_packed_smem(S, lds, nu, sm.rhs, sm, cl.pt);
     } else {
@@ -1431,11 +1433,73 @@ __device__ void solve_broadcast(const ChainCtx &cx, Clu &cl, double *S, int lds,
 // Cluster mode: Sfin[a][b] = sum_q P_q[0][a][b] (- sum_q P_q[1][a][b] when nmat == 2) for a < rows, b < cols, each CTA
 // reducing a slab of rows, ranks summed in a fixed order; optional extra row `rows` = sum_q cw_slot(q, 1) (Cox gradient).
 // Ends with a cluster barrier; afterwards rank 0 stages the system where it will factor it and returns that pointer.
+// Cluster mode, wide systems that the panel-major solver factors in ONE stage: the per-CTA partial Grams are reduced
+// straight into rank 0's shared memory, already in panel-major layout -- every CTA of the cluster sums its share of the
+// lower triangle (4-row x 8-column patches dealt round robin over all warps of the cluster, ranks added in a fixed
+// order) and stores the results through distributed shared memory.  Replaces a full-square reduction into global memory
+// plus rank 0's load of the result (12.5 + 10 us per IRLS step at 200 unknowns).  Ends with a cluster barrier.
+__device__ void reduce_to_panels(const ChainCtx &cx, Clu &cl, int rows, int nmat, bool extra_row, const FitSmem &sm,
+                                 double diag_add, int diag_from, int diag_to)
+{
+    const int ldA = cx.ldA;
+    const int brows = rows + (extra_row ? 1 : 0), nu = brows - 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int il = lane >> 3, cl8 = lane & 7;
+    constexpr int NWC = FIT_NT / 32;
+    const int np = (nu + PNB - 1) / PNB;
+    int *poff = reinterpret_cast<int *>(sm.tile);
+    pm_offsets(poff, nu, 0, np);
+    double *L0 = cg::this_cluster().map_shared_rank(sm.tile + 64, 0);  // rank 0's panel storage (same carve in every CTA)
+    const int nwarps = cl.CL * NWC, gw = cl.rank * NWC + wid;
+    int u = 0;
+    for (int pb = 0; pb < np; pb++) {
+        const int r0 = pb * PNB;
+        const int h = nu + 1 - r0, ld = pm_ld(h);
+        const int nb = min(PNB, nu - r0);
+        double *P = L0 + poff[pb];
+        const int npatch = 2 * ((h + 3) >> 2);
+        for (int pa = (gw - u % nwarps + nwarps) % nwarps; pa < npatch; pa += nwarps) {
+            const int i = (pa >> 1) * 4 + il, c = (pa & 1) * 8 + cl8;
+            if (i >= h) continue;
+            double v = 0.0;
+            if (c < nb) {
+                const int a = r0 + i, b = r0 + c;
+                if (a < rows) {
+                    const size_t o = (size_t)a * ldA + b;
+                    for (int q = 0; q < cl.CL; q++) v += cx.Sp0[q * cx.sp_stride + o];
+                    if (nmat == 2) {
+                        double s2 = 0.0;
+                        for (int q = 0; q < cl.CL; q++) s2 += cx.Sp0[q * cx.sp_stride + (size_t)ldA * ldA + o];
+                        v -= s2;
+                    }
+                    if (a == b && a >= diag_from && a < diag_to) v += diag_add;
+                } else {  // the extra border row (cox gradient)
+                    for (int q = 0; q < cl.CL; q++) v += cw_slot(cx, q, 1)[b];
+                }
+            }
+            P[c * ld + i] = v;
+        }
+        u += npatch;
+    }
+    clu_sync(cl);
+}
+
 __device__ double *reduce_partials(const ChainCtx &cx, Clu &cl, int rows, int cols, int nmat, bool extra_row, int *lds_out,
-                                   const FitSmem &sm_, double diag_add = 0.0, int diag_from = 0, int diag_to = 0)
+                                   const FitSmem &sm_, double diag_add = 0.0, int diag_from = 0, int diag_to = 0,
+                                   bool *preloaded = nullptr)
 {
     const FitSmem sm = sm_shared(sm_);
     const int ldA = cx.ldA;
+    {
+        const int nu = rows + (extra_row ? 1 : 0) - 1;
+        if (preloaded) *preloaded = false;
+        if (preloaded && nu + 1 > FIT_SMEM_MS && g_dbg_solver == 0 && nu < FIT_NT && pm_stage_count(nu, sm.arena_len) == 1) {
+            reduce_to_panels(cx, cl, rows, nmat, extra_row, sm, diag_add, diag_from, diag_to);
+            *preloaded = true;
+            *lds_out = ldA;
+            return cx.Sfin;
+        }
+    }
     const int per = (rows + cl.CL - 1) / cl.CL;
     const int a0 = cl.rank * per, a1 = min(rows, a0 + per);
     const int cnt = max(0, a1 - a0) * cols;
@@ -1499,9 +1563,10 @@ __device__ void gram_solve(const ChainCtx &cx, Clu &cl, const double *V, int ldv
     clu_sync(cl);
     cl.pt.mark(PH_SYRK);
     int lds;
-    double *S = reduce_partials(cx, cl, mm, mm, 1, false, &lds, sm, diag_add, diag_from, mm - 1);
+    bool preloaded;
+    double *S = reduce_partials(cx, cl, mm, mm, 1, false, &lds, sm, diag_add, diag_from, mm - 1, &preloaded);
     cl.pt.mark(PH_REDUCE);
-    solve_broadcast(cx, cl, S, lds, mm - 1, out, sm);
+    solve_broadcast(cx, cl, S, lds, mm - 1, out, sm, preloaded);
 }
 
 __device__ __forceinline__ double row_dot(const double *row, const double *b, int m)
@@ -1822,6 +1887,7 @@ __device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &
         }
         double *S;
         int lds;
+        bool preloaded = false;
         if (cl.CL == 1) {
             for (int it = threadIdx.x; it < m * m; it += FIT_NT) {
                 const int a = it / m, bcol = it % m;
@@ -1834,10 +1900,10 @@ __device__ void fit_cox(const ChainCtx &cx, Clu &cl, double *XB, const FitSmem &
             lds = cx.lds;
         } else {
             clu_sync(cl);
-            S = reduce_partials(cx, cl, m, m, 2, true, &lds, sm, -2.0 * lambda, 0, m);
+            S = reduce_partials(cx, cl, m, m, 2, true, &lds, sm, -2.0 * lambda, 0, m, &preloaded);
         }
         // P d' = g  (d' = -d of Algorithm.h:1472)
-        solve_broadcast(cx, cl, S, lds, m, sm.rhs, sm);
+        solve_broadcast(cx, cl, S, lds, m, sm.rhs, sm, preloaded);
         // line search (Algorithm.h:1474-1481): beta1 = beta0 - 0.5^mm * d = beta0 + 0.5^mm * rhs
         int mm = 1;
         double step = 0.5;
