@@ -452,6 +452,29 @@ def run_ours(args):
                "parallelism": "single GPU" if world == 1 else f"columns sharded over {world} ranks, NCCL all-gather of "
                               "top-k candidates + all-reduce of active columns every PDAS iteration"}
 
+    # ---- config 2 (binomial, n = 2000, p = 20000, golden section over s = 1..263, 10-fold CV): the call the chain kernels
+    # (IRLS: weighted Gram on the FP64 tensor cores + Cholesky, chain_fit.cu) dominate -- the kernel the round-1 review
+    # named as furthest below its roof.  Reported beside the headline, N = 1 only.
+    c2 = None
+    if world == 1 and not args.no_c2:
+        from bess_b200.gen_data import gen_data as _gen
+        d2 = _gen(2000, 20000, "binomial", 20, seed=2)
+        w2 = np.ones(2000)
+        for r2 in range(2):
+            t0 = time.perf_counter()
+            o2 = cbess.fit(d2.x, d2.y, 2, w2, True, 1, 2, 20, 2, 2, True, 1, True, 10, np.arange(1, 2), 1, 263, False, 1,
+                           cv_seed=123, device=local_rank, profile=True, want_trace=False)
+            t1 = time.perf_counter()
+        s2 = o2["stats"]
+        c2 = {"workload": "C2: binomial gen.data n=2000 p=20000 true-s=20, golden section s in [1, 263], 10-fold CV "
+                          "(host design, 320 MB H2D inside the call)",
+              "ms_per_call": (t1 - t0) * 1e3, "fits": s2["n_fits"], "pdas_iters": s2["n_pdas_iters"], "chosen_s": int(o2["s"]),
+              "chain_kernel_ms": s2["prof_ms"]["chain"], "chain_kernel_launches": s2["prof_launches"]["chain"],
+              "dual_sweep_ms": s2["prof_ms"]["dual_sweep"], "upload_ms": s2["prof_ms"]["upload"],
+              "round1_ms_per_call": 1254.0,
+              "evidence": "profiles/r02b_chain_fit_c2_full.md (ncu --set full of one chain_fit launch), "
+                          "profiles/r02b_chain_fit_building_blocks.md (solver / Gram probes, FP64 issue rates)"}
+
     # ---- strong scaling of ONE C5 call with the columns sharded (same folds on every rank, no repetition): what the
     # column axis alone buys at config 5 (only the screening sweep is p-sized)
     col_sharded = None
@@ -516,7 +539,8 @@ def run_ours(args):
                          "kernel_ms_per_step": {k: float(v / args.steps) for k, v in zip(cbess.PROF_CATS, prof_ms)},
                          "kernel_share_of_step": float(total_kernel_ms / args.steps / (ms / args.steps)),
                          "p500k_pdas_sweep": probe},
-            "cpu_baseline": base, "c5b_no_screening": c5b if world == 1 else None, "column_sharded": col_sharded,
+            "cpu_baseline": base, "c5b_no_screening": c5b if world == 1 else None, "c2_glm_path": c2,
+            "column_sharded": col_sharded,
             # the strong-scaling curve of ONE call (columns sharded) starts here: N = 1 of column_sharded.c5_one_call_strong /
             # c5b_no_screening_strong in the N > 1 lines
             "strong_scaling_n1": {"c5_one_call_ms": ms / args.steps, "c5b_no_screening_ms": c5b["ms_per_call"] if c5b else None}
@@ -554,6 +578,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5b", action="store_true")
+    ap.add_argument("--no-c2", action="store_true", help="skip the config-2 (chain-kernel bound) block of the N = 1 line")
     ap.add_argument("--torch-cv-reduce", action="store_true",
                     help="N > 1: average the CV curves with torch.distributed in the bench instead of inside the library")
     ap.add_argument("--torch-design", action="store_true", help="draw the design with torch.randn instead of the library's generator")

@@ -521,15 +521,9 @@ __device__ void fallback_select(const double *bd, int p, int kk, OwnSm &s, int *
             if (tid < 256) s.hbin[tid] = 0;
             __syncthreads();
             if (inreg) {
-                // warp-aggregated: the leading digits of the sacrifices are nearly all equal, a plain atomicAdd per key
-                // serialises the warp on one bin
 #pragma unroll
-                for (int q = 0; q < FB_PER; q++) {
-                    const bool in = tid + q * LP_NT < p && (key[q] & mask) == prefix;
-                    const int dg = in ? (int)((key[q] >> shift) & 255ull) : 256 + (tid & 31);
-                    const unsigned peers = __match_any_sync(0xffffffffu, dg);
-                    if (in && (tid & 31) == __ffs(peers) - 1) atomicAdd(&s.hbin[dg], __popc(peers));
-                }
+                for (int q = 0; q < FB_PER; q++)
+                    if (tid + q * LP_NT < p && (key[q] & mask) == prefix) atomicAdd(&s.hbin[(int)((key[q] >> shift) & 255ull)], 1);
             } else {
                 for (int i = tid; i < p; i += LP_NT) {
                     const unsigned long long u = (unsigned long long)__double_as_longlong(__ldcg(bd + i));
