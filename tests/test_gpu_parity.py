@@ -202,8 +202,9 @@ def test_fit_level_parity_with_oracle(fam, n, p, k, K):
                                         ("binomial", 1500, 800, 80), ("binomial", 1500, 800, 150), ("cox", 900, 700, 70),
                                         ("poisson", 1200, 800, 120)])
 def test_large_support_solvers_against_oracle(fam, n, p, T):
-    """Supports wide enough for every normal-equation path: unblocked smem Cholesky (<= 64), DMMA Gram (> 96), packed
-    in-smem blocked Cholesky (65..~230 unknowns) and the cluster-distributed blocked Cholesky in L2 (> 230)."""
+    """Supports wide enough for every normal-equation path: unblocked smem Cholesky (<= 64 unknowns), tensor-core Gram on the
+    bulk-TMA ring (> 56 columns), the panel-major Cholesky in one stage (65..~225 unknowns, partial Grams reduced into
+    rank 0's shared memory through DSMEM) and in two stages (250).  Observed: <= 6e-14 (tools/gpu_large_err.py)."""
     from bess_b200.engine import GpuEngine
     from bess_b200.gen_data import gen_data
     model_type, data_type = FAM[fam]
@@ -219,8 +220,8 @@ def test_large_support_solvers_against_oracle(fam, n, p, T):
     o = orc.pdas_fit(data, model_type, T, np.zeros(p), 0.0, st.full_mask, st.xtx_full, 20)
     assert r["A"][0].tolist() == o.A.tolist()
     assert int(r["l"][0]) == o.l
-    assert rel_err(r["bA"][0], o.beta[o.A]) < 1e-7  # ill-conditioned by design (k close to n / separation)
-    assert abs(r["coef0"][0] - o.coef0) <= 1e-7 * max(1.0, abs(o.coef0))
+    assert rel_err(r["bA"][0], o.beta[o.A]) < RTOL
+    assert abs(r["coef0"][0] - o.coef0) <= RTOL * max(1.0, abs(o.coef0))
     eng.close()
 
 
