@@ -1036,14 +1036,57 @@ void Engine::normalize(int data_type, bool is_normal)
         m.X = Xc;
         m.x_owned = true;
     }
-    m.config_sweep(1);
     DevArena &ar = m.ctx->ar;
+    m.stats_have_mean = false;
+    m.stats_pending = false;
+    // ---- a design that fits L2 (after screening: config 5's 40 MB): the whole normalisation is ONE launch
+    static const bool one_launch = [] {
+        const char *e = std::getenv("BESS_B200_NORM_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    if (one_launch && is_normal && !sharded_ && (size_t)n * m.ldx * 8 <= ((size_t)64 << 20)) {
+        const int sp = m.span_begin(6);
+        m.h_mean = m.ctx->rb.alloc<double>((size_t)p);
+        m.h_norm = m.ctx->rb.alloc<double>((size_t)p);
+        const bool centre = data_type == 1 || data_type == 2;
+        std::vector<double> g(n), rm(n);
+        for (int i = 0; i < n; i++) g[i] = m.hw[i] / (double)n;  // meanx_j = w.x_j / n (normalize.cpp:25-28, 52-55)
+        if (data_type == 1) {
+            double s = 0.0;
+            for (int i = 0; i < n; i++) s += m.hy[i] * m.hw[i];  // normalize.cpp:29
+            y_mean_ = s / (double)n;
+            for (int i = 0; i < n; i++) m.hy[i] -= y_mean_;
+        }
+        double *d_g = centre ? m.stage_vec(g.data(), (size_t)n, (size_t)n) : nullptr;
+        double *d_w = m.stage_vec(m.hw.data(), (size_t)n, (size_t)n);
+        double *d_rm = nullptr;
+        if (family_ == FAM_LM) {  // add_weight: rows scaled by sqrt(w) (Data.h:70-77)
+            for (int i = 0; i < n; i++) {
+                rm[i] = std::sqrt(m.hw[i]);
+                m.hy[i] *= rm[i];
+            }
+            d_rm = m.stage_vec(rm.data(), (size_t)n, (size_t)n);
+        }
+        m.y = m.stage_vec(m.hy.data(), (size_t)n, (size_t)m.npad);  // the response as the fits see it
+        m.ctx->mir.flush(m.st);
+        double *d_mean = ar.alloc<double>((size_t)p + 2), *d_norm = ar.alloc<double>((size_t)p + 2);
+        launch_normalize_resident(m.X, m.ldx, n, p, d_g, d_w, d_rm, std::sqrt((double)n), d_mean, d_norm, m.st);
+        if (centre) CUDA_CHECK(cudaMemcpyAsync(m.h_mean, d_mean, (size_t)p * 8, cudaMemcpyDeviceToHost, m.st));
+        CUDA_CHECK(cudaMemcpyAsync(m.h_norm, d_norm, (size_t)p * 8, cudaMemcpyDeviceToHost, m.st));
+        m.stats_have_mean = centre;
+        m.stats_pending = true;
+        m.span_end(sp);
+        stats_.kernel_launches += 1;
+        stats_.norm_bytes += 32.0 * n * p;  // three reads and one write of X
+        h_xmean_.clear();
+        h_xnorm_.clear();
+        return;
+    }
+    m.config_sweep(1);
     BatchDesc b{};
     b.nch = 1;
     b.chain[0] = 0;
     double *d_mul = nullptr, *d_rowmul = nullptr;
-    m.stats_have_mean = false;
-    m.stats_pending = false;
     const int sp_all = m.span_begin(6);
     // No host round trip in here: the column statistics stay on the device (the scale factors are derived there) and
     // travel to pinned memory for the de-normalisation at the end of the call (ensure_stats).

@@ -929,6 +929,95 @@ void launch_norm_factors(const double *h, int p, double sn, double *norm_out, do
     CUDA_CHECK(cudaGetLastError());
 }
 
+// Normalisation of a design that fits L2 (the screened design of config 5: 40 MB) in ONE launch: a CTA owns 8 adjacent
+// columns for all rows and makes the three passes of normalize.cpp:20-86 over its own slab (64 KB at n = 1000, re-read
+// from L2 / L1) -- weighted column means, norms of the CENTRED columns, scaling (+ the sqrt(w) row factors of add_weight,
+// Data.h:70-77).  Per element the arithmetic is that of center_scale_kernel ((x - mean) rounded once, then * mul * rm);
+// only the summation order of the two column sums differs from the sweep kernels (fixed: rows warp-strided, warps added
+// in order).  Replaces 7 launches and 6 passes over X by 1 launch and 4.
+constexpr int NR_NT = 256;
+constexpr int NR_TC = 8;  // columns per CTA: a warp load covers 4 rows x 64 bytes; p / 8 CTAs keep every SM streaming
+__global__ void __launch_bounds__(NR_NT) normalize_resident_kernel(double *X, long long ldx, int n, int p, const double *gmean,
+                                                                   const double *wnorm, const double *rowmul, double sn,
+                                                                   double *mean_out, double *norm_out)
+{
+    __shared__ double red[NR_NT / 32][NR_TC];
+    __shared__ double cmean[NR_TC], cmul[NR_TC];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = NR_NT / 32, RS = NW * 4;  // rows per CTA step
+    const int c = lane & (NR_TC - 1), rg = lane >> 3;
+    const long long j = (long long)blockIdx.x * NR_TC + c;
+    const bool live = j < p;
+    double *col = X + (live ? j : 0);
+    const int ifirst = wid * 4 + rg;
+    // column sum of f(x_i, i) over this thread's rows, 8 loads in flight; then lanes of the same column, then warps
+    auto column_sum = [&](auto f) {
+        double s = 0.0;
+        for (int i0 = ifirst; i0 < n; i0 += 8 * RS) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (live && i0 + u * RS < n) ? col[(size_t)(i0 + u * RS) * ldx] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (i0 + u * RS < n) s = f(v[u], i0 + u * RS, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        __syncthreads();
+        if (lane < NR_TC) red[wid][lane] = s;
+        __syncthreads();
+        double t = 0.0;
+        if (threadIdx.x < NR_TC) {
+#pragma unroll
+            for (int q = 0; q < NW; q++) t += red[q][threadIdx.x];
+        }
+        return t;  // valid on threads < NR_TC (thread = column of the tile)
+    };
+    // pass 1: mean_j = sum_i gmean_i x_ij  (gmean = w / n; nullptr: no centring, cox)
+    double mean = 0.0;
+    if (gmean) {
+        const double t = column_sum([&](double v, int i, double s) { return fma(v, gmean[i], s); });
+        if (threadIdx.x < NR_TC) {
+            cmean[threadIdx.x] = t;
+            if (live) mean_out[j] = t;
+        }
+        __syncthreads();
+        mean = cmean[c];
+    }
+    // pass 2: h_j = sum_i wnorm_i (x_ij - mean_j)^2
+    {
+        const double t = column_sum([&](double v, int i, double s) {
+            const double d = v - mean;
+            return fma(d * d, wnorm[i], s);
+        });
+        if (threadIdx.x < NR_TC) {
+            const double nx = sqrt(t);
+            cmul[threadIdx.x] = sn / nx;
+            if (live) norm_out[j] = nx;
+        }
+        __syncthreads();
+    }
+    // pass 3: x_ij <- (x_ij - mean_j) * mul_j * rowmul_i
+    const double mul = cmul[c];
+    for (int i0 = ifirst; i0 < n; i0 += 8 * RS) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (live && i0 + u * RS < n) ? col[(size_t)(i0 + u * RS) * ldx] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (live && i0 + u * RS < n) {
+                const double rm = rowmul ? rowmul[i0 + u * RS] : 1.0;
+                col[(size_t)(i0 + u * RS) * ldx] = (v[u] - mean) * mul * rm;
+            }
+    }
+}
+void launch_normalize_resident(double *X, long long ldx, int n, int p, const double *gmean, const double *wnorm,
+                               const double *rowmul, double sn, double *mean_out, double *norm_out, cudaStream_t st)
+{
+    normalize_resident_kernel<<<(p + NR_TC - 1) / NR_TC, NR_NT, 0, st>>>(X, ldx, n, p, gmean, wnorm, rowmul, sn, mean_out, norm_out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_center_scale(double *X, long long ldx, int n, int p, const double *sub, const double *mul,
                          const double *rowmul, cudaStream_t st)
 {

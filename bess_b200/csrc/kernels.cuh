@@ -163,6 +163,9 @@ void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st);
 void launch_losses(const Dev &d, const LossDesc &jobs, const int *testrows, const int *ntest, const double *y,
                    const double *w, const double *lfact, double *scratch, double *out, cudaStream_t st);
 void launch_norm_factors(const double *h, int p, double sn, double *norm_out, double *mul_out, cudaStream_t st);
+// one-launch normalisation of an L2-resident design (gmean = w / n or nullptr for no centring, wnorm = w, rowmul or nullptr)
+void launch_normalize_resident(double *X, long long ldx, int n, int p, const double *gmean, const double *wnorm,
+                               const double *rowmul, double sn, double *mean_out, double *norm_out, cudaStream_t st);
 void launch_center_scale(double *X, long long ldx, int n, int p, const double *sub, const double *mul,
                          const double *rowmul, cudaStream_t st);
 void launch_gather_cols(const double *X, long long ldx, int n, const int *cols, int pnew, double *Xn, long long ldn,
