@@ -81,7 +81,7 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
         is_warm_start, ic_type, is_cv, K, sequence, s_min, s_max, is_screening, screening_size, always_select=(),
         fold_of_row=None, cv_seed=None, device=-1, x_device_ptr=None, n=None, p=None, want_trace=True, profile=False,
         world=1, rank=0, col_lo=0, p_total=None, nccl_id=None, lambda_seq=(0.0,), lambda_min=0.0, lambda_max=0.0,
-        n_lambda=None, powell_path=1, want_curve=False, g_index=None, cv_reduce_over_ranks=False):
+        n_lambda=None, powell_path=1, want_curve=False, g_index=None, cv_reduce_over_ranks=False, fold_shard=False):
     """``bess_b200_fit``: pywrap_bess + status code + extensions.  Returns a dict.
     ``x`` is a host ndarray, or pass ``x_device_ptr`` (int, row-major n x p fp64 in HBM) with ``n``/``p``.
     ``world > 1``: column-sharded multi-GPU call -- ``x`` is this rank's column shard ``[col_lo, col_lo + p)`` of a
@@ -106,11 +106,18 @@ def fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter
     lam = np.ascontiguousarray(lambda_seq, dtype=np.float64).ravel()
     seq = np.ascontiguousarray(sequence, dtype=np.int32).ravel()
     alw = np.ascontiguousarray(list(always_select), dtype=np.int32).ravel()
-    sharded = world > 1
+    fold_sharded = bool(fold_shard) and world > 1  # axis A inside one call: whole design on every rank, folds dealt out
+    sharded = world > 1 and not fold_sharded
     p_all = int(p_total) if sharded else p
     beta = _lazy_zeros(p_all)
     c0, tl, ic = C.c_double(0), C.c_double(0), C.c_double(0)
     ext = Ext()
+    if fold_sharded:
+        if nccl_id is None or len(nccl_id) != 128:
+            raise ValueError("fold-sharded fit needs the 128-byte NCCL unique id")
+        idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+        ext.world, ext.rank, ext.fold_shard = int(world), int(rank), 1
+        ext.nccl_unique_id = C.cast(idbuf, C.c_void_p)
     if sharded:
         if nccl_id is None or len(nccl_id) != 128:
             raise ValueError("sharded fit needs the 128-byte NCCL unique id")

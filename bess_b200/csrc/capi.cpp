@@ -62,7 +62,8 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
 {
     return guarded([&] {
         if (y_len != x_row || weight_len != x_row) throw EngineError{"y/weight length must equal the number of rows of x"};
-        const bool shard = ext && ext->world > 1;
+        const bool fshard = ext && ext->world > 1 && ext->fold_shard != 0;  // folds over the ranks, design replicated
+        const bool shard = ext && ext->world > 1 && !fshard;                // columns over the ranks
         if (beta_out && beta_out_len < (shard ? ext->p_total : (long long)x_col)) throw EngineError{"beta_out shorter than p"};
         BessArgs a;
         a.x = x; a.n = x_row; a.p = x_col; a.y = y; a.data_type = data_type; a.weight = weight;
@@ -94,6 +95,12 @@ int bess_b200_fit_impl(double *x, int x_row, int x_col, double *y, int y_len, in
                 a.p_total = ext->p_total;
                 a.nccl_id = ext->nccl_unique_id;
                 a.cv_reduce_over_ranks = ext->cv_reduce_over_ranks != 0;
+            }
+            if (fshard) {
+                a.world = ext->world;
+                a.rank = ext->rank;
+                a.nccl_id = ext->nccl_unique_id;
+                a.fold_shard = true;
             }
         }
         BessResult r;

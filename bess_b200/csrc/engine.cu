@@ -639,8 +639,15 @@ bool Engine::has_comm() const { return d_->comm != nullptr && d_->world > 1; }
 
 void Engine::allreduce_mean(std::vector<double> &v)
 {
+    allreduce_sum(v);
+    // the sum is reduced in the same order on every rank (one collective), the division is exact arithmetic on equal
+    // inputs: all ranks hold bit-identical means
+    for (double &x : v) x /= (double)d_->world;
+}
+void Engine::allreduce_sum(std::vector<double> &v)
+{
     Impl &m = *d_;
-    if (!has_comm()) throw EngineError{"allreduce_mean: no communicator (call init_shard first)"};
+    if (!has_comm()) throw EngineError{"allreduce: no communicator (call init_shard / init_comm first)"};
     if (v.empty()) return;
     const NcclApi &api = nccl_api();
     double *buf = dalloc<double>(m.st, v.size());
@@ -649,21 +656,28 @@ void Engine::allreduce_mean(std::vector<double> &v)
     CUDA_CHECK(cudaMemcpyAsync(v.data(), buf, v.size() * 8, cudaMemcpyDeviceToHost, m.st));
     CUDA_CHECK(cudaStreamSynchronize(m.st));
     dfree(m.st, buf);
-    // the sum is reduced in the same order on every rank (one collective), the division is exact arithmetic on equal
-    // inputs: all ranks hold bit-identical means
-    for (double &x : v) x /= (double)m.world;
 }
 
 void Engine::init_shard(int world, int rank, const void *unique_id, long long col_lo, long long p_total)
 {
-    Impl &m = *d_;
-    if (world < 2) throw EngineError{"init_shard: world must be >= 2"};
-    if (rank < 0 || rank >= world) throw EngineError{"init_shard: rank out of range"};
-    if (!unique_id) throw EngineError{"init_shard: the NCCL unique id is missing"};
     if (p_total > 2147483646LL) throw EngineError{"init_shard: p_total must fit a 32-bit index"};
     long long lo, hi;
+    if (world < 2) throw EngineError{"init_shard: world must be >= 2"};
     shard_range(p_total, world, rank, &lo, &hi);
     if (lo != col_lo) throw EngineError{"init_shard: col_lo does not match bess_b200_shard_range(p_total, world, rank)"};
+    init_comm(world, rank, unique_id);
+    sharded_ = true;
+    world_ = world;
+    rank_ = rank;
+    col_lo_ = col_lo;
+    p_total_ = p_total;
+}
+void Engine::init_comm(int world, int rank, const void *unique_id)
+{
+    Impl &m = *d_;
+    if (world < 2) throw EngineError{"init_comm: world must be >= 2"};
+    if (rank < 0 || rank >= world) throw EngineError{"init_comm: rank out of range"};
+    if (!unique_id) throw EngineError{"init_comm: the NCCL unique id is missing"};
     DeviceContext *c = m.ctx;
     if (!(c->comm && c->comm_world == world && c->comm_rank == rank &&
           std::memcmp(c->comm_id, unique_id, NCCL_UNIQUE_ID_BYTES) == 0)) {
@@ -682,11 +696,6 @@ void Engine::init_shard(int world, int rank, const void *unique_id, long long co
     m.comm = c->comm;
     m.world = world;
     m.rank = rank;
-    sharded_ = true;
-    world_ = world;
-    rank_ = rank;
-    col_lo_ = col_lo;
-    p_total_ = p_total;
 }
 void Engine::profile(double *ms_out, long long *n_out) const
 {

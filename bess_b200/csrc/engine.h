@@ -68,11 +68,14 @@ public:
     // communicator is cached per device for the life of the process.
     // This rank will load columns [col_lo, col_lo + p_local) = shard_range(p_total, world, rank) of a p_total-column design.
     void init_shard(int world, int rank, const void *unique_id, long long col_lo, long long p_total);
+    // the communicator alone (fold-sharded mode: the design is replicated, only fold losses travel)
+    void init_comm(int world, int rank, const void *unique_id);
     bool sharded() const { return sharded_; }
     // element-wise mean of `v` over the ranks of the job's communicator (one ncclAllReduce on the engine's stream); every
     // rank gets the same result.  Used for repeated K-fold CV: the ranks hold different fold assignments and average
     // their per-level CV losses before the level is chosen.  Needs init_shard().
     void allreduce_mean(std::vector<double> &v);
+    void allreduce_sum(std::vector<double> &v);
     bool has_comm() const;
     // column count the model sees (IC penalties, validation): p_total while sharded, else p
     long long p_model() const { return sharded_ ? p_total_ : p_; }

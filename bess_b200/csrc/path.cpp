@@ -92,6 +92,7 @@ struct Eval {
     std::vector<int> A;
     std::vector<double> bA;
     double coef0 = 0.0, train_loss = 0.0, ic = 0.0, lambda = 0.0;
+    std::vector<double> fold_part;  // fold-sharded sequential path: this rank's fold losses (K entries, 0 elsewhere)
 };
 
 struct Driver {
@@ -100,14 +101,54 @@ struct Driver {
     int n, p, K;  // p: columns after screening; K: folds (0 when !is_cv)
     int kcap = 0;  // largest sparsity level the chain workspaces were sized for
     std::vector<int> all_chains, fold_chains;
+    // Fold-sharded mode (SURVEY 8e axis A inside one call): this rank runs the full-data chain and the fold chains it
+    // owns (chain c belongs to rank c % world, bess_b200_chain_owner); the per-fold test losses are all-reduced (x + 0 is
+    // exact, so every rank -- and a single GPU -- sums the same K numbers in the same order).  gs_path reads the LAST
+    // fold's model at the end (path.cpp:314-319): there every rank runs chain K as well, its loss counted once.
+    bool fshard = false;
+    std::vector<char> counts;  // per entry of fold_chains: does this rank contribute that fold's loss
 
     Driver(Engine &e, const BessArgs &args) : eng(e), a(args)
     {
         n = eng.n();
         p = (int)eng.p_model();
         K = a.is_cv ? a.K : 0;
-        for (int c = 0; c <= K; c++) all_chains.push_back(c);
-        for (int c = 1; c <= K; c++) fold_chains.push_back(c);
+        fshard = a.fold_shard && a.world > 1 && K > 0;
+        all_chains.push_back(0);
+        for (int c = 1; c <= K; c++) {
+            const bool mine = !fshard || c % a.world == a.rank;
+            const bool everyone = fshard && c == K && a.path_type != 1;
+            if (mine || everyone) {
+                all_chains.push_back(c);
+                fold_chains.push_back(c);
+                counts.push_back(mine ? 1 : 0);
+            }
+        }
+    }
+    int nfc() const { return (int)fold_chains.size(); }
+    // loss jobs of a batch: [full-data train loss] + the test loss of every fold chain this rank runs
+    std::vector<LossJob> make_jobs(bool with_full) const
+    {
+        std::vector<LossJob> jobs;
+        if (with_full) jobs.push_back({0, 0, 0});
+        for (int c : fold_chains) jobs.push_back({c, 1, c - 1});
+        return jobs;
+    }
+    // this rank's share of the K fold losses (v[off + i] = loss of fold_chains[i])
+    std::vector<double> fold_losses(const std::vector<double> &v, size_t off) const
+    {
+        std::vector<double> fl((size_t)K, 0.0);
+        for (int i = 0; i < nfc(); i++)
+            if (counts[(size_t)i]) fl[(size_t)fold_chains[(size_t)i] - 1] = v[off + (size_t)i];
+        return fl;
+    }
+    // the CV criterion of one evaluated level (Metric.h:150-195: mean of the K fold losses)
+    double cv_ic(const std::vector<double> &v, size_t off)
+    {
+        if (!fshard) return mean_of(v, off, off + (size_t)K);
+        std::vector<double> fl = fold_losses(v, off);
+        eng.allreduce_sum(fl);
+        return mean_of(fl, 0, (size_t)K);
     }
 
     // Metric::ic without CV (Metric.h:205-229 gaussian: n*log(loss) + pen; :365-388 etc. GLMs: loss + pen).
@@ -142,12 +183,11 @@ struct Driver {
     Eval step(int T, Eval *last_fold = nullptr, double lambda = 0.0)
     {
         BatchResult br;
-        std::vector<LossJob> jobs;
-        jobs.push_back({0, 0, 0});
-        for (int k = 0; k < K; k++) jobs.push_back({1 + k, 1, k});
+        std::vector<LossJob> jobs = make_jobs(true);
         if (last_fold && K > 0) jobs.push_back({K, 0, 0});
         std::vector<double> v;
         eng.run_batch(T, all_chains, /*new_path_step=*/true, br, &jobs, &v, lambda);
+        const size_t posK = all_chains.size() - 1;  // chain K is the last chain of the batch whenever last_fold is asked for
         Eval e;
         e.T = T;
         e.lambda = lambda;
@@ -156,15 +196,15 @@ struct Driver {
         e.bA = br.bA[0];
         e.coef0 = br.coef0[0];
         e.train_loss = v[0];
-        e.ic = K > 0 ? mean_of(v, 1, 1 + (size_t)K) : ic_formula(e.train_loss, T);
+        e.ic = K > 0 ? cv_ic(v, 1) : ic_formula(e.train_loss, T);
         if (last_fold) {
             if (K > 0) {
                 last_fold->T = T;
-                last_fold->l = br.l[K];
-                last_fold->A = br.A[K];
-                last_fold->bA = br.bA[K];
-                last_fold->coef0 = br.coef0[K];
-                last_fold->train_loss = v[1 + (size_t)K];
+                last_fold->l = br.l[posK];
+                last_fold->A = br.A[posK];
+                last_fold->bA = br.bA[posK];
+                last_fold->coef0 = br.coef0[posK];
+                last_fold->train_loss = v[1 + (size_t)nfc()];
                 last_fold->ic = e.ic;
             } else {
                 *last_fold = e;
@@ -176,9 +216,7 @@ struct Driver {
     // step() in two halves for paths whose order of evaluation is known in advance (Engine::run_batch_enqueue)
     int step_enqueue(int T, double lambda)
     {
-        std::vector<LossJob> jobs;
-        jobs.push_back({0, 0, 0});
-        for (int k = 0; k < K; k++) jobs.push_back({1 + k, 1, k});
+        std::vector<LossJob> jobs = make_jobs(true);
         return eng.run_batch_enqueue(T, all_chains, /*new_path_step=*/true, &jobs, lambda);
     }
     bool step_collect(int ticket, int T, double lambda, Eval &e)
@@ -193,7 +231,8 @@ struct Driver {
         e.bA = br.bA[0];
         e.coef0 = br.coef0[0];
         e.train_loss = v[0];
-        e.ic = K > 0 ? mean_of(v, 1, 1 + (size_t)K) : ic_formula(e.train_loss, T);
+        if (fshard) e.fold_part = fold_losses(v, 1);  // reduced over the ranks once, at the end of the walk
+        else e.ic = K > 0 ? mean_of(v, 1, 1 + (size_t)K) : ic_formula(e.train_loss, T);
         return in_one_go;
     }
 
@@ -203,11 +242,10 @@ struct Driver {
     {
         if (K == 0) return e.ic;
         BatchResult br;
-        std::vector<LossJob> jobs;
-        for (int k = 0; k < K; k++) jobs.push_back({1 + k, 1, k});
+        std::vector<LossJob> jobs = make_jobs(false);
         std::vector<double> v;
         eng.run_batch(e.T, fold_chains, /*new_path_step=*/false, br, &jobs, &v);
-        return mean_of(v, 0, (size_t)K);
+        return cv_ic(v, 0);
     }
 
     // path.cpp:76-110 / :330-343.  bA_out: de-normalised coefficients on the support e.A
@@ -269,8 +307,9 @@ void sequential_path(Driver &dr, BessResult &out, Eval &best)
             e.bA = br.bA[0];
             e.coef0 = br.coef0[0];
             e.train_loss = la[(size_t)t * nch];
-            e.ic = dr.K > 0 ? Driver::mean_of(lt, (size_t)t * nch + 1, (size_t)t * nch + 1 + (size_t)dr.K)
-                            : dr.ic_formula(e.train_loss, e.T);
+            if (dr.fshard) e.fold_part = dr.fold_losses(lt, (size_t)t * nch + 1);
+            else e.ic = dr.K > 0 ? Driver::mean_of(lt, (size_t)t * nch + 1, (size_t)t * nch + 1 + (size_t)dr.K)
+                                 : dr.ic_formula(e.train_loss, e.T);
         }
     } else if (!pipelined) {
         for (int t = 0; t < n_steps; t++) evs[(size_t)order[(size_t)t]] = dr.step(level(t), nullptr, ridge(t));
@@ -285,6 +324,15 @@ void sequential_path(Driver &dr, BessResult &out, Eval &best)
             }
             cur = next;
         }
+    }
+    if (dr.fshard) {
+        // fold-sharded call: one all-reduce of the levels x K matrix of fold losses; then Metric.h:150-195's mean per level
+        const size_t K = (size_t)dr.K;
+        std::vector<double> mat(evs.size() * K, 0.0);
+        for (size_t i = 0; i < evs.size(); i++)
+            if (evs[i].fold_part.size() == K) std::copy(evs[i].fold_part.begin(), evs[i].fold_part.end(), mat.begin() + i * K);
+        dr.eng.allreduce_sum(mat);
+        for (size_t i = 0; i < evs.size(); i++) evs[i].ic = Driver::mean_of(mat, i * K, (i + 1) * K);
     }
     if (a.cv_reduce_over_ranks && a.world > 1) {
         // repeated CV: every rank ran its own fold assignment on the shared screened design; average the CV curves
@@ -709,7 +757,8 @@ static void bess_run_once(const BessArgs &a, BessResult &out, bool tie_exact)
     if (a.data_type < 1 || a.data_type > 3) throw EngineError{"data_type must be 1..3"};
     // bess.cpp:167-180: path_type != 1 runs pgs_path for the L0L2 algorithm types and gs_path otherwise
     const bool pgs = a.path_type != 1 && (a.algorithm_type == 5 || a.algorithm_type == 3);
-    if (pgs && a.world > 1) throw EngineError{"pgs_path is not available in column-sharded mode"};
+    if (pgs && a.world > 1) throw EngineError{"pgs_path is not available in column-sharded / fold-sharded mode"};
+    if (a.fold_shard && a.world > 1 && a.cv_reduce_over_ranks) throw EngineError{"fold_shard and cv_reduce_over_ranks exclude each other"};
     if (a.cv_reduce_over_ranks && a.world > 1 && !(a.path_type == 1 && a.is_cv && a.is_screening))
         throw EngineError{"cv_reduce_over_ranks needs the sequential path with CV and screening (ranks share the screened "
                           "design and differ only in their folds)"};
@@ -729,10 +778,10 @@ static void bess_run_once(const BessArgs &a, BessResult &out, bool tie_exact)
         // the reference un-screens a grouped fit by group number (bess.cpp:186-209 writes beta(screening_A(i))), which
         // scrambles the coefficients; there is no defined behaviour to reproduce
         if (a.is_screening) throw EngineError{"screening together with group selection is not supported"};
-        if (a.world > 1) throw EngineError{"group selection is not available in column-sharded mode"};
+        if (a.world > 1 && !a.fold_shard) throw EngineError{"group selection is not available in column-sharded mode"};
     }
     if (a.is_cv && (a.K < 2 || a.K > MAXC - 1)) throw EngineError{"K (nfolds) must be in [2, 31]"};
-    const bool shard = a.world > 1;
+    const bool shard = a.world > 1 && !a.fold_shard;  // columns sharded (axis B); fold_shard: the design is replicated
     const long long p_all = shard ? a.p_total : a.p;
     if (shard && a.x_on_device == false && a.x == nullptr) throw EngineError{"sharded fit: x shard is null"};
     const long long n_units = grouped ? (long long)a.g_index.size() : p_all;  // what s.list / always_select count
@@ -750,6 +799,7 @@ static void bess_run_once(const BessArgs &a, BessResult &out, bool tie_exact)
     eng.set_tie_exact(tie_exact);
     eng.set_profiling(a.profile);
     if (shard) eng.init_shard(a.world, a.rank, a.nccl_id, a.col_lo, a.p_total);
+    else if (a.fold_shard && a.world > 1 && a.is_cv) eng.init_comm(a.world, a.rank, a.nccl_id);
     eng.load(a.x, a.n, a.p, a.x_on_device, a.y, a.weight, a.model_type, /*borrow=*/a.is_screening);
 
     lap(0);

@@ -51,6 +51,11 @@ struct BessArgs {
     // are averaged over the ranks before the level is chosen, so every rank returns the same model.  Sequential path with
     // CV and screening only (the ranks then share the screened design but not the folds).
     bool cv_reduce_over_ranks = false;
+    // SURVEY 8e axis A inside ONE call: every rank holds the WHOLE design and makes the same call; the K fold chains of
+    // Metric::test_loss (Metric.h:150-195) are dealt over the ranks (bess_b200_chain_owner), every rank runs the full-data
+    // chain, and only the per-fold test losses are reduced (one NCCL all-reduce of K numbers per evaluated level; the
+    // sequential path reduces its whole levels x K matrix once).  world / rank / nccl_id as above, col_lo / p_total unused.
+    bool fold_shard = false;
 };
 
 struct BessResult {

@@ -132,6 +132,29 @@ def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal
                      cv_reduce_over_ranks=cv_reduce_over_ranks)
 
 
+def fit_fold_sharded(x, y, weight, data_type, is_normal, model_type, max_iter, path_type, is_warm_start, ic_type, K,
+                     sequence, s_min, s_max, screening_size=0, algorithm_type=1, cv_seed=123, fold_of_row=None, device=None,
+                     x_device_ptr=None, n=None, p=None, profile=False, always_select=(), g_index=None, lambda_seq=(0.0,),
+                     want_curve=False):
+    """ONE K-fold-CV call spread over the ranks of the current process group by FOLDS (SURVEY 8e axis A): every rank
+    holds the whole design and makes this same call; the library deals the K fold chains of ``Metric::test_loss``
+    (Metric.h:150-195) over the ranks (chain c on rank c % world), runs the full-data chain everywhere and all-reduces only
+    the per-fold test losses (``ext.fold_shard``).  Every rank returns the same model, bit-identical to the single-GPU
+    call.  Sequential and golden-section paths, all four families, groups and screening allowed (the screening is then
+    done redundantly by every rank on its own copy)."""
+    import torch
+    from . import cbess
+    dist = _dist()
+    if device is None:
+        device = torch.cuda.current_device()
+    scr = int(screening_size or 0)
+    return cbess.fit(x, y, data_type, weight, is_normal, algorithm_type, model_type, max_iter, 2, path_type, is_warm_start,
+                     ic_type, True, K, sequence, s_min, s_max, scr > 0, max(scr, 1), always_select=always_select,
+                     fold_of_row=fold_of_row, cv_seed=cv_seed, device=device, x_device_ptr=x_device_ptr, n=n, p=p,
+                     want_trace=False, profile=profile, world=dist.get_world_size(), rank=dist.get_rank(),
+                     nccl_id=nccl_unique_id(), want_curve=want_curve, g_index=g_index, lambda_seq=lambda_seq, fold_shard=True)
+
+
 def repeated_cv_reduce(cv_curve: np.ndarray):
     """Repeated K-fold CV over the ranks of the current process group: ``cv_curve[i]`` is this rank's mean fold loss at
     the i-th sparsity level (its own fold assignment); returns (curve averaged over the ranks, index of its first

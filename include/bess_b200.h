@@ -95,6 +95,11 @@ typedef struct bess_b200_ext {
                                 /* select fallbacks, 3 path steps, 8..15 clock ticks by phase of chain owner 0, 16..18 of    */
                                 /* sweeper 0; 24 + 4 i ..: chain owner i: busy ticks, longest phase, ticks in fallback        */
                                 /* selects, fits solved; all zero when the multi-kernel path ran                             */
+    int fold_shard;             /* world > 1 with the WHOLE design on every rank (col_lo / p_total unused), CV: the K fold    */
+                                /* chains of Metric::test_loss (Metric.h:150-195) are dealt over the ranks (chain c on rank   */
+                                /* c % world, bess_b200_chain_owner), every rank runs the full-data chain, and only the       */
+                                /* per-fold test losses are all-reduced -- SURVEY 8e axis A inside ONE call; every rank       */
+                                /* returns the same model, bit-identical to the single-GPU call                               */
 } bess_b200_ext;
 
 /* Same arguments and outputs as pywrap_bess, returns 0 on success.  The per-level trace of the call (what the reference's

@@ -102,6 +102,34 @@ def main():
               f"{'OK' if ok and same else 'FAIL'}", flush=True)
     if not (ok and same):
         failures.append("repeated_cv")
+    # ---- fold-sharded calls (ext.fold_shard, SURVEY 8e axis A inside ONE call): whole design on every rank, the K fold
+    # chains dealt over the ranks, only the fold losses all-reduced -- bit-identical to the single-GPU call on every rank
+    FOLD_CASES = [("gaussian", 300, 900, 5, 1, 5, 8, 0), ("gaussian", 260, 3000, 5, 1, 4, 8, 150), ("gaussian", 200, 1500, 5, 2, 5, 10, 0),
+                  ("binomial", 400, 800, 4, 1, 5, 6, 0), ("binomial", 360, 700, 4, 2, 3, 9, 0), ("poisson", 400, 600, 4, 1, 4, 5, 0),
+                  ("cox", 300, 500, 4, 2, 3, 6, 0)]
+    for fi, (fam, n, p, k, path_type, K, smax, scr) in enumerate(FOLD_CASES):
+        model_type, data_type = FAM[fam]
+        d = gen_data(n, p, fam, k, seed=300 + fi)
+        w = np.ones(n)
+        seq = np.arange(1, smax + 1)
+        fold = cbess.cv_fold_ids(n, K, 11)
+        ref = cbess.fit(d.x, d.y, data_type, w, True, 1, model_type, 20, 2, path_type, True, 1, True, K, seq, 1, smax, scr > 0,
+                        max(scr, 1), fold_of_row=fold, device=local, want_trace=False)
+        out = bdist.fit_fold_sharded(d.x, d.y, w, data_type, True, model_type, 20, path_type, True, 1, K, seq, 1, smax, scr,
+                                     fold_of_row=fold, device=local)
+        ok = (np.array_equal(out["beta"], ref["beta"]) and out["s"] == ref["s"] and out["ic"] == ref["ic"]
+              and out["coef0"] == ref["coef0"] and out["train_loss"] == ref["train_loss"])
+        fewer = out["stats"]["n_fits"] < ref["stats"]["n_fits"]  # this rank fitted only its share of the fold chains
+        t = torch.from_numpy(out["beta"]).cuda()
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        same = all(torch.equal(g[0], gi) for gi in g)
+        if rank == 0:
+            print(f"fold-sharded {fi} {fam} path={path_type} K={K} scr={scr}: s={out['s']} ic={out['ic']:.6f} fits {out['stats']['n_fits']}"
+                  f"/{ref['stats']['n_fits']} bit_identical={ok} ranks_identical={same} {'OK' if ok and same and fewer else 'FAIL'}",
+                  flush=True)
+        if not (ok and same and fewer):
+            failures.append(f"fold{fi}")
     dist.barrier()
     dist.destroy_process_group()
     if failures:
