@@ -489,6 +489,51 @@ def run_ours(args):
                                                       "every rank; the PDAS path on the screened design is replicated"},
                        "c5b_no_screening_strong": c5b}
 
+    # ---- axis A inside ONE call (ext.fold_shard): config 2 (binomial, golden section, 10-fold CV; chain-kernel bound) with
+    # the whole design on every rank and the fold chains dealt over the ranks; against the same call on one GPU, same run
+    fold_sharded = None
+    if world > 1 and not args.no_c2:
+        from bess_b200.gen_data import gen_data as _gen
+        d2 = _gen(2000, 20000, "binomial", 20, seed=2)
+        w2 = np.ones(2000)
+        X2 = torch.as_tensor(d2.x, device=dev)  # resident on every rank: the comparison is about the chains, not PCIe
+        fold2 = cbess.cv_fold_ids(2000, 10, 123)
+        seq2 = np.arange(1, 2)
+
+        def c2_call(sharded):
+            if sharded:
+                return bdist.fit_fold_sharded(None, d2.y, w2, 2, True, 2, 20, 2, True, 1, 10, seq2, 1, 263, 0, fold_of_row=fold2,
+                                              device=local_rank, x_device_ptr=X2.data_ptr(), n=2000, p=20000)
+            return cbess.fit(None, d2.y, 2, w2, True, 1, 2, 20, 2, 2, True, 1, True, 10, seq2, 1, 263, False, 1, fold_of_row=fold2,
+                             device=local_rank, x_device_ptr=X2.data_ptr(), n=2000, p=20000, want_trace=False)
+        res = {}
+        for mode in (False, True):
+            if not mode and rank != 0:
+                dist.barrier()
+                continue
+            c2_call(mode)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            o = c2_call(mode)
+            torch.cuda.synchronize()
+            res[mode] = ((time.perf_counter() - t0) * 1e3, o)
+            if not mode:
+                dist.barrier()
+        tf = torch.tensor([res[True][0]], dtype=torch.float64, device=dev)
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            o1, oN = res[False][1], res[True][1]
+            fold_sharded = {"workload": "C2 (binomial n=2000 p=20000, golden section s in [1, 263], 10-fold CV), design resident on "
+                                        "every rank, fold chains dealt over the ranks (ext.fold_shard)",
+                            "ms_per_call": float(tf.item()), "single_gpu_ms_per_call": res[False][0],
+                            "fits_this_rank": int(oN["stats"]["n_fits"]), "fits_single_gpu": int(o1["stats"]["n_fits"]),
+                            "same_support_and_s": bool(np.nonzero(oN["beta"])[0].tolist() == np.nonzero(o1["beta"])[0].tolist()
+                                                       and oN["s"] == o1["s"]),
+                            "beta_max_rel_diff": float(np.abs(oN["beta"] - o1["beta"]).max() / max(np.abs(o1["beta"]).max(), 1e-300)),
+                            "note": "a rank runs its share of the 11 chains and gives each a 16-CTA cluster (8 CTAs when all 11 share "
+                                    "one GPU): the Gram sums run over different row slices, hence last-bit differences"}
+        del X2
+
     parity = None
     if world > 1 and rank == 0:
         def cmp(a, b):
@@ -540,7 +585,7 @@ def run_ours(args):
                          "kernel_share_of_step": float(total_kernel_ms / args.steps / (ms / args.steps)),
                          "p500k_pdas_sweep": probe},
             "cpu_baseline": base, "c5b_no_screening": c5b if world == 1 else None, "c2_glm_path": c2,
-            "column_sharded": col_sharded,
+            "column_sharded": col_sharded, "fold_sharded_c2": fold_sharded,
             # the strong-scaling curve of ONE call (columns sharded) starts here: N = 1 of column_sharded.c5_one_call_strong /
             # c5b_no_screening_strong in the N > 1 lines
             "strong_scaling_n1": {"c5_one_call_ms": ms / args.steps, "c5b_no_screening_ms": c5b["ms_per_call"] if c5b else None}

@@ -2379,8 +2379,36 @@ void debug_get(unsigned long long *out32)
 // cluster size for sparsity level T: enough work per CTA to amortise the cluster barriers, all clusters co-resident.
 // work ~ rows x columns^2 of one Gram (x2 for cox: two Grams per Newton step).  Even the small gaussian fits of config 5
 // (900 x 21) gain from 4 CTAs: gather, Gram and gradient are row-parallel and a cluster barrier costs ~0.2 us.
+// how many 16-CTA clusters of chain_fit_kernel the device can hold at once (0: not schedulable); queried once
+static int g_cl16_chains = -1;
+static void query_cl16(size_t smem)
+{
+    if (g_cl16_chains >= 0) return;
+    g_cl16_chains = 0;
+    if (cudaFuncSetAttribute(chain_fit_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaFuncSetAttribute(chain_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16);
+    cfg.blockDim = dim3(FIT_NT);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, chain_fit_kernel, &cfg) == cudaSuccess) g_cl16_chains = std::max(0, ncl);
+    else cudaGetLastError();
+    if (const char *e = std::getenv("BESS_B200_CL16_CHAINS")) g_cl16_chains = std::min(g_cl16_chains, std::max(0, std::atoi(e)));
+}
 int chain_cluster_size(const Dev &d, int T, int nch)
 {
+    query_cl16(fit_smem_bytes(d));
     static double thr = -1.0;
     static int clmax = CLMAX;
     if (thr < 0.0) {
@@ -2392,7 +2420,10 @@ int chain_cluster_size(const Dev &d, int T, int nch)
     const double m = T + 2.0;
     const double work = (double)d.n * m * m * (d.family == FAM_COX ? 2.0 : 1.0);
     int CL = 1;
-    while (CL < clmax && CL < d.CLcap && work / CL > thr && nch * CL * 2 <= 148 && d.n / (CL * 2) >= 128) CL *= 2;
+    while (CL < std::min(clmax, 8) && CL < d.CLcap && work / CL > thr && nch * CL * 2 <= 148 && d.n / (CL * 2) >= 128) CL *= 2;
+    // 16-CTA (non-portable) clusters: one fits a GPC, so at most 8 can run at once -- for batches of few chains with a
+    // lot of work per chain (a single IC chain at n = 5000; the 3-4 chains a rank keeps of a fold-sharded call)
+    if (CL == 8 && clmax >= 16 && d.CLcap >= 16 && nch <= g_cl16_chains && work / 16.0 > 3.0 * thr && d.n / 16 >= 96) CL = 16;
     return CL;
 }
 
@@ -2407,6 +2438,7 @@ void launch_chain_fit(const Dev &d, const BatchDesc &b, cudaStream_t st)
 {
     const size_t smem = fit_smem_bytes(d);
     CUDA_CHECK(cudaFuncSetAttribute(chain_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (b.CL > 8) CUDA_CHECK(cudaFuncSetAttribute(chain_fit_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b.nch * b.CL));
     cfg.blockDim = dim3(FIT_NT);

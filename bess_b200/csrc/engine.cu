@@ -386,6 +386,7 @@ struct Engine::Impl {
     bool chains_ready = false;
     bool x_owned = true;
     bool tie_exact = false;  // Engine::set_tie_exact
+    int cl_chains = 0;       // Engine::set_cluster_chains
     // column-sharded mode
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
@@ -620,6 +621,7 @@ Engine::~Engine()
 
 void Engine::set_profiling(bool on) { d_->prof = on; }
 void Engine::set_tie_exact(bool on) { d_->tie_exact = on; }
+void Engine::set_cluster_chains(int nch) { d_->cl_chains = nch; }
 bool Engine::tie_exact() const { return d_->tie_exact; }
 
 // max_k of the reference, statement for statement (utilities.cpp:179-188): an index array 0..N-1, std::nth_element with
@@ -1734,7 +1736,7 @@ int Engine::run_batch_enqueue(int T, const std::vector<int> &chains, bool new_pa
     b.nch = (int)chains.size();
     b.T = T;
     b.new_path_step = new_path_step ? 1 : 0;
-    b.CL = chain_cluster_size(d, d.grouped ? std::min(d.kcap, T * d.gmax) : T, b.nch);
+    b.CL = chain_cluster_size(d, d.grouped ? std::min(d.kcap, T * d.gmax) : T, m.cl_chains > 0 ? std::max(m.cl_chains, b.nch) : b.nch);
     t.cmin = MAXC;
     t.cmax = -1;
     for (int i = 0; i < b.nch; i++) {

@@ -88,6 +88,10 @@ public:
     // speculative iterations, no resident path).  bess_run repeats a call in this mode when the fast pass saw a tie.
     // Call before load().  Not available in column-sharded mode (ties are then only counted).
     void set_tie_exact(bool on);
+    // fold-sharded calls: size the chain clusters as if every batch had `nch` chains (the most any rank runs), so that
+    // every rank -- whatever its share of the fold chains -- fits the full-data chain with the same cluster size and the
+    // ranks return bit-identical models.  0 = use each batch's own chain count.
+    void set_cluster_chains(int nch);
     bool tie_exact() const;
     Engine(const Engine &) = delete;
     Engine &operator=(const Engine &) = delete;

@@ -12,7 +12,8 @@ constexpr int SWEEP_RC = 64;     // rows per TMA-staged chunk of the gradient ve
 constexpr int FIT_NT = 512;      // threads per chain_fit CTA (one CTA per chain)
 constexpr int TOPK_NT = 1024;
 constexpr int TOPK_LMAX = 16384; // keys per top-k slice held in shared memory (128 KB)
-constexpr int CLMAX = 8;         // max thread-block cluster size of chain_fit_kernel (portable limit)
+constexpr int CLMAX = 16;        // max thread-block cluster size of chain_fit_kernel (8 = the portable limit; 16-CTA
+                                 // clusters, one per GPC, are used when a batch has few chains: single-chain paths, fold shards)
 
 // sweep modes
 enum { MODE_D = 0, MODE_DH = 1, MODE_COX = 2 };

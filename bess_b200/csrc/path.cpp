@@ -126,6 +126,18 @@ struct Driver {
         }
     }
     int nfc() const { return (int)fold_chains.size(); }
+    // the most chains any rank of a fold-sharded call runs in one batch (cluster sizing must not depend on the rank)
+    int max_chains_per_rank() const
+    {
+        int most = 0;
+        for (int r = 0; r < a.world; r++) {
+            int cnt = 1;
+            for (int c = 1; c <= K; c++)
+                if (c % a.world == r || (c == K && a.path_type != 1)) cnt++;
+            most = std::max(most, cnt);
+        }
+        return most;
+    }
     // loss jobs of a batch: [full-data train loss] + the test loss of every fold chain this rank runs
     std::vector<LossJob> make_jobs(bool with_full) const
     {
@@ -845,6 +857,7 @@ static void bess_run_once(const BessArgs &a, BessResult &out, bool tie_exact)
     lap(3);
     Driver dr(eng, a);
     dr.kcap = kcap;
+    if (dr.fshard) eng.set_cluster_chains(dr.max_chains_per_rank());
     Eval best;
     if (a.path_type == 1) sequential_path(dr, out, best);
     else if (pgs) pgs_path(dr, out, best);

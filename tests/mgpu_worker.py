@@ -117,8 +117,14 @@ def main():
                         max(scr, 1), fold_of_row=fold, device=local, want_trace=False)
         out = bdist.fit_fold_sharded(d.x, d.y, w, data_type, True, model_type, 20, path_type, True, 1, K, seq, 1, smax, scr,
                                      fold_of_row=fold, device=local)
-        ok = (np.array_equal(out["beta"], ref["beta"]) and out["s"] == ref["s"] and out["ic"] == ref["ic"]
-              and out["coef0"] == ref["coef0"] and out["train_loss"] == ref["train_loss"])
+        # (bit-identical whenever the chains get the same cluster size as in the single-GPU batch; a rank with fewer chains
+        # may give each a wider cluster -- then the Gram sums run over different row slices and the last bits move)
+        bit = np.array_equal(out["beta"], ref["beta"]) and out["ic"] == ref["ic"]
+        scale = max(np.abs(ref["beta"]).max(), 1e-300)
+        ok = (np.nonzero(out["beta"])[0].tolist() == np.nonzero(ref["beta"])[0].tolist() and out["s"] == ref["s"]
+              and float(np.abs(out["beta"] - ref["beta"]).max() / scale) < 1e-9
+              and abs(out["ic"] - ref["ic"]) <= 1e-9 * max(1.0, abs(ref["ic"]))
+              and abs(out["coef0"] - ref["coef0"]) <= 1e-9 * max(1.0, abs(ref["coef0"])))
         fewer = out["stats"]["n_fits"] < ref["stats"]["n_fits"]  # this rank fitted only its share of the fold chains
         t = torch.from_numpy(out["beta"]).cuda()
         g = [torch.empty_like(t) for _ in range(world)]
@@ -126,7 +132,7 @@ def main():
         same = all(torch.equal(g[0], gi) for gi in g)
         if rank == 0:
             print(f"fold-sharded {fi} {fam} path={path_type} K={K} scr={scr}: s={out['s']} ic={out['ic']:.6f} fits {out['stats']['n_fits']}"
-                  f"/{ref['stats']['n_fits']} bit_identical={ok} ranks_identical={same} {'OK' if ok and same and fewer else 'FAIL'}",
+                  f"/{ref['stats']['n_fits']} bit_identical={bit} ranks_identical={same} {'OK' if ok and same and fewer else 'FAIL'}",
                   flush=True)
         if not (ok and same and fewer):
             failures.append(f"fold{fi}")
