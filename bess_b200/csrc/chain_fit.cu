@@ -1013,20 +1013,24 @@ __device__ __forceinline__ void pm_row_solve(double *P, int ld, int h, int nb, c
     __syncthreads();
 }
 // acc (32 rows from a0 x 16 rows from b0, as 4 x 2 mma tiles) += L[a][q] L[b][q] over the 16 columns q of panel Pq
-// (first row / column cq, leading dimension ldq).  Rows past the border read whatever follows in shared memory: they
-// only reach accumulators that are never stored.
-__device__ __forceinline__ void pm_mma_panel(double (&acc)[4][2][2], const double *Pq, int ldq, int cq, int a0, int b0, int g,
-                                             int t4)
+// (first row / column cq, leading dimension ldq, hq rows).  Rows past the border are clamped to the border row: they only
+// reach accumulators that are never stored, and the loads stay inside the (read-only) source panel.
+__device__ __forceinline__ void pm_mma_panel(double (&acc)[4][2][2], const double *Pq, int ldq, int cq, int hq, int a0, int b0,
+                                             int g, int t4)
 {
-    const double *pa = Pq + t4 * ldq + (a0 - cq) + g;
-    const double *pb = Pq + t4 * ldq + (b0 - cq) + g;
+    const double *pk = Pq + t4 * ldq;
+    int ra[4], rb[2];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) ra[mt] = min(a0 - cq + 8 * mt + g, hq - 1);
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) rb[nt] = min(b0 - cq + 8 * nt + g, hq - 1);
 #pragma unroll
     for (int q0 = 0; q0 < PNB; q0 += 4) {
         double a[4], b[2];
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) a[mt] = pa[q0 * ldq + 8 * mt];
+        for (int mt = 0; mt < 4; mt++) a[mt] = pk[q0 * ldq + ra[mt]];
 #pragma unroll
-        for (int nt = 0; nt < 2; nt++) b[nt] = pb[q0 * ldq + 8 * nt];
+        for (int nt = 0; nt < 2; nt++) b[nt] = pk[q0 * ldq + rb[nt]];
 #pragma unroll
         for (int mt = 0; mt < 4; mt++)
 #pragma unroll
@@ -1055,10 +1059,12 @@ __device__ void pm_trailing(double *L, const int *poff, int mm, int c0, int np, 
         for (int mt = 0; mt < 2; mt++)
 #pragma unroll
             for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-        const double *pa = Pq + t4 * ldq + PNB + g;  // rows cj + g (+ 8) of panel pb
+        const int hq = mm + 1 - cq;
+        const double *pa = Pq + t4 * ldq;  // rows cj + g (+ 8) of panel pb, clamped to its border row
+        const int r0 = min(PNB + g, hq - 1), r1 = min(PNB + 8 + g, hq - 1);
 #pragma unroll
         for (int q0 = 0; q0 < PNB; q0 += 4) {
-            const double f0 = pa[q0 * ldq], f1 = pa[q0 * ldq + 8];
+            const double f0 = pa[q0 * ldq + r0], f1 = pa[q0 * ldq + r1];
             dmma_m8n8k4(acc[0][0], f0, f0);
             dmma_m8n8k4(acc[0][1], f0, f1);
             dmma_m8n8k4(acc[1][0], f1, f0);
@@ -1091,7 +1097,7 @@ __device__ void pm_trailing(double *L, const int *poff, int mm, int c0, int np, 
                 for (int mt = 0; mt < 4; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-                pm_mma_panel(acc, Pq, ldq, cq, a0, cj, g, t4);
+                pm_mma_panel(acc, Pq, ldq, cq, mm + 1 - cq, a0, cj, g, t4);
 #pragma unroll
                 for (int mt = 0; mt < 4; mt++)
 #pragma unroll
@@ -1128,7 +1134,7 @@ __device__ void pm_update_global(const double *L, const int *poff, double *Sg, i
                 for (int nt = 0; nt < 2; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
             for (int pb = 0; pb < np; pb++) {
                 const int cq = c0 + pb * PNB;
-                pm_mma_panel(acc, L + poff[pb], pm_ld(mm + 1 - cq), cq, a0, cj, g, t4);
+                pm_mma_panel(acc, L + poff[pb], pm_ld(mm + 1 - cq), cq, mm + 1 - cq, a0, cj, g, t4);
             }
 #pragma unroll
             for (int mt = 0; mt < 4; mt++)
