@@ -73,6 +73,8 @@ def load():
     lib.bess_b200_shard_range.argtypes = [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong),
                                           C.POINTER(C.c_longlong)]
     lib.bess_b200_chain_owner.argtypes = [C.c_int, C.c_int]
+    lib.bess_b200_fold_shard_chains.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+    lib.bess_b200_fold_shard_chains.restype = C.c_int
     lib.bess_b200_nccl_unique_id.argtypes = [C.c_void_p]
     lib.bess_b200_trace_lambda.argtypes = [dp]
     lib.bess_b200_pgs_line_box.argtypes = [dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]

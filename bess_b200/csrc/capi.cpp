@@ -485,6 +485,22 @@ void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long
     shard_range(p, world, rank, lo, hi);
 }
 int bess_b200_chain_owner(int chain, int world) { return world > 0 ? chain % world : 0; }
+int bess_b200_fold_shard_chains(int K, int world, int rank, int path_type, int *chains_out, int *counts_out)
+{
+    int n = -1;
+    const int rc = guarded([&] {
+        if (K < 0 || world < 1 || rank < 0 || rank >= world) throw EngineError{"fold_shard_chains: need K >= 0, 0 <= rank < world"};
+        std::vector<int> ch;
+        std::vector<char> cnt;
+        fold_shard_chains(K, world, rank, path_type != 1, ch, cnt);
+        for (size_t i = 0; i < ch.size(); i++) {
+            if (chains_out) chains_out[i] = ch[i];
+            if (counts_out) counts_out[i] = cnt[i];
+        }
+        n = (int)ch.size();
+    });
+    return rc == 0 ? n : -1;
+}
 int bess_b200_merge_candidates(const double *vals, const int *idx, int count, int k, int *idx_out)
 {
     return guarded([&] {

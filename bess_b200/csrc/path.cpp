@@ -114,29 +114,23 @@ struct Driver {
         p = (int)eng.p_model();
         K = a.is_cv ? a.K : 0;
         fshard = a.fold_shard && a.world > 1 && K > 0;
-        all_chains.push_back(0);
-        for (int c = 1; c <= K; c++) {
-            const bool mine = !fshard || c % a.world == a.rank;
-            const bool everyone = fshard && c == K && a.path_type != 1;
-            if (mine || everyone) {
-                all_chains.push_back(c);
-                fold_chains.push_back(c);
-                counts.push_back(mine ? 1 : 0);
-            }
-        }
+        std::vector<char> cnt;
+        fold_shard_chains(K, fshard ? a.world : 1, fshard ? a.rank : 0, a.path_type != 1, all_chains, cnt);
+        fold_chains.assign(all_chains.begin() + 1, all_chains.end());
+        counts.assign(cnt.begin() + 1, cnt.end());
     }
     int nfc() const { return (int)fold_chains.size(); }
     // the most chains any rank of a fold-sharded call runs in one batch (cluster sizing must not depend on the rank)
     int max_chains_per_rank() const
     {
-        int most = 0;
+        size_t most = 0;
         for (int r = 0; r < a.world; r++) {
-            int cnt = 1;
-            for (int c = 1; c <= K; c++)
-                if (c % a.world == r || (c == K && a.path_type != 1)) cnt++;
-            most = std::max(most, cnt);
+            std::vector<int> ch;
+            std::vector<char> cnt;
+            fold_shard_chains(K, a.world, r, a.path_type != 1, ch, cnt);
+            most = std::max(most, ch.size());
         }
-        return most;
+        return (int)most;
     }
     // loss jobs of a batch: [full-data train loss] + the test loss of every fold chain this rank runs
     std::vector<LossJob> make_jobs(bool with_full) const
@@ -756,6 +750,20 @@ void pgs_path(Driver &dr, BessResult &out, Eval &best)
 }
 
 }  // namespace
+
+void fold_shard_chains(int K, int world, int rank, bool last_fold_everywhere, std::vector<int> &chains, std::vector<char> &counts)
+{
+    chains.assign(1, 0);
+    counts.assign(1, 0);
+    for (int c = 1; c <= K; c++) {
+        const bool mine = world <= 1 || c % world == rank;
+        const bool everyone = world > 1 && c == K && last_fold_everywhere;
+        if (mine || everyone) {
+            chains.push_back(c);
+            counts.push_back(mine ? 1 : 0);
+        }
+    }
+}
 
 static void bess_run_once(const BessArgs &a, BessResult &out, bool tie_exact)
 {

@@ -95,6 +95,12 @@ std::vector<int> cv_fold_ids(int n, int K, unsigned seed);
 // pgs_path geometry (path.cpp:414-577), host only: where the line p + t*u leaves the (s, log lambda) box
 int pgs_line_box(const double p[2], const double u[2], int s_min, int s_max, double lmin, double lmax, double a[2], double b[2]);
 
+// Fold-sharded calls (BessArgs::fold_shard): the chains rank `rank` of `world` runs -- chain 0 (full data) always, fold chain
+// c (1..K) when c % world == rank, and on every rank the last fold chain K when `last_fold_everywhere` (gs_path reads its
+// model at the end, path.cpp:314-319).  counts[i] = 1 when this rank contributes the test loss of chains[i] (every fold
+// loss is contributed by exactly one rank; chain 0 has no test loss: counts[0] = 0).
+void fold_shard_chains(int K, int world, int rank, bool last_fold_everywhere, std::vector<int> &chains, std::vector<char> &counts);
+
 // throws EngineError
 void bess_run(const BessArgs &a, BessResult &out);
 

@@ -132,6 +132,17 @@ def fit_column_sharded(x_shard, col_lo, p_total, y, weight, data_type, is_normal
                      cv_reduce_over_ranks=cv_reduce_over_ranks)
 
 
+def fold_shard_chains(K, world, rank, path_type=1):
+    """The chains rank ``rank`` runs in a fold-sharded call and which fold losses it contributes (host helper, no GPU)."""
+    ch = np.zeros(K + 1, dtype=np.int32)
+    cnt = np.zeros(K + 1, dtype=np.int32)
+    n = _lib.load().bess_b200_fold_shard_chains(int(K), int(world), int(rank), int(path_type),
+                                                ch.ctypes.data_as(_lib.ip), cnt.ctypes.data_as(_lib.ip))
+    if n < 0:
+        raise ValueError(_lib.last_error())
+    return ch[:n].tolist(), cnt[:n].tolist()
+
+
 def fit_fold_sharded(x, y, weight, data_type, is_normal, model_type, max_iter, path_type, is_warm_start, ic_type, K,
                      sequence, s_min, s_max, screening_size=0, algorithm_type=1, cv_seed=123, fold_of_row=None, device=None,
                      x_device_ptr=None, n=None, p=None, profile=False, always_select=(), g_index=None, lambda_seq=(0.0,),

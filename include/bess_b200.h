@@ -197,6 +197,11 @@ int bess_b200_pgs_line_box(const double *p2, const double *u2, int s_min, int s_
 void bess_b200_shard_range(long long p, int world, int rank, long long *lo, long long *hi);
 /* chain -> rank assignment for fold sharding (SURVEY 8e axis A): round-robin, chain 0 on rank 0 */
 int bess_b200_chain_owner(int chain, int world);
+/* The chains rank `rank` runs in a fold-sharded call (ext.fold_shard) with K folds: chains_out[0] = 0 (full data), then its
+ * fold chains (c % world == rank; on every rank also chain K when path_type != 1, path.cpp:314-319); counts_out[i] = 1
+ * when the rank contributes the test loss of chains_out[i].  Both arrays need K + 1 entries.  Returns the number of
+ * chains, -1 on bad arguments.  Host only. */
+int bess_b200_fold_shard_chains(int K, int world, int rank, int path_type, int *chains_out, int *counts_out);
 /* merge per-rank local top-k candidate lists (value, global index) into the global top-k, ascending indices.
  * Total order: larger value first, lower index first.  vals/idx: [count]. */
 int bess_b200_merge_candidates(const double *vals, const int *idx, int count, int k, int *idx_out);

@@ -36,6 +36,18 @@ def _worker(rank, world, port, q):
         mine = np.array([fold_losses[c] if bdist.chain_owner(1 + c, world) == rank else 0.0 for c in range(K)])
         red = bdist.allreduce_sum(mine)
         ok_red = np.allclose(red, fold_losses)
+        # fold-sharded call (ext.fold_shard): the chain lists of the ranks cover every fold, every fold loss is contributed
+        # exactly once, chain 0 runs everywhere, and under golden section every rank also runs the last fold chain
+        ok_fs = True
+        for Kf, ptype in ((5, 1), (10, 2), (3, 2), (7, 1)):
+            ch, cnt = bdist.fold_shard_chains(Kf, world, rank, ptype)
+            contrib = np.zeros(Kf + 1)
+            for c, ct in zip(ch, cnt):
+                contrib[c] += ct
+            tot = bdist.allreduce_sum(contrib)
+            ok_fs = ok_fs and ch[0] == 0 and cnt[0] == 0 and tot[0] == 0 and np.all(tot[1:] == 1)
+            ok_fs = ok_fs and (ptype == 1 or Kf in ch) and all(c % world == rank or (c == Kf and ptype != 1) for c in ch[1:])
+        ok_red = ok_red and ok_fs
         # repeated CV: every rank holds its own CV curve; all ranks must agree on the averaged curve and the chosen level
         curves = np.array([[5.0, 3.0, 2.5, 2.6, 4.0], [5.5, 2.0, 2.9, 2.7, 4.5]])
         mean, best = bdist.repeated_cv_reduce(curves[rank])
