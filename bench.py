@@ -11,9 +11,9 @@ sequential s.list=1..20  => one step = one full bessCpp call = 220 PDAS fits (20
                                                             rank (weak scaling, see below)
   python bench.py --impl reference ...                      the reference's own CPU code (oracle/_ref) on host cores
 
-N > 1.  A single C5 call is 7 ms of which only the 0.6 ms screening sweep is p-sized; the 220 fits behind it run on a
-40 MB screened design and are a chain of ~55 dependent PDAS iterations, so one call cannot be made shorter by more GPUs
-(measured, one call with the columns sharded over 1 / 2 / 4 / 8 GPUs: 6.9 / 6.3 / 6.3 / 6.3 ms).  What does shard is what north_star names first: "CV folds
+N > 1.  A single C5 call is 2.3 ms of which only the 0.6 ms screening sweep is p-sized; the 220 fits behind it run on a
+40 MB screened design as ONE resident launch whose length is the per-chain dependency chain, so one call cannot be made
+shorter by more GPUs (measured, one call with the columns sharded over 1 / 2 / 4 / 8 GPUs: 2.3 / 2.1 / 2.0 / 2.0 ms).  What does shard is what north_star names first: "CV folds
 and sparsity levels shard embarrassingly, with only per-fold losses reduced".  The N-GPU job is therefore repeated 10-fold
 CV with N repetitions (rank r draws its folds from cv_seed + r): the columns of X are sharded over the ranks for the joint
 screening sweep (local top-k + NCCL all-gather of candidates + all-reduce of the kept columns, inside the library), each
@@ -22,7 +22,9 @@ all-reduce per step -- inside the library, on its own communicator (ext.cv_reduc
 losses so every rank chooses the same sparsity level and returns the same model.  Per-GPU work is fixed
 as N grows => "scaling": "weak".  `value` counts UNIQUE fits only: the full-data chain is identical on every rank and is
 counted once (20*(1 + 10*N) fits per step).  The strong-scaling numbers of the column-sharded path itself (C5 call and the
-no-screening variant C5b, where every PDAS sweep is p = 500k wide) are reported next to it under "column_sharded".
+no-screening variant C5b, where every PDAS sweep is p = 500k wide) are reported next to it under "column_sharded", and
+"fold_sharded_c2" is config 2 as ONE call whose fold chains are dealt over the ranks (ext.fold_shard) against the same call on
+one GPU.  The N = 1 line carries "c2_glm_path": config 2 through the C ABI (the chain kernels: tensor-core Gram + Cholesky).
 
 `value`  : whole-job fits/s with X already resident in HBM when the timed region starts.
 `e2e`    : same metric through the reference-facing C-ABI call with X in pinned HOST memory (H2D inside the region).
