@@ -381,6 +381,8 @@ struct Engine::Impl {
     // pinned host mirrors (owned by the DeviceContext)
     int *h_A = nullptr;
     int *gidx = nullptr, *gsz = nullptr;  // group selection: device copies of Engine::g_index_ / g_size_
+    int *glist = nullptr;                 // the narrow groups (<= GMAX variables) ordered by width class <= 2 | <= 4 | <= 8
+    int gcls_off[4] = {0, 0, 0, 0};       // class k = glist[gcls_off[k] .. gcls_off[k + 1])
     int Tmax = 0;                          // largest sparsity level (in groups when grouped) the workspaces hold
     double *h_bA = nullptr;
     bool chains_ready = false;
@@ -610,7 +612,7 @@ Engine::~Engine()
     m.free_chain_buffers();
     m.free_sweep_buffers();
     if (m.x_owned) dfree(m.st, m.X);
-    dfree(m.st, m.gidx); dfree(m.st, m.gsz);
+    dfree(m.st, m.gidx); dfree(m.st, m.gsz); dfree(m.st, m.glist);
     cudaStreamSynchronize(m.st);
     m.ctx->ar.reset();
     m.ctx->mir.reset();
@@ -1226,6 +1228,18 @@ void Engine::set_groups(const std::vector<int> &g_index)
     m.gsz = dalloc<int>(m.st, (size_t)N);
     CUDA_CHECK(cudaMemcpyAsync(m.gidx, g_index_.data(), (size_t)N * 4, cudaMemcpyHostToDevice, m.st));
     CUDA_CHECK(cudaMemcpyAsync(m.gsz, g_size_.data(), (size_t)N * 4, cudaMemcpyHostToDevice, m.st));
+    // narrow groups by width class, for the chain-batched sacrifice kernels (one instantiation per class)
+    std::vector<int> order;
+    const int bound[3] = {2, 4, GMAX};
+    for (int k = 0; k < 3; k++) {
+        m.gcls_off[k] = (int)order.size();
+        for (int g = 0; g < N; g++)
+            if (g_size_[(size_t)g] <= bound[k] && (k == 0 || g_size_[(size_t)g] > bound[k - 1])) order.push_back(g);
+    }
+    m.gcls_off[3] = (int)order.size();
+    dfree(m.st, m.glist);
+    m.glist = dalloc<int>(m.st, (size_t)std::max<size_t>(order.size(), 1));
+    if (!order.empty()) CUDA_CHECK(cudaMemcpyAsync(m.glist, order.data(), order.size() * 4, cudaMemcpyHostToDevice, m.st));
     CUDA_CHECK(cudaStreamSynchronize(m.st));
 }
 
@@ -1270,6 +1284,8 @@ void Engine::setup_chains(int K, const int *fold_of_row, int kcap, int max_iter,
     d.gmax = grp ? *std::max_element(g_size_.begin(), g_size_.end()) : 1;
     d.gidx = m.gidx;
     d.gsz = m.gsz;
+    d.glist = m.glist;
+    for (int k = 0; k < 4; k++) d.gcls_off[k] = m.gcls_off[k];
 
     // ---- host tables, written straight into the pinned half of the mirror arena: ONE copy moves them all.
     // Row lists (Metric.h:80-103: train masks are the sorted complement of each fold), compacted response / weights.

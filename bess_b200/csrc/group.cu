@@ -149,6 +149,103 @@ __global__ void __launch_bounds__(GS_NT) group_sacrifice_warp_kernel(const Dev d
     if (lane == 0) group_epilogue(d, c, g, j0, gs, dv, M);
 }
 
+// Chain-batched variant for the gaussian / logistic / poisson blocks: ONE pass over X serves every chain of the batch (the
+// warp kernel above re-reads the group's columns once per chain).  A CTA takes 8 groups (one per warp); the gradient
+// vectors G, W of a 64-row tile -- [row][chain slot], the layout chain_begin / chain_fit publish -- are staged in shared
+// memory once per CTA and shared by its warps.  Inside a warp lane = (row phase, chain slot): with FS <= 16 chain slots two
+// rows are in flight per step, the x values of a row are the same address for all its lanes (one broadcast load), and
+// every lane carries the d_g / M_g accumulators of ITS chain (compact, sized by the padded group width GSP in {2, 4, 8}:
+// a group of 4 pays 10 block entries per row, not the 36 of the widest group).  The row phases meet in one shuffle, then
+// the lanes of all chains run the eigen-solve epilogue side by side.
+constexpr int GB_NT = 256;  // 8 warps = 8 groups per CTA share one staged tile of the gradient vectors (4 per CTA measured slower)
+constexpr int GB_RT = 64;
+template <int GSP>
+__global__ void __launch_bounds__(GB_NT) group_sacrifice_batched_kernel(const Dev d, const BatchDesc b, int lo, int hi)
+{
+    __shared__ double sG[GB_RT][32], sW[GB_RT][32];
+    if (d.gate && *d.gate == 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int FS = d.FS;
+    const int CS = FS <= 16 ? 16 : 32, nrp = 32 / CS;  // lanes per row phase, row phases
+    const int c = lane & (CS - 1), rp = lane / CS;
+    const int li = lo + blockIdx.x * (GB_NT / 32) + wid;  // position in the class's group list
+    const bool have = li < hi;
+    const int g = have ? d.glist[li] : 0;
+    const int j0 = d.gidx[g], gs = d.gsz[g];
+    bool live = false;  // is chain slot c part of this batch and still iterating?
+    for (int q = 0; q < b.nch; q++) live = live || (b.chain[q] == c && !d.done[c]);
+    double dv[GSP], M[GSP * (GSP + 1) / 2];
+#pragma unroll
+    for (int a = 0; a < GSP; a++) dv[a] = 0.0;
+#pragma unroll
+    for (int e = 0; e < GSP * (GSP + 1) / 2; e++) M[e] = 0.0;
+    constexpr int RU = GSP == GMAX ? 2 : (GSP == 4 ? 4 : 8);  // rows in flight per lane
+    for (int e = threadIdx.x; e < GB_RT * 32; e += GB_NT) {  // chain slots >= FS stay zero
+        sG[e >> 5][e & 31] = 0.0;
+        sW[e >> 5][e & 31] = 0.0;
+    }
+    for (int t0 = 0; t0 < d.n; t0 += GB_RT) {
+        const int rows = min(GB_RT, d.n - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * FS; e += GB_NT) {  // the tile is one contiguous block of both vectors
+            const int r = e / FS, cc = e - r * FS;
+            sG[r][cc] = d.G[(size_t)t0 * FS + e];
+            sW[r][cc] = d.W[(size_t)t0 * FS + e];
+        }
+        __syncthreads();
+        if (!have) continue;  // warp-uniform
+        for (int r0 = rp; r0 < rows; r0 += RU * nrp) {
+            double x[RU][GSP];
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const int r = r0 + u * nrp;
+                const double *xr = d.X + (size_t)(t0 + min(r, rows - 1)) * d.ldx + j0;
+#pragma unroll
+                for (int a = 0; a < GSP; a++) x[u][a] = a < gs ? __ldg(xr + a) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < RU; u++) {
+                const int r = r0 + u * nrp;
+                if (r < rows) {
+                    const double gi = sG[r][c], wi = sW[r][c];
+#pragma unroll
+                    for (int a = 0; a < GSP; a++) dv[a] = fma(x[u][a], gi, dv[a]);
+                    int e = 0;
+#pragma unroll
+                    for (int a = 0; a < GSP; a++) {
+                        const double wa = wi * x[u][a];
+#pragma unroll
+                        for (int bb = a; bb < GSP; bb++, e++) M[e] = fma(wa, x[u][bb], M[e]);
+                    }
+                }
+            }
+        }
+    }
+    if (!have) return;
+    if (nrp == 2) {
+#pragma unroll
+        for (int a = 0; a < GSP; a++) dv[a] += __shfl_xor_sync(0xffffffffu, dv[a], 16);
+#pragma unroll
+        for (int e = 0; e < GSP * (GSP + 1) / 2; e++) M[e] += __shfl_xor_sync(0xffffffffu, M[e], 16);
+    }
+    if (rp == 0 && live) {
+        // compact accumulators -> the GMAX-packed layout of the epilogue
+        double dvf[GMAX], Mf[GMAX * (GMAX + 1) / 2];
+#pragma unroll
+        for (int a = 0; a < GMAX; a++) dvf[a] = 0.0;
+#pragma unroll
+        for (int e = 0; e < GMAX * (GMAX + 1) / 2; e++) Mf[e] = 0.0;
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < GSP; a++) {
+            dvf[a] = dv[a];
+#pragma unroll
+            for (int bb = a; bb < GSP; bb++, e++) Mf[a * GMAX - a * (a - 1) / 2 + (bb - a)] = M[e];
+        }
+        group_epilogue(d, c, g, j0, gs, dvf, Mf);
+    }
+}
+
 template <bool COX>
 __global__ void __launch_bounds__(GS_NT) group_sacrifice_kernel(const Dev d, const BatchDesc b)
 {
@@ -361,9 +458,25 @@ void launch_group_sacrifice(const Dev &d, const BatchDesc &b, cudaStream_t st)
         if (d.family == FAM_COX) group_sacrifice_kernel<true><<<grid, GS_NT, 0, st>>>(d, b);
         else group_sacrifice_kernel<false><<<grid, GS_NT, 0, st>>>(d, b);
     } else {
-        const int wpb = GS_NT / 32;
-        const dim3 grid((unsigned)((d.N + wpb - 1) / wpb), (unsigned)b.nch);
-        group_sacrifice_warp_kernel<<<grid, GS_NT, 0, st>>>(d, b);
+        static const bool per_chain = [] {
+            const char *e = std::getenv("BESS_B200_GROUP_PER_CHAIN");
+            return e && e[0] == '1';
+        }();
+        if (per_chain || b.nch == 1) {  // a single chain: the warp-per-(group, chain) kernel spreads the rows over 32 lanes
+            const int wpb = GS_NT / 32;
+            const dim3 grid((unsigned)((d.N + wpb - 1) / wpb), (unsigned)b.nch);
+            group_sacrifice_warp_kernel<<<grid, GS_NT, 0, st>>>(d, b);
+        } else {
+            const int wpb = GB_NT / 32;
+            for (int k = 0; k < 3; k++) {  // one instantiation per width class of the narrow groups
+                const int lo = d.gcls_off[k], hi = d.gcls_off[k + 1];
+                if (hi <= lo) continue;
+                const unsigned grid = (unsigned)((hi - lo + wpb - 1) / wpb);
+                if (k == 0) group_sacrifice_batched_kernel<2><<<grid, GB_NT, 0, st>>>(d, b, lo, hi);
+                else if (k == 1) group_sacrifice_batched_kernel<4><<<grid, GB_NT, 0, st>>>(d, b, lo, hi);
+                else group_sacrifice_batched_kernel<GMAX><<<grid, GB_NT, 0, st>>>(d, b, lo, hi);
+            }
+        }
     }
     CUDA_CHECK(cudaGetLastError());
     if (d.gmax > GMAX) {  // some groups are wider than the register kernels take

@@ -71,6 +71,8 @@ struct Dev {
     int grouped;        // 0: every column is its own group, the fields below are unused
     int N;              // number of groups
     int gmax;           // widest group
+    const int *glist;   // narrow groups (<= GMAX variables) ordered by width class <= 2 | <= 4 | <= 8
+    int gcls_off[4];    // class k = glist[gcls_off[k] .. gcls_off[k + 1])
     const int *gidx;    // [N]
     const int *gsz;     // [N]
     int *Tc;            // [MAXC] number of columns of the groups chosen by the last top-k
