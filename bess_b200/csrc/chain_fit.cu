@@ -2419,7 +2419,7 @@ int chain_cluster_size(const Dev &d, int T, int nch)
     static int clmax = CLMAX;
     if (thr < 0.0) {
         const char *e = std::getenv("BESS_B200_CL_WORK");
-        thr = e ? std::atof(e) : 1.0e5;
+        thr = e ? std::atof(e) : 1.25e4;  // swept on configs 3 / 4: 1e5 -> 121 / 81 ms of chain kernels, 2.5e4 -> 108 / 75, 1.25e4 -> 106 / 74
         const char *e2 = std::getenv("BESS_B200_CL_MAX");
         if (e2) clmax = std::max(1, std::min(CLMAX, std::atoi(e2)));
     }
