@@ -250,7 +250,8 @@ struct Driver {
         BatchResult br;
         std::vector<LossJob> jobs = make_jobs(false);
         std::vector<double> v;
-        eng.run_batch(e.T, fold_chains, /*new_path_step=*/false, br, &jobs, &v);
+        // (a rank of a fold-sharded call with more ranks than folds may own no fold chain: it only takes part in the reduce)
+        if (!fold_chains.empty()) eng.run_batch(e.T, fold_chains, /*new_path_step=*/false, br, &jobs, &v);
         return cv_ic(v, 0);
     }
 
