@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(GS_NT) group_sacrifice_warp_kernel(const Dev d
 // warp kernel above re-reads the group's columns once per chain).  A CTA takes 8 groups (one per warp); the gradient
 // vectors G, W of a 64-row tile -- [row][chain slot], the layout chain_begin / chain_fit publish -- are staged in shared
 // memory once per CTA and shared by its warps.  Inside a warp lane = (row phase, chain slot): with FS <= 8 chain slots four
-// rows are in flight per step (two with FS <= 16), the x values of a row are the same address for all its lanes (one broadcast load), and
+// rows are in flight per step (two with FS <= 16, eight with FS <= 4), the x values of a row are the same address for all its lanes (one broadcast load), and
 // every lane carries the d_g / M_g accumulators of ITS chain (compact, sized by the padded group width GSP in {2, 4, 8}:
 // a group of 4 pays 10 block entries per row, not the 36 of the widest group).  The row phases meet in one shuffle, then
 // the lanes of all chains run the eigen-solve epilogue side by side.
@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(GB_NT) group_sacrifice_batched_kernel(const De
     if (d.gate && *d.gate == 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int FS = d.FS;
-    const int CS = FS <= 8 ? 8 : (FS <= 16 ? 16 : 32), nrp = 32 / CS;  // lanes per row phase, row phases (4 / 2 / 1)
+    int CS = 2;  // lanes per row phase: the chain slots rounded up to a power of two
+    while (CS < FS) CS <<= 1;
+    const int nrp = 32 / CS;  // row phases in flight per warp step (FS = 6 or 8: 4, FS = 12 or 16: 2)
     const int c = lane & (CS - 1), rp = lane / CS;
     const int li = lo + blockIdx.x * (GB_NT / 32) + wid;  // position in the class's group list
     const bool have = li < hi;
