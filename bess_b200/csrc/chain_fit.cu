@@ -1684,7 +1684,7 @@ __device__ __forceinline__ void rows_dot(const ChainCtx &cx, const double *beta,
         double sacc[GR];
 #pragma unroll
         for (int u = 0; u < GR; u++) sacc[u] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
         for (int a = lane; a < m; a += 32) {
             const double bv = beta[a];
 #pragma unroll
