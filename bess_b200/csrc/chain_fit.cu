@@ -417,6 +417,11 @@ __device__ __noinline__ void block_syrk_dmma(const double *V, int ldv, int r0, i
     uint64_t *full = reinterpret_cast<uint64_t *>(sm.red);  // [GRAM_NS], empty = full + GRAM_NS
     uint64_t *empty = full + GRAM_NS;
     const int nrow = r1 - r0;
+    if (nrow <= 0) {  // an empty row slice contributes a zero matrix (cluster sizing never produces one; kept for safety)
+        for (int e = tid; e < mm * mm; e += FIT_NT) S[(size_t)(e / mm) * lds + e % mm] = 0.0;
+        __syncthreads();
+        return;
+    }
     const int ntile = (nrow + R - 1) / R;
     const int nstep = ntile * npass;
     __syncthreads();  // the arena and sm.red are free
